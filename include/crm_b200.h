@@ -1,0 +1,155 @@
+/*
+ * crm_b200.h -- C ABI of the B200-native embedded cloud-resolving model (CRM).
+ *
+ * This is the drop-in boundary for the one call site of the reference's CRM driver,
+ *
+ *     call crm(lchnk, icol, ncrms, dt_gl, plev, crm_input, crm_state, crm_rad,
+ *              crm_ecpp_output, crm_output)
+ *
+ * (reference: components/cam/src/physics/cam/crm_physics.F90:1145-1156 calling
+ *  components/cam/src/physics/crm/crm_module.F90:45-56).  A Fortran ISO_C_BINDING shim
+ * (shim/crm_module_b200.F90) does c_loc() on every member array of the reference's
+ * derived types and passes the hidden module inputs explicitly.
+ *
+ * Conventions
+ *  - plain C, no C++/torch types; every array is FP64 (real(crm_rknd)/real(r8), reference
+ *    CRM/params.F90:21-26) or int32.
+ *  - arrays are column-major exactly as the Fortran caller owns them: the GCM-column (CRM)
+ *    index is FASTEST with leading dimension `ld` (= pcols in the reference), i.e.
+ *    A(icrm,i,j,k) lives at  A[icrm + ld*(i + nx*(j + ny*k))]   (0-based),
+ *    profiles P(icrm,l) at P[icrm + ld*l]; only rows 0..ncrms-1 are read/written.
+ *  - pointers may be host (pageable or pinned) or device pointers; the library detects which
+ *    (cudaPointerGetAttributes).  Ownership stays with the caller.
+ *  - outputs are valid on return (synchronous semantics, like the reference).
+ *  - a NULL output pointer means "caller does not want this member".
+ *  - return value 0 = success; otherwise crm_b200_last_error() describes the failure
+ *    (replaces the reference's task_abort/endrun: CRM/kurant.F90:66-75, damping.F90:39-42,
+ *    crm_module.F90:690-691).
+ */
+#ifndef CRM_B200_H
+#define CRM_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRM_B200_ABI_VERSION 1
+
+/* Compile-time constants of the reference (PHYS/crmdims.F90:13-22, CRM/domain.F90:9-13) and the
+ * hidden module inputs of crm() (time_manager:get_nstep, accelerate_crm_mod namelist). */
+typedef struct crm_dims_t {
+  int ncrms;            /* number of CRMs (GCM columns) in this call           */
+  int ld;               /* leading dimension of every array (reference: pcols)   */
+  int plev;             /* GCM levels                                            */
+  int nx, ny, nzm;      /* crm_nx, crm_ny, crm_nz (scalar levels)                */
+  int nx_rad, ny_rad;   /* crm_nx_rad, crm_ny_rad                                */
+  int yes3d;            /* YES3DVAL: 1 if ny>1                                   */
+  double dx;            /* CRM_DX [m] (dy = dx)                                  */
+  double dt;            /* CRM_DT [s]                                            */
+  double dt_gl;         /* GCM time step [s]                                     */
+  int igstep;           /* get_nstep(): setperturb fires when igstep <= 1        */
+  int micro;            /* 0 = sam1mom, 1 = m2005                                */
+  int use_crm_accel;    /* mean-state acceleration (accelerate_crm.F90:55)       */
+  int crm_accel_uv;
+  double crm_accel_factor;
+  int twiddle_f32;      /* 1: REAL(4) FFT trig tables like CRM/fft.F90; 0: FP64 */
+} crm_dims_t;
+
+/* crm_input_type (CRM/crm_input_module.F90:10-47) + phys_grid lookups (crm_module.F90:287-288,679) */
+typedef struct crm_input_t {
+  const double *zmid, *zint;            /* (ld,plev), (ld,plev+1) */
+  const double *tl, *ql, *qccl, *qiil;  /* (ld,plev) */
+  const double *ps;                     /* (ld) */
+  const double *pmid, *pint, *pdel;     /* (ld,plev), (ld,plev+1), (ld,plev) */
+  const double *phis;                   /* (ld) */
+  const double *ul, *vl;                /* (ld,plev) */
+  const double *ocnfrac, *tau00, *wndls, *bflxls;        /* (ld) */
+  const double *fluxu00, *fluxv00, *fluxt00, *fluxq00;   /* (ld) */
+  const double *lat_deg, *lon_deg;      /* (ld) get_rlat_p/get_rlon_p * 57.296 */
+  const int    *gcol;                   /* (ld) get_gcol_p: seed of setperturb */
+} crm_input_t;
+
+/* crm_state_type (CRM/crm_state_module.F90:12-56); all (ld,nx,ny,nzm), in/out */
+typedef struct crm_state_t {
+  double *u_wind, *v_wind, *w_wind, *temperature;
+  double *qt, *qp, *qn;                                  /* sam1mom */
+  double *nc, *qr, *nr, *qi, *ni, *qs, *ns, *qg, *ng, *qc; /* m2005 (may be NULL for sam1mom) */
+} crm_state_t;
+
+/* crm_rad_type (CRM/crm_rad_module.F90:17-34); all (ld,nx_rad,ny_rad,nzm) */
+typedef struct crm_rad_t {
+  const double *qrad;                         /* in: radiative heating [K/s] */
+  double *temperature, *qv, *qc, *qi, *cld;   /* out: time/group means */
+  double *nc, *ni, *qs, *ns;                  /* m2005 only */
+} crm_rad_t;
+
+/* crm_output_type (CRM/crm_output_module.F90:7-133), same member names */
+typedef struct crm_output_t {
+  /* (ld,nx,ny,nzm) */
+  double *qcl, *qci, *qpl, *qpi, *tk, *tkh;
+  /* (ld,nx,ny) */
+  double *prec_crm;
+  /* (ld) */
+  double *cltot, *cllow, *clmed, *clhgh;
+  double *precc, *precl, *precsc, *precsl;
+  double *jt_crm, *mx_crm;
+  double *prectend, *precstend;
+  double *taux, *tauy, *z0m, *timing_factor;
+  /* (ld,plev) */
+  double *cldtop;
+  double *qc_mean, *qi_mean, *qs_mean, *qg_mean, *qr_mean;
+  double *sltend, *qltend, *qcltend, *qiltend;
+  double *cld, *gicewp, *gliqwp;
+  double *mctot, *mcup, *mcdn, *mcuup, *mcudn;
+  double *mu_crm, *md_crm, *du_crm, *eu_crm, *ed_crm;
+  double *flux_qt, *fluxsgs_qt, *tkez, *tkesgsz, *tkz;
+  double *flux_u, *flux_v, *flux_qp, *precflux;
+  double *qt_ls, *qt_trans, *qp_trans, *qp_fall, *qp_src, *qp_evp, *t_ls;
+} crm_output_t;
+
+/* Run statistics (new: replaces the GPTL timers 'crm_gpu_region' etc.) */
+typedef struct crm_run_stats_t {
+  long long nstop;          /* CRM steps taken                              */
+  long long ncycle_sum;     /* sum over steps of ncycle = sub-steps taken    */
+  long long ncycle_max;
+  long long nprec_max;
+  long long kernel_launches;/* device kernels launched by this call          */
+  double    ms_total;       /* wall/device time of the whole call            */
+  double    ms_kernels;     /* device time between first and last kernel     */
+  double    ms_h2d, ms_d2h; /* time spent in boundary copies                 */
+  long long h2d_bytes, d2h_bytes;
+} crm_run_stats_t;
+
+/* ---- entry points --------------------------------------------------------------------- */
+
+/* Create a handle: allocates the persistent workspace arena on `device` for the given
+ * geometry (replaces the per-call allocate_*()/prefetch() of crm_module.F90:199-266). */
+int crm_b200_init(int device, const crm_dims_t *dims, void **handle);
+
+/* One crm() call (crm_module.F90:45-1718).  `dims` may differ from the init dims only in
+ * ncrms (<= init ncrms), ld, dt_gl, igstep and the accel flags. */
+int crm_b200_run(void *handle, const crm_dims_t *dims, const crm_input_t *in,
+                 crm_state_t *state, crm_rad_t *rad, crm_output_t *out);
+
+int crm_b200_free(void *handle);
+
+/* Message of the last failure on this handle (or of a failed init if handle==NULL). */
+const char *crm_b200_last_error(void *handle);
+
+/* Statistics of the most recent crm_b200_run on this handle. */
+int crm_b200_get_stats(void *handle, crm_run_stats_t *stats);
+
+/* Test/diagnostic hook: copy an internal field, as left by the last run, into a host buffer
+ * in the boundary layout (ncrms,nx,ny,nz[m]) with ld = ncrms.  Names: "u","w","t","qt","qp",
+ * "qn","tabs","qv","qcl","qci","qpl","qpi","tk","tkh","tke","p","dudt","dwdt".  Returns the
+ * number of doubles written, or <0 on error. */
+long long crm_b200_debug_fetch(void *handle, const char *name, double *host_buf, size_t n);
+
+int crm_b200_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRM_B200_H */

@@ -1,0 +1,638 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle_common.h).  PARITY UNPINNED (no reference golden vectors).
+// Driver: restatement of subroutine crm() (components/cam/src/physics/crm/crm_module.F90:45-1718) for the
+// sam1mom build (-Dsam1mom -D_MPDATA -DCRM, no CLUBB/ECPP/MAML/SP_ESMT/SPMOMTRANS).  Exposes
+//   crm_oracle_run(dims, in, state, rad, out, stats)  with the structs of include/crm_b200.h
+// so tests can feed identical buffers to the oracle and to the CUDA library.
+// OpenMP parallelism is over CRMs only (they are independent apart from the batch-global maxima
+// ncycle / nprec / MSA ceaseflag, which are reduced between parallel regions).
+#include "crm_state.h"
+#include "crm_routines.h"
+#include <map>
+#include <cstdlib>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace orc;
+
+namespace {
+
+struct Ext {   // boundary-layout accessor: A(icrm,i,j,k) with icrm fastest, leading dimension ld
+  int ld, n1, n2;
+  inline size_t at(int icrm, int i, int j, int k) const { return (size_t)icrm + (size_t)ld * ((size_t)i + (size_t)n1 * ((size_t)j + (size_t)n2 * (size_t)k)); }
+};
+
+std::string g_err;
+std::vector<Crm> g_crms;   // kept after a run for crm_oracle_debug_fetch
+Geo g_geo;
+Step g_step;
+
+void alloc_crm(const Geo &g, Crm &c) {
+  const int nx = g.nx, ny = g.ny, nzm = g.nzm, nz = g.nz, Y = g.YES3D, plev = g.plev;
+  for (P1 *p : {&c.z, &c.zi, &c.presi, &c.adzw, &c.rhow}) p->alloc(1, nz);
+  for (P1 *p : {&c.pres, &c.adz, &c.rho, &c.bet, &c.gamaz, &c.grdf_x, &c.grdf_y, &c.grdf_z}) p->alloc(1, nzm);
+  // vars.F90:172-188 index ranges
+  c.u.alloc(-1, nx + 3, 1 - 2 * Y, ny + 2 * Y, nzm);
+  c.v.alloc(-1, nx + 2, 1 - 2 * Y, ny + 3 * Y, nzm);
+  c.w.alloc(-1, nx + 2, 1 - 2 * Y, ny + 2 * Y, nz);
+  for (F3 *f : {&c.t, &c.qt, &c.qp, &c.tke}) f->alloc(-2, nx + 3, 1 - 3 * Y, ny + 3 * Y, nzm);
+  c.p.alloc(0, nx, 1 - Y, ny, nzm);
+  for (F3 *f : {&c.tabs, &c.qv, &c.qcl, &c.qpl, &c.qci, &c.qpi, &c.qn}) f->alloc(1, nx, 1, ny, nzm);
+  c.cf3d.alloc(1, nx, 1, ny, nzm, 1.0);   // vars.F90:456  CF3D = 1.
+  c.tk.alloc(0, nx + 1, 1 - Y, ny + Y, nzm);
+  c.tkh.alloc(0, nx + 1, 1 - Y, ny + Y, nzm);
+  for (int n = 1; n <= 3; n++) {
+    c.dudt[n].alloc(1, nx + 1, 1, ny, nzm);
+    c.dvdt[n].alloc(1, nx, 1, ny + Y, nzm);
+    c.dwdt[n].alloc(1, nx, 1, ny, nz);
+  }
+  for (auto *v : {&c.precsfc, &c.precssfc, &c.fluxbu, &c.fluxbv, &c.fluxbt, &c.fluxbq, &c.fluxtu, &c.fluxtv, &c.fluxtt, &c.fluxtq})
+    v->assign((size_t)nx * ny, 0.);
+  for (P1 *p : {&c.t0, &c.q0, &c.qv0, &c.tabs0, &c.u0, &c.v0, &c.tg0, &c.qg0, &c.ug0, &c.vg0, &c.tke0, &c.t01, &c.q01, &c.qp0, &c.qn0,
+                &c.qtend, &c.ttend, &c.utend, &c.vtend, &c.t00})
+    p->alloc(1, nz);
+  for (P1 *p : {&c.precflux, &c.uwle, &c.uwsb, &c.vwle, &c.vwsb, &c.tlat, &c.tlatqi, &c.qifall, &c.qpfall, &c.twsb, &c.tdiff, &c.qpsrc, &c.qpevp})
+    p->alloc(1, nz);
+  for (int n = 1; n <= 2; n++) { c.mkwle[n].alloc(1, nz); c.mkwsb[n].alloc(1, nz); c.mkadv[n].alloc(1, nz); c.mkdiff[n].alloc(1, nz); }
+  for (P1 *p : {&c.accrsc, &c.accrsi, &c.accrrc, &c.coefice, &c.accrgc, &c.accrgi, &c.evaps1, &c.evaps2, &c.evapr1, &c.evapr2, &c.evapg1, &c.evapg2})
+    p->alloc(1, nzm);
+  for (P1 *p : {&c.tln, &c.qln, &c.qccln, &c.qiiln, &c.uln, &c.vln, &c.dd_crm}) p->alloc(1, plev);
+  c.mui_crm.alloc(1, plev + 1); c.mdi_crm.alloc(1, plev + 1);
+  for (P1 *p : {&c.acc_t, &c.acc_q, &c.acc_u, &c.acc_v}) p->alloc(1, nzm);
+  for (P1 *p : {&c.o_cld, &c.o_cldtop, &c.o_gicewp, &c.o_gliqwp, &c.o_mcup, &c.o_mcdn, &c.o_mcuup, &c.o_mcudn}) p->alloc(1, plev);
+  for (F3 *f : {&c.rad_t, &c.rad_qv, &c.rad_qc, &c.rad_qi, &c.rad_cld}) f->alloc(1, g.nx_rad, 1, g.ny_rad, nzm);
+}
+
+}  // namespace
+
+extern "C" const char *crm_oracle_last_error(void) { return g_err.c_str(); }
+
+extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_state_t *st, crm_rad_t *rad, crm_output_t *out,
+                              crm_run_stats_t *stats) {
+  g_err.clear();
+  if (d->micro != 0) { g_err = "oracle: only sam1mom (micro=0) is restated"; return 2; }
+  Geo g;
+  g.nx = d->nx; g.ny = d->ny; g.nzm = d->nzm; g.nz = d->nzm + 1; g.plev = d->plev; g.YES3D = d->yes3d;
+  g.nx_rad = d->nx_rad; g.ny_rad = d->ny_rad; g.dx = d->dx; g.dy = d->dx; g.RUN3D = d->ny > 1;
+  if ((g.RUN3D && !g.YES3D) || (!g.RUN3D && g.YES3D)) { g_err = "setparm: RUN3D/YES3D mismatch (setparm.F90:55-62)"; return 3; }
+  const int ncrms = d->ncrms, ld = d->ld, nx = g.nx, ny = g.ny, nzm = g.nzm, nz = g.nz, plev = g.plev;
+  const int ptop = plev - nzm + 1;
+  if (g.nx % g.nx_rad != 0) { g_err = "crm_nx_rad must divide nx (crm_module.F90:686-692)"; return 4; }
+  if (nx < 4 || nzm < 4 || (nx & (nx - 1)) || (g.RUN3D && (ny & (ny - 1)))) { g_err = "oracle: nx, ny must be powers of two >= 4"; return 5; }
+
+  Ext e3{ld, nx, ny}, erad{ld, g.nx_rad, g.ny_rad};
+  auto P2 = [&](const double *a, int icrm, int l) { return a[(size_t)icrm + (size_t)ld * (l - 1)]; };   // (icrm, l) 1-based l
+
+  std::vector<Crm> &crms = g_crms;
+  crms.assign(ncrms, Crm());
+  std::vector<F3> qrad(ncrms);
+  Step s;
+  MicroCoef mc; mc.init();
+  FftPlan fx, fy;
+  fx.init(nx, d->twiddle_f32 != 0);
+  if (g.RUN3D) fy.init(ny, d->twiddle_f32 != 0);
+
+  const double dt_gl = d->dt_gl;
+  const double umax = 0.5 * d->dx / d->dt;   // crm_module.F90:130
+  const double wmin = R4(2.);
+  const double cwp_threshold = R4(0.001);
+  const double idt_gl = 1. / dt_gl;
+  const double factor_xy = 1. / (double)(nx * ny);
+  // nint(gam3) check of precip_init.F90:42-45
+  if (std::lround(mc.gam3) != 2) { g_err = "cannot compute gamma-function in precip_init"; return 6; }
+
+  s.dt = d->dt;   // setparm.F90:28
+  s.dtn = s.dt;
+
+  // =========================== prologue, part 1 (crm_module.F90:286-452) ===========================
+#pragma omp parallel for schedule(static)
+  for (int ic = 0; ic < ncrms; ic++) {
+    Crm &c = crms[ic];
+    alloc_crm(g, c);
+    c.bflx = in->bflxls[ic];
+    c.wnd = in->wndls[ic];
+    for (int k = 1; k <= nzm; k++) {
+      c.z(k) = P2(in->zmid, ic, plev - k + 1) - P2(in->zint, ic, plev + 1);
+      c.zi(k) = P2(in->zint, ic, plev - k + 2) - P2(in->zint, ic, plev + 1);
+      c.pres(k) = P2(in->pmid, ic, plev - k + 1) / R4(100.);
+      c.presi(k) = P2(in->pint, ic, plev - k + 2) / R4(100.);
+      c.bet(k) = ggr / P2(in->tl, ic, plev - k + 1);
+      c.gamaz(k) = ggr / cp * c.z(k);
+    }
+    c.zi(nz) = P2(in->zint, ic, plev - nz + 2) - P2(in->zint, ic, plev + 1);
+    c.presi(nz) = P2(in->pint, ic, plev - nz + 2) / R4(100.);
+    c.dz = 0.5 * (c.z(1) + c.z(2));
+    for (int k = 2; k <= nzm; k++) c.adzw(k) = (c.z(k) - c.z(k - 1)) / c.dz;
+    c.adzw(1) = 1.;
+    c.adzw(nz) = c.adzw(nzm);
+    for (int k = 1; k <= nzm; k++) c.adz(k) = (c.zi(k + 1) - c.zi(k)) / c.dz;
+    for (int k = 1; k <= nzm; k++) c.rho(k) = P2(in->pdel, ic, plev - k + 1) / ggr / (c.adz(k) * c.dz);
+    for (int k = 2; k <= nzm; k++) c.rhow(k) = (P2(in->pmid, ic, plev - k + 2) - P2(in->pmid, ic, plev - k + 1)) / ggr / (c.adzw(k) * c.dz);
+    c.rhow(1) = 2. * c.rhow(2) - c.rhow(3);
+    c.rhow(nz) = 2. * c.rhow(nzm) - c.rhow(nzm - 1);
+    for (int k = 1; k <= nzm; k++)
+      for (int j = 1; j <= ny; j++)
+        for (int i = 1; i <= nx; i++) {
+          size_t o = e3.at(ic, i - 1, j - 1, k - 1);
+          c.u(i, j, k) = st->u_wind[o];
+          c.v(i, j, k) = st->v_wind[o] * g.YES3D;
+          c.w(i, j, k) = st->w_wind[o];
+          c.tabs(i, j, k) = st->temperature[o];
+          c.qt(i, j, k) = st->qt[o];
+          c.qp(i, j, k) = st->qp[o];
+          c.qn(i, j, k) = st->qn[o];
+        }
+    qrad[ic].alloc(1, g.nx_rad, 1, g.ny_rad, nzm);
+    for (int k = 1; k <= nzm; k++)
+      for (int j = 1; j <= g.ny_rad; j++)
+        for (int i = 1; i <= g.nx_rad; i++) qrad[ic](i, j, k) = rad->qrad[erad.at(ic, i - 1, j - 1, k - 1)];
+  }
+  // limit the velocity at the very first step: test uses CRM #1 only (crm_module.F90:400)
+  {
+    const Crm &c1 = crms[0];
+    if (c1.u(1, 1, 1) == c1.u(2, 1, 1) && c1.u(3, 1, 2) == c1.u(4, 1, 2)) {
+#pragma omp parallel for schedule(static)
+      for (int ic = 0; ic < ncrms; ic++) {
+        Crm &c = crms[ic];
+        for (int k = 1; k <= nzm; k++)
+          for (int j = 1; j <= ny; j++)
+            for (int i = 1; i <= nx; i++) {
+              c.u(i, j, k) = dmin(umax, dmax(-umax, c.u(i, j, k)));
+              c.v(i, j, k) = dmin(umax, dmax(-umax, c.v(i, j, k))) * g.YES3D;
+            }
+      }
+    }
+  }
+  // =========================== prologue, part 2 (crm_module.F90:477-681) ===========================
+#pragma omp parallel for schedule(static)
+  for (int ic = 0; ic < ncrms; ic++) {
+    Crm &c = crms[ic];
+    micro_diagnose(g, c, mc);   // micro_init -> micro_diagnose (microphysics.F90:155-226)
+    // sgs_init (sgs.F90:174-226): tke, tk, tkh = 0 (alloc), grdf
+    for (int k = 1; k <= nzm; k++) {
+      double a2 = (c.adz(k) * c.dz) * (c.adz(k) * c.dz);
+      c.grdf_x(k) = dmin(16., g.dx * g.dx / a2);
+      c.grdf_y(k) = dmin(16., g.dy * g.dy / a2);
+      c.grdf_z(k) = 1.;
+    }
+    c.colprec = 0; c.colprecs = 0;
+    for (int k = 1; k <= nzm; k++) {
+      double u0 = 0, v0 = 0, t0 = 0, t00 = 0, tabs0 = 0, q0 = 0, qv0 = 0, qn0 = 0, qp0 = 0, tke0 = 0;
+      double pdel = P2(in->pdel, ic, plev - k + 1);
+      for (int j = 1; j <= ny; j++)
+        for (int i = 1; i <= nx; i++) {
+          c.t(i, j, k) = c.tabs(i, j, k) + c.gamaz(k) - fac_cond * c.qcl(i, j, k) - fac_sub * c.qci(i, j, k) -
+                         fac_cond * c.qpl(i, j, k) - fac_sub * c.qpi(i, j, k);
+          c.colprec += (c.qpl(i, j, k) + c.qpi(i, j, k)) * pdel;
+          c.colprecs += c.qpi(i, j, k) * pdel;
+          u0 += c.u(i, j, k); v0 += c.v(i, j, k); t0 += c.t(i, j, k);
+          t00 += c.t(i, j, k) + fac_cond * c.qpl(i, j, k) + fac_sub * c.qpi(i, j, k);
+          tabs0 += c.tabs(i, j, k);
+          q0 += c.qv(i, j, k) + c.qcl(i, j, k) + c.qci(i, j, k);
+          qv0 += c.qv(i, j, k);
+          qn0 += c.qcl(i, j, k) + c.qci(i, j, k);
+          qp0 += c.qpl(i, j, k) + c.qpi(i, j, k);
+          tke0 += c.tke(i, j, k);
+        }
+      c.u0(k) = u0 * factor_xy; c.v0(k) = v0 * factor_xy; c.t0(k) = t0 * factor_xy; c.t00(k) = t00 * factor_xy;
+      c.tabs0(k) = tabs0 * factor_xy; c.q0(k) = q0 * factor_xy; c.qv0(k) = qv0 * factor_xy; c.qn0(k) = qn0 * factor_xy;
+      c.qp0(k) = qp0 * factor_xy; c.tke0(k) = tke0 * factor_xy;
+      int l = plev - k + 1;
+      c.uln(l) = dmin(umax, dmax(-umax, P2(in->ul, ic, l)));
+      c.vln(l) = dmin(umax, dmax(-umax, P2(in->vl, ic, l))) * g.YES3D;
+      double tl = P2(in->tl, ic, l), ql = P2(in->ql, ic, l), qccl = P2(in->qccl, ic, l), qiil = P2(in->qiil, ic, l);
+      c.ttend(k) = (tl + c.gamaz(k) - fac_cond * (qccl + qiil) - fac_fus * qiil - c.t00(k)) * idt_gl;
+      c.qtend(k) = (ql + qccl + qiil - c.q0(k)) * idt_gl;
+      c.utend(k) = (c.uln(l) - c.u0(k)) * idt_gl;
+      c.vtend(k) = (c.vln(l) - c.v0(k)) * idt_gl;
+      c.ug0(k) = c.uln(l); c.vg0(k) = c.vln(l);
+      c.tg0(k) = tl + c.gamaz(k) - fac_cond * qccl - fac_sub * qiil;
+      c.qg0(k) = ql + qccl + qiil;
+    }
+    c.uhl = c.u0(1); c.vhl = c.v0(1);
+    c.ustar = std::sqrt(in->tau00[ic] / c.rho(1));
+    c.z0 = z0_est(c.z(1), c.bflx, c.wnd, c.ustar);
+    c.z0 = dmax(R4(0.00001), dmin(R4(1.), c.z0));
+    c.o_timing = 0.;
+    c.prectend0 = c.colprec; c.precstend0 = c.colprecs;
+    precip_init(g, c, mc);   // crm_module.F90:673
+    if (d->igstep <= 1) setperturb(g, c, in->gcol[ic] * 1000);   // :677-681, perturb_seed_scale = 1000
+  }
+
+  int nstop = (int)(dt_gl / s.dt);   // crm_module.F90:712 (integer assignment truncates)
+  s.dt = dt_gl / nstop;
+  const double crm_run_time = dt_gl, icrm_run_time = 1. / crm_run_time;
+  bool use_accel = d->use_crm_accel != 0, accel_uv = d->crm_accel_uv != 0;
+  const double accel_factor = d->crm_accel_factor;
+  if (use_accel) {   // accelerate_crm.F90:78-107
+    if (nstop % (int)(1 + accel_factor) != 0) { g_err = "crm main: bad crm_accel_factor and nstop pair"; return 7; }
+    nstop = (int)(nstop / (1 + accel_factor));
+  }
+  bool ceaseflag = false;
+  const double crm_nx_rad_fac = (double)g.nx_rad / (double)nx, crm_ny_rad_fac = (double)g.ny_rad / (double)ny;
+  long long ncycle_sum = 0, ncycle_max = 0, nprec_max = 0;
+  int fail = 0;
+
+  // ======================================= main time loop =======================================
+  s.nstep = 0;
+  while (s.nstep < nstop) {
+    s.nstep++;
+    // kurant (kurant.F90:9-83)
+    double cfl = 0.;
+#pragma omp parallel for schedule(static) reduction(max : cfl)
+    for (int ic = 0; ic < ncrms; ic++) cfl = dmax(cfl, kurant_cfl(g, crms[ic], s));
+    s.ncycle = std::max(1, std::max(1, (int)std::ceil(cfl / R4(0.7))));
+    if (s.ncycle > 16) { g_err = "kurant() - the number of cycles exceeded max_ncycle=16"; return 8; }
+    ncycle_sum += s.ncycle; ncycle_max = std::max<long long>(ncycle_max, s.ncycle);
+
+    for (int icyc = 1; icyc <= s.ncycle; icyc++) {
+      s.icycle = icyc;
+      s.dtn = s.dt / s.ncycle;
+      s.dt3[s.na] = s.dtn;
+      s.dtfactor = s.dtn / s.dt;
+      abcoefs(s);
+      double prec_cfl = 0.;
+#pragma omp parallel for schedule(static) reduction(max : prec_cfl) reduction(+ : fail)
+      for (int ic = 0; ic < ncrms; ic++) {
+        Crm &c = crms[ic];
+        zero(g, c, s);
+        buoyancy(g, c, s);
+        forcing(g, c, s);
+        rad_heating(g, c, s, qrad[ic]);
+        fail += damping(g, c, s);
+        ice_fall(g, c, s);
+        boundaries(g, c, 3);
+        boundaries(g, c, 0);
+        // crmsurface: no-op (sfc_flx_fxd=.false., crmsurface.F90:16)
+        sgs_proc(g, c, s);
+        boundaries(g, c, 4);
+        advect_mom(g, c, s);
+        sgs_mom(g, c, s);
+        pressure(g, c, s, fx, fy);
+        adams(g, c, s);
+        boundaries(g, c, 2);
+        // advect_all_scalars.F90:32-49
+        advect_scalar(g, c, c.t, c.tdiff /*dummy*/, c.twsb /*dummy*/);
+        advect_scalar(g, c, c.qt, c.mkadv[1], c.mkwle[1]);
+        advect_scalar(g, c, c.qp, c.mkadv[2], c.mkwle[2]);
+        prec_cfl = dmax(prec_cfl, precip_fall_part1(g, c, s, mc));
+      }
+      if (fail) { g_err = "Error: in damping() tau_min is too small!"; return 9; }
+      if (prec_cfl > R4(0.9)) nprec_max = std::max<long long>(nprec_max, (long long)std::ceil(prec_cfl / R4(0.9)));
+      else nprec_max = std::max<long long>(nprec_max, 1);
+      bool cease_now = false;
+#pragma omp parallel for schedule(static) reduction(|| : cease_now)
+      for (int ic = 0; ic < ncrms; ic++) {
+        Crm &c = crms[ic];
+        precip_fall_part2(g, c, s, mc, prec_cfl);
+        uvw(g, c, s);
+        boundaries(g, c, 3);
+        // sgs_scalars (sgs.F90:389-447): t, then micro_flux (fluxbq=fluxtq=0), then qt, qp
+        diffuse_scalar(g, c, s, c.t, c.fluxbt, c.fluxtt, c.tdiff, c.twsb);
+        diffuse_scalar(g, c, s, c.qt, c.fluxbq, c.fluxtq, c.mkdiff[1], c.mkwsb[1]);
+        diffuse_scalar(g, c, s, c.qp, c.fluxbq /*=0*/, c.fluxtq /*=0*/, c.mkdiff[2], c.mkwsb[2]);
+        // micro_proc (microphysics.F90:292-329)
+        if (s.icycle == 1) precip_init(g, c, mc);
+        cloud(g, c);
+        precip_proc(g, c, s, mc);
+        micro_diagnose(g, c, mc);
+        if (use_accel && !ceaseflag) cease_now = cease_now || accelerate_part1(g, c, accel_uv);
+      }
+      if (use_accel && !ceaseflag) {
+        if (cease_now) {
+          ceaseflag = true;
+          nstop = (int)(nstop + (nstop - s.nstep + 1) * accel_factor);   // accelerate_crm.F90:243
+        } else {
+#pragma omp parallel for schedule(static)
+          for (int ic = 0; ic < ncrms; ic++) accelerate_part2(g, crms[ic], accel_uv, accel_factor);
+        }
+      }
+#pragma omp parallel for schedule(static)
+      for (int ic = 0; ic < ncrms; ic++) diagnose(g, crms[ic], s);
+      int nn = s.na; s.na = s.nc; s.nc = s.nb; s.nb = nn;   // crm_module.F90:884-887
+    }
+
+    // ---- per-nstep statistics (crm_module.F90:896-1073) ----
+#pragma omp parallel for schedule(static)
+    for (int ic = 0; ic < ncrms; ic++) {
+      Crm &c = crms[ic];
+      c.o_timing += 1;
+      for (int j = 1; j <= ny; j++)
+        for (int i = 1; i <= nx; i++) {
+          double cwp = 0, cwph = 0, cwpm = 0, cwpl = 0, cltemp = 0, cmtemp = 0, chtemp = 0, cttemp = 0;
+          bool flag_top = true;
+          for (int k = 1; k <= nzm; k++) {
+            int l = plev - k + 1, kk = nz - k;
+            double tmp1 = c.rho(kk) * c.adz(kk) * c.dz * (c.qcl(i, j, kk) + c.qci(i, j, kk));
+            cwp += tmp1;
+            cttemp = dmax(c.cf3d(i, j, kk), cttemp);
+            if (cwp > cwp_threshold && flag_top) { c.o_cldtop(l) += 1; flag_top = false; }
+            if (c.pres(kk) >= R4(700.)) { cwpl += tmp1; cltemp = dmax(c.cf3d(i, j, kk), cltemp); }
+            else if (c.pres(kk) < R4(400.)) { cwph += tmp1; chtemp = dmax(c.cf3d(i, j, kk), chtemp); }
+            else { cwpm += tmp1; cmtemp = dmax(c.cf3d(i, j, kk), cmtemp); }
+            tmp1 = c.rho(k) * c.adz(k) * c.dz;
+            double wsum = c.w(i, j, k + 1) + c.w(i, j, k);
+            if (tmp1 * (c.qcl(i, j, k) + c.qci(i, j, k)) > cwp_threshold) {
+              c.o_cld(l) += c.cf3d(i, j, k);
+              if (wsum > 2 * wmin) {
+                c.o_mcup(l) += c.rho(k) * 0.5 * wsum * c.cf3d(i, j, k);
+                c.o_mcuup(l) += c.rho(k) * 0.5 * wsum * (R4(1.0) - c.cf3d(i, j, k));
+              }
+              if (wsum < -2 * wmin) {
+                c.o_mcdn(l) += c.rho(k) * 0.5 * wsum * c.cf3d(i, j, k);
+                c.o_mcudn(l) += c.rho(k) * 0.5 * wsum * (1. - c.cf3d(i, j, k));
+              }
+            } else {
+              if (wsum > 2 * wmin) c.o_mcuup(l) += c.rho(k) * 0.5 * wsum;
+              if (wsum < -2 * wmin) c.o_mcudn(l) += c.rho(k) * 0.5 * wsum;
+            }
+            c.o_gliqwp(l) += c.qcl(i, j, k);
+            c.o_gicewp(l) += c.qci(i, j, k);
+          }
+          if (cwp > cwp_threshold) c.o_cltot += cttemp;
+          if (cwph > cwp_threshold) c.o_clhgh += chtemp;
+          if (cwpm > cwp_threshold) c.o_clmed += cmtemp;
+          if (cwpl > cwp_threshold) c.o_cllow += cltemp;
+        }
+      for (int k = 1; k <= nzm; k++)
+        for (int j = 1; j <= ny; j++)
+          for (int i = 1; i <= nx; i++) {
+            int i_rad = (i - 1) / (nx / g.nx_rad) + 1, j_rad = (j - 1) / (ny / g.ny_rad) + 1;
+            c.rad_t(i_rad, j_rad, k) += c.tabs(i, j, k);
+            c.rad_qv(i_rad, j_rad, k) += dmax(0., c.qv(i, j, k));
+            c.rad_qc(i_rad, j_rad, k) += c.qcl(i, j, k);
+            c.rad_qi(i_rad, j_rad, k) += c.qci(i, j, k);
+            if (c.qcl(i, j, k) + c.qci(i, j, k) > 0) c.rad_cld(i_rad, j_rad, k) += c.cf3d(i, j, k);
+          }
+      for (int j = 1; j <= ny; j++)
+        for (int i = 1; i <= nx; i++)
+          for (int k = 1; k <= nzm + 1; k++) {
+            int l = plev + 1 - k + 1;
+            if (c.w(i, j, k) > 0.) {
+              int kx = std::max(1, k - 1);
+              double qsat = qsatw_crm(c.tabs(i, j, kx), c.pres(kx));
+              if (c.qcl(i, j, kx) + c.qci(i, j, kx) > dmin(R4(1.e-5), R4(0.01) * qsat)) c.mui_crm(l) += c.rhow(k) * c.w(i, j, k);
+            } else if (c.w(i, j, k) < 0.) {
+              int kx = std::min(k + 1, nzm);
+              double qsat = qsatw_crm(c.tabs(i, j, kx), c.pres(kx));
+              if (c.qcl(i, j, kx) + c.qci(i, j, kx) > dmin(R4(1.e-5), R4(0.01) * qsat)) c.mdi_crm(l) += c.rhow(k) * c.w(i, j, k);
+              else if (c.qpl(i, j, kx) + c.qpi(i, j, kx) > R4(1.0e-4)) c.mdi_crm(l) += c.rhow(k) * c.w(i, j, k);
+            }
+          }
+    }
+  }   // nstep
+
+  const double factor_xyt = factor_xy / (double)nstop;
+  const double tmp1r = crm_nx_rad_fac * crm_ny_rad_fac / (double)nstop;
+  s.nstop = nstop;
+
+  // ======================================= epilogue (crm_module.F90:1086-1594) =======================================
+  auto OUT2 = [&](double *a, int icrm, int l) -> double & { return a[(size_t)icrm + (size_t)ld * (l - 1)]; };
+#pragma omp parallel for schedule(static)
+  for (int ic = 0; ic < ncrms; ic++) {
+    Crm &c = crms[ic];
+    for (int k = 1; k <= nzm; k++)
+      for (int j = 1; j <= g.ny_rad; j++)
+        for (int i = 1; i <= g.nx_rad; i++) {
+          size_t o = erad.at(ic, i - 1, j - 1, k - 1);
+          if (rad->temperature) rad->temperature[o] = c.rad_t(i, j, k) * tmp1r;
+          if (rad->qv) rad->qv[o] = c.rad_qv(i, j, k) * tmp1r;
+          if (rad->qc) rad->qc[o] = c.rad_qc(i, j, k) * tmp1r;
+          if (rad->qi) rad->qi[o] = c.rad_qi(i, j, k) * tmp1r;
+          if (rad->cld) rad->cld[o] = c.rad_cld(i, j, k) * tmp1r;
+        }
+    for (int k = 1; k <= ptop - 1; k++) {
+      c.tln(k) = P2(in->tl, ic, k); c.qln(k) = P2(in->ql, ic, k); c.qccln(k) = P2(in->qccl, ic, k);
+      c.qiiln(k) = P2(in->qiil, ic, k); c.uln(k) = P2(in->ul, ic, k); c.vln(k) = P2(in->vl, ic, k);
+    }
+    for (int k = ptop; k <= plev; k++) { c.tln(k) = 0; c.qln(k) = 0; c.qccln(k) = 0; c.qiiln(k) = 0; c.uln(k) = 0; c.vln(k) = 0; }
+    c.colprec = 0; c.colprecs = 0;
+    for (int k = 1; k <= nzm; k++)
+      for (int i = 1; i <= nx; i++)
+        for (int j = 1; j <= ny; j++) {
+          int l = plev - k + 1;
+          double pdel = P2(in->pdel, ic, plev - k + 1);
+          c.colprec += (c.qpl(i, j, k) + c.qpi(i, j, k)) * pdel;
+          c.colprecs += c.qpi(i, j, k) * pdel;
+          c.tln(l) += c.tabs(i, j, k);
+          c.qln(l) += c.qv(i, j, k);
+          c.qccln(l) += c.qcl(i, j, k);
+          c.qiiln(l) += c.qci(i, j, k);
+          c.uln(l) += c.u(i, j, k);
+          c.vln(l) += c.v(i, j, k);
+        }
+    for (int k = ptop; k <= plev; k++) {
+      c.tln(k) *= factor_xy; c.qln(k) *= factor_xy; c.qccln(k) *= factor_xy; c.qiiln(k) *= factor_xy;
+      c.uln(k) *= factor_xy; c.vln(k) *= factor_xy;
+    }
+    for (int k = 1; k <= plev; k++) {
+      if (out->sltend) OUT2(out->sltend, ic, k) = cp * (c.tln(k) - P2(in->tl, ic, k)) * icrm_run_time;
+      if (out->qltend) OUT2(out->qltend, ic, k) = (c.qln(k) - P2(in->ql, ic, k)) * icrm_run_time;
+      if (out->qcltend) OUT2(out->qcltend, ic, k) = (c.qccln(k) - P2(in->qccl, ic, k)) * icrm_run_time;
+      if (out->qiltend) OUT2(out->qiltend, ic, k) = (c.qiiln(k) - P2(in->qiil, ic, k)) * icrm_run_time;
+    }
+    if (out->prectend) out->prectend[ic] = (c.colprec - c.prectend0) / ggr * factor_xy * icrm_run_time;
+    if (out->precstend) out->precstend[ic] = (c.colprecs - c.precstend0) / ggr * factor_xy * icrm_run_time;
+    for (int k = ptop; k <= ptop + 1; k++) {
+      if (out->sltend) OUT2(out->sltend, ic, k) = 0.;
+      if (out->qltend) OUT2(out->qltend, ic, k) = 0.;
+      if (out->qcltend) OUT2(out->qcltend, ic, k) = 0.;
+      if (out->qiltend) OUT2(out->qiltend, ic, k) = 0.;
+    }
+    for (int k = 1; k <= nzm; k++)
+      for (int j = 1; j <= ny; j++)
+        for (int i = 1; i <= nx; i++) {
+          size_t o = e3.at(ic, i - 1, j - 1, k - 1);
+          st->u_wind[o] = c.u(i, j, k); st->v_wind[o] = c.v(i, j, k); st->w_wind[o] = c.w(i, j, k);
+          st->temperature[o] = c.tabs(i, j, k);
+          st->qt[o] = c.qt(i, j, k); st->qp[o] = c.qp(i, j, k); st->qn[o] = c.qn(i, j, k);
+          if (out->tk) out->tk[o] = c.tk(i, j, k);
+          if (out->tkh) out->tkh[o] = c.tkh(i, j, k);
+          if (out->qcl) out->qcl[o] = c.qcl(i, j, k);
+          if (out->qci) out->qci[o] = c.qci(i, j, k);
+          if (out->qpl) out->qpl[o] = c.qpl(i, j, k);
+          if (out->qpi) out->qpi[o] = c.qpi(i, j, k);
+        }
+    if (out->z0m) out->z0m[ic] = c.z0;
+    if (out->taux) out->taux[ic] = c.taux0 / (double)nstop;
+    if (out->tauy) out->tauy[ic] = c.tauy0 / (double)nstop;
+    // ---- diagnostics (:1314-1377)
+    std::vector<double> qc_mean(plev + 1, 0.), qi_mean(plev + 1, 0.), qr_mean(plev + 1, 0.), qg_mean(plev + 1, 0.), qs_mean(plev + 1, 0.);
+    for (int k = 1; k <= nzm; k++)
+      for (int j = 1; j <= ny; j++)
+        for (int i = 1; i <= nx; i++) {
+          int l = plev - k + 1;
+          qc_mean[l] += c.qcl(i, j, k); qi_mean[l] += c.qci(i, j, k); qr_mean[l] += c.qpl(i, j, k);
+          double omg = dmax(0., dmin(1., (c.tabs(i, j, k) - tgrmin) * mc.a_gr));
+          qg_mean[l] += c.qpi(i, j, k) * omg;
+          qs_mean[l] += c.qpi(i, j, k) * (1. - omg);
+        }
+    for (int k = 1; k <= plev; k++) {
+      double pdel = P2(in->pdel, ic, k);
+      double cld = dmin(1., c.o_cld(k) * factor_xyt), cldtop = dmin(1., c.o_cldtop(k) * factor_xyt);
+      double mcup = c.o_mcup(k) * factor_xyt, mcdn = c.o_mcdn(k) * factor_xyt, mcuup = c.o_mcuup(k) * factor_xyt, mcudn = c.o_mcudn(k) * factor_xyt;
+      if (out->cld) OUT2(out->cld, ic, k) = cld;
+      if (out->cldtop) OUT2(out->cldtop, ic, k) = cldtop;
+      if (out->gicewp) OUT2(out->gicewp, ic, k) = c.o_gicewp(k) * pdel * R4(1000.) / ggr * factor_xyt;
+      if (out->gliqwp) OUT2(out->gliqwp, ic, k) = c.o_gliqwp(k) * pdel * R4(1000.) / ggr * factor_xyt;
+      if (out->mcup) OUT2(out->mcup, ic, k) = mcup;
+      if (out->mcdn) OUT2(out->mcdn, ic, k) = mcdn;
+      if (out->mcuup) OUT2(out->mcuup, ic, k) = mcuup;
+      if (out->mcudn) OUT2(out->mcudn, ic, k) = mcudn;
+      if (out->mctot) OUT2(out->mctot, ic, k) = mcup + mcdn + mcuup + mcudn;
+      if (out->qc_mean) OUT2(out->qc_mean, ic, k) = qc_mean[k] * factor_xy;
+      if (out->qi_mean) OUT2(out->qi_mean, ic, k) = qi_mean[k] * factor_xy;
+      if (out->qs_mean) OUT2(out->qs_mean, ic, k) = qs_mean[k] * factor_xy;
+      if (out->qg_mean) OUT2(out->qg_mean, ic, k) = qg_mean[k] * factor_xy;
+      if (out->qr_mean) OUT2(out->qr_mean, ic, k) = qr_mean[k] * factor_xy;
+    }
+    // ---- precipitation (:1417-1481)
+    double precc = 0, precl = 0, precsc = 0, precsl = 0;
+    const double thr = (double)(10.f / 86400.f);
+    for (int j = 1; j <= ny; j++)
+      for (int i = 1; i <= nx; i++) {
+        int o2 = (j - 1) * nx + i - 1;
+        c.precsfc[o2] = c.precsfc[o2] * c.dz / s.dt / (double)nstop;
+        c.precssfc[o2] = c.precssfc[o2] * c.dz / s.dt / (double)nstop;
+        if (c.precsfc[o2] > thr) { precc += c.precsfc[o2]; precsc += c.precssfc[o2]; }
+        else { precl += c.precsfc[o2]; precsl += c.precssfc[o2]; }
+        if (out->prec_crm) out->prec_crm[(size_t)ic + (size_t)ld * ((i - 1) + (size_t)nx * (j - 1))] = c.precsfc[o2] / R4(1000.);
+      }
+    if (out->precc) out->precc[ic] = precc * factor_xy / R4(1000.);
+    if (out->precl) out->precl[ic] = precl * factor_xy / R4(1000.);
+    if (out->precsc) out->precsc[ic] = precsc * factor_xy / R4(1000.);
+    if (out->precsl) out->precsl[ic] = precsl * factor_xy / R4(1000.);
+    if (out->cltot) out->cltot[ic] = c.o_cltot * factor_xyt;
+    if (out->clhgh) out->clhgh[ic] = c.o_clhgh * factor_xyt;
+    if (out->clmed) out->clmed[ic] = c.o_clmed * factor_xyt;
+    if (out->cllow) out->cllow[ic] = c.o_cllow * factor_xyt;
+    // ---- mass fluxes (:1483-1511)
+    double jt = plev * R4(1.0), mx = R4(1.0);
+    for (int k = 1; k <= plev; k++) {
+      double mu = 0.5 * (c.mui_crm(k) + c.mui_crm(k + 1)), md = 0.5 * (c.mdi_crm(k) + c.mdi_crm(k + 1));
+      mu = mu * ggr / R4(100.); md = md * ggr / R4(100.);
+      double pdel = P2(in->pdel, ic, k);
+      double eu = 0., du = 0., ed = 0.;
+      if (c.mui_crm(k) - c.mui_crm(k + 1) > 0) eu = (c.mui_crm(k) - c.mui_crm(k + 1)) * ggr / pdel;
+      else du = R4(-1.0) * (c.mui_crm(k) - c.mui_crm(k + 1)) * ggr / pdel;
+      if (c.mdi_crm(k + 1) - c.mdi_crm(k) < 0) ed = (c.mdi_crm(k) - c.mdi_crm(k + 1)) * ggr / pdel;
+      else c.dd_crm(k) = R4(-1.) * (c.mdi_crm(k) - c.mdi_crm(k + 1)) * ggr / pdel;
+      if (out->mu_crm) OUT2(out->mu_crm, ic, k) = mu;
+      if (out->md_crm) OUT2(out->md_crm, ic, k) = md;
+      if (out->eu_crm) OUT2(out->eu_crm, ic, k) = eu;
+      if (out->du_crm) OUT2(out->du_crm, ic, k) = du;
+      if (out->ed_crm) OUT2(out->ed_crm, ic, k) = ed;
+      if (std::fabs(mu) > R4(1.0e-15) || std::fabs(md) > R4(1.0e-15)) { jt = dmin((double)k, jt); mx = dmax((double)k, mx); }
+    }
+    if (out->jt_crm) out->jt_crm[ic] = jt;
+    if (out->mx_crm) out->mx_crm[ic] = mx;
+    // ---- fluxes and other stat (:1516-1594); levels above the CRM top were zeroed at :620-658
+    for (int k = 1; k <= plev; k++) {
+      for (double *a : {out->flux_qt, out->flux_u, out->flux_v, out->fluxsgs_qt, out->tkez, out->tkesgsz, out->tkz, out->flux_qp,
+                        out->precflux, out->qt_trans, out->qp_trans, out->qp_fall, out->qp_evp, out->qp_src, out->qt_ls, out->t_ls})
+        if (a) OUT2(a, ic, k) = 0.;
+    }
+    for (int k = 1; k <= nzm; k++) {
+      double u2z = 0., v2z = 0., w2z = 0.;
+      for (int j = 1; j <= ny; j++)
+        for (int i = 1; i <= nx; i++) {
+          u2z += (c.u(i, j, k) - c.u0(k)) * (c.u(i, j, k) - c.u0(k));
+          v2z += (c.v(i, j, k) - c.v0(k)) * (c.v(i, j, k) - c.v0(k));
+          w2z += 0.5 * (c.w(i, j, k + 1) * c.w(i, j, k + 1) + c.w(i, j, k) * c.w(i, j, k));
+        }
+      double tmp1 = c.dz / c.rhow(k);
+      double tmp2 = tmp1 / s.dtn;   // last dtn
+      for (int n = 1; n <= 2; n++) {
+        c.mkwsb[n](k) = c.mkwsb[n](k) * tmp1 * c.rhow(k) * factor_xy / nstop;
+        c.mkwle[n](k) = c.mkwle[n](k) * tmp2 * c.rhow(k) * factor_xy / nstop;
+        c.mkadv[n](k) = c.mkadv[n](k) * factor_xy * icrm_run_time;
+        c.mkdiff[n](k) = c.mkdiff[n](k) * factor_xy * icrm_run_time;
+      }
+      c.qpsrc(k) = c.qpsrc(k) * factor_xy * icrm_run_time;
+      c.qpevp(k) = c.qpevp(k) * factor_xy * icrm_run_time;
+      c.qpfall(k) = c.qpfall(k) * factor_xy * icrm_run_time;
+      c.precflux(k) = c.precflux(k) * factor_xy * c.dz / s.dt / nstop;
+      int l = plev - k + 1;
+      if (out->flux_u) OUT2(out->flux_u, ic, l) = (c.uwle(k) + c.uwsb(k)) * tmp1 * factor_xy / nstop;
+      if (out->flux_v) OUT2(out->flux_v, ic, l) = (c.vwle(k) + c.vwsb(k)) * tmp1 * factor_xy / nstop;
+      if (out->flux_qt) OUT2(out->flux_qt, ic, l) = c.mkwle[1](k) + c.mkwsb[1](k);
+      if (out->fluxsgs_qt) OUT2(out->fluxsgs_qt, ic, l) = c.mkwsb[1](k);
+      if (out->flux_qp) OUT2(out->flux_qp, ic, l) = c.mkwle[2](k) + c.mkwsb[2](k);
+      if (out->qt_trans) OUT2(out->qt_trans, ic, l) = c.mkadv[1](k) + c.mkdiff[1](k);
+      if (out->qp_trans) OUT2(out->qp_trans, ic, l) = c.mkadv[2](k) + c.mkdiff[2](k);
+      double tmp = 0;
+      for (int j = 1; j <= ny; j++)
+        for (int i = 1; i <= nx; i++) tmp += c.tke(i, j, k);
+      double tkesgsz = c.rho(k) * tmp * factor_xy;
+      if (out->tkesgsz) OUT2(out->tkesgsz, ic, l) = tkesgsz;
+      if (out->tkez) OUT2(out->tkez, ic, l) = c.rho(k) * 0.5 * (u2z + v2z * g.YES3D + w2z) * factor_xy + tkesgsz;
+      tmp = 0;
+      for (int j = 1; j <= ny; j++)
+        for (int i = 1; i <= nx; i++) tmp += c.tk(i, j, k);
+      if (out->tkz) OUT2(out->tkz, ic, l) = tmp * factor_xy;
+      if (out->precflux) OUT2(out->precflux, ic, l) = c.precflux(k) / R4(1000.);
+      if (out->qp_fall) OUT2(out->qp_fall, ic, l) = c.qpfall(k);
+      if (out->qp_evp) OUT2(out->qp_evp, ic, l) = c.qpevp(k);
+      if (out->qp_src) OUT2(out->qp_src, ic, l) = c.qpsrc(k);
+      if (out->qt_ls) OUT2(out->qt_ls, ic, l) = c.qtend(k);
+      if (out->t_ls) OUT2(out->t_ls, ic, l) = c.ttend(k);
+    }
+    if (out->timing_factor) out->timing_factor[ic] = c.o_timing / nstop;
+  }
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    stats->nstop = nstop; stats->ncycle_sum = ncycle_sum; stats->ncycle_max = ncycle_max; stats->nprec_max = nprec_max;
+  }
+  g_geo = g; g_step = s;
+  return 0;
+}
+
+// Copy an internal field left by the last run: layout (ncrms,nx,ny,nk), icrm fastest, ld = ncrms.
+extern "C" long long crm_oracle_debug_fetch(const char *name, double *buf, size_t n) {
+  const Geo &g = g_geo;
+  const int ncrms = (int)g_crms.size();
+  if (!ncrms) return -1;
+  std::string nm(name);
+  int nk = g.nzm;
+  if (nm == "w" || nm == "dwdt") nk = g.nz;
+  size_t need = (size_t)ncrms * g.nx * g.ny * nk;
+  if (n < need) return -2;
+  for (int ic = 0; ic < ncrms; ic++) {
+    Crm &c = g_crms[ic];
+    F3 *f = nullptr;
+    if (nm == "u") f = &c.u; else if (nm == "v") f = &c.v; else if (nm == "w") f = &c.w; else if (nm == "t") f = &c.t;
+    else if (nm == "qt") f = &c.qt; else if (nm == "qp") f = &c.qp; else if (nm == "qn") f = &c.qn;
+    else if (nm == "tabs") f = &c.tabs; else if (nm == "qv") f = &c.qv; else if (nm == "qcl") f = &c.qcl;
+    else if (nm == "qci") f = &c.qci; else if (nm == "qpl") f = &c.qpl; else if (nm == "qpi") f = &c.qpi;
+    else if (nm == "tk") f = &c.tk; else if (nm == "tkh") f = &c.tkh; else if (nm == "tke") f = &c.tke; else if (nm == "p") f = &c.p;
+    else if (nm == "dudt") f = &c.dudt[g_step.nb]; else if (nm == "dwdt") f = &c.dwdt[g_step.nb];   // slot just computed (after rotation it is nb)
+    else return -3;
+    for (int k = 1; k <= nk; k++)
+      for (int j = 1; j <= g.ny; j++)
+        for (int i = 1; i <= g.nx; i++)
+          buf[(size_t)ic + (size_t)ncrms * ((i - 1) + (size_t)g.nx * ((j - 1) + (size_t)g.ny * (k - 1)))] = (*f)(i, j, k);
+  }
+  return (long long)need;
+}
+
+extern "C" void crm_oracle_release(void) { g_crms.clear(); g_crms.shrink_to_fit(); }
+
+// ---- small KAT hooks used by tests/test_oracle_kat.py ----
+extern "C" void crm_oracle_fft991(int n, int twiddle_f32, int isign, double *a) {
+  FftPlan p; p.init(n, twiddle_f32 != 0); p.fft991(a, isign);
+}
+extern "C" double crm_oracle_esatw(double t) { return esatw_crm(t); }
+extern "C" double crm_oracle_esati(double t) { return esati_crm(t); }
+extern "C" double crm_oracle_qsatw(double t, double p) { return qsatw_crm(t, p); }
+extern "C" double crm_oracle_qsati(double t, double p) { return qsati_crm(t, p); }
+extern "C" void crm_oracle_rng(int seed, int n, double *out) {
+  RngMT r; r.set_seed(seed);
+  for (int i = 0; i < n; i++) out[i] = r.gen_rand();
+}
+extern "C" int crm_oracle_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
