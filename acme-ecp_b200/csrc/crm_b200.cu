@@ -1,0 +1,559 @@
+// crm_b200.cu -- host driver + C ABI (include/crm_b200.h) of the B200-native CRM.
+// Sequencing restates subroutine crm() (reference CRM/crm_module.F90:45-1718): prologue, time loop with the
+// batch-global kurant sub-cycling, per-step statistics, epilogue.  All arithmetic on 3-D fields happens in the
+// sm_100a kernels of crm_k_*.cuh; there is no CPU fallback (with CRM_EMU undefined, this file needs a CUDA device).
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/crm_b200.h"
+#include "crm_k_stats.cuh"
+#include "crm_host_util.h"
+
+using namespace crm;
+
+// ------------------------------------------------------------------------------------------------
+// thin device API (real CUDA or the dev-only emulator)
+// ------------------------------------------------------------------------------------------------
+#ifdef CRM_EMU
+static int dev_init(int) { return 0; }
+static void *dev_alloc(size_t n) { return calloc(1, n ? n : 1); }
+static void dev_free(void *p) { free(p); }
+static int dev_zero(void *p, size_t n) { memset(p, 0, n); return 0; }
+static int dev_copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, int /*kind*/) {
+  for (size_t r = 0; r < height; r++) memcpy((char *)dst + r * dpitch, (const char *)src + r * spitch, width);
+  return 0;
+}
+static int dev_sync() { return 0; }
+static bool is_dev_ptr(const void *) { return false; }
+static const char *dev_errstr() { return "emu"; }
+struct DevTimer { void start() {} double stop() { return 0.; } };
+#else
+static int dev_init(int device) { return cudaSetDevice(device) == cudaSuccess ? 0 : 1; }
+static void *dev_alloc(size_t n) { void *p = nullptr; if (cudaMalloc(&p, n ? n : 1) != cudaSuccess) return nullptr; return p; }
+static void dev_free(void *p) { cudaFree(p); }
+static int dev_zero(void *p, size_t n) { return cudaMemsetAsync(p, 0, n, 0) == cudaSuccess ? 0 : 1; }
+static int dev_copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, int /*kind*/) {
+  return cudaMemcpy2D(dst, dpitch, src, spitch, width, height, cudaMemcpyDefault) == cudaSuccess ? 0 : 1;
+}
+static int dev_sync() { return cudaDeviceSynchronize() == cudaSuccess ? 0 : 1; }
+static bool is_dev_ptr(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+static const char *dev_errstr() { return cudaGetErrorString(cudaGetLastError()); }
+struct DevTimer {
+  cudaEvent_t a, b;
+  DevTimer() { cudaEventCreate(&a); cudaEventCreate(&b); }
+  ~DevTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+  void start() { cudaEventRecord(a, 0); }
+  double stop() { cudaEventRecord(b, 0); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+};
+#endif
+
+namespace {
+
+struct Handle {
+  crm_dims_t d0;          // init dims
+  int device = 0;
+  int CT = 8, ntiles = 0, P = 0, nzp = 0;
+  long long tstride = 0;
+  size_t field_elems = 0, prof_elems = 0, col_elems = 0, slot_elems = 0, rad_elems = 0;
+  std::vector<void *> allocs;
+  CrmP p;                 // pointers filled at init; scalars per run
+  double *ubuf[4], *wbuf[4];
+  double *stage = nullptr;            // one boundary-layout 3-D field (ld_max*nx*ny*nzm)
+  double *esum = nullptr;
+  double *in_dev = nullptr;           // packed device copy of the crm_input arrays
+  double *out_dev = nullptr;          // packed device staging of profile/column outputs
+  double *rnd_dev = nullptr;
+  int *gcol_dev = nullptr;
+  int ld_max = 0;
+  std::string err;
+  crm_run_stats_t stats;
+  long long launches = 0;
+  int last_nb_u = 1;                  // buffer index holding dudt(nb) after the last run (debug fetch)
+};
+
+std::string g_init_err;
+
+template <typename T> T *carve(Handle *h, size_t n) {
+  void *q = dev_alloc(n * sizeof(T));
+  if (!q) return nullptr;
+  h->allocs.push_back(q);
+  dev_zero(q, n * sizeof(T));
+  return (T *)q;
+}
+
+#define LAUNCH(h, kern, grid, block, smem, ...)                 \
+  do {                                                          \
+    CRM_LAUNCH(kern, grid, block, smem, 0, __VA_ARGS__);        \
+    (h)->launches++;                                            \
+  } while (0)
+
+int fail(Handle *h, int code, const std::string &msg) { h->err = msg; return code; }
+
+// copy rows [0,ncrms) of a boundary array (leading dim ld_src) into a device array with leading dim ld_dst
+int copy_rows(void *dst, int ld_dst, const void *src, int ld_src, int ncrms, size_t ncols) {
+  return dev_copy2d(dst, (size_t)ld_dst * 8, src, (size_t)ld_src * 8, (size_t)ncrms * 8, ncols, 0);
+}
+
+}  // namespace
+
+extern "C" int crm_b200_abi_version(void) { return CRM_B200_ABI_VERSION; }
+
+extern "C" const char *crm_b200_last_error(void *handle) {
+  if (!handle) return g_init_err.c_str();
+  return ((Handle *)handle)->err.c_str();
+}
+
+extern "C" int crm_b200_free(void *handle) {
+  if (!handle) return 0;
+  Handle *h = (Handle *)handle;
+  for (void *q : h->allocs) dev_free(q);
+  delete h;
+  return 0;
+}
+
+extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
+  g_init_err.clear();
+  *handle = nullptr;
+  if (d->micro != 0) { g_init_err = "crm_b200_init: only sam1mom (micro=0) is implemented on device (M2005: see DESIGN.md, out of round-1 scope)"; return 2; }
+  if (d->ny != 1 || d->yes3d != 0) { g_init_err = "crm_b200_init: 3-D CRM (ny>1) is not implemented on device yet (DESIGN.md)"; return 3; }
+  if (d->nx < 8 || (d->nx & (d->nx - 1))) { g_init_err = "crm_b200_init: nx must be a power of two >= 8"; return 4; }
+  if (d->nzm < 4 || d->plev < d->nzm) { g_init_err = "crm_b200_init: need 4 <= nzm <= plev"; return 5; }
+  if (d->nx_rad < 1 || d->nx % d->nx_rad != 0) { g_init_err = "crm_nx_rad must divide nx (crm_module.F90:686-692)"; return 6; }
+  if (d->ncrms < 1 || d->ld < d->ncrms) { g_init_err = "crm_b200_init: need 1 <= ncrms <= ld"; return 7; }
+  if (dev_init(device)) { g_init_err = std::string("crm_b200_init: cannot select CUDA device: ") + dev_errstr(); return 8; }
+  Handle *h = new Handle();
+  h->d0 = *d; h->device = device;
+  int CT = 512 / d->nx;
+  if (CT > 16) CT = 16;
+  if (CT < 4) CT = 4;
+  if (const char *e = getenv("CRM_B200_CT")) { int v = atoi(e); if (v >= 1 && v <= 32 && !(v & (v - 1))) CT = v; }
+  while (d->nx * CT > 512 && CT > 1) CT >>= 1;
+  if (d->nx * CT > 512) { g_init_err = "crm_b200_init: nx too large (nx <= 512)"; delete h; return 4; }
+  h->CT = CT;
+  h->ntiles = (d->ncrms + CT - 1) / CT;
+  h->P = d->nx * CT;
+  const int nz = d->nzm + 1;
+  h->nzp = nz + 1;
+  h->tstride = (long long)nz * h->P;
+  h->field_elems = (size_t)h->ntiles * h->tstride;
+  h->prof_elems = (size_t)h->ntiles * h->nzp * CT;
+  h->col_elems = (size_t)h->ntiles * h->P;
+  h->slot_elems = (size_t)h->ntiles * CT;
+  h->rad_elems = (size_t)h->ntiles * d->nzm * d->nx_rad * CT;
+  h->ld_max = d->ld;
+  CrmP &p = h->p;
+  memset(&p, 0, sizeof(p));
+  p.ncrms = d->ncrms; p.ntiles = h->ntiles; p.CT = CT; p.nx = d->nx; p.ny = 1; p.nzm = d->nzm; p.nz = nz; p.nzp = h->nzp;
+  p.plev = d->plev; p.nx_rad = d->nx_rad; p.ny_rad = d->ny_rad; p.P = h->P; p.ld = d->ld; p.tstride = h->tstride;
+  p.dx = d->dx; p.dy = d->dx;
+  bool ok = true;
+  auto F = [&](double *&ptr) { ptr = carve<double>(h, h->field_elems); ok = ok && ptr; };
+  auto PRF = [&](double *&ptr) { ptr = carve<double>(h, h->prof_elems); ok = ok && ptr; };
+  auto SL = [&](double *&ptr) { ptr = carve<double>(h, h->slot_elems); ok = ok && ptr; };
+  for (int n = 0; n < 4; n++) { F(h->ubuf[n]); F(h->wbuf[n]); }
+  F(p.umf); F(p.wmf);
+  for (double **f : {&p.t, &p.qt, &p.qp, &p.qn, &p.tabs, &p.qv, &p.qcl, &p.qci, &p.qpl, &p.qpi, &p.tk, &p.tkh, &p.tke, &p.pbeta, &p.palfa, &p.wp}) F(*f);
+  for (double **f : {&p.qrad, &p.rad_t, &p.rad_qv, &p.rad_qc, &p.rad_qi, &p.rad_cld}) { *f = carve<double>(h, h->rad_elems); ok = ok && *f; }
+  for (double **f : {&p.z, &p.zi, &p.pres, &p.presi, &p.adz, &p.adzw, &p.rho, &p.rhow, &p.bet, &p.gamaz, &p.grdf_x, &p.grdf_z, &p.pdel, &p.tau,
+                     &p.t0, &p.q0, &p.qv0, &p.tabs0, &p.u0, &p.qn0, &p.qp0, &p.t00, &p.ttend, &p.qtend, &p.utend,
+                     &p.tl, &p.ql, &p.qccl, &p.qiil, &p.uln,
+                     &p.accrsc, &p.accrsi, &p.accrrc, &p.coefice, &p.accrgc, &p.accrgi, &p.evaps1, &p.evaps2, &p.evapr1, &p.evapr2, &p.evapg1, &p.evapg2,
+                     &p.precflux, &p.qpfall, &p.qpsrc, &p.qpevp, &p.uwle, &p.uwsb,
+                     &p.mkwle1, &p.mkwle2, &p.mkwsb1, &p.mkwsb2, &p.mkadv1, &p.mkadv2, &p.mkdiff1, &p.mkdiff2,
+                     &p.acc_t, &p.acc_q, &p.acc_u,
+                     &p.s_cld, &p.s_cldtop, &p.s_gicewp, &p.s_gliqwp, &p.s_mcup, &p.s_mcdn, &p.s_mcuup, &p.s_mcudn, &p.s_mui, &p.s_mdi})
+    PRF(*f);
+  for (double **f : {&p.dz, &p.z0, &p.colprec0, &p.colprecs0, &p.s_cltot, &p.s_clhgh, &p.s_clmed, &p.s_cllow}) SL(*f);
+  p.kmin = carve<int>(h, h->slot_elems); p.kmax = carve<int>(h, h->slot_elems); p.ndamp = carve<int>(h, h->slot_elems);
+  p.precsfc = carve<double>(h, h->col_elems); p.precssfc = carve<double>(h, h->col_elems);
+  p.cfl_bits = carve<unsigned long long>(h, 2); p.prec_cfl_bits = p.cfl_bits ? p.cfl_bits + 1 : nullptr;
+  p.flags = carve<int>(h, 4);
+  p.twc = carve<double>(h, d->nx); p.tws = carve<double>(h, d->nx);
+  h->stage = carve<double>(h, (size_t)d->ld * d->nx * d->ny * d->nzm);
+  h->esum = carve<double>(h, (size_t)CRM_NESUM * h->prof_elems);
+  h->in_dev = carve<double>(h, (size_t)d->ld * (11 * (size_t)(d->plev + 1) + 8));
+  h->out_dev = carve<double>(h, (size_t)d->ld * (39 * (size_t)d->plev + 16 + (size_t)d->nx * d->ny));
+  h->rnd_dev = carve<double>(h, (size_t)d->ncrms * 5 * d->nx * d->ny);
+  h->gcol_dev = carve<int>(h, d->ld);
+  ok = ok && p.kmin && p.kmax && p.ndamp && p.precsfc && p.precssfc && p.cfl_bits && p.flags && p.twc && p.tws && h->stage && h->esum &&
+       h->in_dev && h->out_dev && h->rnd_dev && h->gcol_dev;
+  if (!ok) {
+    g_init_err = "crm_b200_init: device allocation failed (workspace arena)";
+    crm_b200_free(h);
+    return 9;
+  }
+  if (!micro_scalars(p.ms)) { g_init_err = "cannot compute gamma-function in precip_init"; crm_b200_free(h); return 10; }
+#ifndef CRM_EMU
+  {
+    const int big = 96 * 1024;
+    cudaFuncSetAttribute(k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_epi_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_p8_micro, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_mpdata, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_prologue_fields, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  }
+#endif
+  if (dev_sync()) { g_init_err = std::string("crm_b200_init: ") + dev_errstr(); crm_b200_free(h); return 11; }
+  *handle = h;
+  return 0;
+}
+
+extern "C" int crm_b200_get_stats(void *handle, crm_run_stats_t *s) {
+  if (!handle || !s) return 1;
+  *s = ((Handle *)handle)->stats;
+  return 0;
+}
+
+extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t *in, crm_state_t *st, crm_rad_t *rad, crm_output_t *out) {
+  if (!handle) return 1;
+  Handle *h = (Handle *)handle;
+  h->err.clear();
+  const crm_dims_t &d0 = h->d0;
+  if (d->nx != d0.nx || d->ny != d0.ny || d->nzm != d0.nzm || d->plev != d0.plev || d->nx_rad != d0.nx_rad || d->ny_rad != d0.ny_rad ||
+      d->dx != d0.dx || d->dt != d0.dt || d->micro != d0.micro)
+    return fail(h, 20, "crm_b200_run: geometry differs from crm_b200_init");
+  if (d->ncrms < 1 || d->ncrms > d0.ncrms || d->ld < d->ncrms || d->ld > h->ld_max) return fail(h, 21, "crm_b200_run: need ncrms <= init ncrms and ncrms <= ld <= init ld");
+  if (dev_init(h->device)) return fail(h, 22, std::string("crm_b200_run: cannot select device: ") + dev_errstr());
+  auto wall0 = std::chrono::steady_clock::now();
+  memset(&h->stats, 0, sizeof(h->stats));
+  h->launches = 0;
+  CrmP &p = h->p;
+  const int CT = h->CT, P = h->P, nx = d->nx, nzm = d->nzm, nz = nzm + 1, plev = d->plev, ld = d->ld, ncrms = d->ncrms;
+  const int ntiles = (ncrms + CT - 1) / CT;
+  p.ncrms = ncrms; p.ntiles = ntiles; p.ld = ld;
+  p.dt = d->dt; p.dt_gl = d->dt_gl; p.igstep = d->igstep;
+  p.use_accel = d->use_crm_accel; p.accel_uv = d->crm_accel_uv; p.accel_factor = d->crm_accel_factor;
+  const size_t fbytes = (size_t)ntiles * h->tstride * 8, pbytes = (size_t)ntiles * h->nzp * CT * 8;
+  const size_t RED1 = sizeof(double);
+  auto red_bytes = [&](int nq) { return (size_t)CRM_RED_DOUBLES(nq, P, CT) * RED1; };
+
+  // ---------------- cold start of the per-call state ----------------
+  for (int n = 0; n < 4; n++) { dev_zero(h->ubuf[n], fbytes); dev_zero(h->wbuf[n], fbytes); }
+  for (double *f : {p.umf, p.wmf, p.tk, p.tkh, p.tke, p.qv, p.qcl, p.qci, p.qpl, p.qpi}) dev_zero(f, fbytes);
+  for (double *f : {p.rad_t, p.rad_qv, p.rad_qc, p.rad_qi, p.rad_cld}) dev_zero(f, (size_t)ntiles * nzm * d->nx_rad * CT * 8);
+  for (double *f : {p.precflux, p.qpfall, p.qpsrc, p.qpevp, p.uwle, p.uwsb, p.mkwle1, p.mkwle2, p.mkwsb1, p.mkwsb2, p.mkadv1, p.mkadv2, p.mkdiff1,
+                    p.mkdiff2, p.s_cld, p.s_cldtop, p.s_gicewp, p.s_gliqwp, p.s_mcup, p.s_mcdn, p.s_mcuup, p.s_mcudn, p.s_mui, p.s_mdi})
+    dev_zero(f, pbytes);
+  for (double *f : {p.s_cltot, p.s_clhgh, p.s_clmed, p.s_cllow}) dev_zero(f, (size_t)ntiles * CT * 8);
+  dev_zero(p.precsfc, (size_t)ntiles * P * 8); dev_zero(p.precssfc, (size_t)ntiles * P * 8);
+  dev_zero(p.cfl_bits, 16); dev_zero(p.flags, 16);
+
+  // ---------------- boundary inputs ----------------
+  DevTimer tm;
+  tm.start();
+  long long h2d = 0;
+  ExtIn ei;
+  {
+    double *q = h->in_dev;
+    auto put = [&](const double *src, int ncols) -> const double * {
+      double *dst = q; q += (size_t)ld * ncols;
+      if (is_dev_ptr(src)) { copy_rows(dst, ld, src, ld, ncrms, ncols); }
+      else { copy_rows(dst, ld, src, ld, ncrms, ncols); h2d += (long long)ncrms * ncols * 8; }
+      return dst;
+    };
+    ei.zmid = put(in->zmid, plev); ei.zint = put(in->zint, plev + 1); ei.tl = put(in->tl, plev); ei.ql = put(in->ql, plev);
+    ei.qccl = put(in->qccl, plev); ei.qiil = put(in->qiil, plev); ei.pmid = put(in->pmid, plev); ei.pint = put(in->pint, plev + 1);
+    ei.pdel = put(in->pdel, plev); ei.ul = put(in->ul, plev); ei.vl = put(in->vl, plev);
+    ei.tau00 = put(in->tau00, 1); ei.wndls = put(in->wndls, 1); ei.bflxls = put(in->bflxls, 1);
+    ei.gcol = h->gcol_dev;
+  }
+  // twiddles
+  {
+    std::vector<double> c, s;
+    twiddles(nx, d->twiddle_f32 != 0, c, s);
+    dev_copy2d(p.twc, nx * 8, c.data(), nx * 8, nx * 8, 1, 0);
+    dev_copy2d(p.tws, nx * 8, s.data(), nx * 8, nx * 8, 1, 0);
+  }
+  // role assignment of the velocity buffers
+  int iu = 0, ina = 1, inb = 2, inc = 3;
+  // 3-D state: boundary -> (staging) -> internal tiles
+  const size_t ncols3 = (size_t)nx * d->ny * nzm;
+  auto load3 = [&](const double *src, double *dst, bool first_u) {
+    const double *ext = src;
+    int lde = ld;
+    if (!is_dev_ptr(src)) { copy_rows(h->stage, ld, src, ld, ncrms, ncols3); ext = h->stage; h2d += (long long)ncrms * ncols3 * 8; }
+    if (first_u) LAUNCH(h, k_clamp_flag, 1, 32, 0, p, ext, lde);
+    LAUNCH(h, k_ext_to_int, ntiles * nzm, P, 0, p, ext, lde, nx, nzm, dst, h->tstride, P, 1.0);
+  };
+  load3(st->u_wind, h->ubuf[iu], true);
+  load3(st->w_wind, h->wbuf[iu], false);
+  load3(st->temperature, p.tabs, false);
+  load3(st->qt, p.qt, false);
+  load3(st->qp, p.qp, false);
+  load3(st->qn, p.qn, false);
+  {
+    const size_t ncr = (size_t)d->nx_rad * d->ny_rad * nzm;
+    const double *ext = rad->qrad;
+    if (!is_dev_ptr(ext)) { copy_rows(h->stage, ld, rad->qrad, ld, ncrms, ncr); ext = h->stage; h2d += (long long)ncrms * ncr * 8; }
+    LAUNCH(h, k_ext_to_int, ntiles * nzm, d->nx_rad * CT, 0, p, ext, ld, d->nx_rad, nzm, p.qrad, (long long)nzm * d->nx_rad * CT, d->nx_rad * CT, 1.0);
+  }
+  if (dev_sync()) return fail(h, 23, std::string("crm_b200_run: input transfer failed: ") + dev_errstr());
+  h->stats.ms_h2d = tm.stop();
+  h->stats.h2d_bytes = h2d;
+
+  DevTimer tk;
+  tk.start();
+  // ---------------- prologue ----------------
+  p.u = h->ubuf[iu]; p.w = h->wbuf[iu];
+  p.du_a = h->ubuf[ina]; p.du_b = h->ubuf[inb]; p.du_c = h->ubuf[inc];
+  p.dw_a = h->wbuf[ina]; p.dw_b = h->wbuf[inb]; p.dw_c = h->wbuf[inc];
+  const int slot_blocks = (ntiles * CT + 127) / 128;
+  LAUNCH(h, k_prologue_grid, slot_blocks, 128, 0, p, ei);
+  LAUNCH(h, k_prologue_fields, ntiles, P, red_bytes(9), p);
+  LAUNCH(h, k_precip_init, (ntiles * nzm * CT + 127) / 128, 128, 0, p);
+  if (d->igstep <= 1) {   // setperturb (crm_module.F90:677-681): RNG draws on the host like the reference
+    const int nxy = nx * d->ny;
+    std::vector<double> rnd((size_t)ncrms * 5 * nxy);
+    std::vector<int> gcol(ld);
+    if (is_dev_ptr(in->gcol)) dev_copy2d(gcol.data(), ld * 4, in->gcol, ld * 4, (size_t)ncrms * 4, 1, 0);
+    else memcpy(gcol.data(), in->gcol, (size_t)ncrms * 4);
+    for (int ic = 0; ic < ncrms; ic++) {
+      RngMT r; r.set_seed((int)((unsigned)gcol[ic] * 1000u));
+      for (int q = 0; q < 5 * nxy; q++) rnd[(size_t)ic * 5 * nxy + q] = r.gen_rand();
+    }
+    dev_copy2d(h->rnd_dev, rnd.size() * 8, rnd.data(), rnd.size() * 8, rnd.size() * 8, 1, 0);
+    LAUNCH(h, k_setperturb, slot_blocks, 128, 0, p, h->rnd_dev);
+  }
+  LAUNCH(h, k_press_alfa, ntiles, P, 0, p);
+
+  int nstop = (int)(d->dt_gl / d->dt);   // crm_module.F90:712-713
+  if (nstop < 1) return fail(h, 24, "crm_b200_run: dt_gl < crm_dt");
+  double dt = d->dt_gl / nstop;
+  p.dt = dt;
+  if (d->use_crm_accel) {   // accelerate_crm.F90:78-107
+    if (nstop % (int)(1 + d->crm_accel_factor) != 0) return fail(h, 25, "crm main: bad crm_accel_factor and nstop pair");
+    nstop = (int)(nstop / (1 + d->crm_accel_factor));
+  }
+  if (R4(60.) < 2 * dt) return fail(h, 26, "Error: in damping() tau_min is too small!");
+  bool ceaseflag = false;
+  int na = 1, nb = 2, nc = 3;
+  double dt3[4] = {0, 0, 0, 0};
+  long long ncycle_sum = 0, ncycle_max = 0, nprec_max = 0;
+  double dtn = dt;
+  const size_t smem_mp = (size_t)9 * P * 8;
+  const int dbg_stop = getenv("CRM_DEBUG_STOP") ? atoi(getenv("CRM_DEBUG_STOP")) : 0;   // test hook: stop inside the first sub-step
+  bool dbg_break = false;
+
+  // ---------------- main time loop ----------------
+  int nstep = 0;
+  while (nstep < nstop) {
+    nstep++;
+    dev_zero(p.cfl_bits, 8);
+    LAUNCH(h, k_kurant, ntiles, P, (size_t)P * 8, p);
+    unsigned long long bits = 0;
+    if (dev_copy2d(&bits, 8, p.cfl_bits, 8, 8, 1, 0)) return fail(h, 27, std::string("crm_b200_run: kurant readback failed: ") + dev_errstr());
+    double cfl; memcpy(&cfl, &bits, 8);
+    if (!(cfl == cfl) || cfl > 1e30) return fail(h, 28, "kurant(): non-finite CFL (model state blew up)");
+    int ncycle = std::max(1, (int)std::ceil(cfl / R4(0.7)));
+    if (ncycle > 16) return fail(h, 29, "kurant() - the number of cycles exceeded max_ncycle = 16");
+    ncycle_sum += ncycle; ncycle_max = std::max<long long>(ncycle_max, ncycle);
+    for (int icyc = 1; icyc <= ncycle; icyc++) {
+      dtn = dt / ncycle;
+      dt3[na] = dtn;
+      double at, bt, ct;
+      if (nstep >= 3) {   // abcoefs.F90:15-29
+        double alpha = dt3[nb] / dt3[na], beta = dt3[nc] / dt3[na];
+        ct = (2. + 3. * alpha) / (6. * (alpha + beta) * beta);
+        bt = -(1. + 2. * (alpha + beta) * ct) / (2. * alpha);
+        at = 1. - bt - ct;
+      } else if (nstep >= 2) { at = (double)(3.f / 2.f); bt = (double)(-1.f / 2.f); ct = 0.; }
+      else { at = 1.; bt = 0.; ct = 0.; }
+      p.dtn = dtn; p.at = at; p.bt = bt; p.ct = ct; p.dt3na = dt3[na];
+      p.nstep = nstep; p.icycle = icyc; p.ncycle = ncycle; p.nstop = nstop;
+      p.last_substep = (nstep == nstop && icyc == ncycle) ? 1 : 0;   // statistics the reference overwrites every sub-step (mk*, uwle, qpsrc..)
+      p.u = h->ubuf[iu]; p.w = h->wbuf[iu];
+      p.du_a = h->ubuf[ina]; p.du_b = h->ubuf[inb]; p.du_c = h->ubuf[inc];
+      p.dw_a = h->wbuf[ina]; p.dw_b = h->wbuf[inb]; p.dw_c = h->wbuf[inc];
+      LAUNCH(h, k_p1_forcing, ntiles, P, red_bytes(3), p);
+      if (dbg_stop == 1) { dbg_break = true; break; }
+      LAUNCH(h, k_p2_sgs, ntiles, P, 0, p);
+      if (dbg_stop == 2) { dbg_break = true; break; }
+      LAUNCH(h, k_p3_mom, ntiles, P, red_bytes(2), p);
+      if (dbg_stop == 3) { dbg_break = true; break; }
+      LAUNCH(h, k_p4_press_fwd, ntiles, P, (size_t)(P + 2 * nx) * 8, p);
+      LAUNCH(h, k_p5_press_bwd, ntiles, P, (size_t)(2 * P + 2 * nx) * 8, p);
+      if (dbg_stop == 4) { dbg_break = true; break; }
+      // advect_all_scalars.F90:32-64
+      LAUNCH(h, k_mpdata, ntiles, P, smem_mp, p, p.t, (double *)nullptr, (double *)nullptr, 0);
+      LAUNCH(h, k_mpdata, ntiles, P, smem_mp + red_bytes(2), p, p.qt, p.mkadv1, p.mkwle1, 1);
+      LAUNCH(h, k_mpdata, ntiles, P, smem_mp + red_bytes(2), p, p.qp, p.mkadv2, p.mkwle2, 1);
+      if (dbg_stop == 5) { dbg_break = true; break; }
+      dev_zero(p.prec_cfl_bits, 8);
+      LAUNCH(h, k_precip_a, ntiles, P, (size_t)P * 8, p);
+      LAUNCH(h, k_precip_b, ntiles, P, red_bytes(2), p);
+      // uvw.F90: u <- dudt(nc) is a role rotation of the buffers (with the AB rotation of crm_module.F90:884-887)
+      { int o_u = iu, o_a = ina, o_b = inb, o_c = inc; iu = o_c; ina = o_u; inb = o_a; inc = o_b; }
+      p.u = h->ubuf[iu]; p.w = h->wbuf[iu];
+      if (dbg_stop == 6) { dbg_break = true; break; }
+      LAUNCH(h, k_p7_diffuse, ntiles, P, red_bytes(4), p);
+      if (dbg_stop == 7) { dbg_break = true; break; }
+      if (icyc == 1) LAUNCH(h, k_precip_init, (ntiles * nzm * CT + 127) / 128, 128, 0, p);
+      LAUNCH(h, k_reset_kminmax, slot_blocks, 128, 0, p);
+      const size_t smem_p8 = red_bytes(9) + 2 * CT * sizeof(int);
+      if (d->use_crm_accel && !ceaseflag) {
+        LAUNCH(h, k_p8_micro, ntiles * nzm, P, smem_p8, p, 1, 0);
+        LAUNCH(h, k_msa_a, ntiles * nzm, P, red_bytes(3), p);
+        int flags[4];
+        if (dev_copy2d(flags, 16, p.flags, 16, 16, 1, 0)) return fail(h, 30, "crm_b200_run: MSA flag readback failed");
+        if (flags[1]) {
+          ceaseflag = true;
+          nstop = (int)(nstop + (nstop - nstep + 1) * d->crm_accel_factor);   // accelerate_crm.F90:243
+        } else {
+          LAUNCH(h, k_msa_b, ntiles * nzm, P, red_bytes(2), p);
+        }
+        LAUNCH(h, k_p8_micro, ntiles * nzm, P, smem_p8, p, 0, 1);
+      } else {
+        LAUNCH(h, k_p8_micro, ntiles * nzm, P, smem_p8, p, 1, 1);
+      }
+      { int nn = na; na = nc; nc = nb; nb = nn; }
+      if (dbg_stop == 8) { dbg_break = true; break; }
+    }
+    if (dbg_break) break;
+    p.nstop = nstop;
+    LAUNCH(h, k_stats, ntiles, P, (size_t)(CRM_RED_DOUBLES(10, P, CT) + 5 * P) * 8, p);
+    // nprec statistic (device value of the last sub-step)
+    if ((nstep & 15) == 0 || nstep == nstop) {
+      unsigned long long pb2 = 0; dev_copy2d(&pb2, 8, p.prec_cfl_bits, 8, 8, 1, 0);
+      double pc; memcpy(&pc, &pb2, 8);
+      long long np_ = pc > R4(0.9) ? (long long)std::ceil(pc / R4(0.9)) : 1;
+      nprec_max = std::max(nprec_max, np_);
+    }
+  }
+  p.nstop = nstop;
+
+  // ---------------- epilogue ----------------
+  ExtOut eo;
+  {
+    double *q = h->out_dev;
+    auto take = [&](size_t ncols) { double *r = q; q += (size_t)ld * ncols; return r; };
+    double **cols[] = {&eo.cltot, &eo.cllow, &eo.clmed, &eo.clhgh, &eo.precc, &eo.precl, &eo.precsc, &eo.precsl, &eo.jt_crm, &eo.mx_crm,
+                       &eo.prectend, &eo.precstend, &eo.taux, &eo.tauy, &eo.z0m, &eo.timing_factor};
+    for (double **c : cols) *c = take(1);
+    double **levs[] = {&eo.cldtop, &eo.qc_mean, &eo.qi_mean, &eo.qs_mean, &eo.qg_mean, &eo.qr_mean, &eo.sltend, &eo.qltend, &eo.qcltend,
+                       &eo.qiltend, &eo.cld, &eo.gicewp, &eo.gliqwp, &eo.mctot, &eo.mcup, &eo.mcdn, &eo.mcuup, &eo.mcudn, &eo.mu_crm, &eo.md_crm,
+                       &eo.du_crm, &eo.eu_crm, &eo.ed_crm, &eo.flux_qt, &eo.fluxsgs_qt, &eo.tkez, &eo.tkesgsz, &eo.tkz, &eo.flux_u, &eo.flux_v,
+                       &eo.flux_qp, &eo.precflux, &eo.qt_ls, &eo.qt_trans, &eo.qp_trans, &eo.qp_fall, &eo.qp_src, &eo.qp_evp, &eo.t_ls};
+    for (double **c : levs) *c = take(plev);
+    eo.prec_crm = take((size_t)nx * d->ny);
+  }
+  LAUNCH(h, k_epi_sums, ntiles * nzm, P, red_bytes(CRM_NESUM), p, h->esum);
+  LAUNCH(h, k_epi_precip, ntiles, P, red_bytes(4), p, eo, dt);
+  LAUNCH(h, k_epi_profiles, (ncrms + 127) / 128, 128, 0, p, ei, eo, (const double *)h->esum, dt, dtn);
+  if (dev_sync()) return fail(h, 31, std::string("crm_b200_run: kernel failure: ") + dev_errstr());
+  h->stats.ms_kernels = tk.stop();
+
+  // ---------------- boundary outputs ----------------
+  tm.start();
+  long long d2h = 0;
+  auto give = [&](double *dst, const double *src, size_t ncols) {
+    if (!dst) return;
+    copy_rows(dst, ld, src, ld, ncrms, ncols);
+    if (!is_dev_ptr(dst)) d2h += (long long)ncrms * ncols * 8;
+  };
+  {
+    double *hc[] = {out->cltot, out->cllow, out->clmed, out->clhgh, out->precc, out->precl, out->precsc, out->precsl, out->jt_crm, out->mx_crm,
+                    out->prectend, out->precstend, out->taux, out->tauy, out->z0m, out->timing_factor};
+    double *dc[] = {eo.cltot, eo.cllow, eo.clmed, eo.clhgh, eo.precc, eo.precl, eo.precsc, eo.precsl, eo.jt_crm, eo.mx_crm,
+                    eo.prectend, eo.precstend, eo.taux, eo.tauy, eo.z0m, eo.timing_factor};
+    for (int q = 0; q < 16; q++) give(hc[q], dc[q], 1);
+    double *hl[] = {out->cldtop, out->qc_mean, out->qi_mean, out->qs_mean, out->qg_mean, out->qr_mean, out->sltend, out->qltend, out->qcltend,
+                    out->qiltend, out->cld, out->gicewp, out->gliqwp, out->mctot, out->mcup, out->mcdn, out->mcuup, out->mcudn, out->mu_crm,
+                    out->md_crm, out->du_crm, out->eu_crm, out->ed_crm, out->flux_qt, out->fluxsgs_qt, out->tkez, out->tkesgsz, out->tkz,
+                    out->flux_u, out->flux_v, out->flux_qp, out->precflux, out->qt_ls, out->qt_trans, out->qp_trans, out->qp_fall, out->qp_src,
+                    out->qp_evp, out->t_ls};
+    double *dl[] = {eo.cldtop, eo.qc_mean, eo.qi_mean, eo.qs_mean, eo.qg_mean, eo.qr_mean, eo.sltend, eo.qltend, eo.qcltend,
+                    eo.qiltend, eo.cld, eo.gicewp, eo.gliqwp, eo.mctot, eo.mcup, eo.mcdn, eo.mcuup, eo.mcudn, eo.mu_crm,
+                    eo.md_crm, eo.du_crm, eo.eu_crm, eo.ed_crm, eo.flux_qt, eo.fluxsgs_qt, eo.tkez, eo.tkesgsz, eo.tkz,
+                    eo.flux_u, eo.flux_v, eo.flux_qp, eo.precflux, eo.qt_ls, eo.qt_trans, eo.qp_trans, eo.qp_fall, eo.qp_src,
+                    eo.qp_evp, eo.t_ls};
+    for (int q = 0; q < 39; q++) give(hl[q], dl[q], plev);
+    give(out->prec_crm, eo.prec_crm, (size_t)nx * d->ny);
+  }
+  auto store3 = [&](double *dst, const double *src, double scale) {
+    if (!dst) return;
+    if (is_dev_ptr(dst)) {
+      LAUNCH(h, k_int_to_ext, ntiles * nzm, P, 0, p, src, h->tstride, P, nx, nzm, dst, ld, scale);
+    } else {
+      LAUNCH(h, k_int_to_ext, ntiles * nzm, P, 0, p, src, h->tstride, P, nx, nzm, h->stage, ld, scale);
+      copy_rows(dst, ld, h->stage, ld, ncrms, ncols3);
+      d2h += (long long)ncrms * ncols3 * 8;
+    }
+  };
+  store3(st->u_wind, h->ubuf[iu], 1.0);
+  store3(st->v_wind, h->ubuf[iu], 0.0);   // 2-D: v == 0 (crm_module.F90:390, YES3D = 0)
+  store3(st->w_wind, h->wbuf[iu], 1.0);
+  store3(st->temperature, p.tabs, 1.0);
+  store3(st->qt, p.qt, 1.0); store3(st->qp, p.qp, 1.0); store3(st->qn, p.qn, 1.0);
+  store3(out->tk, p.tk, 1.0); store3(out->tkh, p.tkh, 1.0);
+  store3(out->qcl, p.qcl, 1.0); store3(out->qci, p.qci, 1.0); store3(out->qpl, p.qpl, 1.0); store3(out->qpi, p.qpi, 1.0);
+  {
+    const double tmp1 = ((double)d->nx_rad / (double)nx) * ((double)d->ny_rad / (double)d->ny) / (double)nstop;
+    const size_t ncr = (size_t)d->nx_rad * d->ny_rad * nzm;
+    double *dsts[] = {rad->temperature, rad->qv, rad->qc, rad->qi, rad->cld};
+    const double *srcs[] = {p.rad_t, p.rad_qv, p.rad_qc, p.rad_qi, p.rad_cld};
+    for (int q = 0; q < 5; q++) {
+      if (!dsts[q]) continue;
+      if (is_dev_ptr(dsts[q])) LAUNCH(h, k_epi_rad, ntiles * nzm, d->nx_rad * CT, 0, p, srcs[q], dsts[q], ld, tmp1);
+      else {
+        LAUNCH(h, k_epi_rad, ntiles * nzm, d->nx_rad * CT, 0, p, srcs[q], h->stage, ld, tmp1);
+        copy_rows(dsts[q], ld, h->stage, ld, ncrms, ncr);
+        d2h += (long long)ncrms * ncr * 8;
+      }
+    }
+  }
+  if (dev_sync()) return fail(h, 32, std::string("crm_b200_run: output transfer failed: ") + dev_errstr());
+  h->stats.ms_d2h = tm.stop();
+  h->stats.d2h_bytes = d2h;
+  h->stats.nstop = nstop; h->stats.ncycle_sum = ncycle_sum; h->stats.ncycle_max = ncycle_max; h->stats.nprec_max = nprec_max;
+  h->stats.kernel_launches = h->launches;
+  h->stats.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+  h->last_nb_u = inb;
+  // keep the role pointers of the final state for crm_b200_debug_fetch
+  p.u = h->ubuf[iu]; p.w = h->wbuf[iu]; p.du_a = h->ubuf[ina]; p.dw_a = h->wbuf[ina]; p.du_b = h->ubuf[inb]; p.dw_b = h->wbuf[inb];
+  p.du_c = h->ubuf[inc]; p.dw_c = h->wbuf[inc];
+  return 0;
+}
+
+extern "C" long long crm_b200_debug_fetch(void *handle, const char *name, double *host_buf, size_t n) {
+  if (!handle) return -1;
+  Handle *h = (Handle *)handle;
+  CrmP &p = h->p;
+  std::string nm(name);
+  const double *src = nullptr;
+  int nk = p.nzm;
+  if (nm == "u") src = p.u; else if (nm == "w") { src = p.w; nk = p.nz; } else if (nm == "t") src = p.t; else if (nm == "qt") src = p.qt;
+  else if (nm == "qp") src = p.qp; else if (nm == "qn") src = p.qn; else if (nm == "tabs") src = p.tabs; else if (nm == "qv") src = p.qv;
+  else if (nm == "qcl") src = p.qcl; else if (nm == "qci") src = p.qci; else if (nm == "qpl") src = p.qpl; else if (nm == "qpi") src = p.qpi;
+  else if (nm == "tk") src = p.tk; else if (nm == "tkh") src = p.tkh; else if (nm == "tke") src = p.tke;
+  else if (nm == "dudt") src = p.du_b; else if (nm == "dwdt") { src = p.dw_b; nk = p.nz; }
+  else if (nm == "dudt_a") src = p.du_a; else if (nm == "dwdt_a") { src = p.dw_a; nk = p.nz; }
+  else if (nm == "dudt_c") src = p.du_c; else if (nm == "dwdt_c") { src = p.dw_c; nk = p.nz; }
+  else if (nm == "umf") src = p.umf; else if (nm == "wmf") { src = p.wmf; nk = p.nz; }
+  else return -3;
+  const size_t need = (size_t)p.ncrms * p.nx * p.ny * nk;
+  if (n < need) return -2;
+  if (nk > p.nzm) {   // staging buffer holds nzm levels only: fetch level by level through a small temporary
+    std::vector<double> tmp((size_t)h->field_elems);
+    dev_copy2d(tmp.data(), tmp.size() * 8, src, tmp.size() * 8, (size_t)p.ntiles * h->tstride * 8, 1, 0);
+    for (int k = 0; k < nk; k++)
+      for (int i = 0; i < p.nx; i++)
+        for (int ic = 0; ic < p.ncrms; ic++) {
+          int tile = ic / p.CT, lane = ic % p.CT;
+          host_buf[(size_t)ic + (size_t)p.ncrms * ((size_t)i + (size_t)p.nx * k)] = tmp[(size_t)tile * h->tstride + (size_t)k * p.P + i * p.CT + lane];
+        }
+    return (long long)need;
+  }
+  LAUNCH(h, k_int_to_ext, p.ntiles * nk, p.P, 0, p, src, h->tstride, p.P, p.nx, nk, h->stage, p.ncrms, 1.0);
+  if (dev_sync()) return -4;
+  dev_copy2d(host_buf, need * 8, h->stage, need * 8, need * 8, 1, 0);
+  return (long long)need;
+}

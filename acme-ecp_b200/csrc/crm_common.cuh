@@ -1,0 +1,198 @@
+// crm_common.cuh -- layout, parameter block and block-level primitives of the B200 CRM kernels.
+//
+// Data layout in HBM: AoSoA with a tile of CT CRMs innermost,
+//     field(tile, k, i, lane)  at  tile*tstride + (k-1)*P + i*CT + lane,      P = nx*CT, tstride = nz*P
+// so the thread index of a block (tid = i*CT + lane) is the in-plane offset, every warp access is a
+// contiguous 256-byte segment, x-neighbours are tid +- CT (periodic wrap = index arithmetic, the reference's
+// 17 bound_exchange calls per sub-step disappear) and vertical neighbours are +-P.
+// One thread block owns one tile (CT CRMs x all i) and marches in k, so slab reductions over x are block
+// reductions in a fixed order (deterministic, no floating-point atomics).
+// Profiles (per CRM and level) live at  (tile*nzp + k)*CT + lane  with 1-based k (nzp = nz+1).
+#pragma once
+#ifdef CRM_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#define CRM_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define CRM_DYN_SMEM(type, name) \
+  extern __shared__ __align__(16) unsigned char name##_raw_[]; \
+  type *name = reinterpret_cast<type *>(name##_raw_)
+#endif
+#include <math.h>
+
+// REAL(4) literal promoted to double, as in the reference build without -r8
+#define R4(x) ((double)(x##f))
+
+namespace crm {
+
+// ---- physical constants (CRM/params.F90:49-69 via shr_const_mod.F90:22-54) ----
+#define CRM_CP      1.00464e3
+#define CRM_GGR     9.80616
+#define CRM_LCOND   2.501e6
+#define CRM_LFUS    3.337e5
+#define CRM_LSUB    (CRM_LCOND + CRM_LFUS)
+#define CRM_RGAS    ((6.02214e26 * 1.38065e-23) / 28.966)
+#define CRM_RV      ((6.02214e26 * 1.38065e-23) / 18.016)
+#define CRM_FAC_COND (CRM_LCOND / CRM_CP)
+#define CRM_FAC_FUS  (CRM_LFUS / CRM_CP)
+#define CRM_FAC_SUB  (CRM_LSUB / CRM_CP)
+#define CRM_EPSV    R4(0.61)
+#define CRM_PI      R4(3.141592653589793)
+// micro_params.F90:12-65
+#define CRM_TBGMIN R4(253.16)
+#define CRM_TBGMAX R4(273.16)
+#define CRM_TPRMIN R4(268.16)
+#define CRM_TPRMAX R4(283.16)
+#define CRM_TGRMIN R4(223.16)
+#define CRM_TGRMAX R4(283.16)
+#define CRM_QCW0 R4(1.e-3)
+#define CRM_QCI0 R4(1.e-4)
+#define CRM_ALPHAELQ R4(1.e-3)
+#define CRM_BETAELQ R4(1.e-3)
+#define CRM_QP_THRESHOLD R4(1.e-8)
+
+struct MicroScalars {   // host-computed once (precip_init.F90:23-43, microphysics.F90:172-174,507-512)
+  double gams1, gams2, gamg1, gamg2, gamr1, gamr2;   // REAL*4 gamma values promoted
+  double a_bg, a_pr, a_gr;
+  double vrain, vsnow, vgrau, crain, csnow, cgrau;
+};
+
+// Parameter block passed by value to every kernel.
+struct CrmP {
+  // geometry
+  int ncrms, ntiles, CT, nx, ny, nzm, nz, nzp, plev, nx_rad, ny_rad, P, ld;
+  long long tstride;
+  double dx, dy, dt, dt_gl;
+  // per-sub-step scalars
+  double dtn, at, bt, ct, dt3na;
+  int nstep, icycle, ncycle, last_substep, nstop, igstep;
+  int use_accel, accel_uv; double accel_factor;
+  MicroScalars ms;
+  // ---- 3-D fields, internal layout, nz levels each ----
+  double *u, *w;                         // current velocities
+  double *du_a, *du_b, *du_c;            // dudt(na,nb,nc)  (du_c receives the new u in adams)
+  double *dw_a, *dw_b, *dw_c;
+  double *umf, *wmf;                     // half-step mass-flux velocities (adams.F90:28-34)
+  double *t, *qt, *qp, *qn, *tabs, *qv, *qcl, *qci, *qpl, *qpi, *tk, *tkh, *tke;
+  double *pbeta, *palfa;                 // tridiagonal scratch (pressure.F90:202-237)
+  double *wp;                            // precipitation fall speed scratch (microphysics.F90:619)
+  double *qrad;                          // (tile, k, i_rad, lane)
+  double *rad_t, *rad_qv, *rad_qc, *rad_qi, *rad_cld;   // accumulators, same layout as qrad
+  // ---- profiles (tile, k, lane) ----
+  double *z, *zi, *pres, *presi, *adz, *adzw, *rho, *rhow, *bet, *gamaz, *grdf_x, *grdf_z, *pdel, *tau;
+  double *t0, *q0, *qv0, *tabs0, *u0, *qn0, *qp0, *t00;
+  double *ttend, *qtend, *utend;
+  double *tl, *ql, *qccl, *qiil, *uln;   // GCM profiles on CRM levels
+  double *accrsc, *accrsi, *accrrc, *coefice, *accrgc, *accrgi, *evaps1, *evaps2, *evapr1, *evapr2, *evapg1, *evapg2;
+  double *precflux, *qpfall, *qpsrc, *qpevp, *uwle, *uwsb;
+  double *mkwle1, *mkwle2, *mkwsb1, *mkwsb2, *mkadv1, *mkadv2, *mkdiff1, *mkdiff2;
+  double *acc_t, *acc_q, *acc_u;        // MSA tendencies
+  // statistics accumulators (tile, k, lane), CRM level indexed
+  double *s_cld, *s_cldtop, *s_gicewp, *s_gliqwp, *s_mcup, *s_mcdn, *s_mcuup, *s_mcudn, *s_mui, *s_mdi;
+  // ---- per-CRM scalars (tile, lane) ----
+  double *dz, *z0, *colprec0, *colprecs0, *s_cltot, *s_clhgh, *s_clmed, *s_cllow;
+  int *kmin, *kmax, *ndamp;
+  // ---- per-column 2-D (tile, tid) ----
+  double *precsfc, *precssfc;
+  // ---- batch-global scalars on device ----
+  unsigned long long *cfl_bits, *prec_cfl_bits;
+  int *flags;                            // [0] = velocity-clamp flag, [1] = MSA ceaseflag
+  // ---- FFT twiddles: cos/sin(2*pi*m/nx), m = 0..nx-1 ----
+  double *twc, *tws;
+};
+
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+__device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
+__device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
+__device__ __forceinline__ double pp_(double y) { return dmax(0., y); }
+__device__ __forceinline__ double pn_(double y) { return -dmin(0., y); }
+
+// ---- sat.F90 (Flatau et al. polynomials with REAL(4) coefficients) ----
+__device__ __forceinline__ double poly8(double a0, double a1, double a2, double a3, double a4, double a5, double a6, double a7,
+                                        double a8, double dt) {
+  return a0 + dt * (a1 + dt * (a2 + dt * (a3 + dt * (a4 + dt * (a5 + dt * (a6 + dt * (a7 + a8 * dt)))))));
+}
+__device__ inline double esatw_crm(double t) {   // sat.F90:12-32
+  double dt = t - R4(273.16);
+  if (dt > R4(-80.))
+    return poly8(R4(6.105851), R4(0.4440316), R4(0.1430341e-1), R4(0.2641412e-3), R4(0.2995057e-5), R4(0.2031998e-7),
+                 R4(0.6936113e-10), R4(0.2564861e-13), R4(-0.3704404e-15), dt);
+  return (double)(2.0f * 0.01f) * exp(R4(9.550426) - R4(5723.265) / t + R4(3.53068) * log(t) - R4(0.00728332) * t);
+}
+__device__ inline double esati_crm(double t) {   // sat.F90:77-94
+  double dt = t - R4(273.16);
+  if (dt > R4(-80.))
+    return poly8(R4(6.11147274), R4(0.503160820), R4(0.188439774e-1), R4(0.420895665e-3), R4(0.615021634e-5),
+                 R4(0.602588177e-7), R4(0.385852041e-9), R4(0.146898966e-11), R4(0.252751365e-14), dt);
+  return R4(0.01) * exp(R4(9.550426) - R4(5723.265) / t + R4(3.53068) * log(t) - R4(0.00728332) * t);
+}
+__device__ inline double dtesatw_crm(double t) {   // sat.F90:46-65
+  double dt = t - R4(273.16);
+  if (dt > R4(-80.))
+    return poly8(R4(0.443956472), R4(0.285976452e-1), R4(0.794747212e-3), R4(0.121167162e-4), R4(0.103167413e-6),
+                 R4(0.385208005e-9), R4(-0.604119582e-12), R4(-0.792933209e-14), R4(-0.599634321e-17), dt);
+  return esatw_crm(t + 1) - esatw_crm(t);
+}
+__device__ inline double dtesati_crm(double t) {   // sat.F90:108-127
+  double dt = t - R4(273.16);
+  if (dt > R4(-80.))
+    return poly8(R4(0.503223089), R4(0.377174432e-1), R4(0.126710138e-2), R4(0.249065913e-4), R4(0.312668753e-6),
+                 R4(0.255653718e-8), R4(0.132073448e-10), R4(0.390204672e-13), R4(0.497275778e-16), dt);
+  return esati_crm(t + R4(1.)) - esati_crm(t);
+}
+__device__ __forceinline__ double qsatw_crm(double t, double p) { double es = esatw_crm(t); return R4(0.622) * es / dmax(es, p - es); }
+__device__ __forceinline__ double qsati_crm(double t, double p) { double es = esati_crm(t); return R4(0.622) * es / dmax(es, p - es); }
+__device__ __forceinline__ double dtqsatw_crm(double t, double p) { return R4(0.622) * dtesatw_crm(t) / p; }
+__device__ __forceinline__ double dtqsati_crm(double t, double p) { return R4(0.622) * dtesati_crm(t) / p; }
+
+// ---------------------------------------------------------------------------------------------------
+// Block reductions over x for each lane (NQ <= 16).  `red` is shared memory of CRM_RED_DOUBLES(NQ,P,CT) doubles.
+// Order: 8 consecutive i summed ascending, then the nx/8 partials ascending (fixed => deterministic).
+// All threads must call; on return v[q] holds the slab sum for the caller's lane.
+// ---------------------------------------------------------------------------------------------------
+template <int NQ>
+__device__ __forceinline__ void block_sum(double (&v)[NQ], int tid, int P, int CT, double *red) {
+  const int i = tid / CT, lane = tid - i * CT, M = P / CT, G = M / 8;
+  // r3 sits at a fixed place so that back-to-back calls with different NQ never alias a result still being read
+  double *r3 = red, *r1 = red + 16 * CT, *r2 = r1 + NQ * P;
+#pragma unroll
+  for (int q = 0; q < NQ; q++) r1[q * P + tid] = v[q];
+  __syncthreads();
+  if ((i & 7) == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+      double s = r1[q * P + tid];
+      for (int d = 1; d < 8; d++) s += r1[q * P + tid + d * CT];
+      r2[(q * G + (i >> 3)) * CT + lane] = s;
+    }
+  }
+  __syncthreads();
+  if (i == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+      double s = r2[(q * G) * CT + lane];
+      for (int g = 1; g < G; g++) s += r2[(q * G + g) * CT + lane];
+      r3[q * CT + lane] = s;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NQ; q++) v[q] = r3[q * CT + lane];
+}
+#define CRM_RED_DOUBLES(NQ, P, CT) (16 * (CT) + (NQ) * ((P) + (P) / 8))
+
+// max over the whole block (all lanes); result returned to every thread.  red: >= P doubles.
+__device__ __forceinline__ double block_max_all(double v, int tid, int P, double *red) {
+  red[tid] = v;
+  __syncthreads();
+  for (int s = P >> 1; s > 0; s >>= 1) {
+    if (tid < s) red[tid] = dmax(red[tid], red[tid + s]);
+    __syncthreads();
+  }
+  double r = red[0];
+  __syncthreads();
+  return r;
+}
+
+}  // namespace crm

@@ -1,0 +1,482 @@
+// crm_k_dyn.cuh -- dynamical-core kernels of one CRM sub-step (2-D), fused by phase:
+//   k_p1_forcing   zero + buoyancy + forcing + rad heating + damping + ice_fall
+//   k_p2_sgs       shear_prod2D + tke_full (Smagorinsky)
+//   k_p3_mom       advect2_mom_xy + advect2_mom_z + diffuse_mom2D
+//   k_p4_press_fwd press_rhs + forward x-DFT + forward tridiagonal sweep
+//   k_p5_press_bwd back substitution + inverse x-DFT + press_grad + adams (+ mass-flux velocities)
+// One block per tile of CT CRMs (all x), marching in k.  No halos: periodic wrap is index arithmetic.
+#pragma once
+#include "crm_k_setup.cuh"
+
+namespace crm {
+
+#define CRM_XNEIGH                                                    \
+  const int tm1 = (i == 0) ? tid + P - CT : tid - CT;                 \
+  const int tp1 = (i == p.nx - 1) ? tid - P + CT : tid + CT;          \
+  (void)tm1; (void)tp1;
+
+// ice_fall.F90:82-116: limited sedimentation flux of cloud ice at level kk (1..nz)
+__device__ __forceinline__ double ice_flux(const CrmP &p, long long fb, int P, int tid, int pb, int CT, int kk, int kmin, int kmax, double dz) {
+  if (kk < imax(1, kmin - 1) || kk > kmax) return 0.;
+  const int nzm = p.nzm;
+  int kc = imin(nzm, kk + 1), kb = imax(1, kk - 1);
+  double coef = p.dtn / (0.5 * (PF(p.adz, kb) + PF(p.adz, kk)) * dz);
+  double qiu = PF(p.rho, kc) * F3(p.qci, kc);
+  double qic = PF(p.rho, kk) * F3(p.qci, kk);
+  double qid = PF(p.rho, kb) * F3(p.qci, kb);
+  double vt_ice = dmin(R4(0.4), R4(8.66) * pow(dmax(0., qic) + R4(1.e-10), R4(0.24)));
+  double tmp_phi;
+  if (fabs(qic - qid) < R4(1.0e-25)) tmp_phi = 0.;
+  else {
+    double tmp_theta = (qiu - qic) / (qic - qid);
+    tmp_phi = dmax(0., dmin(dmin(0.5 * (1. + tmp_theta), 2.), 2. * tmp_theta));
+  }
+  return -vt_ice * (qic - 0.5 * (1. - coef * vt_ice) * tmp_phi * (qic - qid));
+}
+
+// zero.F90, buoyancy.F90:17-36, forcing.F90:38-73, crm_module.F90:766-777, damping.F90:60-110, ice_fall.F90:34-165
+// smem: CRM_RED_DOUBLES(3,P,CT) + 1 int
+__global__ void __launch_bounds__(512) k_p1_forcing(CrmP p) {
+  CRM_TILE_SETUP
+  CRM_DYN_SMEM(double, red);
+  __shared__ int s_kd0;
+  const int nzm = p.nzm, nz = p.nz;
+  const double dz = p.dz[cb], dtn = p.dtn;
+  const int ndamp = p.ndamp[cb], kmin = p.kmin[cb], kmax = p.kmax[cb];
+  if (tid == 0) s_kd0 = nzm;
+  __syncthreads();
+  if (i == 0) atomicMin(&s_kd0, nzm - ndamp);
+  __syncthreads();
+  const int kd0 = s_kd0;   // lowest level at which any CRM of the tile is in the sponge
+  const int nxy = p.nx * p.ny;
+  const int irad = i / (p.nx / p.nx_rad);
+  const long long rb = ((long long)tile * nzm) * (p.nx_rad * CT) + irad * CT + lane;
+  double expr_km1 = 0.;
+  double fz_k = ice_flux(p, fb, P, tid, pb, CT, 1, kmin, kmax, dz);
+  for (int k = 1; k <= nzm; k++) {
+    const double tabs = F3(p.tabs, k), qv = F3(p.qv, k), qcl = F3(p.qcl, k), qci = F3(p.qci, k), qpl = F3(p.qpl, k), qpi = F3(p.qpi, k);
+    const double tabs0 = PF(p.tabs0, k), qv0 = PF(p.qv0, k), qn0 = PF(p.qn0, k), qp0 = PF(p.qp0, k);
+    // --- buoyancy
+    const double expr_k = tabs0 * (CRM_EPSV * (qv - qv0) - (qcl + qci - qn0 + qpl + qpi - qp0)) + (tabs - tabs0) * (1. + CRM_EPSV * qv0 - qn0 - qp0);
+    double dw = 0.;
+    if (k >= 2) {
+      double adzk = PF(p.adz, k), adzb = PF(p.adz, k - 1);
+      double betu = adzb / (adzk + adzb), betd = adzk / (adzk + adzb);
+      dw = dw + PF(p.bet, k) * betu * expr_k + PF(p.bet, k - 1) * betd * expr_km1;
+    }
+    expr_km1 = expr_k;
+    // --- forcing
+    double t = F3(p.t, k) + PF(p.ttend, k) * dtn;
+    double qt = F3(p.qt, k) + PF(p.qtend, k) * dtn;
+    {
+      double v[3];
+      v[0] = (qt < 0.) ? 1. : 0.; v[1] = (qt < 0.) ? qt : 0.; v[2] = (qt < 0.) ? 0. : qt;
+      block_sum<3>(v, tid, P, CT, red);
+      if (v[0] > 0. && v[2] + v[1] > 0.) {
+        double factor = 1. + v[1] / v[2];
+        qt = dmax(0., qt * factor);
+      }
+    }
+    double du = 0. + PF(p.utend, k);
+    // --- radiative heating
+    t = t + p.qrad[rb + (long long)(k - 1) * (p.nx_rad * CT)] * dtn;
+    // --- damping
+    if (k >= kd0) {
+      const double u = F3(p.u, k);
+      double v[2] = {u / nxy, t / nxy};
+      block_sum<2>(v, tid, P, CT, red);
+      if (k >= nzm - ndamp) {
+        const double tau = PF(p.tau, k);
+        du = du - (u - v[0]) * tau;
+        dw = dw - F3(p.w, k) * tau;
+        t = t - dtn * (t - v[1]) * tau;
+        qt = qt - dtn * (qv - qv0) * tau;
+      }
+    }
+    // --- ice fall
+    const double fz_kp1 = ice_flux(p, fb, P, tid, pb, CT, k + 1, kmin, kmax, dz);
+    if (k >= imax(1, kmin - 2) && k <= kmax) {
+      double coef = dtn / (dz * PF(p.adz, k) * PF(p.rho, k));
+      double dqi = coef * (fz_k - fz_kp1);
+      qt = qt + dqi;
+      double lat_heat = (CRM_FAC_COND + CRM_FAC_FUS) * dqi;
+      t = t - lat_heat;
+    }
+    if (k == 1) {
+      double coef = dtn / dz;
+      double dqi = -coef * fz_k;
+      const long long c2 = (long long)tile * P + tid;
+      p.precsfc[c2] += dqi;
+      p.precssfc[c2] += dqi;
+    }
+    fz_k = fz_kp1;
+    F3(p.t, k) = t; F3(p.qt, k) = qt; F3(p.du_a, k) = du; F3(p.dw_a, k) = dw;
+  }
+  F3(p.dw_a, nz) = 0.;
+}
+
+// shear_prod2D.F90:20-94 (v == 0 in 2-D) + tke_full.F90:103-310 with dosmagor.  tk/tkh written for k <= nzm-1.
+__global__ void __launch_bounds__(512) k_p2_sgs(CrmP p) {
+  CRM_TILE_SETUP
+  CRM_XNEIGH
+  const int nzm = p.nzm;
+  const double dz = p.dz[cb], dx = p.dx, rdx0 = 1. / dx, dt = p.dt;
+  const double Cs = R4(0.15), Ck = R4(0.1);
+  const double Ce = Ck * Ck * Ck / (Cs * Cs * Cs * Cs);
+  const double Pr = 1.;
+  const double Ce1 = Ce / R4(0.7) * R4(0.19), Ce2 = Ce / R4(0.7) * R4(0.51);
+  double bsv_km1 = 0.;   // buoy_sgs_vert(k-1); (0) = 0
+  for (int k = 1; k <= nzm - 1; k++) {
+    const int kc = k + 1, kb = k - 1;
+    // ---- def2
+    double def2;
+    {
+      const double rdz = 1. / (dz * PF(p.adz, k));
+      const double rdx = rdx0 * sqrt(dx * rdz);
+      const double u_i = F3(p.u, k), u_ic = F3X(p.u, k, tp1);
+      const double w_k = F3(p.w, k), w_kc = F3(p.w, kc);
+      const double u0k = PF(p.u0, k);
+      const double a1 = (u_ic - u_i) * rdx, a2 = (w_kc - w_k) * rdz;
+      double d = 2. * (a1 * a1 + a2 * a2);
+      // up terms (exist for k <= nzm-1, always here)
+      const double rdzw_up = 1. / (dz * PF(p.adzw, kc));
+      const double rdx_up = rdx0 * sqrt(dx * rdzw_up);
+      const double u0kc = PF(p.u0, kc);
+      const double up1 = (F3X(p.u, kc, tp1) - u0kc - u_ic + u0k) * rdzw_up + (F3X(p.w, kc, tp1) - w_kc) * rdx_up;
+      const double up2 = (F3(p.u, kc) - u0kc - u_i + u0k) * rdzw_up + (w_kc - F3X(p.w, kc, tm1)) * rdx_up;
+      if (k >= 2) {
+        const double rdzw_dn = 1. / (dz * PF(p.adzw, k));
+        const double rdx_dn = rdx0 * sqrt(dx * rdzw_dn);
+        const double u0kb = PF(p.u0, kb);
+        const double dn1 = (u_ic - u0k - F3X(p.u, kb, tp1) + u0kb) * rdzw_dn + (F3X(p.w, k, tp1) - w_k) * rdx_dn;
+        const double dn2 = (u_i - u0k - F3(p.u, kb) + u0kb) * rdzw_dn + (w_k - F3X(p.w, k, tm1)) * rdx_dn;
+        // v-terms of shear_prod2D.F90:36-51 are identically zero in 2-D (v = v0 = 0)
+        d = d + 0.5 * (0. + 0. + up1 * up1 + up2 * up2 + dn1 * dn1 + dn2 * dn2 + 0. + 0.);
+      } else {
+        d = d + 0.5 * (0. + 0.) + 0. + 0.5 * (up1 * up1 + up2 * up2);
+      }
+      def2 = d;
+    }
+    // ---- SGS buoyancy flux at the interface above level k (tke_full.F90:134-218)
+    double buoy_sgs;
+    {
+      const double tabs_c = F3(p.tabs, kc), tabs_b = F3(p.tabs, k);
+      const double qcl_c = F3(p.qcl, kc), qcl_b = F3(p.qcl, k), qci_c = F3(p.qci, kc), qci_b = F3(p.qci, k);
+      const double qv_c = F3(p.qv, kc), qv_b = F3(p.qv, k);
+      const double qpl_c = F3(p.qpl, kc), qpl_b = F3(p.qpl, k), qpi_c = F3(p.qpi, kc), qpi_b = F3(p.qpi, k);
+      const double t_c = F3(p.t, kc), t_b = F3(p.t, k);
+      const double betdz = 0.5 * (PF(p.bet, kc) + PF(p.bet, k)) / dz / PF(p.adzw, k + 1);
+      double tabs_interface = 0.5 * (tabs_c + CRM_FAC_COND * qcl_c + CRM_FAC_SUB * qci_c + tabs_b + CRM_FAC_COND * qcl_b + CRM_FAC_SUB * qci_b);
+      double qtot_interface = 0.5 * (qv_c + qcl_c + qci_c + qv_b + qcl_b + qci_b);
+      double qp_interface = 0.5 * (qpl_c + qpi_c + qpl_b + qpi_b);
+      double bbb = 1. + CRM_EPSV * qtot_interface - qp_interface;
+      buoy_sgs = betdz * (bbb * (t_c - t_b) + CRM_EPSV * tabs_interface * (qv_c + qcl_c + qci_c - qv_b - qcl_b - qci_b) +
+                          (bbb * CRM_FAC_COND - tabs_interface) * (qpl_c - qpl_b) + (bbb * CRM_FAC_SUB - tabs_interface) * (qpi_c - qpi_b));
+      const double qctot = qcl_c + qci_c + qcl_b + qci_b;
+      if (qctot > 0.) {
+        const double omn = (qcl_c + qcl_b) / (qctot + R4(1.e-20));
+        const double presi = PF(p.presi, k + 1);
+        const double qsat_check = omn * qsatw_crm(tabs_interface, presi) + (1. - omn) * qsati_crm(tabs_interface, presi);
+        if (qtot_interface > qsat_check) {
+          const double lstarn = CRM_FAC_COND + (1. - omn) * CRM_FAC_FUS;
+          tabs_interface = 0.5 * (tabs_c + tabs_b);
+          const double dqsat = omn * dtqsatw_crm(tabs_interface, presi) + (1. - omn) * dtqsati_crm(tabs_interface, presi);
+          const double qsatt = omn * qsatw_crm(tabs_interface, presi) + (1. - omn) * qsati_crm(tabs_interface, presi);
+          bbb = 1. + CRM_EPSV * qsatt + qsatt - qtot_interface - qp_interface + R4(1.61) * tabs_interface * dqsat;
+          bbb = bbb / (1. + lstarn * dqsat);
+          buoy_sgs = betdz * (bbb * (t_c - t_b) +
+                              (bbb * lstarn - (1. + lstarn * dqsat) * tabs_interface) * (qv_c + qcl_c + qci_c - qv_b - qcl_b - qci_b) +
+                              (bbb * CRM_FAC_COND - (1. + CRM_FAC_COND * dqsat) * tabs_b) * (qpl_c - qpl_b) +
+                              (bbb * CRM_FAC_SUB - (1. + CRM_FAC_SUB * dqsat) * tabs_b) * (qpi_c - qpi_b));
+        }
+      }
+    }
+    const double bsv_k = buoy_sgs;
+    // ---- eddy viscosity (tke_full.F90:250-304)
+    {
+      const double grd = dz * PF(p.adz, k);
+      const double cx = dx * dx / dt / PF(p.grdf_x, k);
+      const double cy = p.dy * p.dy / dt / PF(p.grdf_x, k);   // grdf_y == grdf_x (dy = dx)
+      const double dzm = dz * dmin(PF(p.adzw, k), PF(p.adzw, k + 1));
+      const double cz = dzm * dzm / dt / PF(p.grdf_z, k);
+      const double tkmax = R4(0.09) / (1. / cx + 1. / cy + 1. / cz);
+      const double bs = 0.5 * (bsv_km1 + bsv_k);
+      double smix;
+      if (bs <= 0.) smix = grd;
+      else smix = dmin(grd, dmax(R4(0.1) * grd, sqrt(R4(0.76) * F3(p.tk, k) / Ck / sqrt(bs + R4(1.e-10)))));
+      const double ratio = smix / grd;
+      const double Cee = Ce1 + Ce2 * ratio;
+      double tk = sqrt(Ck * Ck * Ck / Cee * dmax(0., def2 - Pr * bs)) * (smix * smix);
+      const double r = tk / (Ck * smix);
+      F3(p.tke, k) = r * r;
+      tk = dmin(tk, tkmax);
+      F3(p.tk, k) = tk;
+      F3(p.tkh, k) = Pr * tk;
+    }
+    bsv_km1 = bsv_k;
+  }
+}
+
+// advect2_mom_xy.F90:64-82, advect2_mom_z.F90:31-125, diffuse_mom2D.F90:38-158 (v == 0, fluxb* = fluxt* = 0).
+// smem: CRM_RED_DOUBLES(2,P,CT) (only used on the last sub-step for uwle/uwsb)
+__global__ void __launch_bounds__(512) k_p3_mom(CrmP p) {
+  CRM_TILE_SETUP
+  CRM_XNEIGH
+  CRM_DYN_SMEM(double, red);
+  const int nzm = p.nzm, nz = p.nz;
+  const double dz = p.dz[cb], dx = p.dx;
+  const double dx25 = 0.25 / dx, dz25 = 1. / (4. * dz);
+  const double rdx2 = 1. / dx / dx, rdx25 = 0.25 * rdx2;
+  const double rdz = 1. / dz, dzx = dz / dx;
+  // vertical fluxes at the lower face of the current level (k), carried from the previous iteration
+  double fuz_k = 0., fwz_km1 = 0., fuv_k = 0. /* fu(.,1) = fluxbu*... = 0 */, fwv_k = 0.;
+  // horizontal contributions to dwdt(k) computed while visiting level k-1
+  double dwh_adv = 0., dwh_dif = 0.;
+  for (int k = 1; k <= nzm; k++) {
+    const int kc = k + 1, kcu = imin(kc, nzm);
+    const double u_i = F3(p.u, k), u_im = F3X(p.u, k, tm1), u_ip = F3X(p.u, k, tp1);
+    const double w_k = F3(p.w, k), w_kc = F3(p.w, kc);
+    const double w_kc_m = F3X(p.w, kc, tm1), w_kc_p = F3X(p.w, kc, tp1);
+    const double rho_k = PF(p.rho, k), adz_k = PF(p.adz, k);
+    double du = F3(p.du_a, k);
+    // ---- advect2_mom_xy (2-D branch)
+    {
+      double fu1 = dx25 * (u_i + u_im) * (u_im + u_i);
+      double fu2 = dx25 * (u_ip + u_i) * (u_i + u_ip);
+      du = du - (fu2 - fu1);
+    }
+    // contribution to dwdt(kc) from this level (applied next iteration, in reference order)
+    double dwh_adv_next, dwh_dif_next;
+    {
+      const double irho = 1. / (PF(p.rhow, kc) * PF(p.adzw, kc));
+      const double rho_u = PF(p.rho, kcu), adz_u = PF(p.adz, kcu);
+      const double ucu_i = F3(p.u, kcu), ucu_ip = F3X(p.u, kcu, tp1);
+      double fw1 = dx25 * (u_i * rho_k * adz_k + ucu_i * rho_u * adz_u) * (w_kc_m + w_kc);
+      double fw2 = dx25 * (u_ip * rho_k * adz_k + ucu_ip * rho_u * adz_u) * (w_kc + w_kc_p);
+      dwh_adv_next = irho * (fw2 - fw1);
+      // diffuse_mom2D horizontal part: fw(i,k), fw(i-1,k)
+      const double dxz = dx / (dz * PF(p.adzw, kc));
+      const double rdx251 = rdx25 * PF(p.grdf_x, k);
+      const double tk_i = F3(p.tk, k), tk_ip = F3X(p.tk, k, tp1), tk_im = F3X(p.tk, k, tm1);
+      const double tku_i = F3(p.tk, kcu), tku_ip = F3X(p.tk, kcu, tp1), tku_im = F3X(p.tk, kcu, tm1);
+      double tkx = rdx251 * (tk_i + tk_ip + tku_i + tku_ip);
+      double fwi = -tkx * (w_kc_p - w_kc + (ucu_ip - u_ip) * dxz);
+      tkx = rdx251 * (tk_im + tk_i + tku_im + tku_i);
+      double fwm = -tkx * (w_kc - w_kc_m + (ucu_i - u_i) * dxz);
+      dwh_dif_next = fwi - fwm;
+    }
+    // ---- advect2_mom_z
+    double fuz_kc = 0.;
+    if (kc <= nzm) {
+      const double rhoi = dz25 * PF(p.rhow, kc);
+      const double www = rhoi * (w_kc + w_kc_m);
+      fuz_kc = www * (F3(p.u, kc) + u_i);
+    }
+    const double rhoi_s = 1. / (rho_k * adz_k);
+    du = du - (fuz_kc - fuz_k) * rhoi_s;
+    const double fwz_k = dz25 * (w_kc * PF(p.rhow, kc) + w_k * PF(p.rhow, k)) * (w_kc + w_k);
+    // ---- diffuse_mom2D: horizontal part for u
+    const double tk_i = F3(p.tk, k), tk_im = F3X(p.tk, k, tm1);
+    {
+      const double rdx21 = rdx2 * PF(p.grdf_x, k);
+      double fui = -2. * (rdx21 * tk_i) * (u_ip - u_i);
+      double fum = -2. * (rdx21 * tk_im) * (u_i - u_im);
+      du = du - (fui - fum);
+    }
+    // ---- diffuse_mom2D: vertical part
+    double fuv_kc = 0., fwv_kc;
+    if (k <= nzm - 1) {
+      const double rdz2 = rdz * rdz * PF(p.grdf_z, k), rdz25 = 0.25 * rdz2;
+      const double iadz = 1. / adz_k, iadzw = 1. / PF(p.adzw, kc);
+      double tkz = rdz2 * tk_i;
+      fwv_kc = -2. * tkz * (w_kc - w_k) * rho_k * iadz;
+      tkz = rdz25 * (tk_i + tk_im + F3(p.tk, kc) + F3X(p.tk, kc, tm1));
+      fuv_kc = -tkz * ((F3(p.u, kc) - u_i) * iadzw + (w_kc - w_kc_m) * dzx) * PF(p.rhow, kc);
+    } else {   // k == nzm: fw(.,nz) (diffuse_mom2D.F90:119-123); fu(.,nz) = fluxtu*... = 0
+      const double rdz2 = rdz * rdz * PF(p.grdf_z, nzm - 1);
+      double tkz = rdz2 * PF(p.grdf_z, nzm) * tk_i;
+      fwv_kc = -2. * tkz * (w_kc - w_k) / adz_k * rho_k;
+    }
+    du = du - (fuv_kc - fuv_k) * rhoi_s;
+    F3(p.du_a, k) = du;
+    // ---- dwdt(k), k >= 2, contributions in reference order: xy-advection, z-advection, horizontal diffusion, vertical diffusion
+    if (k >= 2) {
+      double dw = F3(p.dw_a, k);
+      dw = dw - dwh_adv;
+      const double rhoi_w = 1. / (PF(p.rhow, k) * PF(p.adzw, k));
+      dw = dw - (fwz_k - fwz_km1) * rhoi_w;
+      dw = dw - dwh_dif;
+      dw = dw - (fwv_kc - fwv_k) * rhoi_w;
+      F3(p.dw_a, k) = dw;
+    }
+    if (p.last_substep) {   // uwle(k) (advect2_mom_z.F90:76-109), uwsb(k) (diffuse_mom2D.F90:97-130)
+      double v[2] = {fuz_k, fuv_k};
+      block_sum<2>(v, tid, P, CT, red);
+      if (i == 0) { PF(p.uwle, k) = v[0]; PF(p.uwsb, k) = v[1]; }
+    }
+    fuz_k = fuz_kc; fwz_km1 = fwz_k; fuv_k = fuv_kc; fwv_k = fwv_kc;
+    dwh_adv = dwh_adv_next; dwh_dif = dwh_dif_next;
+  }
+  (void)nz;
+}
+
+// pressure.F90:165-237 coefficients for one (CRM, level)
+__device__ __forceinline__ void tri_ac(const CrmP &p, int pb, int CT, int k, double dz, double &a, double &c) {
+  const double adz = PF(p.adz, k);
+  a = PF(p.rhow, k) / (adz * PF(p.adzw, k) * dz * dz);
+  c = PF(p.rhow, k + 1) / (adz * PF(p.adzw, k + 1) * dz * dz);
+}
+// mode owned by thread column i: slots hold (a0, a_{n/2}, a1, b1, a2, b2, ...)   [b0 = b_{n/2} = 0 are not stored]
+__device__ __forceinline__ int mode_of(int i, int nx) { return (i == 1) ? nx / 2 : i / 2; }
+
+// alfa(k) of the Thomas algorithm depends only on the grid: computed once per crm() call (pressure.F90:217-231)
+__global__ void __launch_bounds__(512) k_press_alfa(CrmP p) {
+  CRM_TILE_SETUP
+  const int nzm = p.nzm, m = mode_of(i, p.nx);
+  const double dz = p.dz[cb];
+  const double ddx2 = 1. / (p.dx * p.dx);
+  const double pii = 3.14159265358979323846;
+  const double xnx = pii / p.nx;
+  const double eign = (2. * cos(2. * xnx * (double)m) - 2.) * ddx2;   // + (2cos(0)-2)*ddy2 = 0 in 2-D
+  double a, c;
+  tri_ac(p, pb, CT, 1, dz, a, c);
+  double b = (m == 0) ? 1. / (eign * PF(p.rho, 1) - a - c) : 1. / (eign * PF(p.rho, 1) - c);
+  double alfa = -c * b;
+  F3(p.palfa, 1) = alfa;
+  for (int k = 2; k <= nzm - 1; k++) {
+    tri_ac(p, pb, CT, k, dz, a, c);
+    double e = 1. / (eign * PF(p.rho, k) - a - c + a * alfa);
+    alfa = -c * e;
+    F3(p.palfa, k) = alfa;
+  }
+}
+
+// press_rhs.F90:80-102 + forward transform (fft.F90:49-53 convention) + forward sweep (pressure.F90:202-233).
+// The transform is a direct length-nx DFT per (CRM, level) in shared memory.
+// smem: P + 2*nx doubles
+__global__ void __launch_bounds__(512) k_p4_press_fwd(CrmP p) {
+  CRM_TILE_SETUP
+  CRM_XNEIGH
+  CRM_DYN_SMEM(double, sm);
+  double *sx = sm, *sc = sm + P, *ss = sc + p.nx;
+  const int nzm = p.nzm, nx = p.nx, m = mode_of(i, nx);
+  for (int q = tid; q < nx; q += P) { sc[q] = p.twc[q]; ss[q] = p.tws[q]; }
+  const double dz = p.dz[cb];
+  const double rdx = 1. / p.dx, btat = p.bt / p.at, ctat = p.ct / p.at;
+  const double dta = 1. / p.dt3na / p.at;
+  const double ddx2 = 1. / (p.dx * p.dx);
+  const double pii = 3.14159265358979323846;
+  const double eign = (2. * cos(2. * (pii / nx) * (double)m) - 2.) * ddx2;
+  const double scale = 1.0 / (double)nx;
+  const bool is_sin = (i & 1) && (i != 1);
+  double alfa_km1 = 0., beta_km1 = 0.;
+  for (int k = 1; k <= nzm; k++) {
+    const int kc = k + 1;
+    const double rho = PF(p.rho, k);
+    const double rdzz = 1. / (PF(p.adz, k) * dz);
+    const double rup = PF(p.rhow, kc) / rho * rdzz, rdn = PF(p.rhow, k) / rho * rdzz;
+    double rhs = (rdx * (F3X(p.u, k, tp1) - F3(p.u, k)) + (F3(p.w, kc) * rup - F3(p.w, k) * rdn)) * dta +
+                 (rdx * (F3X(p.du_a, k, tp1) - F3(p.du_a, k)) + (F3(p.dw_a, kc) * rup - F3(p.dw_a, k) * rdn)) +
+                 btat * (rdx * (F3X(p.du_b, k, tp1) - F3(p.du_b, k)) + (F3(p.dw_b, kc) * rup - F3(p.dw_b, k) * rdn)) +
+                 ctat * (rdx * (F3X(p.du_c, k, tp1) - F3(p.du_c, k)) + (F3(p.dw_c, kc) * rup - F3(p.dw_c, k) * rdn));
+    rhs = rhs * rho;
+    __syncthreads();   // previous iteration's reads of sx are complete
+    sx[tid] = rhs;
+    __syncthreads();
+    // forward DFT: a_m = (1/n) sum_j x_j cos(2 pi j m/n),  b_m = -(1/n) sum_j x_j sin(2 pi j m/n)
+    double acc = 0.;
+    int idx = 0;
+    if (is_sin) {
+      for (int j = 0; j < nx; j++) { acc += sx[j * CT + lane] * ss[idx]; idx += m; if (idx >= nx) idx -= nx; }
+      acc = -scale * acc;
+    } else {
+      for (int j = 0; j < nx; j++) { acc += sx[j * CT + lane] * sc[idx]; idx += m; if (idx >= nx) idx -= nx; }
+      acc = scale * acc;
+    }
+    const double ff = acc;
+    // forward elimination for this thread's mode
+    double a, c;
+    tri_ac(p, pb, CT, k, dz, a, c);
+    if (k == 1) {
+      double b = (m == 0) ? 1. / (eign * rho - a - c) : 1. / (eign * rho - c);
+      alfa_km1 = -c * b;
+      beta_km1 = ff * b;
+      F3(p.pbeta, 1) = beta_km1;
+    } else if (k <= nzm - 1) {
+      double e = 1. / (eign * rho - a - c + a * alfa_km1);
+      alfa_km1 = -c * e;
+      beta_km1 = (ff - a * beta_km1) * e;
+      F3(p.pbeta, k) = beta_km1;
+    } else {
+      F3(p.pbeta, k) = (ff - a * beta_km1) / (eign * rho - a + a * alfa_km1);   // solution at nzm
+    }
+  }
+}
+
+// pressure.F90:234-305 (back substitution, inverse transform) + press_grad.F90:20-35 + adams.F90:19-38.
+// Marches downward; w(k+1) is finalised when p(k) is known.  smem: 2*P + 2*nx doubles
+__global__ void __launch_bounds__(512) k_p5_press_bwd(CrmP p) {
+  CRM_TILE_SETUP
+  CRM_XNEIGH
+  CRM_DYN_SMEM(double, sm);
+  double *sX = sm, *sp = sm + P, *sc = sp + P, *ss = sc + p.nx;
+  const int nzm = p.nzm, nx = p.nx;
+  for (int q = tid; q < nx; q += P) { sc[q] = p.twc[q]; ss[q] = p.tws[q]; }
+  const double dz = p.dz[cb];
+  const double rdx = 1. / p.dx;
+  const double dtdx = p.dtn / p.dx, dtdz = p.dtn / dz;
+  const double at = p.at, bt = p.bt, ct = p.ct, dt3na = p.dt3na;
+  double ff_kp1 = 0., p_kp1 = 0.;
+  for (int k = nzm; k >= 1; k--) {
+    double ffk = (k == nzm) ? F3(p.pbeta, k) : F3(p.palfa, k) * ff_kp1 + F3(p.pbeta, k);
+    ff_kp1 = ffk;
+    __syncthreads();
+    sX[tid] = ffk;
+    __syncthreads();
+    // inverse: x_j = a0 + a_{n/2} (-1)^j + 2 sum_{m=1}^{n/2-1} (a_m cos(2 pi j m/n) - b_m sin(2 pi j m/n)), j = i
+    double x = sX[lane] + ((i & 1) ? -sX[CT + lane] : sX[CT + lane]);
+    {
+      int idx = 0;
+      double acc = 0.;
+      for (int m = 1; m < nx / 2; m++) {
+        idx += i; if (idx >= nx) idx -= nx;
+        acc += sX[(2 * m) * CT + lane] * sc[idx] - sX[(2 * m + 1) * CT + lane] * ss[idx];
+      }
+      x = x + 2. * acc;
+    }
+    const double pk = x;
+    sp[tid] = pk;
+    __syncthreads();
+    const double pk_m = sp[tm1];
+    // press_grad + adams for u at level k
+    {
+      double du = F3(p.du_a, k) - (pk - pk_m) * rdx;
+      F3(p.du_a, k) = du;
+      const double u = F3(p.u, k);
+      const double unew = u + dt3na * (at * du + bt * F3(p.du_b, k) + ct * F3(p.du_c, k));
+      F3(p.du_c, k) = unew;
+      F3(p.umf, k) = 0.5 * (u + unew) * (PF(p.rho, k) * dtdx);
+    }
+    // w at level k+1 (needs p(k+1) - p(k))
+    if (k + 1 <= nzm) {
+      const int kw = k + 1;
+      const double rdzw = 1. / (dz * PF(p.adzw, kw));
+      double dw = F3(p.dw_a, kw) - (p_kp1 - pk) * rdzw;
+      F3(p.dw_a, kw) = dw;
+      const double w = F3(p.w, kw);
+      const double wnew = w + dt3na * (at * dw + bt * F3(p.dw_b, kw) + ct * F3(p.dw_c, kw));
+      F3(p.dw_c, kw) = wnew;
+      F3(p.wmf, kw) = 0.5 * (w + wnew) * (PF(p.rhow, kw) * dtdz);
+    }
+    p_kp1 = pk;
+  }
+  {   // w at level 1: no pressure gradient (press_grad.F90:25, kb = max(1,k-1))
+    const double dw = F3(p.dw_a, 1);
+    const double w = F3(p.w, 1);
+    const double wnew = w + dt3na * (at * dw + bt * F3(p.dw_b, 1) + ct * F3(p.dw_c, 1));
+    F3(p.dw_c, 1) = wnew;
+    F3(p.wmf, 1) = 0.5 * (w + wnew) * (PF(p.rhow, 1) * dtdz);
+  }
+}
+
+}  // namespace crm

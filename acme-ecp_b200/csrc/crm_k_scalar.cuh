@@ -1,0 +1,573 @@
+// crm_k_scalar.cuh -- scalar kernels of one CRM sub-step (2-D):
+//   k_mpdata       advect_scalar2D (MPDATA + FCT) for one scalar, fully fused 3-level pipeline in shared memory
+//   k_precip_a/b   micro_precip_fall / precip_fall (terminal velocity + batch-global nprec; column march)
+//   k_p7_diffuse   diffuse_scalar2D for t, qt, qp
+//   k_p8_micro     cloud + precip_proc + micro_diagnose (+ diagnose when MSA is off); plane kernel
+//   k_msa_a/b      accelerate_crm
+#pragma once
+#include "crm_k_dyn.cuh"
+
+namespace crm {
+
+__device__ __forceinline__ double andiff(double x1, double x2, double a, double b) { return (fabs(a) - a * a * b) * 0.5 * (x2 - x1); }
+__device__ __forceinline__ double across(double x1, double a1, double a2) { return 0.03125 * a1 * a2 * x1; }
+__device__ __forceinline__ double max3(double a, double b, double c) { return dmax(dmax(a, b), c); }
+__device__ __forceinline__ double min3(double a, double b, double c) { return dmin(dmin(a, b), c); }
+
+// ADV_MPDATA/advect_scalar2D.F90:93-234 + advect_scalar.F90:55-72.
+// Pipeline per iteration ka (1..nzm+2):  A: upwind pass -> F1(ka);  B: antidiffusive velocities UU(ka-1), WW(ka),
+// FCT ratios mx/mn(ka-1);  C: limited fluxes and final update of level ka-2.  U = umf, W = wmf (mass-flux
+// velocities of adams).  fadv/flux: optional profile outputs (mkadv/mkwle), written only when `stats`.
+// smem: 9*P doubles (+ CRM_RED_DOUBLES(2,P,CT) when stats)
+__global__ void __launch_bounds__(512) k_mpdata(CrmP p, double *f, double *fadv, double *flux, int stats) {
+  CRM_TILE_SETUP
+  CRM_XNEIGH
+  CRM_DYN_SMEM(double, sm);
+  double *sF1 = sm, *sUU = sm + 3 * P, *smx = sm + 4 * P, *smn = sm + 6 * P, *sUL = sm + 8 * P, *red = sm + 9 * P;
+  const int nzm = p.nzm;
+  const double eps = R4(1.e-10);
+  const double *U = p.umf, *W = p.wmf;
+  // own-column windows
+  double f0mm = 0., f0m = 0., f0c = F3(f, 1), f0p = (nzm >= 2) ? F3(f, 2) : 0.;
+  double WW_prev = 0. /* WW(ka-1) */, UU_prev = 0. /* UU(ka-2) after shift */, WWlim_k = 0.;
+  double mx_prev = 0., mn_prev = 0.;   // normalised mx/mn at level ka-2 (own column)
+  double upw_m1 = 0., upw_m2 = 0.;     // upwind www at levels ka-1, ka-2 (stats only)
+  for (int ka = 1; ka <= nzm + 2; ka++) {
+    // ------------------------------- stage A: first (upwind) pass at level ka
+    double upw = 0.;
+    if (ka <= nzm) {
+      const double f_im = F3X(f, ka, tm1), f_ip = F3X(f, ka, tp1);
+      const double Ui = F3(U, ka), Uip = F3X(U, ka, tp1);
+      const double Wk = F3(W, ka);
+      const double uuu_i = dmax(0., Ui) * f_im + dmin(0., Ui) * f0c;
+      const double uuu_ip = dmax(0., Uip) * f0c + dmin(0., Uip) * f_ip;
+      const double fkb = (ka == 1) ? f0c : f0m;
+      const double www_k = dmax(0., Wk) * fkb + dmin(0., Wk) * f0c;
+      double www_kp = 0.;
+      if (ka < nzm) { const double Wp = F3(W, ka + 1); www_kp = dmax(0., Wp) * f0c + dmin(0., Wp) * f0p; }
+      const double irho = 1. / PF(p.rho, ka), iadz = 1. / PF(p.adz, ka);
+      sF1[(ka % 3) * P + tid] = f0c - (uuu_ip - uuu_i + (www_kp - www_k) * iadz) * irho;
+      upw = www_k;
+    }
+    __syncthreads();   // (1)
+    // ------------------------------- stage B
+    double WW_ka = 0.;
+    if (ka >= 2 && ka <= nzm) {   // WW(1) = 0 (advect_scalar2D.F90:165-169), WW(nz) = 0
+      const double *Fa = sF1 + (ka % 3) * P, *Fb = sF1 + ((ka - 1) % 3) * P;
+      const double Wk = F3(W, ka);
+      const double irho = 1. / PF(p.rho, ka), irhow = 1. / (PF(p.rhow, ka) * PF(p.adz, ka));
+      WW_ka = andiff(Fb[tid], Fa[tid], Wk, irhow) -
+              across(Fb[tp1] + Fa[tp1] - Fb[tm1] - Fa[tm1], Wk, F3(U, ka - 1) + F3(U, ka) + F3X(U, ka, tp1) + F3X(U, ka - 1, tp1)) * irho;
+    }
+    const int kb_ = ka - 1;
+    double UU = 0., mxr = 0., mnr = 0., F1c = 0.;
+    const bool vB = (kb_ >= 1 && kb_ <= nzm);
+    if (vB) {
+      const int kcc = imin(nzm, kb_ + 1), kbb = imax(1, kb_ - 1);
+      const double *Fc = sF1 + (kb_ % 3) * P, *Fu = sF1 + (kcc % 3) * P, *Fd = sF1 + (kbb % 3) * P;
+      const double irho = 1. / PF(p.rho, kb_);
+      const double dd = (double)(2.f / (float)(kcc - kbb)) / PF(p.adz, kb_);
+      const double Ui = F3(U, kb_);
+      F1c = Fc[tid];
+      const double F1m = Fc[tm1], F1p = Fc[tp1];
+      UU = andiff(F1m, F1c, Ui, irho) -
+           across(dd * (Fu[tm1] + Fu[tid] - Fd[tm1] - Fd[tid]), Ui, F3X(W, kb_, tm1) + F3X(W, kcc, tm1) + F3(W, kb_) + F3(W, kcc)) * irho;
+      // raw extrema over the 5-point stencils of the old and the first-pass field
+      const double g_im = F3X(f, kb_, tm1), g_ip = F3X(f, kb_, tp1);
+      const double g_kb = (kb_ == 1) ? f0m : f0mm, g_kc = (kb_ == nzm) ? f0m : f0c, g_c = f0m;
+      const double mx0 = dmax(dmax(dmax(dmax(g_im, g_ip), g_kb), g_kc), g_c);
+      const double mn0 = dmin(dmin(dmin(dmin(g_im, g_ip), g_kb), g_kc), g_c);
+      mxr = dmax(dmax(dmax(dmax(dmax(F1m, F1p), Fd[tid]), Fu[tid]), F1c), mx0);
+      mnr = dmin(dmin(dmin(dmin(dmin(F1m, F1p), Fd[tid]), Fu[tid]), F1c), mn0);
+      sUU[tid] = UU;
+    }
+    __syncthreads();   // (2)
+    double mx_new = 0., mn_new = 0.;
+    if (vB) {
+      const double UUp = sUU[tp1];
+      const double rho = PF(p.rho, kb_), iadz = 1. / PF(p.adz, kb_);
+      const double WWk = WW_prev;                                  // WW(kb_)
+      const double WWkc = (kb_ == nzm) ? WW_prev : WW_ka;           // WW(min(nzm,kb_+1))
+      mx_new = rho * (mxr - F1c) / (pn_(UUp) + pp_(UU) + iadz * (pn_(WWkc) + pp_(WWk)) + eps);
+      mn_new = rho * (F1c - mnr) / (pp_(UUp) + pn_(UU) + iadz * (pp_(WWkc) + pn_(WWk)) + eps);
+      smx[(kb_ & 1) * P + tid] = mx_new;
+      smn[(kb_ & 1) * P + tid] = mn_new;
+    }
+    __syncthreads();   // (3)
+    // ------------------------------- stage C: limited fluxes, final update of level kc_ = ka-2
+    const int kc_ = ka - 2;
+    const bool vC = (kc_ >= 1 && kc_ <= nzm);
+    // WW'(kb_): limited vertical flux at the lower face of level kb_ (needs mx/mn at kb_ and kb_-1)
+    double WWlim_kp1 = 0.;
+    if (vB && kb_ >= 2) {
+      const double WWl = WW_prev;
+      WWlim_kp1 = pp_(WWl) * dmin(dmin(1., mx_new), mn_prev) - pn_(WWl) * dmin(dmin(1., mx_prev), mn_new);
+    }
+    double ULim = 0.;
+    if (vC) {
+      const double mx_c = smx[(kc_ & 1) * P + tid], mx_m = smx[(kc_ & 1) * P + tm1];
+      const double mn_c = smn[(kc_ & 1) * P + tid], mn_m = smn[(kc_ & 1) * P + tm1];
+      ULim = pp_(UU_prev) * dmin(dmin(1., mx_c), mn_m) - pn_(UU_prev) * dmin(dmin(1., mx_m), mn_c);
+      sUL[tid] = ULim;
+    }
+    __syncthreads();   // (4)
+    if (vC) {
+      const double ULp = sUL[tp1];
+      const double irho = 1. / PF(p.rho, kc_), iadz = 1. / PF(p.adz, kc_);
+      const double F1k = sF1[(kc_ % 3) * P + tid];
+      const double fnew = dmax(0., F1k - (ULp - ULim + (WWlim_kp1 - WWlim_k) * iadz) * irho);
+      F3(f, kc_) = fnew;
+      if (stats) {
+        double v[2] = {fnew - f0mm, upw_m2 + WWlim_k};
+        block_sum<2>(v, tid, P, CT, red);
+        if (i == 0) { PF(fadv, kc_) = v[0]; PF(flux, kc_) = v[1]; }
+      }
+    }
+    // ------------------------------- shift windows
+    WWlim_k = WWlim_kp1;
+    UU_prev = UU;
+    WW_prev = WW_ka;
+    mx_prev = mx_new; mn_prev = mn_new;
+    upw_m2 = upw_m1; upw_m1 = upw;
+    f0mm = f0m; f0m = f0c; f0c = f0p;
+    f0p = (ka + 2 <= nzm) ? F3(f, ka + 2) : 0.;
+  }
+}
+
+// microphysics.F90:453-486
+__device__ __forceinline__ double term_vel_qp(const MicroScalars &m, double qploc, double rho, double tabs) {
+  double term_vel = 0.;
+  if (qploc > CRM_QP_THRESHOLD) {
+    const double omp = dmax(0., dmin(1., (tabs - CRM_TPRMIN) * m.a_pr));
+    if (omp == 1.) {
+      term_vel = m.vrain * pow(rho * qploc, m.crain);
+    } else if (omp == 0.) {
+      const double omg = dmax(0., dmin(1., (tabs - CRM_TGRMIN) * m.a_gr));
+      const double qgg = omg * qploc;
+      const double qss = qploc - qgg;
+      term_vel = (omg * m.vgrau * pow(rho * qgg, m.cgrau) + (1. - omg) * m.vsnow * pow(rho * qss, m.csnow));
+    } else {
+      const double omg = dmax(0., dmin(1., (tabs - CRM_TGRMIN) * m.a_gr));
+      const double qrr = omp * qploc;
+      double qss = qploc - qrr;
+      const double qgg = omg * qss;
+      qss = qss - qgg;
+      term_vel = (omp * m.vrain * pow(rho * qrr, m.crain) +
+                  (1. - omp) * (omg * m.vgrau * pow(rho * qgg, m.cgrau) + (1. - omg) * m.vsnow * pow(rho * qss, m.csnow)));
+    }
+  }
+  return term_vel;
+}
+
+// microphysics.F90:578-640: fall speed of every cell + batch-global prec_cfl.  smem: P doubles.
+__global__ void __launch_bounds__(512) k_precip_a(CrmP p) {
+  CRM_TILE_SETUP
+  CRM_DYN_SMEM(double, red);
+  const double dz = p.dz[cb];
+  double cfl = 0.;
+  for (int k = 1; k <= p.nzm; k++) {
+    const double rho = PF(p.rho, k);
+    const double rhofac = sqrt(R4(1.29) / rho);
+    const int kb = imax(1, k - 1);
+    const double wmax = dz * PF(p.adz, kb) / p.dtn;
+    const double iwmax = 1. / wmax;
+    const double tv = term_vel_qp(p.ms, F3(p.qp, k), rho, F3(p.tabs, k));
+    const double wpv = rhofac * tv;
+    cfl = dmax(cfl, wpv * iwmax);
+    F3(p.wp, k) = -wpv * PF(p.rhow, k) * p.dtn / dz;
+  }
+  const double m = block_max_all(cfl, tid, P, red);
+  if (tid == 0) atomicMax(p.prec_cfl_bits, (unsigned long long)__double_as_longlong(m));
+}
+
+// microphysics.F90:642-830: nprec sub-iterations of the 1-D MPDATA/FCT sedimentation, one thread per column with a
+// sliding register window (q, wp, tq 3 levels ahead of the level being finalised).
+// smem: CRM_RED_DOUBLES(2,P,CT)
+__global__ void __launch_bounds__(512) k_precip_b(CrmP p) {
+  CRM_TILE_SETUP
+  CRM_DYN_SMEM(double, red);
+  const int nzm = p.nzm;
+  const double eps = R4(1.e-10);
+  const double dz = p.dz[cb];
+  const double prec_cfl = __longlong_as_double((long long)*p.prec_cfl_bits);
+  int nprec = 1;
+  if (prec_cfl > R4(0.9)) nprec = (int)ceil(prec_cfl / R4(0.9));
+  const long long c2 = (long long)tile * P + tid;
+  for (int iprec = 1; iprec <= nprec; iprec++) {
+    const bool scale_wp = (iprec == 1 && nprec > 1);   // wp = wp/nprec (microphysics.F90:648-660); later iterations store scaled wp
+    // window variables, index s = level being loaded
+    double q0 = 0., q1 = 0., q2 = 0., q3 = 0.;          // q(s-3), q(s-2), q(s-1), q(s)
+    double w1 = 0., w2 = 0., w3 = 0.;                   // wp(s-2), wp(s-1), wp(s)
+    double fz2 = 0., fz3 = 0.;                          // fz(s-1), fz(s)
+    double tq0 = 0., tq1 = 0., tq2 = 0.;                // tq(s-3), tq(s-2), tq(s-1)
+    double ww1 = 0., ww2 = 0.;                          // www(s-2), www(s-1)
+    double mxn0 = 0., mnn0 = 0., mxn1 = 0., mnn1 = 0.;  // normalised at s-3, s-2
+    double fzl0 = 0., fzl1 = 0.;                        // limited flux at s-3, s-2
+    double om0 = 0., om1 = 0., om2 = 0., om3 = 0.;      // omega(s-3..s)
+    for (int s = 1; s <= nzm + 3; s++) {
+      // ---- load level s
+      q0 = q1; q1 = q2; q2 = q3; w1 = w2; w2 = w3; fz2 = fz3; om0 = om1; om1 = om2; om2 = om3;
+      if (s <= nzm) {
+        q3 = F3(p.qp, s);
+        w3 = F3(p.wp, s);
+        if (scale_wp) { w3 = w3 / (double)nprec; }
+        fz3 = q3 * w3;
+        om3 = dmax(0., dmin(1., (F3(p.tabs, s) - CRM_TPRMIN) * p.ms.a_pr));
+      } else { q3 = 0.; w3 = 0.; fz3 = 0.; om3 = 0.; }
+      // ---- tq(s-1)
+      tq0 = tq1; tq1 = tq2;
+      const int k1 = s - 1;
+      if (k1 >= 1 && k1 <= nzm) tq2 = q2 - (fz3 - fz2) / 1. * (1. / (PF(p.rho, k1) * PF(p.adz, k1)));
+      else tq2 = 0.;
+      // ---- www(s-1) = 0.5*(1+wp*irhoadz)*(tq(kb)*wp(kb) - tq(k)*wp(k)), kb = max(1,k-1)
+      ww1 = ww2;
+      if (k1 >= 2 && k1 <= nzm) {
+        const double irhoadz = 1. / (PF(p.rho, k1) * PF(p.adz, k1));
+        ww2 = 0.5 * (1. + w2 * irhoadz) * (tq1 * w1 - tq2 * w2);
+      } else ww2 = 0.;   // level 1: kb = k -> exactly 0; level nz: www(nz) = 0
+      // ---- normalised extrema at k2 = s-2
+      const int k2 = s - 2;
+      mxn0 = mxn1; mnn0 = mnn1;
+      if (k2 >= 1 && k2 <= nzm) {
+        // q and tq at kb=max(1,k2-1), kc=min(nzm,k2+1)
+        const double qb = (k2 == 1) ? q1 : q0, qc = (k2 == nzm) ? q1 : q2;
+        const double tb = (k2 == 1) ? tq1 : tq0, tc = (k2 == nzm) ? tq1 : tq2;
+        double mx = max3(qb, qc, q1), mn = min3(qb, qc, q1);
+        mx = dmax(max3(tb, tc, tq1), mx);
+        mn = dmin(min3(tb, tc, tq1), mn);
+        const double wwc = (k2 == nzm) ? ww1 : ww2;   // www(min(nzm,k2+1))
+        const double ra = PF(p.rho, k2) * PF(p.adz, k2);
+        mxn1 = ra * (mx - tq1) / (pn_(wwc) + pp_(ww1) + eps);
+        mnn1 = ra * (tq1 - mn) / (pp_(wwc) + pn_(ww1) + eps);
+      } else { mxn1 = 0.; mnn1 = 0.; }
+      // ---- limited flux at k2: fz(k2) + pp(www)*min(1,mx(k2),mn(kb)) - pn(www)*min(1,mx(kb),mn(k2))
+      fzl0 = fzl1;
+      if (k2 >= 1 && k2 <= nzm) {
+        const double mxb = (k2 == 1) ? mxn1 : mxn0, mnb = (k2 == 1) ? mnn1 : mnn0;
+        const double fzk2 = q1 * w1;
+        fzl1 = fzk2 + pp_(ww1) * dmin(dmin(1., mxn1), mnb) - pn_(ww1) * dmin(dmin(1., mxb), mnn1);
+      } else fzl1 = 0.;   // fz(nz) = 0
+      // ---- final update at k3 = s-3
+      const int k3 = s - 3;
+      if (k3 >= 1 && k3 <= nzm) {
+        const double irhoadz = 1. / (PF(p.rho, k3) * PF(p.adz, k3));
+        const double dq = -(fzl1 - fzl0) * irhoadz;
+        const double qnew = q0 - (fzl1 - fzl0) * irhoadz;
+        F3(p.qp, k3) = qnew;
+        const double lf0 = CRM_FAC_COND + (1 - om0) * CRM_FAC_FUS;
+        const double lf1 = (k3 + 1 <= nzm) ? CRM_FAC_COND + (1 - om1) * CRM_FAC_FUS : 0.;
+        const double lat_heat = -(lf1 * fzl1 - lf0 * fzl0) * irhoadz;
+        F3(p.t, k3) = F3(p.t, k3) - lat_heat;
+        if (k3 == 1) {
+          p.precsfc[c2] = p.precsfc[c2] - fzl0 * 1.;
+          p.precssfc[c2] = p.precssfc[c2] - fzl0 * (1. - om0) * 1.;
+        }
+        if (iprec < nprec) {   // new fall speed for the next iteration (microphysics.F90:794-817)
+          const double rho = PF(p.rho, k3);
+          const double tv = term_vel_qp(p.ms, qnew, rho, F3(p.tabs, k3));
+          const double wpv = sqrt(R4(1.29) / rho) * tv;
+          F3(p.wp, k3) = -wpv * PF(p.rhow, k3) * p.dtn / dz / (double)nprec;
+        }
+        double v[2] = {dq, fzl0};
+        block_sum<2>(v, tid, P, CT, red);
+        if (i == 0) { PF(p.qpfall, k3) = PF(p.qpfall, k3) + v[0]; PF(p.precflux, k3) = PF(p.precflux, k3) - v[1]; }
+      }
+    }
+  }
+}
+
+// diffuse_scalar2D.F90:70-138 + diffuse_scalar.F90:55-70 for t, qt, qp in one pass (fluxb = fluxt = 0).
+// smem: CRM_RED_DOUBLES(4,P,CT) (stats only)
+__global__ void __launch_bounds__(512) k_p7_diffuse(CrmP p) {
+  CRM_TILE_SETUP
+  CRM_XNEIGH
+  CRM_DYN_SMEM(double, red);
+  const int nzm = p.nzm;
+  const double dz = p.dz[cb];
+  const double rdx2 = 1. / (p.dx * p.dx);
+  const double rdz2 = 1. / (dz * dz);
+  double *fld[3] = {p.t, p.qt, p.qp};
+  double flz_km1[3] = {0., 0., 0.};   // flx(.,0) = fluxb*rdz*rhow(1) = 0
+  for (int k = 1; k <= nzm; k++) {
+    const double tkh_i = F3(p.tkh, k), tkh_m = F3X(p.tkh, k, tm1), tkh_p = F3X(p.tkh, k, tp1);
+    const double rdx5 = 0.5 * rdx2 * PF(p.grdf_x, k);
+    const double rhoi2 = 1. / (PF(p.adz, k) * PF(p.rho, k));
+    double tkz = 0., rhoi = 0.;
+    if (k <= nzm - 1) {
+      rhoi = PF(p.rhow, k + 1) / PF(p.adzw, k + 1);
+      const double rdz5 = 0.5 * rdz2 * PF(p.grdf_z, k);
+      tkz = rdz5 * (tkh_i + F3(p.tkh, k + 1));
+    }
+    double fnew[3], fold[3], flz[3];
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+      const double *f = fld[s];
+      const double f_i = F3(f, k), f_m = F3X(f, k, tm1), f_p = F3X(f, k, tp1);
+      const double flx_i = -(rdx5 * (tkh_i + tkh_p)) * (f_p - f_i);
+      const double flx_m = -(rdx5 * (tkh_m + tkh_i)) * (f_i - f_m);
+      double dfdt = 0. - (flx_i - flx_m);
+      flz[s] = (k <= nzm - 1) ? -tkz * (F3(f, k + 1) - f_i) * rhoi : 0.;
+      dfdt = p.dtn * (dfdt - (flz[s] - flz_km1[s]) * rhoi2);
+      fold[s] = f_i;
+      fnew[s] = f_i + dfdt;
+    }
+    __syncthreads();   // all neighbour reads of level k are done before anyone overwrites it
+#pragma unroll
+    for (int s = 0; s < 3; s++) fld[s][fb + (long long)(k - 1) * P + tid] = fnew[s];
+    if (p.last_substep) {   // mkdiff (fdiff) and mkwsb (flux at the lower face of level k) for qt, qp
+      double v[4] = {fnew[1] - fold[1], fnew[2] - fold[2], flz_km1[1], flz_km1[2]};
+      block_sum<4>(v, tid, P, CT, red);
+      if (i == 0) { PF(p.mkdiff1, k) = v[0]; PF(p.mkdiff2, k) = v[1]; PF(p.mkwsb1, k) = v[2]; PF(p.mkwsb2, k) = v[3]; }
+    }
+#pragma unroll
+    for (int s = 0; s < 3; s++) flz_km1[s] = flz[s];
+  }
+}
+
+// cloud.F90:29-112 for one cell; returns tabs1, updates q, qp, qn
+__device__ inline void cloud_cell(double t, double gamaz, double pres, double &q, double &qp, double &qn, double &tabs_out) {
+  const double an = 1. / (CRM_TBGMAX - CRM_TBGMIN), bn = CRM_TBGMIN * an;
+  const double ap = 1. / (CRM_TPRMAX - CRM_TPRMIN), bp = CRM_TPRMIN * ap;
+  const double fac1 = CRM_FAC_COND + (1 + bp) * CRM_FAC_FUS, fac2 = CRM_FAC_FUS * ap;
+  q = dmax(0., q);
+  const double tabs = t - gamaz;
+  double tabs1 = (tabs + fac1 * qp) / (1. + fac2 * qp);
+  double qsatt, dqsat = 0., dtabs = 0.;
+  if (tabs1 >= CRM_TBGMAX) {
+    tabs1 = tabs + CRM_FAC_COND * qp;
+    qsatt = qsatw_crm(tabs1, pres);
+  } else if (tabs1 <= CRM_TBGMIN) {
+    tabs1 = tabs + CRM_FAC_SUB * qp;
+    qsatt = qsati_crm(tabs1, pres);
+  } else {
+    const double om = an * tabs1 - bn;
+    qsatt = om * qsatw_crm(tabs1, pres) + (1. - om) * qsati_crm(tabs1, pres);
+  }
+  if (q > qsatt) {
+    int niter = 0;
+    dtabs = R4(100.);
+    while (fabs(dtabs) > R4(0.01) && niter < 10) {
+      double lstarn, dlstarn, lstarp, dlstarp;
+      if (tabs1 >= CRM_TBGMAX) {
+        lstarn = CRM_FAC_COND; dlstarn = 0.;
+        qsatt = qsatw_crm(tabs1, pres);
+        dqsat = dtqsatw_crm(tabs1, pres);
+      } else if (tabs1 <= CRM_TBGMIN) {
+        lstarn = CRM_FAC_SUB; dlstarn = 0.;
+        qsatt = qsati_crm(tabs1, pres);
+        dqsat = dtqsati_crm(tabs1, pres);
+      } else {
+        const double om = an * tabs1 - bn;
+        lstarn = CRM_FAC_COND + (1. - om) * CRM_FAC_FUS;
+        dlstarn = an * CRM_FAC_FUS;
+        qsatt = om * qsatw_crm(tabs1, pres) + (1. - om) * qsati_crm(tabs1, pres);
+        dqsat = om * dtqsatw_crm(tabs1, pres) + (1. - om) * dtqsati_crm(tabs1, pres);
+      }
+      if (tabs1 >= CRM_TPRMAX) { lstarp = CRM_FAC_COND; dlstarp = 0.; }
+      else if (tabs1 <= CRM_TPRMIN) { lstarp = CRM_FAC_SUB; dlstarp = 0.; }
+      else { const double omp = ap * tabs1 - bp; lstarp = CRM_FAC_COND + (1. - omp) * CRM_FAC_FUS; dlstarp = ap * CRM_FAC_FUS; }
+      const double fff = tabs - tabs1 + lstarn * (q - qsatt) + lstarp * qp;
+      const double dfff = dlstarn * (q - qsatt) + dlstarp * qp - lstarn * dqsat - 1.;
+      dtabs = -fff / dfff;
+      niter = niter + 1;
+      tabs1 = tabs1 + dtabs;
+    }
+    qsatt = qsatt + dqsat * dtabs;
+    qn = dmax(0., q - qsatt);
+  } else {
+    qn = 0.;
+  }
+  tabs_out = tabs1;
+  qp = dmax(0., qp);
+}
+
+// precip_proc.F90:47-148 for one cell.  dsrc/devp: this cell's contribution to qpsrc/qpevp.
+__device__ inline void precip_proc_cell(const CrmP &p, int pb, int CT, int k, double tabs, double pres, double &q, double &qp, double &qn,
+                                        double &dsrc, double &devp) {
+  const double b_rain = R4(0.8), b_snow = R4(0.25), b_grau = R4(0.5);
+  const double powr1 = (3 + b_rain) / 4., powr2 = (5 + b_rain) / 8.;
+  const double pows1 = (3 + b_snow) / 4., pows2 = (5 + b_snow) / 8.;
+  const double powg1 = (3 + b_grau) / 4., powg2 = (5 + b_grau) / 8.;
+  const double dtn = p.dtn;
+  dsrc = 0.; devp = 0.;
+  if (qn + qp > 0.) {
+    const double omn = dmax(0., dmin(1., (tabs - CRM_TBGMIN) * p.ms.a_bg));
+    const double omp = dmax(0., dmin(1., (tabs - CRM_TPRMIN) * p.ms.a_pr));
+    const double omg = dmax(0., dmin(1., (tabs - CRM_TGRMIN) * p.ms.a_gr));
+    if (qn > 0.) {
+      double qcc = qn * omn;
+      double qii = qn * (1. - omn);
+      const double autor = (qcc > CRM_QCW0) ? CRM_ALPHAELQ : 0.;
+      const double autos = (qii > CRM_QCI0) ? CRM_BETAELQ * PF(p.coefice, k) : 0.;
+      double accrr = 0.;
+      if (omp > R4(0.001)) {
+        const double qrr = qp * omp;
+        accrr = PF(p.accrrc, k) * pow(qrr, powr1);
+      }
+      double accrcs = 0., accris = 0.;
+      if (omp < R4(0.999) && omg < R4(0.999)) {
+        const double qss = qp * (1. - omp) * (1. - omg);
+        const double tmp = pow(qss, pows1);
+        accrcs = PF(p.accrsc, k) * tmp;
+        accris = PF(p.accrsi, k) * tmp;
+      }
+      double accrcg = 0., accrig = 0.;
+      if (omp < R4(0.999) && omg > R4(0.001)) {
+        const double qgg = qp * (1. - omp) * omg;
+        const double tmp = pow(qgg, powg1);
+        accrcg = PF(p.accrgc, k) * tmp;
+        accrig = PF(p.accrgi, k) * tmp;
+      }
+      qcc = (qcc + dtn * autor * CRM_QCW0) / (1. + dtn * (accrr + accrcs + accrcg + autor));
+      qii = (qii + dtn * autos * CRM_QCI0) / (1. + dtn * (accris + accrig + autos));
+      double dq = dtn * (accrr * qcc + autor * (qcc - CRM_QCW0) + (accris + accrig) * qii + (accrcs + accrcg) * qcc + autos * (qii - CRM_QCI0));
+      dq = dmin(dq, qn);
+      qp = qp + dq;
+      q = q - dq;
+      qn = qn - dq;
+      dsrc = dq;
+    } else if (qp > CRM_QP_THRESHOLD && qn == 0.) {
+      double qsatt = 0.;
+      if (omn > R4(0.001)) qsatt = qsatt + omn * qsatw_crm(tabs, pres);
+      if (omn < R4(0.999)) qsatt = qsatt + (1. - omn) * qsati_crm(tabs, pres);
+      double dq = 0.;
+      if (omp > R4(0.001)) {
+        const double qrr = qp * omp;
+        dq = dq + PF(p.evapr1, k) * sqrt(qrr) + PF(p.evapr2, k) * pow(qrr, powr2);
+      }
+      if (omp < R4(0.999) && omg < R4(0.999)) {
+        const double qss = qp * (1. - omp) * (1. - omg);
+        dq = dq + PF(p.evaps1, k) * sqrt(qss) + PF(p.evaps2, k) * pow(qss, pows2);
+      }
+      if (omp < R4(0.999) && omg > R4(0.001)) {
+        const double qgg = qp * (1. - omp) * omg;
+        dq = dq + PF(p.evapg1, k) * sqrt(qgg) + PF(p.evapg2, k) * pow(qgg, powg2);
+      }
+      dq = dq * dtn * (q / qsatt - 1.);
+      dq = dmax(-0.5 * qp, dq);
+      qp = qp + dq;
+      q = q - dq;
+      devp = dq;
+    } else {
+      q = q + qp;
+      devp = -qp;
+      qp = 0.;
+    }
+  }
+  const double dq = qp;
+  qp = dmax(0., qp);
+  q = q + (dq - qp);
+}
+
+// micro_proc (microphysics.F90:292-329: cloud, precip_proc, micro_diagnose) and, when do_diag, diagnose.F90:37-104
+// (tabs, slab means) + the kmin/kmax scan of ice_fall.F90:34-47 for the NEXT sub-step.
+// Plane kernel: one block per (tile, level).  smem: CRM_RED_DOUBLES(9,P,CT) + 2*CT ints
+__global__ void __launch_bounds__(512) k_p8_micro(CrmP p, int do_micro, int do_diag) {
+  const int tid = threadIdx.x, P = p.P, CT = p.CT;
+  const int tile = blockIdx.x / p.nzm, k = blockIdx.x - tile * p.nzm + 1;
+  const int i = tid / CT, lane = tid - i * CT;
+  const long long fb = (long long)tile * p.tstride;
+  const int pb = tile * p.nzp * CT + lane;
+  const int cb = tile * CT + lane;
+  CRM_DYN_SMEM(double, red);
+  int *sflag = (int *)(red + CRM_RED_DOUBLES(9, P, CT));
+  double t = F3(p.t, k), q = F3(p.qt, k), qp = F3(p.qp, k), qn = F3(p.qn, k), tabs = F3(p.tabs, k);
+  double qv = F3(p.qv, k), qcl = F3(p.qcl, k), qci = F3(p.qci, k), qpl = F3(p.qpl, k), qpi = F3(p.qpi, k);
+  double dsrc = 0., devp = 0.;
+  if (do_micro) {
+    const double pres = PF(p.pres, k);
+    cloud_cell(t, PF(p.gamaz, k), pres, q, qp, qn, tabs);
+    precip_proc_cell(p, pb, CT, k, tabs, pres, q, qp, qn, dsrc, devp);
+    micro_diag_cell(p.ms, q, qn, qp, tabs, qv, qcl, qci, qpl, qpi);
+    F3(p.qt, k) = q; F3(p.qp, k) = qp; F3(p.qn, k) = qn;
+    F3(p.qv, k) = qv; F3(p.qcl, k) = qcl; F3(p.qci, k) = qci; F3(p.qpl, k) = qpl; F3(p.qpi, k) = qpi;
+    if (!do_diag) F3(p.tabs, k) = tabs;
+  }
+  if (tid < 2 * CT) sflag[tid] = 0;
+  if (do_diag) {
+    tabs = t - PF(p.gamaz, k) + CRM_FAC_COND * (qcl + qpl) + CRM_FAC_SUB * (qci + qpi);
+    F3(p.tabs, k) = tabs;
+  }
+  double v[9];
+  v[0] = F3(p.u, k); v[1] = t; v[2] = tabs; v[3] = qv + qcl + qci; v[4] = qcl + qci; v[5] = qpl + qpi; v[6] = dsrc; v[7] = devp; v[8] = 0.;
+  block_sum<9>(v, tid, P, CT, red);   // (contains the barrier that orders the sflag reset)
+  if (do_diag) {
+    if (qcl + qci > 0. && tabs < R4(273.15)) sflag[lane] = 1;
+  }
+  if (i == 0) {
+    if (do_diag) {
+      const double coef = (double)1.f / (double)(p.nx * p.ny);
+      PF(p.u0, k) = v[0] * coef; PF(p.t0, k) = v[1] * coef; PF(p.tabs0, k) = v[2] * coef;
+      const double q0 = v[3] * coef, qn0 = v[4] * coef;
+      PF(p.q0, k) = q0; PF(p.qn0, k) = qn0; PF(p.qp0, k) = v[5] * coef;
+      PF(p.qv0, k) = q0 - qn0;
+    }
+    if (do_micro && p.last_substep) { PF(p.qpsrc, k) = v[6]; PF(p.qpevp, k) = v[7]; }
+  }
+  __syncthreads();
+  if (do_diag && i == 0 && sflag[lane]) { atomicMin(&p.kmin[cb], k); atomicMax(&p.kmax[cb], k); }
+}
+
+__global__ void k_reset_kminmax(CrmP p) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot < p.ntiles * p.CT) { p.kmin[slot] = p.nzm + 1; p.kmax[slot] = 0; }
+}
+
+// accelerate_crm.F90:166-225: horizontal means, MSA tendencies, batch-global ceaseflag.  Plane kernel.
+// smem: CRM_RED_DOUBLES(3,P,CT)
+__global__ void __launch_bounds__(512) k_msa_a(CrmP p) {
+  const int tid = threadIdx.x, P = p.P, CT = p.CT;
+  const int tile = blockIdx.x / p.nzm, k = blockIdx.x - tile * p.nzm + 1;
+  const int i = tid / CT, lane = tid - i * CT;
+  const long long fb = (long long)tile * p.tstride;
+  const int pb = tile * p.nzp * CT + lane;
+  CRM_DYN_SMEM(double, red);
+  const double coef = 1. / (double)(p.nx * p.ny);
+  double v[3] = {F3(p.t, k) * coef, (F3(p.qcl, k) + F3(p.qci, k) + F3(p.qv, k)) * coef, F3(p.u, k) * coef};
+  block_sum<3>(v, tid, P, CT, red);
+  if (i == 0) {
+    const double ta = v[0] - PF(p.t0, k);
+    PF(p.acc_t, k) = ta;
+    PF(p.acc_q, k) = v[1] - PF(p.q0, k);
+    PF(p.acc_u, k) = v[2] - PF(p.u0, k);
+    if (fabs(ta) > R4(5.) && tile * CT + lane < p.ncrms) atomicOr(&p.flags[1], 1);
+  }
+}
+
+// accelerate_crm.F90:250-352: apply the tendencies, fix negative moisture.  Plane kernel.  smem: CRM_RED_DOUBLES(2,P,CT)
+__global__ void __launch_bounds__(512) k_msa_b(CrmP p) {
+  const int tid = threadIdx.x, P = p.P, CT = p.CT;
+  const int tile = blockIdx.x / p.nzm, k = blockIdx.x - tile * p.nzm + 1;
+  const int i = tid / CT, lane = tid - i * CT;
+  const long long fb = (long long)tile * p.tstride;
+  const int pb = tile * p.nzp * CT + lane;
+  (void)i;
+  CRM_DYN_SMEM(double, red);
+  const double fac = p.accel_factor;
+  F3(p.t, k) = dmax(R4(50.), F3(p.t, k) + fac * PF(p.acc_t, k));
+  if (p.accel_uv) F3(p.u, k) = F3(p.u, k) + fac * PF(p.acc_u, k);
+  double qt = F3(p.qt, k) + fac * PF(p.acc_q, k);
+  double v[2] = {(qt < 0.) ? 0. : qt, (qt < 0.) ? qt : 0.};
+  block_sum<2>(v, tid, P, CT, red);
+  const double qpoz = v[0], qneg = v[1];
+  double qv = F3(p.qv, k), qcl = F3(p.qcl, k), qci = F3(p.qci, k);
+  if (qpoz + qneg <= 0.) {
+    qt = 0.; qv = 0.; qcl = 0.; qci = 0.;
+  } else {
+    double factor = 1. + qneg / qpoz;
+    qt = dmax(0., qt * factor);
+    if (qt <= 0.) { qv = 0.; qcl = 0.; qci = 0.; }
+    else {
+      const double qt_res = qt - qcl - qci;
+      qv = dmax(0., qt_res);
+      if (qt_res < 0.) {
+        factor = 1. + qt_res / (qcl + qci);
+        qcl = qcl * factor;
+        qci = qci * factor;
+      }
+    }
+  }
+  F3(p.qt, k) = qt; F3(p.qv, k) = qv; F3(p.qcl, k) = qcl; F3(p.qci, k) = qci;
+}
+
+}  // namespace crm

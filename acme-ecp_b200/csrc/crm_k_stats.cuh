@@ -1,0 +1,267 @@
+// crm_k_stats.cuh -- per-step statistics (crm_module.F90:896-1073) and the epilogue reductions / outputs
+// (crm_module.F90:1086-1594).  CF3D == 1 everywhere in the sam1mom/non-CLUBB build (vars.F90:456).
+#pragma once
+#include "crm_k_scalar.cuh"
+
+namespace crm {
+
+// Per-nstep statistics.  Block per tile; marches from the top (the reference's cwp scan uses kk = nz-k, and books
+// the cloud-top hit at GCM level l(k), i.e. at CRM level k = nz-kk: quirk kept).
+// smem: CRM_RED_DOUBLES(10,P,CT) + 5*P doubles
+__global__ void __launch_bounds__(512) k_stats(CrmP p) {
+  CRM_TILE_SETUP
+  CRM_DYN_SMEM(double, sm);
+  double *red = sm, *srad = sm + CRM_RED_DOUBLES(10, P, CT);
+  const int nzm = p.nzm, nz = p.nz;
+  const double dz = p.dz[cb];
+  const double cwp_threshold = R4(0.001), wmin = R4(2.);
+  const int grp = p.nx / p.nx_rad;
+  double cwp = 0., cwph = 0., cwpm = 0., cwpl = 0., cltemp = 0., cmtemp = 0., chtemp = 0., cttemp = 0.;
+  bool flag_top = true;
+  for (int kk = nzm; kk >= 1; kk--) {   // kk = nz-k of the reference's loop counter k
+    const int kmir = nz - kk;           // the loop counter k (1..nzm) at which level kk is scanned
+    const double qcl = F3(p.qcl, kk), qci = F3(p.qci, kk);
+    const double rho = PF(p.rho, kk), adz = PF(p.adz, kk), pres = PF(p.pres, kk);
+    double tmp1 = rho * adz * dz * (qcl + qci);
+    cwp = cwp + tmp1;
+    cttemp = dmax(1., cttemp);
+    double top_hit = 0.;
+    if (cwp > cwp_threshold && flag_top) { top_hit = 1.; flag_top = false; }
+    if (pres >= R4(700.)) { cwpl = cwpl + tmp1; cltemp = dmax(1., cltemp); }
+    else if (pres < R4(400.)) { cwph = cwph + tmp1; chtemp = dmax(1., chtemp); }
+    else { cwpm = cwpm + tmp1; cmtemp = dmax(1., cmtemp); }
+    // level-local part, evaluated for level kk (sums over levels are order independent across k)
+    tmp1 = rho * adz * dz;
+    const double w_k = F3(p.w, kk), w_kc = F3(p.w, kk + 1);
+    const double wsum = w_kc + w_k;
+    double cld = 0., mcup = 0., mcdn = 0., mcuup = 0., mcudn = 0.;
+    if (tmp1 * (qcl + qci) > cwp_threshold) {
+      cld = 1.;
+      if (wsum > 2 * wmin) { mcup = rho * 0.5 * wsum * 1.; mcuup = rho * 0.5 * wsum * (R4(1.0) - 1.); }
+      if (wsum < -2 * wmin) { mcdn = rho * 0.5 * wsum * 1.; mcudn = rho * 0.5 * wsum * (1. - 1.); }
+    } else {
+      if (wsum > 2 * wmin) mcuup = rho * 0.5 * wsum;
+      if (wsum < -2 * wmin) mcudn = rho * 0.5 * wsum;
+    }
+    // mass fluxes at the lower interface of level kk (w-level kk) (crm_module.F90:1019-1049)
+    double mui = 0., mdi = 0.;
+    if (w_k > 0.) {
+      const int kx = imax(1, kk - 1);
+      const double qsat = qsatw_crm(F3(p.tabs, kx), PF(p.pres, kx));
+      if (F3(p.qcl, kx) + F3(p.qci, kx) > dmin(R4(1.e-5), R4(0.01) * qsat)) mui = PF(p.rhow, kk) * w_k;
+    } else if (w_k < 0.) {
+      const int kx = imin(kk + 1, nzm);
+      const double qsat = qsatw_crm(F3(p.tabs, kx), PF(p.pres, kx));
+      if (F3(p.qcl, kx) + F3(p.qci, kx) > dmin(R4(1.e-5), R4(0.01) * qsat)) mdi = PF(p.rhow, kk) * w_k;
+      else if (F3(p.qpl, kx) + F3(p.qpi, kx) > R4(1.0e-4)) mdi = PF(p.rhow, kk) * w_k;
+    }
+    double v[10] = {cld, mcup, mcdn, mcuup, mcudn, qcl, qci, top_hit, mui, mdi};
+    block_sum<10>(v, tid, P, CT, red);
+    if (i == 0) {
+      PF(p.s_cld, kk) += v[0]; PF(p.s_mcup, kk) += v[1]; PF(p.s_mcdn, kk) += v[2]; PF(p.s_mcuup, kk) += v[3]; PF(p.s_mcudn, kk) += v[4];
+      PF(p.s_gliqwp, kk) += v[5]; PF(p.s_gicewp, kk) += v[6];
+      PF(p.s_cldtop, kmir) += v[7];
+      PF(p.s_mui, kk) += v[8]; PF(p.s_mdi, kk) += v[9];
+    }
+    // radiation-group accumulators (crm_module.F90:979-1015): groups of nx/nx_rad adjacent columns
+    const double tabs = F3(p.tabs, kk), qv = F3(p.qv, kk);
+    __syncthreads();
+    srad[tid] = tabs; srad[P + tid] = dmax(0., qv); srad[2 * P + tid] = qcl; srad[3 * P + tid] = qci;
+    srad[4 * P + tid] = (qcl + qci > 0) ? 1. : 0.;
+    __syncthreads();
+    if (i % grp == 0) {
+      const int ir = i / grp;
+      const long long ro = ((long long)tile * nzm + (kk - 1)) * (p.nx_rad * CT) + ir * CT + lane;
+      double a[5];
+      for (int q = 0; q < 5; q++) {
+        double s = srad[q * P + tid];
+        for (int d = 1; d < grp; d++) s += srad[q * P + tid + d * CT];
+        a[q] = s;
+      }
+      p.rad_t[ro] += a[0]; p.rad_qv[ro] += a[1]; p.rad_qc[ro] += a[2]; p.rad_qi[ro] += a[3]; p.rad_cld[ro] += a[4];
+    }
+  }
+  // w-level nz (k = nzm+1 of crm_module.F90:1023): w(nz) = 0 -> no contribution.
+  double v[4];
+  v[0] = (cwp > cwp_threshold) ? cttemp : 0.; v[1] = (cwph > cwp_threshold) ? chtemp : 0.;
+  v[2] = (cwpm > cwp_threshold) ? cmtemp : 0.; v[3] = (cwpl > cwp_threshold) ? cltemp : 0.;
+  block_sum<4>(v, tid, P, CT, red);
+  if (i == 0) { p.s_cltot[cb] += v[0]; p.s_clhgh[cb] += v[1]; p.s_clmed[cb] += v[2]; p.s_cllow[cb] += v[3]; }
+}
+
+// Epilogue slab sums (crm_module.F90:1147-1183, 1314-1356, 1517-1584).  Plane kernel; results in the scratch
+// profile block esum (14 profiles).  smem: CRM_RED_DOUBLES(14,P,CT)
+#define CRM_NESUM 14
+__global__ void __launch_bounds__(512) k_epi_sums(CrmP p, double *esum) {
+  const int tid = threadIdx.x, P = p.P, CT = p.CT;
+  const int tile = blockIdx.x / p.nzm, k = blockIdx.x - tile * p.nzm + 1;
+  const int i = tid / CT, lane = tid - i * CT;
+  const long long fb = (long long)tile * p.tstride;
+  const int pb = tile * p.nzp * CT + lane;
+  CRM_DYN_SMEM(double, red);
+  const double tabs = F3(p.tabs, k), qv = F3(p.qv, k), qcl = F3(p.qcl, k), qci = F3(p.qci, k), qpl = F3(p.qpl, k), qpi = F3(p.qpi, k);
+  const double u = F3(p.u, k), w_k = F3(p.w, k), w_kc = F3(p.w, k + 1);
+  const double pdel = PF(p.pdel, k), u0 = PF(p.u0, k);
+  const double omg = dmax(0., dmin(1., (tabs - CRM_TGRMIN) * p.ms.a_gr));
+  double v[CRM_NESUM];
+  v[0] = tabs; v[1] = qv; v[2] = qcl; v[3] = qci; v[4] = u;
+  v[5] = (qpl + qpi) * pdel; v[6] = qpi * pdel;
+  v[7] = qpl; v[8] = qpi * omg; v[9] = qpi * (1. - omg);
+  v[10] = (u - u0) * (u - u0); v[11] = 0.5 * (w_kc * w_kc + w_k * w_k);
+  v[12] = F3(p.tke, k); v[13] = F3(p.tk, k);
+  block_sum<CRM_NESUM>(v, tid, P, CT, red);
+  if (i == 0) {
+    const size_t np = (size_t)p.ntiles * p.nzp * CT;
+    for (int q = 0; q < CRM_NESUM; q++) esum[q * np + pb + k * CT] = v[q];
+  }
+}
+
+struct ExtOut {   // device staging of the (ld,plev) / (ld) outputs; same member names as crm_output_type
+  double *cltot, *cllow, *clmed, *clhgh, *precc, *precl, *precsc, *precsl, *jt_crm, *mx_crm, *prectend, *precstend, *taux, *tauy, *z0m,
+      *timing_factor;
+  double *cldtop, *qc_mean, *qi_mean, *qs_mean, *qg_mean, *qr_mean, *sltend, *qltend, *qcltend, *qiltend, *cld, *gicewp, *gliqwp, *mctot,
+      *mcup, *mcdn, *mcuup, *mcudn, *mu_crm, *md_crm, *du_crm, *eu_crm, *ed_crm, *flux_qt, *fluxsgs_qt, *tkez, *tkesgsz, *tkz, *flux_u,
+      *flux_v, *flux_qp, *precflux, *qt_ls, *qt_trans, *qp_trans, *qp_fall, *qp_src, *qp_evp, *t_ls;
+  double *prec_crm;   // (ld,nx,ny)
+};
+
+// precsfc -> precc/precl split and prec_crm (crm_module.F90:1417-1481).  Block per tile.  smem: CRM_RED_DOUBLES(4,P,CT)
+__global__ void __launch_bounds__(512) k_epi_precip(CrmP p, ExtOut o, double dt_eff) {
+  CRM_TILE_SETUP
+  CRM_DYN_SMEM(double, red);
+  const double dz = p.dz[cb];
+  const long long c2 = (long long)tile * P + tid;
+  const double nst = (double)p.nstop;
+  const double ps = p.precsfc[c2] * dz / dt_eff / nst;
+  const double pss = p.precssfc[c2] * dz / dt_eff / nst;
+  p.precsfc[c2] = ps; p.precssfc[c2] = pss;
+  const double thr = (double)(10.f / 86400.f);
+  double v[4];
+  if (ps > thr) { v[0] = ps; v[1] = pss; v[2] = 0.; v[3] = 0.; }
+  else { v[0] = 0.; v[1] = 0.; v[2] = ps; v[3] = pss; }
+  block_sum<4>(v, tid, P, CT, red);
+  const int icrm = cb;
+  if (icrm < p.ncrms) {
+    o.prec_crm[(size_t)icrm + (size_t)p.ld * (size_t)i] = ps / R4(1000.);
+    if (i == 0) {
+      const double factor_xy = 1. / (double)(p.nx * p.ny);
+      o.precc[icrm] = v[0] * factor_xy / R4(1000.);
+      o.precsc[icrm] = v[1] * factor_xy / R4(1000.);
+      o.precl[icrm] = v[2] * factor_xy / R4(1000.);
+      o.precsl[icrm] = v[3] * factor_xy / R4(1000.);
+    }
+  }
+}
+
+// All (ld,plev) and (ld) outputs; one thread per CRM (crm_module.F90:1109-1251, 1358-1377, 1467-1594).
+__global__ void k_epi_profiles(CrmP p, ExtIn in, ExtOut o, const double *esum, double dt_eff, double dtn_last) {
+  const int icrm = blockIdx.x * blockDim.x + threadIdx.x;
+  if (icrm >= p.ncrms) return;
+  const int CT = p.CT, tile = icrm / CT, lane = icrm - tile * CT;
+  const int pb = tile * p.nzp * CT + lane;
+  const int nzm = p.nzm, plev = p.plev, ld = p.ld;
+  const int ptop = plev - nzm + 1;
+  const size_t np = (size_t)p.ntiles * p.nzp * CT;
+  auto ES = [&](int q, int k) { return esum[q * np + pb + k * CT]; };
+  auto IN = [&](const double *a, int l) { return a[(size_t)icrm + (size_t)ld * (l - 1)]; };
+  auto O = [&](double *a, int l) -> double & { return a[(size_t)icrm + (size_t)ld * (l - 1)]; };
+  const double factor_xy = 1. / (double)(p.nx * p.ny);
+  const double nst = (double)p.nstop;
+  const double factor_xyt = factor_xy / nst;
+  const double icrm_run_time = 1. / p.dt_gl;
+  const double dz = p.dz[icrm];
+  // levels above the CRM top: zero tendencies and zero statistics (crm_module.F90:620-658, 1110-1120)
+  for (int l = 1; l <= plev; l++) {
+    double *z0[] = {o.cld, o.cldtop, o.gicewp, o.gliqwp, o.mctot, o.mcup, o.mcdn, o.mcuup, o.mcudn, o.qc_mean, o.qi_mean, o.qs_mean,
+                    o.qg_mean, o.qr_mean, o.mu_crm, o.md_crm, o.eu_crm, o.du_crm, o.ed_crm, o.flux_qt, o.flux_u, o.flux_v, o.fluxsgs_qt,
+                    o.tkez, o.tkesgsz, o.tkz, o.flux_qp, o.precflux, o.qt_trans, o.qp_trans, o.qp_fall, o.qp_evp, o.qp_src, o.qt_ls, o.t_ls,
+                    o.sltend, o.qltend, o.qcltend, o.qiltend};
+    for (double *a : z0) O(a, l) = 0.;
+  }
+  double colprec = 0., colprecs = 0.;
+  for (int k = 1; k <= nzm; k++) { colprec += ES(5, k); colprecs += ES(6, k); }
+  for (int k = 1; k <= nzm; k++) {
+    const int l = plev - k + 1;
+    const double tln = ES(0, k) * factor_xy, qln = ES(1, k) * factor_xy, qccln = ES(2, k) * factor_xy, qiiln = ES(3, k) * factor_xy;
+    O(o.sltend, l) = CRM_CP * (tln - IN(in.tl, l)) * icrm_run_time;
+    O(o.qltend, l) = (qln - IN(in.ql, l)) * icrm_run_time;
+    O(o.qcltend, l) = (qccln - IN(in.qccl, l)) * icrm_run_time;
+    O(o.qiltend, l) = (qiiln - IN(in.qiil, l)) * icrm_run_time;
+    const double pdel = IN(in.pdel, l);
+    O(o.cld, l) = dmin(1., PF(p.s_cld, k) * factor_xyt);
+    O(o.cldtop, l) = dmin(1., PF(p.s_cldtop, k) * factor_xyt);
+    O(o.gicewp, l) = PF(p.s_gicewp, k) * pdel * R4(1000.) / CRM_GGR * factor_xyt;
+    O(o.gliqwp, l) = PF(p.s_gliqwp, k) * pdel * R4(1000.) / CRM_GGR * factor_xyt;
+    const double mcup = PF(p.s_mcup, k) * factor_xyt, mcdn = PF(p.s_mcdn, k) * factor_xyt;
+    const double mcuup = PF(p.s_mcuup, k) * factor_xyt, mcudn = PF(p.s_mcudn, k) * factor_xyt;
+    O(o.mcup, l) = mcup; O(o.mcdn, l) = mcdn; O(o.mcuup, l) = mcuup; O(o.mcudn, l) = mcudn;
+    O(o.mctot, l) = mcup + mcdn + mcuup + mcudn;
+    O(o.qc_mean, l) = ES(2, k) * factor_xy; O(o.qi_mean, l) = ES(3, k) * factor_xy; O(o.qr_mean, l) = ES(7, k) * factor_xy;
+    O(o.qg_mean, l) = ES(8, k) * factor_xy; O(o.qs_mean, l) = ES(9, k) * factor_xy;
+    // fluxes and other stat (crm_module.F90:1516-1594)
+    const double rhow = PF(p.rhow, k), rho = PF(p.rho, k);
+    const double tmp1 = dz / rhow;
+    const double tmp2 = tmp1 / dtn_last;
+    const double mkwsb1 = PF(p.mkwsb1, k) * tmp1 * rhow * factor_xy / nst, mkwsb2 = PF(p.mkwsb2, k) * tmp1 * rhow * factor_xy / nst;
+    const double mkwle1 = PF(p.mkwle1, k) * tmp2 * rhow * factor_xy / nst, mkwle2 = PF(p.mkwle2, k) * tmp2 * rhow * factor_xy / nst;
+    const double mkadv1 = PF(p.mkadv1, k) * factor_xy * icrm_run_time, mkadv2 = PF(p.mkadv2, k) * factor_xy * icrm_run_time;
+    const double mkdiff1 = PF(p.mkdiff1, k) * factor_xy * icrm_run_time, mkdiff2 = PF(p.mkdiff2, k) * factor_xy * icrm_run_time;
+    O(o.flux_u, l) = (PF(p.uwle, k) + PF(p.uwsb, k)) * tmp1 * factor_xy / nst;
+    O(o.flux_v, l) = (0. + 0.) * tmp1 * factor_xy / nst;
+    O(o.flux_qt, l) = mkwle1 + mkwsb1;
+    O(o.fluxsgs_qt, l) = mkwsb1;
+    O(o.flux_qp, l) = mkwle2 + mkwsb2;
+    O(o.qt_trans, l) = mkadv1 + mkdiff1;
+    O(o.qp_trans, l) = mkadv2 + mkdiff2;
+    const double tkesgsz = rho * ES(12, k) * factor_xy;
+    O(o.tkesgsz, l) = tkesgsz;
+    O(o.tkez, l) = rho * 0.5 * (ES(10, k) + 0. * 0 + ES(11, k)) * factor_xy + tkesgsz;
+    O(o.tkz, l) = ES(13, k) * factor_xy;
+    O(o.precflux, l) = (PF(p.precflux, k) * factor_xy * dz / dt_eff / nst) / R4(1000.);
+    O(o.qp_fall, l) = PF(p.qpfall, k) * factor_xy * icrm_run_time;
+    O(o.qp_evp, l) = PF(p.qpevp, k) * factor_xy * icrm_run_time;
+    O(o.qp_src, l) = PF(p.qpsrc, k) * factor_xy * icrm_run_time;
+    O(o.qt_ls, l) = PF(p.qtend, k);
+    O(o.t_ls, l) = PF(p.ttend, k);
+  }
+  for (int l = ptop; l <= ptop + 1; l++) { O(o.sltend, l) = 0.; O(o.qltend, l) = 0.; O(o.qcltend, l) = 0.; O(o.qiltend, l) = 0.; }
+  o.prectend[icrm] = (colprec - p.colprec0[icrm]) / CRM_GGR * factor_xy * icrm_run_time;
+  o.precstend[icrm] = (colprecs - p.colprecs0[icrm]) / CRM_GGR * factor_xy * icrm_run_time;
+  o.z0m[icrm] = p.z0[icrm];
+  o.taux[icrm] = 0. / nst;
+  o.tauy[icrm] = 0. / nst;
+  o.cltot[icrm] = p.s_cltot[icrm] * factor_xyt; o.clhgh[icrm] = p.s_clhgh[icrm] * factor_xyt;
+  o.clmed[icrm] = p.s_clmed[icrm] * factor_xyt; o.cllow[icrm] = p.s_cllow[icrm] * factor_xyt;
+  o.timing_factor[icrm] = nst / nst;
+  // mass fluxes (crm_module.F90:1483-1511); mui/mdi at GCM interface l <-> CRM w-level k = plev+2-l
+  double jt = plev * R4(1.0), mx = R4(1.0);
+  auto MUI = [&](int l) { int k = plev + 2 - l; return (k >= 1 && k <= nzm) ? PF(p.s_mui, k) : 0.; };
+  auto MDI = [&](int l) { int k = plev + 2 - l; return (k >= 1 && k <= nzm) ? PF(p.s_mdi, k) : 0.; };
+  for (int l = 1; l <= plev; l++) {
+    const double mui0 = MUI(l), mui1 = MUI(l + 1), mdi0 = MDI(l), mdi1 = MDI(l + 1);
+    double mu = 0.5 * (mui0 + mui1), md = 0.5 * (mdi0 + mdi1);
+    mu = mu * CRM_GGR / R4(100.); md = md * CRM_GGR / R4(100.);
+    const double pdel = IN(in.pdel, l);
+    double eu = 0., du = 0., ed = 0.;
+    if (mui0 - mui1 > 0) eu = (mui0 - mui1) * CRM_GGR / pdel;
+    else du = R4(-1.0) * (mui0 - mui1) * CRM_GGR / pdel;
+    if (mdi1 - mdi0 < 0) ed = (mdi0 - mdi1) * CRM_GGR / pdel;
+    O(o.mu_crm, l) = mu; O(o.md_crm, l) = md; O(o.eu_crm, l) = eu; O(o.du_crm, l) = du; O(o.ed_crm, l) = ed;
+    if (fabs(mu) > R4(1.0e-15) || fabs(md) > R4(1.0e-15)) { jt = dmin((double)l, jt); mx = dmax((double)l, mx); }
+  }
+  o.jt_crm[icrm] = jt;
+  o.mx_crm[icrm] = mx;
+}
+
+// crm_rad outputs scaled by nx_rad_fac*ny_rad_fac/nstop, written straight to the boundary layout (crm_module.F90:1086-1107).
+__global__ void k_epi_rad(CrmP p, const double *acc, double *ext, int ld, double scale) {
+  const int tid = threadIdx.x, CT = p.CT, Pd = p.nx_rad * CT;
+  const int tile = blockIdx.x / p.nzm, k = blockIdx.x - tile * p.nzm;
+  if (tid >= Pd) return;
+  const int ir = tid / CT, lane = tid - ir * CT;
+  const int icrm = tile * CT + lane;
+  if (icrm >= p.ncrms) return;
+  ext[(size_t)icrm + (size_t)ld * ((size_t)ir + (size_t)p.nx_rad * (size_t)k)] = acc[((long long)tile * p.nzm + k) * Pd + tid] * scale;
+}
+
+}  // namespace crm

@@ -1,0 +1,93 @@
+"""Loader and thin object wrapper of the C-ABI library libcrm_b200.so (include/crm_b200.h).
+
+There is NO CPU fallback: if the CUDA library has not been built (``python -c "import __graft_entry__ as g; g.build()"``)
+or no CUDA device is present, loading / init raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .crm_types import crm_output_type
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, "csrc", "libcrm_b200.so")
+_libs = {}
+
+
+class CrmB200Error(RuntimeError):
+    pass
+
+
+def load(path=None):
+    path = path or os.environ.get("CRM_B200_LIB", DEFAULT_LIB)
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise CrmB200Error("CUDA library %s not built; run __graft_entry__.build() (nvcc, sm_100a). No CPU fallback exists." % path)
+    lib = C.CDLL(path)
+    lib.crm_b200_init.restype = C.c_int
+    lib.crm_b200_init.argtypes = [C.c_int, C.POINTER(abi.crm_dims_t), C.POINTER(C.c_void_p)]
+    lib.crm_b200_run.restype = C.c_int
+    lib.crm_b200_run.argtypes = [C.c_void_p, C.POINTER(abi.crm_dims_t), C.POINTER(abi.crm_input_t), C.POINTER(abi.crm_state_t),
+                                 C.POINTER(abi.crm_rad_t), C.POINTER(abi.crm_output_t)]
+    lib.crm_b200_free.argtypes = [C.c_void_p]
+    lib.crm_b200_last_error.restype = C.c_char_p
+    lib.crm_b200_last_error.argtypes = [C.c_void_p]
+    lib.crm_b200_get_stats.argtypes = [C.c_void_p, C.POINTER(abi.crm_run_stats_t)]
+    lib.crm_b200_debug_fetch.restype = C.c_longlong
+    lib.crm_b200_debug_fetch.argtypes = [C.c_void_p, C.c_char_p, abi.c_dp, C.c_size_t]
+    lib.crm_b200_abi_version.restype = C.c_int
+    _libs[path] = lib
+    return lib
+
+
+class CrmHandle:
+    """One workspace arena on one GPU (crm_b200_init / crm_b200_run / crm_b200_free)."""
+
+    def __init__(self, dims, device=0, lib_path=None):
+        self.lib = load(lib_path)
+        self.dims = dims
+        self.h = C.c_void_p()
+        d = dims.c_struct()
+        rc = self.lib.crm_b200_init(int(device), C.byref(d), C.byref(self.h))
+        if rc != 0:
+            raise CrmB200Error("crm_b200_init failed (%d): %s" % (rc, self.lib.crm_b200_last_error(None).decode()))
+
+    def run_structs(self, dims, ci, cs, cr, co):
+        d = dims.c_struct()
+        rc = self.lib.crm_b200_run(self.h, C.byref(d), C.byref(ci), C.byref(cs), C.byref(cr), C.byref(co))
+        if rc != 0:
+            raise CrmB200Error("crm_b200_run failed (%d): %s" % (rc, self.lib.crm_b200_last_error(self.h).decode()))
+
+    def run(self, dims, inp, state, rad, out=None):
+        if out is None:
+            out = crm_output_type().initialize(dims)
+        self.run_structs(dims, inp.c_struct(), state.c_struct(), rad.c_struct(), out.c_struct())
+        return out
+
+    def stats(self):
+        s = abi.crm_run_stats_t()
+        self.lib.crm_b200_get_stats(self.h, C.byref(s))
+        return s.as_dict()
+
+    def debug_fetch(self, name, dims=None):
+        dims = dims or self.dims
+        nk = dims.nzm + 1 if name in ("w", "dwdt", "dwdt_a", "dwdt_c", "wmf") else dims.nzm
+        buf = np.zeros((dims.ncrms, dims.nx, dims.ny, nk), order="F")
+        n = self.lib.crm_b200_debug_fetch(self.h, name.encode(), abi.dptr(buf), buf.size)
+        if n < 0:
+            raise CrmB200Error("crm_b200_debug_fetch(%s) -> %d" % (name, n))
+        return buf
+
+    def close(self):
+        if self.h:
+            self.lib.crm_b200_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

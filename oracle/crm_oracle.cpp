@@ -232,6 +232,8 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
   const double crm_nx_rad_fac = (double)g.nx_rad / (double)nx, crm_ny_rad_fac = (double)g.ny_rad / (double)ny;
   long long ncycle_sum = 0, ncycle_max = 0, nprec_max = 0;
   int fail = 0;
+  const int dbg_stop = getenv("CRM_DEBUG_STOP") ? atoi(getenv("CRM_DEBUG_STOP")) : 0;   // test hook: stop inside the first sub-step
+  bool dbg_break = false;
 
   // ======================================= main time loop =======================================
   s.nstep = 0;
@@ -261,22 +263,28 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
         rad_heating(g, c, s, qrad[ic]);
         fail += damping(g, c, s);
         ice_fall(g, c, s);
+        if (dbg_stop == 1) continue;
         boundaries(g, c, 3);
         boundaries(g, c, 0);
         // crmsurface: no-op (sfc_flx_fxd=.false., crmsurface.F90:16)
         sgs_proc(g, c, s);
+        if (dbg_stop == 2) continue;
         boundaries(g, c, 4);
         advect_mom(g, c, s);
         sgs_mom(g, c, s);
+        if (dbg_stop == 3) continue;
         pressure(g, c, s, fx, fy);
         adams(g, c, s);
+        if (dbg_stop == 4) continue;
         boundaries(g, c, 2);
         // advect_all_scalars.F90:32-49
         advect_scalar(g, c, c.t, c.tdiff /*dummy*/, c.twsb /*dummy*/);
         advect_scalar(g, c, c.qt, c.mkadv[1], c.mkwle[1]);
         advect_scalar(g, c, c.qp, c.mkadv[2], c.mkwle[2]);
+        if (dbg_stop == 5) continue;
         prec_cfl = dmax(prec_cfl, precip_fall_part1(g, c, s, mc));
       }
+      if (dbg_stop >= 1 && dbg_stop <= 5) { dbg_break = true; break; }
       if (fail) { g_err = "Error: in damping() tau_min is too small!"; return 9; }
       if (prec_cfl > R4(0.9)) nprec_max = std::max<long long>(nprec_max, (long long)std::ceil(prec_cfl / R4(0.9)));
       else nprec_max = std::max<long long>(nprec_max, 1);
@@ -286,11 +294,13 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
         Crm &c = crms[ic];
         precip_fall_part2(g, c, s, mc, prec_cfl);
         uvw(g, c, s);
+        if (dbg_stop == 6) continue;
         boundaries(g, c, 3);
         // sgs_scalars (sgs.F90:389-447): t, then micro_flux (fluxbq=fluxtq=0), then qt, qp
         diffuse_scalar(g, c, s, c.t, c.fluxbt, c.fluxtt, c.tdiff, c.twsb);
         diffuse_scalar(g, c, s, c.qt, c.fluxbq, c.fluxtq, c.mkdiff[1], c.mkwsb[1]);
         diffuse_scalar(g, c, s, c.qp, c.fluxbq /*=0*/, c.fluxtq /*=0*/, c.mkdiff[2], c.mkwsb[2]);
+        if (dbg_stop == 7) continue;
         // micro_proc (microphysics.F90:292-329)
         if (s.icycle == 1) precip_init(g, c, mc);
         cloud(g, c);
@@ -298,6 +308,7 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
         micro_diagnose(g, c, mc);
         if (use_accel && !ceaseflag) cease_now = cease_now || accelerate_part1(g, c, accel_uv);
       }
+      if (dbg_stop == 6 || dbg_stop == 7) { dbg_break = true; break; }
       if (use_accel && !ceaseflag) {
         if (cease_now) {
           ceaseflag = true;
@@ -310,7 +321,9 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
 #pragma omp parallel for schedule(static)
       for (int ic = 0; ic < ncrms; ic++) diagnose(g, crms[ic], s);
       int nn = s.na; s.na = s.nc; s.nc = s.nb; s.nb = nn;   // crm_module.F90:884-887
+      if (dbg_stop == 8) { dbg_break = true; break; }
     }
+    if (dbg_break) break;
 
     // ---- per-nstep statistics (crm_module.F90:896-1073) ----
 #pragma omp parallel for schedule(static)
@@ -594,7 +607,7 @@ extern "C" long long crm_oracle_debug_fetch(const char *name, double *buf, size_
   if (!ncrms) return -1;
   std::string nm(name);
   int nk = g.nzm;
-  if (nm == "w" || nm == "dwdt") nk = g.nz;
+  if (nm == "w" || nm == "dwdt" || nm == "dwdt_a" || nm == "dwdt_c") nk = g.nz;
   size_t need = (size_t)ncrms * g.nx * g.ny * nk;
   if (n < need) return -2;
   for (int ic = 0; ic < ncrms; ic++) {
@@ -605,6 +618,8 @@ extern "C" long long crm_oracle_debug_fetch(const char *name, double *buf, size_
     else if (nm == "tabs") f = &c.tabs; else if (nm == "qv") f = &c.qv; else if (nm == "qcl") f = &c.qcl;
     else if (nm == "qci") f = &c.qci; else if (nm == "qpl") f = &c.qpl; else if (nm == "qpi") f = &c.qpi;
     else if (nm == "tk") f = &c.tk; else if (nm == "tkh") f = &c.tkh; else if (nm == "tke") f = &c.tke; else if (nm == "p") f = &c.p;
+    else if (nm == "dudt_a") f = &c.dudt[g_step.na]; else if (nm == "dwdt_a") f = &c.dwdt[g_step.na];
+    else if (nm == "dudt_c") f = &c.dudt[g_step.nc]; else if (nm == "dwdt_c") f = &c.dwdt[g_step.nc];
     else if (nm == "dudt") f = &c.dudt[g_step.nb]; else if (nm == "dwdt") f = &c.dwdt[g_step.nb];   // slot just computed (after rotation it is nb)
     else return -3;
     for (int k = 1; k <= nk; k++)

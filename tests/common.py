@@ -1,0 +1,63 @@
+"""Shared helpers of the parity tests: build a case, run oracle and device library on identical buffers, compare."""
+import importlib
+import os
+
+import numpy as np
+
+pkg = importlib.import_module("acme-ecp_b200")
+libmod = importlib.import_module("acme-ecp_b200.lib")
+import oracle_binding as ob  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_LIB = os.path.join(ROOT, "tests", "emu", "_build", "libcrm_emu.so")
+
+STATE = ("u_wind", "v_wind", "w_wind", "temperature", "qt", "qp", "qn")
+RAD = ("temperature", "qv", "qc", "qi", "cld")
+
+
+def small_dims(ncrms=5, nx=8, nzm=28, plev=30, nsteps=1, igstep=3, ld=None, **kw):
+    dx, dt = (4000.0, 20.0) if plev == 30 else (1000.0, 10.0)
+    return pkg.CrmDims(ncrms=ncrms, nx=nx, ny=1, nzm=nzm, plev=plev, dx=dx, dt=dt, dt_gl=dt * nsteps, igstep=igstep,
+                       ld=ld, nx_rad=max(1, nx // 4), **kw)
+
+
+def make_case(dims, spinup_steps=90, seed=None):
+    """Synthetic inputs, optionally spun up with the oracle so that clouds / precipitation / sub-cycling are active."""
+    dims, inp, st, rad = pkg.synthetic.make_case(dims, seed=seed)
+    if spinup_steps:
+        ob.run(dims.copy(dt_gl=dims.dt * spinup_steps, igstep=1, use_crm_accel=False), inp, st, rad)
+    return dims, inp, st, rad
+
+
+def rel_err(a, b, ncrms):
+    a = np.asarray(a)[:ncrms]
+    b = np.asarray(b)[:ncrms]
+    scale = max(float(np.abs(a).max()), 1e-300)
+    return float(np.abs(a - b).max()) / scale, scale
+
+
+def run_both(dims, inp, st, rad, lib_path=None, device=0):
+    st_o, rad_o, st_g, rad_g = st.copy(), rad.copy(), st.copy(), rad.copy()
+    out_o, stats_o = ob.run(dims, inp, st_o, rad_o)
+    h = libmod.CrmHandle(dims, device=device, lib_path=lib_path)
+    out_g = h.run(dims, inp, st_g, rad_g)
+    stats_g = h.stats()
+    h.close()
+    return (st_o, rad_o, out_o, stats_o), (st_g, rad_g, out_g, stats_g)
+
+
+def compare_all(dims, res_o, res_g, tol, abs_floor=1e-18, skip=()):
+    """Relative (to the field maximum) max-norm comparison of every returned array.  Returns list of failures."""
+    st_o, rad_o, out_o, _ = res_o
+    st_g, rad_g, out_g, _ = res_g
+    bad = []
+    items = [("state." + n, getattr(st_o, n), getattr(st_g, n)) for n in STATE]
+    items += [("rad." + n, getattr(rad_o, n), getattr(rad_g, n)) for n in RAD]
+    items += [(n, getattr(out_o, n), getattr(out_g, n)) for n, _ in pkg.abi.OUTPUT_FIELDS]
+    for name, a, b in items:
+        if name in skip:
+            continue
+        err, scale = rel_err(a, b, dims.ncrms)
+        if err > tol and err * scale > abs_floor:
+            bad.append((name, err, scale))
+    return bad

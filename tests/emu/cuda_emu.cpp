@@ -1,0 +1,26 @@
+// DEV/TEST TOOL ONLY (see cuda_emu.h).
+#include "cuda_emu.h"
+
+thread_local emu_dim3 threadIdx, blockIdx;
+emu_dim3 blockDim, gridDim;
+pthread_barrier_t emu_barrier;
+char *emu_dyn_smem = nullptr;
+
+void emu_launch(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body) {
+  gridDim.x = grid; blockDim.x = block;
+  std::vector<char> dyn(smem + 64);
+  emu_dyn_smem = dyn.data();
+  pthread_barrier_init(&emu_barrier, nullptr, block);
+  for (unsigned b = 0; b < grid; b++) {
+    std::vector<std::thread> th;
+    th.reserve(block);
+    for (unsigned t = 0; t < block; t++)
+      th.emplace_back([&, t, b]() {
+        threadIdx.x = t; blockIdx.x = b;
+        body();
+      });
+    for (auto &x : th) x.join();
+  }
+  pthread_barrier_destroy(&emu_barrier);
+  emu_dyn_smem = nullptr;
+}

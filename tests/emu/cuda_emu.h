@@ -1,0 +1,56 @@
+// DEV/TEST TOOL ONLY -- never compiled into, loaded by, or shipped with the product library.
+// Minimal host emulation of the CUDA execution model so that the kernel *logic* of acme-ecp_b200/csrc can be
+// exercised in a container without a GPU: every CUDA thread of a block becomes an OS thread, __syncthreads() is
+// a pthread barrier, blocks run one after another, __shared__ variables become function-local statics.
+// Built only by tests/emu/Makefile into tests/emu/_build/libcrm_emu.so (used by tests/test_emu_parity.py to
+// compare the device code path against the oracle on tiny cases).  The product (libcrm_b200.so) is built by
+// nvcc for sm_100a from the same sources with CRM_EMU undefined.
+#pragma once
+#include <pthread.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static
+
+struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
+extern thread_local emu_dim3 threadIdx, blockIdx;
+extern emu_dim3 blockDim, gridDim;
+extern pthread_barrier_t emu_barrier;
+extern char *emu_dyn_smem;
+
+static inline void __syncthreads() { pthread_barrier_wait(&emu_barrier); }
+
+static inline unsigned long long atomicMax(unsigned long long *a, unsigned long long v) {
+  unsigned long long old = *a;
+  while (old < v && !__atomic_compare_exchange_n(a, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
+static inline int atomicMax(int *a, int v) {
+  int old = *a;
+  while (old < v && !__atomic_compare_exchange_n(a, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
+static inline int atomicMin(int *a, int v) {
+  int old = *a;
+  while (old > v && !__atomic_compare_exchange_n(a, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
+static inline int atomicOr(int *a, int v) { return __atomic_fetch_or(a, v, __ATOMIC_SEQ_CST); }
+static inline long long __double_as_longlong(double x) { long long r; memcpy(&r, &x, 8); return r; }
+static inline double __longlong_as_double(long long x) { double r; memcpy(&r, &x, 8); return r; }
+
+void emu_launch(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body);
+
+#define CRM_LAUNCH(kern, grid, block, smem, stream, ...) \
+  emu_launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), [&]() { kern(__VA_ARGS__); })
+#define CRM_DYN_SMEM(type, name) type *name = (type *)emu_dyn_smem

@@ -53,7 +53,7 @@ def run(dims, inp, state, rad, out=None):
 
 
 def debug_fetch(name, dims):
-    nk = dims.nzm + 1 if name in ("w", "dwdt") else dims.nzm
+    nk = dims.nzm + 1 if name in ("w", "dwdt", "dwdt_a", "dwdt_c", "wmf") else dims.nzm
     buf = np.zeros((dims.ncrms, dims.nx, dims.ny, nk), order="F")
     n = lib().crm_oracle_debug_fetch(name.encode(), abi.dptr(buf), buf.size)
     if n < 0:
