@@ -58,7 +58,13 @@ struct DevTimer {
 
 namespace {
 
+struct KTime { const char *name; double ms; long long n; };
+
 struct Handle {
+  bool ktiming = false;
+  DevTimer ktimer;
+  std::vector<KTime> ktimes;
+  std::string ktime_report;
   crm_dims_t d0;          // init dims
   int device = 0;
   int CT = 8, ntiles = 0, P = 0, nzp = 0;
@@ -90,9 +96,17 @@ template <typename T> T *carve(Handle *h, size_t n) {
   return (T *)q;
 }
 
+// Optional per-kernel device timing (crm_b200_set_kernel_timing): CUDA events around every launch, accumulated by
+// kernel name.  Off by default (it serialises the launch queue).
+static void ktime_add(std::vector<KTime> &v, const char *name, double ms) {
+  for (auto &k : v) if (k.name == name || !strcmp(k.name, name)) { k.ms += ms; k.n++; return; }
+  v.push_back({name, ms, 1});
+}
 #define LAUNCH(h, kern, grid, block, smem, ...)                 \
   do {                                                          \
+    if ((h)->ktiming) (h)->ktimer.start();                      \
     CRM_LAUNCH(kern, grid, block, smem, 0, __VA_ARGS__);        \
+    if ((h)->ktiming) ktime_add((h)->ktimes, #kern, (h)->ktimer.stop()); \
     (h)->launches++;                                            \
   } while (0)
 
@@ -207,6 +221,24 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   return 0;
 }
 
+extern "C" int crm_b200_set_kernel_timing(void *handle, int on) {
+  if (!handle) return 1;
+  ((Handle *)handle)->ktiming = on != 0;
+  return 0;
+}
+
+extern "C" const char *crm_b200_kernel_times(void *handle) {
+  if (!handle) return "";
+  Handle *h = (Handle *)handle;
+  h->ktime_report.clear();
+  char line[256];
+  for (auto &k : h->ktimes) {
+    snprintf(line, sizeof(line), "%s %.6f %lld\n", k.name, k.ms, k.n);
+    h->ktime_report += line;
+  }
+  return h->ktime_report.c_str();
+}
+
 extern "C" int crm_b200_get_stats(void *handle, crm_run_stats_t *s) {
   if (!handle || !s) return 1;
   *s = ((Handle *)handle)->stats;
@@ -226,6 +258,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   auto wall0 = std::chrono::steady_clock::now();
   memset(&h->stats, 0, sizeof(h->stats));
   h->launches = 0;
+  h->ktimes.clear();
   CrmP &p = h->p;
   const int CT = h->CT, P = h->P, nx = d->nx, nzm = d->nzm, nz = nzm + 1, plev = d->plev, ld = d->ld, ncrms = d->ncrms;
   const int ntiles = (ncrms + CT - 1) / CT;

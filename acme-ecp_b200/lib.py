@@ -39,6 +39,9 @@ def load(path=None):
     lib.crm_b200_debug_fetch.restype = C.c_longlong
     lib.crm_b200_debug_fetch.argtypes = [C.c_void_p, C.c_char_p, abi.c_dp, C.c_size_t]
     lib.crm_b200_abi_version.restype = C.c_int
+    lib.crm_b200_set_kernel_timing.argtypes = [C.c_void_p, C.c_int]
+    lib.crm_b200_kernel_times.restype = C.c_char_p
+    lib.crm_b200_kernel_times.argtypes = [C.c_void_p]
     _libs[path] = lib
     return lib
 
@@ -71,6 +74,17 @@ class CrmHandle:
         s = abi.crm_run_stats_t()
         self.lib.crm_b200_get_stats(self.h, C.byref(s))
         return s.as_dict()
+
+    def set_kernel_timing(self, on=True):
+        self.lib.crm_b200_set_kernel_timing(self.h, int(bool(on)))
+
+    def kernel_times(self):
+        """{kernel: (total_ms, launches)} of the last run (needs set_kernel_timing(True))."""
+        out = {}
+        for line in self.lib.crm_b200_kernel_times(self.h).decode().splitlines():
+            name, ms, n = line.split()
+            out[name] = (float(ms), int(n))
+        return out
 
     def debug_fetch(self, name, dims=None):
         dims = dims or self.dims

@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- CRM cell-updates/s of the B200-native crm() (BASELINE.json metric) + roofline + CPU baseline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2] [--ncrms n]
+
+A "step" is one crm() call (one GCM time step, dt_gl = 1800 s => nstop = 180 CRM steps, each split into ncycle
+sub-steps by the batch-global CFL) over the whole batch of synthetic aquaplanet columns.  Workload at N=1: BASELINE
+config 2 (48,602 CRMs of 64x1x58, sam1mom, dt 10 s).  N>1: the same per-GPU batch on every rank (weak scaling; GCM
+columns partition with no inter-GPU traffic, so there is no collective on the data path).
+value  = cell-updates/s with the CRM state resident in HBM (device pointers through the C ABI)
+e2e    = same through the C ABI with HOST buffers (pinned): H2D of crm_state/crm_rad + D2H of state and all outputs
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+BYTES_PER_CELL_UPDATE = {"2d_sam1mom": 872.0}   # SURVEY.md 8(d) / App. C algorithmic traffic model
+# distinct 3-D arrays read + written per cell by each kernel of this implementation
+KERNEL_WORDS = {"k_p1_forcing": 14, "k_p2_sgs": 14, "k_p3_mom": 7, "k_p4_press_fwd": 9, "k_p5_press_bwd": 15,
+                "k_mpdata": 4, "k_precip_a": 3, "k_precip_b": 6, "k_p7_diffuse": 7, "k_p8_micro": 15, "k_stats": 8,
+                "k_kurant": 3}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        sm, mx, reasons = [], [], set()
+        with open(self.f.name) as f:
+            for line in f:
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons)}
+        return out
+
+
+def build_case(pkg, cfg, ncrms, seed):
+    kw = dict(pkg.synthetic.CONFIGS[cfg])
+    if ncrms:
+        kw["ncrms"] = ncrms
+    dims = pkg.CrmDims(dt_gl=1800.0, igstep=1, **kw)
+    return pkg.synthetic.make_case(dims, seed=seed)
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path.  The Fortran cannot be compiled here (no
+    Fortran compiler), so this is the restated reference (oracle/, kind "port") with all host threads, on a bounded
+    sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pkg = importlib.import_module("acme-ecp_b200")
+    import oracle_binding as ob
+    ncrms, nstop = args.cpu_ncrms, args.cpu_nstop
+    dims, inp, st, rad = build_case(pkg, args.config, ncrms, 20260101 + int(args.config[3:]))
+    dims = dims.copy(dt_gl=dims.dt * nstop)
+    cores = ob.lib().crm_oracle_num_threads()
+    for w in range(args.warmup):
+        ob.run(dims.copy(igstep=1 if w == 0 else 3), inp, st, rad)
+    t0 = time.time()
+    upd = 0
+    for _ in range(args.steps):
+        _, s = ob.run(dims.copy(igstep=3), inp, st, rad)
+        upd += dims.cells * s["ncycle_sum"]
+    dt = time.time() - t0
+    val = upd / dt
+    sample = "%d CRMs x %d CRM steps per step of the %s geometry (same seed), all host threads" % (ncrms, nstop, args.config)
+    line = {"impl": "reference", "metric": "CRM cell-updates/s", "value": val, "unit": "cell-updates/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args, dims), "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_name(args, dims):
+    return "%s: %d CRMs/GPU of %dx%dx%d sam1mom, crm_dt %g s, dt_gl %g s (nstop %d), synthetic aquaplanet columns" % (
+        args.config, dims.ncrms, dims.nx, dims.ny, dims.nzm, dims.dt, dims.dt_gl, int(dims.dt_gl / dims.dt))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("acme-ecp_b200")
+    libmod = importlib.import_module("acme-ecp_b200.lib")
+    abi = pkg.abi
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); lrank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(lrank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
+    dims, inp, st, rad = build_case(pkg, args.config, args.ncrms, 20260101 + int(args.config[3:]) + 1000 * rank)
+    if args.nstop:
+        dims = dims.copy(dt_gl=dims.dt * args.nstop)
+    h = libmod.CrmHandle(dims, device=lrank)
+    out = pkg.crm_output_type().initialize(dims)
+    big = ("qcl", "qci", "qpl", "qpi", "tk", "tkh")
+
+    # ---- device-resident arm: crm_state, crm_rad and the 3-D outputs live in HBM
+    def to_dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a.ravel(order="F"))).cuda()
+    dstate = {n: to_dev(getattr(st, n)) for n in abi.STATE_FIELDS_SAM1MOM}
+    drad = {n: to_dev(getattr(rad, n)) for n in abi.RAD_FIELDS_SAM1MOM}
+    dout = {n: torch.zeros(dstate["qt"].numel(), dtype=torch.float64, device="cuda") for n in big}
+    cs = abi.crm_state_t(); cr = abi.crm_rad_t(); co = out.c_struct(); ci = inp.c_struct()
+    for n, tns in dstate.items():
+        setattr(cs, n, abi.dptr(tns.data_ptr()))
+    for n, tns in drad.items():
+        setattr(cr, n, abi.dptr(tns.data_ptr()))
+    for n, tns in dout.items():
+        setattr(co, n, abi.dptr(tns.data_ptr()))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def call(igstep):
+        h.run_structs(dims.copy(igstep=igstep), ci, cs, cr, co)
+        return h.stats()
+
+    for w in range(args.warmup):
+        call(1 if w == 0 else 3)
+    barrier()
+    sampler = ClockSampler(lrank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    upd, launches, ncyc, kms = 0, 0, 0, 0.0
+    ev0.record()
+    for _ in range(args.steps):
+        s = call(3)
+        upd += dims.cells * s["ncycle_sum"]; launches += s["kernel_launches"]; ncyc += s["ncycle_sum"]; kms += s["ms_kernels"]
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms, float(upd), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, upd_all, launches_all = float(tmax[0]), float(tsum[1]), int(tsum[2])
+    else:
+        upd_all, launches_all = float(upd), int(launches)
+    value = upd_all / (ms * 1e-3)
+
+    # ---- per-kernel device times of one more call (events around every launch) -> roofline of the dominant kernel
+    peak, peak_src = peaks()
+    roof = None
+    if rank == 0:
+        h.set_kernel_timing(True)
+        s = call(3)
+        kt = h.kernel_times()
+        h.set_kernel_timing(False)
+        tot = sum(v[0] for v in kt.values())
+        name = max((k for k in kt if k in KERNEL_WORDS), key=lambda k: kt[k][0])
+        ms_k, n_k = kt[name]
+        alg = KERNEL_WORDS[name] * 8.0 * dims.cells            # bytes per launch
+        ach = alg / (ms_k / n_k * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "kernel_share_of_step": ms_k / tot,
+                "algorithmic_bytes_per_launch": alg,
+                "whole_step": {"bytes_per_cell_update": BYTES_PER_CELL_UPDATE["2d_sam1mom"],
+                               "achieved": BYTES_PER_CELL_UPDATE["2d_sam1mom"] * (value / world) / 1e9,
+                               "frac": BYTES_PER_CELL_UPDATE["2d_sam1mom"] * (value / world) / 1e9 / peak},
+                "kernel_ms": {k: round(v[0], 3) for k, v in sorted(kt.items(), key=lambda kv: -kv[1][0])}}
+
+    # ---- end-to-end arm: HOST (pinned) buffers through the same C-ABI call
+    def pinned_like(a):
+        tns = torch.empty(a.size, dtype=torch.float64).pin_memory()
+        v = tns.numpy().reshape(a.shape, order="F")
+        v[...] = a
+        return tns, v
+    keep = []
+    hst = pkg.crm_state_type(); hrad = pkg.crm_rad_type(); hout = pkg.crm_output_type().initialize(dims)
+    for n in abi.STATE_FIELDS_SAM1MOM:
+        tns, v = pinned_like(dstate[n].cpu().numpy().reshape(getattr(st, n).shape, order="F")); keep.append(tns); setattr(hst, n, v)
+    for n in abi.RAD_FIELDS_SAM1MOM:
+        tns, v = pinned_like(getattr(rad, n)); keep.append(tns); setattr(hrad, n, v)
+    for n in big:
+        tns, v = pinned_like(getattr(hout, n)); keep.append(tns); setattr(hout, n, v)
+    hcs, hcr, hco = hst.c_struct(), hrad.c_struct(), hout.c_struct()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    h.run_structs(dims.copy(igstep=3), ci, hcs, hcr, hco)   # warm-up (page-locks / first touch)
+    barrier()
+    t0 = time.time()
+    upd_e, h2d, d2h = 0, 0, 0
+    for _ in range(e2e_steps):
+        h.run_structs(dims.copy(igstep=3), ci, hcs, hcr, hco)
+        s = h.stats()
+        upd_e += dims.cells * s["ncycle_sum"]; h2d = s["h2d_bytes"]; d2h = s["d2h_bytes"]
+    barrier()
+    te = time.time() - t0
+    t = torch.tensor([te, float(upd_e)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        te, upd_e = float(tmax[0]), float(tsum[1])
+    e2e = {"value": upd_e / te, "unit": "cell-updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "steps": e2e_steps, "host_buffers": "pinned"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle_binding as ob
+        d2, i2, s2, r2 = build_case(pkg, args.config, args.cpu_ncrms, 20260101 + int(args.config[3:]))
+        d2 = d2.copy(dt_gl=d2.dt * args.cpu_nstop)
+        ob.run(d2.copy(igstep=1), i2, s2, r2)
+        t0 = time.time()
+        _, so = ob.run(d2.copy(igstep=3), i2, s2, r2)
+        tc = time.time() - t0
+        cpu = {"value": d2.cells * so["ncycle_sum"] / tc, "unit": "cell-updates/s", "cores": ob.lib().crm_oracle_num_threads(),
+               "kind": "port", "sample": "%d CRMs x %d CRM steps of the %s geometry after a %d-step spin-up, OpenMP over CRMs" %
+               (args.cpu_ncrms, args.cpu_nstop, args.config, args.cpu_nstop)}
+    if rank == 0:
+        line = {"metric": "CRM cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(args, dims), "l2": "inputs larger than L2 (44 GB of state per GPU)" if dims.cells > 2e7 else "small batch",
+                           "mean_ncycle": ncyc / max(1, args.steps * int(dims.dt_gl / dims.dt)), "partition": "columns block-partitioned, no collective"},
+                "gpu_launches": launches_all, "kernel_ms_per_step": kms / max(args.steps, 1),
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks}
+        print(json.dumps(line))
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--ncrms", type=int, default=0, help="override the batch size (testing only)")
+    ap.add_argument("--nstop", type=int, default=0, help="override CRM steps per call (testing only)")
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--cpu-ncrms", type=int, default=128)
+    ap.add_argument("--cpu-nstop", type=int, default=20)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

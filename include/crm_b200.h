@@ -147,6 +147,11 @@ int crm_b200_get_stats(void *handle, crm_run_stats_t *stats);
  * number of doubles written, or <0 on error. */
 long long crm_b200_debug_fetch(void *handle, const char *name, double *host_buf, size_t n);
 
+/* Measurement hook: when on, every kernel launch of crm_b200_run is bracketed by CUDA events (this serialises the
+ * launch queue) and crm_b200_kernel_times returns "kernel_name total_ms launches\n" lines for the last run. */
+int crm_b200_set_kernel_timing(void *handle, int on);
+const char *crm_b200_kernel_times(void *handle);
+
 int crm_b200_abi_version(void);
 
 #ifdef __cplusplus

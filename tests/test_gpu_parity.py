@@ -71,7 +71,8 @@ def test_device_pointers_and_repeat_calls():
     for _ in range(2):
         out_o, _ = cm.ob.run(dims, inp, st_o, rad_o)
     h = cm.libmod.CrmHandle(dims)
-    ci, cr = inp.c_struct(), rad.copy().c_struct()
+    rad_g = rad.copy()               # keep the arrays alive: the C struct only holds raw pointers
+    ci, cr = inp.c_struct(), rad_g.c_struct()
     dev = {n: torch.from_numpy(np.ascontiguousarray(getattr(st, n).ravel(order="F"))).cuda() for n in cm.STATE}
     cs = cm.pkg.abi.crm_state_t()
     for n in cm.STATE:
