@@ -146,12 +146,12 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   if (dev_init(device)) { g_init_err = std::string("crm_b200_init: cannot select CUDA device: ") + dev_errstr(); return 8; }
   Handle *h = new Handle();
   h->d0 = *d; h->device = device;
-  int CT = 512 / d->nx;
+  // CRM tile: P = nx*CT threads per block, at most CRM_MAX_P (kernels are compiled with __launch_bounds__(CRM_MAX_P))
+  int CT = CRM_MAX_P / d->nx;
   if (CT > 16) CT = 16;
-  if (CT < 4) CT = 4;
   if (const char *e = getenv("CRM_B200_CT")) { int v = atoi(e); if (v >= 1 && v <= 32 && !(v & (v - 1))) CT = v; }
-  while (d->nx * CT > 512 && CT > 1) CT >>= 1;
-  if (d->nx * CT > 512) { g_init_err = "crm_b200_init: nx too large (nx <= 512)"; delete h; return 4; }
+  while (d->nx * CT > CRM_MAX_P && CT > 1) CT >>= 1;
+  if (CT < 1 || d->nx * CT > CRM_MAX_P) { g_init_err = "crm_b200_init: nx too large (nx <= 256)"; delete h; return 4; }
   h->CT = CT;
   h->ntiles = (d->ncrms + CT - 1) / CT;
   h->P = d->nx * CT;
@@ -208,12 +208,14 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   if (!micro_scalars(p.ms)) { g_init_err = "cannot compute gamma-function in precip_init"; crm_b200_free(h); return 10; }
 #ifndef CRM_EMU
   {
-    const int big = 96 * 1024;
+    const int big = 200 * 1024;
     cudaFuncSetAttribute(k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(k_epi_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(k_p8_micro, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(k_mpdata, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(k_prologue_fields, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_p7_diffuse, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_p3_mom, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   }
 #endif
   if (dev_sync()) { g_init_err = std::string("crm_b200_init: ") + dev_errstr(); crm_b200_free(h); return 11; }
@@ -410,7 +412,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
       if (dbg_stop == 1) { dbg_break = true; break; }
       LAUNCH(h, k_p2_sgs, ntiles, P, 0, p);
       if (dbg_stop == 2) { dbg_break = true; break; }
-      LAUNCH(h, k_p3_mom, ntiles, P, red_bytes(2), p);
+      LAUNCH(h, k_p3_mom, ntiles, P, CRM_P3_SMEM(P, CT, h->nzp), p);
       if (dbg_stop == 3) { dbg_break = true; break; }
       LAUNCH(h, k_p4_press_fwd, ntiles, P, (size_t)(P + 2 * nx) * 8, p);
       LAUNCH(h, k_p5_press_bwd, ntiles, P, (size_t)(2 * P + 2 * nx) * 8, p);
@@ -427,7 +429,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
       { int o_u = iu, o_a = ina, o_b = inb, o_c = inc; iu = o_c; ina = o_u; inb = o_a; inc = o_b; }
       p.u = h->ubuf[iu]; p.w = h->wbuf[iu];
       if (dbg_stop == 6) { dbg_break = true; break; }
-      LAUNCH(h, k_p7_diffuse, ntiles, P, red_bytes(4), p);
+      LAUNCH(h, k_p7_diffuse, ntiles, P, CRM_P7_SMEM(P, CT, h->nzp), p);
       if (dbg_stop == 7) { dbg_break = true; break; }
       if (icyc == 1) LAUNCH(h, k_precip_init, (ntiles * nzm * CT + 127) / 128, 128, 0, p);
       LAUNCH(h, k_reset_kminmax, slot_blocks, 128, 0, p);

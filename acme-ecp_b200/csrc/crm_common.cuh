@@ -23,6 +23,8 @@
 // REAL(4) literal promoted to double, as in the reference build without -r8
 #define R4(x) ((double)(x##f))
 
+#define CRM_MAX_P 256   // threads per block = nx * CT (one k-plane of one CRM tile)
+
 namespace crm {
 
 // ---- physical constants (CRM/params.F90:49-69 via shr_const_mod.F90:22-54) ----

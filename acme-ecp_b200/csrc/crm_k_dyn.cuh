@@ -36,7 +36,7 @@ __device__ __forceinline__ double ice_flux(const CrmP &p, long long fb, int P, i
 
 // zero.F90, buoyancy.F90:17-36, forcing.F90:38-73, crm_module.F90:766-777, damping.F90:60-110, ice_fall.F90:34-165
 // smem: CRM_RED_DOUBLES(3,P,CT) + 1 int
-__global__ void __launch_bounds__(512) k_p1_forcing(CrmP p) {
+__global__ void __launch_bounds__(CRM_MAX_P) k_p1_forcing(CrmP p) {
   CRM_TILE_SETUP
   CRM_DYN_SMEM(double, red);
   __shared__ int s_kd0;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(512) k_p1_forcing(CrmP p) {
 }
 
 // shear_prod2D.F90:20-94 (v == 0 in 2-D) + tke_full.F90:103-310 with dosmagor.  tk/tkh written for k <= nzm-1.
-__global__ void __launch_bounds__(512) k_p2_sgs(CrmP p) {
+__global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
   CRM_TILE_SETUP
   CRM_XNEIGH
   const int nzm = p.nzm;
@@ -218,12 +218,31 @@ __global__ void __launch_bounds__(512) k_p2_sgs(CrmP p) {
 }
 
 // advect2_mom_xy.F90:64-82, advect2_mom_z.F90:31-125, diffuse_mom2D.F90:38-158 (v == 0, fluxb* = fluxt* = 0).
-// smem: CRM_RED_DOUBLES(2,P,CT) (only used on the last sub-step for uwle/uwsb)
-__global__ void __launch_bounds__(512) k_p3_mom(CrmP p) {
+// u, w, tk, dudt(na), dwdt(na) stream through a 4-stage TMA plane ring (levels k, k+1 resident, 2 levels of prefetch);
+// the six grid profiles of the tile are staged in shared memory once.
+#define CRM_P3_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(5, 4, P) + CRM_PROF_BYTES(6, nzp, CT) + (size_t)CRM_RED_DOUBLES(2, P, CT) * 8)
+__global__ void __launch_bounds__(CRM_MAX_P) k_p3_mom(CrmP p) {
   CRM_TILE_SETUP
   CRM_XNEIGH
-  CRM_DYN_SMEM(double, red);
-  const int nzm = p.nzm, nz = p.nz;
+  CRM_DYN_SMEM(unsigned char, smraw);
+  const int nzm = p.nzm, nz = p.nz, npf = p.nzp * CT;
+  PlanePipe<5, 4> pipe;
+  pipe.src[0] = p.u + fb; pipe.src[1] = p.w + fb; pipe.src[2] = p.tk + fb; pipe.src[3] = p.du_a + fb; pipe.src[4] = p.dw_a + fb;
+  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(5, 4, P));
+  double *red = sprof + 6 * npf;
+  {
+    const double *const g[6] = {p.rho, p.adz, p.rhow, p.adzw, p.grdf_x, p.grdf_z};
+    stage_profiles<6>(sprof, g, tile, p.nzp, CT, tid, P);
+  }
+  pipe.init(smraw, P, tid);
+#define S_RHO(k) sprof[0 * npf + (k)*CT + lane]
+#define S_ADZ(k) sprof[1 * npf + (k)*CT + lane]
+#define S_RHOW(k) sprof[2 * npf + (k)*CT + lane]
+#define S_ADZW(k) sprof[3 * npf + (k)*CT + lane]
+#define S_GRDX(k) sprof[4 * npf + (k)*CT + lane]
+#define S_GRDZ(k) sprof[5 * npf + (k)*CT + lane]
+  if (tid == 0) for (int L = 1; L <= imin(nz, 3); L++) pipe.issue(L);
+  pipe.wait(1);
   const double dz = p.dz[cb], dx = p.dx;
   const double dx25 = 0.25 / dx, dz25 = 1. / (4. * dz);
   const double rdx2 = 1. / dx / dx, rdx25 = 0.25 * rdx2;
@@ -234,11 +253,17 @@ __global__ void __launch_bounds__(512) k_p3_mom(CrmP p) {
   double dwh_adv = 0., dwh_dif = 0.;
   for (int k = 1; k <= nzm; k++) {
     const int kc = k + 1, kcu = imin(kc, nzm);
-    const double u_i = F3(p.u, k), u_im = F3X(p.u, k, tm1), u_ip = F3X(p.u, k, tp1);
-    const double w_k = F3(p.w, k), w_kc = F3(p.w, kc);
-    const double w_kc_m = F3X(p.w, kc, tm1), w_kc_p = F3X(p.w, kc, tp1);
-    const double rho_k = PF(p.rho, k), adz_k = PF(p.adz, k);
-    double du = F3(p.du_a, k);
+    __syncthreads();
+    if (tid == 0 && k + 3 <= nz) pipe.issue(k + 3);
+    pipe.wait(kc);
+    const double *U_k = pipe.plane(0, k), *U_c = pipe.plane(0, kc), *U_u = pipe.plane(0, kcu);
+    const double *W_k = pipe.plane(1, k), *W_c = pipe.plane(1, kc);
+    const double *TK_k = pipe.plane(2, k), *TK_c = pipe.plane(2, kc), *TK_u = pipe.plane(2, kcu);
+    const double u_i = U_k[tid], u_im = U_k[tm1], u_ip = U_k[tp1];
+    const double w_k = W_k[tid], w_kc = W_c[tid];
+    const double w_kc_m = W_c[tm1], w_kc_p = W_c[tp1];
+    const double rho_k = S_RHO(k), adz_k = S_ADZ(k);
+    double du = pipe.plane(3, k)[tid];
     // ---- advect2_mom_xy (2-D branch)
     {
       double fu1 = dx25 * (u_i + u_im) * (u_im + u_i);
@@ -248,17 +273,17 @@ __global__ void __launch_bounds__(512) k_p3_mom(CrmP p) {
     // contribution to dwdt(kc) from this level (applied next iteration, in reference order)
     double dwh_adv_next, dwh_dif_next;
     {
-      const double irho = 1. / (PF(p.rhow, kc) * PF(p.adzw, kc));
-      const double rho_u = PF(p.rho, kcu), adz_u = PF(p.adz, kcu);
-      const double ucu_i = F3(p.u, kcu), ucu_ip = F3X(p.u, kcu, tp1);
+      const double irho = 1. / (S_RHOW(kc) * S_ADZW(kc));
+      const double rho_u = S_RHO(kcu), adz_u = S_ADZ(kcu);
+      const double ucu_i = U_u[tid], ucu_ip = U_u[tp1];
       double fw1 = dx25 * (u_i * rho_k * adz_k + ucu_i * rho_u * adz_u) * (w_kc_m + w_kc);
       double fw2 = dx25 * (u_ip * rho_k * adz_k + ucu_ip * rho_u * adz_u) * (w_kc + w_kc_p);
       dwh_adv_next = irho * (fw2 - fw1);
       // diffuse_mom2D horizontal part: fw(i,k), fw(i-1,k)
-      const double dxz = dx / (dz * PF(p.adzw, kc));
-      const double rdx251 = rdx25 * PF(p.grdf_x, k);
-      const double tk_i = F3(p.tk, k), tk_ip = F3X(p.tk, k, tp1), tk_im = F3X(p.tk, k, tm1);
-      const double tku_i = F3(p.tk, kcu), tku_ip = F3X(p.tk, kcu, tp1), tku_im = F3X(p.tk, kcu, tm1);
+      const double dxz = dx / (dz * S_ADZW(kc));
+      const double rdx251 = rdx25 * S_GRDX(k);
+      const double tk_i = TK_k[tid], tk_ip = TK_k[tp1], tk_im = TK_k[tm1];
+      const double tku_i = TK_u[tid], tku_ip = TK_u[tp1], tku_im = TK_u[tm1];
       double tkx = rdx251 * (tk_i + tk_ip + tku_i + tku_ip);
       double fwi = -tkx * (w_kc_p - w_kc + (ucu_ip - u_ip) * dxz);
       tkx = rdx251 * (tk_im + tk_i + tku_im + tku_i);
@@ -268,17 +293,17 @@ __global__ void __launch_bounds__(512) k_p3_mom(CrmP p) {
     // ---- advect2_mom_z
     double fuz_kc = 0.;
     if (kc <= nzm) {
-      const double rhoi = dz25 * PF(p.rhow, kc);
+      const double rhoi = dz25 * S_RHOW(kc);
       const double www = rhoi * (w_kc + w_kc_m);
-      fuz_kc = www * (F3(p.u, kc) + u_i);
+      fuz_kc = www * (U_c[tid] + u_i);
     }
     const double rhoi_s = 1. / (rho_k * adz_k);
     du = du - (fuz_kc - fuz_k) * rhoi_s;
-    const double fwz_k = dz25 * (w_kc * PF(p.rhow, kc) + w_k * PF(p.rhow, k)) * (w_kc + w_k);
+    const double fwz_k = dz25 * (w_kc * S_RHOW(kc) + w_k * S_RHOW(k)) * (w_kc + w_k);
     // ---- diffuse_mom2D: horizontal part for u
-    const double tk_i = F3(p.tk, k), tk_im = F3X(p.tk, k, tm1);
+    const double tk_i = TK_k[tid], tk_im = TK_k[tm1];
     {
-      const double rdx21 = rdx2 * PF(p.grdf_x, k);
+      const double rdx21 = rdx2 * S_GRDX(k);
       double fui = -2. * (rdx21 * tk_i) * (u_ip - u_i);
       double fum = -2. * (rdx21 * tk_im) * (u_i - u_im);
       du = du - (fui - fum);
@@ -286,24 +311,24 @@ __global__ void __launch_bounds__(512) k_p3_mom(CrmP p) {
     // ---- diffuse_mom2D: vertical part
     double fuv_kc = 0., fwv_kc;
     if (k <= nzm - 1) {
-      const double rdz2 = rdz * rdz * PF(p.grdf_z, k), rdz25 = 0.25 * rdz2;
-      const double iadz = 1. / adz_k, iadzw = 1. / PF(p.adzw, kc);
+      const double rdz2 = rdz * rdz * S_GRDZ(k), rdz25 = 0.25 * rdz2;
+      const double iadz = 1. / adz_k, iadzw = 1. / S_ADZW(kc);
       double tkz = rdz2 * tk_i;
       fwv_kc = -2. * tkz * (w_kc - w_k) * rho_k * iadz;
-      tkz = rdz25 * (tk_i + tk_im + F3(p.tk, kc) + F3X(p.tk, kc, tm1));
-      fuv_kc = -tkz * ((F3(p.u, kc) - u_i) * iadzw + (w_kc - w_kc_m) * dzx) * PF(p.rhow, kc);
+      tkz = rdz25 * (tk_i + tk_im + TK_c[tid] + TK_c[tm1]);
+      fuv_kc = -tkz * ((U_c[tid] - u_i) * iadzw + (w_kc - w_kc_m) * dzx) * S_RHOW(kc);
     } else {   // k == nzm: fw(.,nz) (diffuse_mom2D.F90:119-123); fu(.,nz) = fluxtu*... = 0
-      const double rdz2 = rdz * rdz * PF(p.grdf_z, nzm - 1);
-      double tkz = rdz2 * PF(p.grdf_z, nzm) * tk_i;
+      const double rdz2 = rdz * rdz * S_GRDZ(nzm - 1);
+      double tkz = rdz2 * S_GRDZ(nzm) * tk_i;
       fwv_kc = -2. * tkz * (w_kc - w_k) / adz_k * rho_k;
     }
     du = du - (fuv_kc - fuv_k) * rhoi_s;
     F3(p.du_a, k) = du;
     // ---- dwdt(k), k >= 2, contributions in reference order: xy-advection, z-advection, horizontal diffusion, vertical diffusion
     if (k >= 2) {
-      double dw = F3(p.dw_a, k);
+      double dw = pipe.plane(4, k)[tid];
       dw = dw - dwh_adv;
-      const double rhoi_w = 1. / (PF(p.rhow, k) * PF(p.adzw, k));
+      const double rhoi_w = 1. / (S_RHOW(k) * S_ADZW(k));
       dw = dw - (fwz_k - fwz_km1) * rhoi_w;
       dw = dw - dwh_dif;
       dw = dw - (fwv_kc - fwv_k) * rhoi_w;
@@ -317,7 +342,12 @@ __global__ void __launch_bounds__(512) k_p3_mom(CrmP p) {
     fuz_k = fuz_kc; fwz_km1 = fwz_k; fuv_k = fuv_kc; fwv_k = fwv_kc;
     dwh_adv = dwh_adv_next; dwh_dif = dwh_dif_next;
   }
-  (void)nz;
+#undef S_RHO
+#undef S_ADZ
+#undef S_RHOW
+#undef S_ADZW
+#undef S_GRDX
+#undef S_GRDZ
 }
 
 // pressure.F90:165-237 coefficients for one (CRM, level)
@@ -330,7 +360,7 @@ __device__ __forceinline__ void tri_ac(const CrmP &p, int pb, int CT, int k, dou
 __device__ __forceinline__ int mode_of(int i, int nx) { return (i == 1) ? nx / 2 : i / 2; }
 
 // alfa(k) of the Thomas algorithm depends only on the grid: computed once per crm() call (pressure.F90:217-231)
-__global__ void __launch_bounds__(512) k_press_alfa(CrmP p) {
+__global__ void __launch_bounds__(CRM_MAX_P) k_press_alfa(CrmP p) {
   CRM_TILE_SETUP
   const int nzm = p.nzm, m = mode_of(i, p.nx);
   const double dz = p.dz[cb];
@@ -354,7 +384,7 @@ __global__ void __launch_bounds__(512) k_press_alfa(CrmP p) {
 // press_rhs.F90:80-102 + forward transform (fft.F90:49-53 convention) + forward sweep (pressure.F90:202-233).
 // The transform is a direct length-nx DFT per (CRM, level) in shared memory.
 // smem: P + 2*nx doubles
-__global__ void __launch_bounds__(512) k_p4_press_fwd(CrmP p) {
+__global__ void __launch_bounds__(CRM_MAX_P) k_p4_press_fwd(CrmP p) {
   CRM_TILE_SETUP
   CRM_XNEIGH
   CRM_DYN_SMEM(double, sm);
@@ -415,7 +445,7 @@ __global__ void __launch_bounds__(512) k_p4_press_fwd(CrmP p) {
 
 // pressure.F90:234-305 (back substitution, inverse transform) + press_grad.F90:20-35 + adams.F90:19-38.
 // Marches downward; w(k+1) is finalised when p(k) is known.  smem: 2*P + 2*nx doubles
-__global__ void __launch_bounds__(512) k_p5_press_bwd(CrmP p) {
+__global__ void __launch_bounds__(CRM_MAX_P) k_p5_press_bwd(CrmP p) {
   CRM_TILE_SETUP
   CRM_XNEIGH
   CRM_DYN_SMEM(double, sm);

@@ -19,7 +19,7 @@ __device__ __forceinline__ double min3(double a, double b, double c) { return dm
 // FCT ratios mx/mn(ka-1);  C: limited fluxes and final update of level ka-2.  U = umf, W = wmf (mass-flux
 // velocities of adams).  fadv/flux: optional profile outputs (mkadv/mkwle), written only when `stats`.
 // smem: 9*P doubles (+ CRM_RED_DOUBLES(2,P,CT) when stats)
-__global__ void __launch_bounds__(512) k_mpdata(CrmP p, double *f, double *fadv, double *flux, int stats) {
+__global__ void __launch_bounds__(CRM_MAX_P) k_mpdata(CrmP p, double *f, double *fadv, double *flux, int stats) {
   CRM_TILE_SETUP
   CRM_XNEIGH
   CRM_DYN_SMEM(double, sm);
@@ -160,7 +160,7 @@ __device__ __forceinline__ double term_vel_qp(const MicroScalars &m, double qplo
 }
 
 // microphysics.F90:578-640: fall speed of every cell + batch-global prec_cfl.  smem: P doubles.
-__global__ void __launch_bounds__(512) k_precip_a(CrmP p) {
+__global__ void __launch_bounds__(CRM_MAX_P) k_precip_a(CrmP p) {
   CRM_TILE_SETUP
   CRM_DYN_SMEM(double, red);
   const double dz = p.dz[cb];
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(512) k_precip_a(CrmP p) {
 // microphysics.F90:642-830: nprec sub-iterations of the 1-D MPDATA/FCT sedimentation, one thread per column with a
 // sliding register window (q, wp, tq 3 levels ahead of the level being finalised).
 // smem: CRM_RED_DOUBLES(2,P,CT)
-__global__ void __launch_bounds__(512) k_precip_b(CrmP p) {
+__global__ void __launch_bounds__(CRM_MAX_P) k_precip_b(CrmP p) {
   CRM_TILE_SETUP
   CRM_DYN_SMEM(double, red);
   const int nzm = p.nzm;
@@ -277,41 +277,57 @@ __global__ void __launch_bounds__(512) k_precip_b(CrmP p) {
 }
 
 // diffuse_scalar2D.F90:70-138 + diffuse_scalar.F90:55-70 for t, qt, qp in one pass (fluxb = fluxt = 0).
-// smem: CRM_RED_DOUBLES(4,P,CT) (stats only)
-__global__ void __launch_bounds__(512) k_p7_diffuse(CrmP p) {
+// Inputs stream through a 4-stage TMA plane ring (tkh, t, qt, qp; levels k and k+1 resident, 2 levels of prefetch).
+#define CRM_P7_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(4, 4, P) + CRM_PROF_BYTES(6, nzp, CT) + (size_t)CRM_RED_DOUBLES(4, P, CT) * 8)
+__global__ void __launch_bounds__(256) k_p7_diffuse(CrmP p) {
   CRM_TILE_SETUP
   CRM_XNEIGH
-  CRM_DYN_SMEM(double, red);
-  const int nzm = p.nzm;
+  CRM_DYN_SMEM(unsigned char, smraw);
+  const int nzm = p.nzm, npf = p.nzp * CT;
+  PlanePipe<4, 4> pipe;
+  pipe.src[0] = p.tkh + fb; pipe.src[1] = p.t + fb; pipe.src[2] = p.qt + fb; pipe.src[3] = p.qp + fb;
+  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(4, 4, P));
+  double *red = sprof + 6 * npf;
+  {
+    const double *const g[6] = {p.grdf_x, p.adz, p.rho, p.rhow, p.adzw, p.grdf_z};
+    stage_profiles<6>(sprof, g, tile, p.nzp, CT, tid, P);
+  }
+  pipe.init(smraw, P, tid);   // (barrier: profiles visible)
+#define SPF(r, k) sprof[(r) * npf + (k) * CT + lane]
+  if (tid == 0) for (int L = 1; L <= imin(nzm, 3); L++) pipe.issue(L);
+  pipe.wait(1);
   const double dz = p.dz[cb];
   const double rdx2 = 1. / (p.dx * p.dx);
   const double rdz2 = 1. / (dz * dz);
   double *fld[3] = {p.t, p.qt, p.qp};
   double flz_km1[3] = {0., 0., 0.};   // flx(.,0) = fluxb*rdz*rhow(1) = 0
   for (int k = 1; k <= nzm; k++) {
-    const double tkh_i = F3(p.tkh, k), tkh_m = F3X(p.tkh, k, tm1), tkh_p = F3X(p.tkh, k, tp1);
-    const double rdx5 = 0.5 * rdx2 * PF(p.grdf_x, k);
-    const double rhoi2 = 1. / (PF(p.adz, k) * PF(p.rho, k));
+    __syncthreads();   // level k-1 fully consumed: its ring slot may be refilled
+    if (tid == 0 && k + 3 <= nzm) pipe.issue(k + 3);
+    if (k + 1 <= nzm) pipe.wait(k + 1);
+    const double *tkh_k = pipe.plane(0, k), *tkh_c = pipe.plane(0, k + 1);
+    const double tkh_i = tkh_k[tid], tkh_m = tkh_k[tm1], tkh_p = tkh_k[tp1];
+    const double rdx5 = 0.5 * rdx2 * SPF(0, k);
+    const double rhoi2 = 1. / (SPF(1, k) * SPF(2, k));
     double tkz = 0., rhoi = 0.;
     if (k <= nzm - 1) {
-      rhoi = PF(p.rhow, k + 1) / PF(p.adzw, k + 1);
-      const double rdz5 = 0.5 * rdz2 * PF(p.grdf_z, k);
-      tkz = rdz5 * (tkh_i + F3(p.tkh, k + 1));
+      rhoi = SPF(3, k + 1) / SPF(4, k + 1);
+      const double rdz5 = 0.5 * rdz2 * SPF(5, k);
+      tkz = rdz5 * (tkh_i + tkh_c[tid]);
     }
     double fnew[3], fold[3], flz[3];
 #pragma unroll
     for (int s = 0; s < 3; s++) {
-      const double *f = fld[s];
-      const double f_i = F3(f, k), f_m = F3X(f, k, tm1), f_p = F3X(f, k, tp1);
+      const double *f_k = pipe.plane(1 + s, k), *f_c = pipe.plane(1 + s, k + 1);
+      const double f_i = f_k[tid], f_m = f_k[tm1], f_p = f_k[tp1];
       const double flx_i = -(rdx5 * (tkh_i + tkh_p)) * (f_p - f_i);
       const double flx_m = -(rdx5 * (tkh_m + tkh_i)) * (f_i - f_m);
       double dfdt = 0. - (flx_i - flx_m);
-      flz[s] = (k <= nzm - 1) ? -tkz * (F3(f, k + 1) - f_i) * rhoi : 0.;
+      flz[s] = (k <= nzm - 1) ? -tkz * (f_c[tid] - f_i) * rhoi : 0.;
       dfdt = p.dtn * (dfdt - (flz[s] - flz_km1[s]) * rhoi2);
       fold[s] = f_i;
       fnew[s] = f_i + dfdt;
     }
-    __syncthreads();   // all neighbour reads of level k are done before anyone overwrites it
 #pragma unroll
     for (int s = 0; s < 3; s++) fld[s][fb + (long long)(k - 1) * P + tid] = fnew[s];
     if (p.last_substep) {   // mkdiff (fdiff) and mkwsb (flux at the lower face of level k) for qt, qp
@@ -322,6 +338,7 @@ __global__ void __launch_bounds__(512) k_p7_diffuse(CrmP p) {
 #pragma unroll
     for (int s = 0; s < 3; s++) flz_km1[s] = flz[s];
   }
+#undef SPF
 }
 
 // cloud.F90:29-112 for one cell; returns tabs1, updates q, qp, qn
@@ -462,7 +479,7 @@ __device__ inline void precip_proc_cell(const CrmP &p, int pb, int CT, int k, do
 // micro_proc (microphysics.F90:292-329: cloud, precip_proc, micro_diagnose) and, when do_diag, diagnose.F90:37-104
 // (tabs, slab means) + the kmin/kmax scan of ice_fall.F90:34-47 for the NEXT sub-step.
 // Plane kernel: one block per (tile, level).  smem: CRM_RED_DOUBLES(9,P,CT) + 2*CT ints
-__global__ void __launch_bounds__(512) k_p8_micro(CrmP p, int do_micro, int do_diag) {
+__global__ void __launch_bounds__(CRM_MAX_P) k_p8_micro(CrmP p, int do_micro, int do_diag) {
   const int tid = threadIdx.x, P = p.P, CT = p.CT;
   const int tile = blockIdx.x / p.nzm, k = blockIdx.x - tile * p.nzm + 1;
   const int i = tid / CT, lane = tid - i * CT;
@@ -515,7 +532,7 @@ __global__ void k_reset_kminmax(CrmP p) {
 
 // accelerate_crm.F90:166-225: horizontal means, MSA tendencies, batch-global ceaseflag.  Plane kernel.
 // smem: CRM_RED_DOUBLES(3,P,CT)
-__global__ void __launch_bounds__(512) k_msa_a(CrmP p) {
+__global__ void __launch_bounds__(CRM_MAX_P) k_msa_a(CrmP p) {
   const int tid = threadIdx.x, P = p.P, CT = p.CT;
   const int tile = blockIdx.x / p.nzm, k = blockIdx.x - tile * p.nzm + 1;
   const int i = tid / CT, lane = tid - i * CT;
@@ -535,7 +552,7 @@ __global__ void __launch_bounds__(512) k_msa_a(CrmP p) {
 }
 
 // accelerate_crm.F90:250-352: apply the tendencies, fix negative moisture.  Plane kernel.  smem: CRM_RED_DOUBLES(2,P,CT)
-__global__ void __launch_bounds__(512) k_msa_b(CrmP p) {
+__global__ void __launch_bounds__(CRM_MAX_P) k_msa_b(CrmP p) {
   const int tid = threadIdx.x, P = p.P, CT = p.CT;
   const int tile = blockIdx.x / p.nzm, k = blockIdx.x - tile * p.nzm + 1;
   const int i = tid / CT, lane = tid - i * CT;

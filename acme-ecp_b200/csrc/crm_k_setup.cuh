@@ -1,6 +1,7 @@
 // crm_k_setup.cuh -- boundary transposes and the prologue of crm() (reference CRM/crm_module.F90:286-681).
 #pragma once
 #include "crm_common.cuh"
+#include "crm_pipe.cuh"
 
 namespace crm {
 
@@ -155,7 +156,7 @@ __device__ __forceinline__ void micro_diag_cell(const MicroScalars &ms, double q
 
 // crm_module.F90:400-417, 477-581: clamp, micro_init->micro_diagnose, t from tabs, slab means, LS tendencies.
 // Block per tile, k-march.  smem: CRM_RED_DOUBLES(10, P, CT).
-__global__ void __launch_bounds__(512) k_prologue_fields(CrmP p) {
+__global__ void __launch_bounds__(CRM_MAX_P) k_prologue_fields(CrmP p) {
   CRM_TILE_SETUP
   CRM_DYN_SMEM(double, red);
   const int nzm = p.nzm;
@@ -279,7 +280,7 @@ __global__ void k_setperturb(CrmP p, const double *rnd) {
 // kurant.F90:9-64 + sgs.F90:329-372.  max over i commutes with the per-level scaling, so every thread folds its own
 // column and only one block max + one atomicMax on the (non-negative) double bit pattern are needed.
 // smem: P doubles.
-__global__ void __launch_bounds__(512) k_kurant(CrmP p) {
+__global__ void __launch_bounds__(CRM_MAX_P) k_kurant(CrmP p) {
   CRM_TILE_SETUP
   CRM_DYN_SMEM(double, red);
   const double idx = 1. / p.dx;

@@ -8,7 +8,7 @@ namespace crm {
 // Per-nstep statistics.  Block per tile; marches from the top (the reference's cwp scan uses kk = nz-k, and books
 // the cloud-top hit at GCM level l(k), i.e. at CRM level k = nz-kk: quirk kept).
 // smem: CRM_RED_DOUBLES(10,P,CT) + 5*P doubles
-__global__ void __launch_bounds__(512) k_stats(CrmP p) {
+__global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
   CRM_TILE_SETUP
   CRM_DYN_SMEM(double, sm);
   double *red = sm, *srad = sm + CRM_RED_DOUBLES(10, P, CT);
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(512) k_stats(CrmP p) {
 // Epilogue slab sums (crm_module.F90:1147-1183, 1314-1356, 1517-1584).  Plane kernel; results in the scratch
 // profile block esum (14 profiles).  smem: CRM_RED_DOUBLES(14,P,CT)
 #define CRM_NESUM 14
-__global__ void __launch_bounds__(512) k_epi_sums(CrmP p, double *esum) {
+__global__ void __launch_bounds__(CRM_MAX_P) k_epi_sums(CrmP p, double *esum) {
   const int tid = threadIdx.x, P = p.P, CT = p.CT;
   const int tile = blockIdx.x / p.nzm, k = blockIdx.x - tile * p.nzm + 1;
   const int i = tid / CT, lane = tid - i * CT;
@@ -126,7 +126,7 @@ struct ExtOut {   // device staging of the (ld,plev) / (ld) outputs; same member
 };
 
 // precsfc -> precc/precl split and prec_crm (crm_module.F90:1417-1481).  Block per tile.  smem: CRM_RED_DOUBLES(4,P,CT)
-__global__ void __launch_bounds__(512) k_epi_precip(CrmP p, ExtOut o, double dt_eff) {
+__global__ void __launch_bounds__(CRM_MAX_P) k_epi_precip(CrmP p, ExtOut o, double dt_eff) {
   CRM_TILE_SETUP
   CRM_DYN_SMEM(double, red);
   const double dz = p.dz[cb];
