@@ -102,6 +102,7 @@ static void ktime_add(std::vector<KTime> &v, const char *name, double ms) {
   for (auto &k : v) if (k.name == name || !strcmp(k.name, name)) { k.ms += ms; k.n++; return; }
   v.push_back({name, ms, 1});
 }
+static std::string kname(const char *s) { std::string n(s); size_t q = n.find('<'); return q == std::string::npos ? n : n.substr(0, q); }
 #define LAUNCH(h, kern, grid, block, smem, ...)                 \
   do {                                                          \
     if ((h)->ktiming) (h)->ktimer.start();                      \
@@ -183,7 +184,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
                      &p.accrsc, &p.accrsi, &p.accrrc, &p.coefice, &p.accrgc, &p.accrgi, &p.evaps1, &p.evaps2, &p.evapr1, &p.evapr2, &p.evapg1, &p.evapg2,
                      &p.precflux, &p.qpfall, &p.qpsrc, &p.qpevp, &p.uwle, &p.uwsb,
                      &p.mkwle1, &p.mkwle2, &p.mkwsb1, &p.mkwsb2, &p.mkadv1, &p.mkadv2, &p.mkdiff1, &p.mkdiff2,
-                     &p.acc_t, &p.acc_q, &p.acc_u,
+                     &p.acc_t, &p.acc_q, &p.acc_u, &p.tri_a, &p.tri_c,
                      &p.s_cld, &p.s_cldtop, &p.s_gicewp, &p.s_gliqwp, &p.s_mcup, &p.s_mcdn, &p.s_mcuup, &p.s_mcudn, &p.s_mui, &p.s_mdi})
     PRF(*f);
   for (double **f : {&p.dz, &p.z0, &p.colprec0, &p.colprecs0, &p.s_cltot, &p.s_clhgh, &p.s_clmed, &p.s_cllow}) SL(*f);
@@ -216,6 +217,15 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
     cudaFuncSetAttribute(k_prologue_fields, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(k_p7_diffuse, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(k_p3_mom, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_p1_forcing, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_p2_sgs, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_kurant, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_precip_a, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+#define PRESS_ATTR(NXV)                                                                              \
+  cudaFuncSetAttribute(k_p4_press_fwd<NXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);       \
+  cudaFuncSetAttribute(k_p5_press_bwd<NXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    PRESS_ATTR(8) PRESS_ATTR(16) PRESS_ATTR(32) PRESS_ATTR(64) PRESS_ATTR(128) PRESS_ATTR(256)
+#undef PRESS_ATTR
   }
 #endif
   if (dev_sync()) { g_init_err = std::string("crm_b200_init: ") + dev_errstr(); crm_b200_free(h); return 11; }
@@ -235,7 +245,7 @@ extern "C" const char *crm_b200_kernel_times(void *handle) {
   h->ktime_report.clear();
   char line[256];
   for (auto &k : h->ktimes) {
-    snprintf(line, sizeof(line), "%s %.6f %lld\n", k.name, k.ms, k.n);
+    snprintf(line, sizeof(line), "%s %.6f %lld\n", kname(k.name).c_str(), k.ms, k.n);
     h->ktime_report += line;
   }
   return h->ktime_report.c_str();
@@ -383,7 +393,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   while (nstep < nstop) {
     nstep++;
     dev_zero(p.cfl_bits, 8);
-    LAUNCH(h, k_kurant, ntiles, P, (size_t)P * 8, p);
+    LAUNCH(h, k_kurant, ntiles, P, CRM_KURANT_SMEM(P, CT, h->nzp), p);
     unsigned long long bits = 0;
     if (dev_copy2d(&bits, 8, p.cfl_bits, 8, 8, 1, 0)) return fail(h, 27, std::string("crm_b200_run: kurant readback failed: ") + dev_errstr());
     double cfl; memcpy(&cfl, &bits, 8);
@@ -408,14 +418,19 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
       p.u = h->ubuf[iu]; p.w = h->wbuf[iu];
       p.du_a = h->ubuf[ina]; p.du_b = h->ubuf[inb]; p.du_c = h->ubuf[inc];
       p.dw_a = h->wbuf[ina]; p.dw_b = h->wbuf[inb]; p.dw_c = h->wbuf[inc];
-      LAUNCH(h, k_p1_forcing, ntiles, P, red_bytes(3), p);
+      LAUNCH(h, k_p1_forcing, ntiles, P, CRM_P1_SMEM(P, CT, h->nzp), p);
       if (dbg_stop == 1) { dbg_break = true; break; }
-      LAUNCH(h, k_p2_sgs, ntiles, P, 0, p);
+      LAUNCH(h, k_p2_sgs, ntiles, P, CRM_P2_SMEM(P, CT, h->nzp), p);
       if (dbg_stop == 2) { dbg_break = true; break; }
       LAUNCH(h, k_p3_mom, ntiles, P, CRM_P3_SMEM(P, CT, h->nzp), p);
       if (dbg_stop == 3) { dbg_break = true; break; }
-      LAUNCH(h, k_p4_press_fwd, ntiles, P, (size_t)(P + 2 * nx) * 8, p);
-      LAUNCH(h, k_p5_press_bwd, ntiles, P, (size_t)(2 * P + 2 * nx) * 8, p);
+#define PRESS_CASE(NXV)                                                                           \
+  case NXV:                                                                                       \
+    LAUNCH(h, k_p4_press_fwd<NXV>, ntiles, P, CRM_P4_SMEM(P, CT, h->nzp, NXV), p);                \
+    LAUNCH(h, k_p5_press_bwd<NXV>, ntiles, P, CRM_P5_SMEM(P, CT, h->nzp, NXV), p);                \
+    break;
+      switch (nx) { PRESS_CASE(8) PRESS_CASE(16) PRESS_CASE(32) PRESS_CASE(64) PRESS_CASE(128) PRESS_CASE(256) default: return fail(h, 33, "unsupported nx"); }
+#undef PRESS_CASE
       if (dbg_stop == 4) { dbg_break = true; break; }
       // advect_all_scalars.F90:32-64
       LAUNCH(h, k_mpdata, ntiles, P, smem_mp, p, p.t, (double *)nullptr, (double *)nullptr, 0);
@@ -423,7 +438,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
       LAUNCH(h, k_mpdata, ntiles, P, smem_mp + red_bytes(2), p, p.qp, p.mkadv2, p.mkwle2, 1);
       if (dbg_stop == 5) { dbg_break = true; break; }
       dev_zero(p.prec_cfl_bits, 8);
-      LAUNCH(h, k_precip_a, ntiles, P, (size_t)P * 8, p);
+      LAUNCH(h, k_precip_a, ntiles, P, CRM_PRECIPA_SMEM(P, CT, h->nzp), p);
       LAUNCH(h, k_precip_b, ntiles, P, red_bytes(2), p);
       // uvw.F90: u <- dudt(nc) is a role rotation of the buffers (with the AB rotation of crm_module.F90:884-887)
       { int o_u = iu, o_a = ina, o_b = inb, o_c = inc; iu = o_c; ina = o_u; inb = o_a; inc = o_b; }

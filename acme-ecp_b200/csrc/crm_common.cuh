@@ -77,6 +77,7 @@ struct CrmP {
   double *umf, *wmf;                     // half-step mass-flux velocities (adams.F90:28-34)
   double *t, *qt, *qp, *qn, *tabs, *qv, *qcl, *qci, *qpl, *qpi, *tk, *tkh, *tke;
   double *pbeta, *palfa;                 // tridiagonal scratch (pressure.F90:202-237)
+  double *tri_a, *tri_c;                 // profiles: tridiagonal coefficients a(k), c(k) (pressure.F90:165-170)
   double *wp;                            // precipitation fall speed scratch (microphysics.F90:619)
   double *qrad;                          // (tile, k, i_rad, lane)
   double *rad_t, *rad_qv, *rad_qc, *rad_qi, *rad_cld;   // accumulators, same layout as qrad

@@ -15,15 +15,18 @@ namespace crm {
   const int tp1 = (i == p.nx - 1) ? tid - P + CT : tid + CT;          \
   (void)tm1; (void)tp1;
 
-// ice_fall.F90:82-116: limited sedimentation flux of cloud ice at level kk (1..nz)
-__device__ __forceinline__ double ice_flux(const CrmP &p, long long fb, int P, int tid, int pb, int CT, int kk, int kmin, int kmax, double dz) {
+// ice_fall.F90:82-116: limited sedimentation flux of cloud ice at level kk (1..nz).  Q = plane ring of qci,
+// sp_* = staged profiles (rho, adz).
+template <class PipeQ>
+__device__ __forceinline__ double ice_flux(const CrmP &p, const PipeQ &Q, const double *s_rho, const double *s_adz, int tid, int lane, int CT,
+                                           int kk, int kmin, int kmax, double dz) {
   if (kk < imax(1, kmin - 1) || kk > kmax) return 0.;
   const int nzm = p.nzm;
   int kc = imin(nzm, kk + 1), kb = imax(1, kk - 1);
-  double coef = p.dtn / (0.5 * (PF(p.adz, kb) + PF(p.adz, kk)) * dz);
-  double qiu = PF(p.rho, kc) * F3(p.qci, kc);
-  double qic = PF(p.rho, kk) * F3(p.qci, kk);
-  double qid = PF(p.rho, kb) * F3(p.qci, kb);
+  double coef = p.dtn / (0.5 * (s_adz[kb * CT + lane] + s_adz[kk * CT + lane]) * dz);
+  double qiu = s_rho[kc * CT + lane] * Q.plane(0, kc)[tid];
+  double qic = s_rho[kk * CT + lane] * Q.plane(0, kk)[tid];
+  double qid = s_rho[kb * CT + lane] * Q.plane(0, kb)[tid];
   double vt_ice = dmin(R4(0.4), R4(8.66) * pow(dmax(0., qic) + R4(1.e-10), R4(0.24)));
   double tmp_phi;
   if (fabs(qic - qid) < R4(1.0e-25)) tmp_phi = 0.;
@@ -35,39 +38,65 @@ __device__ __forceinline__ double ice_flux(const CrmP &p, long long fb, int P, i
 }
 
 // zero.F90, buoyancy.F90:17-36, forcing.F90:38-73, crm_module.F90:766-777, damping.F90:60-110, ice_fall.F90:34-165
-// smem: CRM_RED_DOUBLES(3,P,CT) + 1 int
+// Two TMA plane rings: qci (levels k..k+2 resident, 6 stages) and the nine single-level inputs (3 stages).
+#define CRM_P1_NPROF 11
+#define CRM_P1_SMEM(P, CT, nzp) \
+  (CRM_PIPE_BYTES(1, 6, P) + CRM_PIPE_BYTES(9, 3, P) + CRM_PROF_BYTES(CRM_P1_NPROF, nzp, CT) + (size_t)CRM_RED_DOUBLES(3, P, CT) * 8)
 __global__ void __launch_bounds__(CRM_MAX_P) k_p1_forcing(CrmP p) {
   CRM_TILE_SETUP
-  CRM_DYN_SMEM(double, red);
+  CRM_DYN_SMEM(unsigned char, smraw);
   __shared__ int s_kd0;
-  const int nzm = p.nzm, nz = p.nz;
+  const int nzm = p.nzm, nz = p.nz, npf = p.nzp * CT;
+  PlanePipe<1, 6> Q;
+  PlanePipe<9, 3> A;
+  Q.src[0] = p.qci + fb;
+  A.src[0] = p.tabs + fb; A.src[1] = p.qv + fb; A.src[2] = p.qcl + fb; A.src[3] = p.qpl + fb; A.src[4] = p.qpi + fb;
+  A.src[5] = p.t + fb; A.src[6] = p.qt + fb; A.src[7] = p.u + fb; A.src[8] = p.w + fb;
+  unsigned char *sm2 = smraw + CRM_PIPE_BYTES(1, 6, P);
+  double *sprof = (double *)(sm2 + CRM_PIPE_BYTES(9, 3, P));
+  double *red = sprof + CRM_P1_NPROF * npf;
+  {
+    const double *const g[CRM_P1_NPROF] = {p.rho, p.adz, p.tabs0, p.qv0, p.qn0, p.qp0, p.bet, p.ttend, p.qtend, p.utend, p.tau};
+    stage_profiles<CRM_P1_NPROF>(sprof, g, tile, p.nzp, CT, tid, P);
+  }
+  const double *s_rho = sprof, *s_adz = sprof + npf;
+#define SPF(r, k) sprof[(r) * npf + (k) * CT + lane]
   const double dz = p.dz[cb], dtn = p.dtn;
   const int ndamp = p.ndamp[cb], kmin = p.kmin[cb], kmax = p.kmax[cb];
   if (tid == 0) s_kd0 = nzm;
-  __syncthreads();
+  Q.init(smraw, P, tid);
+  A.init(sm2, P, tid);
   if (i == 0) atomicMin(&s_kd0, nzm - ndamp);
+  CRM_PIPE_PROLOGUE(Q, nzm, 5, 2)
+  CRM_PIPE_PROLOGUE(A, nzm, 2, 0)
   __syncthreads();
   const int kd0 = s_kd0;   // lowest level at which any CRM of the tile is in the sponge
   const int nxy = p.nx * p.ny;
   const int irad = i / (p.nx / p.nx_rad);
   const long long rb = ((long long)tile * nzm) * (p.nx_rad * CT) + irad * CT + lane;
   double expr_km1 = 0.;
-  double fz_k = ice_flux(p, fb, P, tid, pb, CT, 1, kmin, kmax, dz);
+  double fz_k = ice_flux(p, Q, s_rho, s_adz, tid, lane, CT, 1, kmin, kmax, dz);
+  double qrad_k = p.qrad[rb];
   for (int k = 1; k <= nzm; k++) {
-    const double tabs = F3(p.tabs, k), qv = F3(p.qv, k), qcl = F3(p.qcl, k), qci = F3(p.qci, k), qpl = F3(p.qpl, k), qpi = F3(p.qpi, k);
-    const double tabs0 = PF(p.tabs0, k), qv0 = PF(p.qv0, k), qn0 = PF(p.qn0, k), qp0 = PF(p.qp0, k);
+    __syncthreads();
+    CRM_PIPE_STEP(Q, k, nzm, 5, 2)
+    CRM_PIPE_STEP(A, k, nzm, 2, 0)
+    const double qrad_next = (k < nzm) ? p.qrad[rb + (long long)k * (p.nx_rad * CT)] : 0.;   // software prefetch of the next level
+    const double tabs = A.plane(0, k)[tid], qv = A.plane(1, k)[tid], qcl = A.plane(2, k)[tid], qci = Q.plane(0, k)[tid],
+                 qpl = A.plane(3, k)[tid], qpi = A.plane(4, k)[tid];
+    const double tabs0 = SPF(2, k), qv0 = SPF(3, k), qn0 = SPF(4, k), qp0 = SPF(5, k);
     // --- buoyancy
     const double expr_k = tabs0 * (CRM_EPSV * (qv - qv0) - (qcl + qci - qn0 + qpl + qpi - qp0)) + (tabs - tabs0) * (1. + CRM_EPSV * qv0 - qn0 - qp0);
     double dw = 0.;
     if (k >= 2) {
-      double adzk = PF(p.adz, k), adzb = PF(p.adz, k - 1);
+      double adzk = SPF(1, k), adzb = SPF(1, k - 1);
       double betu = adzb / (adzk + adzb), betd = adzk / (adzk + adzb);
-      dw = dw + PF(p.bet, k) * betu * expr_k + PF(p.bet, k - 1) * betd * expr_km1;
+      dw = dw + SPF(6, k) * betu * expr_k + SPF(6, k - 1) * betd * expr_km1;
     }
     expr_km1 = expr_k;
     // --- forcing
-    double t = F3(p.t, k) + PF(p.ttend, k) * dtn;
-    double qt = F3(p.qt, k) + PF(p.qtend, k) * dtn;
+    double t = A.plane(5, k)[tid] + SPF(7, k) * dtn;
+    double qt = A.plane(6, k)[tid] + SPF(8, k) * dtn;
     {
       double v[3];
       v[0] = (qt < 0.) ? 1. : 0.; v[1] = (qt < 0.) ? qt : 0.; v[2] = (qt < 0.) ? 0. : qt;
@@ -77,26 +106,27 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p1_forcing(CrmP p) {
         qt = dmax(0., qt * factor);
       }
     }
-    double du = 0. + PF(p.utend, k);
+    double du = 0. + SPF(9, k);
     // --- radiative heating
-    t = t + p.qrad[rb + (long long)(k - 1) * (p.nx_rad * CT)] * dtn;
+    t = t + qrad_k * dtn;
+    qrad_k = qrad_next;
     // --- damping
     if (k >= kd0) {
-      const double u = F3(p.u, k);
+      const double u = A.plane(7, k)[tid];
       double v[2] = {u / nxy, t / nxy};
       block_sum<2>(v, tid, P, CT, red);
       if (k >= nzm - ndamp) {
-        const double tau = PF(p.tau, k);
+        const double tau = SPF(10, k);
         du = du - (u - v[0]) * tau;
-        dw = dw - F3(p.w, k) * tau;
+        dw = dw - A.plane(8, k)[tid] * tau;
         t = t - dtn * (t - v[1]) * tau;
         qt = qt - dtn * (qv - qv0) * tau;
       }
     }
     // --- ice fall
-    const double fz_kp1 = ice_flux(p, fb, P, tid, pb, CT, k + 1, kmin, kmax, dz);
+    const double fz_kp1 = ice_flux(p, Q, s_rho, s_adz, tid, lane, CT, k + 1, kmin, kmax, dz);
     if (k >= imax(1, kmin - 2) && k <= kmax) {
-      double coef = dtn / (dz * PF(p.adz, k) * PF(p.rho, k));
+      double coef = dtn / (dz * SPF(1, k) * SPF(0, k));
       double dqi = coef * (fz_k - fz_kp1);
       qt = qt + dqi;
       double lat_heat = (CRM_FAC_COND + CRM_FAC_FUS) * dqi;
@@ -113,43 +143,63 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p1_forcing(CrmP p) {
     F3(p.t, k) = t; F3(p.qt, k) = qt; F3(p.du_a, k) = du; F3(p.dw_a, k) = dw;
   }
   F3(p.dw_a, nz) = 0.;
+#undef SPF
 }
 
 // shear_prod2D.F90:20-94 (v == 0 in 2-D) + tke_full.F90:103-310 with dosmagor.  tk/tkh written for k <= nzm-1.
+// One TMA plane ring of 10 fields, levels k and k+1 resident (4 stages); u(k-1) is carried in registers.
+#define CRM_P2_NPROF 7
+#define CRM_P2_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(10, 4, P) + CRM_PROF_BYTES(CRM_P2_NPROF, nzp, CT))
 __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
   CRM_TILE_SETUP
   CRM_XNEIGH
-  const int nzm = p.nzm;
+  CRM_DYN_SMEM(unsigned char, smraw);
+  const int nzm = p.nzm, npf = p.nzp * CT;
+  PlanePipe<10, 4> R;
+  R.src[0] = p.u + fb; R.src[1] = p.w + fb; R.src[2] = p.tabs + fb; R.src[3] = p.qcl + fb; R.src[4] = p.qci + fb; R.src[5] = p.qv + fb;
+  R.src[6] = p.qpl + fb; R.src[7] = p.qpi + fb; R.src[8] = p.t + fb; R.src[9] = p.tk + fb;
+  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(10, 4, P));
+  {
+    const double *const g[CRM_P2_NPROF] = {p.adz, p.adzw, p.u0, p.bet, p.presi, p.grdf_x, p.grdf_z};
+    stage_profiles<CRM_P2_NPROF>(sprof, g, tile, p.nzp, CT, tid, P);
+  }
+#define SPF(r, k) sprof[(r) * npf + (k) * CT + lane]
+  R.init(smraw, P, tid);
+  CRM_PIPE_PROLOGUE(R, nzm, 3, 1)
   const double dz = p.dz[cb], dx = p.dx, rdx0 = 1. / dx, dt = p.dt;
   const double Cs = R4(0.15), Ck = R4(0.1);
   const double Ce = Ck * Ck * Ck / (Cs * Cs * Cs * Cs);
   const double Pr = 1.;
   const double Ce1 = Ce / R4(0.7) * R4(0.19), Ce2 = Ce / R4(0.7) * R4(0.51);
   double bsv_km1 = 0.;   // buoy_sgs_vert(k-1); (0) = 0
+  double u_i_b = 0., u_ic_b = 0.;   // u(i,k-1), u(i+1,k-1)
   for (int k = 1; k <= nzm - 1; k++) {
     const int kc = k + 1, kb = k - 1;
+    __syncthreads();
+    CRM_PIPE_STEP(R, k, nzm, 3, 1)
+    const double *U_k = R.plane(0, k), *U_c = R.plane(0, kc), *W_k = R.plane(1, k), *W_c = R.plane(1, kc);
+    const double u_i = U_k[tid], u_ic = U_k[tp1];
     // ---- def2
     double def2;
     {
-      const double rdz = 1. / (dz * PF(p.adz, k));
+      const double rdz = 1. / (dz * SPF(0, k));
       const double rdx = rdx0 * sqrt(dx * rdz);
-      const double u_i = F3(p.u, k), u_ic = F3X(p.u, k, tp1);
-      const double w_k = F3(p.w, k), w_kc = F3(p.w, kc);
-      const double u0k = PF(p.u0, k);
+      const double w_k = W_k[tid], w_kc = W_c[tid];
+      const double u0k = SPF(2, k);
       const double a1 = (u_ic - u_i) * rdx, a2 = (w_kc - w_k) * rdz;
       double d = 2. * (a1 * a1 + a2 * a2);
       // up terms (exist for k <= nzm-1, always here)
-      const double rdzw_up = 1. / (dz * PF(p.adzw, kc));
+      const double rdzw_up = 1. / (dz * SPF(1, kc));
       const double rdx_up = rdx0 * sqrt(dx * rdzw_up);
-      const double u0kc = PF(p.u0, kc);
-      const double up1 = (F3X(p.u, kc, tp1) - u0kc - u_ic + u0k) * rdzw_up + (F3X(p.w, kc, tp1) - w_kc) * rdx_up;
-      const double up2 = (F3(p.u, kc) - u0kc - u_i + u0k) * rdzw_up + (w_kc - F3X(p.w, kc, tm1)) * rdx_up;
+      const double u0kc = SPF(2, kc);
+      const double up1 = (U_c[tp1] - u0kc - u_ic + u0k) * rdzw_up + (W_c[tp1] - w_kc) * rdx_up;
+      const double up2 = (U_c[tid] - u0kc - u_i + u0k) * rdzw_up + (w_kc - W_c[tm1]) * rdx_up;
       if (k >= 2) {
-        const double rdzw_dn = 1. / (dz * PF(p.adzw, k));
+        const double rdzw_dn = 1. / (dz * SPF(1, k));
         const double rdx_dn = rdx0 * sqrt(dx * rdzw_dn);
-        const double u0kb = PF(p.u0, kb);
-        const double dn1 = (u_ic - u0k - F3X(p.u, kb, tp1) + u0kb) * rdzw_dn + (F3X(p.w, k, tp1) - w_k) * rdx_dn;
-        const double dn2 = (u_i - u0k - F3(p.u, kb) + u0kb) * rdzw_dn + (w_k - F3X(p.w, k, tm1)) * rdx_dn;
+        const double u0kb = SPF(2, kb);
+        const double dn1 = (u_ic - u0k - u_ic_b + u0kb) * rdzw_dn + (W_k[tp1] - w_k) * rdx_dn;
+        const double dn2 = (u_i - u0k - u_i_b + u0kb) * rdzw_dn + (w_k - W_k[tm1]) * rdx_dn;
         // v-terms of shear_prod2D.F90:36-51 are identically zero in 2-D (v = v0 = 0)
         d = d + 0.5 * (0. + 0. + up1 * up1 + up2 * up2 + dn1 * dn1 + dn2 * dn2 + 0. + 0.);
       } else {
@@ -157,15 +207,16 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
       }
       def2 = d;
     }
+    u_i_b = u_i; u_ic_b = u_ic;
     // ---- SGS buoyancy flux at the interface above level k (tke_full.F90:134-218)
     double buoy_sgs;
     {
-      const double tabs_c = F3(p.tabs, kc), tabs_b = F3(p.tabs, k);
-      const double qcl_c = F3(p.qcl, kc), qcl_b = F3(p.qcl, k), qci_c = F3(p.qci, kc), qci_b = F3(p.qci, k);
-      const double qv_c = F3(p.qv, kc), qv_b = F3(p.qv, k);
-      const double qpl_c = F3(p.qpl, kc), qpl_b = F3(p.qpl, k), qpi_c = F3(p.qpi, kc), qpi_b = F3(p.qpi, k);
-      const double t_c = F3(p.t, kc), t_b = F3(p.t, k);
-      const double betdz = 0.5 * (PF(p.bet, kc) + PF(p.bet, k)) / dz / PF(p.adzw, k + 1);
+      const double tabs_c = R.plane(2, kc)[tid], tabs_b = R.plane(2, k)[tid];
+      const double qcl_c = R.plane(3, kc)[tid], qcl_b = R.plane(3, k)[tid], qci_c = R.plane(4, kc)[tid], qci_b = R.plane(4, k)[tid];
+      const double qv_c = R.plane(5, kc)[tid], qv_b = R.plane(5, k)[tid];
+      const double qpl_c = R.plane(6, kc)[tid], qpl_b = R.plane(6, k)[tid], qpi_c = R.plane(7, kc)[tid], qpi_b = R.plane(7, k)[tid];
+      const double t_c = R.plane(8, kc)[tid], t_b = R.plane(8, k)[tid];
+      const double betdz = 0.5 * (SPF(3, kc) + SPF(3, k)) / dz / SPF(1, k + 1);
       double tabs_interface = 0.5 * (tabs_c + CRM_FAC_COND * qcl_c + CRM_FAC_SUB * qci_c + tabs_b + CRM_FAC_COND * qcl_b + CRM_FAC_SUB * qci_b);
       double qtot_interface = 0.5 * (qv_c + qcl_c + qci_c + qv_b + qcl_b + qci_b);
       double qp_interface = 0.5 * (qpl_c + qpi_c + qpl_b + qpi_b);
@@ -175,7 +226,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
       const double qctot = qcl_c + qci_c + qcl_b + qci_b;
       if (qctot > 0.) {
         const double omn = (qcl_c + qcl_b) / (qctot + R4(1.e-20));
-        const double presi = PF(p.presi, k + 1);
+        const double presi = SPF(4, k + 1);
         const double qsat_check = omn * qsatw_crm(tabs_interface, presi) + (1. - omn) * qsati_crm(tabs_interface, presi);
         if (qtot_interface > qsat_check) {
           const double lstarn = CRM_FAC_COND + (1. - omn) * CRM_FAC_FUS;
@@ -194,16 +245,16 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
     const double bsv_k = buoy_sgs;
     // ---- eddy viscosity (tke_full.F90:250-304)
     {
-      const double grd = dz * PF(p.adz, k);
-      const double cx = dx * dx / dt / PF(p.grdf_x, k);
-      const double cy = p.dy * p.dy / dt / PF(p.grdf_x, k);   // grdf_y == grdf_x (dy = dx)
-      const double dzm = dz * dmin(PF(p.adzw, k), PF(p.adzw, k + 1));
-      const double cz = dzm * dzm / dt / PF(p.grdf_z, k);
+      const double grd = dz * SPF(0, k);
+      const double cx = dx * dx / dt / SPF(5, k);
+      const double cy = p.dy * p.dy / dt / SPF(5, k);   // grdf_y == grdf_x (dy = dx)
+      const double dzm = dz * dmin(SPF(1, k), SPF(1, k + 1));
+      const double cz = dzm * dzm / dt / SPF(6, k);
       const double tkmax = R4(0.09) / (1. / cx + 1. / cy + 1. / cz);
       const double bs = 0.5 * (bsv_km1 + bsv_k);
       double smix;
       if (bs <= 0.) smix = grd;
-      else smix = dmin(grd, dmax(R4(0.1) * grd, sqrt(R4(0.76) * F3(p.tk, k) / Ck / sqrt(bs + R4(1.e-10)))));
+      else smix = dmin(grd, dmax(R4(0.1) * grd, sqrt(R4(0.76) * R.plane(9, k)[tid] / Ck / sqrt(bs + R4(1.e-10)))));
       const double ratio = smix / grd;
       const double Cee = Ce1 + Ce2 * ratio;
       double tk = sqrt(Ck * Ck * Ck / Cee * dmax(0., def2 - Pr * bs)) * (smix * smix);
@@ -215,6 +266,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
     }
     bsv_km1 = bsv_k;
   }
+#undef SPF
 }
 
 // advect2_mom_xy.F90:64-82, advect2_mom_z.F90:31-125, diffuse_mom2D.F90:38-158 (v == 0, fluxb* = fluxt* = 0).
@@ -359,7 +411,8 @@ __device__ __forceinline__ void tri_ac(const CrmP &p, int pb, int CT, int k, dou
 // mode owned by thread column i: slots hold (a0, a_{n/2}, a1, b1, a2, b2, ...)   [b0 = b_{n/2} = 0 are not stored]
 __device__ __forceinline__ int mode_of(int i, int nx) { return (i == 1) ? nx / 2 : i / 2; }
 
-// alfa(k) of the Thomas algorithm depends only on the grid: computed once per crm() call (pressure.F90:217-231)
+// alfa(k) of the Thomas algorithm depends only on the grid: computed once per crm() call (pressure.F90:217-231),
+// together with the tridiagonal coefficient profiles a(k), c(k) (pressure.F90:165-170).
 __global__ void __launch_bounds__(CRM_MAX_P) k_press_alfa(CrmP p) {
   CRM_TILE_SETUP
   const int nzm = p.nzm, m = mode_of(i, p.nx);
@@ -370,63 +423,108 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_press_alfa(CrmP p) {
   const double eign = (2. * cos(2. * xnx * (double)m) - 2.) * ddx2;   // + (2cos(0)-2)*ddy2 = 0 in 2-D
   double a, c;
   tri_ac(p, pb, CT, 1, dz, a, c);
+  if (i == 0) { PF(p.tri_a, 1) = a; PF(p.tri_c, 1) = c; }
   double b = (m == 0) ? 1. / (eign * PF(p.rho, 1) - a - c) : 1. / (eign * PF(p.rho, 1) - c);
   double alfa = -c * b;
   F3(p.palfa, 1) = alfa;
-  for (int k = 2; k <= nzm - 1; k++) {
+  for (int k = 2; k <= nzm; k++) {
     tri_ac(p, pb, CT, k, dz, a, c);
-    double e = 1. / (eign * PF(p.rho, k) - a - c + a * alfa);
-    alfa = -c * e;
-    F3(p.palfa, k) = alfa;
+    if (i == 0) { PF(p.tri_a, k) = a; PF(p.tri_c, k) = c; }
+    if (k <= nzm - 1) {
+      double e = 1. / (eign * PF(p.rho, k) - a - c + a * alfa);
+      alfa = -c * e;
+      F3(p.palfa, k) = alfa;
+    }
   }
 }
 
-// press_rhs.F90:80-102 + forward transform (fft.F90:49-53 convention) + forward sweep (pressure.F90:202-233).
-// The transform is a direct length-nx DFT per (CRM, level) in shared memory.
-// smem: P + 2*nx doubles
+// ---------------------------------------------------------------------------------------------------------------
+// Real transforms of length NX per (CRM, level) in shared memory, fft.F90:49-53 convention
+//   forward  a_m = (1/n) sum_j x_j cos(2 pi j m/n),  b_m = -(1/n) sum_j x_j sin(2 pi j m/n)
+//   inverse  x_j = a_0 + a_{n/2} (-1)^j + 2 sum_{m=1}^{n/2-1} (a_m cos(2 pi j m/n) - b_m sin(2 pi j m/n))
+// Thread column i owns spectral slot i: (a0, a_{n/2}, a1, b1, a2, b2, ...).  Both directions use the two reflection
+// symmetries of the trig functions (j -> n-j, j -> n/2-j) to fold the length-n sums into length n/4+1 sums whose trig
+// factors are per-thread constants held in registers (no table look-ups in the inner loop): 4x fewer multiply-adds and
+// 6x fewer shared-memory reads than the direct sum.
+// ---------------------------------------------------------------------------------------------------------------
+
+// press_rhs.F90:80-102 + forward transform + forward sweep (pressure.F90:202-233).
+// u, w and the three AB levels of dudt, dwdt stream through a 4-stage TMA plane ring (levels k, k+1 resident).
+#define CRM_P4_SMEM(P, CT, nzp, NX) \
+  (CRM_PIPE_BYTES(8, 4, P) + CRM_PROF_BYTES(5, nzp, CT) + (size_t)((P) + ((NX) + 2) * (CT) + ((NX) / 4 + 1) * 4 * (CT)) * 8)
+template <int NX>
 __global__ void __launch_bounds__(CRM_MAX_P) k_p4_press_fwd(CrmP p) {
+  constexpr int H = NX / 2, Q = NX / 4;
   CRM_TILE_SETUP
   CRM_XNEIGH
-  CRM_DYN_SMEM(double, sm);
-  double *sx = sm, *sc = sm + P, *ss = sc + p.nx;
-  const int nzm = p.nzm, nx = p.nx, m = mode_of(i, nx);
-  for (int q = tid; q < nx; q += P) { sc[q] = p.twc[q]; ss[q] = p.tws[q]; }
+  CRM_DYN_SMEM(unsigned char, smraw);
+  const int nzm = p.nzm, nz = p.nz, npf = p.nzp * CT, m = mode_of(i, NX);
+  PlanePipe<8, 4> R;
+  R.src[0] = p.u + fb; R.src[1] = p.w + fb; R.src[2] = p.du_a + fb; R.src[3] = p.dw_a + fb; R.src[4] = p.du_b + fb; R.src[5] = p.dw_b + fb;
+  R.src[6] = p.du_c + fb; R.src[7] = p.dw_c + fb;
+  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(8, 4, P));
+  double *sx = sprof + 5 * npf;            // P
+  double *sE = sx + P;                     // (H+1)*CT : E[0..H]
+  double *sO = sE + (H + 1) * CT;          // H*CT     : O[1..H-1] (O[0] unused)
+  double *sF = sO + H * CT;                // (Q+1)*4*CT : [j][type][lane], type 0=EP 1=EM 2=OM 3=OP
+  {
+    const double *const g[5] = {p.rho, p.adz, p.rhow, p.tri_a, p.tri_c};
+    stage_profiles<5>(sprof, g, tile, p.nzp, CT, tid, P);
+  }
+#define SPF(r, k) sprof[(r) * npf + (k) * CT + lane]
+  R.init(smraw, P, tid);
+  CRM_PIPE_PROLOGUE(R, nz, 3, 1)
+  const bool is_sin = (i & 1) && (i != 1);
+  const int type = (is_sin ? 2 : 0) + (m & 1);
+  double tw[Q + 1];
+#pragma unroll
+  for (int j = 0; j <= Q; j++) { const int idx = (j * m) & (NX - 1); tw[j] = is_sin ? p.tws[idx] : p.twc[idx]; }
   const double dz = p.dz[cb];
   const double rdx = 1. / p.dx, btat = p.bt / p.at, ctat = p.ct / p.at;
   const double dta = 1. / p.dt3na / p.at;
   const double ddx2 = 1. / (p.dx * p.dx);
   const double pii = 3.14159265358979323846;
-  const double eign = (2. * cos(2. * (pii / nx) * (double)m) - 2.) * ddx2;
-  const double scale = 1.0 / (double)nx;
-  const bool is_sin = (i & 1) && (i != 1);
+  const double eign = (2. * cos(2. * (pii / NX) * (double)m) - 2.) * ddx2;
+  const double scale = 1.0 / (double)NX;
   double alfa_km1 = 0., beta_km1 = 0.;
   for (int k = 1; k <= nzm; k++) {
     const int kc = k + 1;
-    const double rho = PF(p.rho, k);
-    const double rdzz = 1. / (PF(p.adz, k) * dz);
-    const double rup = PF(p.rhow, kc) / rho * rdzz, rdn = PF(p.rhow, k) / rho * rdzz;
-    double rhs = (rdx * (F3X(p.u, k, tp1) - F3(p.u, k)) + (F3(p.w, kc) * rup - F3(p.w, k) * rdn)) * dta +
-                 (rdx * (F3X(p.du_a, k, tp1) - F3(p.du_a, k)) + (F3(p.dw_a, kc) * rup - F3(p.dw_a, k) * rdn)) +
-                 btat * (rdx * (F3X(p.du_b, k, tp1) - F3(p.du_b, k)) + (F3(p.dw_b, kc) * rup - F3(p.dw_b, k) * rdn)) +
-                 ctat * (rdx * (F3X(p.du_c, k, tp1) - F3(p.du_c, k)) + (F3(p.dw_c, kc) * rup - F3(p.dw_c, k) * rdn));
+    __syncthreads();   // previous level's smem reads are complete; ring slot of level k-1 is free
+    CRM_PIPE_STEP(R, k, nz, 3, 1)
+    const double rho = SPF(0, k);
+    const double rdzz = 1. / (SPF(1, k) * dz);
+    const double rup = SPF(2, kc) / rho * rdzz, rdn = SPF(2, k) / rho * rdzz;
+    double rhs = (rdx * (R.plane(0, k)[tp1] - R.plane(0, k)[tid]) + (R.plane(1, kc)[tid] * rup - R.plane(1, k)[tid] * rdn)) * dta +
+                 (rdx * (R.plane(2, k)[tp1] - R.plane(2, k)[tid]) + (R.plane(3, kc)[tid] * rup - R.plane(3, k)[tid] * rdn)) +
+                 btat * (rdx * (R.plane(4, k)[tp1] - R.plane(4, k)[tid]) + (R.plane(5, kc)[tid] * rup - R.plane(5, k)[tid] * rdn)) +
+                 ctat * (rdx * (R.plane(6, k)[tp1] - R.plane(6, k)[tid]) + (R.plane(7, kc)[tid] * rup - R.plane(7, k)[tid] * rdn));
     rhs = rhs * rho;
-    __syncthreads();   // previous iteration's reads of sx are complete
     sx[tid] = rhs;
     __syncthreads();
-    // forward DFT: a_m = (1/n) sum_j x_j cos(2 pi j m/n),  b_m = -(1/n) sum_j x_j sin(2 pi j m/n)
-    double acc = 0.;
-    int idx = 0;
-    if (is_sin) {
-      for (int j = 0; j < nx; j++) { acc += sx[j * CT + lane] * ss[idx]; idx += m; if (idx >= nx) idx -= nx; }
-      acc = -scale * acc;
-    } else {
-      for (int j = 0; j < nx; j++) { acc += sx[j * CT + lane] * sc[idx]; idx += m; if (idx >= nx) idx -= nx; }
-      acc = scale * acc;
+    // fold 1: E[j] = x_j + x_{n-j} (j = 0..H; ends single), O[j] = x_j - x_{n-j} (j = 1..H-1)
+    if (i <= H) sE[tid] = (i == 0 || i == H) ? sx[tid] : sx[tid] + sx[(NX - i) * CT + lane];
+    else { const int jj = i - H; sO[jj * CT + lane] = sx[jj * CT + lane] - sx[(NX - jj) * CT + lane]; }
+    __syncthreads();
+    // fold 2: EP/EM[j] = E[j] +- E[H-j], OM/OP[j] = O[j] -+ O[H-j] (j < Q); singles E[Q], O[Q]
+    {
+      const int g = i / Q, j = i - g * Q;
+      if (g == 0) sF[(j * 4 + 0) * CT + lane] = sE[j * CT + lane] + sE[(H - j) * CT + lane];
+      else if (g == 1) sF[(j * 4 + 1) * CT + lane] = sE[j * CT + lane] - sE[(H - j) * CT + lane];
+      else if (g == 2) {
+        if (j == 0) { sF[2 * CT + lane] = 0.; const double eq = sE[Q * CT + lane]; sF[(Q * 4 + 0) * CT + lane] = eq; sF[(Q * 4 + 1) * CT + lane] = eq; }
+        else sF[(j * 4 + 2) * CT + lane] = sO[j * CT + lane] - sO[(H - j) * CT + lane];
+      } else {
+        if (j == 0) { sF[3 * CT + lane] = 0.; const double oq = sO[Q * CT + lane]; sF[(Q * 4 + 2) * CT + lane] = oq; sF[(Q * 4 + 3) * CT + lane] = oq; }
+        else sF[(j * 4 + 3) * CT + lane] = sO[j * CT + lane] + sO[(H - j) * CT + lane];
+      }
     }
-    const double ff = acc;
+    __syncthreads();
+    double acc = 0.;
+#pragma unroll
+    for (int j = 0; j <= Q; j++) acc += sF[(j * 4 + type) * CT + lane] * tw[j];
+    const double ff = is_sin ? -scale * acc : scale * acc;
     // forward elimination for this thread's mode
-    double a, c;
-    tri_ac(p, pb, CT, k, dz, a, c);
+    const double a = SPF(3, k), c = SPF(4, k);
     if (k == 1) {
       double b = (m == 0) ? 1. / (eign * rho - a - c) : 1. / (eign * rho - c);
       alfa_km1 = -c * b;
@@ -441,72 +539,111 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p4_press_fwd(CrmP p) {
       F3(p.pbeta, k) = (ff - a * beta_km1) / (eign * rho - a + a * alfa_km1);   // solution at nzm
     }
   }
+#undef SPF
 }
 
 // pressure.F90:234-305 (back substitution, inverse transform) + press_grad.F90:20-35 + adams.F90:19-38.
-// Marches downward; w(k+1) is finalised when p(k) is known.  smem: 2*P + 2*nx doubles
+// Marches downward; w(k+1) is finalised when p(k) is known.  Ten fields through a descending 4-stage TMA plane ring.
+#define CRM_P5_SMEM(P, CT, nzp, NX) \
+  (CRM_PIPE_BYTES(10, 4, P) + CRM_PROF_BYTES(3, nzp, CT) + (size_t)(2 * (P) + 5 * ((NX) / 4 + 1) * (CT)) * 8)
+template <int NX>
 __global__ void __launch_bounds__(CRM_MAX_P) k_p5_press_bwd(CrmP p) {
+  constexpr int H = NX / 2, Q = NX / 4, NM = H / 2;
   CRM_TILE_SETUP
   CRM_XNEIGH
-  CRM_DYN_SMEM(double, sm);
-  double *sX = sm, *sp = sm + P, *sc = sp + P, *ss = sc + p.nx;
-  const int nzm = p.nzm, nx = p.nx;
-  for (int q = tid; q < nx; q += P) { sc[q] = p.twc[q]; ss[q] = p.tws[q]; }
+  CRM_DYN_SMEM(unsigned char, smraw);
+  const int nzm = p.nzm, npf = p.nzp * CT;
+  PlanePipe<10, 4> R;
+  R.src[0] = p.pbeta + fb; R.src[1] = p.palfa + fb; R.src[2] = p.du_a + fb; R.src[3] = p.u + fb; R.src[4] = p.du_b + fb; R.src[5] = p.du_c + fb;
+  R.src[6] = p.dw_a + fb; R.src[7] = p.w + fb; R.src[8] = p.dw_b + fb; R.src[9] = p.dw_c + fb;
+  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(10, 4, P));
+  double *sX = sprof + 3 * npf;             // P: spectrum of this level
+  double *sp = sX + P;                      // P: pressure of this level
+  double *part = sp + P;                    // 4*(Q+1)*CT: partial sums [r][j][lane], r = Ce, Co, Se, So
+  double *sbase = part + 4 * (Q + 1) * CT;  // (Q+1)*CT: a0 + (-1)^j a_{n/2}
+  {
+    const double *const g[3] = {p.rho, p.rhow, p.adzw};
+    stage_profiles<3>(sprof, g, tile, p.nzp, CT, tid, P);
+  }
+#define SPF(r, k) sprof[(r) * npf + (k) * CT + lane]
+  for (int q = tid; q < 4 * (Q + 1) * CT; q += P) part[q] = 0.;   // tasks that do not exist (Se, So at j = 0; Co, Se at j = Q) stay zero
+  R.init(smraw, P, tid);
+  if (tid == 0) { R.issue(nzm); if (nzm >= 2) R.issue(nzm - 1); }
+  // task of this thread: partial sum r at point j (see header comment): x_j, x_{n-j}, x_{n/2-j}, x_{n/2+j} share them
+  int r, j;
+  if (i < 4) { r = (i == 1) ? 1 : (i == 3) ? 3 : 0; j = (i < 2) ? 0 : Q; }
+  else { j = i >> 2; r = i & 3; }
+  const int off0 = (r == 0) ? 0 : (r == 1) ? 2 : (r == 2) ? 1 : 3;
+  double tw[NM];
+#pragma unroll
+  for (int mm = 0; mm < NM; mm++) {
+    const int mo = 2 * mm + (r & 1);
+    const int idx = (j * mo) & (NX - 1);
+    tw[mm] = (r < 2) ? p.twc[idx] : p.tws[idx];
+    if (mm == 0 && !(r & 1)) tw[mm] = 0.;   // m = 0: a_0 is part of the base term; slot 1 holds a_{n/2}, not b_0
+  }
+  // output point of this thread: which partial sums, with which signs
+  int jc; double sCo, sSe, sSo;
+  if (i <= Q) { jc = i; sCo = 1.; sSe = -1.; sSo = -1.; }
+  else if (i <= H) { jc = H - i; sCo = -1.; sSe = 1.; sSo = -1.; }
+  else if (i < H + Q) { jc = i - H; sCo = -1.; sSe = -1.; sSo = 1.; }
+  else { jc = NX - i; sCo = 1.; sSe = 1.; sSo = 1.; }
   const double dz = p.dz[cb];
   const double rdx = 1. / p.dx;
   const double dtdx = p.dtn / p.dx, dtdz = p.dtn / dz;
   const double at = p.at, bt = p.bt, ct = p.ct, dt3na = p.dt3na;
   double ff_kp1 = 0., p_kp1 = 0.;
   for (int k = nzm; k >= 1; k--) {
-    double ffk = (k == nzm) ? F3(p.pbeta, k) : F3(p.palfa, k) * ff_kp1 + F3(p.pbeta, k);
-    ff_kp1 = ffk;
     __syncthreads();
+    if (tid == 0 && k - 2 >= 1) R.issue(k - 2);
+    R.wait_desc(k, nzm);
+    double ffk = (k == nzm) ? R.plane(0, k)[tid] : R.plane(1, k)[tid] * ff_kp1 + R.plane(0, k)[tid];
+    ff_kp1 = ffk;
     sX[tid] = ffk;
     __syncthreads();
-    // inverse: x_j = a0 + a_{n/2} (-1)^j + 2 sum_{m=1}^{n/2-1} (a_m cos(2 pi j m/n) - b_m sin(2 pi j m/n)), j = i
-    double x = sX[lane] + ((i & 1) ? -sX[CT + lane] : sX[CT + lane]);
     {
-      int idx = 0;
       double acc = 0.;
-      for (int m = 1; m < nx / 2; m++) {
-        idx += i; if (idx >= nx) idx -= nx;
-        acc += sX[(2 * m) * CT + lane] * sc[idx] - sX[(2 * m + 1) * CT + lane] * ss[idx];
-      }
-      x = x + 2. * acc;
+#pragma unroll
+      for (int mm = 0; mm < NM; mm++) acc += sX[(off0 + 4 * mm) * CT + lane] * tw[mm];
+      part[(r * (Q + 1) + j) * CT + lane] = acc;
+      if (r == 0) sbase[j * CT + lane] = sX[lane] + ((j & 1) ? -sX[CT + lane] : sX[CT + lane]);
     }
-    const double pk = x;
+    __syncthreads();
+    const double pk = sbase[jc * CT + lane] + 2. * (((part[jc * CT + lane] + sCo * part[((Q + 1) + jc) * CT + lane]) +
+                                                    sSe * part[(2 * (Q + 1) + jc) * CT + lane]) + sSo * part[(3 * (Q + 1) + jc) * CT + lane]);
     sp[tid] = pk;
     __syncthreads();
     const double pk_m = sp[tm1];
     // press_grad + adams for u at level k
     {
-      double du = F3(p.du_a, k) - (pk - pk_m) * rdx;
+      double du = R.plane(2, k)[tid] - (pk - pk_m) * rdx;
       F3(p.du_a, k) = du;
-      const double u = F3(p.u, k);
-      const double unew = u + dt3na * (at * du + bt * F3(p.du_b, k) + ct * F3(p.du_c, k));
+      const double u = R.plane(3, k)[tid];
+      const double unew = u + dt3na * (at * du + bt * R.plane(4, k)[tid] + ct * R.plane(5, k)[tid]);
       F3(p.du_c, k) = unew;
-      F3(p.umf, k) = 0.5 * (u + unew) * (PF(p.rho, k) * dtdx);
+      F3(p.umf, k) = 0.5 * (u + unew) * (SPF(0, k) * dtdx);
     }
     // w at level k+1 (needs p(k+1) - p(k))
     if (k + 1 <= nzm) {
       const int kw = k + 1;
-      const double rdzw = 1. / (dz * PF(p.adzw, kw));
-      double dw = F3(p.dw_a, kw) - (p_kp1 - pk) * rdzw;
+      const double rdzw = 1. / (dz * SPF(2, kw));
+      double dw = R.plane(6, kw)[tid] - (p_kp1 - pk) * rdzw;
       F3(p.dw_a, kw) = dw;
-      const double w = F3(p.w, kw);
-      const double wnew = w + dt3na * (at * dw + bt * F3(p.dw_b, kw) + ct * F3(p.dw_c, kw));
+      const double w = R.plane(7, kw)[tid];
+      const double wnew = w + dt3na * (at * dw + bt * R.plane(8, kw)[tid] + ct * R.plane(9, kw)[tid]);
       F3(p.dw_c, kw) = wnew;
-      F3(p.wmf, kw) = 0.5 * (w + wnew) * (PF(p.rhow, kw) * dtdz);
+      F3(p.wmf, kw) = 0.5 * (w + wnew) * (SPF(1, kw) * dtdz);
     }
     p_kp1 = pk;
   }
   {   // w at level 1: no pressure gradient (press_grad.F90:25, kb = max(1,k-1))
-    const double dw = F3(p.dw_a, 1);
-    const double w = F3(p.w, 1);
-    const double wnew = w + dt3na * (at * dw + bt * F3(p.dw_b, 1) + ct * F3(p.dw_c, 1));
+    const double dw = R.plane(6, 1)[tid];
+    const double w = R.plane(7, 1)[tid];
+    const double wnew = w + dt3na * (at * dw + bt * R.plane(8, 1)[tid] + ct * R.plane(9, 1)[tid]);
     F3(p.dw_c, 1) = wnew;
-    F3(p.wmf, 1) = 0.5 * (w + wnew) * (PF(p.rhow, 1) * dtdz);
+    F3(p.wmf, 1) = 0.5 * (w + wnew) * (SPF(1, 1) * dtdz);
   }
+#undef SPF
 }
 
 }  // namespace crm

@@ -159,22 +159,36 @@ __device__ __forceinline__ double term_vel_qp(const MicroScalars &m, double qplo
   return term_vel;
 }
 
-// microphysics.F90:578-640: fall speed of every cell + batch-global prec_cfl.  smem: P doubles.
+// microphysics.F90:578-640: fall speed of every cell + batch-global prec_cfl.  qp, tabs through a 3-stage TMA ring.
+#define CRM_PRECIPA_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(2, 3, P) + CRM_PROF_BYTES(3, nzp, CT) + (size_t)(P) * 8)
 __global__ void __launch_bounds__(CRM_MAX_P) k_precip_a(CrmP p) {
   CRM_TILE_SETUP
-  CRM_DYN_SMEM(double, red);
+  CRM_DYN_SMEM(unsigned char, smraw);
+  const int nzm = p.nzm, npf = p.nzp * CT;
+  PlanePipe<2, 3> R;
+  R.src[0] = p.qp + fb; R.src[1] = p.tabs + fb;
+  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(2, 3, P));
+  double *red = sprof + 3 * npf;
+  {
+    const double *const g[3] = {p.rho, p.adz, p.rhow};
+    stage_profiles<3>(sprof, g, tile, p.nzp, CT, tid, P);
+  }
+  R.init(smraw, P, tid);
+  CRM_PIPE_PROLOGUE(R, nzm, 2, 0)
   const double dz = p.dz[cb];
   double cfl = 0.;
-  for (int k = 1; k <= p.nzm; k++) {
-    const double rho = PF(p.rho, k);
+  for (int k = 1; k <= nzm; k++) {
+    __syncthreads();
+    CRM_PIPE_STEP(R, k, nzm, 2, 0)
+    const double rho = sprof[k * CT + lane];
     const double rhofac = sqrt(R4(1.29) / rho);
     const int kb = imax(1, k - 1);
-    const double wmax = dz * PF(p.adz, kb) / p.dtn;
+    const double wmax = dz * sprof[npf + kb * CT + lane] / p.dtn;
     const double iwmax = 1. / wmax;
-    const double tv = term_vel_qp(p.ms, F3(p.qp, k), rho, F3(p.tabs, k));
+    const double tv = term_vel_qp(p.ms, R.plane(0, k)[tid], rho, R.plane(1, k)[tid]);
     const double wpv = rhofac * tv;
     cfl = dmax(cfl, wpv * iwmax);
-    F3(p.wp, k) = -wpv * PF(p.rhow, k) * p.dtn / dz;
+    F3(p.wp, k) = -wpv * sprof[2 * npf + k * CT + lane] * p.dtn / dz;
   }
   const double m = block_max_all(cfl, tid, P, red);
   if (tid == 0) atomicMax(p.prec_cfl_bits, (unsigned long long)__double_as_longlong(m));

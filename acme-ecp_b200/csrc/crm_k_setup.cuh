@@ -279,24 +279,38 @@ __global__ void k_setperturb(CrmP p, const double *rnd) {
 
 // kurant.F90:9-64 + sgs.F90:329-372.  max over i commutes with the per-level scaling, so every thread folds its own
 // column and only one block max + one atomicMax on the (non-negative) double bit pattern are needed.
-// smem: P doubles.
+// u, w, tkh stream through a TMA plane ring (4 stages, levels k and k+1 resident).
+#define CRM_KURANT_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(3, 4, P) + CRM_PROF_BYTES(3, nzp, CT) + (size_t)(P) * 8)
 __global__ void __launch_bounds__(CRM_MAX_P) k_kurant(CrmP p) {
   CRM_TILE_SETUP
-  CRM_DYN_SMEM(double, red);
+  CRM_DYN_SMEM(unsigned char, smraw);
+  const int nzm = p.nzm, nz = p.nz, npf = p.nzp * CT;
+  PlanePipe<3, 4> R;
+  R.src[0] = p.u + fb; R.src[1] = p.w + fb; R.src[2] = p.tkh + fb;
+  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(3, 4, P));
+  double *red = sprof + 3 * npf;
+  {
+    const double *const g[3] = {p.adzw, p.grdf_z, p.grdf_x};
+    stage_profiles<3>(sprof, g, tile, p.nzp, CT, tid, P);
+  }
+  R.init(smraw, P, tid);
+  CRM_PIPE_PROLOGUE(R, nz, 3, 1)
   const double idx = 1. / p.dx;
   const double sq = sqrt(idx * idx);
   const double dz = p.dz[cb];
   double cfl = 0.;
-  double wk = fabs(F3(p.w, 1));
-  for (int k = 1; k <= p.nzm; k++) {
-    double wk1 = fabs(F3(p.w, k + 1));
-    double u = F3(p.u, k);
+  double wk = fabs(R.plane(1, 1)[tid]);
+  for (int k = 1; k <= nzm; k++) {
+    __syncthreads();
+    CRM_PIPE_STEP(R, k, nz, 3, 1)
+    double wk1 = fabs(R.plane(1, k + 1)[tid]);
+    double u = R.plane(0, k)[tid];
     double uh = sqrt(u * u);
-    double adzw = PF(p.adzw, k);
+    double adzw = sprof[0 * npf + k * CT + lane];
     cfl = dmax(cfl, dmax(uh * p.dt * sq, dmax(wk, wk1) * p.dt / (dz * adzw)));
-    double tkh = F3(p.tkh, k);
+    double tkh = R.plane(2, k)[tid];
     double dzw = dz * adzw;
-    cfl = dmax(cfl, dmax(0.5 * tkh * PF(p.grdf_z, k) * p.dt / (dzw * dzw), 0.5 * tkh * PF(p.grdf_x, k) * p.dt / (p.dx * p.dx)));
+    cfl = dmax(cfl, dmax(0.5 * tkh * sprof[1 * npf + k * CT + lane] * p.dt / (dzw * dzw), 0.5 * tkh * sprof[2 * npf + k * CT + lane] * p.dt / (p.dx * p.dx)));
     wk = wk1;
   }
   double m = block_max_all(cfl, tid, P, red);

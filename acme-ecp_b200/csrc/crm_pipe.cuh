@@ -91,8 +91,25 @@ struct PlanePipe {
     __syncthreads();
 #endif
   }
+  // descending march starting at level Ltop: same slots, parity counts uses of the slot from the top
+  __device__ __forceinline__ void wait_desc(int L, int Ltop) {
+#ifndef CRM_EMU
+    mbar_wait(bar + (L - 1) % NS, (unsigned)(((Ltop - L) / NS) & 1));
+#else
+    __syncthreads();
+#endif
+  }
   __device__ __forceinline__ const double *plane(int f, int L) const { return buf + ((size_t)((L - 1) % NS) * NF + f) * P; }
 };
+
+// March boilerplate.  NPRE = NS-1-back levels are issued ahead; FWD = highest level above k that iteration k reads.
+#define CRM_PIPE_PROLOGUE(pipe, nlev, NPRE, FWD)                                   \
+  if (tid == 0) for (int L_ = 1; L_ <= imin((nlev), (NPRE)); L_++) (pipe).issue(L_); \
+  for (int L_ = 1; L_ <= imin((nlev), (FWD)); L_++) (pipe).wait(L_);
+// top of iteration k (after the caller's __syncthreads()): refill the freed slot, wait for level k+FWD
+#define CRM_PIPE_STEP(pipe, k, nlev, NPRE, FWD)                        \
+  if (tid == 0 && (k) + (NPRE) <= (nlev)) (pipe).issue((k) + (NPRE)); \
+  if ((k) + (FWD) <= (nlev)) (pipe).wait((k) + (FWD));
 
 // Column profiles of one tile staged in shared memory: NPR profiles of nzp*CT doubles each.
 #define CRM_PROF_BYTES(NPR, nzp, CT) ((size_t)(NPR) * (nzp) * (CT) * 8)
