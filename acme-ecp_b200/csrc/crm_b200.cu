@@ -152,6 +152,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   if (CT > 16) CT = 16;
   if (const char *e = getenv("CRM_B200_CT")) { int v = atoi(e); if (v >= 1 && v <= 32 && !(v & (v - 1))) CT = v; }
   while (d->nx * CT > CRM_MAX_P && CT > 1) CT >>= 1;
+  while (d->nx * CT < 32) CT <<= 1;   // a block is at least one warp (warp-shuffle slab reductions)
   if (CT < 1 || d->nx * CT > CRM_MAX_P) { g_init_err = "crm_b200_init: nx too large (nx <= 256)"; delete h; return 4; }
   h->CT = CT;
   h->ntiles = (d->ncrms + CT - 1) / CT;
@@ -221,6 +222,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
     cudaFuncSetAttribute(k_p2_sgs, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(k_kurant, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(k_precip_a, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(k_precip_b, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 #define PRESS_ATTR(NXV)                                                                              \
   cudaFuncSetAttribute(k_p4_press_fwd<NXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);       \
   cudaFuncSetAttribute(k_p5_press_bwd<NXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
@@ -384,7 +386,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   double dt3[4] = {0, 0, 0, 0};
   long long ncycle_sum = 0, ncycle_max = 0, nprec_max = 0;
   double dtn = dt;
-  const size_t smem_mp = (size_t)9 * P * 8;
+  const size_t smem_mp = CRM_MP_SMEM(P, CT, h->nzp);
   const int dbg_stop = getenv("CRM_DEBUG_STOP") ? atoi(getenv("CRM_DEBUG_STOP")) : 0;   // test hook: stop inside the first sub-step
   bool dbg_break = false;
 
@@ -434,12 +436,12 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
       if (dbg_stop == 4) { dbg_break = true; break; }
       // advect_all_scalars.F90:32-64
       LAUNCH(h, k_mpdata, ntiles, P, smem_mp, p, p.t, (double *)nullptr, (double *)nullptr, 0);
-      LAUNCH(h, k_mpdata, ntiles, P, smem_mp + red_bytes(2), p, p.qt, p.mkadv1, p.mkwle1, 1);
-      LAUNCH(h, k_mpdata, ntiles, P, smem_mp + red_bytes(2), p, p.qp, p.mkadv2, p.mkwle2, 1);
+      LAUNCH(h, k_mpdata, ntiles, P, smem_mp, p, p.qt, p.mkadv1, p.mkwle1, 1);
+      LAUNCH(h, k_mpdata, ntiles, P, smem_mp, p, p.qp, p.mkadv2, p.mkwle2, 1);
       if (dbg_stop == 5) { dbg_break = true; break; }
       dev_zero(p.prec_cfl_bits, 8);
       LAUNCH(h, k_precip_a, ntiles, P, CRM_PRECIPA_SMEM(P, CT, h->nzp), p);
-      LAUNCH(h, k_precip_b, ntiles, P, red_bytes(2), p);
+      LAUNCH(h, k_precip_b, ntiles, P, CRM_PRECIPB_SMEM(P, CT, h->nzp), p);
       // uvw.F90: u <- dudt(nc) is a role rotation of the buffers (with the AB rotation of crm_module.F90:884-887)
       { int o_u = iu, o_a = ina, o_b = inb, o_c = inc; iu = o_c; ina = o_u; inb = o_a; inc = o_b; }
       p.u = h->ubuf[iu]; p.w = h->wbuf[iu];
@@ -469,7 +471,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
     }
     if (dbg_break) break;
     p.nstop = nstop;
-    LAUNCH(h, k_stats, ntiles, P, (size_t)(CRM_RED_DOUBLES(10, P, CT) + 5 * P) * 8, p);
+    LAUNCH(h, k_stats, ntiles, P, CRM_STATS_SMEM(P, CT, h->nzp), p);
     // nprec statistic (device value of the last sub-step)
     if ((nstep & 15) == 0 || nstep == nstop) {
       unsigned long long pb2 = 0; dev_copy2d(&pb2, 8, p.prec_cfl_bits, 8, 8, 1, 0);

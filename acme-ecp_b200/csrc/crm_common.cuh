@@ -150,40 +150,39 @@ __device__ __forceinline__ double dtqsatw_crm(double t, double p) { return R4(0.
 __device__ __forceinline__ double dtqsati_crm(double t, double p) { return R4(0.622) * dtesati_crm(t) / p; }
 
 // ---------------------------------------------------------------------------------------------------
-// Block reductions over x for each lane (NQ <= 16).  `red` is shared memory of CRM_RED_DOUBLES(NQ,P,CT) doubles.
-// Order: 8 consecutive i summed ascending, then the nx/8 partials ascending (fixed => deterministic).
-// All threads must call; on return v[q] holds the slab sum for the caller's lane.
+// Block reductions over x for each lane.  tid = i*CT + lane with CT a power of two <= 32 and P a multiple of 32, so
+// every warp holds 32/CT consecutive i for each lane: xor-shuffles over the i-bits reduce inside the warp (fixed
+// pairwise tree), the P/32 warp partials are then summed in ascending warp order.  Deterministic, no atomics.
+// `red` is shared memory of CRM_RED_DOUBLES(NQ,P,CT) doubles.  All threads must call.
+//   block_sum:       on return v[q] holds the slab sum for the caller's lane in EVERY thread
+//   block_sum_lead:  only threads with i == 0 (tid < CT) get the sums (cheaper: the others skip the final pass)
 // ---------------------------------------------------------------------------------------------------
-template <int NQ>
-__device__ __forceinline__ void block_sum(double (&v)[NQ], int tid, int P, int CT, double *red) {
-  const int i = tid / CT, lane = tid - i * CT, M = P / CT, G = M / 8;
-  // r3 sits at a fixed place so that back-to-back calls with different NQ never alias a result still being read
-  double *r3 = red, *r1 = red + 16 * CT, *r2 = r1 + NQ * P;
+template <int NQ, bool ALL>
+__device__ __forceinline__ void block_sum_impl(double (&v)[NQ], int tid, int P, int CT, double *red) {
+  const int lane = tid & (CT - 1), w = tid >> 5, nw = P >> 5;
 #pragma unroll
-  for (int q = 0; q < NQ; q++) r1[q * P + tid] = v[q];
-  __syncthreads();
-  if ((i & 7) == 0) {
+  for (int q = 0; q < NQ; q++)
+    for (int off = CT; off < 32; off <<= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], off);
+  __syncthreads();   // earlier readers of `red` are done
+  if ((tid & 31) < CT) {
 #pragma unroll
-    for (int q = 0; q < NQ; q++) {
-      double s = r1[q * P + tid];
-      for (int d = 1; d < 8; d++) s += r1[q * P + tid + d * CT];
-      r2[(q * G + (i >> 3)) * CT + lane] = s;
-    }
+    for (int q = 0; q < NQ; q++) red[(w * NQ + q) * CT + lane] = v[q];
   }
   __syncthreads();
-  if (i == 0) {
+  if (ALL || tid < CT) {
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
-      double s = r2[(q * G) * CT + lane];
-      for (int g = 1; g < G; g++) s += r2[(q * G + g) * CT + lane];
-      r3[q * CT + lane] = s;
+      double s = red[q * CT + lane];
+      for (int g = 1; g < nw; g++) s += red[(g * NQ + q) * CT + lane];
+      v[q] = s;
     }
   }
-  __syncthreads();
-#pragma unroll
-  for (int q = 0; q < NQ; q++) v[q] = r3[q * CT + lane];
 }
-#define CRM_RED_DOUBLES(NQ, P, CT) (16 * (CT) + (NQ) * ((P) + (P) / 8))
+template <int NQ>
+__device__ __forceinline__ void block_sum(double (&v)[NQ], int tid, int P, int CT, double *red) { block_sum_impl<NQ, true>(v, tid, P, CT, red); }
+template <int NQ>
+__device__ __forceinline__ void block_sum_lead(double (&v)[NQ], int tid, int P, int CT, double *red) { block_sum_impl<NQ, false>(v, tid, P, CT, red); }
+#define CRM_RED_DOUBLES(NQ, P, CT) ((NQ) * ((P) / 32) * (CT))
 
 // max over the whole block (all lanes); result returned to every thread.  red: >= P doubles.
 __device__ __forceinline__ double block_max_all(double v, int tid, int P, double *red) {

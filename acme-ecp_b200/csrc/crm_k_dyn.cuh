@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p1_forcing(CrmP p) {
 
 // shear_prod2D.F90:20-94 (v == 0 in 2-D) + tke_full.F90:103-310 with dosmagor.  tk/tkh written for k <= nzm-1.
 // One TMA plane ring of 10 fields, levels k and k+1 resident (4 stages); u(k-1) is carried in registers.
-#define CRM_P2_NPROF 7
+#define CRM_P2_NPROF 9
 #define CRM_P2_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(10, 4, P) + CRM_PROF_BYTES(CRM_P2_NPROF, nzp, CT))
 __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
   CRM_TILE_SETUP
@@ -159,14 +159,34 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
   R.src[0] = p.u + fb; R.src[1] = p.w + fb; R.src[2] = p.tabs + fb; R.src[3] = p.qcl + fb; R.src[4] = p.qci + fb; R.src[5] = p.qv + fb;
   R.src[6] = p.qpl + fb; R.src[7] = p.qpi + fb; R.src[8] = p.t + fb; R.src[9] = p.tk + fb;
   double *sprof = (double *)(smraw + CRM_PIPE_BYTES(10, 4, P));
-  {
-    const double *const g[CRM_P2_NPROF] = {p.adz, p.adzw, p.u0, p.bet, p.presi, p.grdf_x, p.grdf_z};
-    stage_profiles<CRM_P2_NPROF>(sprof, g, tile, p.nzp, CT, tid, P);
+  const double dx = p.dx, rdx0 = 1. / dx, dt = p.dt;
+  // per-(CRM, level) factors, evaluated once per block with the reference's expressions:
+  // 0 rdz=1/(dz adz)  1 rdx0 sqrt(dx rdz)  2 rdzw=1/(dz adzw)  3 rdx0 sqrt(dx rdzw)  4 u0  5 betdz  6 presi(k+1)  7 grd=dz adz  8 tkmax
+  for (int q = tid; q < p.nz * CT; q += P) {
+    const int k = q / CT + 1, ln = q - (k - 1) * CT;
+    const int o = tile * p.nzp * CT + k * CT + ln, so = k * CT + ln;
+    const double dzq = p.dz[tile * CT + ln];
+    const double adzw = p.adzw[o];
+    const double rdzw = 1. / (dzq * adzw);
+    sprof[2 * npf + so] = rdzw; sprof[3 * npf + so] = rdx0 * sqrt(dx * rdzw);
+    if (k <= nzm) {
+      const double adz = p.adz[o], adzw1 = p.adzw[o + CT];
+      const double rdz = 1. / (dzq * adz);
+      sprof[so] = rdz; sprof[npf + so] = rdx0 * sqrt(dx * rdz);
+      sprof[4 * npf + so] = p.u0[o];
+      sprof[5 * npf + so] = (k <= nzm - 1) ? 0.5 * (p.bet[o + CT] + p.bet[o]) / dzq / adzw1 : 0.;
+      sprof[6 * npf + so] = p.presi[o + CT];
+      sprof[7 * npf + so] = dzq * adz;
+      const double cx = dx * dx / dt / p.grdf_x[o];
+      const double cy = p.dy * p.dy / dt / p.grdf_x[o];   // grdf_y == grdf_x (dy = dx)
+      const double dzm = dzq * dmin(adzw, adzw1);
+      const double cz = dzm * dzm / dt / p.grdf_z[o];
+      sprof[8 * npf + so] = R4(0.09) / (1. / cx + 1. / cy + 1. / cz);
+    }
   }
 #define SPF(r, k) sprof[(r) * npf + (k) * CT + lane]
   R.init(smraw, P, tid);
   CRM_PIPE_PROLOGUE(R, nzm, 3, 1)
-  const double dz = p.dz[cb], dx = p.dx, rdx0 = 1. / dx, dt = p.dt;
   const double Cs = R4(0.15), Ck = R4(0.1);
   const double Ce = Ck * Ck * Ck / (Cs * Cs * Cs * Cs);
   const double Pr = 1.;
@@ -182,22 +202,22 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
     // ---- def2
     double def2;
     {
-      const double rdz = 1. / (dz * SPF(0, k));
-      const double rdx = rdx0 * sqrt(dx * rdz);
+      const double rdz = SPF(0, k);
+      const double rdx = SPF(1, k);
       const double w_k = W_k[tid], w_kc = W_c[tid];
-      const double u0k = SPF(2, k);
+      const double u0k = SPF(4, k);
       const double a1 = (u_ic - u_i) * rdx, a2 = (w_kc - w_k) * rdz;
       double d = 2. * (a1 * a1 + a2 * a2);
       // up terms (exist for k <= nzm-1, always here)
-      const double rdzw_up = 1. / (dz * SPF(1, kc));
-      const double rdx_up = rdx0 * sqrt(dx * rdzw_up);
-      const double u0kc = SPF(2, kc);
+      const double rdzw_up = SPF(2, kc);
+      const double rdx_up = SPF(3, kc);
+      const double u0kc = SPF(4, kc);
       const double up1 = (U_c[tp1] - u0kc - u_ic + u0k) * rdzw_up + (W_c[tp1] - w_kc) * rdx_up;
       const double up2 = (U_c[tid] - u0kc - u_i + u0k) * rdzw_up + (w_kc - W_c[tm1]) * rdx_up;
       if (k >= 2) {
-        const double rdzw_dn = 1. / (dz * SPF(1, k));
-        const double rdx_dn = rdx0 * sqrt(dx * rdzw_dn);
-        const double u0kb = SPF(2, kb);
+        const double rdzw_dn = SPF(2, k);
+        const double rdx_dn = SPF(3, k);
+        const double u0kb = SPF(4, kb);
         const double dn1 = (u_ic - u0k - u_ic_b + u0kb) * rdzw_dn + (W_k[tp1] - w_k) * rdx_dn;
         const double dn2 = (u_i - u0k - u_i_b + u0kb) * rdzw_dn + (w_k - W_k[tm1]) * rdx_dn;
         // v-terms of shear_prod2D.F90:36-51 are identically zero in 2-D (v = v0 = 0)
@@ -216,7 +236,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
       const double qv_c = R.plane(5, kc)[tid], qv_b = R.plane(5, k)[tid];
       const double qpl_c = R.plane(6, kc)[tid], qpl_b = R.plane(6, k)[tid], qpi_c = R.plane(7, kc)[tid], qpi_b = R.plane(7, k)[tid];
       const double t_c = R.plane(8, kc)[tid], t_b = R.plane(8, k)[tid];
-      const double betdz = 0.5 * (SPF(3, kc) + SPF(3, k)) / dz / SPF(1, k + 1);
+      const double betdz = SPF(5, k);
       double tabs_interface = 0.5 * (tabs_c + CRM_FAC_COND * qcl_c + CRM_FAC_SUB * qci_c + tabs_b + CRM_FAC_COND * qcl_b + CRM_FAC_SUB * qci_b);
       double qtot_interface = 0.5 * (qv_c + qcl_c + qci_c + qv_b + qcl_b + qci_b);
       double qp_interface = 0.5 * (qpl_c + qpi_c + qpl_b + qpi_b);
@@ -226,7 +246,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
       const double qctot = qcl_c + qci_c + qcl_b + qci_b;
       if (qctot > 0.) {
         const double omn = (qcl_c + qcl_b) / (qctot + R4(1.e-20));
-        const double presi = SPF(4, k + 1);
+        const double presi = SPF(6, k);
         const double qsat_check = omn * qsatw_crm(tabs_interface, presi) + (1. - omn) * qsati_crm(tabs_interface, presi);
         if (qtot_interface > qsat_check) {
           const double lstarn = CRM_FAC_COND + (1. - omn) * CRM_FAC_FUS;
@@ -245,12 +265,8 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
     const double bsv_k = buoy_sgs;
     // ---- eddy viscosity (tke_full.F90:250-304)
     {
-      const double grd = dz * SPF(0, k);
-      const double cx = dx * dx / dt / SPF(5, k);
-      const double cy = p.dy * p.dy / dt / SPF(5, k);   // grdf_y == grdf_x (dy = dx)
-      const double dzm = dz * dmin(SPF(1, k), SPF(1, k + 1));
-      const double cz = dzm * dzm / dt / SPF(6, k);
-      const double tkmax = R4(0.09) / (1. / cx + 1. / cy + 1. / cz);
+      const double grd = SPF(7, k);
+      const double tkmax = SPF(8, k);
       const double bs = 0.5 * (bsv_km1 + bsv_k);
       double smix;
       if (bs <= 0.) smix = grd;
@@ -388,7 +404,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p3_mom(CrmP p) {
     }
     if (p.last_substep) {   // uwle(k) (advect2_mom_z.F90:76-109), uwsb(k) (diffuse_mom2D.F90:97-130)
       double v[2] = {fuz_k, fuv_k};
-      block_sum<2>(v, tid, P, CT, red);
+      block_sum_lead<2>(v, tid, P, CT, red);
       if (i == 0) { PF(p.uwle, k) = v[0]; PF(p.uwsb, k) = v[1]; }
     }
     fuz_k = fuz_kc; fwz_km1 = fwz_k; fuv_k = fuv_kc; fwv_k = fwv_kc;

@@ -18,34 +18,61 @@ __device__ __forceinline__ double min3(double a, double b, double c) { return dm
 // Pipeline per iteration ka (1..nzm+2):  A: upwind pass -> F1(ka);  B: antidiffusive velocities UU(ka-1), WW(ka),
 // FCT ratios mx/mn(ka-1);  C: limited fluxes and final update of level ka-2.  U = umf, W = wmf (mass-flux
 // velocities of adams).  fadv/flux: optional profile outputs (mkadv/mkwle), written only when `stats`.
-// smem: 9*P doubles (+ CRM_RED_DOUBLES(2,P,CT) when stats)
+// f, U, W stream through a 6-stage TMA plane ring (levels ka-2..ka+1 resident, 2 levels of prefetch); the reciprocal
+// grid profiles (1/rho, 1/adz, 1/(rhow*adz), 2/((kc-kb)*adz)) are evaluated once per block into shared memory.
+#define CRM_MP_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(3, 6, P) + CRM_PROF_BYTES(5, nzp, CT) + (size_t)(9 * (P) + CRM_RED_DOUBLES(2, P, CT)) * 8)
 __global__ void __launch_bounds__(CRM_MAX_P) k_mpdata(CrmP p, double *f, double *fadv, double *flux, int stats) {
   CRM_TILE_SETUP
   CRM_XNEIGH
-  CRM_DYN_SMEM(double, sm);
+  CRM_DYN_SMEM(unsigned char, smraw);
+  const int nzm = p.nzm, nz = p.nz, npf = p.nzp * CT;
+  PlanePipe<3, 6> R;
+  R.src[0] = f + fb; R.src[1] = p.umf + fb; R.src[2] = p.wmf + fb;
+  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(3, 6, P));
+  double *sm = sprof + 5 * npf;
   double *sF1 = sm, *sUU = sm + 3 * P, *smx = sm + 4 * P, *smn = sm + 6 * P, *sUL = sm + 8 * P, *red = sm + 9 * P;
-  const int nzm = p.nzm;
+  // profile slots: 0 = 1/rho, 1 = 1/adz, 2 = 1/(rhow*adz), 3 = rho, 4 = dd/adz with dd = 2/(kc-kb)
+  for (int q = tid; q < nzm * CT; q += P) {
+    const int k = q / CT + 1, ln = q - (k - 1) * CT;
+    const int o = tile * p.nzp * CT + k * CT + ln, so = k * CT + ln;
+    const double rho = p.rho[o], adz = p.adz[o];
+    const int kcc = imin(nzm, k + 1), kbb = imax(1, k - 1);
+    sprof[so] = 1. / rho; sprof[npf + so] = 1. / adz; sprof[2 * npf + so] = 1. / (p.rhow[o] * adz);
+    sprof[3 * npf + so] = rho; sprof[4 * npf + so] = (double)(2.f / (float)(kcc - kbb)) / adz;
+  }
+#define S_IRHO(k) sprof[(k) * CT + lane]
+#define S_IADZ(k) sprof[npf + (k) * CT + lane]
+#define S_IRHOW(k) sprof[2 * npf + (k) * CT + lane]
+#define S_RHO(k) sprof[3 * npf + (k) * CT + lane]
+#define S_DD(k) sprof[4 * npf + (k) * CT + lane]
+  R.init(smraw, P, tid);
+  CRM_PIPE_PROLOGUE(R, nz, 3, 1)
   const double eps = R4(1.e-10);
-  const double *U = p.umf, *W = p.wmf;
-  // own-column windows
-  double f0mm = 0., f0m = 0., f0c = F3(f, 1), f0p = (nzm >= 2) ? F3(f, 2) : 0.;
   double WW_prev = 0. /* WW(ka-1) */, UU_prev = 0. /* UU(ka-2) after shift */, WWlim_k = 0.;
   double mx_prev = 0., mn_prev = 0.;   // normalised mx/mn at level ka-2 (own column)
   double upw_m1 = 0., upw_m2 = 0.;     // upwind www at levels ka-1, ka-2 (stats only)
   for (int ka = 1; ka <= nzm + 2; ka++) {
+    __syncthreads();   // (0) iteration ka-1 complete: ring slot of level ka-3 is free
+    CRM_PIPE_STEP(R, ka, nz, 3, 1)
+    // own-column window of the old field: f(ka-2), f(ka-1), f(ka), f(ka+1)
+    const double f0mm = (ka - 2 >= 1) ? R.plane(0, ka - 2)[tid] : 0.;
+    const double f0m = (ka - 1 >= 1 && ka - 1 <= nzm) ? R.plane(0, ka - 1)[tid] : 0.;
+    const double f0c = (ka <= nzm) ? R.plane(0, ka)[tid] : 0.;
+    const double f0p = (ka + 1 <= nzm) ? R.plane(0, ka + 1)[tid] : 0.;
     // ------------------------------- stage A: first (upwind) pass at level ka
     double upw = 0.;
     if (ka <= nzm) {
-      const double f_im = F3X(f, ka, tm1), f_ip = F3X(f, ka, tp1);
-      const double Ui = F3(U, ka), Uip = F3X(U, ka, tp1);
-      const double Wk = F3(W, ka);
+      const double *F_k = R.plane(0, ka), *U_k = R.plane(1, ka);
+      const double f_im = F_k[tm1], f_ip = F_k[tp1];
+      const double Ui = U_k[tid], Uip = U_k[tp1];
+      const double Wk = R.plane(2, ka)[tid];
       const double uuu_i = dmax(0., Ui) * f_im + dmin(0., Ui) * f0c;
       const double uuu_ip = dmax(0., Uip) * f0c + dmin(0., Uip) * f_ip;
       const double fkb = (ka == 1) ? f0c : f0m;
       const double www_k = dmax(0., Wk) * fkb + dmin(0., Wk) * f0c;
       double www_kp = 0.;
-      if (ka < nzm) { const double Wp = F3(W, ka + 1); www_kp = dmax(0., Wp) * f0c + dmin(0., Wp) * f0p; }
-      const double irho = 1. / PF(p.rho, ka), iadz = 1. / PF(p.adz, ka);
+      if (ka < nzm) { const double Wp = R.plane(2, ka + 1)[tid]; www_kp = dmax(0., Wp) * f0c + dmin(0., Wp) * f0p; }
+      const double irho = S_IRHO(ka), iadz = S_IADZ(ka);
       sF1[(ka % 3) * P + tid] = f0c - (uuu_ip - uuu_i + (www_kp - www_k) * iadz) * irho;
       upw = www_k;
     }
@@ -54,10 +81,11 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_mpdata(CrmP p, double *f, double 
     double WW_ka = 0.;
     if (ka >= 2 && ka <= nzm) {   // WW(1) = 0 (advect_scalar2D.F90:165-169), WW(nz) = 0
       const double *Fa = sF1 + (ka % 3) * P, *Fb = sF1 + ((ka - 1) % 3) * P;
-      const double Wk = F3(W, ka);
-      const double irho = 1. / PF(p.rho, ka), irhow = 1. / (PF(p.rhow, ka) * PF(p.adz, ka));
+      const double *U_k = R.plane(1, ka), *U_b = R.plane(1, ka - 1);
+      const double Wk = R.plane(2, ka)[tid];
+      const double irho = S_IRHO(ka), irhow = S_IRHOW(ka);
       WW_ka = andiff(Fb[tid], Fa[tid], Wk, irhow) -
-              across(Fb[tp1] + Fa[tp1] - Fb[tm1] - Fa[tm1], Wk, F3(U, ka - 1) + F3(U, ka) + F3X(U, ka, tp1) + F3X(U, ka - 1, tp1)) * irho;
+              across(Fb[tp1] + Fa[tp1] - Fb[tm1] - Fa[tm1], Wk, U_b[tid] + U_k[tid] + U_k[tp1] + U_b[tp1]) * irho;
     }
     const int kb_ = ka - 1;
     double UU = 0., mxr = 0., mnr = 0., F1c = 0.;
@@ -65,15 +93,16 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_mpdata(CrmP p, double *f, double 
     if (vB) {
       const int kcc = imin(nzm, kb_ + 1), kbb = imax(1, kb_ - 1);
       const double *Fc = sF1 + (kb_ % 3) * P, *Fu = sF1 + (kcc % 3) * P, *Fd = sF1 + (kbb % 3) * P;
-      const double irho = 1. / PF(p.rho, kb_);
-      const double dd = (double)(2.f / (float)(kcc - kbb)) / PF(p.adz, kb_);
-      const double Ui = F3(U, kb_);
+      const double irho = S_IRHO(kb_);
+      const double dd = S_DD(kb_);
+      const double *W_b = R.plane(2, kb_), *W_c = R.plane(2, kcc), *G_b = R.plane(0, kb_);
+      const double Ui = R.plane(1, kb_)[tid];
       F1c = Fc[tid];
       const double F1m = Fc[tm1], F1p = Fc[tp1];
       UU = andiff(F1m, F1c, Ui, irho) -
-           across(dd * (Fu[tm1] + Fu[tid] - Fd[tm1] - Fd[tid]), Ui, F3X(W, kb_, tm1) + F3X(W, kcc, tm1) + F3(W, kb_) + F3(W, kcc)) * irho;
+           across(dd * (Fu[tm1] + Fu[tid] - Fd[tm1] - Fd[tid]), Ui, W_b[tm1] + W_c[tm1] + W_b[tid] + W_c[tid]) * irho;
       // raw extrema over the 5-point stencils of the old and the first-pass field
-      const double g_im = F3X(f, kb_, tm1), g_ip = F3X(f, kb_, tp1);
+      const double g_im = G_b[tm1], g_ip = G_b[tp1];
       const double g_kb = (kb_ == 1) ? f0m : f0mm, g_kc = (kb_ == nzm) ? f0m : f0c, g_c = f0m;
       const double mx0 = dmax(dmax(dmax(dmax(g_im, g_ip), g_kb), g_kc), g_c);
       const double mn0 = dmin(dmin(dmin(dmin(g_im, g_ip), g_kb), g_kc), g_c);
@@ -85,7 +114,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_mpdata(CrmP p, double *f, double 
     double mx_new = 0., mn_new = 0.;
     if (vB) {
       const double UUp = sUU[tp1];
-      const double rho = PF(p.rho, kb_), iadz = 1. / PF(p.adz, kb_);
+      const double rho = S_RHO(kb_), iadz = S_IADZ(kb_);
       const double WWk = WW_prev;                                  // WW(kb_)
       const double WWkc = (kb_ == nzm) ? WW_prev : WW_ka;           // WW(min(nzm,kb_+1))
       mx_new = rho * (mxr - F1c) / (pn_(UUp) + pp_(UU) + iadz * (pn_(WWkc) + pp_(WWk)) + eps);
@@ -113,13 +142,13 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_mpdata(CrmP p, double *f, double 
     __syncthreads();   // (4)
     if (vC) {
       const double ULp = sUL[tp1];
-      const double irho = 1. / PF(p.rho, kc_), iadz = 1. / PF(p.adz, kc_);
+      const double irho = S_IRHO(kc_), iadz = S_IADZ(kc_);
       const double F1k = sF1[(kc_ % 3) * P + tid];
       const double fnew = dmax(0., F1k - (ULp - ULim + (WWlim_kp1 - WWlim_k) * iadz) * irho);
       F3(f, kc_) = fnew;
       if (stats) {
         double v[2] = {fnew - f0mm, upw_m2 + WWlim_k};
-        block_sum<2>(v, tid, P, CT, red);
+        block_sum_lead<2>(v, tid, P, CT, red);
         if (i == 0) { PF(fadv, kc_) = v[0]; PF(flux, kc_) = v[1]; }
       }
     }
@@ -129,9 +158,12 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_mpdata(CrmP p, double *f, double 
     WW_prev = WW_ka;
     mx_prev = mx_new; mn_prev = mn_new;
     upw_m2 = upw_m1; upw_m1 = upw;
-    f0mm = f0m; f0m = f0c; f0c = f0p;
-    f0p = (ka + 2 <= nzm) ? F3(f, ka + 2) : 0.;
   }
+#undef S_IRHO
+#undef S_IADZ
+#undef S_IRHOW
+#undef S_RHO
+#undef S_DD
 }
 
 // microphysics.F90:453-486
@@ -196,11 +228,29 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_precip_a(CrmP p) {
 
 // microphysics.F90:642-830: nprec sub-iterations of the 1-D MPDATA/FCT sedimentation, one thread per column with a
 // sliding register window (q, wp, tq 3 levels ahead of the level being finalised).
-// smem: CRM_RED_DOUBLES(2,P,CT)
+// First pass (iprec = 1): qp, wp, tabs, t stream through a 6-stage TMA plane ring (levels s-3..s resident).  Later
+// passes re-read what this kernel has just written, so they use ordinary loads (own column only: program order).
+#define CRM_PRECIPB_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(4, 6, P) + CRM_PROF_BYTES(3, nzp, CT) + (size_t)CRM_RED_DOUBLES(2, P, CT) * 8)
 __global__ void __launch_bounds__(CRM_MAX_P) k_precip_b(CrmP p) {
   CRM_TILE_SETUP
-  CRM_DYN_SMEM(double, red);
-  const int nzm = p.nzm;
+  CRM_DYN_SMEM(unsigned char, smraw);
+  const int nzm = p.nzm, npf = p.nzp * CT;
+  PlanePipe<4, 6> R;
+  R.src[0] = p.qp + fb; R.src[1] = p.wp + fb; R.src[2] = p.tabs + fb; R.src[3] = p.t + fb;
+  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(4, 6, P));
+  double *red = sprof + 3 * npf;
+  // profile slots: 0 = 1/(rho*adz), 1 = rho*adz, 2 = rho
+  for (int q = tid; q < nzm * CT; q += P) {
+    const int k = q / CT + 1, ln = q - (k - 1) * CT;
+    const int o = tile * p.nzp * CT + k * CT + ln, so = k * CT + ln;
+    const double rho = p.rho[o], adz = p.adz[o];
+    sprof[so] = 1. / (rho * adz); sprof[npf + so] = rho * adz; sprof[2 * npf + so] = rho;
+  }
+#define S_IRA(k) sprof[(k) * CT + lane]
+#define S_RA(k) sprof[npf + (k) * CT + lane]
+#define S_RHO(k) sprof[2 * npf + (k) * CT + lane]
+  R.init(smraw, P, tid);
+  CRM_PIPE_PROLOGUE(R, nzm, 2, 0)
   const double eps = R4(1.e-10);
   const double dz = p.dz[cb];
   const double prec_cfl = __longlong_as_double((long long)*p.prec_cfl_bits);
@@ -208,6 +258,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_precip_b(CrmP p) {
   if (prec_cfl > R4(0.9)) nprec = (int)ceil(prec_cfl / R4(0.9));
   const long long c2 = (long long)tile * P + tid;
   for (int iprec = 1; iprec <= nprec; iprec++) {
+    const bool ring = (iprec == 1);
     const bool scale_wp = (iprec == 1 && nprec > 1);   // wp = wp/nprec (microphysics.F90:648-660); later iterations store scaled wp
     // window variables, index s = level being loaded
     double q0 = 0., q1 = 0., q2 = 0., q3 = 0.;          // q(s-3), q(s-2), q(s-1), q(s)
@@ -219,24 +270,28 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_precip_b(CrmP p) {
     double fzl0 = 0., fzl1 = 0.;                        // limited flux at s-3, s-2
     double om0 = 0., om1 = 0., om2 = 0., om3 = 0.;      // omega(s-3..s)
     for (int s = 1; s <= nzm + 3; s++) {
+      if (ring) {
+        __syncthreads();
+        CRM_PIPE_STEP(R, s, nzm, 2, 0)
+      }
       // ---- load level s
       q0 = q1; q1 = q2; q2 = q3; w1 = w2; w2 = w3; fz2 = fz3; om0 = om1; om1 = om2; om2 = om3;
       if (s <= nzm) {
-        q3 = F3(p.qp, s);
-        w3 = F3(p.wp, s);
+        q3 = ring ? R.plane(0, s)[tid] : F3(p.qp, s);
+        w3 = ring ? R.plane(1, s)[tid] : F3(p.wp, s);
         if (scale_wp) { w3 = w3 / (double)nprec; }
         fz3 = q3 * w3;
-        om3 = dmax(0., dmin(1., (F3(p.tabs, s) - CRM_TPRMIN) * p.ms.a_pr));
+        om3 = dmax(0., dmin(1., ((ring ? R.plane(2, s)[tid] : F3(p.tabs, s)) - CRM_TPRMIN) * p.ms.a_pr));
       } else { q3 = 0.; w3 = 0.; fz3 = 0.; om3 = 0.; }
       // ---- tq(s-1)
       tq0 = tq1; tq1 = tq2;
       const int k1 = s - 1;
-      if (k1 >= 1 && k1 <= nzm) tq2 = q2 - (fz3 - fz2) / 1. * (1. / (PF(p.rho, k1) * PF(p.adz, k1)));
+      if (k1 >= 1 && k1 <= nzm) tq2 = q2 - (fz3 - fz2) / 1. * S_IRA(k1);
       else tq2 = 0.;
       // ---- www(s-1) = 0.5*(1+wp*irhoadz)*(tq(kb)*wp(kb) - tq(k)*wp(k)), kb = max(1,k-1)
       ww1 = ww2;
       if (k1 >= 2 && k1 <= nzm) {
-        const double irhoadz = 1. / (PF(p.rho, k1) * PF(p.adz, k1));
+        const double irhoadz = S_IRA(k1);
         ww2 = 0.5 * (1. + w2 * irhoadz) * (tq1 * w1 - tq2 * w2);
       } else ww2 = 0.;   // level 1: kb = k -> exactly 0; level nz: www(nz) = 0
       // ---- normalised extrema at k2 = s-2
@@ -250,7 +305,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_precip_b(CrmP p) {
         mx = dmax(max3(tb, tc, tq1), mx);
         mn = dmin(min3(tb, tc, tq1), mn);
         const double wwc = (k2 == nzm) ? ww1 : ww2;   // www(min(nzm,k2+1))
-        const double ra = PF(p.rho, k2) * PF(p.adz, k2);
+        const double ra = S_RA(k2);
         mxn1 = ra * (mx - tq1) / (pn_(wwc) + pp_(ww1) + eps);
         mnn1 = ra * (tq1 - mn) / (pp_(wwc) + pn_(ww1) + eps);
       } else { mxn1 = 0.; mnn1 = 0.; }
@@ -264,30 +319,33 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_precip_b(CrmP p) {
       // ---- final update at k3 = s-3
       const int k3 = s - 3;
       if (k3 >= 1 && k3 <= nzm) {
-        const double irhoadz = 1. / (PF(p.rho, k3) * PF(p.adz, k3));
+        const double irhoadz = S_IRA(k3);
         const double dq = -(fzl1 - fzl0) * irhoadz;
         const double qnew = q0 - (fzl1 - fzl0) * irhoadz;
         F3(p.qp, k3) = qnew;
         const double lf0 = CRM_FAC_COND + (1 - om0) * CRM_FAC_FUS;
         const double lf1 = (k3 + 1 <= nzm) ? CRM_FAC_COND + (1 - om1) * CRM_FAC_FUS : 0.;
         const double lat_heat = -(lf1 * fzl1 - lf0 * fzl0) * irhoadz;
-        F3(p.t, k3) = F3(p.t, k3) - lat_heat;
+        F3(p.t, k3) = (ring ? R.plane(3, k3)[tid] : F3(p.t, k3)) - lat_heat;
         if (k3 == 1) {
           p.precsfc[c2] = p.precsfc[c2] - fzl0 * 1.;
           p.precssfc[c2] = p.precssfc[c2] - fzl0 * (1. - om0) * 1.;
         }
         if (iprec < nprec) {   // new fall speed for the next iteration (microphysics.F90:794-817)
-          const double rho = PF(p.rho, k3);
-          const double tv = term_vel_qp(p.ms, qnew, rho, F3(p.tabs, k3));
+          const double rho = S_RHO(k3);
+          const double tv = term_vel_qp(p.ms, qnew, rho, ring ? R.plane(2, k3)[tid] : F3(p.tabs, k3));
           const double wpv = sqrt(R4(1.29) / rho) * tv;
           F3(p.wp, k3) = -wpv * PF(p.rhow, k3) * p.dtn / dz / (double)nprec;
         }
         double v[2] = {dq, fzl0};
-        block_sum<2>(v, tid, P, CT, red);
+        block_sum_lead<2>(v, tid, P, CT, red);
         if (i == 0) { PF(p.qpfall, k3) = PF(p.qpfall, k3) + v[0]; PF(p.precflux, k3) = PF(p.precflux, k3) - v[1]; }
       }
     }
   }
+#undef S_IRA
+#undef S_RA
+#undef S_RHO
 }
 
 // diffuse_scalar2D.F90:70-138 + diffuse_scalar.F90:55-70 for t, qt, qp in one pass (fluxb = fluxt = 0).
@@ -346,7 +404,7 @@ __global__ void __launch_bounds__(256) k_p7_diffuse(CrmP p) {
     for (int s = 0; s < 3; s++) fld[s][fb + (long long)(k - 1) * P + tid] = fnew[s];
     if (p.last_substep) {   // mkdiff (fdiff) and mkwsb (flux at the lower face of level k) for qt, qp
       double v[4] = {fnew[1] - fold[1], fnew[2] - fold[2], flz_km1[1], flz_km1[2]};
-      block_sum<4>(v, tid, P, CT, red);
+      block_sum_lead<4>(v, tid, P, CT, red);
       if (i == 0) { PF(p.mkdiff1, k) = v[0]; PF(p.mkdiff2, k) = v[1]; PF(p.mkwsb1, k) = v[2]; PF(p.mkwsb2, k) = v[3]; }
     }
 #pragma unroll
@@ -521,7 +579,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p8_micro(CrmP p, int do_micro, in
   }
   double v[9];
   v[0] = F3(p.u, k); v[1] = t; v[2] = tabs; v[3] = qv + qcl + qci; v[4] = qcl + qci; v[5] = qpl + qpi; v[6] = dsrc; v[7] = devp; v[8] = 0.;
-  block_sum<9>(v, tid, P, CT, red);   // (contains the barrier that orders the sflag reset)
+  block_sum_lead<9>(v, tid, P, CT, red);   // (contains the barrier that orders the sflag reset)
   if (do_diag) {
     if (qcl + qci > 0. && tabs < R4(273.15)) sflag[lane] = 1;
   }
@@ -555,7 +613,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_msa_a(CrmP p) {
   CRM_DYN_SMEM(double, red);
   const double coef = 1. / (double)(p.nx * p.ny);
   double v[3] = {F3(p.t, k) * coef, (F3(p.qcl, k) + F3(p.qci, k) + F3(p.qv, k)) * coef, F3(p.u, k) * coef};
-  block_sum<3>(v, tid, P, CT, red);
+  block_sum_lead<3>(v, tid, P, CT, red);
   if (i == 0) {
     const double ta = v[0] - PF(p.t0, k);
     PF(p.acc_t, k) = ta;

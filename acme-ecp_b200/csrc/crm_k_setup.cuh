@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_prologue_fields(CrmP p) {
     double v[9];
     v[0] = u; v[1] = t; v[2] = t + CRM_FAC_COND * qpl + CRM_FAC_SUB * qpi; v[3] = tabs; v[4] = qv + qcl + qci;
     v[5] = qv; v[6] = qcl + qci; v[7] = qpl + qpi; v[8] = 0.;
-    block_sum<9>(v, tid, P, CT, red);
+    block_sum_lead<9>(v, tid, P, CT, red);
     if (i == 0) {
       double u0 = v[0] * factor_xy, t0 = v[1] * factor_xy, t00 = v[2] * factor_xy, tabs0 = v[3] * factor_xy, q0 = v[4] * factor_xy;
       PF(p.u0, k) = u0; PF(p.t0, k) = t0; PF(p.t00, k) = t00; PF(p.tabs0, k) = tabs0; PF(p.q0, k) = q0;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_prologue_fields(CrmP p) {
     }
   }
   double v[2] = {colprec, colprecs};
-  block_sum<2>(v, tid, P, CT, red);
+  block_sum_lead<2>(v, tid, P, CT, red);
   if (i == 0) { p.colprec0[cb] = v[0]; p.colprecs0[cb] = v[1]; }
   if (kmax > 0) { atomicMin(&p.kmin[cb], kmin); atomicMax(&p.kmax[cb], kmax); }
 }

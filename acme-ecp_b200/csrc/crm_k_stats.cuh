@@ -7,21 +7,49 @@ namespace crm {
 
 // Per-nstep statistics.  Block per tile; marches from the top (the reference's cwp scan uses kk = nz-k, and books
 // the cloud-top hit at GCM level l(k), i.e. at CRM level k = nz-kk: quirk kept).
-// smem: CRM_RED_DOUBLES(10,P,CT) + 5*P doubles
+// Descending TMA plane rings: A = qcl, qci, tabs, qpl, qpi (levels kk-1..kk+1 resident, 5 stages), B = w, qv (levels
+// kk, kk+1, 4 stages).  Radiation-group sums use warp shuffles when a group lies inside a warp.
+#define CRM_STATS_SMEM(P, CT, nzp) \
+  (CRM_PIPE_BYTES(5, 5, P) + CRM_PIPE_BYTES(2, 4, P) + CRM_PROF_BYTES(4, nzp, CT) + (size_t)(CRM_RED_DOUBLES(10, P, CT) + 5 * (P)) * 8)
 __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
   CRM_TILE_SETUP
-  CRM_DYN_SMEM(double, sm);
-  double *red = sm, *srad = sm + CRM_RED_DOUBLES(10, P, CT);
-  const int nzm = p.nzm, nz = p.nz;
+  CRM_DYN_SMEM(unsigned char, smraw);
+  const int nzm = p.nzm, nz = p.nz, npf = p.nzp * CT;
+  PlanePipe<5, 5> A;
+  PlanePipe<2, 4> B;
+  A.src[0] = p.qcl + fb; A.src[1] = p.qci + fb; A.src[2] = p.tabs + fb; A.src[3] = p.qpl + fb; A.src[4] = p.qpi + fb;
+  B.src[0] = p.w + fb; B.src[1] = p.qv + fb;
+  unsigned char *sm2 = smraw + CRM_PIPE_BYTES(5, 5, P);
+  double *sprof = (double *)(sm2 + CRM_PIPE_BYTES(2, 4, P));
+  double *red = sprof + 4 * npf, *srad = red + CRM_RED_DOUBLES(10, P, CT);
+  {
+    const double *const g[4] = {p.rho, p.adz, p.pres, p.rhow};
+    stage_profiles<4>(sprof, g, tile, p.nzp, CT, tid, P);
+  }
+#define SPF(r, k) sprof[(r) * npf + (k) * CT + lane]
+  A.init(smraw, P, tid);
+  B.init(sm2, P, tid);
+  // top level nz of B (w(nz)) is needed by level nzm; A starts at nzm
+  if (tid == 0) {
+    A.issue(nzm); if (nzm >= 2) A.issue(nzm - 1); if (nzm >= 3) A.issue(nzm - 2);
+    B.issue(nz); B.issue(nzm); if (nzm >= 2) B.issue(nzm - 1);
+  }
+  A.wait_desc(nzm, nzm);
+  B.wait_desc(nz, nz);
   const double dz = p.dz[cb];
   const double cwp_threshold = R4(0.001), wmin = R4(2.);
   const int grp = p.nx / p.nx_rad;
+  const bool grp_in_warp = (grp * CT <= 32) && !(grp & (grp - 1));
   double cwp = 0., cwph = 0., cwpm = 0., cwpl = 0., cltemp = 0., cmtemp = 0., chtemp = 0., cttemp = 0.;
   bool flag_top = true;
   for (int kk = nzm; kk >= 1; kk--) {   // kk = nz-k of the reference's loop counter k
     const int kmir = nz - kk;           // the loop counter k (1..nzm) at which level kk is scanned
-    const double qcl = F3(p.qcl, kk), qci = F3(p.qci, kk);
-    const double rho = PF(p.rho, kk), adz = PF(p.adz, kk), pres = PF(p.pres, kk);
+    __syncthreads();
+    if (tid == 0) { if (kk - 3 >= 1) A.issue(kk - 3); if (kk - 2 >= 1) B.issue(kk - 2); }
+    if (kk - 1 >= 1) A.wait_desc(kk - 1, nzm);
+    B.wait_desc(kk, nz);
+    const double qcl = A.plane(0, kk)[tid], qci = A.plane(1, kk)[tid];
+    const double rho = SPF(0, kk), adz = SPF(1, kk), pres = SPF(2, kk);
     double tmp1 = rho * adz * dz * (qcl + qci);
     cwp = cwp + tmp1;
     cttemp = dmax(1., cttemp);
@@ -32,7 +60,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
     else { cwpm = cwpm + tmp1; cmtemp = dmax(1., cmtemp); }
     // level-local part, evaluated for level kk (sums over levels are order independent across k)
     tmp1 = rho * adz * dz;
-    const double w_k = F3(p.w, kk), w_kc = F3(p.w, kk + 1);
+    const double w_k = B.plane(0, kk)[tid], w_kc = B.plane(0, kk + 1)[tid];
     const double wsum = w_kc + w_k;
     double cld = 0., mcup = 0., mcdn = 0., mcuup = 0., mcudn = 0.;
     if (tmp1 * (qcl + qci) > cwp_threshold) {
@@ -47,16 +75,16 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
     double mui = 0., mdi = 0.;
     if (w_k > 0.) {
       const int kx = imax(1, kk - 1);
-      const double qsat = qsatw_crm(F3(p.tabs, kx), PF(p.pres, kx));
-      if (F3(p.qcl, kx) + F3(p.qci, kx) > dmin(R4(1.e-5), R4(0.01) * qsat)) mui = PF(p.rhow, kk) * w_k;
+      const double qsat = qsatw_crm(A.plane(2, kx)[tid], SPF(2, kx));
+      if (A.plane(0, kx)[tid] + A.plane(1, kx)[tid] > dmin(R4(1.e-5), R4(0.01) * qsat)) mui = SPF(3, kk) * w_k;
     } else if (w_k < 0.) {
       const int kx = imin(kk + 1, nzm);
-      const double qsat = qsatw_crm(F3(p.tabs, kx), PF(p.pres, kx));
-      if (F3(p.qcl, kx) + F3(p.qci, kx) > dmin(R4(1.e-5), R4(0.01) * qsat)) mdi = PF(p.rhow, kk) * w_k;
-      else if (F3(p.qpl, kx) + F3(p.qpi, kx) > R4(1.0e-4)) mdi = PF(p.rhow, kk) * w_k;
+      const double qsat = qsatw_crm(A.plane(2, kx)[tid], SPF(2, kx));
+      if (A.plane(0, kx)[tid] + A.plane(1, kx)[tid] > dmin(R4(1.e-5), R4(0.01) * qsat)) mdi = SPF(3, kk) * w_k;
+      else if (A.plane(3, kx)[tid] + A.plane(4, kx)[tid] > R4(1.0e-4)) mdi = SPF(3, kk) * w_k;
     }
     double v[10] = {cld, mcup, mcdn, mcuup, mcudn, qcl, qci, top_hit, mui, mdi};
-    block_sum<10>(v, tid, P, CT, red);
+    block_sum_lead<10>(v, tid, P, CT, red);
     if (i == 0) {
       PF(p.s_cld, kk) += v[0]; PF(p.s_mcup, kk) += v[1]; PF(p.s_mcdn, kk) += v[2]; PF(p.s_mcuup, kk) += v[3]; PF(p.s_mcudn, kk) += v[4];
       PF(p.s_gliqwp, kk) += v[5]; PF(p.s_gicewp, kk) += v[6];
@@ -64,20 +92,29 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
       PF(p.s_mui, kk) += v[8]; PF(p.s_mdi, kk) += v[9];
     }
     // radiation-group accumulators (crm_module.F90:979-1015): groups of nx/nx_rad adjacent columns
-    const double tabs = F3(p.tabs, kk), qv = F3(p.qv, kk);
-    __syncthreads();
-    srad[tid] = tabs; srad[P + tid] = dmax(0., qv); srad[2 * P + tid] = qcl; srad[3 * P + tid] = qci;
-    srad[4 * P + tid] = (qcl + qci > 0) ? 1. : 0.;
-    __syncthreads();
+    const double tabs = A.plane(2, kk)[tid], qv = B.plane(1, kk)[tid];
+    double a[5] = {tabs, dmax(0., qv), qcl, qci, (qcl + qci > 0) ? 1. : 0.};
+    if (grp_in_warp) {   // ascending-pair tree inside the warp
+      for (int off = CT; off < grp * CT; off <<= 1) {
+#pragma unroll
+        for (int q = 0; q < 5; q++) a[q] += __shfl_xor_sync(0xffffffffu, a[q], off);
+      }
+    } else {
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 5; q++) srad[q * P + tid] = a[q];
+      __syncthreads();
+      if (i % grp == 0) {
+        for (int q = 0; q < 5; q++) {
+          double s = srad[q * P + tid];
+          for (int d = 1; d < grp; d++) s += srad[q * P + tid + d * CT];
+          a[q] = s;
+        }
+      }
+    }
     if (i % grp == 0) {
       const int ir = i / grp;
       const long long ro = ((long long)tile * nzm + (kk - 1)) * (p.nx_rad * CT) + ir * CT + lane;
-      double a[5];
-      for (int q = 0; q < 5; q++) {
-        double s = srad[q * P + tid];
-        for (int d = 1; d < grp; d++) s += srad[q * P + tid + d * CT];
-        a[q] = s;
-      }
       p.rad_t[ro] += a[0]; p.rad_qv[ro] += a[1]; p.rad_qc[ro] += a[2]; p.rad_qi[ro] += a[3]; p.rad_cld[ro] += a[4];
     }
   }
@@ -85,8 +122,9 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
   double v[4];
   v[0] = (cwp > cwp_threshold) ? cttemp : 0.; v[1] = (cwph > cwp_threshold) ? chtemp : 0.;
   v[2] = (cwpm > cwp_threshold) ? cmtemp : 0.; v[3] = (cwpl > cwp_threshold) ? cltemp : 0.;
-  block_sum<4>(v, tid, P, CT, red);
+  block_sum_lead<4>(v, tid, P, CT, red);
   if (i == 0) { p.s_cltot[cb] += v[0]; p.s_clhgh[cb] += v[1]; p.s_clmed[cb] += v[2]; p.s_cllow[cb] += v[3]; }
+#undef SPF
 }
 
 // Epilogue slab sums (crm_module.F90:1147-1183, 1314-1356, 1517-1584).  Plane kernel; results in the scratch
@@ -109,7 +147,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_epi_sums(CrmP p, double *esum) {
   v[7] = qpl; v[8] = qpi * omg; v[9] = qpi * (1. - omg);
   v[10] = (u - u0) * (u - u0); v[11] = 0.5 * (w_kc * w_kc + w_k * w_k);
   v[12] = F3(p.tke, k); v[13] = F3(p.tk, k);
-  block_sum<CRM_NESUM>(v, tid, P, CT, red);
+  block_sum_lead<CRM_NESUM>(v, tid, P, CT, red);
   if (i == 0) {
     const size_t np = (size_t)p.ntiles * p.nzp * CT;
     for (int q = 0; q < CRM_NESUM; q++) esum[q * np + pb + k * CT] = v[q];
@@ -139,7 +177,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_epi_precip(CrmP p, ExtOut o, doub
   double v[4];
   if (ps > thr) { v[0] = ps; v[1] = pss; v[2] = 0.; v[3] = 0.; }
   else { v[0] = 0.; v[1] = 0.; v[2] = ps; v[3] = pss; }
-  block_sum<4>(v, tid, P, CT, red);
+  block_sum_lead<4>(v, tid, P, CT, red);
   const int icrm = cb;
   if (icrm < p.ncrms) {
     o.prec_crm[(size_t)icrm + (size_t)p.ld * (size_t)i] = ps / R4(1000.);

@@ -5,6 +5,7 @@ thread_local emu_dim3 threadIdx, blockIdx;
 emu_dim3 blockDim, gridDim;
 pthread_barrier_t emu_barrier;
 char *emu_dyn_smem = nullptr;
+double emu_shfl_buf[2048];
 
 void emu_launch(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body) {
   gridDim.x = grid; blockDim.x = block;

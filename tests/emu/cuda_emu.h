@@ -30,6 +30,16 @@ extern char *emu_dyn_smem;
 
 static inline void __syncthreads() { pthread_barrier_wait(&emu_barrier); }
 
+// warp shuffles: emulated block-wide (all threads of the block must call convergently, which the kernels guarantee)
+extern double emu_shfl_buf[2048];
+static inline double __shfl_xor_sync(unsigned, double v, int lanemask) {
+  emu_shfl_buf[threadIdx.x] = v;
+  pthread_barrier_wait(&emu_barrier);
+  double r = emu_shfl_buf[threadIdx.x ^ (unsigned)lanemask];
+  pthread_barrier_wait(&emu_barrier);
+  return r;
+}
+
 static inline unsigned long long atomicMax(unsigned long long *a, unsigned long long v) {
   unsigned long long old = *a;
   while (old < v && !__atomic_compare_exchange_n(a, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
