@@ -108,6 +108,15 @@ __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : 
 __device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
 __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
 __device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
+// accumulate into a global accumulator that only this thread updates during the kernel: a fire-and-forget reduction
+// (RED.ADD.F64) instead of a load-add-store round trip that would stall the whole block at the next barrier
+__device__ __forceinline__ void acc_add(double *a, double v) {
+#ifdef CRM_EMU
+  *a += v;
+#else
+  atomicAdd(a, v);
+#endif
+}
 __device__ __forceinline__ double pp_(double y) { return dmax(0., y); }
 __device__ __forceinline__ double pn_(double y) { return -dmin(0., y); }
 
@@ -176,6 +185,27 @@ __device__ __forceinline__ void block_sum_impl(double (&v)[NQ], int tid, int P, 
       for (int g = 1; g < nw; g++) s += red[(g * NQ + q) * CT + lane];
       v[q] = s;
     }
+  }
+}
+// block_sum_each: the NQ*CT final sums are spread over the first NQ*CT threads (one short chain each instead of NQ
+// chains in CT leader threads); f(q, lane, sum) is called once per (quantity, CRM lane).
+template <int NQ, class F>
+__device__ __forceinline__ void block_sum_each(double (&v)[NQ], int tid, int P, int CT, double *red, F f) {
+  const int lane = tid & (CT - 1), w = tid >> 5, nw = P >> 5;
+#pragma unroll
+  for (int q = 0; q < NQ; q++)
+    for (int off = CT; off < 32; off <<= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], off);
+  __syncthreads();
+  if ((tid & 31) < CT) {
+#pragma unroll
+    for (int q = 0; q < NQ; q++) red[(w * NQ + q) * CT + lane] = v[q];
+  }
+  __syncthreads();
+  for (int t = tid; t < NQ * CT; t += P) {
+    const int q = t / CT, ln = t - q * CT;
+    double s = red[q * CT + ln];
+    for (int g = 1; g < nw; g++) s += red[(g * NQ + q) * CT + ln];
+    f(q, ln, s);
   }
 }
 template <int NQ>

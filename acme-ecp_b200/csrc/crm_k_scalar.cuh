@@ -18,7 +18,7 @@ __device__ __forceinline__ double min3(double a, double b, double c) { return dm
 // Pipeline per iteration ka (1..nzm+2):  A: upwind pass -> F1(ka);  B: antidiffusive velocities UU(ka-1), WW(ka),
 // FCT ratios mx/mn(ka-1);  C: limited fluxes and final update of level ka-2.  U = umf, W = wmf (mass-flux
 // velocities of adams).  fadv/flux: optional profile outputs (mkadv/mkwle), written only when `stats`.
-// f, U, W stream through a 6-stage TMA plane ring (levels ka-2..ka+1 resident, 2 levels of prefetch); the reciprocal
+// f, U, W stream through a 6-stage TMA plane ring (levels ka-2..ka+1 resident, up to 3 levels of prefetch); the reciprocal
 // grid profiles (1/rho, 1/adz, 1/(rhow*adz), 2/((kc-kb)*adz)) are evaluated once per block into shared memory.
 #define CRM_MP_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(3, 6, P) + CRM_PROF_BYTES(5, nzp, CT) + (size_t)(9 * (P) + CRM_RED_DOUBLES(2, P, CT)) * 8)
 __global__ void __launch_bounds__(CRM_MAX_P) k_mpdata(CrmP p, double *f, double *fadv, double *flux, int stats) {
@@ -46,14 +46,13 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_mpdata(CrmP p, double *f, double 
 #define S_RHO(k) sprof[3 * npf + (k) * CT + lane]
 #define S_DD(k) sprof[4 * npf + (k) * CT + lane]
   R.init(smraw, P, tid);
-  CRM_PIPE_PROLOGUE(R, nz, 3, 1)
+  CRM_PIPE_PROLOGUE(R, nz, 4, 1)
   const double eps = R4(1.e-10);
   double WW_prev = 0. /* WW(ka-1) */, UU_prev = 0. /* UU(ka-2) after shift */, WWlim_k = 0.;
   double mx_prev = 0., mn_prev = 0.;   // normalised mx/mn at level ka-2 (own column)
   double upw_m1 = 0., upw_m2 = 0.;     // upwind www at levels ka-1, ka-2 (stats only)
   for (int ka = 1; ka <= nzm + 2; ka++) {
-    __syncthreads();   // (0) iteration ka-1 complete: ring slot of level ka-3 is free
-    CRM_PIPE_STEP(R, ka, nz, 3, 1)
+    if (ka + 1 <= nz) R.wait(ka + 1);
     // own-column window of the old field: f(ka-2), f(ka-1), f(ka), f(ka+1)
     const double f0mm = (ka - 2 >= 1) ? R.plane(0, ka - 2)[tid] : 0.;
     const double f0m = (ka - 1 >= 1 && ka - 1 <= nzm) ? R.plane(0, ka - 1)[tid] : 0.;
@@ -76,7 +75,8 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_mpdata(CrmP p, double *f, double 
       sF1[(ka % 3) * P + tid] = f0c - (uuu_ip - uuu_i + (www_kp - www_k) * iadz) * irho;
       upw = www_k;
     }
-    __syncthreads();   // (1)
+    __syncthreads();   // (1)  (also: every thread has read level ka-2 of the ring, its slot can be refilled)
+    if (tid == 0 && ka + 4 <= nz) R.issue(ka + 4);
     // ------------------------------- stage B
     double WW_ka = 0.;
     if (ka >= 2 && ka <= nzm) {   // WW(1) = 0 (advect_scalar2D.F90:165-169), WW(nz) = 0
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_precip_b(CrmP p) {
         }
         double v[2] = {dq, fzl0};
         block_sum_lead<2>(v, tid, P, CT, red);
-        if (i == 0) { PF(p.qpfall, k3) = PF(p.qpfall, k3) + v[0]; PF(p.precflux, k3) = PF(p.precflux, k3) - v[1]; }
+        if (i == 0) { acc_add(&PF(p.qpfall, k3), v[0]); acc_add(&PF(p.precflux, k3), -v[1]); }
       }
     }
   }
@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p8_micro(CrmP p, int do_micro, in
   const int pb = tile * p.nzp * CT + lane;
   const int cb = tile * CT + lane;
   CRM_DYN_SMEM(double, red);
-  int *sflag = (int *)(red + CRM_RED_DOUBLES(9, P, CT));
+  int *sflag = (int *)(red + CRM_RED_DOUBLES(8, P, CT));
   double t = F3(p.t, k), q = F3(p.qt, k), qp = F3(p.qp, k), qn = F3(p.qn, k), tabs = F3(p.tabs, k);
   double qv = F3(p.qv, k), qcl = F3(p.qcl, k), qci = F3(p.qci, k), qpl = F3(p.qpl, k), qpi = F3(p.qpi, k);
   double dsrc = 0., devp = 0.;
@@ -573,27 +573,38 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p8_micro(CrmP p, int do_micro, in
     if (!do_diag) F3(p.tabs, k) = tabs;
   }
   if (tid < 2 * CT) sflag[tid] = 0;
+  __syncthreads();
   if (do_diag) {
     tabs = t - PF(p.gamaz, k) + CRM_FAC_COND * (qcl + qpl) + CRM_FAC_SUB * (qci + qpi);
     F3(p.tabs, k) = tabs;
   }
-  double v[9];
-  v[0] = F3(p.u, k); v[1] = t; v[2] = tabs; v[3] = qv + qcl + qci; v[4] = qcl + qci; v[5] = qpl + qpi; v[6] = dsrc; v[7] = devp; v[8] = 0.;
-  block_sum_lead<9>(v, tid, P, CT, red);   // (contains the barrier that orders the sflag reset)
+  double v[8];
+  v[0] = F3(p.u, k); v[1] = t; v[2] = tabs; v[3] = qv + qcl + qci; v[4] = qcl + qci; v[5] = qpl + qpi; v[6] = dsrc; v[7] = devp;
   if (do_diag) {
-    if (qcl + qci > 0. && tabs < R4(273.15)) sflag[lane] = 1;
+    if (qcl + qci > 0. && tabs < R4(273.15)) sflag[lane] = 1;   // (the reset above is ordered by the barrier that follows it)
   }
-  if (i == 0) {
-    if (do_diag) {
-      const double coef = (double)1.f / (double)(p.nx * p.ny);
-      PF(p.u0, k) = v[0] * coef; PF(p.t0, k) = v[1] * coef; PF(p.tabs0, k) = v[2] * coef;
-      const double q0 = v[3] * coef, qn0 = v[4] * coef;
-      PF(p.q0, k) = q0; PF(p.qn0, k) = qn0; PF(p.qp0, k) = v[5] * coef;
-      PF(p.qv0, k) = q0 - qn0;
+  const int last = p.last_substep;
+  block_sum_each<8>(v, tid, P, CT, red, [&](int q, int ln, double sum) {
+    const int o = tile * p.nzp * CT + k * CT + ln;
+    if (q < 6) {
+      if (do_diag) {
+        const double coef = (double)1.f / (double)(p.nx * p.ny);
+        const double m = sum * coef;
+        if (q == 0) p.u0[o] = m;
+        else if (q == 1) p.t0[o] = m;
+        else if (q == 2) p.tabs0[o] = m;
+        else if (q == 3) p.q0[o] = m;
+        else if (q == 4) {   // qn0 and qv0 = q0 - qn0: re-sum quantity 3 in the same fixed order
+          const int nw = P >> 5;
+          double s3 = red[3 * CT + ln];
+          for (int g = 1; g < nw; g++) s3 += red[(g * 8 + 3) * CT + ln];
+          p.qn0[o] = m; p.qv0[o] = s3 * coef - m;
+        } else p.qp0[o] = m;
+      }
+    } else if (do_micro && last) {
+      if (q == 6) p.qpsrc[o] = sum; else p.qpevp[o] = sum;
     }
-    if (do_micro && p.last_substep) { PF(p.qpsrc, k) = v[6]; PF(p.qpevp, k) = v[7]; }
-  }
-  __syncthreads();
+  });
   if (do_diag && i == 0 && sflag[lane]) { atomicMin(&p.kmin[cb], k); atomicMax(&p.kmax[cb], k); }
 }
 

@@ -84,13 +84,11 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
       else if (A.plane(3, kx)[tid] + A.plane(4, kx)[tid] > R4(1.0e-4)) mdi = SPF(3, kk) * w_k;
     }
     double v[10] = {cld, mcup, mcdn, mcuup, mcudn, qcl, qci, top_hit, mui, mdi};
-    block_sum_lead<10>(v, tid, P, CT, red);
-    if (i == 0) {
-      PF(p.s_cld, kk) += v[0]; PF(p.s_mcup, kk) += v[1]; PF(p.s_mcdn, kk) += v[2]; PF(p.s_mcuup, kk) += v[3]; PF(p.s_mcudn, kk) += v[4];
-      PF(p.s_gliqwp, kk) += v[5]; PF(p.s_gicewp, kk) += v[6];
-      PF(p.s_cldtop, kmir) += v[7];
-      PF(p.s_mui, kk) += v[8]; PF(p.s_mdi, kk) += v[9];
-    }
+    block_sum_each<10>(v, tid, P, CT, red, [&](int q, int ln, double sum) {
+      double *dst = (q == 0) ? p.s_cld : (q == 1) ? p.s_mcup : (q == 2) ? p.s_mcdn : (q == 3) ? p.s_mcuup : (q == 4) ? p.s_mcudn :
+                    (q == 5) ? p.s_gliqwp : (q == 6) ? p.s_gicewp : (q == 7) ? p.s_cldtop : (q == 8) ? p.s_mui : p.s_mdi;
+      acc_add(dst + tile * p.nzp * CT + ((q == 7) ? kmir : kk) * CT + ln, sum);
+    });
     // radiation-group accumulators (crm_module.F90:979-1015): groups of nx/nx_rad adjacent columns
     const double tabs = A.plane(2, kk)[tid], qv = B.plane(1, kk)[tid];
     double a[5] = {tabs, dmax(0., qv), qcl, qci, (qcl + qci > 0) ? 1. : 0.};
@@ -115,7 +113,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
     if (i % grp == 0) {
       const int ir = i / grp;
       const long long ro = ((long long)tile * nzm + (kk - 1)) * (p.nx_rad * CT) + ir * CT + lane;
-      p.rad_t[ro] += a[0]; p.rad_qv[ro] += a[1]; p.rad_qc[ro] += a[2]; p.rad_qi[ro] += a[3]; p.rad_cld[ro] += a[4];
+      acc_add(p.rad_t + ro, a[0]); acc_add(p.rad_qv + ro, a[1]); acc_add(p.rad_qc + ro, a[2]); acc_add(p.rad_qi + ro, a[3]); acc_add(p.rad_cld + ro, a[4]);
     }
   }
   // w-level nz (k = nzm+1 of crm_module.F90:1023): w(nz) = 0 -> no contribution.
@@ -147,11 +145,8 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_epi_sums(CrmP p, double *esum) {
   v[7] = qpl; v[8] = qpi * omg; v[9] = qpi * (1. - omg);
   v[10] = (u - u0) * (u - u0); v[11] = 0.5 * (w_kc * w_kc + w_k * w_k);
   v[12] = F3(p.tke, k); v[13] = F3(p.tk, k);
-  block_sum_lead<CRM_NESUM>(v, tid, P, CT, red);
-  if (i == 0) {
-    const size_t np = (size_t)p.ntiles * p.nzp * CT;
-    for (int q = 0; q < CRM_NESUM; q++) esum[q * np + pb + k * CT] = v[q];
-  }
+  const size_t np = (size_t)p.ntiles * p.nzp * CT;
+  block_sum_each<CRM_NESUM>(v, tid, P, CT, red, [&](int q, int ln, double sum) { esum[q * np + tile * p.nzp * CT + k * CT + ln] = sum; });
 }
 
 struct ExtOut {   // device staging of the (ld,plev) / (ld) outputs; same member names as crm_output_type
