@@ -68,6 +68,7 @@ struct Handle {
   crm_dims_t d0;          // init dims
   int device = 0;
   int CT = 8, ntiles = 0, P = 0, nzp = 0;
+  int geo = 0;            // static-geometry kernel variant (nx) or 0 = runtime geometry
   long long tstride = 0;
   size_t field_elems = 0, prof_elems = 0, col_elems = 0, slot_elems = 0, rad_elems = 0;
   std::vector<void *> allocs;
@@ -102,13 +103,23 @@ static void ktime_add(std::vector<KTime> &v, const char *name, double ms) {
   for (auto &k : v) if (k.name == name || !strcmp(k.name, name)) { k.ms += ms; k.n++; return; }
   v.push_back({name, ms, 1});
 }
-static std::string kname(const char *s) { std::string n(s); size_t q = n.find('<'); return q == std::string::npos ? n : n.substr(0, q); }
+static std::string kname(const char *s) { std::string n(s); while (!n.empty() && n[0] == '(') n.erase(0, 1); size_t q = n.find('<'); return q == std::string::npos ? n : n.substr(0, q); }
 #define LAUNCH(h, kern, grid, block, smem, ...)                 \
   do {                                                          \
     if ((h)->ktiming) (h)->ktimer.start();                      \
     CRM_LAUNCH(kern, grid, block, smem, 0, __VA_ARGS__);        \
     if ((h)->ktiming) ktime_add((h)->ktimes, #kern, (h)->ktimer.stop()); \
     (h)->launches++;                                            \
+  } while (0)
+
+// Launch a kernel templated on the static tile geometry (NXT = nx when the tile uses the default CT of that nx, else 0).
+#define LAUNCH_G(h, kern, grid, block, smem, ...)                                        \
+  do {                                                                                   \
+    switch ((h)->geo) {                                                                  \
+      case 64: LAUNCH(h, kern<64>, grid, block, smem, __VA_ARGS__); break;               \
+      case 32: LAUNCH(h, kern<32>, grid, block, smem, __VA_ARGS__); break;               \
+      default: LAUNCH(h, kern<0>, grid, block, smem, __VA_ARGS__); break;                \
+    }                                                                                    \
   } while (0)
 
 int fail(Handle *h, int code, const std::string &msg) { h->err = msg; return code; }
@@ -155,6 +166,10 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   while (d->nx * CT < 32) CT <<= 1;   // a block is at least one warp (warp-shuffle slab reductions)
   if (CT < 1 || d->nx * CT > CRM_MAX_P) { g_init_err = "crm_b200_init: nx too large (nx <= 256)"; delete h; return 4; }
   h->CT = CT;
+  h->geo = ((d->nx == 64 || d->nx == 32) && CT == crm_static_ct(d->nx)) ? d->nx : 0;
+#ifdef CRM_EMU
+  h->geo = 0;
+#endif
   h->ntiles = (d->ncrms + CT - 1) / CT;
   h->P = d->nx * CT;
   const int nz = d->nzm + 1;
@@ -211,23 +226,17 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
 #ifndef CRM_EMU
   {
     const int big = 200 * 1024;
-    cudaFuncSetAttribute(k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(k_epi_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(k_p8_micro, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(k_mpdata, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(k_prologue_fields, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(k_p7_diffuse, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(k_p3_mom, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(k_p1_forcing, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(k_p2_sgs, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(k_kurant, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(k_precip_a, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(k_precip_b, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-#define PRESS_ATTR(NXV)                                                                              \
-  cudaFuncSetAttribute(k_p4_press_fwd<NXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);       \
-  cudaFuncSetAttribute(k_p5_press_bwd<NXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+#define BIG(kern) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, big)
+#define BIG_G(kern) BIG(kern<0>); BIG(kern<32>); BIG(kern<64>)
+    BIG(k_epi_sums); BIG(k_prologue_fields);
+    BIG_G(k_stats); BIG_G(k_p8_micro); BIG_G(k_mpdata); BIG_G(k_p7_diffuse); BIG_G(k_p3_mom); BIG_G(k_p1_forcing); BIG_G(k_p2_sgs);
+    BIG_G(k_kurant); BIG_G(k_precip_a); BIG_G(k_precip_b);
+#define PRESS_ATTR(NXV) BIG((k_p4_press_fwd<NXV, 0>)); BIG((k_p5_press_bwd<NXV, 0>));
     PRESS_ATTR(8) PRESS_ATTR(16) PRESS_ATTR(32) PRESS_ATTR(64) PRESS_ATTR(128) PRESS_ATTR(256)
+    BIG((k_p4_press_fwd<32, 32>)); BIG((k_p5_press_bwd<32, 32>)); BIG((k_p4_press_fwd<64, 64>)); BIG((k_p5_press_bwd<64, 64>));
 #undef PRESS_ATTR
+#undef BIG_G
+#undef BIG
   }
 #endif
   if (dev_sync()) { g_init_err = std::string("crm_b200_init: ") + dev_errstr(); crm_b200_free(h); return 11; }
@@ -395,7 +404,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   while (nstep < nstop) {
     nstep++;
     dev_zero(p.cfl_bits, 8);
-    LAUNCH(h, k_kurant, ntiles, P, CRM_KURANT_SMEM(P, CT, h->nzp), p);
+    LAUNCH_G(h, k_kurant, ntiles, P, CRM_KURANT_SMEM(P, CT, h->nzp), p);
     unsigned long long bits = 0;
     if (dev_copy2d(&bits, 8, p.cfl_bits, 8, 8, 1, 0)) return fail(h, 27, std::string("crm_b200_run: kurant readback failed: ") + dev_errstr());
     double cfl; memcpy(&cfl, &bits, 8);
@@ -420,39 +429,46 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
       p.u = h->ubuf[iu]; p.w = h->wbuf[iu];
       p.du_a = h->ubuf[ina]; p.du_b = h->ubuf[inb]; p.du_c = h->ubuf[inc];
       p.dw_a = h->wbuf[ina]; p.dw_b = h->wbuf[inb]; p.dw_c = h->wbuf[inc];
-      LAUNCH(h, k_p1_forcing, ntiles, P, CRM_P1_SMEM(P, CT, h->nzp), p);
+      LAUNCH_G(h, k_p1_forcing, ntiles, P, CRM_P1_SMEM(P, CT, h->nzp), p);
       if (dbg_stop == 1) { dbg_break = true; break; }
-      LAUNCH(h, k_p2_sgs, ntiles, P, CRM_P2_SMEM(P, CT, h->nzp), p);
+      LAUNCH_G(h, k_p2_sgs, ntiles, P, CRM_P2_SMEM(P, CT, h->nzp), p);
       if (dbg_stop == 2) { dbg_break = true; break; }
-      LAUNCH(h, k_p3_mom, ntiles, P, CRM_P3_SMEM(P, CT, h->nzp), p);
+      LAUNCH_G(h, k_p3_mom, ntiles, P, CRM_P3_SMEM(P, CT, h->nzp), p);
       if (dbg_stop == 3) { dbg_break = true; break; }
 #define PRESS_CASE(NXV)                                                                           \
   case NXV:                                                                                       \
-    LAUNCH(h, k_p4_press_fwd<NXV>, ntiles, P, CRM_P4_SMEM(P, CT, h->nzp, NXV), p);                \
-    LAUNCH(h, k_p5_press_bwd<NXV>, ntiles, P, CRM_P5_SMEM(P, CT, h->nzp, NXV), p);                \
+    LAUNCH(h, (k_p4_press_fwd<NXV, 0>), ntiles, P, CRM_P4_SMEM(P, CT, h->nzp, NXV), p);           \
+    LAUNCH(h, (k_p5_press_bwd<NXV, 0>), ntiles, P, CRM_P5_SMEM(P, CT, h->nzp, NXV), p);           \
     break;
+      if (h->geo == 64) {
+        LAUNCH(h, (k_p4_press_fwd<64, 64>), ntiles, P, CRM_P4_SMEM(P, CT, h->nzp, 64), p);
+        LAUNCH(h, (k_p5_press_bwd<64, 64>), ntiles, P, CRM_P5_SMEM(P, CT, h->nzp, 64), p);
+      } else if (h->geo == 32) {
+        LAUNCH(h, (k_p4_press_fwd<32, 32>), ntiles, P, CRM_P4_SMEM(P, CT, h->nzp, 32), p);
+        LAUNCH(h, (k_p5_press_bwd<32, 32>), ntiles, P, CRM_P5_SMEM(P, CT, h->nzp, 32), p);
+      } else
       switch (nx) { PRESS_CASE(8) PRESS_CASE(16) PRESS_CASE(32) PRESS_CASE(64) PRESS_CASE(128) PRESS_CASE(256) default: return fail(h, 33, "unsupported nx"); }
 #undef PRESS_CASE
       if (dbg_stop == 4) { dbg_break = true; break; }
       // advect_all_scalars.F90:32-64
-      LAUNCH(h, k_mpdata, ntiles, P, smem_mp, p, p.t, (double *)nullptr, (double *)nullptr, 0);
-      LAUNCH(h, k_mpdata, ntiles, P, smem_mp, p, p.qt, p.mkadv1, p.mkwle1, 1);
-      LAUNCH(h, k_mpdata, ntiles, P, smem_mp, p, p.qp, p.mkadv2, p.mkwle2, 1);
+      LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, p.t, (double *)nullptr, (double *)nullptr, 0);
+      LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, p.qt, p.mkadv1, p.mkwle1, 1);
+      LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, p.qp, p.mkadv2, p.mkwle2, 1);
       if (dbg_stop == 5) { dbg_break = true; break; }
       dev_zero(p.prec_cfl_bits, 8);
-      LAUNCH(h, k_precip_a, ntiles, P, CRM_PRECIPA_SMEM(P, CT, h->nzp), p);
-      LAUNCH(h, k_precip_b, ntiles, P, CRM_PRECIPB_SMEM(P, CT, h->nzp), p);
+      LAUNCH_G(h, k_precip_a, ntiles, P, CRM_PRECIPA_SMEM(P, CT, h->nzp), p);
+      LAUNCH_G(h, k_precip_b, ntiles, P, CRM_PRECIPB_SMEM(P, CT, h->nzp), p);
       // uvw.F90: u <- dudt(nc) is a role rotation of the buffers (with the AB rotation of crm_module.F90:884-887)
       { int o_u = iu, o_a = ina, o_b = inb, o_c = inc; iu = o_c; ina = o_u; inb = o_a; inc = o_b; }
       p.u = h->ubuf[iu]; p.w = h->wbuf[iu];
       if (dbg_stop == 6) { dbg_break = true; break; }
-      LAUNCH(h, k_p7_diffuse, ntiles, P, CRM_P7_SMEM(P, CT, h->nzp), p);
+      LAUNCH_G(h, k_p7_diffuse, ntiles, P, CRM_P7_SMEM(P, CT, h->nzp), p);
       if (dbg_stop == 7) { dbg_break = true; break; }
       if (icyc == 1) LAUNCH(h, k_precip_init, (ntiles * nzm * CT + 127) / 128, 128, 0, p);
       LAUNCH(h, k_reset_kminmax, slot_blocks, 128, 0, p);
       const size_t smem_p8 = red_bytes(9) + 2 * CT * sizeof(int);
       if (d->use_crm_accel && !ceaseflag) {
-        LAUNCH(h, k_p8_micro, ntiles * nzm, P, smem_p8, p, 1, 0);
+        LAUNCH_G(h, k_p8_micro, ntiles * nzm, P, smem_p8, p, 1, 0);
         LAUNCH(h, k_msa_a, ntiles * nzm, P, red_bytes(3), p);
         int flags[4];
         if (dev_copy2d(flags, 16, p.flags, 16, 16, 1, 0)) return fail(h, 30, "crm_b200_run: MSA flag readback failed");
@@ -462,16 +478,16 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
         } else {
           LAUNCH(h, k_msa_b, ntiles * nzm, P, red_bytes(2), p);
         }
-        LAUNCH(h, k_p8_micro, ntiles * nzm, P, smem_p8, p, 0, 1);
+        LAUNCH_G(h, k_p8_micro, ntiles * nzm, P, smem_p8, p, 0, 1);
       } else {
-        LAUNCH(h, k_p8_micro, ntiles * nzm, P, smem_p8, p, 1, 1);
+        LAUNCH_G(h, k_p8_micro, ntiles * nzm, P, smem_p8, p, 1, 1);
       }
       { int nn = na; na = nc; nc = nb; nb = nn; }
       if (dbg_stop == 8) { dbg_break = true; break; }
     }
     if (dbg_break) break;
     p.nstop = nstop;
-    LAUNCH(h, k_stats, ntiles, P, CRM_STATS_SMEM(P, CT, h->nzp), p);
+    LAUNCH_G(h, k_stats, ntiles, P, CRM_STATS_SMEM(P, CT, h->nzp, !(((nx / d->nx_rad) * CT <= 32) && !((nx / d->nx_rad) & ((nx / d->nx_rad) - 1)))), p);
     // nprec statistic (device value of the last sub-step)
     if ((nstep & 15) == 0 || nstep == nstop) {
       unsigned long long pb2 = 0; dev_copy2d(&pb2, 8, p.prec_cfl_bits, 8, 8, 1, 0);

@@ -12,7 +12,7 @@ namespace crm {
 
 #define CRM_XNEIGH                                                    \
   const int tm1 = (i == 0) ? tid + P - CT : tid - CT;                 \
-  const int tp1 = (i == p.nx - 1) ? tid - P + CT : tid + CT;          \
+  const int tp1 = (i == nx_ - 1) ? tid - P + CT : tid + CT;           \
   (void)tm1; (void)tp1;
 
 // ice_fall.F90:82-116: limited sedimentation flux of cloud ice at level kk (1..nz).  Q = plane ring of qci,
@@ -38,22 +38,24 @@ __device__ __forceinline__ double ice_flux(const CrmP &p, const PipeQ &Q, const 
 }
 
 // zero.F90, buoyancy.F90:17-36, forcing.F90:38-73, crm_module.F90:766-777, damping.F90:60-110, ice_fall.F90:34-165
-// Two TMA plane rings: qci (levels k..k+2 resident, 6 stages) and the nine single-level inputs (3 stages).
+// Two TMA plane rings: qci (levels k..k+2 resident, 6 stages) and the nine single-level inputs (2 stages; three
+// blocks per SM keep enough loads in flight).
 #define CRM_P1_NPROF 11
 #define CRM_P1_SMEM(P, CT, nzp) \
-  (CRM_PIPE_BYTES(1, 6, P) + CRM_PIPE_BYTES(9, 3, P) + CRM_PROF_BYTES(CRM_P1_NPROF, nzp, CT) + (size_t)CRM_RED_DOUBLES(3, P, CT) * 8)
+  (CRM_PIPE_BYTES(1, 6, P) + CRM_PIPE_BYTES(9, 2, P) + CRM_PROF_BYTES(CRM_P1_NPROF, nzp, CT) + (size_t)CRM_RED_DOUBLES(3, P, CT) * 8)
+template <int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P) k_p1_forcing(CrmP p) {
-  CRM_TILE_SETUP
+  CRM_TILE_SETUP_T(NXT)
   CRM_DYN_SMEM(unsigned char, smraw);
   __shared__ int s_kd0;
   const int nzm = p.nzm, nz = p.nz, npf = p.nzp * CT;
   PlanePipe<1, 6> Q;
-  PlanePipe<9, 3> A;
+  PlanePipe<9, 2> A;
   Q.src[0] = p.qci + fb;
   A.src[0] = p.tabs + fb; A.src[1] = p.qv + fb; A.src[2] = p.qcl + fb; A.src[3] = p.qpl + fb; A.src[4] = p.qpi + fb;
   A.src[5] = p.t + fb; A.src[6] = p.qt + fb; A.src[7] = p.u + fb; A.src[8] = p.w + fb;
   unsigned char *sm2 = smraw + CRM_PIPE_BYTES(1, 6, P);
-  double *sprof = (double *)(sm2 + CRM_PIPE_BYTES(9, 3, P));
+  double *sprof = (double *)(sm2 + CRM_PIPE_BYTES(9, 2, P));
   double *red = sprof + CRM_P1_NPROF * npf;
   {
     const double *const g[CRM_P1_NPROF] = {p.rho, p.adz, p.tabs0, p.qv0, p.qn0, p.qp0, p.bet, p.ttend, p.qtend, p.utend, p.tau};
@@ -68,11 +70,11 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p1_forcing(CrmP p) {
   A.init(sm2, P, tid);
   if (i == 0) atomicMin(&s_kd0, nzm - ndamp);
   CRM_PIPE_PROLOGUE(Q, nzm, 5, 2)
-  CRM_PIPE_PROLOGUE(A, nzm, 2, 0)
+  CRM_PIPE_PROLOGUE(A, nzm, 1, 0)
   __syncthreads();
   const int kd0 = s_kd0;   // lowest level at which any CRM of the tile is in the sponge
-  const int nxy = p.nx * p.ny;
-  const int irad = i / (p.nx / p.nx_rad);
+  const int nxy = nx_ * p.ny;
+  const int irad = i / (nx_ / p.nx_rad);
   const long long rb = ((long long)tile * nzm) * (p.nx_rad * CT) + irad * CT + lane;
   double expr_km1 = 0.;
   double fz_k = ice_flux(p, Q, s_rho, s_adz, tid, lane, CT, 1, kmin, kmax, dz);
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p1_forcing(CrmP p) {
   for (int k = 1; k <= nzm; k++) {
     __syncthreads();
     CRM_PIPE_STEP(Q, k, nzm, 5, 2)
-    CRM_PIPE_STEP(A, k, nzm, 2, 0)
+    CRM_PIPE_STEP(A, k, nzm, 1, 0)
     const double qrad_next = (k < nzm) ? p.qrad[rb + (long long)k * (p.nx_rad * CT)] : 0.;   // software prefetch of the next level
     const double tabs = A.plane(0, k)[tid], qv = A.plane(1, k)[tid], qcl = A.plane(2, k)[tid], qci = Q.plane(0, k)[tid],
                  qpl = A.plane(3, k)[tid], qpi = A.plane(4, k)[tid];
@@ -147,18 +149,20 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p1_forcing(CrmP p) {
 }
 
 // shear_prod2D.F90:20-94 (v == 0 in 2-D) + tke_full.F90:103-310 with dosmagor.  tk/tkh written for k <= nzm-1.
-// One TMA plane ring of 10 fields, levels k and k+1 resident (4 stages); u(k-1) is carried in registers.
+// One TMA plane ring of 9 fields, levels k and k+1 resident (3 stages); u(k-1) is carried in registers; the old tk
+// (own column, one value per level) is an ordinary load issued at the top of the iteration.
 #define CRM_P2_NPROF 9
-#define CRM_P2_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(10, 4, P) + CRM_PROF_BYTES(CRM_P2_NPROF, nzp, CT))
+#define CRM_P2_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(9, 3, P) + CRM_PROF_BYTES(CRM_P2_NPROF, nzp, CT))
+template <int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
-  CRM_TILE_SETUP
+  CRM_TILE_SETUP_T(NXT)
   CRM_XNEIGH
   CRM_DYN_SMEM(unsigned char, smraw);
   const int nzm = p.nzm, npf = p.nzp * CT;
-  PlanePipe<10, 4> R;
+  PlanePipe<9, 3> R;
   R.src[0] = p.u + fb; R.src[1] = p.w + fb; R.src[2] = p.tabs + fb; R.src[3] = p.qcl + fb; R.src[4] = p.qci + fb; R.src[5] = p.qv + fb;
-  R.src[6] = p.qpl + fb; R.src[7] = p.qpi + fb; R.src[8] = p.t + fb; R.src[9] = p.tk + fb;
-  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(10, 4, P));
+  R.src[6] = p.qpl + fb; R.src[7] = p.qpi + fb; R.src[8] = p.t + fb;
+  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(9, 3, P));
   const double dx = p.dx, rdx0 = 1. / dx, dt = p.dt;
   // per-(CRM, level) factors, evaluated once per block with the reference's expressions:
   // 0 rdz=1/(dz adz)  1 rdx0 sqrt(dx rdz)  2 rdzw=1/(dz adzw)  3 rdx0 sqrt(dx rdzw)  4 u0  5 betdz  6 presi(k+1)  7 grd=dz adz  8 tkmax
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
   }
 #define SPF(r, k) sprof[(r) * npf + (k) * CT + lane]
   R.init(smraw, P, tid);
-  CRM_PIPE_PROLOGUE(R, nzm, 3, 1)
+  CRM_PIPE_PROLOGUE(R, nzm, 2, 1)
   const double Cs = R4(0.15), Ck = R4(0.1);
   const double Ce = Ck * Ck * Ck / (Cs * Cs * Cs * Cs);
   const double Pr = 1.;
@@ -196,7 +200,8 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
   for (int k = 1; k <= nzm - 1; k++) {
     const int kc = k + 1, kb = k - 1;
     __syncthreads();
-    CRM_PIPE_STEP(R, k, nzm, 3, 1)
+    CRM_PIPE_STEP(R, k, nzm, 2, 1)
+    const double tk_old = F3(p.tk, k);
     const double *U_k = R.plane(0, k), *U_c = R.plane(0, kc), *W_k = R.plane(1, k), *W_c = R.plane(1, kc);
     const double u_i = U_k[tid], u_ic = U_k[tp1];
     // ---- def2
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
       const double bs = 0.5 * (bsv_km1 + bsv_k);
       double smix;
       if (bs <= 0.) smix = grd;
-      else smix = dmin(grd, dmax(R4(0.1) * grd, sqrt(R4(0.76) * R.plane(9, k)[tid] / Ck / sqrt(bs + R4(1.e-10)))));
+      else smix = dmin(grd, dmax(R4(0.1) * grd, sqrt(R4(0.76) * tk_old / Ck / sqrt(bs + R4(1.e-10)))));
       const double ratio = smix / grd;
       const double Cee = Ce1 + Ce2 * ratio;
       double tk = sqrt(Ck * Ck * Ck / Cee * dmax(0., def2 - Pr * bs)) * (smix * smix);
@@ -289,8 +294,9 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
 // u, w, tk, dudt(na), dwdt(na) stream through a 4-stage TMA plane ring (levels k, k+1 resident, 2 levels of prefetch);
 // the six grid profiles of the tile are staged in shared memory once.
 #define CRM_P3_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(5, 4, P) + CRM_PROF_BYTES(6, nzp, CT) + (size_t)CRM_RED_DOUBLES(2, P, CT) * 8)
-__global__ void __launch_bounds__(CRM_MAX_P) k_p3_mom(CrmP p) {
-  CRM_TILE_SETUP
+template <int NXT>
+__global__ void __launch_bounds__(CRM_MAX_P, 3) k_p3_mom(CrmP p) {
+  CRM_TILE_SETUP_T(NXT)
   CRM_XNEIGH
   CRM_DYN_SMEM(unsigned char, smraw);
   const int nzm = p.nzm, nz = p.nz, npf = p.nzp * CT;
@@ -465,20 +471,20 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_press_alfa(CrmP p) {
 // ---------------------------------------------------------------------------------------------------------------
 
 // press_rhs.F90:80-102 + forward transform + forward sweep (pressure.F90:202-233).
-// u, w and the three AB levels of dudt, dwdt stream through a 4-stage TMA plane ring (levels k, k+1 resident).
+// u, w and the three AB levels of dudt, dwdt stream through a 3-stage TMA plane ring (levels k, k+1 resident).
 #define CRM_P4_SMEM(P, CT, nzp, NX) \
-  (CRM_PIPE_BYTES(8, 4, P) + CRM_PROF_BYTES(5, nzp, CT) + (size_t)((P) + ((NX) + 2) * (CT) + ((NX) / 4 + 1) * 4 * (CT)) * 8)
-template <int NX>
-__global__ void __launch_bounds__(CRM_MAX_P) k_p4_press_fwd(CrmP p) {
+  (CRM_PIPE_BYTES(8, 3, P) + CRM_PROF_BYTES(5, nzp, CT) + (size_t)((P) + ((NX) + 2) * (CT) + ((NX) / 4 + 1) * 4 * (CT)) * 8)
+template <int NX, int NXT>
+__global__ void __launch_bounds__(CRM_MAX_P, 3) k_p4_press_fwd(CrmP p) {
   constexpr int H = NX / 2, Q = NX / 4;
-  CRM_TILE_SETUP
+  CRM_TILE_SETUP_T(NXT)
   CRM_XNEIGH
   CRM_DYN_SMEM(unsigned char, smraw);
   const int nzm = p.nzm, nz = p.nz, npf = p.nzp * CT, m = mode_of(i, NX);
-  PlanePipe<8, 4> R;
+  PlanePipe<8, 3> R;
   R.src[0] = p.u + fb; R.src[1] = p.w + fb; R.src[2] = p.du_a + fb; R.src[3] = p.dw_a + fb; R.src[4] = p.du_b + fb; R.src[5] = p.dw_b + fb;
   R.src[6] = p.du_c + fb; R.src[7] = p.dw_c + fb;
-  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(8, 4, P));
+  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(8, 3, P));
   double *sx = sprof + 5 * npf;            // P
   double *sE = sx + P;                     // (H+1)*CT : E[0..H]
   double *sO = sE + (H + 1) * CT;          // H*CT     : O[1..H-1] (O[0] unused)
@@ -489,7 +495,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p4_press_fwd(CrmP p) {
   }
 #define SPF(r, k) sprof[(r) * npf + (k) * CT + lane]
   R.init(smraw, P, tid);
-  CRM_PIPE_PROLOGUE(R, nz, 3, 1)
+  CRM_PIPE_PROLOGUE(R, nz, 2, 1)
   const bool is_sin = (i & 1) && (i != 1);
   const int type = (is_sin ? 2 : 0) + (m & 1);
   double tw[Q + 1];
@@ -506,7 +512,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p4_press_fwd(CrmP p) {
   for (int k = 1; k <= nzm; k++) {
     const int kc = k + 1;
     __syncthreads();   // previous level's smem reads are complete; ring slot of level k-1 is free
-    CRM_PIPE_STEP(R, k, nz, 3, 1)
+    CRM_PIPE_STEP(R, k, nz, 2, 1)
     const double rho = SPF(0, k);
     const double rdzz = 1. / (SPF(1, k) * dz);
     const double rup = SPF(2, kc) / rho * rdzz, rdn = SPF(2, k) / rho * rdzz;
@@ -559,20 +565,20 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p4_press_fwd(CrmP p) {
 }
 
 // pressure.F90:234-305 (back substitution, inverse transform) + press_grad.F90:20-35 + adams.F90:19-38.
-// Marches downward; w(k+1) is finalised when p(k) is known.  Ten fields through a descending 4-stage TMA plane ring.
+// Marches downward; w(k+1) is finalised when p(k) is known.  Ten fields through a descending 3-stage TMA plane ring.
 #define CRM_P5_SMEM(P, CT, nzp, NX) \
-  (CRM_PIPE_BYTES(10, 4, P) + CRM_PROF_BYTES(3, nzp, CT) + (size_t)(2 * (P) + 5 * ((NX) / 4 + 1) * (CT)) * 8)
-template <int NX>
+  (CRM_PIPE_BYTES(10, 3, P) + CRM_PROF_BYTES(3, nzp, CT) + (size_t)(2 * (P) + 5 * ((NX) / 4 + 1) * (CT)) * 8)
+template <int NX, int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P) k_p5_press_bwd(CrmP p) {
   constexpr int H = NX / 2, Q = NX / 4, NM = H / 2;
-  CRM_TILE_SETUP
+  CRM_TILE_SETUP_T(NXT)
   CRM_XNEIGH
   CRM_DYN_SMEM(unsigned char, smraw);
   const int nzm = p.nzm, npf = p.nzp * CT;
-  PlanePipe<10, 4> R;
+  PlanePipe<10, 3> R;
   R.src[0] = p.pbeta + fb; R.src[1] = p.palfa + fb; R.src[2] = p.du_a + fb; R.src[3] = p.u + fb; R.src[4] = p.du_b + fb; R.src[5] = p.du_c + fb;
   R.src[6] = p.dw_a + fb; R.src[7] = p.w + fb; R.src[8] = p.dw_b + fb; R.src[9] = p.dw_c + fb;
-  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(10, 4, P));
+  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(10, 3, P));
   double *sX = sprof + 3 * npf;             // P: spectrum of this level
   double *sp = sX + P;                      // P: pressure of this level
   double *part = sp + P;                    // 4*(Q+1)*CT: partial sums [r][j][lane], r = Ce, Co, Se, So
@@ -584,7 +590,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p5_press_bwd(CrmP p) {
 #define SPF(r, k) sprof[(r) * npf + (k) * CT + lane]
   for (int q = tid; q < 4 * (Q + 1) * CT; q += P) part[q] = 0.;   // tasks that do not exist (Se, So at j = 0; Co, Se at j = Q) stay zero
   R.init(smraw, P, tid);
-  if (tid == 0) { R.issue(nzm); if (nzm >= 2) R.issue(nzm - 1); }
+  if (tid == 0) R.issue(nzm);
   // task of this thread: partial sum r at point j (see header comment): x_j, x_{n-j}, x_{n/2-j}, x_{n/2+j} share them
   int r, j;
   if (i < 4) { r = (i == 1) ? 1 : (i == 3) ? 3 : 0; j = (i < 2) ? 0 : Q; }
@@ -611,7 +617,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p5_press_bwd(CrmP p) {
   double ff_kp1 = 0., p_kp1 = 0.;
   for (int k = nzm; k >= 1; k--) {
     __syncthreads();
-    if (tid == 0 && k - 2 >= 1) R.issue(k - 2);
+    if (tid == 0 && k - 1 >= 1) R.issue(k - 1);   // into the slot of level k+2
     R.wait_desc(k, nzm);
     double ffk = (k == nzm) ? R.plane(0, k)[tid] : R.plane(1, k)[tid] * ff_kp1 + R.plane(0, k)[tid];
     ff_kp1 = ffk;

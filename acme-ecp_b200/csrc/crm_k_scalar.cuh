@@ -21,8 +21,9 @@ __device__ __forceinline__ double min3(double a, double b, double c) { return dm
 // f, U, W stream through a 6-stage TMA plane ring (levels ka-2..ka+1 resident, up to 3 levels of prefetch); the reciprocal
 // grid profiles (1/rho, 1/adz, 1/(rhow*adz), 2/((kc-kb)*adz)) are evaluated once per block into shared memory.
 #define CRM_MP_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(3, 6, P) + CRM_PROF_BYTES(5, nzp, CT) + (size_t)(9 * (P) + CRM_RED_DOUBLES(2, P, CT)) * 8)
+template <int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P) k_mpdata(CrmP p, double *f, double *fadv, double *flux, int stats) {
-  CRM_TILE_SETUP
+  CRM_TILE_SETUP_T(NXT)
   CRM_XNEIGH
   CRM_DYN_SMEM(unsigned char, smraw);
   const int nzm = p.nzm, nz = p.nz, npf = p.nzp * CT;
@@ -193,8 +194,9 @@ __device__ __forceinline__ double term_vel_qp(const MicroScalars &m, double qplo
 
 // microphysics.F90:578-640: fall speed of every cell + batch-global prec_cfl.  qp, tabs through a 3-stage TMA ring.
 #define CRM_PRECIPA_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(2, 3, P) + CRM_PROF_BYTES(3, nzp, CT) + (size_t)(P) * 8)
+template <int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P) k_precip_a(CrmP p) {
-  CRM_TILE_SETUP
+  CRM_TILE_SETUP_T(NXT)
   CRM_DYN_SMEM(unsigned char, smraw);
   const int nzm = p.nzm, npf = p.nzp * CT;
   PlanePipe<2, 3> R;
@@ -231,8 +233,9 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_precip_a(CrmP p) {
 // First pass (iprec = 1): qp, wp, tabs, t stream through a 6-stage TMA plane ring (levels s-3..s resident).  Later
 // passes re-read what this kernel has just written, so they use ordinary loads (own column only: program order).
 #define CRM_PRECIPB_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(4, 6, P) + CRM_PROF_BYTES(3, nzp, CT) + (size_t)CRM_RED_DOUBLES(2, P, CT) * 8)
-__global__ void __launch_bounds__(CRM_MAX_P) k_precip_b(CrmP p) {
-  CRM_TILE_SETUP
+template <int NXT>
+__global__ void __launch_bounds__(CRM_MAX_P, 3) k_precip_b(CrmP p) {
+  CRM_TILE_SETUP_T(NXT)
   CRM_DYN_SMEM(unsigned char, smraw);
   const int nzm = p.nzm, npf = p.nzp * CT;
   PlanePipe<4, 6> R;
@@ -351,8 +354,9 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_precip_b(CrmP p) {
 // diffuse_scalar2D.F90:70-138 + diffuse_scalar.F90:55-70 for t, qt, qp in one pass (fluxb = fluxt = 0).
 // Inputs stream through a 4-stage TMA plane ring (tkh, t, qt, qp; levels k and k+1 resident, 2 levels of prefetch).
 #define CRM_P7_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(4, 4, P) + CRM_PROF_BYTES(6, nzp, CT) + (size_t)CRM_RED_DOUBLES(4, P, CT) * 8)
-__global__ void __launch_bounds__(256) k_p7_diffuse(CrmP p) {
-  CRM_TILE_SETUP
+template <int NXT>
+__global__ void __launch_bounds__(CRM_MAX_P) k_p7_diffuse(CrmP p) {
+  CRM_TILE_SETUP_T(NXT)
   CRM_XNEIGH
   CRM_DYN_SMEM(unsigned char, smraw);
   const int nzm = p.nzm, npf = p.nzp * CT;
@@ -551,8 +555,10 @@ __device__ inline void precip_proc_cell(const CrmP &p, int pb, int CT, int k, do
 // micro_proc (microphysics.F90:292-329: cloud, precip_proc, micro_diagnose) and, when do_diag, diagnose.F90:37-104
 // (tabs, slab means) + the kmin/kmax scan of ice_fall.F90:34-47 for the NEXT sub-step.
 // Plane kernel: one block per (tile, level).  smem: CRM_RED_DOUBLES(9,P,CT) + 2*CT ints
+template <int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P) k_p8_micro(CrmP p, int do_micro, int do_diag) {
-  const int tid = threadIdx.x, P = p.P, CT = p.CT;
+  const int tid = threadIdx.x;
+  const int CT = (NXT) > 0 ? crm_static_ct(NXT) : p.CT, P = (NXT) > 0 ? (NXT) * crm_static_ct(NXT) : p.P;
   const int tile = blockIdx.x / p.nzm, k = blockIdx.x - tile * p.nzm + 1;
   const int i = tid / CT, lane = tid - i * CT;
   const long long fb = (long long)tile * p.tstride;

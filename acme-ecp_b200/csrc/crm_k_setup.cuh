@@ -7,11 +7,25 @@ namespace crm {
 
 #define CRM_TILE_SETUP                                                        \
   const int tid = threadIdx.x, tile = blockIdx.x, P = p.P, CT = p.CT;         \
+  const int nx_ = p.nx;                                                       \
   const int i = tid / CT, lane = tid - i * CT;                                \
   const long long fb = (long long)tile * p.tstride;                           \
   const int pb = tile * p.nzp * CT + lane;                                    \
   const int cb = tile * CT + lane;                                            \
-  (void)i; (void)fb; (void)pb; (void)cb;
+  (void)i; (void)fb; (void)pb; (void)cb; (void)nx_;
+// Same with the tile geometry as compile-time constants when NXT > 0 (nx = NXT, CT = crm_static_ct(NXT), P = nx*CT):
+// index arithmetic folds into shifts/immediates.  NXT == 0: geometry from the parameter block.
+__host__ __device__ constexpr int crm_static_ct(int nx) { return nx <= 0 ? 0 : (CRM_MAX_P / nx > 16 ? 16 : (CRM_MAX_P / nx < 1 ? 1 : CRM_MAX_P / nx)); }
+#define CRM_TILE_SETUP_T(NXT)                                                 \
+  const int tid = threadIdx.x, tile = blockIdx.x;                             \
+  const int CT = (NXT) > 0 ? crm_static_ct(NXT) : p.CT;                       \
+  const int nx_ = (NXT) > 0 ? (NXT) : p.nx;                                   \
+  const int P = (NXT) > 0 ? (NXT) * crm_static_ct(NXT) : p.P;                 \
+  const int i = tid / CT, lane = tid - i * CT;                                \
+  const long long fb = (long long)tile * p.tstride;                           \
+  const int pb = tile * p.nzp * CT + lane;                                    \
+  const int cb = tile * CT + lane;                                            \
+  (void)i; (void)fb; (void)pb; (void)cb; (void)nx_;
 #define F3(a, k) a[fb + (long long)((k)-1) * P + tid]
 #define F3X(a, k, t2) a[fb + (long long)((k)-1) * P + (t2)]
 #define PF(a, k) a[pb + (k)*CT]
@@ -281,8 +295,9 @@ __global__ void k_setperturb(CrmP p, const double *rnd) {
 // column and only one block max + one atomicMax on the (non-negative) double bit pattern are needed.
 // u, w, tkh stream through a TMA plane ring (4 stages, levels k and k+1 resident).
 #define CRM_KURANT_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(3, 4, P) + CRM_PROF_BYTES(3, nzp, CT) + (size_t)(P) * 8)
+template <int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P) k_kurant(CrmP p) {
-  CRM_TILE_SETUP
+  CRM_TILE_SETUP_T(NXT)
   CRM_DYN_SMEM(unsigned char, smraw);
   const int nzm = p.nzm, nz = p.nz, npf = p.nzp * CT;
   PlanePipe<3, 4> R;

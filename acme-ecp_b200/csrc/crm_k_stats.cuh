@@ -7,20 +7,21 @@ namespace crm {
 
 // Per-nstep statistics.  Block per tile; marches from the top (the reference's cwp scan uses kk = nz-k, and books
 // the cloud-top hit at GCM level l(k), i.e. at CRM level k = nz-kk: quirk kept).
-// Descending TMA plane rings: A = qcl, qci, tabs, qpl, qpi (levels kk-1..kk+1 resident, 5 stages), B = w, qv (levels
-// kk, kk+1, 4 stages).  Radiation-group sums use warp shuffles when a group lies inside a warp.
-#define CRM_STATS_SMEM(P, CT, nzp) \
-  (CRM_PIPE_BYTES(5, 5, P) + CRM_PIPE_BYTES(2, 4, P) + CRM_PROF_BYTES(4, nzp, CT) + (size_t)(CRM_RED_DOUBLES(10, P, CT) + 5 * (P)) * 8)
+// Descending TMA plane rings: A = qcl, qci, tabs, qpl, qpi (levels kk-1..kk+1 resident, 4 stages), B = w, qv (levels
+// kk, kk+1, 3 stages).  Radiation-group sums use warp shuffles when a group lies inside a warp.
+#define CRM_STATS_SMEM(P, CT, nzp, need_srad) \
+  (CRM_PIPE_BYTES(5, 4, P) + CRM_PIPE_BYTES(2, 3, P) + CRM_PROF_BYTES(4, nzp, CT) + (size_t)(CRM_RED_DOUBLES(10, P, CT) + ((need_srad) ? 5 * (P) : 0)) * 8)
+template <int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
-  CRM_TILE_SETUP
+  CRM_TILE_SETUP_T(NXT)
   CRM_DYN_SMEM(unsigned char, smraw);
   const int nzm = p.nzm, nz = p.nz, npf = p.nzp * CT;
-  PlanePipe<5, 5> A;
-  PlanePipe<2, 4> B;
+  PlanePipe<5, 4> A;
+  PlanePipe<2, 3> B;
   A.src[0] = p.qcl + fb; A.src[1] = p.qci + fb; A.src[2] = p.tabs + fb; A.src[3] = p.qpl + fb; A.src[4] = p.qpi + fb;
   B.src[0] = p.w + fb; B.src[1] = p.qv + fb;
-  unsigned char *sm2 = smraw + CRM_PIPE_BYTES(5, 5, P);
-  double *sprof = (double *)(sm2 + CRM_PIPE_BYTES(2, 4, P));
+  unsigned char *sm2 = smraw + CRM_PIPE_BYTES(5, 4, P);
+  double *sprof = (double *)(sm2 + CRM_PIPE_BYTES(2, 3, P));
   double *red = sprof + 4 * npf, *srad = red + CRM_RED_DOUBLES(10, P, CT);
   {
     const double *const g[4] = {p.rho, p.adz, p.pres, p.rhow};
@@ -31,21 +32,21 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
   B.init(sm2, P, tid);
   // top level nz of B (w(nz)) is needed by level nzm; A starts at nzm
   if (tid == 0) {
-    A.issue(nzm); if (nzm >= 2) A.issue(nzm - 1); if (nzm >= 3) A.issue(nzm - 2);
-    B.issue(nz); B.issue(nzm); if (nzm >= 2) B.issue(nzm - 1);
+    A.issue(nzm); if (nzm >= 2) A.issue(nzm - 1);
+    B.issue(nz); B.issue(nzm);
   }
   A.wait_desc(nzm, nzm);
   B.wait_desc(nz, nz);
   const double dz = p.dz[cb];
   const double cwp_threshold = R4(0.001), wmin = R4(2.);
-  const int grp = p.nx / p.nx_rad;
+  const int grp = nx_ / p.nx_rad;
   const bool grp_in_warp = (grp * CT <= 32) && !(grp & (grp - 1));
   double cwp = 0., cwph = 0., cwpm = 0., cwpl = 0., cltemp = 0., cmtemp = 0., chtemp = 0., cttemp = 0.;
   bool flag_top = true;
   for (int kk = nzm; kk >= 1; kk--) {   // kk = nz-k of the reference's loop counter k
     const int kmir = nz - kk;           // the loop counter k (1..nzm) at which level kk is scanned
     __syncthreads();
-    if (tid == 0) { if (kk - 3 >= 1) A.issue(kk - 3); if (kk - 2 >= 1) B.issue(kk - 2); }
+    if (tid == 0) { if (kk - 2 >= 1) A.issue(kk - 2); if (kk - 1 >= 1) B.issue(kk - 1); }
     if (kk - 1 >= 1) A.wait_desc(kk - 1, nzm);
     B.wait_desc(kk, nz);
     const double qcl = A.plane(0, kk)[tid], qci = A.plane(1, kk)[tid];
