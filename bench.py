@@ -128,6 +128,43 @@ def workload_name(args, dims):
         args.config, dims.ncrms, dims.nx, dims.ny, dims.nzm, dims.dt, dims.dt_gl, int(dims.dt_gl / dims.dt))
 
 
+def run_e2e(args, pkg, abi, h, dims, inp, ci, st, rad, dstate, big, world, barrier, torch, dist):
+    """End-to-end arm: HOST (pinned) buffers through the same C-ABI call (H2D of crm_state/crm_rad, D2H of the state
+    and of every output inside the timed region)."""
+    def pinned_like(a):
+        tns = torch.empty(a.size, dtype=torch.float64).pin_memory()
+        v = tns.numpy().reshape(a.shape, order="F")
+        v[...] = a
+        return tns, v
+    keep = []
+    hst = pkg.crm_state_type(); hrad = pkg.crm_rad_type(); hout = pkg.crm_output_type().initialize(dims)
+    for n in abi.STATE_FIELDS_SAM1MOM:
+        tns, v = pinned_like(dstate[n].cpu().numpy().reshape(getattr(st, n).shape, order="F")); keep.append(tns); setattr(hst, n, v)
+    for n in abi.RAD_FIELDS_SAM1MOM:
+        tns, v = pinned_like(getattr(rad, n)); keep.append(tns); setattr(hrad, n, v)
+    for n in big:
+        tns, v = pinned_like(getattr(hout, n)); keep.append(tns); setattr(hout, n, v)
+    hcs, hcr, hco = hst.c_struct(), hrad.c_struct(), hout.c_struct()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    h.run_structs(dims.copy(igstep=3), ci, hcs, hcr, hco)   # warm-up (page-locks / first touch)
+    barrier()
+    t0 = time.time()
+    upd_e, h2d, d2h = 0, 0, 0
+    for _ in range(e2e_steps):
+        h.run_structs(dims.copy(igstep=3), ci, hcs, hcr, hco)
+        s = h.stats()
+        upd_e += dims.cells * s["ncycle_sum"]; h2d = s["h2d_bytes"]; d2h = s["d2h_bytes"]
+    barrier()
+    te = time.time() - t0
+    t = torch.tensor([te, float(upd_e)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        te, upd_e = float(tmax[0]), float(tsum[1])
+    return {"value": upd_e / te, "unit": "cell-updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "steps": e2e_steps, "host_buffers": "pinned"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -213,39 +250,9 @@ def run_ours(args):
                                "frac": BYTES_PER_CELL_UPDATE["2d_sam1mom"] * (value / world) / 1e9 / peak},
                 "kernel_ms": {k: round(v[0], 3) for k, v in sorted(kt.items(), key=lambda kv: -kv[1][0])}}
 
-    # ---- end-to-end arm: HOST (pinned) buffers through the same C-ABI call
-    def pinned_like(a):
-        tns = torch.empty(a.size, dtype=torch.float64).pin_memory()
-        v = tns.numpy().reshape(a.shape, order="F")
-        v[...] = a
-        return tns, v
-    keep = []
-    hst = pkg.crm_state_type(); hrad = pkg.crm_rad_type(); hout = pkg.crm_output_type().initialize(dims)
-    for n in abi.STATE_FIELDS_SAM1MOM:
-        tns, v = pinned_like(dstate[n].cpu().numpy().reshape(getattr(st, n).shape, order="F")); keep.append(tns); setattr(hst, n, v)
-    for n in abi.RAD_FIELDS_SAM1MOM:
-        tns, v = pinned_like(getattr(rad, n)); keep.append(tns); setattr(hrad, n, v)
-    for n in big:
-        tns, v = pinned_like(getattr(hout, n)); keep.append(tns); setattr(hout, n, v)
-    hcs, hcr, hco = hst.c_struct(), hrad.c_struct(), hout.c_struct()
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    h.run_structs(dims.copy(igstep=3), ci, hcs, hcr, hco)   # warm-up (page-locks / first touch)
-    barrier()
-    t0 = time.time()
-    upd_e, h2d, d2h = 0, 0, 0
-    for _ in range(e2e_steps):
-        h.run_structs(dims.copy(igstep=3), ci, hcs, hcr, hco)
-        s = h.stats()
-        upd_e += dims.cells * s["ncycle_sum"]; h2d = s["h2d_bytes"]; d2h = s["d2h_bytes"]
-    barrier()
-    te = time.time() - t0
-    t = torch.tensor([te, float(upd_e)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        te, upd_e = float(tmax[0]), float(tsum[1])
-    e2e = {"value": upd_e / te, "unit": "cell-updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "steps": e2e_steps, "host_buffers": "pinned"}
+    e2e = None
+    if args.e2e_steps > 0:
+        e2e = run_e2e(args, pkg, abi, h, dims, inp, ci, st, rad, dstate, big, world, barrier, torch, dist)
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on a bounded sample
     cpu = None
