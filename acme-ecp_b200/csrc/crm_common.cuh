@@ -208,6 +208,29 @@ __device__ __forceinline__ void block_sum_each(double (&v)[NQ], int tid, int P, 
     f(q, ln, s);
   }
 }
+// Deferred variant for march loops that already have one barrier per level: red_put() after computing a level (no
+// barrier), red_get() after the next barrier.  Alternate two `red` buffers between consecutive levels.
+template <int NQ>
+__device__ __forceinline__ void red_put(double (&v)[NQ], int tid, int CT, double *red) {
+  const int lane = tid & (CT - 1), w = tid >> 5;
+#pragma unroll
+  for (int q = 0; q < NQ; q++)
+    for (int off = CT; off < 32; off <<= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], off);
+  if ((tid & 31) < CT) {
+#pragma unroll
+    for (int q = 0; q < NQ; q++) red[(w * NQ + q) * CT + lane] = v[q];
+  }
+}
+template <int NQ, class F>
+__device__ __forceinline__ void red_get(int tid, int P, int CT, const double *red, F f) {
+  const int nw = P >> 5;
+  for (int t = tid; t < NQ * CT; t += P) {
+    const int q = t / CT, ln = t - q * CT;
+    double s = red[q * CT + ln];
+    for (int g = 1; g < nw; g++) s += red[(g * NQ + q) * CT + ln];
+    f(q, ln, s);
+  }
+}
 template <int NQ>
 __device__ __forceinline__ void block_sum(double (&v)[NQ], int tid, int P, int CT, double *red) { block_sum_impl<NQ, true>(v, tid, P, CT, red); }
 template <int NQ>

@@ -566,8 +566,13 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p8_micro(CrmP p, int do_micro, in
   const int cb = tile * CT + lane;
   CRM_DYN_SMEM(double, red);
   int *sflag = (int *)(red + CRM_RED_DOUBLES(8, P, CT));
-  double t = F3(p.t, k), q = F3(p.qt, k), qp = F3(p.qp, k), qn = F3(p.qn, k), tabs = F3(p.tabs, k);
-  double qv = F3(p.qv, k), qcl = F3(p.qcl, k), qci = F3(p.qci, k), qpl = F3(p.qpl, k), qpi = F3(p.qpi, k);
+  double t = F3(p.t, k), q = F3(p.qt, k), qp = F3(p.qp, k);
+  // with do_micro every one of these is recomputed before use (cloud -> qn, tabs; micro_diagnose -> qv..qpi): skip the loads
+  double qn = 0., tabs = 0., qv = 0., qcl = 0., qci = 0., qpl = 0., qpi = 0.;
+  if (!do_micro) {
+    qn = F3(p.qn, k); tabs = F3(p.tabs, k);
+    qv = F3(p.qv, k); qcl = F3(p.qcl, k); qci = F3(p.qci, k); qpl = F3(p.qpl, k); qpi = F3(p.qpi, k);
+  }
   double dsrc = 0., devp = 0.;
   if (do_micro) {
     const double pres = PF(p.pres, k);

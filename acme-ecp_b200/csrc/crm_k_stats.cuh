@@ -10,7 +10,7 @@ namespace crm {
 // Descending TMA plane rings: A = qcl, qci, tabs, qpl, qpi (levels kk-1..kk+1 resident, 4 stages), B = w, qv (levels
 // kk, kk+1, 3 stages).  Radiation-group sums use warp shuffles when a group lies inside a warp.
 #define CRM_STATS_SMEM(P, CT, nzp, need_srad) \
-  (CRM_PIPE_BYTES(5, 4, P) + CRM_PIPE_BYTES(2, 3, P) + CRM_PROF_BYTES(4, nzp, CT) + (size_t)(CRM_RED_DOUBLES(10, P, CT) + ((need_srad) ? 5 * (P) : 0)) * 8)
+  (CRM_PIPE_BYTES(5, 4, P) + CRM_PIPE_BYTES(2, 3, P) + CRM_PROF_BYTES(4, nzp, CT) + (size_t)(2 * CRM_RED_DOUBLES(10, P, CT) + ((need_srad) ? 5 * (P) : 0)) * 8)
 template <int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
   CRM_TILE_SETUP_T(NXT)
@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
   B.src[0] = p.w + fb; B.src[1] = p.qv + fb;
   unsigned char *sm2 = smraw + CRM_PIPE_BYTES(5, 4, P);
   double *sprof = (double *)(sm2 + CRM_PIPE_BYTES(2, 3, P));
-  double *red = sprof + 4 * npf, *srad = red + CRM_RED_DOUBLES(10, P, CT);
+  double *red = sprof + 4 * npf, *srad = red + 2 * CRM_RED_DOUBLES(10, P, CT);
+  const int RS = CRM_RED_DOUBLES(10, P, CT);
   {
     const double *const g[4] = {p.rho, p.adz, p.pres, p.rhow};
     stage_profiles<4>(sprof, g, tile, p.nzp, CT, tid, P);
@@ -43,10 +44,16 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
   const bool grp_in_warp = (grp * CT <= 32) && !(grp & (grp - 1));
   double cwp = 0., cwph = 0., cwpm = 0., cwpl = 0., cltemp = 0., cmtemp = 0., chtemp = 0., cttemp = 0.;
   bool flag_top = true;
+  // slab sum q of level lev -> its accumulator (cloud-top hits are booked at the mirrored level nz-lev)
+  auto book = [&](int q, int ln, double sum, int lev) {
+    double *dst = (q == 0) ? p.s_cld : (q == 1) ? p.s_mcup : (q == 2) ? p.s_mcdn : (q == 3) ? p.s_mcuup : (q == 4) ? p.s_mcudn :
+                  (q == 5) ? p.s_gliqwp : (q == 6) ? p.s_gicewp : (q == 7) ? p.s_cldtop : (q == 8) ? p.s_mui : p.s_mdi;
+    acc_add(dst + tile * p.nzp * CT + ((q == 7) ? nz - lev : lev) * CT + ln, sum);
+  };
   for (int kk = nzm; kk >= 1; kk--) {   // kk = nz-k of the reference's loop counter k
-    const int kmir = nz - kk;           // the loop counter k (1..nzm) at which level kk is scanned
-    __syncthreads();
+    __syncthreads();   // ring slots of level kk+2 are free; warp partials of level kk+1 are visible
     if (tid == 0) { if (kk - 2 >= 1) A.issue(kk - 2); if (kk - 1 >= 1) B.issue(kk - 1); }
+    if (kk < nzm) red_get<10>(tid, P, CT, red + ((kk + 1) & 1) * RS, [&](int q, int ln, double sum) { book(q, ln, sum, kk + 1); });
     if (kk - 1 >= 1) A.wait_desc(kk - 1, nzm);
     B.wait_desc(kk, nz);
     const double qcl = A.plane(0, kk)[tid], qci = A.plane(1, kk)[tid];
@@ -85,11 +92,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
       else if (A.plane(3, kx)[tid] + A.plane(4, kx)[tid] > R4(1.0e-4)) mdi = SPF(3, kk) * w_k;
     }
     double v[10] = {cld, mcup, mcdn, mcuup, mcudn, qcl, qci, top_hit, mui, mdi};
-    block_sum_each<10>(v, tid, P, CT, red, [&](int q, int ln, double sum) {
-      double *dst = (q == 0) ? p.s_cld : (q == 1) ? p.s_mcup : (q == 2) ? p.s_mcdn : (q == 3) ? p.s_mcuup : (q == 4) ? p.s_mcudn :
-                    (q == 5) ? p.s_gliqwp : (q == 6) ? p.s_gicewp : (q == 7) ? p.s_cldtop : (q == 8) ? p.s_mui : p.s_mdi;
-      acc_add(dst + tile * p.nzp * CT + ((q == 7) ? kmir : kk) * CT + ln, sum);
-    });
+    red_put<10>(v, tid, CT, red + (kk & 1) * RS);   // finished after the next barrier (deferred: one barrier per level)
     // radiation-group accumulators (crm_module.F90:979-1015): groups of nx/nx_rad adjacent columns
     const double tabs = A.plane(2, kk)[tid], qv = B.plane(1, kk)[tid];
     double a[5] = {tabs, dmax(0., qv), qcl, qci, (qcl + qci > 0) ? 1. : 0.};
@@ -117,6 +120,8 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
       acc_add(p.rad_t + ro, a[0]); acc_add(p.rad_qv + ro, a[1]); acc_add(p.rad_qc + ro, a[2]); acc_add(p.rad_qi + ro, a[3]); acc_add(p.rad_cld + ro, a[4]);
     }
   }
+  __syncthreads();
+  red_get<10>(tid, P, CT, red + (1 & 1) * RS, [&](int q, int ln, double sum) { book(q, ln, sum, 1); });
   // w-level nz (k = nzm+1 of crm_module.F90:1023): w(nz) = 0 -> no contribution.
   double v[4];
   v[0] = (cwp > cwp_threshold) ? cttemp : 0.; v[1] = (cwph > cwp_threshold) ? chtemp : 0.;
