@@ -222,7 +222,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
     crm_b200_free(h);
     return 9;
   }
-  if (!micro_scalars(p.ms)) { g_init_err = "cannot compute gamma-function in precip_init"; crm_b200_free(h); return 10; }
+  if (!micro_scalars(p.ms) || p.ms.csnow != 0.0625 || p.ms.cgrau != 0.125) { g_init_err = "cannot compute gamma-function in precip_init"; crm_b200_free(h); return 10; }
 #ifndef CRM_EMU
   {
     const int big = 200 * 1024;

@@ -120,6 +120,34 @@ __device__ __forceinline__ void acc_add(double *a, double v) {
 __device__ __forceinline__ double pp_(double y) { return dmax(0., y); }
 __device__ __forceinline__ double pn_(double y) { return -dmin(0., y); }
 
+// ---- powers with the fixed exponents of the sam1mom scheme (micro_params.F90:17-45: b_rain = 0.8, b_snow = 0.25,
+// b_grau = 0.5 as REAL(4) literals).  The snow/graupel exponents b/4, (3+b)/4, (5+b)/8 are dyadic rationals, so x**c is a
+// product of repeated square roots (each correctly rounded; a few ulp in total instead of the ~250-instruction generic
+// pow).  The rain exponents and ice_fall's 0.24 are not dyadic: x**c = exp(c*log(x)) (relative error ~ |c ln x| ulp).
+__device__ __forceinline__ double pow_c(double x, double c) { return exp(c * log(x)); }   // x >= 0, c > 0
+__device__ __forceinline__ double pow_1_16(double x) { return sqrt(sqrt(sqrt(sqrt(x)))); }   // csnow = 0.25/4
+__device__ __forceinline__ double pow_1_8(double x) { return sqrt(sqrt(sqrt(x))); }          // cgrau = 0.5/4
+__device__ __forceinline__ double pow_13_16(double x) {   // pows1 = (3+0.25)/4 = 1/2 + 1/4 + 1/16
+  const double s1 = sqrt(x), s2 = sqrt(s1), s4 = sqrt(sqrt(s2));
+  return s1 * s2 * s4;
+}
+__device__ __forceinline__ double pow_7_8(double x) {     // powg1 = (3+0.5)/4 = 1/2 + 1/4 + 1/8
+  const double s1 = sqrt(x), s2 = sqrt(s1), s3 = sqrt(s2);
+  return s1 * s2 * s3;
+}
+// sqrt(x) and x**(21/32) (pows2 = (5+0.25)/8 = 1/2 + 1/8 + 1/32)
+__device__ __forceinline__ void sqrt_pow_21_32(double x, double &s1, double &pw) {
+  s1 = sqrt(x);
+  const double s3 = sqrt(sqrt(s1)), s5 = sqrt(sqrt(s3));
+  pw = s1 * s3 * s5;
+}
+// sqrt(x) and x**(11/16) (powg2 = (5+0.5)/8 = 1/2 + 1/8 + 1/16)
+__device__ __forceinline__ void sqrt_pow_11_16(double x, double &s1, double &pw) {
+  s1 = sqrt(x);
+  const double s3 = sqrt(sqrt(s1)), s4 = sqrt(s3);
+  pw = s1 * s3 * s4;
+}
+
 // ---- sat.F90 (Flatau et al. polynomials with REAL(4) coefficients) ----
 __device__ __forceinline__ double poly8(double a0, double a1, double a2, double a3, double a4, double a5, double a6, double a7,
                                         double a8, double dt) {

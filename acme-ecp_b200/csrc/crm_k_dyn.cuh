@@ -27,7 +27,7 @@ __device__ __forceinline__ double ice_flux(const CrmP &p, const PipeQ &Q, const 
   double qiu = s_rho[kc * CT + lane] * Q.plane(0, kc)[tid];
   double qic = s_rho[kk * CT + lane] * Q.plane(0, kk)[tid];
   double qid = s_rho[kb * CT + lane] * Q.plane(0, kb)[tid];
-  double vt_ice = dmin(R4(0.4), R4(8.66) * pow(dmax(0., qic) + R4(1.e-10), R4(0.24)));
+  double vt_ice = dmin(R4(0.4), R4(8.66) * pow_c(dmax(0., qic) + R4(1.e-10), R4(0.24)));
   double tmp_phi;
   if (fabs(qic - qid) < R4(1.0e-25)) tmp_phi = 0.;
   else {

@@ -118,8 +118,9 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_mpdata(CrmP p, double *f, double 
       const double rho = S_RHO(kb_), iadz = S_IADZ(kb_);
       const double WWk = WW_prev;                                  // WW(kb_)
       const double WWkc = (kb_ == nzm) ? WW_prev : WW_ka;           // WW(min(nzm,kb_+1))
-      mx_new = rho * (mxr - F1c) / (pn_(UUp) + pp_(UU) + iadz * (pn_(WWkc) + pp_(WWk)) + eps);
-      mn_new = rho * (F1c - mnr) / (pp_(UUp) + pn_(UU) + iadz * (pp_(WWkc) + pn_(WWk)) + eps);
+      // zero numerators give exactly +0 (denominators >= eps > 0): no division where the field is locally uniform (qp = 0 ...)
+      mx_new = (mxr == F1c) ? 0. : rho * (mxr - F1c) / (pn_(UUp) + pp_(UU) + iadz * (pn_(WWkc) + pp_(WWk)) + eps);
+      mn_new = (F1c == mnr) ? 0. : rho * (F1c - mnr) / (pp_(UUp) + pn_(UU) + iadz * (pp_(WWkc) + pn_(WWk)) + eps);
       smx[(kb_ & 1) * P + tid] = mx_new;
       smn[(kb_ & 1) * P + tid] = mn_new;
     }
@@ -173,20 +174,20 @@ __device__ __forceinline__ double term_vel_qp(const MicroScalars &m, double qplo
   if (qploc > CRM_QP_THRESHOLD) {
     const double omp = dmax(0., dmin(1., (tabs - CRM_TPRMIN) * m.a_pr));
     if (omp == 1.) {
-      term_vel = m.vrain * pow(rho * qploc, m.crain);
+      term_vel = m.vrain * pow_c(rho * qploc, m.crain);
     } else if (omp == 0.) {
       const double omg = dmax(0., dmin(1., (tabs - CRM_TGRMIN) * m.a_gr));
       const double qgg = omg * qploc;
       const double qss = qploc - qgg;
-      term_vel = (omg * m.vgrau * pow(rho * qgg, m.cgrau) + (1. - omg) * m.vsnow * pow(rho * qss, m.csnow));
+      term_vel = (omg * m.vgrau * pow_1_8(rho * qgg) + (1. - omg) * m.vsnow * pow_1_16(rho * qss));
     } else {
       const double omg = dmax(0., dmin(1., (tabs - CRM_TGRMIN) * m.a_gr));
       const double qrr = omp * qploc;
       double qss = qploc - qrr;
       const double qgg = omg * qss;
       qss = qss - qgg;
-      term_vel = (omp * m.vrain * pow(rho * qrr, m.crain) +
-                  (1. - omp) * (omg * m.vgrau * pow(rho * qgg, m.cgrau) + (1. - omg) * m.vsnow * pow(rho * qss, m.csnow)));
+      term_vel = (omp * m.vrain * pow_c(rho * qrr, m.crain) +
+                  (1. - omp) * (omg * m.vgrau * pow_1_8(rho * qgg) + (1. - omg) * m.vsnow * pow_1_16(rho * qss)));
     }
   }
   return term_vel;
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_precip_a(CrmP p) {
 // sliding register window (q, wp, tq 3 levels ahead of the level being finalised).
 // First pass (iprec = 1): qp, wp, tabs, t stream through a 6-stage TMA plane ring (levels s-3..s resident).  Later
 // passes re-read what this kernel has just written, so they use ordinary loads (own column only: program order).
-#define CRM_PRECIPB_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(4, 6, P) + CRM_PROF_BYTES(3, nzp, CT) + (size_t)CRM_RED_DOUBLES(2, P, CT) * 8)
+#define CRM_PRECIPB_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(4, 6, P) + CRM_PROF_BYTES(3, nzp, CT) + (size_t)2 * CRM_RED_DOUBLES(2, P, CT) * 8)
 template <int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P, 3) k_precip_b(CrmP p) {
   CRM_TILE_SETUP_T(NXT)
@@ -260,6 +261,14 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_precip_b(CrmP p) {
   int nprec = 1;
   if (prec_cfl > R4(0.9)) nprec = (int)ceil(prec_cfl / R4(0.9));
   const long long c2 = (long long)tile * P + tid;
+  const int RS = CRM_RED_DOUBLES(2, P, CT);
+  // slab sums of level lev: qpfall += sum(dq), precflux -= sum(fz)   (microphysics.F90:772-776)
+  auto book_at = [&](int lev) {
+    return [&p, tile, CT, lev](int q, int ln, double sum) {
+      const int o = tile * p.nzp * CT + lev * CT + ln;
+      if (q == 0) acc_add(p.qpfall + o, sum); else acc_add(p.precflux + o, -sum);
+    };
+  };
   for (int iprec = 1; iprec <= nprec; iprec++) {
     const bool ring = (iprec == 1);
     const bool scale_wp = (iprec == 1 && nprec > 1);   // wp = wp/nprec (microphysics.F90:648-660); later iterations store scaled wp
@@ -272,19 +281,28 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_precip_b(CrmP p) {
     double mxn0 = 0., mnn0 = 0., mxn1 = 0., mnn1 = 0.;  // normalised at s-3, s-2
     double fzl0 = 0., fzl1 = 0.;                        // limited flux at s-3, s-2
     double om0 = 0., om1 = 0., om2 = 0., om3 = 0.;      // omega(s-3..s)
+    // later passes (ordinary loads): the next level is fetched one iteration ahead
+    double nq = 0., nwp = 0., ntb = 0., nt = 0.;
+    if (!ring) { nq = F3(p.qp, 1); nwp = F3(p.wp, 1); ntb = F3(p.tabs, 1); }
     for (int s = 1; s <= nzm + 3; s++) {
-      if (ring) {
-        __syncthreads();
-        CRM_PIPE_STEP(R, s, nzm, 2, 0)
-      }
+      __syncthreads();   // ring slot of level s-4 is free; warp partials of level k3 = s-4 are visible
+      if (ring) { CRM_PIPE_STEP(R, s, nzm, 2, 0) }
+      if (s - 4 >= 1) red_get<2>(tid, P, CT, red + (s & 1) * RS, book_at(s - 4));
       // ---- load level s
       q0 = q1; q1 = q2; q2 = q3; w1 = w2; w2 = w3; fz2 = fz3; om0 = om1; om1 = om2; om2 = om3;
+      double t_k3 = 0.;
+      if (ring) { if (s - 3 >= 1) t_k3 = R.plane(3, s - 3)[tid]; }
+      else { t_k3 = nt; if (s - 2 >= 1 && s - 2 <= nzm) nt = F3(p.t, s - 2); }
       if (s <= nzm) {
-        q3 = ring ? R.plane(0, s)[tid] : F3(p.qp, s);
-        w3 = ring ? R.plane(1, s)[tid] : F3(p.wp, s);
+        double tb;
+        if (ring) { q3 = R.plane(0, s)[tid]; w3 = R.plane(1, s)[tid]; tb = R.plane(2, s)[tid]; }
+        else {
+          q3 = nq; w3 = nwp; tb = ntb;
+          if (s + 1 <= nzm) { nq = F3(p.qp, s + 1); nwp = F3(p.wp, s + 1); ntb = F3(p.tabs, s + 1); }
+        }
         if (scale_wp) { w3 = w3 / (double)nprec; }
         fz3 = q3 * w3;
-        om3 = dmax(0., dmin(1., ((ring ? R.plane(2, s)[tid] : F3(p.tabs, s)) - CRM_TPRMIN) * p.ms.a_pr));
+        om3 = dmax(0., dmin(1., (tb - CRM_TPRMIN) * p.ms.a_pr));
       } else { q3 = 0.; w3 = 0.; fz3 = 0.; om3 = 0.; }
       // ---- tq(s-1)
       tq0 = tq1; tq1 = tq2;
@@ -309,8 +327,9 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_precip_b(CrmP p) {
         mn = dmin(min3(tb, tc, tq1), mn);
         const double wwc = (k2 == nzm) ? ww1 : ww2;   // www(min(nzm,k2+1))
         const double ra = S_RA(k2);
-        mxn1 = ra * (mx - tq1) / (pn_(wwc) + pp_(ww1) + eps);
-        mnn1 = ra * (tq1 - mn) / (pp_(wwc) + pn_(ww1) + eps);
+        // a zero numerator gives exactly +0 (the denominators are >= eps > 0): skip the two divisions in precipitation-free air
+        mxn1 = (mx == tq1) ? 0. : ra * (mx - tq1) / (pn_(wwc) + pp_(ww1) + eps);
+        mnn1 = (tq1 == mn) ? 0. : ra * (tq1 - mn) / (pp_(wwc) + pn_(ww1) + eps);
       } else { mxn1 = 0.; mnn1 = 0.; }
       // ---- limited flux at k2: fz(k2) + pp(www)*min(1,mx(k2),mn(kb)) - pn(www)*min(1,mx(kb),mn(k2))
       fzl0 = fzl1;
@@ -329,7 +348,7 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_precip_b(CrmP p) {
         const double lf0 = CRM_FAC_COND + (1 - om0) * CRM_FAC_FUS;
         const double lf1 = (k3 + 1 <= nzm) ? CRM_FAC_COND + (1 - om1) * CRM_FAC_FUS : 0.;
         const double lat_heat = -(lf1 * fzl1 - lf0 * fzl0) * irhoadz;
-        F3(p.t, k3) = (ring ? R.plane(3, k3)[tid] : F3(p.t, k3)) - lat_heat;
+        F3(p.t, k3) = t_k3 - lat_heat;
         if (k3 == 1) {
           p.precsfc[c2] = p.precsfc[c2] - fzl0 * 1.;
           p.precssfc[c2] = p.precssfc[c2] - fzl0 * (1. - om0) * 1.;
@@ -341,10 +360,11 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_precip_b(CrmP p) {
           F3(p.wp, k3) = -wpv * PF(p.rhow, k3) * p.dtn / dz / (double)nprec;
         }
         double v[2] = {dq, fzl0};
-        block_sum_lead<2>(v, tid, P, CT, red);
-        if (i == 0) { acc_add(&PF(p.qpfall, k3), v[0]); acc_add(&PF(p.precflux, k3), -v[1]); }
+        red_put<2>(v, tid, CT, red + (k3 & 1) * RS);   // finished after the next barrier (deferred: one barrier per level)
       }
     }
+    __syncthreads();
+    red_get<2>(tid, P, CT, red + (nzm & 1) * RS, book_at(nzm));
   }
 #undef S_IRA
 #undef S_RA
@@ -495,19 +515,19 @@ __device__ inline void precip_proc_cell(const CrmP &p, int pb, int CT, int k, do
       double accrr = 0.;
       if (omp > R4(0.001)) {
         const double qrr = qp * omp;
-        accrr = PF(p.accrrc, k) * pow(qrr, powr1);
+        accrr = PF(p.accrrc, k) * pow_c(qrr, powr1);
       }
       double accrcs = 0., accris = 0.;
       if (omp < R4(0.999) && omg < R4(0.999)) {
         const double qss = qp * (1. - omp) * (1. - omg);
-        const double tmp = pow(qss, pows1);
+        const double tmp = pow_13_16(qss);
         accrcs = PF(p.accrsc, k) * tmp;
         accris = PF(p.accrsi, k) * tmp;
       }
       double accrcg = 0., accrig = 0.;
       if (omp < R4(0.999) && omg > R4(0.001)) {
         const double qgg = qp * (1. - omp) * omg;
-        const double tmp = pow(qgg, powg1);
+        const double tmp = pow_7_8(qgg);
         accrcg = PF(p.accrgc, k) * tmp;
         accrig = PF(p.accrgi, k) * tmp;
       }
@@ -526,15 +546,19 @@ __device__ inline void precip_proc_cell(const CrmP &p, int pb, int CT, int k, do
       double dq = 0.;
       if (omp > R4(0.001)) {
         const double qrr = qp * omp;
-        dq = dq + PF(p.evapr1, k) * sqrt(qrr) + PF(p.evapr2, k) * pow(qrr, powr2);
+        dq = dq + PF(p.evapr1, k) * sqrt(qrr) + PF(p.evapr2, k) * pow_c(qrr, powr2);
       }
       if (omp < R4(0.999) && omg < R4(0.999)) {
         const double qss = qp * (1. - omp) * (1. - omg);
-        dq = dq + PF(p.evaps1, k) * sqrt(qss) + PF(p.evaps2, k) * pow(qss, pows2);
+        double sq, pw;
+        sqrt_pow_21_32(qss, sq, pw);
+        dq = dq + PF(p.evaps1, k) * sq + PF(p.evaps2, k) * pw;
       }
       if (omp < R4(0.999) && omg > R4(0.001)) {
         const double qgg = qp * (1. - omp) * omg;
-        dq = dq + PF(p.evapg1, k) * sqrt(qgg) + PF(p.evapg2, k) * pow(qgg, powg2);
+        double sq, pw;
+        sqrt_pow_11_16(qgg, sq, pw);
+        dq = dq + PF(p.evapg1, k) * sq + PF(p.evapg2, k) * pw;
       }
       dq = dq * dtn * (q / qsatt - 1.);
       dq = dmax(-0.5 * qp, dq);
