@@ -149,36 +149,42 @@ __device__ __forceinline__ void sqrt_pow_11_16(double x, double &s1, double &pw)
 }
 
 // ---- sat.F90 (Flatau et al. polynomials with REAL(4) coefficients) ----
-__device__ __forceinline__ double poly8(double a0, double a1, double a2, double a3, double a4, double a5, double a6, double a7,
-                                        double a8, double dt) {
-  return a0 + dt * (a1 + dt * (a2 + dt * (a3 + dt * (a4 + dt * (a5 + dt * (a6 + dt * (a7 + a8 * dt)))))));
+// Coefficient tables live in constant memory: DFMA takes a constant-bank operand directly, whereas a 64-bit literal
+// costs two extra moves per use (profiles/r01e: 17 % of k_p8_micro's instructions were UMOV).
+#ifdef CRM_EMU
+#define CRM_CONST static const
+#else
+#define CRM_CONST __constant__
+#endif
+CRM_CONST double c_esatw[9] = {R4(6.105851), R4(0.4440316), R4(0.1430341e-1), R4(0.2641412e-3), R4(0.2995057e-5), R4(0.2031998e-7),
+                               R4(0.6936113e-10), R4(0.2564861e-13), R4(-0.3704404e-15)};
+CRM_CONST double c_esati[9] = {R4(6.11147274), R4(0.503160820), R4(0.188439774e-1), R4(0.420895665e-3), R4(0.615021634e-5),
+                               R4(0.602588177e-7), R4(0.385852041e-9), R4(0.146898966e-11), R4(0.252751365e-14)};
+CRM_CONST double c_dtesatw[9] = {R4(0.443956472), R4(0.285976452e-1), R4(0.794747212e-3), R4(0.121167162e-4), R4(0.103167413e-6),
+                                 R4(0.385208005e-9), R4(-0.604119582e-12), R4(-0.792933209e-14), R4(-0.599634321e-17)};
+CRM_CONST double c_dtesati[9] = {R4(0.503223089), R4(0.377174432e-1), R4(0.126710138e-2), R4(0.249065913e-4), R4(0.312668753e-6),
+                                 R4(0.255653718e-8), R4(0.132073448e-10), R4(0.390204672e-13), R4(0.497275778e-16)};
+__device__ __forceinline__ double poly8(const double *a, double dt) {
+  return a[0] + dt * (a[1] + dt * (a[2] + dt * (a[3] + dt * (a[4] + dt * (a[5] + dt * (a[6] + dt * (a[7] + a[8] * dt)))))));
 }
 __device__ inline double esatw_crm(double t) {   // sat.F90:12-32
   double dt = t - R4(273.16);
-  if (dt > R4(-80.))
-    return poly8(R4(6.105851), R4(0.4440316), R4(0.1430341e-1), R4(0.2641412e-3), R4(0.2995057e-5), R4(0.2031998e-7),
-                 R4(0.6936113e-10), R4(0.2564861e-13), R4(-0.3704404e-15), dt);
+  if (dt > R4(-80.)) return poly8(c_esatw, dt);
   return (double)(2.0f * 0.01f) * exp(R4(9.550426) - R4(5723.265) / t + R4(3.53068) * log(t) - R4(0.00728332) * t);
 }
 __device__ inline double esati_crm(double t) {   // sat.F90:77-94
   double dt = t - R4(273.16);
-  if (dt > R4(-80.))
-    return poly8(R4(6.11147274), R4(0.503160820), R4(0.188439774e-1), R4(0.420895665e-3), R4(0.615021634e-5),
-                 R4(0.602588177e-7), R4(0.385852041e-9), R4(0.146898966e-11), R4(0.252751365e-14), dt);
+  if (dt > R4(-80.)) return poly8(c_esati, dt);
   return R4(0.01) * exp(R4(9.550426) - R4(5723.265) / t + R4(3.53068) * log(t) - R4(0.00728332) * t);
 }
 __device__ inline double dtesatw_crm(double t) {   // sat.F90:46-65
   double dt = t - R4(273.16);
-  if (dt > R4(-80.))
-    return poly8(R4(0.443956472), R4(0.285976452e-1), R4(0.794747212e-3), R4(0.121167162e-4), R4(0.103167413e-6),
-                 R4(0.385208005e-9), R4(-0.604119582e-12), R4(-0.792933209e-14), R4(-0.599634321e-17), dt);
+  if (dt > R4(-80.)) return poly8(c_dtesatw, dt);
   return esatw_crm(t + 1) - esatw_crm(t);
 }
 __device__ inline double dtesati_crm(double t) {   // sat.F90:108-127
   double dt = t - R4(273.16);
-  if (dt > R4(-80.))
-    return poly8(R4(0.503223089), R4(0.377174432e-1), R4(0.126710138e-2), R4(0.249065913e-4), R4(0.312668753e-6),
-                 R4(0.255653718e-8), R4(0.132073448e-10), R4(0.390204672e-13), R4(0.497275778e-16), dt);
+  if (dt > R4(-80.)) return poly8(c_dtesati, dt);
   return esati_crm(t + R4(1.)) - esati_crm(t);
 }
 __device__ __forceinline__ double qsatw_crm(double t, double p) { double es = esatw_crm(t); return R4(0.622) * es / dmax(es, p - es); }

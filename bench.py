@@ -28,8 +28,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 BYTES_PER_CELL_UPDATE = {"2d_sam1mom": 872.0}   # SURVEY.md 8(d) / App. C algorithmic traffic model
 # distinct 3-D arrays read + written per cell by each kernel of this implementation
-KERNEL_WORDS = {"k_p1_forcing": 14, "k_p2_sgs": 14, "k_p3_mom": 7, "k_p4_press_fwd": 9, "k_p5_press_bwd": 15,
-                "k_mpdata": 4, "k_precip_a": 3, "k_precip_b": 6, "k_p7_diffuse": 7, "k_p8_micro": 15, "k_stats": 8,
+KERNEL_WORDS = {"k_p1_forcing": 14, "k_p2_sgs": 13, "k_p3_mom": 7, "k_p4_press_fwd": 9, "k_p5_press_bwd": 16,
+                "k_mpdata": 4, "k_precip_a": 3, "k_precip_b": 7, "k_p7_diffuse": 7, "k_p8_micro": 13, "k_stats": 7,
                 "k_kurant": 3}
 
 
