@@ -19,6 +19,7 @@
   type *name = reinterpret_cast<type *>(name##_raw_)
 #endif
 #include <math.h>
+#include <type_traits>
 
 // REAL(4) literal promoted to double, as in the reference build without -r8
 #define R4(x) ((double)(x##f))

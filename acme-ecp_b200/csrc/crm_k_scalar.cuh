@@ -19,40 +19,50 @@ __device__ __forceinline__ double min3(double a, double b, double c) { return dm
 // FCT ratios mx/mn(ka-1);  C: limited fluxes and final update of level ka-2.  U = umf, W = wmf (mass-flux
 // velocities of adams).  fadv/flux: optional profile outputs (mkadv/mkwle), written only when `stats`.
 // f, U, W stream through a 6-stage TMA plane ring (levels ka-2..ka+1 resident, up to 3 levels of prefetch); the reciprocal
-// grid profiles (1/rho, 1/adz, 1/(rhow*adz), 2/((kc-kb)*adz)) are evaluated once per block into shared memory.
+// grid profiles (1/rho, 1/adz, 1/(rhow*adz), rho, dd/adz) are evaluated once per block into shared memory (interleaved
+// per level).
+// The kernel is issue-bound (profiles/r01e: 84 % issue-slot use, only 21 % of the instructions were FP64 math), so the
+// interior levels (3 <= ka <= nzm-1, no boundary case) run a second body, unrolled by the ring depth: every ring /
+// F1 / mx-mn slot is a compile-time shared-memory offset, the own-column and previous-level operands are carried in
+// registers instead of being re-read, and max(0,v)*a + min(0,v)*b is evaluated as v * (v > 0 ? a : b).  The general
+// body below it handles the first two and the last levels.
 #define CRM_MP_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(3, 6, P) + CRM_PROF_BYTES(5, nzp, CT) + (size_t)(9 * (P) + CRM_RED_DOUBLES(2, P, CT)) * 8)
+__device__ __forceinline__ double upw_flux(double v, double below, double above) { return v * (v > 0. ? below : above); }
 template <int NXT>
-__global__ void __launch_bounds__(CRM_MAX_P) k_mpdata(CrmP p, double *f, double *fadv, double *flux, int stats) {
+__global__ void __launch_bounds__(CRM_MAX_P, 3) k_mpdata(CrmP p, double *f, double *fadv, double *flux, int stats) {
   CRM_TILE_SETUP_T(NXT)
   CRM_XNEIGH
   CRM_DYN_SMEM(unsigned char, smraw);
-  const int nzm = p.nzm, nz = p.nz, npf = p.nzp * CT;
+  const int nzm = p.nzm, nz = p.nz;
   PlanePipe<3, 6> R;
   R.src[0] = f + fb; R.src[1] = p.umf + fb; R.src[2] = p.wmf + fb;
   double *sprof = (double *)(smraw + CRM_PIPE_BYTES(3, 6, P));
-  double *sm = sprof + 5 * npf;
+  double *sm = sprof + 5 * p.nzp * CT;
   double *sF1 = sm, *sUU = sm + 3 * P, *smx = sm + 4 * P, *smn = sm + 6 * P, *sUL = sm + 8 * P, *red = sm + 9 * P;
-  // profile slots: 0 = 1/rho, 1 = 1/adz, 2 = 1/(rhow*adz), 3 = rho, 4 = dd/adz with dd = 2/(kc-kb)
+  // profile slots (interleaved per level): 0 = 1/rho, 1 = 1/adz, 2 = 1/(rhow*adz), 3 = rho, 4 = dd/adz with dd = 2/(kc-kb)
   for (int q = tid; q < nzm * CT; q += P) {
     const int k = q / CT + 1, ln = q - (k - 1) * CT;
-    const int o = tile * p.nzp * CT + k * CT + ln, so = k * CT + ln;
+    const int o = tile * p.nzp * CT + k * CT + ln, so = k * 5 * CT + ln;
     const double rho = p.rho[o], adz = p.adz[o];
     const int kcc = imin(nzm, k + 1), kbb = imax(1, k - 1);
-    sprof[so] = 1. / rho; sprof[npf + so] = 1. / adz; sprof[2 * npf + so] = 1. / (p.rhow[o] * adz);
-    sprof[3 * npf + so] = rho; sprof[4 * npf + so] = (double)(2.f / (float)(kcc - kbb)) / adz;
+    sprof[so] = 1. / rho; sprof[so + CT] = 1. / adz; sprof[so + 2 * CT] = 1. / (p.rhow[o] * adz);
+    sprof[so + 3 * CT] = rho; sprof[so + 4 * CT] = (double)(2.f / (float)(kcc - kbb)) / adz;
   }
-#define S_IRHO(k) sprof[(k) * CT + lane]
-#define S_IADZ(k) sprof[npf + (k) * CT + lane]
-#define S_IRHOW(k) sprof[2 * npf + (k) * CT + lane]
-#define S_RHO(k) sprof[3 * npf + (k) * CT + lane]
-#define S_DD(k) sprof[4 * npf + (k) * CT + lane]
+#define S_PR(r, k) sprof[((k) * 5 + (r)) * CT + lane]
+#define S_IRHO(k) S_PR(0, k)
+#define S_IADZ(k) S_PR(1, k)
+#define S_IRHOW(k) S_PR(2, k)
+#define S_RHO(k) S_PR(3, k)
+#define S_DD(k) S_PR(4, k)
   R.init(smraw, P, tid);
   CRM_PIPE_PROLOGUE(R, nz, 4, 1)
   const double eps = R4(1.e-10);
   double WW_prev = 0. /* WW(ka-1) */, UU_prev = 0. /* UU(ka-2) after shift */, WWlim_k = 0.;
   double mx_prev = 0., mn_prev = 0.;   // normalised mx/mn at level ka-2 (own column)
   double upw_m1 = 0., upw_m2 = 0.;     // upwind www at levels ka-1, ka-2 (stats only)
-  for (int ka = 1; ka <= nzm + 2; ka++) {
+
+  // ------------------------------------------------------------------ general body (any ka)
+  auto edge_step = [&](const int ka) {
     if (ka + 1 <= nz) R.wait(ka + 1);
     // own-column window of the old field: f(ka-2), f(ka-1), f(ka), f(ka+1)
     const double f0mm = (ka - 2 >= 1) ? R.plane(0, ka - 2)[tid] : 0.;
@@ -160,7 +170,114 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_mpdata(CrmP p, double *f, double 
     WW_prev = WW_ka;
     mx_prev = mx_new; mn_prev = mn_new;
     upw_m2 = upw_m1; upw_m1 = upw;
+  };
+
+  // ------------------------------------------------------------------ interior body: ka = ka0 + G, 3 <= ka <= nzm-1,
+  // (ka0 - 1) % 6 == 2, so level ka + d lives in ring slot (2 + G + d) % 6, F1 slot (ka0 + G + d) % 3 with ka0 % 3 == 0.
+  // register carries (values at the top of iteration ka)
+  double c_f0 = 0., c_f1 = 0., c_f2 = 0.;           // f(ka-2), f(ka-1), f(ka)      own column
+  double c_gm = 0., c_gp = 0.;                       // f(ka-1) at i-1, i+1
+  double c_Ub = 0., c_Ubp = 0.;                      // U(ka-1) at i, i+1
+  double c_Wk = 0., c_Wb = 0., c_Wbm = 0.;           // W(ka) own; W(ka-1) own and at i-1
+  double c_www = 0.;                                 // upwind vertical flux at the lower face of level ka
+  double c_F1b = 0., c_F1bm = 0., c_F1bp = 0.;       // F1(ka-1) at i, i-1, i+1
+  double c_F1d = 0., c_F1dm = 0.;                    // F1(ka-2) at i, i-1
+  const double *rbuf = R.buf;
+  auto interior_step = [&](auto Gc, const int ka0) {
+    constexpr int G = decltype(Gc)::value;
+    constexpr int S_C = (2 + G) % 6, S_P = (3 + G) % 6;            // ring slots of levels ka, ka+1
+    constexpr int A_A = G % 3;                                      // F1 slot of level ka (ka0 % 3 == 0)
+    constexpr int X_B = (G + 0) & 1;                                // mx/mn slot of level kb_ = ka-1: (ka0-1+G) & 1, ka0 odd
+    constexpr int X_C = X_B ^ 1;                                    // ... of level ka-2
+    const int ka = ka0 + G;
+    R.wait(ka + 1);
+    const double *Fk = rbuf + (size_t)(S_C * 3 + 0) * P, *Uk = rbuf + (size_t)(S_C * 3 + 1) * P, *Wc = rbuf + (size_t)(S_C * 3 + 2) * P;
+    const double *Fp = rbuf + (size_t)(S_P * 3 + 0) * P, *Wp_ = rbuf + (size_t)(S_P * 3 + 2) * P;
+    const double *pr = sprof + (size_t)ka * 5 * CT + lane;          // profiles of level ka; level ka-1 at pr - 5*CT
+    // ---- stage A
+    const double f_p = Fp[tid];
+    const double fk_m = Fk[tm1], fk_p = Fk[tp1];
+    const double Ui = Uk[tid], Uip = Uk[tp1];
+    const double Wp = Wp_[tid];
+    const double uuu_i = upw_flux(Ui, fk_m, c_f2);
+    const double uuu_ip = upw_flux(Uip, c_f2, fk_p);
+    const double www_kp = upw_flux(Wp, c_f2, f_p);
+    const double irho_a = pr[0], iadz_a = pr[CT];
+    const double F1a = c_f2 - (uuu_ip - uuu_i + (www_kp - c_www) * iadz_a) * irho_a;
+    sF1[A_A * P + tid] = F1a;
+    const double upw = c_www;
+    __syncthreads();   // (1)
+    if (tid == 0 && ka + 4 <= nz) R.issue(ka + 4);
+    // ---- stage B
+    const double Fa_p = sF1[A_A * P + tp1], Fa_m = sF1[A_A * P + tm1];
+    const double WW_ka = andiff(c_F1b, F1a, c_Wk, pr[2 * CT]) -
+                         across(c_F1bp + Fa_p - c_F1bm - Fa_m, c_Wk, c_Ub + Ui + Uip + c_Ubp) * irho_a;
+    const double irho_b = pr[-5 * CT], dd = pr[-CT];
+    const double Wc_m = Wc[tm1];
+    const double UU = andiff(c_F1bm, c_F1b, c_Ub, irho_b) -
+                      across(dd * (Fa_m + F1a - c_F1dm - c_F1d), c_Ub, c_Wbm + Wc_m + c_Wb + c_Wk) * irho_b;
+    const double mx0 = dmax(dmax(dmax(dmax(c_gm, c_gp), c_f0), c_f2), c_f1);
+    const double mn0 = dmin(dmin(dmin(dmin(c_gm, c_gp), c_f0), c_f2), c_f1);
+    const double mxr = dmax(dmax(dmax(dmax(dmax(c_F1bm, c_F1bp), c_F1d), F1a), c_F1b), mx0);
+    const double mnr = dmin(dmin(dmin(dmin(dmin(c_F1bm, c_F1bp), c_F1d), F1a), c_F1b), mn0);
+    sUU[tid] = UU;
+    __syncthreads();   // (2)
+    const double UUp = sUU[tp1];
+    const double rho_b = pr[-2 * CT], iadz_b = pr[-4 * CT];
+    const double mx_new = (mxr == c_F1b) ? 0. : rho_b * (mxr - c_F1b) / (pn_(UUp) + pp_(UU) + iadz_b * (pn_(WW_ka) + pp_(WW_prev)) + eps);
+    const double mn_new = (c_F1b == mnr) ? 0. : rho_b * (c_F1b - mnr) / (pp_(UUp) + pn_(UU) + iadz_b * (pp_(WW_ka) + pn_(WW_prev)) + eps);
+    smx[X_B * P + tid] = mx_new;
+    smn[X_B * P + tid] = mn_new;
+    __syncthreads();   // (3)
+    // ---- stage C: level ka-2
+    const double WWlim_kp1 = WW_prev * (WW_prev > 0. ? dmin(dmin(1., mx_new), mn_prev) : dmin(dmin(1., mx_prev), mn_new));
+    const double mx_m = smx[X_C * P + tm1], mn_m = smn[X_C * P + tm1];
+    const double ULim = UU_prev * (UU_prev > 0. ? dmin(dmin(1., mx_prev), mn_m) : dmin(dmin(1., mx_m), mn_prev));
+    sUL[tid] = ULim;
+    __syncthreads();   // (4)
+    const double ULp = sUL[tp1];
+    const double fnew = dmax(0., c_F1d - (ULp - ULim + (WWlim_kp1 - WWlim_k) * pr[-9 * CT]) * pr[-10 * CT]);
+    F3(f, ka - 2) = fnew;
+    if (stats) {
+      double v[2] = {fnew - c_f0, upw_m2 + WWlim_k};
+      block_sum_lead<2>(v, tid, P, CT, red);
+      if (i == 0) { PF(fadv, ka - 2) = v[0]; PF(flux, ka - 2) = v[1]; }
+    }
+    // ---- shift
+    WWlim_k = WWlim_kp1; UU_prev = UU; WW_prev = WW_ka; mx_prev = mx_new; mn_prev = mn_new;
+    upw_m2 = upw_m1; upw_m1 = upw;
+    c_f0 = c_f1; c_f1 = c_f2; c_f2 = f_p;
+    c_gm = fk_m; c_gp = fk_p;
+    c_Ub = Ui; c_Ubp = Uip;
+    c_Wbm = Wc_m; c_Wb = c_Wk; c_Wk = Wp; c_www = www_kp;
+    c_F1d = c_F1b; c_F1dm = c_F1bm;
+    c_F1b = F1a; c_F1bm = Fa_m; c_F1bp = Fa_p;
+  };
+
+  int ka = 1;
+  edge_step(1);
+  edge_step(2);
+  ka = 3;
+  if (ka + 5 <= nzm - 1) {
+    // enter the interior region at ka = 3: fill the register carries from the ring / F1 planes
+    c_f0 = R.plane(0, 1)[tid]; c_f1 = R.plane(0, 2)[tid]; c_f2 = R.plane(0, 3)[tid];
+    c_gm = R.plane(0, 2)[tm1]; c_gp = R.plane(0, 2)[tp1];
+    c_Ub = R.plane(1, 2)[tid]; c_Ubp = R.plane(1, 2)[tp1];
+    c_Wk = R.plane(2, 3)[tid]; c_Wb = R.plane(2, 2)[tid]; c_Wbm = R.plane(2, 2)[tm1];
+    c_www = upw_flux(c_Wk, c_f1, c_f2);
+    c_F1b = sF1[2 * P + tid]; c_F1bm = sF1[2 * P + tm1]; c_F1bp = sF1[2 * P + tp1];
+    c_F1d = sF1[1 * P + tid]; c_F1dm = sF1[1 * P + tm1];
+    for (; ka + 5 <= nzm - 1; ka += 6) {
+      interior_step(std::integral_constant<int, 0>{}, ka);
+      interior_step(std::integral_constant<int, 1>{}, ka);
+      interior_step(std::integral_constant<int, 2>{}, ka);
+      interior_step(std::integral_constant<int, 3>{}, ka);
+      interior_step(std::integral_constant<int, 4>{}, ka);
+      interior_step(std::integral_constant<int, 5>{}, ka);
+    }
   }
+  for (; ka <= nzm + 2; ka++) edge_step(ka);
+#undef S_PR
 #undef S_IRHO
 #undef S_IADZ
 #undef S_IRHOW

@@ -1,7 +1,9 @@
 #!/bin/bash
-# ncu full capture of one steady sub-step in the DEVELOPED state (180-step spin-up, profiler started after it), 4736 CRMs
+# One ncu --set full capture (with source counters) of one developed-state sub-step, 4736 CRMs of the cfg2 geometry.
+# The profiler range starts after the untimed spin-up call (tools/prof_run.py --spinup -> cudaProfilerStart).
 mkdir -p gpurun_out
-timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off \
-   -k regex:'k_(p[0-9]|mpdata|precip_[ab]|stats|kurant)' -s 15 -c 16 \
-   -o gpurun_out/prof_cur -f python tools/prof_run.py --ncrms 4736 --spinup 180 --nstop 6 --calls 1 > gpurun_out/prof.log 2>&1
+REGEX=${1:-'k_(p[0-9]|mpdata|precip_[ab]|stats|kurant)'}
+timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"$REGEX" -s 14 -c ${2:-16} \
+   -o gpurun_out/prof_dev -f python tools/prof_run.py --ncrms 4736 --nstop 4 --calls 1 --spinup 180 > gpurun_out/prof.log 2>&1
 tail -3 gpurun_out/prof.log
+ls -la gpurun_out/
