@@ -84,6 +84,7 @@ struct Handle {
   std::string err;
   crm_run_stats_t stats;
   long long launches = 0;
+  int precip_launches = 4;            // k_precip_b launches per sub-step (the last one runs any remaining sub-iterations)
   int last_nb_u = 1;                  // buffer index holding dudt(nb) after the last run (debug fetch)
 };
 
@@ -166,6 +167,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   while (d->nx * CT < 32) CT <<= 1;   // a block is at least one warp (warp-shuffle slab reductions)
   if (CT < 1 || d->nx * CT > CRM_MAX_P) { g_init_err = "crm_b200_init: nx too large (nx <= 256)"; delete h; return 4; }
   h->CT = CT;
+  if (const char *e = getenv("CRM_B200_PRECIP_LAUNCHES")) { int v = atoi(e); if (v >= 1 && v <= 16) h->precip_launches = v; }
   h->geo = ((d->nx == 64 || d->nx == 32) && CT == crm_static_ct(d->nx)) ? d->nx : 0;
 #ifdef CRM_EMU
   h->geo = 0;
@@ -205,6 +207,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
     PRF(*f);
   for (double **f : {&p.dz, &p.z0, &p.colprec0, &p.colprecs0, &p.s_cltot, &p.s_clhgh, &p.s_clmed, &p.s_cllow}) SL(*f);
   p.kmin = carve<int>(h, h->slot_elems); p.kmax = carve<int>(h, h->slot_elems); p.ndamp = carve<int>(h, h->slot_elems);
+  p.kprec = carve<int>(h, h->ntiles);
   p.precsfc = carve<double>(h, h->col_elems); p.precssfc = carve<double>(h, h->col_elems);
   p.cfl_bits = carve<unsigned long long>(h, 2); p.prec_cfl_bits = p.cfl_bits ? p.cfl_bits + 1 : nullptr;
   p.flags = carve<int>(h, 4);
@@ -215,7 +218,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   h->out_dev = carve<double>(h, (size_t)d->ld * (39 * (size_t)d->plev + 16 + (size_t)d->nx * d->ny));
   h->rnd_dev = carve<double>(h, (size_t)d->ncrms * 5 * d->nx * d->ny);
   h->gcol_dev = carve<int>(h, d->ld);
-  ok = ok && p.kmin && p.kmax && p.ndamp && p.precsfc && p.precssfc && p.cfl_bits && p.flags && p.twc && p.tws && h->stage && h->esum &&
+  ok = ok && p.kmin && p.kmax && p.ndamp && p.kprec && p.precsfc && p.precssfc && p.cfl_bits && p.flags && p.twc && p.tws && h->stage && h->esum &&
        h->in_dev && h->out_dev && h->rnd_dev && h->gcol_dev;
   if (!ok) {
     g_init_err = "crm_b200_init: device allocation failed (workspace arena)";
@@ -457,7 +460,9 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
       if (dbg_stop == 5) { dbg_break = true; break; }
       dev_zero(p.prec_cfl_bits, 8);
       LAUNCH_G(h, k_precip_a, ntiles, P, CRM_PRECIPA_SMEM(P, CT, h->nzp), p);
-      LAUNCH_G(h, k_precip_b, ntiles, P, CRM_PRECIPB_SMEM(P, CT, h->nzp), p);
+      // one launch per sedimentation sub-iteration; nprec is only known on the device, launches beyond it return at once
+      for (int ip = 1; ip <= h->precip_launches; ip++)
+        LAUNCH_G(h, k_precip_b, ntiles, P, CRM_PRECIPB_SMEM(P, CT, h->nzp), p, ip, ip == h->precip_launches ? 1 : 0);
       // uvw.F90: u <- dudt(nc) is a role rotation of the buffers (with the AB rotation of crm_module.F90:884-887)
       { int o_u = iu, o_a = ina, o_b = inb, o_c = inc; iu = o_c; ina = o_u; inb = o_a; inc = o_b; }
       p.u = h->ubuf[iu]; p.w = h->wbuf[iu];

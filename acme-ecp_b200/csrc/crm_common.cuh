@@ -96,6 +96,7 @@ struct CrmP {
   // ---- per-CRM scalars (tile, lane) ----
   double *dz, *z0, *colprec0, *colprecs0, *s_cltot, *s_clhgh, *s_clmed, *s_cllow;
   int *kmin, *kmax, *ndamp;
+  int *kprec;                            // per tile: highest level holding precipitation (k_precip_a)
   // ---- per-column 2-D (tile, tid) ----
   double *precsfc, *precssfc;
   // ---- batch-global scalars on device ----

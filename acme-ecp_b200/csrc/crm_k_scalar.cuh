@@ -311,11 +311,14 @@ __device__ __forceinline__ double term_vel_qp(const MicroScalars &m, double qplo
 }
 
 // microphysics.F90:578-640: fall speed of every cell + batch-global prec_cfl.  qp, tabs through a 3-stage TMA ring.
+// Also records, per tile, the highest level that holds any precipitation (kprec): above it the sedimentation of
+// k_precip_b is the identity and is skipped.
 #define CRM_PRECIPA_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(2, 3, P) + CRM_PROF_BYTES(3, nzp, CT) + (size_t)(P) * 8)
 template <int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P) k_precip_a(CrmP p) {
   CRM_TILE_SETUP_T(NXT)
   CRM_DYN_SMEM(unsigned char, smraw);
+  __shared__ int s_kt;
   const int nzm = p.nzm, npf = p.nzp * CT;
   PlanePipe<2, 3> R;
   R.src[0] = p.qp + fb; R.src[1] = p.tabs + fb;
@@ -325,70 +328,97 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_precip_a(CrmP p) {
     const double *const g[3] = {p.rho, p.adz, p.rhow};
     stage_profiles<3>(sprof, g, tile, p.nzp, CT, tid, P);
   }
+  if (tid == 0) s_kt = 0;
   R.init(smraw, P, tid);
   CRM_PIPE_PROLOGUE(R, nzm, 2, 0)
   const double dz = p.dz[cb];
+  const double idtn = 1. / p.dtn;
   double cfl = 0.;
+  int kt = 0;
   for (int k = 1; k <= nzm; k++) {
     __syncthreads();
     CRM_PIPE_STEP(R, k, nzm, 2, 0)
-    const double rho = sprof[k * CT + lane];
-    const double rhofac = sqrt(R4(1.29) / rho);
-    const int kb = imax(1, k - 1);
-    const double wmax = dz * sprof[npf + kb * CT + lane] / p.dtn;
-    const double iwmax = 1. / wmax;
-    const double tv = term_vel_qp(p.ms, R.plane(0, k)[tid], rho, R.plane(1, k)[tid]);
-    const double wpv = rhofac * tv;
-    cfl = dmax(cfl, wpv * iwmax);
+    const double q = R.plane(0, k)[tid];
+    if (q != 0.) kt = k;
+    double wpv = 0.;
+    if (q > CRM_QP_THRESHOLD) {
+      const double rho = sprof[k * CT + lane];
+      const double rhofac = sqrt(R4(1.29) / rho);
+      const int kb = imax(1, k - 1);
+      const double wmax = dz * sprof[npf + kb * CT + lane] * idtn;
+      wpv = rhofac * term_vel_qp(p.ms, q, rho, R.plane(1, k)[tid]);
+      cfl = dmax(cfl, wpv / wmax);
+    }
     F3(p.wp, k) = -wpv * sprof[2 * npf + k * CT + lane] * p.dtn / dz;
   }
+  if (kt > 0) atomicMax(&s_kt, kt);
   const double m = block_max_all(cfl, tid, P, red);
-  if (tid == 0) atomicMax(p.prec_cfl_bits, (unsigned long long)__double_as_longlong(m));
+  if (tid == 0) {
+    atomicMax(p.prec_cfl_bits, (unsigned long long)__double_as_longlong(m));
+    p.kprec[tile] = s_kt;
+  }
 }
 
-// microphysics.F90:642-830: nprec sub-iterations of the 1-D MPDATA/FCT sedimentation, one thread per column with a
-// sliding register window (q, wp, tq 3 levels ahead of the level being finalised).
-// First pass (iprec = 1): qp, wp, tabs, t stream through a 6-stage TMA plane ring (levels s-3..s resident).  Later
-// passes re-read what this kernel has just written, so they use ordinary loads (own column only: program order).
-#define CRM_PRECIPB_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(4, 6, P) + CRM_PROF_BYTES(3, nzp, CT) + (size_t)2 * CRM_RED_DOUBLES(2, P, CT) * 8)
+// microphysics.F90:642-830: the nprec sub-iterations of the 1-D MPDATA/FCT sedimentation, one thread per column with a
+// sliding register window (q, wp, tq 3 levels ahead of the level being finalised).  One launch = one sub-iteration
+// `iprec0` (launches beyond the batch-global nprec return at once; the last launch of the host's fixed series also runs
+// any remaining iterations), so every pass streams qp, wp, tabs, t through the 6-stage TMA plane ring.
+//  * only levels 1..kprec+1 of the tile are marched (all fluxes above are exactly zero);
+//  * a warp whose columns have seen six consecutive precipitation-free levels skips the level (every window variable
+//    is exactly zero there, the update is the identity);
+//  * slab sums: only F(k) = sum_x of the limited flux is reduced; qpfall(k) += -(F(k+1)-F(k))/(rho*adz) follows from it
+//    because 1/(rho*adz) is constant over the slab (microphysics.F90:772-776).
+#define CRM_PRECIPB_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(4, 6, P) + CRM_PROF_BYTES(5, nzp, CT) + (size_t)2 * CRM_RED_DOUBLES(1, P, CT) * 8)
 template <int NXT>
-__global__ void __launch_bounds__(CRM_MAX_P, 3) k_precip_b(CrmP p) {
+__global__ void __launch_bounds__(CRM_MAX_P, 3) k_precip_b(CrmP p, int iprec0, int run_rest) {
   CRM_TILE_SETUP_T(NXT)
   CRM_DYN_SMEM(unsigned char, smraw);
+  const double prec_cfl = __longlong_as_double((long long)*p.prec_cfl_bits);
+  int nprec = 1;
+  if (prec_cfl > R4(0.9)) nprec = (int)ceil(prec_cfl / R4(0.9));
+  if (iprec0 > nprec) return;
+  const int ktp = p.kprec[tile];
+  if (ktp == 0) return;                        // no precipitation anywhere in this tile
   const int nzm = p.nzm, npf = p.nzp * CT;
+  const int KT = imin(nzm, ktp + 1);           // levels above KT: q = 0 and every flux is exactly 0
+  const int iprec1 = run_rest ? nprec : iprec0;
   PlanePipe<4, 6> R;
   R.src[0] = p.qp + fb; R.src[1] = p.wp + fb; R.src[2] = p.tabs + fb; R.src[3] = p.t + fb;
   double *sprof = (double *)(smraw + CRM_PIPE_BYTES(4, 6, P));
-  double *red = sprof + 3 * npf;
-  // profile slots: 0 = 1/(rho*adz), 1 = rho*adz, 2 = rho
-  for (int q = tid; q < nzm * CT; q += P) {
+  double *red = sprof + 5 * npf;
+  // profile slots: 0 = 1/(rho*adz), 1 = rho*adz, 2 = rho, 3 = sqrt(1.29/rho), 4 = rhow*dtn/dz/nprec
+  const double dz = p.dz[cb];
+  for (int q = tid; q < imin(nzm, KT + 3) * CT; q += P) {   // the window reaches three levels above KT
     const int k = q / CT + 1, ln = q - (k - 1) * CT;
     const int o = tile * p.nzp * CT + k * CT + ln, so = k * CT + ln;
     const double rho = p.rho[o], adz = p.adz[o];
     sprof[so] = 1. / (rho * adz); sprof[npf + so] = rho * adz; sprof[2 * npf + so] = rho;
+    sprof[3 * npf + so] = sqrt(R4(1.29) / rho);
+    sprof[4 * npf + so] = p.rhow[o] * p.dtn / p.dz[tile * CT + ln] / (double)nprec;
   }
 #define S_IRA(k) sprof[(k) * CT + lane]
 #define S_RA(k) sprof[npf + (k) * CT + lane]
 #define S_RHO(k) sprof[2 * npf + (k) * CT + lane]
+#define S_RHOFAC(k) sprof[3 * npf + (k) * CT + lane]
+#define S_WC(k) sprof[4 * npf + (k) * CT + lane]
+  (void)dz;
   R.init(smraw, P, tid);
-  CRM_PIPE_PROLOGUE(R, nzm, 2, 0)
   const double eps = R4(1.e-10);
-  const double dz = p.dz[cb];
-  const double prec_cfl = __longlong_as_double((long long)*p.prec_cfl_bits);
-  int nprec = 1;
-  if (prec_cfl > R4(0.9)) nprec = (int)ceil(prec_cfl / R4(0.9));
   const long long c2 = (long long)tile * P + tid;
-  const int RS = CRM_RED_DOUBLES(2, P, CT);
-  // slab sums of level lev: qpfall += sum(dq), precflux -= sum(fz)   (microphysics.F90:772-776)
-  auto book_at = [&](int lev) {
-    return [&p, tile, CT, lev](int q, int ln, double sum) {
-      const int o = tile * p.nzp * CT + lev * CT + ln;
-      if (q == 0) acc_add(p.qpfall + o, sum); else acc_add(p.precflux + o, -sum);
-    };
-  };
-  for (int iprec = 1; iprec <= nprec; iprec++) {
-    const bool ring = (iprec == 1);
-    const bool scale_wp = (iprec == 1 && nprec > 1);   // wp = wp/nprec (microphysics.F90:648-660); later iterations store scaled wp
+  const int RS = CRM_RED_DOUBLES(1, P, CT);
+  const int wrp = tid >> 5, nw = P >> 5;
+  for (int iprec = iprec0; iprec <= iprec1; iprec++) {
+    if (iprec > iprec0) {
+#ifndef CRM_EMU
+      // the ring re-reads what this block has just written with ordinary stores: order them before the bulk copies
+      asm volatile("fence.proxy.async;" ::: "memory");
+#endif
+      __syncthreads();
+      R.init(smraw, P, tid);   // fresh barrier phases
+    }
+    CRM_PIPE_PROLOGUE(R, KT, 2, 0)
+    const bool scale_wp = (iprec == 1 && nprec > 1);   // wp = wp/nprec (microphysics.F90:648-660); later iterations read scaled wp
+    const bool more = iprec < nprec;
     // window variables, index s = level being loaded
     double q0 = 0., q1 = 0., q2 = 0., q3 = 0.;          // q(s-3), q(s-2), q(s-1), q(s)
     double w1 = 0., w2 = 0., w3 = 0.;                   // wp(s-2), wp(s-1), wp(s)
@@ -398,33 +428,40 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_precip_b(CrmP p) {
     double mxn0 = 0., mnn0 = 0., mxn1 = 0., mnn1 = 0.;  // normalised at s-3, s-2
     double fzl0 = 0., fzl1 = 0.;                        // limited flux at s-3, s-2
     double om0 = 0., om1 = 0., om2 = 0., om3 = 0.;      // omega(s-3..s)
-    // later passes (ordinary loads): the next level is fetched one iteration ahead
-    double nq = 0., nwp = 0., ntb = 0., nt = 0.;
-    if (!ring) { nq = F3(p.qp, 1); nwp = F3(p.wp, 1); ntb = F3(p.tabs, 1); }
-    for (int s = 1; s <= nzm + 3; s++) {
+    double Fprev = 0.;                                  // threads tid < CT: slab sum F(L-1) of lane tid
+    int zc = 6;                                         // consecutive precipitation-free levels loaded so far
+    for (int s = 1; s <= KT + 3; s++) {
       __syncthreads();   // ring slot of level s-4 is free; warp partials of level k3 = s-4 are visible
-      if (ring) { CRM_PIPE_STEP(R, s, nzm, 2, 0) }
-      if (s - 4 >= 1) red_get<2>(tid, P, CT, red + (s & 1) * RS, book_at(s - 4));
+      CRM_PIPE_STEP(R, s, KT, 2, 0)
+      if (s - 4 >= 1 && tid < CT) {   // F(L), L = s-4: precflux(L) -= F(L); qpfall(L-1) += -(F(L) - F(L-1))/(rho*adz)(L-1)
+        const int L = s - 4;
+        const double *rd = red + (s & 1) * RS;
+        double F = rd[tid];
+        for (int g = 1; g < nw; g++) F += rd[g * CT + tid];
+        const int o = tile * p.nzp * CT + L * CT + tid;
+        acc_add(p.precflux + o, -F);
+        if (L >= 2) acc_add(p.qpfall + o - CT, -(F - Fprev) * sprof[(L - 1) * CT + tid]);
+        Fprev = F;
+      }
       // ---- load level s
       q0 = q1; q1 = q2; q2 = q3; w1 = w2; w2 = w3; fz2 = fz3; om0 = om1; om1 = om2; om2 = om3;
-      double t_k3 = 0.;
-      if (ring) { if (s - 3 >= 1) t_k3 = R.plane(3, s - 3)[tid]; }
-      else { t_k3 = nt; if (s - 2 >= 1 && s - 2 <= nzm) nt = F3(p.t, s - 2); }
-      if (s <= nzm) {
-        double tb;
-        if (ring) { q3 = R.plane(0, s)[tid]; w3 = R.plane(1, s)[tid]; tb = R.plane(2, s)[tid]; }
-        else {
-          q3 = nq; w3 = nwp; tb = ntb;
-          if (s + 1 <= nzm) { nq = F3(p.qp, s + 1); nwp = F3(p.wp, s + 1); ntb = F3(p.tabs, s + 1); }
-        }
-        if (scale_wp) { w3 = w3 / (double)nprec; }
+      if (s <= KT) {
+        q3 = R.plane(0, s)[tid]; w3 = R.plane(1, s)[tid];
+        const double tb = R.plane(2, s)[tid];
+        if (scale_wp) w3 = w3 / (double)nprec;
         fz3 = q3 * w3;
         om3 = dmax(0., dmin(1., (tb - CRM_TPRMIN) * p.ms.a_pr));
       } else { q3 = 0.; w3 = 0.; fz3 = 0.; om3 = 0.; }
+      zc = (q3 == 0.) ? zc + 1 : 0;
+      const int k3 = s - 3;
+      if (__all_sync(0xffffffffu, zc >= 6)) {   // warp-uniform: the whole window is exactly zero, the update is the identity
+        if (k3 >= 1 && (tid & 31) < CT) red[(k3 & 1) * RS + wrp * CT + lane] = 0.;
+        continue;
+      }
       // ---- tq(s-1)
       tq0 = tq1; tq1 = tq2;
       const int k1 = s - 1;
-      if (k1 >= 1 && k1 <= nzm) tq2 = q2 - (fz3 - fz2) / 1. * S_IRA(k1);
+      if (k1 >= 1 && k1 <= nzm) tq2 = q2 - (fz3 - fz2) * S_IRA(k1);
       else tq2 = 0.;
       // ---- www(s-1) = 0.5*(1+wp*irhoadz)*(tq(kb)*wp(kb) - tq(k)*wp(k)), kb = max(1,k-1)
       ww1 = ww2;
@@ -456,36 +493,43 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_precip_b(CrmP p) {
         fzl1 = fzk2 + pp_(ww1) * dmin(dmin(1., mxn1), mnb) - pn_(ww1) * dmin(dmin(1., mxb), mnn1);
       } else fzl1 = 0.;   // fz(nz) = 0
       // ---- final update at k3 = s-3
-      const int k3 = s - 3;
-      if (k3 >= 1 && k3 <= nzm) {
+      if (k3 >= 1) {   // k3 <= KT by the loop bound
         const double irhoadz = S_IRA(k3);
-        const double dq = -(fzl1 - fzl0) * irhoadz;
         const double qnew = q0 - (fzl1 - fzl0) * irhoadz;
         F3(p.qp, k3) = qnew;
         const double lf0 = CRM_FAC_COND + (1 - om0) * CRM_FAC_FUS;
         const double lf1 = (k3 + 1 <= nzm) ? CRM_FAC_COND + (1 - om1) * CRM_FAC_FUS : 0.;
         const double lat_heat = -(lf1 * fzl1 - lf0 * fzl0) * irhoadz;
-        F3(p.t, k3) = t_k3 - lat_heat;
+        F3(p.t, k3) = R.plane(3, k3)[tid] - lat_heat;
         if (k3 == 1) {
           p.precsfc[c2] = p.precsfc[c2] - fzl0 * 1.;
           p.precssfc[c2] = p.precssfc[c2] - fzl0 * (1. - om0) * 1.;
         }
-        if (iprec < nprec) {   // new fall speed for the next iteration (microphysics.F90:794-817)
-          const double rho = S_RHO(k3);
-          const double tv = term_vel_qp(p.ms, qnew, rho, ring ? R.plane(2, k3)[tid] : F3(p.tabs, k3));
-          const double wpv = sqrt(R4(1.29) / rho) * tv;
-          F3(p.wp, k3) = -wpv * PF(p.rhow, k3) * p.dtn / dz / (double)nprec;
+        if (more) {   // new fall speed for the next iteration (microphysics.F90:794-817)
+          double wpn = 0.;
+          if (qnew > CRM_QP_THRESHOLD) wpn = S_RHOFAC(k3) * term_vel_qp(p.ms, qnew, S_RHO(k3), R.plane(2, k3)[tid]);
+          F3(p.wp, k3) = -wpn * S_WC(k3);
         }
-        double v[2] = {dq, fzl0};
-        red_put<2>(v, tid, CT, red + (k3 & 1) * RS);   // finished after the next barrier (deferred: one barrier per level)
+        double v[1] = {fzl0};
+        red_put<1>(v, tid, CT, red + (k3 & 1) * RS);   // finished after the next barrier (deferred: one barrier per level)
       }
     }
     __syncthreads();
-    red_get<2>(tid, P, CT, red + (nzm & 1) * RS, book_at(nzm));
+    if (tid < CT) {   // F(KT) and the top level: F(KT+1) = 0
+      const double *rd = red + (KT & 1) * RS;
+      double F = rd[tid];
+      for (int g = 1; g < nw; g++) F += rd[g * CT + tid];
+      const int o = tile * p.nzp * CT + KT * CT + tid;
+      acc_add(p.precflux + o, -F);
+      if (KT >= 2) acc_add(p.qpfall + o - CT, -(F - Fprev) * sprof[(KT - 1) * CT + tid]);
+      acc_add(p.qpfall + o, -(0. - F) * sprof[KT * CT + tid]);
+    }
   }
 #undef S_IRA
 #undef S_RA
 #undef S_RHO
+#undef S_RHOFAC
+#undef S_WC
 }
 
 // diffuse_scalar2D.F90:70-138 + diffuse_scalar.F90:55-70 for t, qt, qp in one pass (fluxb = fluxt = 0).

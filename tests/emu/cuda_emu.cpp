@@ -6,12 +6,16 @@ emu_dim3 blockDim, gridDim;
 pthread_barrier_t emu_barrier;
 char *emu_dyn_smem = nullptr;
 double emu_shfl_buf[2048];
+int emu_vote_buf[2048];
+pthread_barrier_t emu_warp_barrier[64];
 
 void emu_launch(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body) {
   gridDim.x = grid; blockDim.x = block;
   std::vector<char> dyn(smem + 64);
   emu_dyn_smem = dyn.data();
   pthread_barrier_init(&emu_barrier, nullptr, block);
+  const unsigned nwarps = (block + 31) / 32;
+  for (unsigned w = 0; w < nwarps; w++) pthread_barrier_init(&emu_warp_barrier[w], nullptr, block - 32 * w < 32 ? block - 32 * w : 32);
   for (unsigned b = 0; b < grid; b++) {
     std::vector<std::thread> th;
     th.reserve(block);
@@ -23,5 +27,6 @@ void emu_launch(unsigned grid, unsigned block, size_t smem, const std::function<
     for (auto &x : th) x.join();
   }
   pthread_barrier_destroy(&emu_barrier);
+  for (unsigned w = 0; w < nwarps; w++) pthread_barrier_destroy(&emu_warp_barrier[w]);
   emu_dyn_smem = nullptr;
 }

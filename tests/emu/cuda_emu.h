@@ -30,14 +30,35 @@ extern char *emu_dyn_smem;
 
 static inline void __syncthreads() { pthread_barrier_wait(&emu_barrier); }
 
-// warp shuffles: emulated block-wide (all threads of the block must call convergently, which the kernels guarantee)
+// warp primitives: emulated per warp of 32 consecutive threads (one pthread barrier per warp), so that warp-uniform
+// branches around shuffles/votes behave as on the device
 extern double emu_shfl_buf[2048];
+extern int emu_vote_buf[2048];
+extern pthread_barrier_t emu_warp_barrier[64];
 static inline double __shfl_xor_sync(unsigned, double v, int lanemask) {
+  pthread_barrier_t *wb = &emu_warp_barrier[threadIdx.x >> 5];
   emu_shfl_buf[threadIdx.x] = v;
-  pthread_barrier_wait(&emu_barrier);
+  pthread_barrier_wait(wb);
   double r = emu_shfl_buf[threadIdx.x ^ (unsigned)lanemask];
-  pthread_barrier_wait(&emu_barrier);
+  pthread_barrier_wait(wb);
   return r;
+}
+static inline unsigned __ballot_sync(unsigned, int pred) {
+  pthread_barrier_t *wb = &emu_warp_barrier[threadIdx.x >> 5];
+  emu_vote_buf[threadIdx.x] = pred != 0;
+  pthread_barrier_wait(wb);
+  unsigned r = 0;
+  const unsigned w0 = threadIdx.x & ~31u;
+  for (unsigned l = 0; l < 32 && w0 + l < blockDim.x; l++) r |= (unsigned)emu_vote_buf[w0 + l] << l;
+  pthread_barrier_wait(wb);
+  return r;
+}
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+static inline int __all_sync(unsigned m, int pred) {
+  const unsigned w0 = threadIdx.x & ~31u;
+  const unsigned n = blockDim.x - w0 < 32 ? blockDim.x - w0 : 32;
+  const unsigned full = n == 32 ? 0xffffffffu : ((1u << n) - 1);
+  return __ballot_sync(m, pred) == full;
 }
 
 static inline unsigned long long atomicMax(unsigned long long *a, unsigned long long v) {
