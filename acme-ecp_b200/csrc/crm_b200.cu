@@ -207,7 +207,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
     PRF(*f);
   for (double **f : {&p.dz, &p.z0, &p.colprec0, &p.colprecs0, &p.s_cltot, &p.s_clhgh, &p.s_clmed, &p.s_cllow}) SL(*f);
   p.kmin = carve<int>(h, h->slot_elems); p.kmax = carve<int>(h, h->slot_elems); p.ndamp = carve<int>(h, h->slot_elems);
-  p.kprec = carve<int>(h, h->ntiles);
+  p.kprec = carve<int>(h, h->ntiles); p.kqp = carve<int>(h, h->ntiles);
   p.precsfc = carve<double>(h, h->col_elems); p.precssfc = carve<double>(h, h->col_elems);
   p.cfl_bits = carve<unsigned long long>(h, 2); p.prec_cfl_bits = p.cfl_bits ? p.cfl_bits + 1 : nullptr;
   p.flags = carve<int>(h, 4);
@@ -218,7 +218,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   h->out_dev = carve<double>(h, (size_t)d->ld * (39 * (size_t)d->plev + 16 + (size_t)d->nx * d->ny));
   h->rnd_dev = carve<double>(h, (size_t)d->ncrms * 5 * d->nx * d->ny);
   h->gcol_dev = carve<int>(h, d->ld);
-  ok = ok && p.kmin && p.kmax && p.ndamp && p.kprec && p.precsfc && p.precssfc && p.cfl_bits && p.flags && p.twc && p.tws && h->stage && h->esum &&
+  ok = ok && p.kmin && p.kmax && p.ndamp && p.kprec && p.kqp && p.precsfc && p.precssfc && p.cfl_bits && p.flags && p.twc && p.tws && h->stage && h->esum &&
        h->in_dev && h->out_dev && h->rnd_dev && h->gcol_dev;
   if (!ok) {
     g_init_err = "crm_b200_init: device allocation failed (workspace arena)";
@@ -454,9 +454,9 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
 #undef PRESS_CASE
       if (dbg_stop == 4) { dbg_break = true; break; }
       // advect_all_scalars.F90:32-64
-      LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, p.t, (double *)nullptr, (double *)nullptr, 0);
-      LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, p.qt, p.mkadv1, p.mkwle1, 1);
-      LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, p.qp, p.mkadv2, p.mkwle2, 1);
+      LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, p.t, (double *)nullptr, (double *)nullptr, 0, (const int *)nullptr);
+      LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, p.qt, p.mkadv1, p.mkwle1, 1, (const int *)nullptr);
+      LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, p.qp, p.mkadv2, p.mkwle2, 1, (const int *)p.kqp);
       if (dbg_stop == 5) { dbg_break = true; break; }
       dev_zero(p.prec_cfl_bits, 8);
       LAUNCH_G(h, k_precip_a, ntiles, P, CRM_PRECIPA_SMEM(P, CT, h->nzp), p);
@@ -471,7 +471,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
       if (dbg_stop == 7) { dbg_break = true; break; }
       if (icyc == 1) LAUNCH(h, k_precip_init, (ntiles * nzm * CT + 127) / 128, 128, 0, p);
       LAUNCH(h, k_reset_kminmax, slot_blocks, 128, 0, p);
-      const size_t smem_p8 = red_bytes(9) + 2 * CT * sizeof(int);
+      const size_t smem_p8 = red_bytes(9) + (2 * CT + 2) * sizeof(int);
       if (d->use_crm_accel && !ceaseflag) {
         LAUNCH_G(h, k_p8_micro, ntiles * nzm, P, smem_p8, p, 1, 0);
         LAUNCH(h, k_msa_a, ntiles * nzm, P, red_bytes(3), p);

@@ -97,6 +97,7 @@ struct CrmP {
   double *dz, *z0, *colprec0, *colprecs0, *s_cltot, *s_clhgh, *s_clmed, *s_cllow;
   int *kmin, *kmax, *ndamp;
   int *kprec;                            // per tile: highest level holding precipitation (k_precip_a)
+  int *kqp;                              // per tile: highest level with qp != 0 after micro_proc (k_p8_micro); nzm at call start
   // ---- per-column 2-D (tile, tid) ----
   double *precsfc, *precssfc;
   // ---- batch-global scalars on device ----

@@ -29,11 +29,25 @@ __device__ __forceinline__ double min3(double a, double b, double c) { return dm
 #define CRM_MP_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(3, 6, P) + CRM_PROF_BYTES(5, nzp, CT) + (size_t)(9 * (P) + CRM_RED_DOUBLES(2, P, CT)) * 8)
 __device__ __forceinline__ double upw_flux(double v, double below, double above) { return v * (v > 0. ? below : above); }
 template <int NXT>
-__global__ void __launch_bounds__(CRM_MAX_P, 3) k_mpdata(CrmP p, double *f, double *fadv, double *flux, int stats) {
+__global__ void __launch_bounds__(CRM_MAX_P, 3) k_mpdata(CrmP p, double *f, double *fadv, double *flux, int stats, const int *ktop) {
   CRM_TILE_SETUP_T(NXT)
   CRM_XNEIGH
   CRM_DYN_SMEM(unsigned char, smraw);
-  const int nzm = p.nzm, nz = p.nz;
+  // ktop (optional): highest level of the tile with f != 0.  The scheme reaches three levels up (F1(k) needs f(k+-1), the
+  // antidiffusive fluxes and FCT ratios of level k need F1(k+-1), (k+-2)), so with f == 0 above ktop every level above
+  // ktop+2 keeps f = 0 with zero fluxes: the march treats ktop+3 as the top level (all boundary terms act on zeros).
+  const int kt_ = ktop ? ktop[tile] : p.nzm;
+  const int nzm = imin(p.nzm, kt_ + 3), nz = nzm + 1;
+  if (stats && nzm < p.nzm) {
+    for (int q = tid; q < (p.nzm - nzm) * CT; q += P) {
+      const int o = tile * p.nzp * CT + (nzm + 1) * CT + q;
+      fadv[o] = 0.; flux[o] = 0.;
+    }
+  }
+  if (kt_ == 0) {   // f == 0 in the whole tile
+    if (stats) for (int q = tid; q < nzm * CT; q += P) { const int o = tile * p.nzp * CT + CT + q; fadv[o] = 0.; flux[o] = 0.; }
+    return;
+  }
   PlanePipe<3, 6> R;
   R.src[0] = f + fb; R.src[1] = p.umf + fb; R.src[2] = p.wmf + fb;
   double *sprof = (double *)(smraw + CRM_PIPE_BYTES(3, 6, P));
@@ -319,7 +333,8 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_precip_a(CrmP p) {
   CRM_TILE_SETUP_T(NXT)
   CRM_DYN_SMEM(unsigned char, smraw);
   __shared__ int s_kt;
-  const int nzm = p.nzm, npf = p.nzp * CT;
+  const int npf = p.nzp * CT;
+  const int nzm = imin(p.nzm, p.kqp[tile] + 3);   // qp == 0 above kqp+2 after advection (k_mpdata): wp there is never read
   PlanePipe<2, 3> R;
   R.src[0] = p.qp + fb; R.src[1] = p.tabs + fb;
   double *sprof = (double *)(smraw + CRM_PIPE_BYTES(2, 3, P));
@@ -330,6 +345,10 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_precip_a(CrmP p) {
   }
   if (tid == 0) s_kt = 0;
   R.init(smraw, P, tid);
+  if (p.kqp[tile] == 0) {   // no precipitation in the tile before advection: none now
+    if (tid == 0) p.kprec[tile] = 0;
+    return;
+  }
   CRM_PIPE_PROLOGUE(R, nzm, 2, 0)
   const double dz = p.dz[cb];
   const double idtn = 1. / p.dtn;
@@ -741,7 +760,7 @@ __device__ inline void precip_proc_cell(const CrmP &p, int pb, int CT, int k, do
 // (tabs, slab means) + the kmin/kmax scan of ice_fall.F90:34-47 for the NEXT sub-step.
 // Plane kernel: one block per (tile, level).  smem: CRM_RED_DOUBLES(9,P,CT) + 2*CT ints
 template <int NXT>
-__global__ void __launch_bounds__(CRM_MAX_P) k_p8_micro(CrmP p, int do_micro, int do_diag) {
+__global__ void __launch_bounds__(CRM_MAX_P, 5) k_p8_micro(CrmP p, int do_micro, int do_diag) {
   const int tid = threadIdx.x;
   const int CT = (NXT) > 0 ? crm_static_ct(NXT) : p.CT, P = (NXT) > 0 ? (NXT) * crm_static_ct(NXT) : p.P;
   const int tile = blockIdx.x / p.nzm, k = blockIdx.x - tile * p.nzm + 1;
@@ -768,8 +787,9 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p8_micro(CrmP p, int do_micro, in
     F3(p.qv, k) = qv; F3(p.qcl, k) = qcl; F3(p.qci, k) = qci; F3(p.qpl, k) = qpl; F3(p.qpi, k) = qpi;
     if (!do_diag) F3(p.tabs, k) = tabs;
   }
-  if (tid < 2 * CT) sflag[tid] = 0;
+  if (tid < 2 * CT + 1) sflag[tid] = 0;
   __syncthreads();
+  if (do_micro && qp != 0.) sflag[2 * CT] = 1;
   if (do_diag) {
     tabs = t - PF(p.gamaz, k) + CRM_FAC_COND * (qcl + qpl) + CRM_FAC_SUB * (qci + qpi);
     F3(p.tabs, k) = tabs;
@@ -802,11 +822,13 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p8_micro(CrmP p, int do_micro, in
     }
   });
   if (do_diag && i == 0 && sflag[lane]) { atomicMin(&p.kmin[cb], k); atomicMax(&p.kmax[cb], k); }
+  if (do_micro && tid == 0 && sflag[2 * CT]) atomicMax(&p.kqp[tile], k);
 }
 
 __global__ void k_reset_kminmax(CrmP p) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot < p.ntiles * p.CT) { p.kmin[slot] = p.nzm + 1; p.kmax[slot] = 0; }
+  if (slot < p.ntiles) p.kqp[slot] = 0;
 }
 
 // accelerate_crm.F90:166-225: horizontal means, MSA tendencies, batch-global ceaseflag.  Plane kernel.

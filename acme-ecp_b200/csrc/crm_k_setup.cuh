@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_prologue_fields(CrmP p) {
   const double idt_gl = 1. / p.dt_gl;
   double colprec = 0., colprecs = 0.;
   int kmin = nzm + 1, kmax = 0;
+  if (tid == 0) p.kqp[tile] = nzm;   // no level skipping in the first sub-step of a call
   for (int k = 1; k <= nzm; k++) {
     double u = F3(p.u, k);
     if (clamp) { u = dmin(umax, dmax(-umax, u)); F3(p.u, k) = u; }
