@@ -471,7 +471,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
       if (dbg_stop == 7) { dbg_break = true; break; }
       if (icyc == 1) LAUNCH(h, k_precip_init, (ntiles * nzm * CT + 127) / 128, 128, 0, p);
       LAUNCH(h, k_reset_kminmax, slot_blocks, 128, 0, p);
-      const size_t smem_p8 = red_bytes(9) + (2 * CT + 2) * sizeof(int);
+      const size_t smem_p8 = CRM_P8_SMEM(P, CT);
       if (d->use_crm_accel && !ceaseflag) {
         LAUNCH_G(h, k_p8_micro, ntiles * nzm, P, smem_p8, p, 1, 0);
         LAUNCH(h, k_msa_a, ntiles * nzm, P, red_bytes(3), p);

@@ -170,25 +170,38 @@ CRM_CONST double c_dtesati[9] = {R4(0.503223089), R4(0.377174432e-1), R4(0.12671
 __device__ __forceinline__ double poly8(const double *a, double dt) {
   return a[0] + dt * (a[1] + dt * (a[2] + dt * (a[3] + dt * (a[4] + dt * (a[5] + dt * (a[6] + dt * (a[7] + a[8] * dt)))))));
 }
-__device__ inline double esatw_crm(double t) {   // sat.F90:12-32
+// The T <= 193.16 K branches (Goff-Gratch over ice, never taken in the troposphere) are out of line: inlined at the ~20
+// call sites they made up most of the SASS of k_p8_micro / k_p2_sgs (profiles/r01f: 14 % of the stalls of k_p8_micro were
+// instruction-cache misses).
+#ifdef CRM_EMU
+#define CRM_COLD
+#else
+#define CRM_COLD __noinline__
+#endif
+__device__ CRM_COLD double esat_cold(double t, double scale) {
+  return scale * exp(R4(9.550426) - R4(5723.265) / t + R4(3.53068) * log(t) - R4(0.00728332) * t);
+}
+__device__ __forceinline__ double esatw_crm(double t) {   // sat.F90:12-32
   double dt = t - R4(273.16);
   if (dt > R4(-80.)) return poly8(c_esatw, dt);
-  return (double)(2.0f * 0.01f) * exp(R4(9.550426) - R4(5723.265) / t + R4(3.53068) * log(t) - R4(0.00728332) * t);
+  return esat_cold(t, (double)(2.0f * 0.01f));
 }
-__device__ inline double esati_crm(double t) {   // sat.F90:77-94
+__device__ __forceinline__ double esati_crm(double t) {   // sat.F90:77-94
   double dt = t - R4(273.16);
   if (dt > R4(-80.)) return poly8(c_esati, dt);
-  return R4(0.01) * exp(R4(9.550426) - R4(5723.265) / t + R4(3.53068) * log(t) - R4(0.00728332) * t);
+  return esat_cold(t, R4(0.01));
 }
-__device__ inline double dtesatw_crm(double t) {   // sat.F90:46-65
+__device__ CRM_COLD double dtesatw_cold(double t) { return esatw_crm(t + 1) - esatw_crm(t); }
+__device__ CRM_COLD double dtesati_cold(double t) { return esati_crm(t + R4(1.)) - esati_crm(t); }
+__device__ __forceinline__ double dtesatw_crm(double t) {   // sat.F90:46-65
   double dt = t - R4(273.16);
   if (dt > R4(-80.)) return poly8(c_dtesatw, dt);
-  return esatw_crm(t + 1) - esatw_crm(t);
+  return dtesatw_cold(t);
 }
-__device__ inline double dtesati_crm(double t) {   // sat.F90:108-127
+__device__ __forceinline__ double dtesati_crm(double t) {   // sat.F90:108-127
   double dt = t - R4(273.16);
   if (dt > R4(-80.)) return poly8(c_dtesati, dt);
-  return esati_crm(t + R4(1.)) - esati_crm(t);
+  return dtesati_cold(t);
 }
 __device__ __forceinline__ double qsatw_crm(double t, double p) { double es = esatw_crm(t); return R4(0.622) * es / dmax(es, p - es); }
 __device__ __forceinline__ double qsati_crm(double t, double p) { double es = esati_crm(t); return R4(0.622) * es / dmax(es, p - es); }
@@ -266,6 +279,31 @@ __device__ __forceinline__ void red_get(int tid, int P, int CT, const double *re
     double s = red[q * CT + ln];
     for (int g = 1; g < nw; g++) s += red[(g * NQ + q) * CT + ln];
     f(q, ln, s);
+  }
+}
+// Transposed slab sums for many quantities: every thread stores its NQ values (tr[q*P + tid], conflict-free), after a
+// barrier warp w owns quantities q = w, w + nw, ...: each of its threads adds the P/32 values tr[q*P + sub + 32*j]
+// (all of the CRM lane sub % CT), xor-shuffles combine the 32/CT threads of a lane, and f(q, lane, sum) runs in the
+// threads sub < CT.  ~(NQ + P/32 + 3*log2(32/CT)) instructions per thread instead of NQ shuffle trees; fixed order.
+// tr: NQ*P doubles.  tr_get must be called by all threads (whole warps) after the barrier that follows tr_put.
+template <int NQ>
+__device__ __forceinline__ void tr_put(const double (&v)[NQ], int tid, int P, double *tr) {
+#pragma unroll
+  for (int q = 0; q < NQ; q++) tr[q * P + tid] = v[q];
+}
+__device__ __forceinline__ double tr_sum(int q, int tid, int P, int CT, const double *tr) {
+  const int sub = tid & 31, nw = P >> 5;
+  double s = tr[q * P + sub];
+  for (int j = 1; j < nw; j++) s += tr[q * P + sub + 32 * j];
+  for (int off = CT; off < 32; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  return s;
+}
+template <int NQ, class F>
+__device__ __forceinline__ void tr_get(int tid, int P, int CT, const double *tr, F f) {
+  const int sub = tid & 31, nw = P >> 5;
+  for (int q = tid >> 5; q < NQ; q += nw) {
+    const double s = tr_sum(q, tid, P, CT, tr);
+    if (sub < CT) f(q, sub, s);
   }
 }
 template <int NQ>

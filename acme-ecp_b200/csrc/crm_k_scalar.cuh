@@ -26,7 +26,7 @@ __device__ __forceinline__ double min3(double a, double b, double c) { return dm
 // F1 / mx-mn slot is a compile-time shared-memory offset, the own-column and previous-level operands are carried in
 // registers instead of being re-read, and max(0,v)*a + min(0,v)*b is evaluated as v * (v > 0 ? a : b).  The general
 // body below it handles the first two and the last levels.
-#define CRM_MP_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(3, 6, P) + CRM_PROF_BYTES(5, nzp, CT) + (size_t)(9 * (P) + CRM_RED_DOUBLES(2, P, CT)) * 8)
+#define CRM_MP_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(3, 6, P) + CRM_PROF_BYTES(5, nzp, CT) + (size_t)(9 * (P) + 2 * CRM_RED_DOUBLES(2, P, CT)) * 8)
 __device__ __forceinline__ double upw_flux(double v, double below, double above) { return v * (v > 0. ? below : above); }
 template <int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P, 3) k_mpdata(CrmP p, double *f, double *fadv, double *flux, int stats, const int *ktop) {
@@ -75,6 +75,16 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_mpdata(CrmP p, double *f, doub
   double mx_prev = 0., mn_prev = 0.;   // normalised mx/mn at level ka-2 (own column)
   double upw_m1 = 0., upw_m2 = 0.;     // upwind www at levels ka-1, ka-2 (stats only)
 
+  // deferred slab sums of the statistics (fadv, flux): warp partials are written when a level is finalised and summed
+  // after the first barrier of the next iteration (no extra barriers)
+  const int RS = CRM_RED_DOUBLES(2, P, CT);
+  auto book_stats = [&](const int lev) {
+    if (lev < 1) return;
+    red_get<2>(tid, P, CT, red + (lev & 1) * RS, [&](int q, int ln, double sum) {
+      const int o = tile * p.nzp * CT + lev * CT + ln;
+      if (q == 0) fadv[o] = sum; else flux[o] = sum;
+    });
+  };
   // ------------------------------------------------------------------ general body (any ka)
   auto edge_step = [&](const int ka) {
     if (ka + 1 <= nz) R.wait(ka + 1);
@@ -102,6 +112,7 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_mpdata(CrmP p, double *f, doub
     }
     __syncthreads();   // (1)  (also: every thread has read level ka-2 of the ring, its slot can be refilled)
     if (tid == 0 && ka + 4 <= nz) R.issue(ka + 4);
+    if (stats && ka - 3 >= 1) book_stats(ka - 3);   // slab sums of the level finalised in the previous iteration
     // ------------------------------- stage B
     double WW_ka = 0.;
     if (ka >= 2 && ka <= nzm) {   // WW(1) = 0 (advect_scalar2D.F90:165-169), WW(nz) = 0
@@ -174,8 +185,7 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_mpdata(CrmP p, double *f, doub
       F3(f, kc_) = fnew;
       if (stats) {
         double v[2] = {fnew - f0mm, upw_m2 + WWlim_k};
-        block_sum_lead<2>(v, tid, P, CT, red);
-        if (i == 0) { PF(fadv, kc_) = v[0]; PF(flux, kc_) = v[1]; }
+        red_put<2>(v, tid, CT, red + (kc_ & 1) * RS);   // booked after the next barrier (book_stats)
       }
     }
     // ------------------------------- shift windows
@@ -222,6 +232,7 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_mpdata(CrmP p, double *f, doub
     const double upw = c_www;
     __syncthreads();   // (1)
     if (tid == 0 && ka + 4 <= nz) R.issue(ka + 4);
+    if (stats) book_stats(ka - 3);   // ka >= 4 here, or ka = 3: level 0 does not exist
     // ---- stage B
     const double Fa_p = sF1[A_A * P + tp1], Fa_m = sF1[A_A * P + tm1];
     const double WW_ka = andiff(c_F1b, F1a, c_Wk, pr[2 * CT]) -
@@ -254,8 +265,7 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_mpdata(CrmP p, double *f, doub
     F3(f, ka - 2) = fnew;
     if (stats) {
       double v[2] = {fnew - c_f0, upw_m2 + WWlim_k};
-      block_sum_lead<2>(v, tid, P, CT, red);
-      if (i == 0) { PF(fadv, ka - 2) = v[0]; PF(flux, ka - 2) = v[1]; }
+      red_put<2>(v, tid, CT, red + ((ka - 2) & 1) * RS);
     }
     // ---- shift
     WWlim_k = WWlim_kp1; UU_prev = UU; WW_prev = WW_ka; mx_prev = mx_new; mn_prev = mn_new;
@@ -291,6 +301,7 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_mpdata(CrmP p, double *f, doub
     }
   }
   for (; ka <= nzm + 2; ka++) edge_step(ka);
+  if (stats) { __syncthreads(); book_stats(nzm); }
 #undef S_PR
 #undef S_IRHO
 #undef S_IADZ
@@ -617,7 +628,14 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p7_diffuse(CrmP p) {
 #undef SPF
 }
 
-// cloud.F90:29-112 for one cell; returns tabs1, updates q, qp, qn
+// cloud.F90:29-112 for one cell; returns tabs1, updates q, qp, qn.
+// The three temperature regimes of the reference (liquid / ice / mixed) are folded into one expression with the
+// mixing weight om forced to exactly 1 or 0 outside the mixed range: om*qsatw + (1-om)*qsati is then bit-identical to
+// the single-phase value (x*1 + y*0), the two Flatau polynomials are independent Horner chains that overlap in the
+// FP64 pipe, and the warp no longer diverges three ways per Newton iteration.
+__device__ __forceinline__ double cloud_qsat_mix(double tabs1, double pres, double om) {
+  return om * qsatw_crm(tabs1, pres) + (1. - om) * qsati_crm(tabs1, pres);
+}
 __device__ inline void cloud_cell(double t, double gamaz, double pres, double &q, double &qp, double &qn, double &tabs_out) {
   const double an = 1. / (CRM_TBGMAX - CRM_TBGMIN), bn = CRM_TBGMIN * an;
   const double ap = 1. / (CRM_TPRMAX - CRM_TPRMIN), bp = CRM_TPRMIN * ap;
@@ -625,40 +643,24 @@ __device__ inline void cloud_cell(double t, double gamaz, double pres, double &q
   q = dmax(0., q);
   const double tabs = t - gamaz;
   double tabs1 = (tabs + fac1 * qp) / (1. + fac2 * qp);
-  double qsatt, dqsat = 0., dtabs = 0.;
-  if (tabs1 >= CRM_TBGMAX) {
-    tabs1 = tabs + CRM_FAC_COND * qp;
-    qsatt = qsatw_crm(tabs1, pres);
-  } else if (tabs1 <= CRM_TBGMIN) {
-    tabs1 = tabs + CRM_FAC_SUB * qp;
-    qsatt = qsati_crm(tabs1, pres);
-  } else {
-    const double om = an * tabs1 - bn;
-    qsatt = om * qsatw_crm(tabs1, pres) + (1. - om) * qsati_crm(tabs1, pres);
-  }
+  double om;
+  if (tabs1 >= CRM_TBGMAX) { tabs1 = tabs + CRM_FAC_COND * qp; om = 1.; }
+  else if (tabs1 <= CRM_TBGMIN) { tabs1 = tabs + CRM_FAC_SUB * qp; om = 0.; }
+  else om = an * tabs1 - bn;
+  double qsatt = cloud_qsat_mix(tabs1, pres, om);
   if (q > qsatt) {
     int niter = 0;
-    dtabs = R4(100.);
+    double dtabs = R4(100.), dqsat = 0.;
     while (fabs(dtabs) > R4(0.01) && niter < 10) {
-      double lstarn, dlstarn, lstarp, dlstarp;
-      if (tabs1 >= CRM_TBGMAX) {
-        lstarn = CRM_FAC_COND; dlstarn = 0.;
-        qsatt = qsatw_crm(tabs1, pres);
-        dqsat = dtqsatw_crm(tabs1, pres);
-      } else if (tabs1 <= CRM_TBGMIN) {
-        lstarn = CRM_FAC_SUB; dlstarn = 0.;
-        qsatt = qsati_crm(tabs1, pres);
-        dqsat = dtqsati_crm(tabs1, pres);
-      } else {
-        const double om = an * tabs1 - bn;
-        lstarn = CRM_FAC_COND + (1. - om) * CRM_FAC_FUS;
-        dlstarn = an * CRM_FAC_FUS;
-        qsatt = om * qsatw_crm(tabs1, pres) + (1. - om) * qsati_crm(tabs1, pres);
-        dqsat = om * dtqsatw_crm(tabs1, pres) + (1. - om) * dtqsati_crm(tabs1, pres);
-      }
-      if (tabs1 >= CRM_TPRMAX) { lstarp = CRM_FAC_COND; dlstarp = 0.; }
-      else if (tabs1 <= CRM_TPRMIN) { lstarp = CRM_FAC_SUB; dlstarp = 0.; }
-      else { const double omp = ap * tabs1 - bp; lstarp = CRM_FAC_COND + (1. - omp) * CRM_FAC_FUS; dlstarp = ap * CRM_FAC_FUS; }
+      const bool liq = tabs1 >= CRM_TBGMAX, ice = tabs1 <= CRM_TBGMIN;
+      const double omn = liq ? 1. : (ice ? 0. : an * tabs1 - bn);
+      const double lstarn = liq ? CRM_FAC_COND : (ice ? CRM_FAC_SUB : CRM_FAC_COND + (1. - omn) * CRM_FAC_FUS);
+      const double dlstarn = (liq || ice) ? 0. : an * CRM_FAC_FUS;
+      qsatt = cloud_qsat_mix(tabs1, pres, omn);
+      dqsat = omn * dtqsatw_crm(tabs1, pres) + (1. - omn) * dtqsati_crm(tabs1, pres);
+      const bool pliq = tabs1 >= CRM_TPRMAX, pice = tabs1 <= CRM_TPRMIN;
+      const double lstarp = pliq ? CRM_FAC_COND : (pice ? CRM_FAC_SUB : CRM_FAC_COND + (1. - (ap * tabs1 - bp)) * CRM_FAC_FUS);
+      const double dlstarp = (pliq || pice) ? 0. : ap * CRM_FAC_FUS;
       const double fff = tabs - tabs1 + lstarn * (q - qsatt) + lstarp * qp;
       const double dfff = dlstarn * (q - qsatt) + dlstarp * qp - lstarn * dqsat - 1.;
       dtabs = -fff / dfff;
@@ -758,7 +760,8 @@ __device__ inline void precip_proc_cell(const CrmP &p, int pb, int CT, int k, do
 
 // micro_proc (microphysics.F90:292-329: cloud, precip_proc, micro_diagnose) and, when do_diag, diagnose.F90:37-104
 // (tabs, slab means) + the kmin/kmax scan of ice_fall.F90:34-47 for the NEXT sub-step.
-// Plane kernel: one block per (tile, level).  smem: CRM_RED_DOUBLES(9,P,CT) + 2*CT ints
+// Plane kernel: one block per (tile, level).  smem: CRM_P8_SMEM (transposed slab sums of 8 quantities + flags)
+#define CRM_P8_SMEM(P, CT) ((size_t)8 * (P) * 8 + (2 * (CT) + 2) * sizeof(int))
 template <int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P, 5) k_p8_micro(CrmP p, int do_micro, int do_diag) {
   const int tid = threadIdx.x;
@@ -769,7 +772,7 @@ __global__ void __launch_bounds__(CRM_MAX_P, 5) k_p8_micro(CrmP p, int do_micro,
   const int pb = tile * p.nzp * CT + lane;
   const int cb = tile * CT + lane;
   CRM_DYN_SMEM(double, red);
-  int *sflag = (int *)(red + CRM_RED_DOUBLES(8, P, CT));
+  int *sflag = (int *)(red + 8 * P);
   double t = F3(p.t, k), q = F3(p.qt, k), qp = F3(p.qp, k);
   // with do_micro every one of these is recomputed before use (cloud -> qn, tabs; micro_diagnose -> qv..qpi): skip the loads
   double qn = 0., tabs = 0., qv = 0., qcl = 0., qci = 0., qpl = 0., qpi = 0.;
@@ -800,7 +803,9 @@ __global__ void __launch_bounds__(CRM_MAX_P, 5) k_p8_micro(CrmP p, int do_micro,
     if (qcl + qci > 0. && tabs < R4(273.15)) sflag[lane] = 1;   // (the reset above is ordered by the barrier that follows it)
   }
   const int last = p.last_substep;
-  block_sum_each<8>(v, tid, P, CT, red, [&](int q, int ln, double sum) {
+  tr_put<8>(v, tid, P, red);
+  __syncthreads();
+  tr_get<8>(tid, P, CT, red, [&](int q, int ln, double sum) {
     const int o = tile * p.nzp * CT + k * CT + ln;
     if (q < 6) {
       if (do_diag) {
@@ -810,17 +815,18 @@ __global__ void __launch_bounds__(CRM_MAX_P, 5) k_p8_micro(CrmP p, int do_micro,
         else if (q == 1) p.t0[o] = m;
         else if (q == 2) p.tabs0[o] = m;
         else if (q == 3) p.q0[o] = m;
-        else if (q == 4) {   // qn0 and qv0 = q0 - qn0: re-sum quantity 3 in the same fixed order
-          const int nw = P >> 5;
-          double s3 = red[3 * CT + ln];
-          for (int g = 1; g < nw; g++) s3 += red[(g * 8 + 3) * CT + ln];
-          p.qn0[o] = m; p.qv0[o] = s3 * coef - m;
-        } else p.qp0[o] = m;
+        else if (q == 4) p.qn0[o] = m;
+        else p.qp0[o] = m;
       }
     } else if (do_micro && last) {
       if (q == 6) p.qpsrc[o] = sum; else p.qpevp[o] = sum;
     }
   });
+  if (do_diag && (tid >> 5) == (4 % (P >> 5))) {   // qv0 = q0 - qn0 from the same two sums (diagnose.F90:93), by the warp that owns quantity 4
+    const double s3 = tr_sum(3, tid, P, CT, red), s4 = tr_sum(4, tid, P, CT, red);
+    const double coef = (double)1.f / (double)(p.nx * p.ny);
+    if ((tid & 31) < CT) p.qv0[tile * p.nzp * CT + k * CT + (tid & 31)] = s3 * coef - s4 * coef;
+  }
   if (do_diag && i == 0 && sflag[lane]) { atomicMin(&p.kmin[cb], k); atomicMax(&p.kmax[cb], k); }
   if (do_micro && tid == 0 && sflag[2 * CT]) atomicMax(&p.kqp[tile], k);
 }
