@@ -473,7 +473,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
       LAUNCH(h, k_reset_kminmax, slot_blocks, 128, 0, p);
       const size_t smem_p8 = CRM_P8_SMEM(P, CT);
       if (d->use_crm_accel && !ceaseflag) {
-        LAUNCH_G(h, k_p8_micro, ntiles * nzm, P, smem_p8, p, 1, 0);
+        LAUNCH_G(h, k_p8_micro, ntiles * ((nzm + CRM_P8_NL - 1) / CRM_P8_NL), P, smem_p8, p, 1, 0);
         LAUNCH(h, k_msa_a, ntiles * nzm, P, red_bytes(3), p);
         int flags[4];
         if (dev_copy2d(flags, 16, p.flags, 16, 16, 1, 0)) return fail(h, 30, "crm_b200_run: MSA flag readback failed");
@@ -483,9 +483,9 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
         } else {
           LAUNCH(h, k_msa_b, ntiles * nzm, P, red_bytes(2), p);
         }
-        LAUNCH_G(h, k_p8_micro, ntiles * nzm, P, smem_p8, p, 0, 1);
+        LAUNCH_G(h, k_p8_micro, ntiles * ((nzm + CRM_P8_NL - 1) / CRM_P8_NL), P, smem_p8, p, 0, 1);
       } else {
-        LAUNCH_G(h, k_p8_micro, ntiles * nzm, P, smem_p8, p, 1, 1);
+        LAUNCH_G(h, k_p8_micro, ntiles * ((nzm + CRM_P8_NL - 1) / CRM_P8_NL), P, smem_p8, p, 1, 1);
       }
       { int nn = na; na = nc; nc = nb; nb = nn; }
       if (dbg_stop == 8) { dbg_break = true; break; }

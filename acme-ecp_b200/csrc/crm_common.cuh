@@ -285,24 +285,24 @@ __device__ __forceinline__ void red_get(int tid, int P, int CT, const double *re
 // barrier warp w owns quantities q = w, w + nw, ...: each of its threads adds the P/32 values tr[q*P + sub + 32*j]
 // (all of the CRM lane sub % CT), xor-shuffles combine the 32/CT threads of a lane, and f(q, lane, sum) runs in the
 // threads sub < CT.  ~(NQ + P/32 + 3*log2(32/CT)) instructions per thread instead of NQ shuffle trees; fixed order.
-// tr: NQ*P doubles.  tr_get must be called by all threads (whole warps) after the barrier that follows tr_put.
+// tr: NQ planes of QS doubles.  tr_get must be called by all threads (whole warps) after the barrier that follows tr_put.
 template <int NQ>
-__device__ __forceinline__ void tr_put(const double (&v)[NQ], int tid, int P, double *tr) {
+__device__ __forceinline__ void tr_put(const double (&v)[NQ], int tid, int QS, double *tr) {   // QS: stride between quantities (>= P)
 #pragma unroll
-  for (int q = 0; q < NQ; q++) tr[q * P + tid] = v[q];
+  for (int q = 0; q < NQ; q++) tr[q * QS + tid] = v[q];
 }
-__device__ __forceinline__ double tr_sum(int q, int tid, int P, int CT, const double *tr) {
+__device__ __forceinline__ double tr_sum(int q, int tid, int P, int CT, int QS, const double *tr) {
   const int sub = tid & 31, nw = P >> 5;
-  double s = tr[q * P + sub];
-  for (int j = 1; j < nw; j++) s += tr[q * P + sub + 32 * j];
+  double s = tr[q * QS + sub];
+  for (int j = 1; j < nw; j++) s += tr[q * QS + sub + 32 * j];
   for (int off = CT; off < 32; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
   return s;
 }
 template <int NQ, class F>
-__device__ __forceinline__ void tr_get(int tid, int P, int CT, const double *tr, F f) {
+__device__ __forceinline__ void tr_get(int tid, int P, int CT, int QS, const double *tr, F f) {
   const int sub = tid & 31, nw = P >> 5;
   for (int q = tid >> 5; q < NQ; q += nw) {
-    const double s = tr_sum(q, tid, P, CT, tr);
+    const double s = tr_sum(q, tid, P, CT, QS, tr);
     if (sub < CT) f(q, sub, s);
   }
 }

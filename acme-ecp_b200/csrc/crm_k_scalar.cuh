@@ -636,44 +636,45 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p7_diffuse(CrmP p) {
 __device__ __forceinline__ double cloud_qsat_mix(double tabs1, double pres, double om) {
   return om * qsatw_crm(tabs1, pres) + (1. - om) * qsati_crm(tabs1, pres);
 }
-__device__ inline void cloud_cell(double t, double gamaz, double pres, double &q, double &qp, double &qn, double &tabs_out) {
+// cloud_init: everything before the saturation test (cloud.F90:40-70); cloud_newton: the iteration for a saturated cell
+// (cloud.F90:75-105).  k_p8_micro runs the first on every cell and the second only on the compacted saturated cells.
+__device__ __forceinline__ void cloud_init(double t, double gamaz, double pres, double &q, double qp, double &tabs, double &tabs1, double &qsatt) {
   const double an = 1. / (CRM_TBGMAX - CRM_TBGMIN), bn = CRM_TBGMIN * an;
   const double ap = 1. / (CRM_TPRMAX - CRM_TPRMIN), bp = CRM_TPRMIN * ap;
   const double fac1 = CRM_FAC_COND + (1 + bp) * CRM_FAC_FUS, fac2 = CRM_FAC_FUS * ap;
   q = dmax(0., q);
-  const double tabs = t - gamaz;
-  double tabs1 = (tabs + fac1 * qp) / (1. + fac2 * qp);
+  tabs = t - gamaz;
+  tabs1 = (tabs + fac1 * qp) / (1. + fac2 * qp);
   double om;
   if (tabs1 >= CRM_TBGMAX) { tabs1 = tabs + CRM_FAC_COND * qp; om = 1.; }
   else if (tabs1 <= CRM_TBGMIN) { tabs1 = tabs + CRM_FAC_SUB * qp; om = 0.; }
   else om = an * tabs1 - bn;
-  double qsatt = cloud_qsat_mix(tabs1, pres, om);
-  if (q > qsatt) {
-    int niter = 0;
-    double dtabs = R4(100.), dqsat = 0.;
-    while (fabs(dtabs) > R4(0.01) && niter < 10) {
-      const bool liq = tabs1 >= CRM_TBGMAX, ice = tabs1 <= CRM_TBGMIN;
-      const double omn = liq ? 1. : (ice ? 0. : an * tabs1 - bn);
-      const double lstarn = liq ? CRM_FAC_COND : (ice ? CRM_FAC_SUB : CRM_FAC_COND + (1. - omn) * CRM_FAC_FUS);
-      const double dlstarn = (liq || ice) ? 0. : an * CRM_FAC_FUS;
-      qsatt = cloud_qsat_mix(tabs1, pres, omn);
-      dqsat = omn * dtqsatw_crm(tabs1, pres) + (1. - omn) * dtqsati_crm(tabs1, pres);
-      const bool pliq = tabs1 >= CRM_TPRMAX, pice = tabs1 <= CRM_TPRMIN;
-      const double lstarp = pliq ? CRM_FAC_COND : (pice ? CRM_FAC_SUB : CRM_FAC_COND + (1. - (ap * tabs1 - bp)) * CRM_FAC_FUS);
-      const double dlstarp = (pliq || pice) ? 0. : ap * CRM_FAC_FUS;
-      const double fff = tabs - tabs1 + lstarn * (q - qsatt) + lstarp * qp;
-      const double dfff = dlstarn * (q - qsatt) + dlstarp * qp - lstarn * dqsat - 1.;
-      dtabs = -fff / dfff;
-      niter = niter + 1;
-      tabs1 = tabs1 + dtabs;
-    }
-    qsatt = qsatt + dqsat * dtabs;
-    qn = dmax(0., q - qsatt);
-  } else {
-    qn = 0.;
+  qsatt = cloud_qsat_mix(tabs1, pres, om);
+}
+// requires q > qsatt on entry; returns qn, updates tabs1
+__device__ __forceinline__ double cloud_newton(double tabs, double pres, double q, double qp, double &tabs1, double qsatt) {
+  const double an = 1. / (CRM_TBGMAX - CRM_TBGMIN), bn = CRM_TBGMIN * an;
+  const double ap = 1. / (CRM_TPRMAX - CRM_TPRMIN), bp = CRM_TPRMIN * ap;
+  int niter = 0;
+  double dtabs = R4(100.), dqsat = 0.;
+  while (fabs(dtabs) > R4(0.01) && niter < 10) {
+    const bool liq = tabs1 >= CRM_TBGMAX, ice = tabs1 <= CRM_TBGMIN;
+    const double omn = liq ? 1. : (ice ? 0. : an * tabs1 - bn);
+    const double lstarn = liq ? CRM_FAC_COND : (ice ? CRM_FAC_SUB : CRM_FAC_COND + (1. - omn) * CRM_FAC_FUS);
+    const double dlstarn = (liq || ice) ? 0. : an * CRM_FAC_FUS;
+    qsatt = cloud_qsat_mix(tabs1, pres, omn);
+    dqsat = omn * dtqsatw_crm(tabs1, pres) + (1. - omn) * dtqsati_crm(tabs1, pres);
+    const bool pliq = tabs1 >= CRM_TPRMAX, pice = tabs1 <= CRM_TPRMIN;
+    const double lstarp = pliq ? CRM_FAC_COND : (pice ? CRM_FAC_SUB : CRM_FAC_COND + (1. - (ap * tabs1 - bp)) * CRM_FAC_FUS);
+    const double dlstarp = (pliq || pice) ? 0. : ap * CRM_FAC_FUS;
+    const double fff = tabs - tabs1 + lstarn * (q - qsatt) + lstarp * qp;
+    const double dfff = dlstarn * (q - qsatt) + dlstarp * qp - lstarn * dqsat - 1.;
+    dtabs = -fff / dfff;
+    niter = niter + 1;
+    tabs1 = tabs1 + dtabs;
   }
-  tabs_out = tabs1;
-  qp = dmax(0., qp);
+  qsatt = qsatt + dqsat * dtabs;
+  return dmax(0., q - qsatt);
 }
 
 // precip_proc.F90:47-148 for one cell.  dsrc/devp: this cell's contribution to qpsrc/qpevp.
@@ -760,75 +761,164 @@ __device__ inline void precip_proc_cell(const CrmP &p, int pb, int CT, int k, do
 
 // micro_proc (microphysics.F90:292-329: cloud, precip_proc, micro_diagnose) and, when do_diag, diagnose.F90:37-104
 // (tabs, slab means) + the kmin/kmax scan of ice_fall.F90:34-47 for the NEXT sub-step.
-// Plane kernel: one block per (tile, level).  smem: CRM_P8_SMEM (transposed slab sums of 8 quantities + flags)
-#define CRM_P8_SMEM(P, CT) ((size_t)8 * (P) * 8 + (2 * (CT) + 2) * sizeof(int))
+// Plane kernel: one block per (tile, NL consecutive levels), P threads.
+// Divergence control (profiles/r01f-g): ~19 % of the cells are saturated (Newton iteration + autoconversion/accretion)
+// and ~23 % hold precipitation in unsaturated air (evaporation), but 60 % / 57 % of the warps contained at least one such
+// cell and executed those branches for all 32 lanes (16.5 of 32 threads active per instruction).  The block therefore
+//   phase 0  classifies its NL*P cells (A saturated, B evaporating, C neither: finished in place),
+//   phase 1  compacts the A and B cells into a queue (ballot/popc ranks, A first) and processes queue entries tid,
+//            tid+P, ...: the Newton loop runs in ~nA/32 full warps; with NL = 2 the queue (~0.4*NL*P entries) keeps most
+//            of the block busy (a single level left 60 % of the threads idle at the barrier: slower than no compaction),
+//   phase 2  returns the results to the owning thread through shared memory for the coalesced stores and slab sums.
+// smem: X[8][NL*P]: cell exchange (5 inputs / 6 results in place), then each thread overwrites its own column with the 8
+// values of the transposed slab sums (quantity stride NL*P) + queue + flags.
+#define CRM_P8_NL 2
+#define CRM_P8_SMEM(P, CT) ((size_t)8 * CRM_P8_NL * (P) * 8 + (CRM_P8_NL * (P) + 64 + CRM_P8_NL * 40) * sizeof(int))
 template <int NXT>
-__global__ void __launch_bounds__(CRM_MAX_P, 5) k_p8_micro(CrmP p, int do_micro, int do_diag) {
+__global__ void __launch_bounds__(CRM_MAX_P, 4) k_p8_micro(CrmP p, int do_micro, int do_diag) {
+  constexpr int NL = CRM_P8_NL;
   const int tid = threadIdx.x;
   const int CT = (NXT) > 0 ? crm_static_ct(NXT) : p.CT, P = (NXT) > 0 ? (NXT) * crm_static_ct(NXT) : p.P;
-  const int tile = blockIdx.x / p.nzm, k = blockIdx.x - tile * p.nzm + 1;
+  const int nkb = (p.nzm + NL - 1) / NL;
+  const int tile = blockIdx.x / nkb, k0 = (blockIdx.x - tile * nkb) * NL + 1;
   const int i = tid / CT, lane = tid - i * CT;
   const long long fb = (long long)tile * p.tstride;
   const int pb = tile * p.nzp * CT + lane;
   const int cb = tile * CT + lane;
-  CRM_DYN_SMEM(double, red);
-  int *sflag = (int *)(red + 8 * P);
-  double t = F3(p.t, k), q = F3(p.qt, k), qp = F3(p.qp, k);
-  // with do_micro every one of these is recomputed before use (cloud -> qn, tabs; micro_diagnose -> qv..qpi): skip the loads
-  double qn = 0., tabs = 0., qv = 0., qcl = 0., qci = 0., qpl = 0., qpi = 0.;
-  if (!do_micro) {
-    qn = F3(p.qn, k); tabs = F3(p.tabs, k);
-    qv = F3(p.qv, k); qcl = F3(p.qcl, k); qci = F3(p.qci, k); qpl = F3(p.qpl, k); qpi = F3(p.qpi, k);
+  const int NC = NL * P;
+  CRM_DYN_SMEM(double, X);                 // X[j*NC + cell], j = 0..7
+  int *qcell = (int *)(X + 8 * NC);        // NC queue entries
+  int *cnt = qcell + NC;                   // [2][NL*nw] class counts per (level, warp), NL*nw <= 32
+  int *sflag = cnt + 64;                   // [NL][2*CT+1 (<= 40)]
+  const int sub = tid & 31, wrp = tid >> 5, nw = P >> 5;
+  double t[NL], q[NL], qp[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    const int k = k0 + l;
+    if (k <= p.nzm) { t[l] = F3(p.t, k); q[l] = F3(p.qt, k); qp[l] = F3(p.qp, k); }
+    else { t[l] = 0.; q[l] = 0.; qp[l] = 0.; }
   }
-  double dsrc = 0., devp = 0.;
+  for (int f = tid; f < NL * 40; f += P) sflag[f] = 0;
+  int nA = 0, nB = 0;
   if (do_micro) {
-    const double pres = PF(p.pres, k);
-    cloud_cell(t, PF(p.gamaz, k), pres, q, qp, qn, tabs);
-    precip_proc_cell(p, pb, CT, k, tabs, pres, q, qp, qn, dsrc, devp);
-    micro_diag_cell(p.ms, q, qn, qp, tabs, qv, qcl, qci, qpl, qpi);
-    F3(p.qt, k) = q; F3(p.qp, k) = qp; F3(p.qn, k) = qn;
-    F3(p.qv, k) = qv; F3(p.qcl, k) = qcl; F3(p.qci, k) = qci; F3(p.qpl, k) = qpl; F3(p.qpi, k) = qpi;
-    if (!do_diag) F3(p.tabs, k) = tabs;
-  }
-  if (tid < 2 * CT + 1) sflag[tid] = 0;
-  __syncthreads();
-  if (do_micro && qp != 0.) sflag[2 * CT] = 1;
-  if (do_diag) {
-    tabs = t - PF(p.gamaz, k) + CRM_FAC_COND * (qcl + qpl) + CRM_FAC_SUB * (qci + qpi);
-    F3(p.tabs, k) = tabs;
-  }
-  double v[8];
-  v[0] = F3(p.u, k); v[1] = t; v[2] = tabs; v[3] = qv + qcl + qci; v[4] = qcl + qci; v[5] = qpl + qpi; v[6] = dsrc; v[7] = devp;
-  if (do_diag) {
-    if (qcl + qci > 0. && tabs < R4(273.15)) sflag[lane] = 1;   // (the reset above is ordered by the barrier that follows it)
-  }
-  const int last = p.last_substep;
-  tr_put<8>(v, tid, P, red);
-  __syncthreads();
-  tr_get<8>(tid, P, CT, red, [&](int q, int ln, double sum) {
-    const int o = tile * p.nzp * CT + k * CT + ln;
-    if (q < 6) {
-      if (do_diag) {
-        const double coef = (double)1.f / (double)(p.nx * p.ny);
-        const double m = sum * coef;
-        if (q == 0) p.u0[o] = m;
-        else if (q == 1) p.t0[o] = m;
-        else if (q == 2) p.tabs0[o] = m;
-        else if (q == 3) p.q0[o] = m;
-        else if (q == 4) p.qn0[o] = m;
-        else p.qp0[o] = m;
+    // ---- phase 0
+    bool isA[NL], isB[NL];
+    unsigned mA[NL], mB[NL];
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      const int k = k0 + l, c = l * P + tid;
+      isA[l] = false; isB[l] = false;
+      if (k <= p.nzm) {
+        double ql = q[l], tabs0, tabs1, qsatt;
+        const double qpl_ = qp[l];
+        cloud_init(t[l], PF(p.gamaz, k), PF(p.pres, k), ql, qpl_, tabs0, tabs1, qsatt);
+        isA[l] = ql > qsatt;
+        isB[l] = !isA[l] && dmax(0., qpl_) > CRM_QP_THRESHOLD;
+        if (isA[l] || isB[l]) {
+          X[c] = tabs0; X[NC + c] = tabs1; X[2 * NC + c] = ql; X[3 * NC + c] = qpl_; X[4 * NC + c] = qsatt;
+        } else {
+          // class C: cloud.F90:107-111 with qn = 0, then precip_proc.F90:139-147 (qn = 0, qp <= qp_threshold: the trace evaporates)
+          double qpc = dmax(0., qpl_), devp = 0.;
+          if (qpc > 0.) { ql = ql + qpc; devp = -qpc; qpc = 0.; }
+          X[c] = ql; X[NC + c] = qpc; X[2 * NC + c] = 0.; X[3 * NC + c] = tabs1; X[4 * NC + c] = 0.; X[5 * NC + c] = devp;
+        }
       }
-    } else if (do_micro && last) {
-      if (q == 6) p.qpsrc[o] = sum; else p.qpevp[o] = sum;
+      mA[l] = __ballot_sync(0xffffffffu, isA[l]); mB[l] = __ballot_sync(0xffffffffu, isB[l]);
+      if (sub == 0) { cnt[l * nw + wrp] = __popc(mA[l]); cnt[32 + l * nw + wrp] = __popc(mB[l]); }
     }
-  });
-  if (do_diag && (tid >> 5) == (4 % (P >> 5))) {   // qv0 = q0 - qn0 from the same two sums (diagnose.F90:93), by the warp that owns quantity 4
-    const double s3 = tr_sum(3, tid, P, CT, red), s4 = tr_sum(4, tid, P, CT, red);
-    const double coef = (double)1.f / (double)(p.nx * p.ny);
-    if ((tid & 31) < CT) p.qv0[tile * p.nzp * CT + k * CT + (tid & 31)] = s3 * coef - s4 * coef;
+    __syncthreads();
+    int offA[NL], offB[NL];
+#pragma unroll
+    for (int l = 0; l < NL; l++) { offA[l] = 0; offB[l] = 0; }
+    for (int g = 0; g < NL * nw; g++) {
+      const int a = cnt[g], b = cnt[32 + g];
+#pragma unroll
+      for (int l = 0; l < NL; l++) if (g < l * nw + wrp) { offA[l] += a; offB[l] += b; }
+      nA += a; nB += b;
+    }
+    const unsigned lt = (1u << sub) - 1u;
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      if (isA[l]) qcell[offA[l] + __popc(mA[l] & lt)] = l * P + tid;
+      else if (isB[l]) qcell[nA + offB[l] + __popc(mB[l] & lt)] = l * P + tid;
+    }
+    __syncthreads();
+    // ---- phase 1: queue entries (A first)
+    for (int e = tid; e < nA + nB; e += P) {
+      const int c = qcell[e];
+      const int l = c / P, ct = c - l * P;
+      const int k = k0 + l;
+      const int pbc = tile * p.nzp * CT + (ct & (CT - 1));
+      const double pres = p.pres[pbc + k * CT];
+      const double c_tabs0 = X[c];
+      double c_tabs = X[NC + c], c_q = X[2 * NC + c], c_qp = X[3 * NC + c], c_qn = 0., c_dsrc, c_devp;
+      if (e < nA) c_qn = cloud_newton(c_tabs0, pres, c_q, c_qp, c_tabs, X[4 * NC + c]);
+      c_qp = dmax(0., c_qp);
+      precip_proc_cell(p, pbc, CT, k, c_tabs, pres, c_q, c_qp, c_qn, c_dsrc, c_devp);
+      X[c] = c_q; X[NC + c] = c_qp; X[2 * NC + c] = c_qn; X[3 * NC + c] = c_tabs; X[4 * NC + c] = c_dsrc; X[5 * NC + c] = c_devp;
+    }
   }
-  if (do_diag && i == 0 && sflag[lane]) { atomicMin(&p.kmin[cb], k); atomicMax(&p.kmax[cb], k); }
-  if (do_micro && tid == 0 && sflag[2 * CT]) atomicMax(&p.kqp[tile], k);
+  __syncthreads();   // phase-1 results (and the flag reset) visible
+  // ---- phase 2: own cells, level by level
+  const int last = p.last_substep;
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    const int k = k0 + l, c = l * P + tid;
+    if (k > p.nzm) break;
+    int *sf = sflag + l * 40;
+    double qn, tabs, qv, qcl, qci, qpl, qpi, dsrc = 0., devp = 0.;
+    double ql = q[l], qpp = qp[l];
+    if (do_micro) {
+      ql = X[c]; qpp = X[NC + c]; qn = X[2 * NC + c]; tabs = X[3 * NC + c]; dsrc = X[4 * NC + c]; devp = X[5 * NC + c];
+      micro_diag_cell(p.ms, ql, qn, qpp, tabs, qv, qcl, qci, qpl, qpi);
+      F3(p.qt, k) = ql; F3(p.qp, k) = qpp; F3(p.qn, k) = qn;
+      F3(p.qv, k) = qv; F3(p.qcl, k) = qcl; F3(p.qci, k) = qci; F3(p.qpl, k) = qpl; F3(p.qpi, k) = qpi;
+      if (!do_diag) F3(p.tabs, k) = tabs;
+      if (qpp != 0.) sf[2 * CT] = 1;
+    } else {
+      qn = F3(p.qn, k); tabs = F3(p.tabs, k);
+      qv = F3(p.qv, k); qcl = F3(p.qcl, k); qci = F3(p.qci, k); qpl = F3(p.qpl, k); qpi = F3(p.qpi, k);
+    }
+    if (do_diag) {
+      tabs = t[l] - PF(p.gamaz, k) + CRM_FAC_COND * (qcl + qpl) + CRM_FAC_SUB * (qci + qpi);
+      F3(p.tabs, k) = tabs;
+      if (qcl + qci > 0. && tabs < R4(273.15)) sf[lane] = 1;
+    }
+    double v[8];
+    v[0] = F3(p.u, k); v[1] = t[l]; v[2] = tabs; v[3] = qv + qcl + qci; v[4] = qcl + qci; v[5] = qpl + qpi; v[6] = dsrc; v[7] = devp;
+    tr_put<8>(v, tid, NC, X + l * P);   // own column of X: nobody else reads it after phase 1
+  }
+  __syncthreads();
+  for (int l = 0; l < NL; l++) {
+    const int k = k0 + l;
+    if (k > p.nzm) break;
+    const double *trl = X + l * P;
+    const int *sf = sflag + l * 40;
+    tr_get<8>(tid, P, CT, NC, trl, [&](int qq, int ln, double sum) {
+      const int o = tile * p.nzp * CT + k * CT + ln;
+      if (qq < 6) {
+        if (do_diag) {
+          const double coef = (double)1.f / (double)(p.nx * p.ny);
+          const double m = sum * coef;
+          if (qq == 0) p.u0[o] = m;
+          else if (qq == 1) p.t0[o] = m;
+          else if (qq == 2) p.tabs0[o] = m;
+          else if (qq == 3) p.q0[o] = m;
+          else if (qq == 4) p.qn0[o] = m;
+          else p.qp0[o] = m;
+        }
+      } else if (do_micro && last) {
+        if (qq == 6) p.qpsrc[o] = sum; else p.qpevp[o] = sum;
+      }
+    });
+    if (do_diag && wrp == (4 % nw)) {   // qv0 = q0 - qn0 from the same two sums (diagnose.F90:93), by the warp that owns quantity 4
+      const double s3 = tr_sum(3, tid, P, CT, NC, trl), s4 = tr_sum(4, tid, P, CT, NC, trl);
+      const double coef = (double)1.f / (double)(p.nx * p.ny);
+      if (sub < CT) p.qv0[tile * p.nzp * CT + k * CT + sub] = s3 * coef - s4 * coef;
+    }
+    if (do_diag && i == 0 && sf[lane]) { atomicMin(&p.kmin[cb], k); atomicMax(&p.kmax[cb], k); }
+    if (do_micro && tid == 0 && sf[2 * CT]) atomicMax(&p.kqp[tile], k);
+  }
 }
 
 __global__ void k_reset_kminmax(CrmP p) {
