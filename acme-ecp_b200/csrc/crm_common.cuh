@@ -274,7 +274,9 @@ __device__ __forceinline__ void red_put(double (&v)[NQ], int tid, int CT, double
 template <int NQ, class F>
 __device__ __forceinline__ void red_get(int tid, int P, int CT, const double *red, F f) {
   const int nw = P >> 5;
-  for (int t = tid; t < NQ * CT; t += P) {
+  // the final chains run in the LAST threads of the block: thread 0 issues the bulk copies of the next level at the same
+  // point of every march loop, and the rest of the block waits for both at the next barrier
+  for (int t = P - 1 - tid; t < NQ * CT; t += P) {
     const int q = t / CT, ln = t - q * CT;
     double s = red[q * CT + ln];
     for (int g = 1; g < nw; g++) s += red[(g * NQ + q) * CT + ln];

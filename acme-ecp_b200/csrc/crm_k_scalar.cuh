@@ -458,19 +458,19 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_precip_b(CrmP p, int iprec0, i
     double mxn0 = 0., mnn0 = 0., mxn1 = 0., mnn1 = 0.;  // normalised at s-3, s-2
     double fzl0 = 0., fzl1 = 0.;                        // limited flux at s-3, s-2
     double om0 = 0., om1 = 0., om2 = 0., om3 = 0.;      // omega(s-3..s)
-    double Fprev = 0.;                                  // threads tid < CT: slab sum F(L-1) of lane tid
+    double Fprev = 0.;                                  // threads tid >= P-CT: slab sum F(L-1) of lane tid-(P-CT)
     int zc = 6;                                         // consecutive precipitation-free levels loaded so far
     for (int s = 1; s <= KT + 3; s++) {
       __syncthreads();   // ring slot of level s-4 is free; warp partials of level k3 = s-4 are visible
       CRM_PIPE_STEP(R, s, KT, 2, 0)
-      if (s - 4 >= 1 && tid < CT) {   // F(L), L = s-4: precflux(L) -= F(L); qpfall(L-1) += -(F(L) - F(L-1))/(rho*adz)(L-1)
-        const int L = s - 4;
+      if (s - 4 >= 1 && tid >= P - CT) {   // F(L), L = s-4: precflux(L) -= F(L); qpfall(L-1) += -(F(L) - F(L-1))/(rho*adz)(L-1)
+        const int L = s - 4, ln = tid - (P - CT);   // (last threads of the block: thread 0 is busy issuing the ring copies)
         const double *rd = red + (s & 1) * RS;
-        double F = rd[tid];
-        for (int g = 1; g < nw; g++) F += rd[g * CT + tid];
-        const int o = tile * p.nzp * CT + L * CT + tid;
+        double F = rd[ln];
+        for (int g = 1; g < nw; g++) F += rd[g * CT + ln];
+        const int o = tile * p.nzp * CT + L * CT + ln;
         acc_add(p.precflux + o, -F);
-        if (L >= 2) acc_add(p.qpfall + o - CT, -(F - Fprev) * sprof[(L - 1) * CT + tid]);
+        if (L >= 2) acc_add(p.qpfall + o - CT, -(F - Fprev) * sprof[(L - 1) * CT + ln]);
         Fprev = F;
       }
       // ---- load level s
@@ -545,14 +545,15 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_precip_b(CrmP p, int iprec0, i
       }
     }
     __syncthreads();
-    if (tid < CT) {   // F(KT) and the top level: F(KT+1) = 0
+    if (tid >= P - CT) {   // F(KT) and the top level: F(KT+1) = 0
+      const int ln = tid - (P - CT);
       const double *rd = red + (KT & 1) * RS;
-      double F = rd[tid];
-      for (int g = 1; g < nw; g++) F += rd[g * CT + tid];
-      const int o = tile * p.nzp * CT + KT * CT + tid;
+      double F = rd[ln];
+      for (int g = 1; g < nw; g++) F += rd[g * CT + ln];
+      const int o = tile * p.nzp * CT + KT * CT + ln;
       acc_add(p.precflux + o, -F);
-      if (KT >= 2) acc_add(p.qpfall + o - CT, -(F - Fprev) * sprof[(KT - 1) * CT + tid]);
-      acc_add(p.qpfall + o, -(0. - F) * sprof[KT * CT + tid]);
+      if (KT >= 2) acc_add(p.qpfall + o - CT, -(F - Fprev) * sprof[(KT - 1) * CT + ln]);
+      acc_add(p.qpfall + o, -(0. - F) * sprof[KT * CT + ln]);
     }
   }
 #undef S_IRA
