@@ -128,27 +128,78 @@ __device__ __forceinline__ double pn_(double y) { return -dmin(0., y); }
 // product of repeated square roots (each correctly rounded; a few ulp in total instead of the ~250-instruction generic
 // pow).  The rain exponents and ice_fall's 0.24 are not dyadic: x**c = exp(c*log(x)) (relative error ~ |c ln x| ulp).
 __device__ __forceinline__ double pow_c(double x, double c) { return exp(c * log(x)); }   // x >= 0, c > 0
-__device__ __forceinline__ double pow_1_16(double x) { return sqrt(sqrt(sqrt(sqrt(x)))); }   // csnow = 0.25/4
-__device__ __forceinline__ double pow_1_8(double x) { return sqrt(sqrt(sqrt(x))); }          // cgrau = 0.5/4
-__device__ __forceinline__ double pow_13_16(double x) {   // pows1 = (3+0.25)/4 = 1/2 + 1/4 + 1/16
-  const double s1 = sqrt(x), s2 = sqrt(s1), s4 = sqrt(sqrt(s2));
-  return s1 * s2 * s4;
+// The dyadic powers are built from r = x**(-1/16) (or x**(-1/32)): an FP32 seed exp2(-log2(x)/16) (two MUFU operations,
+// relative error ~1e-6) refined by two division-free Newton steps r <- r*(17 - x*r**16)/16 (error 8.5*e**2 per step, so
+// ~1e-21 before rounding); x**(k/16) = x * r**(16-k).  ~27 FP64 instructions instead of four chained IEEE square roots
+// (~60, all serially dependent).  Results agree with pow() to ~(16-k) ulp.  Outside the FP32 range (never reached by
+// mixing ratios above qp_threshold) the square-root chain is used.
+#ifdef CRM_EMU
+#define CRM_LOG2F(x) log2f(x)
+#else
+#define CRM_LOG2F(x) __log2f(x)
+#endif
+__device__ __forceinline__ bool rpow_ok(double x) { return x > 1.e-30 && x < 1.e30; }
+__device__ __forceinline__ double rpow16(double x) {   // x**(-1/16)
+  double r = (double)exp2f(-0.0625f * CRM_LOG2F((float)x));
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4, r16 = r8 * r8;
+    r = r * (17. - x * r16) * 0.0625;
+  }
+  return r;
 }
-__device__ __forceinline__ double pow_7_8(double x) {     // powg1 = (3+0.5)/4 = 1/2 + 1/4 + 1/8
-  const double s1 = sqrt(x), s2 = sqrt(s1), s3 = sqrt(s2);
-  return s1 * s2 * s3;
+__device__ __forceinline__ double rpow32(double x) {   // x**(-1/32)
+  double r = (double)exp2f(-0.03125f * CRM_LOG2F((float)x));
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4, r16 = r8 * r8, r32 = r16 * r16;
+    r = r * (33. - x * r32) * 0.03125;
+  }
+  return r;
 }
-// sqrt(x) and x**(21/32) (pows2 = (5+0.25)/8 = 1/2 + 1/8 + 1/32)
+__device__ __forceinline__ double pow_1_16(double x) {   // csnow = 0.25/4
+  if (!rpow_ok(x)) return sqrt(sqrt(sqrt(sqrt(x))));
+  const double r = rpow16(x), r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+  return x * (r8 * r4) * (r2 * r);
+}
+__device__ __forceinline__ double pow_1_8(double x) {    // cgrau = 0.5/4
+  if (!rpow_ok(x)) return sqrt(sqrt(sqrt(x)));
+  const double r = rpow16(x), r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+  return x * (r8 * r4) * r2;
+}
+__device__ __forceinline__ double pow_13_16(double x) {   // pows1 = (3+0.25)/4
+  if (!rpow_ok(x)) { const double s1 = sqrt(x), s2 = sqrt(s1), s4 = sqrt(sqrt(s2)); return s1 * s2 * s4; }
+  const double r = rpow16(x);
+  return x * (r * r * r);
+}
+__device__ __forceinline__ double pow_7_8(double x) {     // powg1 = (3+0.5)/4
+  if (!rpow_ok(x)) { const double s1 = sqrt(x), s2 = sqrt(s1), s3 = sqrt(s2); return s1 * s2 * s3; }
+  const double r = rpow16(x);
+  return x * (r * r);
+}
+// sqrt(x) and x**(21/32) (pows2 = (5+0.25)/8)
 __device__ __forceinline__ void sqrt_pow_21_32(double x, double &s1, double &pw) {
-  s1 = sqrt(x);
-  const double s3 = sqrt(sqrt(s1)), s5 = sqrt(sqrt(s3));
-  pw = s1 * s3 * s5;
+  if (!rpow_ok(x)) {
+    s1 = sqrt(x);
+    const double s3 = sqrt(sqrt(s1)), s5 = sqrt(sqrt(s3));
+    pw = s1 * s3 * s5;
+    return;
+  }
+  const double r = rpow32(x), r2 = r * r, r4 = r2 * r2, r8 = r4 * r4, r16 = r8 * r8;
+  s1 = x * r16;
+  pw = x * (r8 * r2 * r);
 }
-// sqrt(x) and x**(11/16) (powg2 = (5+0.5)/8 = 1/2 + 1/8 + 1/16)
+// sqrt(x) and x**(11/16) (powg2 = (5+0.5)/8)
 __device__ __forceinline__ void sqrt_pow_11_16(double x, double &s1, double &pw) {
-  s1 = sqrt(x);
-  const double s3 = sqrt(sqrt(s1)), s4 = sqrt(s3);
-  pw = s1 * s3 * s4;
+  if (!rpow_ok(x)) {
+    s1 = sqrt(x);
+    const double s3 = sqrt(sqrt(s1)), s4 = sqrt(s3);
+    pw = s1 * s3 * s4;
+    return;
+  }
+  const double r = rpow16(x), r2 = r * r, r4 = r2 * r2;
+  s1 = x * (r4 * r4);
+  pw = x * (r4 * r);
 }
 
 // ---- sat.F90 (Flatau et al. polynomials with REAL(4) coefficients) ----
