@@ -4,6 +4,7 @@
 // sm_100a kernels of crm_k_*.cuh; there is no CPU fallback (with CRM_EMU undefined, this file needs a CUDA device).
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -225,7 +226,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
     crm_b200_free(h);
     return 9;
   }
-  if (!micro_scalars(p.ms) || p.ms.csnow != 0.0625 || p.ms.cgrau != 0.125) { g_init_err = "cannot compute gamma-function in precip_init"; crm_b200_free(h); return 10; }
+  if (!micro_scalars(p.ms) || p.ms.csnow != 0.0625 || p.ms.cgrau != 0.125 || std::fabs(p.ms.crain - 0.2) > 1e-7) { g_init_err = "cannot compute gamma-function in precip_init"; crm_b200_free(h); return 10; }
 #ifndef CRM_EMU
   {
     const int big = 200 * 1024;

@@ -177,6 +177,41 @@ __device__ __forceinline__ double pow_7_8(double x) {     // powg1 = (3+0.5)/4
   const double r = rpow16(x);
   return x * (r * r);
 }
+// Rain exponents (b_rain = 0.8 as a REAL(4) literal): c = 1/5, 19/20, 29/40 plus d ~ 3e-9 (the float rounding of 0.8).
+// x**c = x * r**m with r = x**(-1/N) from the same seeded Newton iteration (N = 5, 20, 40), times the first two terms of
+// exp(d*ln x) with ln x from the FP32 seed (d*ln x ~ 6e-8, so its 1e-7 relative error contributes < 1e-14).  ~35 FP64
+// instructions instead of ~100 for exp(c*log(x)); agrees with pow() to ~1e-14 relative.
+template <int N>
+__device__ __forceinline__ double rpowN(double x, double &lnx) {   // x**(-1/N); also ln(x) to FP32 accuracy
+  const float l2 = CRM_LOG2F((float)x);
+  lnx = 0.6931471805599453 * (double)l2;
+  double r = (double)exp2f((-1.f / (float)N) * l2);
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    const double r2 = r * r, r4 = r2 * r2;
+    double rn;
+    if (N == 5) rn = r4 * r;
+    else { const double r8 = r4 * r4, r16 = r8 * r8; rn = (N == 20) ? r16 * r4 : (r16 * r16) * r8; }
+    r = r * ((double)(N + 1) - x * rn) * (1. / (double)N);
+  }
+  return r;
+}
+__device__ __forceinline__ double pow_fix(double y0, double d, double lnx) { const double t = d * lnx; return y0 + y0 * (t + 0.5 * t * t); }
+__device__ __forceinline__ double pow_rain_c(double x, double c) {    // c = b_rain/4 ~ 0.2
+  if (!rpow_ok(x)) return pow_c(x, c);
+  double lnx; const double r = rpowN<5>(x, lnx), r2 = r * r;
+  return pow_fix(x * (r2 * r2), c - 0.2, lnx);
+}
+__device__ __forceinline__ double pow_rain_1(double x, double c) {    // c = (3+b_rain)/4 ~ 0.95
+  if (!rpow_ok(x)) return pow_c(x, c);
+  double lnx; const double r = rpowN<20>(x, lnx);
+  return pow_fix(x * r, c - 0.95, lnx);
+}
+__device__ __forceinline__ double pow_rain_2(double x, double c) {    // c = (5+b_rain)/8 ~ 0.725
+  if (!rpow_ok(x)) return pow_c(x, c);
+  double lnx; const double r = rpowN<40>(x, lnx), r2 = r * r, r8 = (r2 * r2) * (r2 * r2);
+  return pow_fix(x * (r8 * r2 * r), c - 0.725, lnx);
+}
 // sqrt(x) and x**(21/32) (pows2 = (5+0.25)/8)
 __device__ __forceinline__ void sqrt_pow_21_32(double x, double &s1, double &pw) {
   if (!rpow_ok(x)) {

@@ -316,7 +316,7 @@ __device__ __forceinline__ double term_vel_qp(const MicroScalars &m, double qplo
   if (qploc > CRM_QP_THRESHOLD) {
     const double omp = dmax(0., dmin(1., (tabs - CRM_TPRMIN) * m.a_pr));
     if (omp == 1.) {
-      term_vel = m.vrain * pow_c(rho * qploc, m.crain);
+      term_vel = m.vrain * pow_rain_c(rho * qploc, m.crain);
     } else if (omp == 0.) {
       const double omg = dmax(0., dmin(1., (tabs - CRM_TGRMIN) * m.a_gr));
       const double qgg = omg * qploc;
@@ -328,7 +328,7 @@ __device__ __forceinline__ double term_vel_qp(const MicroScalars &m, double qplo
       double qss = qploc - qrr;
       const double qgg = omg * qss;
       qss = qss - qgg;
-      term_vel = (omp * m.vrain * pow_c(rho * qrr, m.crain) +
+      term_vel = (omp * m.vrain * pow_rain_c(rho * qrr, m.crain) +
                   (1. - omp) * (omg * m.vgrau * pow_1_8(rho * qgg) + (1. - omg) * m.vsnow * pow_1_16(rho * qss)));
     }
   }
@@ -699,7 +699,7 @@ __device__ inline void precip_proc_cell(const CrmP &p, int pb, int CT, int k, do
       double accrr = 0.;
       if (omp > R4(0.001)) {
         const double qrr = qp * omp;
-        accrr = PF(p.accrrc, k) * pow_c(qrr, powr1);
+        accrr = PF(p.accrrc, k) * pow_rain_1(qrr, powr1);
       }
       double accrcs = 0., accris = 0.;
       if (omp < R4(0.999) && omg < R4(0.999)) {
@@ -730,7 +730,7 @@ __device__ inline void precip_proc_cell(const CrmP &p, int pb, int CT, int k, do
       double dq = 0.;
       if (omp > R4(0.001)) {
         const double qrr = qp * omp;
-        dq = dq + PF(p.evapr1, k) * sqrt(qrr) + PF(p.evapr2, k) * pow_c(qrr, powr2);
+        dq = dq + PF(p.evapr1, k) * sqrt(qrr) + PF(p.evapr2, k) * pow_rain_2(qrr, powr2);
       }
       if (omp < R4(0.999) && omg < R4(0.999)) {
         const double qss = qp * (1. - omp) * (1. - omg);
