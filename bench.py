@@ -83,6 +83,22 @@ class ClockSampler:
         return out
 
 
+def ncu_traffic(kernel, ncrms):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture of the same
+    batch size (profiles/*ncu_traffic*.json, written by tools/ncu_traffic.py from tools/gpu_traffic.sh); None if no
+    capture of this batch size exists."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_traffic*.json"))):
+        try:
+            d = json.load(open(f))
+        except Exception:
+            continue
+        if d.get("ncrms") == ncrms and kernel in d.get("kernels", {}):
+            best = d["kernels"][kernel]["dram_bytes_per_launch"]
+    return best
+
+
 def build_case(pkg, cfg, ncrms, seed):
     kw = dict(pkg.synthetic.CONFIGS[cfg])
     if ncrms:
@@ -242,7 +258,8 @@ def run_ours(args):
         ms_k, n_k = kt[name]
         alg = KERNEL_WORDS[name] * 8.0 * dims.cells            # bytes per launch
         ach = alg / (ms_k / n_k * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": ncu_traffic(name, dims.ncrms),
                 "peak_source": peak_src, "kernel_share_of_step": ms_k / tot,
                 "algorithmic_bytes_per_launch": alg,
                 "whole_step": {"bytes_per_cell_update": BYTES_PER_CELL_UPDATE["2d_sam1mom"],
