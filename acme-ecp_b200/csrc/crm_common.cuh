@@ -191,7 +191,10 @@ __device__ __forceinline__ double rpowN(double x, double &lnx) {   // x**(-1/N);
     const double r2 = r * r, r4 = r2 * r2;
     double rn;
     if (N == 5) rn = r4 * r;
-    else { const double r8 = r4 * r4, r16 = r8 * r8; rn = (N == 20) ? r16 * r4 : (r16 * r16) * r8; }
+    else {
+      const double r8 = r4 * r4, r16 = r8 * r8;
+      rn = (N == 20) ? r16 * r4 : (N == 25) ? (r16 * r8) * r : (r16 * r16) * r8;
+    }
     r = r * ((double)(N + 1) - x * rn) * (1. / (double)N);
   }
   return r;
@@ -201,6 +204,11 @@ __device__ __forceinline__ double pow_rain_c(double x, double c) {    // c = b_r
   if (!rpow_ok(x)) return pow_c(x, c);
   double lnx; const double r = rpowN<5>(x, lnx), r2 = r * r;
   return pow_fix(x * (r2 * r2), c - 0.2, lnx);
+}
+__device__ __forceinline__ double pow_ice_024(double x, double c) {   // ice_fall.F90:94: c = 0.24 as a REAL(4) literal; 6/25 = 1 - 19/25
+  if (!rpow_ok(x)) return pow_c(x, c);
+  double lnx; const double r = rpowN<25>(x, lnx), r2 = r * r, r4 = r2 * r2, r16 = (r4 * r4) * (r4 * r4);
+  return pow_fix(x * (r16 * r2 * r), c - 0.24, lnx);
 }
 __device__ __forceinline__ double pow_rain_1(double x, double c) {    // c = (3+b_rain)/4 ~ 0.95
   if (!rpow_ok(x)) return pow_c(x, c);

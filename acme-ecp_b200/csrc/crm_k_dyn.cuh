@@ -27,7 +27,7 @@ __device__ __forceinline__ double ice_flux(const CrmP &p, const PipeQ &Q, const 
   double qiu = s_rho[kc * CT + lane] * Q.plane(0, kc)[tid];
   double qic = s_rho[kk * CT + lane] * Q.plane(0, kk)[tid];
   double qid = s_rho[kb * CT + lane] * Q.plane(0, kb)[tid];
-  double vt_ice = dmin(R4(0.4), R4(8.66) * pow_c(dmax(0., qic) + R4(1.e-10), R4(0.24)));
+  double vt_ice = dmin(R4(0.4), R4(8.66) * pow_ice_024(dmax(0., qic) + R4(1.e-10), R4(0.24)));
   double tmp_phi;
   if (fabs(qic - qid) < R4(1.0e-25)) tmp_phi = 0.;
   else {
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p1_forcing(CrmP p) {
 // shear_prod2D.F90:20-94 (v == 0 in 2-D) + tke_full.F90:103-310 with dosmagor.  tk/tkh written for k <= nzm-1.
 // One TMA plane ring of 9 fields, levels k and k+1 resident (3 stages); u(k-1) is carried in registers; the old tk
 // (own column, one value per level) is an ordinary load issued at the top of the iteration.
-#define CRM_P2_NPROF 9
+#define CRM_P2_NPROF 10
 #define CRM_P2_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(9, 3, P) + CRM_PROF_BYTES(CRM_P2_NPROF, nzp, CT))
 template <int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
   double *sprof = (double *)(smraw + CRM_PIPE_BYTES(9, 3, P));
   const double dx = p.dx, rdx0 = 1. / dx, dt = p.dt;
   // per-(CRM, level) factors, evaluated once per block with the reference's expressions:
-  // 0 rdz=1/(dz adz)  1 rdx0 sqrt(dx rdz)  2 rdzw=1/(dz adzw)  3 rdx0 sqrt(dx rdzw)  4 u0  5 betdz  6 presi(k+1)  7 grd=dz adz  8 tkmax
+  // 0 rdz=1/(dz adz)  1 rdx0 sqrt(dx rdz)  2 rdzw=1/(dz adzw)  3 rdx0 sqrt(dx rdzw)  4 u0  5 betdz  6 presi(k+1)  7 grd=dz adz  8 tkmax  9 1/grd
   for (int q = tid; q < p.nz * CT; q += P) {
     const int k = q / CT + 1, ln = q - (k - 1) * CT;
     const int o = tile * p.nzp * CT + k * CT + ln, so = k * CT + ln;
@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
       sprof[5 * npf + so] = (k <= nzm - 1) ? 0.5 * (p.bet[o + CT] + p.bet[o]) / dzq / adzw1 : 0.;
       sprof[6 * npf + so] = p.presi[o + CT];
       sprof[7 * npf + so] = dzq * adz;
+      sprof[9 * npf + so] = 1. / (dzq * adz);
       const double cx = dx * dx / dt / p.grdf_x[o];
       const double cy = p.dy * p.dy / dt / p.grdf_x[o];   // grdf_y == grdf_x (dy = dx)
       const double dzm = dzq * dmin(adzw, adzw1);
@@ -274,12 +275,15 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
       const double tkmax = SPF(8, k);
       const double bs = 0.5 * (bsv_km1 + bsv_k);
       double smix;
+      // (tke_full.F90:262-280 with the divisions folded: x/Ck/sqrt(b) = (x/Ck)*rsqrt(b), smix/grd through the staged
+      // reciprocal, tk/(Ck*smix) = sqrt(..)*smix/Ck; the results differ from the literal expressions by a few ulp)
       if (bs <= 0.) smix = grd;
-      else smix = dmin(grd, dmax(R4(0.1) * grd, sqrt(R4(0.76) * tk_old / Ck / sqrt(bs + R4(1.e-10)))));
-      const double ratio = smix / grd;
+      else smix = dmin(grd, dmax(R4(0.1) * grd, sqrt((R4(0.76) / Ck) * tk_old * rsqrt(bs + R4(1.e-10)))));
+      const double ratio = smix * SPF(9, k);
       const double Cee = Ce1 + Ce2 * ratio;
-      double tk = sqrt(Ck * Ck * Ck / Cee * dmax(0., def2 - Pr * bs)) * (smix * smix);
-      const double r = tk / (Ck * smix);
+      const double sq = sqrt(Ck * Ck * Ck / Cee * dmax(0., def2 - Pr * bs));
+      double tk = sq * (smix * smix);
+      const double r = sq * smix * (1. / Ck);
       F3(p.tke, k) = r * r;
       tk = dmin(tk, tkmax);
       F3(p.tk, k) = tk;

@@ -53,6 +53,7 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
   pthread_barrier_wait(wb);
   return r;
 }
+static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 static inline int __all_sync(unsigned m, int pred) {

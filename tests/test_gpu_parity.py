@@ -181,7 +181,9 @@ def test_partition_invariance_property_full_width():
     """Size-independent property at a batch that fills the GPU several times (no oracle): columns are independent, so a
     CRM's result must not depend on the batch it is in as long as the batch-global sub-cycling counts agree.  The
     same 96 columns are run alone and embedded, shifted by one column (so every CRM gets other tile partners and the
-    per-tile level skipping sees other mixes), in a 3073-column batch made of copies of themselves: bit-identical."""
+    per-tile level skipping sees other mixes), in a 3073-column batch made of copies of themselves.  With the same tile
+    partners the results are bit-identical; with other partners a level may run through the unrolled interior body of
+    k_mpdata instead of its boundary body (different FMA contraction), so the bound is 1e-11 relative after 5 steps."""
     dims = cm.small_dims(ncrms=96, nx=64, nzm=58, plev=72, nsteps=5)
     dims, inp, st, rad = cm.make_case(dims, 30)
     h = cm.libmod.CrmHandle(dims)
@@ -210,5 +212,7 @@ def test_partition_invariance_property_full_width():
     for n in cm.STATE:
         a, b = getattr(st_a, n)[:dims.ncrms], getattr(st_b, n)
         for r in (0, rep // 2, rep - 1):
-            assert np.array_equal(a, b[1 + r * dims.ncrms:1 + (r + 1) * dims.ncrms]), (n, r)
-    assert np.array_equal(out_a.sltend[:dims.ncrms], out_b.sltend[1 + (rep - 1) * dims.ncrms:])
+            err, scale = cm.rel_err(a, b[1 + r * dims.ncrms:1 + (r + 1) * dims.ncrms], dims.ncrms)
+            assert err < 1e-11, (n, r, err)
+    err, _ = cm.rel_err(out_a.sltend[:dims.ncrms], out_b.sltend[1 + (rep - 1) * dims.ncrms:], dims.ncrms)
+    assert err < 1e-10
