@@ -23,7 +23,7 @@ __device__ __forceinline__ double ice_flux(const CrmP &p, const PipeQ &Q, const 
   if (kk < imax(1, kmin - 1) || kk > kmax) return 0.;
   const int nzm = p.nzm;
   int kc = imin(nzm, kk + 1), kb = imax(1, kk - 1);
-  double coef = p.dtn / (0.5 * (s_adz[kb * CT + lane] + s_adz[kk * CT + lane]) * dz);
+  double coef = s_adz[11 * p.nzp * CT + kk * CT + lane];   // slot 12 of the staged profiles: dtn/(0.5*(adz(kb)+adz(kk))*dz)
   double qiu = s_rho[kc * CT + lane] * Q.plane(0, kc)[tid];
   double qic = s_rho[kk * CT + lane] * Q.plane(0, kk)[tid];
   double qid = s_rho[kb * CT + lane] * Q.plane(0, kb)[tid];
@@ -40,7 +40,7 @@ __device__ __forceinline__ double ice_flux(const CrmP &p, const PipeQ &Q, const 
 // zero.F90, buoyancy.F90:17-36, forcing.F90:38-73, crm_module.F90:766-777, damping.F90:60-110, ice_fall.F90:34-165
 // Two TMA plane rings: qci (levels k..k+2 resident, 6 stages) and the nine single-level inputs (2 stages; three
 // blocks per SM keep enough loads in flight).
-#define CRM_P1_NPROF 11
+#define CRM_P1_NPROF 13
 #define CRM_P1_SMEM(P, CT, nzp) \
   (CRM_PIPE_BYTES(1, 6, P) + CRM_PIPE_BYTES(9, 2, P) + CRM_PROF_BYTES(CRM_P1_NPROF, nzp, CT) + (size_t)CRM_RED_DOUBLES(3, P, CT) * 8)
 template <int NXT>
@@ -58,8 +58,21 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p1_forcing(CrmP p) {
   double *sprof = (double *)(sm2 + CRM_PIPE_BYTES(9, 2, P));
   double *red = sprof + CRM_P1_NPROF * npf;
   {
-    const double *const g[CRM_P1_NPROF] = {p.rho, p.adz, p.tabs0, p.qv0, p.qn0, p.qp0, p.bet, p.ttend, p.qtend, p.utend, p.tau};
-    stage_profiles<CRM_P1_NPROF>(sprof, g, tile, p.nzp, CT, tid, P);
+    const double *const g[11] = {p.rho, p.adz, p.tabs0, p.qv0, p.qn0, p.qp0, p.bet, p.ttend, p.qtend, p.utend, p.tau};
+    stage_profiles<11>(sprof, g, tile, p.nzp, CT, tid, P);
+  }
+  // per-(CRM, level) quotients evaluated once per block instead of once per cell (the FP64 divide runs on the MUFU pipe):
+  // slot 6 = bet(k)*adz(k-1)/(adz(k)+adz(k-1)) (buoyancy.F90:27-28, replaces bet), 11 = bet(k-1)*adz(k)/(adz(k)+adz(k-1)),
+  // 12 = dtn/(0.5*(adz(kb)+adz(k))*dz) (ice_fall.F90:88)
+  __syncthreads();
+  for (int q = tid; q < nzm * CT; q += P) {
+    const int k = q / CT + 1, ln = q - (k - 1) * CT;
+    const int so = k * CT + ln, kb = imax(1, k - 1);
+    const double adzk = sprof[npf + so], adzb = sprof[npf + kb * CT + ln];
+    const double betk = p.bet[tile * p.nzp * CT + so], betb = p.bet[tile * p.nzp * CT + kb * CT + ln];
+    sprof[6 * npf + so] = betk * (adzb / (adzk + adzb));
+    sprof[11 * npf + so] = betb * (adzk / (adzk + adzb));
+    sprof[12 * npf + so] = p.dtn / (0.5 * (adzb + adzk) * p.dz[tile * CT + ln]);
   }
   const double *s_rho = sprof, *s_adz = sprof + npf;
 #define SPF(r, k) sprof[(r) * npf + (k) * CT + lane]
@@ -91,9 +104,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p1_forcing(CrmP p) {
     const double expr_k = tabs0 * (CRM_EPSV * (qv - qv0) - (qcl + qci - qn0 + qpl + qpi - qp0)) + (tabs - tabs0) * (1. + CRM_EPSV * qv0 - qn0 - qp0);
     double dw = 0.;
     if (k >= 2) {
-      double adzk = SPF(1, k), adzb = SPF(1, k - 1);
-      double betu = adzb / (adzk + adzb), betd = adzk / (adzk + adzb);
-      dw = dw + SPF(6, k) * betu * expr_k + SPF(6, k - 1) * betd * expr_km1;
+      dw = dw + SPF(6, k) * expr_k + SPF(11, k) * expr_km1;
     }
     expr_km1 = expr_k;
     // --- forcing
@@ -297,7 +308,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
 // advect2_mom_xy.F90:64-82, advect2_mom_z.F90:31-125, diffuse_mom2D.F90:38-158 (v == 0, fluxb* = fluxt* = 0).
 // u, w, tk, dudt(na), dwdt(na) stream through a 4-stage TMA plane ring (levels k, k+1 resident, 2 levels of prefetch);
 // the six grid profiles of the tile are staged in shared memory once.
-#define CRM_P3_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(5, 4, P) + CRM_PROF_BYTES(6, nzp, CT) + (size_t)CRM_RED_DOUBLES(2, P, CT) * 8)
+#define CRM_P3_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(5, 4, P) + CRM_PROF_BYTES(11, nzp, CT) + (size_t)CRM_RED_DOUBLES(2, P, CT) * 8)
 template <int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P, 3) k_p3_mom(CrmP p) {
   CRM_TILE_SETUP_T(NXT)
@@ -307,12 +318,31 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_p3_mom(CrmP p) {
   PlanePipe<5, 4> pipe;
   pipe.src[0] = p.u + fb; pipe.src[1] = p.w + fb; pipe.src[2] = p.tk + fb; pipe.src[3] = p.du_a + fb; pipe.src[4] = p.dw_a + fb;
   double *sprof = (double *)(smraw + CRM_PIPE_BYTES(5, 4, P));
-  double *red = sprof + 6 * npf;
+  double *red = sprof + 11 * npf;
   {
     const double *const g[6] = {p.rho, p.adz, p.rhow, p.adzw, p.grdf_x, p.grdf_z};
     stage_profiles<6>(sprof, g, tile, p.nzp, CT, tid, P);
   }
+  // per-(CRM, level) reciprocals, evaluated once per block with the reference's expressions (the FP64 divide runs on the
+  // MUFU pipe: six of them per cell and level made this kernel XU-bound, profiles/r01g):
+  // 6 1/(rhow adzw)  7 dx/(dz adzw)  8 1/(rho adz)  9 1/adz  10 1/adzw
+  for (int q = tid; q < p.nz * CT; q += P) {
+    const int k = q / CT + 1, ln = q - (k - 1) * CT;
+    const int o = tile * p.nzp * CT + k * CT + ln, so = k * CT + ln;
+    const double dzq = p.dz[tile * CT + ln];
+    const double rhow = p.rhow[o], adzw = p.adzw[o], rho = p.rho[o], adz = p.adz[o];
+    sprof[6 * npf + so] = 1. / (rhow * adzw);
+    sprof[7 * npf + so] = p.dx / (dzq * adzw);
+    sprof[8 * npf + so] = (k <= nzm) ? 1. / (rho * adz) : 0.;
+    sprof[9 * npf + so] = (k <= nzm) ? 1. / adz : 0.;
+    sprof[10 * npf + so] = 1. / adzw;
+  }
   pipe.init(smraw, P, tid);
+#define S_IRW(k) sprof[6 * npf + (k)*CT + lane]
+#define S_DXZ(k) sprof[7 * npf + (k)*CT + lane]
+#define S_IRS(k) sprof[8 * npf + (k)*CT + lane]
+#define S_IADZ(k) sprof[9 * npf + (k)*CT + lane]
+#define S_IADZW(k) sprof[10 * npf + (k)*CT + lane]
 #define S_RHO(k) sprof[0 * npf + (k)*CT + lane]
 #define S_ADZ(k) sprof[1 * npf + (k)*CT + lane]
 #define S_RHOW(k) sprof[2 * npf + (k)*CT + lane]
@@ -351,14 +381,14 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_p3_mom(CrmP p) {
     // contribution to dwdt(kc) from this level (applied next iteration, in reference order)
     double dwh_adv_next, dwh_dif_next;
     {
-      const double irho = 1. / (S_RHOW(kc) * S_ADZW(kc));
+      const double irho = S_IRW(kc);
       const double rho_u = S_RHO(kcu), adz_u = S_ADZ(kcu);
       const double ucu_i = U_u[tid], ucu_ip = U_u[tp1];
       double fw1 = dx25 * (u_i * rho_k * adz_k + ucu_i * rho_u * adz_u) * (w_kc_m + w_kc);
       double fw2 = dx25 * (u_ip * rho_k * adz_k + ucu_ip * rho_u * adz_u) * (w_kc + w_kc_p);
       dwh_adv_next = irho * (fw2 - fw1);
       // diffuse_mom2D horizontal part: fw(i,k), fw(i-1,k)
-      const double dxz = dx / (dz * S_ADZW(kc));
+      const double dxz = S_DXZ(kc);
       const double rdx251 = rdx25 * S_GRDX(k);
       const double tk_i = TK_k[tid], tk_ip = TK_k[tp1], tk_im = TK_k[tm1];
       const double tku_i = TK_u[tid], tku_ip = TK_u[tp1], tku_im = TK_u[tm1];
@@ -375,7 +405,7 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_p3_mom(CrmP p) {
       const double www = rhoi * (w_kc + w_kc_m);
       fuz_kc = www * (U_c[tid] + u_i);
     }
-    const double rhoi_s = 1. / (rho_k * adz_k);
+    const double rhoi_s = S_IRS(k);
     du = du - (fuz_kc - fuz_k) * rhoi_s;
     const double fwz_k = dz25 * (w_kc * S_RHOW(kc) + w_k * S_RHOW(k)) * (w_kc + w_k);
     // ---- diffuse_mom2D: horizontal part for u
@@ -390,7 +420,7 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_p3_mom(CrmP p) {
     double fuv_kc = 0., fwv_kc;
     if (k <= nzm - 1) {
       const double rdz2 = rdz * rdz * S_GRDZ(k), rdz25 = 0.25 * rdz2;
-      const double iadz = 1. / adz_k, iadzw = 1. / S_ADZW(kc);
+      const double iadz = S_IADZ(k), iadzw = S_IADZW(kc);
       double tkz = rdz2 * tk_i;
       fwv_kc = -2. * tkz * (w_kc - w_k) * rho_k * iadz;
       tkz = rdz25 * (tk_i + tk_im + TK_c[tid] + TK_c[tm1]);
@@ -406,7 +436,7 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_p3_mom(CrmP p) {
     if (k >= 2) {
       double dw = pipe.plane(4, k)[tid];
       dw = dw - dwh_adv;
-      const double rhoi_w = 1. / (S_RHOW(k) * S_ADZW(k));
+      const double rhoi_w = S_IRW(k);
       dw = dw - (fwz_k - fwz_km1) * rhoi_w;
       dw = dw - dwh_dif;
       dw = dw - (fwv_kc - fwv_k) * rhoi_w;
@@ -426,6 +456,11 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_p3_mom(CrmP p) {
 #undef S_ADZW
 #undef S_GRDX
 #undef S_GRDZ
+#undef S_IRW
+#undef S_DXZ
+#undef S_IRS
+#undef S_IADZ
+#undef S_IADZW
 }
 
 // pressure.F90:165-237 coefficients for one (CRM, level)
@@ -477,7 +512,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_press_alfa(CrmP p) {
 // press_rhs.F90:80-102 + forward transform + forward sweep (pressure.F90:202-233).
 // u, w and the three AB levels of dudt, dwdt stream through a 3-stage TMA plane ring (levels k, k+1 resident).
 #define CRM_P4_SMEM(P, CT, nzp, NX) \
-  (CRM_PIPE_BYTES(8, 3, P) + CRM_PROF_BYTES(5, nzp, CT) + (size_t)((P) + ((NX) + 2) * (CT) + ((NX) / 4 + 1) * 4 * (CT)) * 8)
+  (CRM_PIPE_BYTES(8, 3, P) + CRM_PROF_BYTES(7, nzp, CT) + (size_t)((P) + ((NX) + 2) * (CT) + ((NX) / 4 + 1) * 4 * (CT)) * 8)
 template <int NX, int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P, 3) k_p4_press_fwd(CrmP p) {
   constexpr int H = NX / 2, Q = NX / 4;
@@ -489,13 +524,23 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_p4_press_fwd(CrmP p) {
   R.src[0] = p.u + fb; R.src[1] = p.w + fb; R.src[2] = p.du_a + fb; R.src[3] = p.dw_a + fb; R.src[4] = p.du_b + fb; R.src[5] = p.dw_b + fb;
   R.src[6] = p.du_c + fb; R.src[7] = p.dw_c + fb;
   double *sprof = (double *)(smraw + CRM_PIPE_BYTES(8, 3, P));
-  double *sx = sprof + 5 * npf;            // P
+  double *sx = sprof + 7 * npf;            // P
   double *sE = sx + P;                     // (H+1)*CT : E[0..H]
   double *sO = sE + (H + 1) * CT;          // H*CT     : O[1..H-1] (O[0] unused)
   double *sF = sO + H * CT;                // (Q+1)*4*CT : [j][type][lane], type 0=EP 1=EM 2=OM 3=OP
   {
     const double *const g[5] = {p.rho, p.adz, p.rhow, p.tri_a, p.tri_c};
     stage_profiles<5>(sprof, g, tile, p.nzp, CT, tid, P);
+  }
+  // slots 5, 6: rhow(k+1)/rho/(adz*dz) and rhow(k)/rho/(adz*dz) (press_rhs.F90:56-70), once per block instead of three
+  // divisions per cell and level
+  for (int q = tid; q < nzm * CT; q += P) {
+    const int k = q / CT + 1, ln = q - (k - 1) * CT;
+    const int o = tile * p.nzp * CT + k * CT + ln, so = k * CT + ln;
+    const double rho_ = p.rho[o];
+    const double rdzz_ = 1. / (p.adz[o] * p.dz[tile * CT + ln]);
+    sprof[5 * npf + so] = p.rhow[o + CT] / rho_ * rdzz_;
+    sprof[6 * npf + so] = p.rhow[o] / rho_ * rdzz_;
   }
 #define SPF(r, k) sprof[(r) * npf + (k) * CT + lane]
   R.init(smraw, P, tid);
@@ -518,8 +563,7 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_p4_press_fwd(CrmP p) {
     __syncthreads();   // previous level's smem reads are complete; ring slot of level k-1 is free
     CRM_PIPE_STEP(R, k, nz, 2, 1)
     const double rho = SPF(0, k);
-    const double rdzz = 1. / (SPF(1, k) * dz);
-    const double rup = SPF(2, kc) / rho * rdzz, rdn = SPF(2, k) / rho * rdzz;
+    const double rup = SPF(5, k), rdn = SPF(6, k);
     double rhs = (rdx * (R.plane(0, k)[tp1] - R.plane(0, k)[tid]) + (R.plane(1, kc)[tid] * rup - R.plane(1, k)[tid] * rdn)) * dta +
                  (rdx * (R.plane(2, k)[tp1] - R.plane(2, k)[tid]) + (R.plane(3, kc)[tid] * rup - R.plane(3, k)[tid] * rdn)) +
                  btat * (rdx * (R.plane(4, k)[tp1] - R.plane(4, k)[tid]) + (R.plane(5, kc)[tid] * rup - R.plane(5, k)[tid] * rdn)) +
@@ -590,6 +634,8 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p5_press_bwd(CrmP p) {
   {
     const double *const g[3] = {p.rho, p.rhow, p.adzw};
     stage_profiles<3>(sprof, g, tile, p.nzp, CT, tid, P);
+    // slot 2 becomes 1/(dz*adzw) (press_grad.F90:38), evaluated once per block (each thread converts the entries it staged)
+    for (int q = tid; q < p.nzp * CT; q += P) sprof[2 * (p.nzp * CT) + q] = 1. / (p.dz[tile * CT + (q % CT)] * sprof[2 * (p.nzp * CT) + q]);
   }
 #define SPF(r, k) sprof[(r) * npf + (k) * CT + lane]
   for (int q = tid; q < 4 * (Q + 1) * CT; q += P) part[q] = 0.;   // tasks that do not exist (Se, So at j = 0; Co, Se at j = Q) stay zero
@@ -652,7 +698,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p5_press_bwd(CrmP p) {
     // w at level k+1 (needs p(k+1) - p(k))
     if (k + 1 <= nzm) {
       const int kw = k + 1;
-      const double rdzw = 1. / (dz * SPF(2, kw));
+      const double rdzw = SPF(2, kw);
       double dw = R.plane(6, kw)[tid] - (p_kp1 - pk) * rdzw;
       F3(p.dw_a, kw) = dw;
       const double w = R.plane(7, kw)[tid];

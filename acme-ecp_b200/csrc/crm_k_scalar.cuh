@@ -28,6 +28,14 @@ __device__ __forceinline__ double min3(double a, double b, double c) { return dm
 // body below it handles the first two and the last levels.
 #define CRM_MP_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(3, 6, P) + CRM_PROF_BYTES(5, nzp, CT) + (size_t)(9 * (P) + 2 * CRM_RED_DOUBLES(2, P, CT)) * 8)
 __device__ __forceinline__ double upw_flux(double v, double below, double above) { return v * (v > 0. ? below : above); }
+// The two FCT ratios of a cell, q1 = n1/d1 and q2 = n2/d2 (d >= eps > 0), with ONE FP64 division (it runs on the MUFU
+// pipe, which bounded these kernels): both quotients over the common denominator d1*d2 (>= 1e-20).  A zero numerator
+// gives exactly +0 without dividing (precipitation-free or locally uniform air).  The quotients agree with the literal
+// divisions to 2 ulp; they only act through min(1, .) limiters.
+__device__ __forceinline__ void ratio2(double n1, double d1, double n2, double d2, double &q1, double &q2) {
+  q1 = 0.; q2 = 0.;
+  if (n1 != 0. || n2 != 0.) { const double r = 1. / (d1 * d2); q1 = n1 * d2 * r; q2 = n2 * d1 * r; }
+}
 template <int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P, 3) k_mpdata(CrmP p, double *f, double *fadv, double *flux, int stats, const int *ktop) {
   CRM_TILE_SETUP_T(NXT)
@@ -154,8 +162,8 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_mpdata(CrmP p, double *f, doub
       const double WWk = WW_prev;                                  // WW(kb_)
       const double WWkc = (kb_ == nzm) ? WW_prev : WW_ka;           // WW(min(nzm,kb_+1))
       // zero numerators give exactly +0 (denominators >= eps > 0): no division where the field is locally uniform (qp = 0 ...)
-      mx_new = (mxr == F1c) ? 0. : rho * (mxr - F1c) / (pn_(UUp) + pp_(UU) + iadz * (pn_(WWkc) + pp_(WWk)) + eps);
-      mn_new = (F1c == mnr) ? 0. : rho * (F1c - mnr) / (pp_(UUp) + pn_(UU) + iadz * (pp_(WWkc) + pn_(WWk)) + eps);
+      ratio2(rho * (mxr - F1c), pn_(UUp) + pp_(UU) + iadz * (pn_(WWkc) + pp_(WWk)) + eps,
+             rho * (F1c - mnr), pp_(UUp) + pn_(UU) + iadz * (pp_(WWkc) + pn_(WWk)) + eps, mx_new, mn_new);
       smx[(kb_ & 1) * P + tid] = mx_new;
       smn[(kb_ & 1) * P + tid] = mn_new;
     }
@@ -249,8 +257,9 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_mpdata(CrmP p, double *f, doub
     __syncthreads();   // (2)
     const double UUp = sUU[tp1];
     const double rho_b = pr[-2 * CT], iadz_b = pr[-4 * CT];
-    const double mx_new = (mxr == c_F1b) ? 0. : rho_b * (mxr - c_F1b) / (pn_(UUp) + pp_(UU) + iadz_b * (pn_(WW_ka) + pp_(WW_prev)) + eps);
-    const double mn_new = (c_F1b == mnr) ? 0. : rho_b * (c_F1b - mnr) / (pp_(UUp) + pn_(UU) + iadz_b * (pp_(WW_ka) + pn_(WW_prev)) + eps);
+    double mx_new, mn_new;
+    ratio2(rho_b * (mxr - c_F1b), pn_(UUp) + pp_(UU) + iadz_b * (pn_(WW_ka) + pp_(WW_prev)) + eps,
+           rho_b * (c_F1b - mnr), pp_(UUp) + pn_(UU) + iadz_b * (pp_(WW_ka) + pn_(WW_prev)) + eps, mx_new, mn_new);
     smx[X_B * P + tid] = mx_new;
     smn[X_B * P + tid] = mn_new;
     __syncthreads();   // (3)
@@ -512,8 +521,7 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_precip_b(CrmP p, int iprec0, i
         const double wwc = (k2 == nzm) ? ww1 : ww2;   // www(min(nzm,k2+1))
         const double ra = S_RA(k2);
         // a zero numerator gives exactly +0 (the denominators are >= eps > 0): skip the two divisions in precipitation-free air
-        mxn1 = (mx == tq1) ? 0. : ra * (mx - tq1) / (pn_(wwc) + pp_(ww1) + eps);
-        mnn1 = (tq1 == mn) ? 0. : ra * (tq1 - mn) / (pp_(wwc) + pn_(ww1) + eps);
+        ratio2(ra * (mx - tq1), pn_(wwc) + pp_(ww1) + eps, ra * (tq1 - mn), pp_(wwc) + pn_(ww1) + eps, mxn1, mnn1);
       } else { mxn1 = 0.; mnn1 = 0.; }
       // ---- limited flux at k2: fz(k2) + pp(www)*min(1,mx(k2),mn(kb)) - pn(www)*min(1,mx(kb),mn(k2))
       fzl0 = fzl1;
@@ -579,6 +587,13 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p7_diffuse(CrmP p) {
   {
     const double *const g[6] = {p.grdf_x, p.adz, p.rho, p.rhow, p.adzw, p.grdf_z};
     stage_profiles<6>(sprof, g, tile, p.nzp, CT, tid, P);
+    // slot 1 becomes 1/(adz*rho), slot 3 becomes rhow/adzw (diffuse_scalar2D.F90:96-118): once per block instead of two
+    // divisions per cell and level (each thread converts the entries it staged)
+    const int n = p.nzp * CT;
+    for (int q = tid; q < n; q += P) {
+      sprof[n + q] = 1. / (sprof[n + q] * sprof[2 * n + q]);
+      sprof[3 * n + q] = sprof[3 * n + q] / sprof[4 * n + q];
+    }
   }
   pipe.init(smraw, P, tid);   // (barrier: profiles visible)
 #define SPF(r, k) sprof[(r) * npf + (k) * CT + lane]
@@ -596,10 +611,10 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p7_diffuse(CrmP p) {
     const double *tkh_k = pipe.plane(0, k), *tkh_c = pipe.plane(0, k + 1);
     const double tkh_i = tkh_k[tid], tkh_m = tkh_k[tm1], tkh_p = tkh_k[tp1];
     const double rdx5 = 0.5 * rdx2 * SPF(0, k);
-    const double rhoi2 = 1. / (SPF(1, k) * SPF(2, k));
+    const double rhoi2 = SPF(1, k);
     double tkz = 0., rhoi = 0.;
     if (k <= nzm - 1) {
-      rhoi = SPF(3, k + 1) / SPF(4, k + 1);
+      rhoi = SPF(3, k + 1);
       const double rdz5 = 0.5 * rdz2 * SPF(5, k);
       tkz = rdz5 * (tkh_i + tkh_c[tid]);
     }
@@ -634,8 +649,13 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p7_diffuse(CrmP p) {
 // mixing weight om forced to exactly 1 or 0 outside the mixed range: om*qsatw + (1-om)*qsati is then bit-identical to
 // the single-phase value (x*1 + y*0), the two Flatau polynomials are independent Horner chains that overlap in the
 // FP64 pipe, and the warp no longer diverges three ways per Newton iteration.
+// One FP64 division for the pair (the divide runs on the MUFU pipe): both saturation mixing ratios over the common
+// denominator max(esw,p-esw)*max(esi,p-esi); agrees with qsatw_crm/qsati_crm (sat.F90:34-44, 96-105) to 2 ulp.
 __device__ __forceinline__ double cloud_qsat_mix(double tabs1, double pres, double om) {
-  return om * qsatw_crm(tabs1, pres) + (1. - om) * qsati_crm(tabs1, pres);
+  const double esw = esatw_crm(tabs1), esi = esati_crm(tabs1);
+  const double dw = dmax(esw, pres - esw), di = dmax(esi, pres - esi);
+  const double r = R4(0.622) / (dw * di);
+  return om * (esw * di * r) + (1. - om) * (esi * dw * r);
 }
 // cloud_init: everything before the saturation test (cloud.F90:40-70); cloud_newton: the iteration for a saturated cell
 // (cloud.F90:75-105).  k_p8_micro runs the first on every cell and the second only on the compacted saturated cells.
@@ -658,13 +678,14 @@ __device__ __forceinline__ double cloud_newton(double tabs, double pres, double 
   const double ap = 1. / (CRM_TPRMAX - CRM_TPRMIN), bp = CRM_TPRMIN * ap;
   int niter = 0;
   double dtabs = R4(100.), dqsat = 0.;
+  const double c622_ip = R4(0.622) / pres;
   while (fabs(dtabs) > R4(0.01) && niter < 10) {
     const bool liq = tabs1 >= CRM_TBGMAX, ice = tabs1 <= CRM_TBGMIN;
     const double omn = liq ? 1. : (ice ? 0. : an * tabs1 - bn);
     const double lstarn = liq ? CRM_FAC_COND : (ice ? CRM_FAC_SUB : CRM_FAC_COND + (1. - omn) * CRM_FAC_FUS);
     const double dlstarn = (liq || ice) ? 0. : an * CRM_FAC_FUS;
     qsatt = cloud_qsat_mix(tabs1, pres, omn);
-    dqsat = omn * dtqsatw_crm(tabs1, pres) + (1. - omn) * dtqsati_crm(tabs1, pres);
+    dqsat = (omn * dtesatw_crm(tabs1) + (1. - omn) * dtesati_crm(tabs1)) * c622_ip;   // dtqsat = 0.622*dtesat/p (sat.F90:67-74, 129-136)
     const bool pliq = tabs1 >= CRM_TPRMAX, pice = tabs1 <= CRM_TPRMIN;
     const double lstarp = pliq ? CRM_FAC_COND : (pice ? CRM_FAC_SUB : CRM_FAC_COND + (1. - (ap * tabs1 - bp)) * CRM_FAC_FUS);
     const double dlstarp = (pliq || pice) ? 0. : ap * CRM_FAC_FUS;
@@ -715,8 +736,12 @@ __device__ inline void precip_proc_cell(const CrmP &p, int pb, int CT, int k, do
         accrcg = PF(p.accrgc, k) * tmp;
         accrig = PF(p.accrgi, k) * tmp;
       }
-      qcc = (qcc + dtn * autor * CRM_QCW0) / (1. + dtn * (accrr + accrcs + accrcg + autor));
-      qii = (qii + dtn * autos * CRM_QCI0) / (1. + dtn * (accris + accrig + autos));
+      {   // the two quotients of precip_proc.F90:94-95 over their common denominator: one division
+        const double d1 = 1. + dtn * (accrr + accrcs + accrcg + autor), d2 = 1. + dtn * (accris + accrig + autos);
+        const double r = 1. / (d1 * d2);
+        qcc = (qcc + dtn * autor * CRM_QCW0) * d2 * r;
+        qii = (qii + dtn * autos * CRM_QCI0) * d1 * r;
+      }
       double dq = dtn * (accrr * qcc + autor * (qcc - CRM_QCW0) + (accris + accrig) * qii + (accrcs + accrcg) * qcc + autos * (qii - CRM_QCI0));
       dq = dmin(dq, qn);
       qp = qp + dq;
