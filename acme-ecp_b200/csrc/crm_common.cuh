@@ -302,6 +302,15 @@ __device__ __forceinline__ double qsati_crm(double t, double p) { double es = es
 __device__ __forceinline__ double dtqsatw_crm(double t, double p) { return R4(0.622) * dtesatw_crm(t) / p; }
 __device__ __forceinline__ double dtqsati_crm(double t, double p) { return R4(0.622) * dtesati_crm(t) / p; }
 
+// One FP64 division for the pair (the divide runs on the MUFU pipe): both saturation mixing ratios over the common
+// denominator max(esw,p-esw)*max(esi,p-esi); agrees with qsatw_crm/qsati_crm (sat.F90:34-44, 96-105) to 2 ulp.
+__device__ __forceinline__ double qsat_mix(double tabs1, double pres, double om) {
+  const double esw = esatw_crm(tabs1), esi = esati_crm(tabs1);
+  const double dw = dmax(esw, pres - esw), di = dmax(esi, pres - esi);
+  const double r = R4(0.622) / (dw * di);
+  return om * (esw * di * r) + (1. - om) * (esi * dw * r);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Block reductions over x for each lane.  tid = i*CT + lane with CT a power of two <= 32 and P a multiple of 32, so
 // every warp holds 32/CT consecutive i for each lane: xor-shuffles over the i-bits reduce inside the warp (fixed

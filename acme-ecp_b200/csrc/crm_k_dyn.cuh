@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p1_forcing(CrmP p) {
   __syncthreads();
   const int kd0 = s_kd0;   // lowest level at which any CRM of the tile is in the sponge
   const int nxy = nx_ * p.ny;
+  const double inxy = 1. / (double)nxy;
   const int irad = i / (nx_ / p.nx_rad);
   const long long rb = ((long long)tile * nzm) * (p.nx_rad * CT) + irad * CT + lane;
   double expr_km1 = 0.;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p1_forcing(CrmP p) {
     // --- damping
     if (k >= kd0) {
       const double u = A.plane(7, k)[tid];
-      double v[2] = {u / nxy, t / nxy};
+      double v[2] = {u * inxy, t * inxy};   // == u/nxy, t/nxy exactly: nx*ny is a power of two
       block_sum<2>(v, tid, P, CT, red);
       if (k >= nzm - ndamp) {
         const double tau = SPF(10, k);
@@ -264,12 +265,12 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
       if (qctot > 0.) {
         const double omn = (qcl_c + qcl_b) / (qctot + R4(1.e-20));
         const double presi = SPF(6, k);
-        const double qsat_check = omn * qsatw_crm(tabs_interface, presi) + (1. - omn) * qsati_crm(tabs_interface, presi);
+        const double qsat_check = qsat_mix(tabs_interface, presi, omn);   // omn*qsatw + (1-omn)*qsati with one division
         if (qtot_interface > qsat_check) {
           const double lstarn = CRM_FAC_COND + (1. - omn) * CRM_FAC_FUS;
           tabs_interface = 0.5 * (tabs_c + tabs_b);
-          const double dqsat = omn * dtqsatw_crm(tabs_interface, presi) + (1. - omn) * dtqsati_crm(tabs_interface, presi);
-          const double qsatt = omn * qsatw_crm(tabs_interface, presi) + (1. - omn) * qsati_crm(tabs_interface, presi);
+          const double dqsat = (omn * dtesatw_crm(tabs_interface) + (1. - omn) * dtesati_crm(tabs_interface)) * (R4(0.622) / presi);
+          const double qsatt = qsat_mix(tabs_interface, presi, omn);
           bbb = 1. + CRM_EPSV * qsatt + qsatt - qtot_interface - qp_interface + R4(1.61) * tabs_interface * dqsat;
           bbb = bbb / (1. + lstarn * dqsat);
           buoy_sgs = betdz * (bbb * (t_c - t_b) +

@@ -347,7 +347,7 @@ __device__ __forceinline__ double term_vel_qp(const MicroScalars &m, double qplo
 // microphysics.F90:578-640: fall speed of every cell + batch-global prec_cfl.  qp, tabs through a 3-stage TMA ring.
 // Also records, per tile, the highest level that holds any precipitation (kprec): above it the sedimentation of
 // k_precip_b is the identity and is skipped.
-#define CRM_PRECIPA_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(2, 3, P) + CRM_PROF_BYTES(3, nzp, CT) + (size_t)(P) * 8)
+#define CRM_PRECIPA_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(2, 3, P) + CRM_PROF_BYTES(4, nzp, CT) + (size_t)(P) * 8)
 template <int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P) k_precip_a(CrmP p) {
   CRM_TILE_SETUP_T(NXT)
@@ -358,10 +358,20 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_precip_a(CrmP p) {
   PlanePipe<2, 3> R;
   R.src[0] = p.qp + fb; R.src[1] = p.tabs + fb;
   double *sprof = (double *)(smraw + CRM_PIPE_BYTES(2, 3, P));
-  double *red = sprof + 3 * npf;
+  double *red = sprof + 4 * npf;
   {
     const double *const g[3] = {p.rho, p.adz, p.rhow};
     stage_profiles<3>(sprof, g, tile, p.nzp, CT, tid, P);
+    // slot 0 becomes sqrt(1.29/rho), slot 1 becomes 1/wmax = 1/(dz*adz/dtn), slot 2 rhow*dtn/dz (microphysics.F90:583-640):
+    // once per block instead of per cell (each thread converts the entries it staged)
+    const int n = p.nzp * CT;
+    for (int q = tid; q < n; q += P) {
+      const double dzq = p.dz[tile * CT + (q % CT)];
+      sprof[3 * n + q] = sprof[q];
+      sprof[q] = sqrt(R4(1.29) / sprof[q]);
+      sprof[n + q] = 1. / (dzq * sprof[n + q] / p.dtn);
+      sprof[2 * n + q] = sprof[2 * n + q] * p.dtn / dzq;
+    }
   }
   if (tid == 0) s_kt = 0;
   R.init(smraw, P, tid);
@@ -370,8 +380,6 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_precip_a(CrmP p) {
     return;
   }
   CRM_PIPE_PROLOGUE(R, nzm, 2, 0)
-  const double dz = p.dz[cb];
-  const double idtn = 1. / p.dtn;
   double cfl = 0.;
   int kt = 0;
   for (int k = 1; k <= nzm; k++) {
@@ -381,14 +389,13 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_precip_a(CrmP p) {
     if (q != 0.) kt = k;
     double wpv = 0.;
     if (q > CRM_QP_THRESHOLD) {
-      const double rho = sprof[k * CT + lane];
-      const double rhofac = sqrt(R4(1.29) / rho);
+      const double rho = sprof[3 * npf + k * CT + lane];
+      const double rhofac = sprof[k * CT + lane];
       const int kb = imax(1, k - 1);
-      const double wmax = dz * sprof[npf + kb * CT + lane] * idtn;
       wpv = rhofac * term_vel_qp(p.ms, q, rho, R.plane(1, k)[tid]);
-      cfl = dmax(cfl, wpv / wmax);
+      cfl = dmax(cfl, wpv * sprof[npf + kb * CT + lane]);   // slot 1 holds 1/wmax = dtn/(dz*adz)
     }
-    F3(p.wp, k) = -wpv * sprof[2 * npf + k * CT + lane] * p.dtn / dz;
+    F3(p.wp, k) = -wpv * sprof[2 * npf + k * CT + lane];
   }
   if (kt > 0) atomicMax(&s_kt, kt);
   const double m = block_max_all(cfl, tid, P, red);
@@ -649,14 +656,6 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p7_diffuse(CrmP p) {
 // mixing weight om forced to exactly 1 or 0 outside the mixed range: om*qsatw + (1-om)*qsati is then bit-identical to
 // the single-phase value (x*1 + y*0), the two Flatau polynomials are independent Horner chains that overlap in the
 // FP64 pipe, and the warp no longer diverges three ways per Newton iteration.
-// One FP64 division for the pair (the divide runs on the MUFU pipe): both saturation mixing ratios over the common
-// denominator max(esw,p-esw)*max(esi,p-esi); agrees with qsatw_crm/qsati_crm (sat.F90:34-44, 96-105) to 2 ulp.
-__device__ __forceinline__ double cloud_qsat_mix(double tabs1, double pres, double om) {
-  const double esw = esatw_crm(tabs1), esi = esati_crm(tabs1);
-  const double dw = dmax(esw, pres - esw), di = dmax(esi, pres - esi);
-  const double r = R4(0.622) / (dw * di);
-  return om * (esw * di * r) + (1. - om) * (esi * dw * r);
-}
 // cloud_init: everything before the saturation test (cloud.F90:40-70); cloud_newton: the iteration for a saturated cell
 // (cloud.F90:75-105).  k_p8_micro runs the first on every cell and the second only on the compacted saturated cells.
 __device__ __forceinline__ void cloud_init(double t, double gamaz, double pres, double &q, double qp, double &tabs, double &tabs1, double &qsatt) {
@@ -670,7 +669,7 @@ __device__ __forceinline__ void cloud_init(double t, double gamaz, double pres, 
   if (tabs1 >= CRM_TBGMAX) { tabs1 = tabs + CRM_FAC_COND * qp; om = 1.; }
   else if (tabs1 <= CRM_TBGMIN) { tabs1 = tabs + CRM_FAC_SUB * qp; om = 0.; }
   else om = an * tabs1 - bn;
-  qsatt = cloud_qsat_mix(tabs1, pres, om);
+  qsatt = qsat_mix(tabs1, pres, om);
 }
 // requires q > qsatt on entry; returns qn, updates tabs1
 __device__ __forceinline__ double cloud_newton(double tabs, double pres, double q, double qp, double &tabs1, double qsatt) {
@@ -684,7 +683,7 @@ __device__ __forceinline__ double cloud_newton(double tabs, double pres, double 
     const double omn = liq ? 1. : (ice ? 0. : an * tabs1 - bn);
     const double lstarn = liq ? CRM_FAC_COND : (ice ? CRM_FAC_SUB : CRM_FAC_COND + (1. - omn) * CRM_FAC_FUS);
     const double dlstarn = (liq || ice) ? 0. : an * CRM_FAC_FUS;
-    qsatt = cloud_qsat_mix(tabs1, pres, omn);
+    qsatt = qsat_mix(tabs1, pres, omn);
     dqsat = (omn * dtesatw_crm(tabs1) + (1. - omn) * dtesati_crm(tabs1)) * c622_ip;   // dtqsat = 0.622*dtesat/p (sat.F90:67-74, 129-136)
     const bool pliq = tabs1 >= CRM_TPRMAX, pice = tabs1 <= CRM_TPRMIN;
     const double lstarp = pliq ? CRM_FAC_COND : (pice ? CRM_FAC_SUB : CRM_FAC_COND + (1. - (ap * tabs1 - bp)) * CRM_FAC_FUS);
@@ -750,8 +749,9 @@ __device__ inline void precip_proc_cell(const CrmP &p, int pb, int CT, int k, do
       dsrc = dq;
     } else if (qp > CRM_QP_THRESHOLD && qn == 0.) {
       double qsatt = 0.;
-      if (omn > R4(0.001)) qsatt = qsatt + omn * qsatw_crm(tabs, pres);
-      if (omn < R4(0.999)) qsatt = qsatt + (1. - omn) * qsati_crm(tabs, pres);
+      if (omn > R4(0.001) && omn < R4(0.999)) qsatt = qsat_mix(tabs, pres, omn);   // 0 + omn*qsatw + (1-omn)*qsati, one division
+      else if (omn > R4(0.001)) qsatt = qsatt + omn * qsatw_crm(tabs, pres);
+      else qsatt = qsatt + (1. - omn) * qsati_crm(tabs, pres);
       double dq = 0.;
       if (omp > R4(0.001)) {
         const double qrr = qp * omp;

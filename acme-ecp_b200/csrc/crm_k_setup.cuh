@@ -295,7 +295,7 @@ __global__ void k_setperturb(CrmP p, const double *rnd) {
 // kurant.F90:9-64 + sgs.F90:329-372.  max over i commutes with the per-level scaling, so every thread folds its own
 // column and only one block max + one atomicMax on the (non-negative) double bit pattern are needed.
 // u, w, tkh stream through a TMA plane ring (4 stages, levels k and k+1 resident).
-#define CRM_KURANT_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(3, 4, P) + CRM_PROF_BYTES(3, nzp, CT) + (size_t)(P) * 8)
+#define CRM_KURANT_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(3, 4, P) + CRM_PROF_BYTES(4, nzp, CT) + (size_t)(P) * 8)
 template <int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P) k_kurant(CrmP p) {
   CRM_TILE_SETUP_T(NXT)
@@ -304,29 +304,45 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_kurant(CrmP p) {
   PlanePipe<3, 4> R;
   R.src[0] = p.u + fb; R.src[1] = p.w + fb; R.src[2] = p.tkh + fb;
   double *sprof = (double *)(smraw + CRM_PIPE_BYTES(3, 4, P));
-  double *red = sprof + 3 * npf;
+  double *red = sprof + 4 * npf;
   {
     const double *const g[3] = {p.adzw, p.grdf_z, p.grdf_x};
     stage_profiles<3>(sprof, g, tile, p.nzp, CT, tid, P);
+    for (int q = tid; q < npf; q += P) sprof[3 * npf + q] = 1. / (p.dz[tile * CT + (q % CT)] * sprof[q]);   // slot 3: 1/(dz*adzw)
   }
   R.init(smraw, P, tid);
   CRM_PIPE_PROLOGUE(R, nz, 3, 1)
   const double idx = 1. / p.dx;
   const double sq = sqrt(idx * idx);
   const double dz = p.dz[cb];
+  const double idx2 = 1. / (p.dx * p.dx);
   double cfl = 0.;
+  // The three quotients x*dt/c(k) run on the MUFU pipe; the batch maximum only needs them for candidates that can raise
+  // this thread's running maximum.  Each candidate is first estimated with the reciprocal of c(k) (one multiply, 2 ulp);
+  // the exact reference expression is evaluated only when the estimate comes within 1e-12 of the best estimate so far,
+  // so the maximum is bit-identical to dividing every time (ncycle depends on it).
+  double best = 0.;
   double wk = fabs(R.plane(1, 1)[tid]);
   for (int k = 1; k <= nzm; k++) {
     __syncthreads();
     CRM_PIPE_STEP(R, k, nz, 3, 1)
     double wk1 = fabs(R.plane(1, k + 1)[tid]);
     double u = R.plane(0, k)[tid];
-    double uh = sqrt(u * u);
+    double uh = fabs(u);   // == sqrt(u*u) of kurant.F90:40 with v = 0
     double adzw = sprof[0 * npf + k * CT + lane];
-    cfl = dmax(cfl, dmax(uh * p.dt * sq, dmax(wk, wk1) * p.dt / (dz * adzw)));
+    cfl = dmax(cfl, uh * p.dt * sq);
     double tkh = R.plane(2, k)[tid];
     double dzw = dz * adzw;
-    cfl = dmax(cfl, dmax(0.5 * tkh * sprof[1 * npf + k * CT + lane] * p.dt / (dzw * dzw), 0.5 * tkh * sprof[2 * npf + k * CT + lane] * p.dt / (p.dx * p.dx)));
+    const double idzw = sprof[3 * npf + k * CT + lane];
+    const double wm = dmax(wk, wk1);
+    const double e1 = wm * p.dt * idzw;
+    const double a2 = 0.5 * tkh * sprof[1 * npf + k * CT + lane] * p.dt, a3 = 0.5 * tkh * sprof[2 * npf + k * CT + lane] * p.dt;
+    const double e2 = a2 * idzw * idzw, e3 = a3 * idx2;
+    const double em = dmax(e1, dmax(e2, e3));
+    if (em >= best * (1. - 1.e-12)) {
+      cfl = dmax(cfl, dmax(wm * p.dt / (dz * adzw), dmax(a2 / (dzw * dzw), a3 / (p.dx * p.dx))));
+      best = dmax(best, em);
+    }
     wk = wk1;
   }
   double m = block_max_all(cfl, tid, P, red);
