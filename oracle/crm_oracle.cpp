@@ -644,6 +644,14 @@ extern "C" void crm_oracle_rng(int seed, int n, double *out) {
   RngMT r; r.set_seed(seed);
   for (int i = 0; i < n; i++) out[i] = r.gen_rand();
 }
+// torchrun exports OMP_NUM_THREADS=1 to every rank: the reference arm of bench.py asks for all host threads explicitly
+extern "C" void crm_oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 extern "C" int crm_oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
