@@ -216,3 +216,11 @@ def test_partition_invariance_property_full_width():
             assert err < 1e-11, (n, r, err)
     err, _ = cm.rel_err(out_a.sltend[:dims.ncrms], out_b.sltend[1 + (rep - 1) * dims.ncrms:], dims.ncrms)
     assert err < 1e-10
+
+
+def test_cfg1_full_batch_one_gcm_step():
+    """BASELINE config 1 exactly: 866 columns, 2-D CRM 32x1x28 (L30, dx 4 km, crm_dt 20 s), one GCM step of 1800 s
+    (nstop 90), replayed through the C ABI and the oracle from the same spun-up state."""
+    dims = cm.pkg.CrmDims(ncrms=866, nx=32, ny=1, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=1800.0, igstep=3, nx_rad=8)
+    ro, rg = _check(dims, 45, 1e-6)
+    assert rg[3]["nstop"] == 90
