@@ -224,3 +224,10 @@ def test_cfg1_full_batch_one_gcm_step():
     dims = cm.pkg.CrmDims(ncrms=866, nx=32, ny=1, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=1800.0, igstep=3, nx_rad=8)
     ro, rg = _check(dims, 45, 1e-6)
     assert rg[3]["nstop"] == 90
+
+
+@pytest.mark.parametrize("nx,ncrms", [(128, 7), (256, 3)])
+def test_wide_crm_geometries(nx, ncrms):
+    # nx = 128 -> CRM tile of 2 columns, nx = 256 -> one CRM per block (runtime-geometry kernel variants, 64/128-point FFT folds)
+    dims = cm.small_dims(ncrms=ncrms, nx=nx, nsteps=4)
+    _check(dims, 40, 1e-9)
