@@ -135,6 +135,18 @@ int copy_rows(void *dst, int ld_dst, const void *src, int ld_src, int ncrms, siz
 
 extern "C" int crm_b200_abi_version(void) { return CRM_B200_ABI_VERSION; }
 
+extern "C" long long crm_b200_sizeof(int which) {
+  switch (which) {
+    case 0: return (long long)sizeof(crm_dims_t);
+    case 1: return (long long)sizeof(crm_input_t);
+    case 2: return (long long)sizeof(crm_state_t);
+    case 3: return (long long)sizeof(crm_rad_t);
+    case 4: return (long long)sizeof(crm_output_t);
+    case 5: return (long long)sizeof(crm_run_stats_t);
+    default: return -1;
+  }
+}
+
 extern "C" const char *crm_b200_last_error(void *handle) {
   if (!handle) return g_init_err.c_str();
   return ((Handle *)handle)->err.c_str();

@@ -154,6 +154,10 @@ const char *crm_b200_kernel_times(void *handle);
 
 int crm_b200_abi_version(void);
 
+/* sizeof() of the boundary structs as compiled into the library, for binding-side layout checks:
+ * which = 0 crm_dims_t, 1 crm_input_t, 2 crm_state_t, 3 crm_rad_t, 4 crm_output_t, 5 crm_run_stats_t; -1 otherwise. */
+long long crm_b200_sizeof(int which);
+
 #ifdef __cplusplus
 }
 #endif
