@@ -643,3 +643,27 @@ extern "C" long long crm_b200_debug_fetch(void *handle, const char *name, double
   dev_copy2d(host_buf, need * 8, h->stage, need * 8, need * 8, 1, 0);
   return (long long)need;
 }
+
+#ifdef CRM_EMU
+// DEV/TEST ONLY (host emulation build, tests/emu): exposes the device math helpers of crm_common.cuh / crm_k_scalar.cuh to the
+// CPU unit tests (tests/test_device_math_cpu.py).  Not compiled into libcrm_b200.so.
+extern "C" double crm_emu_math(int which, double x, double c) {
+  switch (which) {
+    case 0: return pow_1_16(x);
+    case 1: return pow_1_8(x);
+    case 2: return pow_13_16(x);
+    case 3: return pow_7_8(x);
+    case 4: { double s1, pw; sqrt_pow_21_32(x, s1, pw); return (c == 0.) ? pw : s1; }
+    case 5: { double s1, pw; sqrt_pow_11_16(x, s1, pw); return (c == 0.) ? pw : s1; }
+    case 6: return pow_rain_c(x, c);
+    case 7: return pow_rain_1(x, c);
+    case 8: return pow_rain_2(x, c);
+    case 9: return pow_ice_024(x, c);
+    case 10: return qsat_mix(x, c, 0.37);            // x = T [K], c = p [hPa]
+    case 11: return 0.37 * qsatw_crm(x, c) + (1. - 0.37) * qsati_crm(x, c);
+    case 12: { double q1, q2; ratio2(x, c, 3. * x, 7. * c + 1., q1, q2); return q1 + 1e3 * q2; }
+    case 13: return x / c + 1e3 * ((3. * x) / (7. * c + 1.));
+    default: return 0.;
+  }
+}
+#endif

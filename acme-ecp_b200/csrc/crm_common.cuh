@@ -131,7 +131,7 @@ __device__ __forceinline__ double pow_c(double x, double c) { return exp(c * log
 // The dyadic powers are built from r = x**(-1/16) (or x**(-1/32)): an FP32 seed exp2(-log2(x)/16) (two MUFU operations,
 // relative error ~1e-6) refined by two division-free Newton steps r <- r*(17 - x*r**16)/16 (error 8.5*e**2 per step, so
 // ~1e-21 before rounding); x**(k/16) = x * r**(16-k).  ~27 FP64 instructions instead of four chained IEEE square roots
-// (~60, all serially dependent).  Results agree with pow() to ~(16-k) ulp.  Outside the FP32 range (never reached by
+// (~60, all serially dependent).  Results agree with pow() to 5e-15 relative (tests/test_device_math_cpu.py).  Outside the FP32 range (never reached by
 // mixing ratios above qp_threshold) the square-root chain is used.
 #ifdef CRM_EMU
 #define CRM_LOG2F(x) log2f(x)
