@@ -659,3 +659,47 @@ extern "C" int crm_oracle_num_threads(void) {
   return 1;
 #endif
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Routine-level test hooks (tests/test_oracle_kat.py): one routine of the restatement on caller-supplied fields of ONE
+// CRM, interior arrays in Fortran order (i fastest).
+// ---------------------------------------------------------------------------------------------------
+// advect_scalar (MPDATA + FCT, ADV_MPDATA/advect_scalar.F90:9-76) of f with the mass-flux velocities u, v (nx,ny,nzm) and
+// w (nx,ny,nzm+1) exactly as adams.F90:28-34 leaves them (velocity * rho * dtn/dx, w * rhow * dtn/dz).
+extern "C" int crm_oracle_test_advect(int nx, int ny, int nzm, const double *u, const double *v, const double *w, const double *rho,
+                                      const double *rhow, const double *adz, double *f, double *fadv, double *flux) {
+  Geo g; g.nx = nx; g.ny = ny; g.nzm = nzm; g.nz = nzm + 1; g.plev = nzm; g.YES3D = ny > 1 ? 1 : 0; g.RUN3D = ny > 1;
+  g.nx_rad = 1; g.ny_rad = 1; g.dx = 1000.; g.dy = 1000.;
+  Crm c; alloc_crm(g, c);
+  for (int k = 1; k <= nzm + 1; k++) { c.rhow(k) = rhow[k - 1]; if (k <= nzm) { c.rho(k) = rho[k - 1]; c.adz(k) = adz[k - 1]; } }
+  for (int k = 1; k <= nzm + 1; k++)
+    for (int j = 1; j <= ny; j++)
+      for (int i = 1; i <= nx; i++) {
+        const size_t o = (size_t)(i - 1) + (size_t)nx * ((j - 1) + (size_t)ny * (k - 1));
+        c.w(i, j, k) = w[o];
+        if (k <= nzm) { c.u(i, j, k) = u[o]; c.v(i, j, k) = v[o]; c.t(i, j, k) = f[o]; }
+      }
+  boundaries(g, c, 2);
+  P1 fa, fl; fa.alloc(1, nzm + 1); fl.alloc(1, nzm + 1);
+  advect_scalar(g, c, c.t, fa, fl);
+  for (int k = 1; k <= nzm; k++) {
+    fadv[k - 1] = fa(k); flux[k - 1] = fl(k);
+    for (int j = 1; j <= ny; j++)
+      for (int i = 1; i <= nx; i++) f[(size_t)(i - 1) + (size_t)nx * ((j - 1) + (size_t)ny * (k - 1))] = c.t(i, j, k);
+  }
+  return 0;
+}
+
+// cloud() (MICRO_SAM1MOM/cloud.F90:7-117) on n independent cells: t (liquid/ice static energy / cp), gamaz, pres, total water q and
+// precipitation qp in; tabs, qn and the clipped q, qp out.
+extern "C" int crm_oracle_test_cloud(int n, const double *t, const double *gamaz, const double *pres, double *q, double *qp, double *tabs,
+                                     double *qn) {
+  for (int m = 0; m < n; m++) {
+    Geo g; g.nx = 1; g.ny = 1; g.nzm = 1; g.nz = 2; g.plev = 1; g.YES3D = 0; g.RUN3D = false; g.nx_rad = 1; g.ny_rad = 1; g.dx = g.dy = 1000.;
+    Crm c; alloc_crm(g, c);
+    c.t(1, 1, 1) = t[m]; c.gamaz(1) = gamaz[m]; c.pres(1) = pres[m]; c.qt(1, 1, 1) = q[m]; c.qp(1, 1, 1) = qp[m];
+    cloud(g, c);
+    q[m] = c.qt(1, 1, 1); qp[m] = c.qp(1, 1, 1); tabs[m] = c.tabs(1, 1, 1); qn[m] = c.qn(1, 1, 1);
+  }
+  return 0;
+}

@@ -200,3 +200,86 @@ def test_oracle_matches_golden_fixture(name):
         np.testing.assert_allclose(getattr(st, nme), z["state_" + nme], rtol=0, atol=1e-11 * max(1e-30, np.abs(z["state_" + nme]).max()))
     for nme in ("sltend", "qltend", "qcltend", "qiltend", "precc", "precl", "cld", "mcup", "flux_qt"):
         np.testing.assert_allclose(getattr(out, nme), z["out_" + nme], rtol=0, atol=1e-10 * max(1e-30, np.abs(z["out_" + nme]).max()))
+
+
+# ---------------------------------------------------------------- routine-level invariants
+def _nondivergent_flux(nx, ny, nzm, adz, rng, cmax=0.25):
+    """Mass-flux velocities as adams.F90 leaves them, discretely non-divergent in the sense of advect_scalar:
+    u(i+1)-u(i) + v(j+1)-v(j) + (w(k+1)-w(k))/adz(k) == 0, from two stream functions; w = 0 at the bottom and top faces."""
+    psi = rng.standard_normal((nx, ny, nzm + 1)); chi = rng.standard_normal((nx, ny, nzm + 1)) * (ny > 1)
+    psi[:, :, 0] = psi[:, :, -1] = 0.0; chi[:, :, 0] = chi[:, :, -1] = 0.0
+    iadz = 1.0 / adz[None, None, :]
+    u = (psi[:, :, 1:] - psi[:, :, :-1]) * iadz
+    v = (chi[:, :, 1:] - chi[:, :, :-1]) * iadz
+    w = -(np.roll(psi, -1, axis=0) - psi) - (np.roll(chi, -1, axis=1) - chi)
+    s = cmax / max(np.abs(u).max(), np.abs(v).max(), np.abs(w).max())
+    return u * s, v * s, w * s
+
+
+def _advect(nx, ny, nzm, u, v, w, rho, rhow, adz, f):
+    L = ob.lib()
+    g = np.asfortranarray(f.copy())
+    fadv = np.zeros(nzm); flux = np.zeros(nzm)
+    P = cm.pkg.abi.dptr
+    rc = L.crm_oracle_test_advect(nx, ny, nzm, P(np.asfortranarray(u)), P(np.asfortranarray(v)), P(np.asfortranarray(w)), P(rho), P(rhow), P(adz),
+                                  P(g), P(fadv), P(flux))
+    assert rc == 0
+    return g, fadv, flux
+
+
+@pytest.mark.parametrize("nx,ny", [(16, 1), (8, 8)])
+def test_mpdata_constant_conservation_and_extrema(nx, ny):
+    """advect_scalar (MPDATA + FCT, ADV_MPDATA/advect_scalar2D/3D.F90) under a discretely non-divergent mass flux:
+    a constant stays constant, sum(rho*adz*f) is conserved, no new extrema appear, zeros stay non-negative."""
+    rng = np.random.default_rng(5 + ny)
+    nzm = 12
+    adz = rng.uniform(0.6, 1.6, nzm); rho = np.linspace(1.2, 0.4, nzm); rhow = np.linspace(1.25, 0.35, nzm + 1)
+    u, v, w = _nondivergent_flux(nx, ny, nzm, adz, rng)
+    c0 = np.full((nx, ny, nzm), 3.25)
+    g, _, _ = _advect(nx, ny, nzm, u, v, w, rho, rhow, adz, c0)
+    assert np.abs(g - 3.25).max() < 1e-13
+    f0 = np.zeros((nx, ny, nzm)); f0[nx // 4: nx // 2, :, 3:7] = 1.0; f0 += 0.2 * rng.uniform(size=f0.shape) * (f0 > 0)
+    g, fadv, flux = _advect(nx, ny, nzm, u, v, w, rho, rhow, adz, f0)
+    wgt = (rho * adz)[None, None, :]
+    assert abs((g * wgt).sum() - (f0 * wgt).sum()) < 1e-12 * (f0 * wgt).sum()
+    assert g.min() >= 0.0 and g.max() <= f0.max() + 1e-13
+    assert np.abs(g - f0).max() > 1e-3                       # the field did move
+    assert abs(fadv.sum() - (g - f0).sum()) < 1e-12 * np.abs(g - f0).sum()   # fadv(k) = sum_xy (f_new - f_old)
+
+
+def test_cloud_saturation_adjustment_invariants():
+    """cloud() (MICRO_SAM1MOM/cloud.F90): where condensate forms, q - qn equals the mixed-phase saturation value at the new
+    tabs to the Newton tolerance (0.01 K) and the liquid/ice static energy t is consistent with (tabs, qn, qp); unsaturated
+    cells keep qn = 0 and the closed-form tabs; negative inputs are clipped."""
+    rng = np.random.default_rng(11)
+    n = 4000
+    pres = rng.uniform(150., 1010., n)
+    tabs_true = rng.uniform(215., 305., n)
+    gamaz = rng.uniform(0., 120., n)
+    omw = np.clip((tabs_true - 253.16) / 20.0, 0, 1)
+    qs = np.array([omw[m] * ob.lib().crm_oracle_qsatw(tabs_true[m], pres[m]) + (1 - omw[m]) * ob.lib().crm_oracle_qsati(tabs_true[m], pres[m])
+                   for m in range(n)])
+    q = qs * rng.uniform(0.3, 1.6, n); q[:50] = -1e-6
+    qp = np.where(rng.uniform(size=n) < 0.5, 0.0, rng.uniform(0, 2e-3, n)); qp[50:80] = -1e-7
+    t = tabs_true + gamaz                                   # t = tabs + gamaz when there is no condensate
+    q_in, qp_in = q.copy(), qp.copy()
+    tabs = np.zeros(n); qn = np.zeros(n)
+    P = cm.pkg.abi.dptr
+    assert ob.lib().crm_oracle_test_cloud(n, P(t), P(gamaz), P(pres), P(q), P(qp), P(tabs), P(qn)) == 0
+    assert (q >= 0).all() and (qp >= 0).all() and (qn >= 0).all() and (qn <= q + 1e-18).all()
+    sat = qn > 0
+    assert sat.sum() > 500 and (~sat).sum() > 500
+    fac_cond, fac_fus = 2.501e6 / 1004.64, 3.337e5 / 1004.64
+    omn = np.clip((tabs - 253.16) / 20.0, 0, 1); omp = np.clip((tabs - 268.16) / 15.0, 0, 1)
+    lat = fac_cond * (qn * omn + qp * omp) + (fac_cond + fac_fus) * (qn * (1 - omn) + qp * (1 - omp))
+    # energy: tabs = t - gamaz + L*condensate (diagnose.F90:37-41) to the 0.01 K Newton tolerance.  Checked where qp = 0: with
+    # precipitation the reference's first guess uses the mixed-phase closed form over the whole 253-273 K cloud range
+    # (cloud.F90:45-57 tests tbgmin/tbgmax, not tprmin/tprmax), so tabs is only an intermediate there (diagnose recomputes it).
+    noprec = (qp_in <= 0.0) & (qs < 0.04)                   # (and only physical T-p pairs: hot air at 150 hPa has es ~ p)
+    assert noprec.sum() > 1000 and np.abs(tabs - (t - gamaz + lat))[noprec].max() < 2e-3
+    qs_new = np.array([omn[m] * ob.lib().crm_oracle_qsatw(tabs[m], pres[m]) + (1 - omn[m]) * ob.lib().crm_oracle_qsati(tabs[m], pres[m])
+                       for m in range(n)])
+    ok = sat & (qs < 0.04)
+    assert (np.abs((q - qn) - qs_new)[ok] < 1e-4 * qs_new[ok] + 1e-9).all()
+    unsat_noprec = (~sat) & (qp_in <= 0.0) & (qs < 0.04)
+    assert ((q - qs_new)[unsat_noprec] <= 1e-6 * qs_new[unsat_noprec]).all()
