@@ -293,7 +293,9 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p2_sgs(CrmP p) {
       else smix = dmin(grd, dmax(R4(0.1) * grd, sqrt((R4(0.76) / Ck) * tk_old * rsqrt(bs + R4(1.e-10)))));
       const double ratio = smix * SPF(9, k);
       const double Cee = Ce1 + Ce2 * ratio;
-      const double sq = sqrt(Ck * Ck * Ck / Cee * dmax(0., def2 - Pr * bs));
+      // sqrt(a/Cee) = a*rsqrt(a*Cee) for a > 0: one MUFU operation instead of a divide and a square root
+      const double a_ = Ck * Ck * Ck * dmax(0., def2 - Pr * bs);
+      const double sq = (a_ > 0.) ? a_ * rsqrt(a_ * Cee) : 0.;
       double tk = sq * (smix * smix);
       const double r = sq * smix * (1. / Ck);
       F3(p.tke, k) = r * r;
