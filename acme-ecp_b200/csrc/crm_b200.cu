@@ -662,7 +662,7 @@ extern "C" double crm_emu_math(int which, double x, double c) {
     case 10: return qsat_mix(x, c, 0.37);            // x = T [K], c = p [hPa]
     case 11: return 0.37 * qsatw_crm(x, c) + (1. - 0.37) * qsati_crm(x, c);
     case 12: { double q1, q2; ratio2(x, c, 3. * x, 7. * c + 1., q1, q2); return q1 + 1e3 * q2; }
-    case 13: return x / c + 1e3 * ((3. * x) / (7. * c + 1.));
+    case 13: return fmin(1., x / c) + 1e3 * fmin(1., (3. * x) / (7. * c + 1.));
     default: return 0.;
   }
 }

@@ -28,13 +28,18 @@ __device__ __forceinline__ double min3(double a, double b, double c) { return dm
 // body below it handles the first two and the last levels.
 #define CRM_MP_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(3, 6, P) + CRM_PROF_BYTES(5, nzp, CT) + (size_t)(9 * (P) + 2 * CRM_RED_DOUBLES(2, P, CT)) * 8)
 __device__ __forceinline__ double upw_flux(double v, double below, double above) { return v * (v > 0. ? below : above); }
-// The two FCT ratios of a cell, q1 = n1/d1 and q2 = n2/d2 (d >= eps > 0), with ONE FP64 division (it runs on the MUFU
-// pipe, which bounded these kernels): both quotients over the common denominator d1*d2 (>= 1e-20).  A zero numerator
-// gives exactly +0 without dividing (precipitation-free or locally uniform air).  The quotients agree with the literal
-// divisions to 2 ulp; they only act through min(1, .) limiters.
+// The two FCT ratios of a cell, min(1, n1/d1) and min(1, n2/d2) (n >= 0, d >= eps > 0).  Every use of the ratios is
+// min(1, ratio, ...) (advect_scalar2D.F90:214-229, microphysics.F90:745-760), so a ratio >= 1 (limiter inactive: smooth
+// field) needs no quotient at all, and when one is needed both share ONE FP64 division over the common denominator
+// d1*d2 (>= 1e-20).  A zero numerator gives exactly +0.  The quotients agree with the literal divisions to 2 ulp.
 __device__ __forceinline__ void ratio2(double n1, double d1, double n2, double d2, double &q1, double &q2) {
-  q1 = 0.; q2 = 0.;
-  if (n1 != 0. || n2 != 0.) { const double r = 1. / (d1 * d2); q1 = n1 * d2 * r; q2 = n2 * d1 * r; }
+  const bool a1 = n1 < d1, a2 = n2 < d2;
+  q1 = 1.; q2 = 1.;
+  if (a1 || a2) {
+    const double r = 1. / (d1 * d2);
+    if (a1) q1 = n1 * d2 * r;
+    if (a2) q2 = n2 * d1 * r;
+  }
 }
 template <int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P, 3) k_mpdata(CrmP p, double *f, double *fadv, double *flux, int stats, const int *ktop) {
@@ -453,6 +458,7 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_precip_b(CrmP p, int iprec0, i
   const long long c2 = (long long)tile * P + tid;
   const int RS = CRM_RED_DOUBLES(1, P, CT);
   const int wrp = tid >> 5, nw = P >> 5;
+  const double inprec = 1. / (double)nprec;
   for (int iprec = iprec0; iprec <= iprec1; iprec++) {
     if (iprec > iprec0) {
 #ifndef CRM_EMU
@@ -494,7 +500,7 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_precip_b(CrmP p, int iprec0, i
       if (s <= KT) {
         q3 = R.plane(0, s)[tid]; w3 = R.plane(1, s)[tid];
         const double tb = R.plane(2, s)[tid];
-        if (scale_wp) w3 = w3 / (double)nprec;
+        if (scale_wp) w3 = w3 * inprec;   // wp/nprec (microphysics.F90:648-660) through the reciprocal (1 ulp)
         fz3 = q3 * w3;
         om3 = dmax(0., dmin(1., (tb - CRM_TPRMIN) * p.ms.a_pr));
       } else { q3 = 0.; w3 = 0.; fz3 = 0.; om3 = 0.; }

@@ -55,7 +55,8 @@ def test_one_division_pairs(emu):
         a, b = emu.crm_emu_math(10, t, p), emu.crm_emu_math(11, t, p)
         assert abs(a - b) <= 4 * ULP * abs(b), (t, p, a, b)
         x, c = float(10.0 ** rng.uniform(-12, 2)), float(10.0 ** rng.uniform(-10, 3))
-        a, b = emu.crm_emu_math(12, x, c), emu.crm_emu_math(13, x, c)
+        a, b = emu.crm_emu_math(12, x, c), emu.crm_emu_math(13, x, c)   # ratio2 returns min(1, n/d) for both quotients
         assert abs(a - b) <= 4 * ULP * abs(b), (x, c, a, b)
-    # zero numerators give exact zeros without dividing
+    # zero numerators give exact zeros; ratios >= 1 come back as exactly 1 without a division
     assert emu.crm_emu_math(12, 0.0, 5.0) == 0.0
+    assert emu.crm_emu_math(12, 50.0, 5.0) == 1.0 + 1e3 * 1.0
