@@ -703,3 +703,30 @@ extern "C" int crm_oracle_test_cloud(int n, const double *t, const double *gamaz
   }
   return 0;
 }
+
+// micro_precip_fall (MICRO_SAM1MOM/microphysics.F90:491-830) on ncol independent columns of nzm levels (interior arrays
+// (ncol, nzm), column index fastest): qp, t updated in place; precsfc (ncol) returns the surface precipitation of the call
+// in the units of the reference's accumulator (mm of water per call: sum over sub-iterations of -fz(1)); returns nprec.
+extern "C" int crm_oracle_test_precip_fall(int ncol, int nzm, double dz, double dtn, const double *rho, const double *rhow, const double *adz,
+                                           const double *tabs, double *qp, double *t, double *precsfc) {
+  Geo g; g.nx = ncol; g.ny = 1; g.nzm = nzm; g.nz = nzm + 1; g.plev = nzm; g.YES3D = 0; g.RUN3D = false; g.nx_rad = 1; g.ny_rad = 1; g.dx = g.dy = 1000.;
+  Crm c; alloc_crm(g, c);
+  MicroCoef mc; mc.init();
+  Step s; s.dtn = dtn; s.dt = dtn; s.nstep = 1; s.icycle = 1; s.ncycle = 1;
+  c.dz = dz;
+  for (int k = 1; k <= nzm + 1; k++) { c.rhow(k) = rhow[k - 1]; if (k <= nzm) { c.rho(k) = rho[k - 1]; c.adz(k) = adz[k - 1]; } }
+  for (int k = 1; k <= nzm; k++)
+    for (int i = 1; i <= ncol; i++) {
+      const size_t o = (size_t)(i - 1) + (size_t)ncol * (k - 1);
+      c.qp(i, 1, k) = qp[o]; c.t(i, 1, k) = t[o]; c.tabs(i, 1, k) = tabs[o];
+    }
+  const double cfl = precip_fall_part1(g, c, s, mc);
+  precip_fall_part2(g, c, s, mc, cfl);
+  for (int k = 1; k <= nzm; k++)
+    for (int i = 1; i <= ncol; i++) {
+      const size_t o = (size_t)(i - 1) + (size_t)ncol * (k - 1);
+      qp[o] = c.qp(i, 1, k); t[o] = c.t(i, 1, k);
+    }
+  for (int i = 1; i <= ncol; i++) precsfc[i - 1] = c.precsfc[i - 1];
+  return cfl > R4(0.9) ? (int)std::ceil(cfl / R4(0.9)) : 1;
+}

@@ -283,3 +283,35 @@ def test_cloud_saturation_adjustment_invariants():
     assert (np.abs((q - qn) - qs_new)[ok] < 1e-4 * qs_new[ok] + 1e-9).all()
     unsat_noprec = (~sat) & (qp_in <= 0.0) & (qs < 0.04)
     assert ((q - qs_new)[unsat_noprec] <= 1e-6 * qs_new[unsat_noprec]).all()
+
+
+def test_precip_fall_conserves_water_and_only_moves_it_down():
+    """micro_precip_fall (MICRO_SAM1MOM/microphysics.F90:491-830): per column, sum_k rho*adz*(qp_new - qp_old) equals minus
+    the surface precipitation booked in precsfc (flux form, any number of sub-iterations), qp stays non-negative, nothing
+    appears above the highest precipitating level, and thin bottom layers force nprec > 1 (the sub-iterated path)."""
+    rng = np.random.default_rng(3)
+    ncol, nzm = 64, 40
+    zi = np.concatenate([[0.0], np.cumsum(np.concatenate([np.full(6, 40.0), np.linspace(80., 900., nzm - 6)]))])
+    z = 0.5 * (zi[1:] + zi[:-1])
+    dz = 0.5 * (z[0] + z[1])
+    adz = (zi[1:] - zi[:-1]) / dz
+    rho = 1.2 * np.exp(-z / 8000.); rhow = 1.2 * np.exp(-zi / 8000.)
+    tabs = np.asfortranarray(np.repeat((295. - 6.5e-3 * z)[None, :], ncol, axis=0) + rng.normal(0, 1.0, (ncol, nzm)))
+    qp = np.zeros((ncol, nzm), order="F")
+    top = 25
+    qp[:, :top] = np.where(rng.uniform(size=(ncol, top)) < 0.6, rng.uniform(0, 3e-3, (ncol, top)), 0.0)
+    qp[:8] = 0.0                                          # some precipitation-free columns
+    t = np.asfortranarray(tabs + 9.80616 / 1004.64 * z[None, :])
+    qp0, t0 = qp.copy(), t.copy()
+    prec = np.zeros(ncol)
+    P = cm.pkg.abi.dptr
+    import ctypes as C
+    nprec = ob.lib().crm_oracle_test_precip_fall(ncol, nzm, C.c_double(float(dz)), C.c_double(10.0), P(rho), P(rhow), P(adz), P(tabs), P(qp), P(t), P(prec))
+    assert nprec >= 2, "the thin bottom layers must force sub-iterations"
+    w = (rho * adz)[None, :]
+    resid = ((qp - qp0) * w).sum(axis=1) + prec
+    assert np.abs(resid).max() <= 1e-13 * max((qp0 * w).sum(axis=1).max(), 1e-30)
+    assert qp.min() >= 0.0 and prec.min() >= 0.0 and prec[8:].max() > 0.0
+    assert np.all(qp[:8] == 0.0) and np.all(prec[:8] == 0.0) and np.array_equal(t[:8], t0[:8])
+    assert np.all(qp[:, top:] == 0.0)                     # sedimentation never moves water upward
+    assert np.abs(qp - qp0).max() > 1e-5                  # and it did move
