@@ -76,6 +76,14 @@ class crm_run_stats_t(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class crm_ptend_t(C.Structure):
+    """crm_physics_tend glue outputs (include/crm_b200.h: crm_ptend_t)."""
+    _fields_ = [(n, c_dp) for n in ("s", "q_vapor", "q_cldliq", "q_cldice", "prec_dp", "snow_dp", "cld")]
+
+
+PTEND_FIELDS = (("s", "lev"), ("q_vapor", "lev"), ("q_cldliq", "lev"), ("q_cldice", "lev"), ("prec_dp", "col"), ("snow_dp", "col"), ("cld", "lev"))
+
+
 def shape_of(kind, d):
     """Shape of a boundary array of the given kind for dims ``d`` (crm_dims_t or anything with the same attributes)."""
     ld = d.ld

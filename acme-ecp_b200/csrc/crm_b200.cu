@@ -609,6 +609,83 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// crm_physics_tend glue (include/crm_b200.h): elementwise kernels on the boundary arrays.  Host arrays are staged through
+// the handle's scratch (h->stage for qrad, h->out_dev for the (ld,plev) / (ld) arrays) and written back.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Staged {   // device view of one boundary array of `cols` columns
+  double *dev = nullptr; double *host = nullptr; size_t cols = 0;
+};
+Staged stage_in(Handle *, double *&cursor, const double *a, int ld, int ncrms, size_t cols, bool copy) {
+  Staged v; v.cols = cols;
+  if (!a) return v;
+  if (is_dev_ptr(a)) { v.dev = const_cast<double *>(a); return v; }
+  v.host = const_cast<double *>(a); v.dev = cursor; cursor += (size_t)ld * cols;
+  if (copy) copy_rows(v.dev, ld, a, ld, ncrms, cols);
+  return v;
+}
+void stage_out(const Staged &v, int ld, int ncrms) { if (v.host) copy_rows(v.host, ld, v.dev, ld, ncrms, v.cols); }
+int glue_check(Handle *h, const crm_dims_t *d) {
+  const crm_dims_t &d0 = h->d0;
+  if (d->plev != d0.plev || d->nzm != d0.nzm || d->nx_rad != d0.nx_rad || d->ny_rad != d0.ny_rad) return fail(h, 40, "crm_b200_physics_*: geometry differs from crm_b200_init");
+  if (d->ncrms < 1 || d->ncrms > d0.ncrms || d->ld < d->ncrms || d->ld > h->ld_max) return fail(h, 41, "crm_b200_physics_*: need ncrms <= init ncrms and ncrms <= ld <= init ld");
+  if (dev_init(h->device)) return fail(h, 42, std::string("crm_b200_physics_*: cannot select device: ") + dev_errstr());
+  return 0;
+}
+int glue_qrad(Handle *h, const crm_dims_t *d, const double *pdel, double *qrad, int invert) {
+  if (!pdel || !qrad) return fail(h, 43, "crm_b200_physics_*: pdel and qrad must not be NULL");
+  const int ncr = d->nx_rad * d->ny_rad;
+  double *cur_q = h->stage, *cur_p = h->out_dev;
+  Staged q = stage_in(h, cur_q, qrad, d->ld, d->ncrms, (size_t)ncr * d->nzm, true);
+  Staged pd = stage_in(h, cur_p, pdel, d->ld, d->ncrms, (size_t)d->plev, true);
+  const long long n = (long long)d->ncrms * ncr * d->nzm;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+  LAUNCH(h, k_glue_qrad, blocks, 256, 0, q.dev, pd.dev, d->ncrms, d->ld, ncr, d->nzm, d->plev, invert);
+  if (dev_sync()) return fail(h, 44, std::string("crm_b200_physics_*: kernel failure: ") + dev_errstr());
+  stage_out(q, d->ld, d->ncrms);
+  return 0;
+}
+}  // namespace
+
+extern "C" int crm_b200_physics_pre(void *handle, const crm_dims_t *d, const double *pdel, double *qrad) {
+  if (!handle) return 1;
+  Handle *h = (Handle *)handle;
+  h->err.clear();
+  if (int rc = glue_check(h, d)) return rc;
+  return glue_qrad(h, d, pdel, qrad, 1);
+}
+
+extern "C" int crm_b200_physics_post(void *handle, const crm_dims_t *d, const double *pdel, double *qrad, crm_output_t *out, crm_ptend_t *pt) {
+  if (!handle) return 1;
+  Handle *h = (Handle *)handle;
+  h->err.clear();
+  if (int rc = glue_check(h, d)) return rc;
+  if (!out || !pt) return fail(h, 45, "crm_b200_physics_post: out and ptend must not be NULL");
+  if (!out->sltend || !out->qltend || !out->qcltend || !out->qiltend || !out->cld || !out->precc || !out->precl || !out->precsc || !out->precsl)
+    return fail(h, 46, "crm_b200_physics_post: crm_output members sltend, qltend, qcltend, qiltend, cld, precc, precl, precsc, precsl are required");
+  const int ld = d->ld, n = d->ncrms, plev = d->plev;
+  double *cur = h->out_dev + (size_t)ld * plev;   // (the first plev columns of the scratch hold pdel in glue_qrad)
+  Staged sl = stage_in(h, cur, out->sltend, ld, n, plev, true), qv = stage_in(h, cur, out->qltend, ld, n, plev, true);
+  Staged ql = stage_in(h, cur, out->qcltend, ld, n, plev, true), qi = stage_in(h, cur, out->qiltend, ld, n, plev, true);
+  Staged cl = stage_in(h, cur, out->cld, ld, n, plev, true);
+  Staged pc = stage_in(h, cur, out->precc, ld, n, 1, true), pl = stage_in(h, cur, out->precl, ld, n, 1, true);
+  Staged sc = stage_in(h, cur, out->precsc, ld, n, 1, true), sn = stage_in(h, cur, out->precsl, ld, n, 1, true);
+  Staged ts = stage_in(h, cur, pt->s, ld, n, plev, false), tv = stage_in(h, cur, pt->q_vapor, ld, n, plev, false);
+  Staged tl = stage_in(h, cur, pt->q_cldliq, ld, n, plev, false), ti = stage_in(h, cur, pt->q_cldice, ld, n, plev, false);
+  Staged tc = stage_in(h, cur, pt->cld, ld, n, plev, false);
+  Staged pdp = stage_in(h, cur, pt->prec_dp, ld, n, 1, false), sdp = stage_in(h, cur, pt->snow_dp, ld, n, 1, false);
+  GluePost g;
+  g.sltend = sl.dev; g.qltend = qv.dev; g.qcltend = ql.dev; g.qiltend = qi.dev; g.cld_in = cl.dev;
+  g.precc = pc.dev; g.precl = pl.dev; g.precsc = sc.dev; g.precsl = sn.dev;
+  g.s = ts.dev; g.qv = tv.dev; g.ql = tl.dev; g.qi = ti.dev; g.cld = tc.dev; g.prec_dp = pdp.dev; g.snow_dp = sdp.dev;
+  const long long ne = (long long)n * plev;
+  LAUNCH(h, k_glue_post, (int)std::min<long long>((ne + 255) / 256, 148 * 16), 256, 0, g, n, ld, plev);
+  if (dev_sync()) return fail(h, 47, std::string("crm_b200_physics_post: kernel failure: ") + dev_errstr());
+  for (const Staged *v : {&pc, &pl, &sc, &sn, &ts, &tv, &tl, &ti, &tc, &pdp, &sdp}) stage_out(*v, ld, n);
+  return glue_qrad(h, d, pdel, qrad, 0);
+}
+
 extern "C" long long crm_b200_debug_fetch(void *handle, const char *name, double *host_buf, size_t n) {
   if (!handle) return -1;
   Handle *h = (Handle *)handle;

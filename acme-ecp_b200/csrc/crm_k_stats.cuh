@@ -303,4 +303,41 @@ __global__ void k_epi_rad(CrmP p, const double *acc, double *ext, int ld, double
   ext[(size_t)icrm + (size_t)ld * ((size_t)ir + (size_t)p.nx_rad * (size_t)k)] = acc[((long long)tile * p.nzm + k) * Pd + tid] * scale;
 }
 
+// ---- crm_physics_tend glue (crm_physics.F90:1006-1011, 1160-1209): boundary layout (ld leading), one thread per element ----
+// qrad(i,c,m) = invert ? qrad / pdel(i, plev-m) : qrad * pdel(i, plev-m)   (0-based m = CRM level, c = rad column)
+__global__ void k_glue_qrad(double *qrad, const double *pdel, int ncrms, int ld, int ncr, int nzm, int plev, int invert) {
+  const long long n = (long long)ncrms * ncr * nzm;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % ncrms);
+    const long long r = e / ncrms;
+    const int c = (int)(r % ncr), m = (int)(r / ncr);
+    const size_t o = (size_t)i + (size_t)ld * ((size_t)c + (size_t)ncr * m);
+    const double pd = pdel[(size_t)i + (size_t)ld * (size_t)(plev - 1 - m)];
+    qrad[o] = invert ? qrad[o] / pd : qrad[o] * pd;
+  }
+}
+struct GluePost {
+  const double *sltend, *qltend, *qcltend, *qiltend, *cld_in;
+  double *precc, *precl, *precsc, *precsl;
+  double *s, *qv, *ql, *qi, *prec_dp, *snow_dp, *cld;
+};
+__global__ void k_glue_post(GluePost g, int ncrms, int ld, int plev) {
+  const long long n = (long long)ncrms * plev;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % ncrms), l = (int)(e / ncrms);
+    const size_t o = (size_t)i + (size_t)ld * l;
+    if (g.s) g.s[o] = g.sltend[o];
+    if (g.qv) g.qv[o] = g.qltend[o];
+    if (g.ql) g.ql[o] = g.qcltend[o];
+    if (g.qi) g.qi[o] = g.qiltend[o];
+    if (g.cld) g.cld[o] = g.cld_in[o];
+    if (l == 0) {   // no separate convective and stratiform precipitation for the CRM (crm_physics.F90:1168-1177)
+      const double pc = g.precc[i] + g.precl[i], ps = g.precsc[i] + g.precsl[i];
+      g.precc[i] = pc; g.precsc[i] = ps; g.precl[i] = 0.; g.precsl[i] = 0.;
+      if (g.prec_dp) g.prec_dp[i] = pc;
+      if (g.snow_dp) g.snow_dp[i] = ps;
+    }
+  }
+}
+
 }  // namespace crm

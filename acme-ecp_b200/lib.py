@@ -42,6 +42,11 @@ def load(path=None):
     lib.crm_b200_set_kernel_timing.argtypes = [C.c_void_p, C.c_int]
     lib.crm_b200_kernel_times.restype = C.c_char_p
     lib.crm_b200_kernel_times.argtypes = [C.c_void_p]
+    lib.crm_b200_physics_pre.restype = C.c_int
+    lib.crm_b200_physics_pre.argtypes = [C.c_void_p, C.POINTER(abi.crm_dims_t), abi.c_dp, abi.c_dp]
+    lib.crm_b200_physics_post.restype = C.c_int
+    lib.crm_b200_physics_post.argtypes = [C.c_void_p, C.POINTER(abi.crm_dims_t), abi.c_dp, abi.c_dp, C.POINTER(abi.crm_output_t),
+                                          C.POINTER(abi.crm_ptend_t)]
     _libs[path] = lib
     return lib
 
@@ -69,6 +74,27 @@ class CrmHandle:
             out = crm_output_type().initialize(dims)
         self.run_structs(dims, inp.c_struct(), state.c_struct(), rad.c_struct(), out.c_struct())
         return out
+
+    def physics_pre(self, dims, pdel, qrad):
+        """crm_physics_tend before crm(): qrad /= pdel on the CRM levels, in place (crm_physics.F90:1006-1011)."""
+        d = dims.c_struct()
+        rc = self.lib.crm_b200_physics_pre(self.h, C.byref(d), abi.dptr(pdel), abi.dptr(qrad))
+        if rc != 0:
+            raise CrmB200Error("crm_b200_physics_pre failed (%d): %s" % (rc, self.lib.crm_b200_last_error(self.h).decode()))
+
+    def physics_post(self, dims, pdel, qrad, out):
+        """crm_physics_tend after crm() (crm_physics.F90:1160-1209): returns {name: array} of the ptend members, merges the
+        precipitation members of ``out`` in place and restores qrad *= pdel."""
+        d = dims.c_struct()
+        pt = {n: np.zeros(abi.shape_of(kind, dims), order="F") for n, kind in abi.PTEND_FIELDS}
+        cpt = abi.crm_ptend_t()
+        for n in pt:
+            setattr(cpt, n, abi.dptr(pt[n]))
+        co = out.c_struct()
+        rc = self.lib.crm_b200_physics_post(self.h, C.byref(d), abi.dptr(pdel), abi.dptr(qrad), C.byref(co), C.byref(cpt))
+        if rc != 0:
+            raise CrmB200Error("crm_b200_physics_post failed (%d): %s" % (rc, self.lib.crm_b200_last_error(self.h).decode()))
+        return pt
 
     def stats(self):
         s = abi.crm_run_stats_t()

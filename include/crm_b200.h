@@ -135,6 +135,25 @@ int crm_b200_run(void *handle, const crm_dims_t *dims, const crm_input_t *in,
 
 int crm_b200_free(void *handle);
 
+/* ---- crm_physics_tend glue around the crm() call (reference PHYS/crm_physics.F90:1006-1011 and 1160-1209) ----------
+ * with crm_state / crm_rad / crm_output resident on the GPU across GCM steps these two calls keep
+ * the pre/post arithmetic of the caller on the device as well.  Arrays as in crm_b200_run (host or device pointers,
+ * leading dimension ld, rows 0..ncrms-1); pdel is state%pdel (ld,plev). */
+typedef struct crm_ptend_t {
+  double *s;                            /* ptend%s            (ld,plev) <- crm_output%sltend  */
+  double *q_vapor, *q_cldliq, *q_cldice;/* ptend%q(:,:,1|ixcldliq|ixcldice) <- qltend, qcltend, qiltend */
+  double *prec_dp, *snow_dp;            /* (ld): precc + precl, precsc + precsl (crm_physics.F90:1168-1177) */
+  double *cld;                          /* (ld,plev) pbuf CLD <- crm_output%cld (crm_physics.F90:1195)  */
+} crm_ptend_t;
+
+/* before crm(): crm_rad%qrad(i,:,:,m) /= pdel(i, plev-m+1), m = 1..crm_nz  ("for energy conservation", :1006-1011) */
+int crm_b200_physics_pre(void *handle, const crm_dims_t *dims, const double *pdel, double *qrad);
+
+/* after crm(): ptend assembly, the convective/stratiform precipitation merge (crm_output%precc += precl; precl = 0; the same
+ * for precsc/precsl, updated in place in `out`), CLD, and qrad *= pdel (:1160-1209).  NULL members of ptend are skipped. */
+int crm_b200_physics_post(void *handle, const crm_dims_t *dims, const double *pdel, double *qrad, crm_output_t *out,
+                          crm_ptend_t *ptend);
+
 /* Message of the last failure on this handle (or of a failed init if handle==NULL). */
 const char *crm_b200_last_error(void *handle);
 

@@ -730,3 +730,48 @@ extern "C" int crm_oracle_test_precip_fall(int ncol, int nzm, double dz, double 
   for (int i = 1; i <= ncol; i++) precsfc[i - 1] = c.precsfc[i - 1];
   return cfl > R4(0.9) ? (int)std::ceil(cfl / R4(0.9)) : 1;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// crm_physics_tend glue around crm() (PHYS/crm_physics.F90:1006-1011, 1160-1209), restated for the parity tests of
+// crm_b200_physics_pre / crm_b200_physics_post.
+// ---------------------------------------------------------------------------------------------------
+extern "C" int crm_oracle_physics_pre(const crm_dims_t *d, const double *pdel, double *qrad) {
+  const int ncr = d->nx_rad * d->ny_rad;
+  for (int m = 1; m <= d->nzm; m++) {
+    const int k = d->plev - m + 1;                                   // crm_physics.F90:1006-1011
+    for (int c = 0; c < ncr; c++)
+      for (int i = 0; i < d->ncrms; i++) {
+        const size_t o = (size_t)i + (size_t)d->ld * ((size_t)c + (size_t)ncr * (m - 1));
+        qrad[o] = qrad[o] / pdel[(size_t)i + (size_t)d->ld * (k - 1)];
+      }
+  }
+  return 0;
+}
+extern "C" int crm_oracle_physics_post(const crm_dims_t *d, const double *pdel, double *qrad, crm_output_t *out, crm_ptend_t *pt) {
+  const int ncr = d->nx_rad * d->ny_rad, ld = d->ld;
+  for (int l = 0; l < d->plev; l++)
+    for (int i = 0; i < d->ncrms; i++) {
+      const size_t o = (size_t)i + (size_t)ld * l;
+      if (pt->q_vapor) pt->q_vapor[o] = out->qltend[o];               // :1160-1163
+      if (pt->q_cldliq) pt->q_cldliq[o] = out->qcltend[o];
+      if (pt->q_cldice) pt->q_cldice[o] = out->qiltend[o];
+      if (pt->s) pt->s[o] = out->sltend[o];
+      if (pt->cld) pt->cld[o] = out->cld[o];                          // :1195
+    }
+  for (int i = 0; i < d->ncrms; i++) {                                // :1165-1177
+    out->precc[i] = out->precc[i] + out->precl[i];
+    out->precsc[i] = out->precsc[i] + out->precsl[i];
+    out->precl[i] = 0.; out->precsl[i] = 0.;
+    if (pt->prec_dp) pt->prec_dp[i] = out->precc[i];
+    if (pt->snow_dp) pt->snow_dp[i] = out->precsc[i];
+  }
+  for (int m = 1; m <= d->nzm; m++) {                                 // :1202-1209
+    const int k = d->plev - m + 1;
+    for (int c = 0; c < ncr; c++)
+      for (int i = 0; i < d->ncrms; i++) {
+        const size_t o = (size_t)i + (size_t)ld * ((size_t)c + (size_t)ncr * (m - 1));
+        qrad[o] = qrad[o] * pdel[(size_t)i + (size_t)ld * (k - 1)];
+      }
+  }
+  return 0;
+}

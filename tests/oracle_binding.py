@@ -66,3 +66,20 @@ def fft991(a, isign, twiddle_f32=False):
     b = np.array(a, dtype=np.float64)
     lib().crm_oracle_fft991(n, int(twiddle_f32), isign, abi.dptr(np.asfortranarray(b)) if False else b.ctypes.data_as(abi.c_dp))
     return b
+
+
+def physics_pre(dims, pdel, qrad):
+    d = dims.c_struct()
+    assert lib().crm_oracle_physics_pre(C.byref(d), abi.dptr(pdel), abi.dptr(qrad)) == 0
+
+
+def physics_post(dims, pdel, qrad, out):
+    import numpy as _np
+    d = dims.c_struct()
+    pt = {n: _np.zeros(abi.shape_of(kind, dims), order="F") for n, kind in abi.PTEND_FIELDS}
+    cpt = abi.crm_ptend_t()
+    for n in pt:
+        setattr(cpt, n, abi.dptr(pt[n]))
+    co = out.c_struct()
+    assert lib().crm_oracle_physics_post(C.byref(d), abi.dptr(pdel), abi.dptr(qrad), C.byref(co), C.byref(cpt)) == 0
+    return pt
