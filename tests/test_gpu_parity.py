@@ -259,3 +259,10 @@ def test_ensemble_statistics_over_many_steps():
     for nme in cm.STATE:
         err, _ = cm.rel_err(getattr(st_o, nme), getattr(st_g, nme), n)
         assert err < 1e-6, (nme, err)
+
+
+@pytest.mark.parametrize("nx,ncrms,nzm,plev,nsteps,spin", [(32, 9, 27, 30, 4, 60), (64, 12, 57, 72, 6, 90), (16, 5, 21, 30, 3, 0)])
+def test_odd_level_counts(nx, ncrms, nzm, plev, nsteps, spin):
+    # crm_nz need not be even: k_p8_micro processes level pairs, the rings prefetch by fixed distances
+    dims = cm.small_dims(ncrms=ncrms, nx=nx, nzm=nzm, plev=plev, nsteps=nsteps, igstep=1 if spin == 0 else 3)
+    _check(dims, spin, 1e-9)
