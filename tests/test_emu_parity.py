@@ -45,3 +45,23 @@ def test_emu_msa(emu):
     dims = cm.small_dims(ncrms=4, nx=8, nsteps=6, use_crm_accel=True, crm_accel_factor=1.0, crm_accel_uv=True)
     ro, rg = _check(emu, dims, 90, 1e-10)
     assert rg[3]["nstop"] >= 3
+
+
+def test_emu_sedimentation_subiterations(emu):
+    # L72 grid (thin bottom layers): nprec >= 2, one k_precip_b launch per sub-iteration
+    dims = cm.small_dims(ncrms=6, nx=8, nzm=58, plev=72, nsteps=3)
+    ro, rg = _check(emu, dims, 120, 1e-11)
+    assert ro[3]["nprec_max"] >= 2
+
+
+def test_emu_sedimentation_fallback_in_kernel(emu, monkeypatch):
+    # sub-iterations beyond the host's series of launches run inside the last launch
+    monkeypatch.setenv("CRM_B200_PRECIP_LAUNCHES", "1")
+    dims = cm.small_dims(ncrms=6, nx=8, nzm=58, plev=72, nsteps=3)
+    ro, rg = _check(emu, dims, 120, 1e-11)
+    assert ro[3]["nprec_max"] >= 2
+
+
+def test_emu_multi_warp_tiles_and_odd_levels(emu):
+    # nx = 32 with a 4-column CRM tile: four warps per block (warp votes, compaction queue, transposed sums); odd crm_nz
+    _check(emu, cm.small_dims(ncrms=5, nx=32, nzm=27, plev=30, nsteps=2), 30, 1e-11)
