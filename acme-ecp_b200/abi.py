@@ -59,7 +59,7 @@ OUTPUT_FIELDS = (
                           "sltend", "qltend", "qcltend", "qiltend", "cld", "gicewp", "gliqwp",
                           "mctot", "mcup", "mcdn", "mcuup", "mcudn", "mu_crm", "md_crm", "du_crm", "eu_crm", "ed_crm",
                           "flux_qt", "fluxsgs_qt", "tkez", "tkesgsz", "tkz", "flux_u", "flux_v", "flux_qp", "precflux",
-                          "qt_ls", "qt_trans", "qp_trans", "qp_fall", "qp_src", "qp_evp", "t_ls")])
+                          "qt_ls", "qt_trans", "qp_trans", "qp_fall", "qp_src", "qp_evp", "t_ls", "ultend", "vltend")])
 
 
 class crm_output_t(C.Structure):

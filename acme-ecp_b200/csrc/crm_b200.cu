@@ -228,7 +228,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   h->stage = carve<double>(h, (size_t)d->ld * d->nx * d->ny * d->nzm);
   h->esum = carve<double>(h, (size_t)CRM_NESUM * h->prof_elems);
   h->in_dev = carve<double>(h, (size_t)d->ld * (11 * (size_t)(d->plev + 1) + 8));
-  h->out_dev = carve<double>(h, (size_t)d->ld * (39 * (size_t)d->plev + 16 + (size_t)d->nx * d->ny));
+  h->out_dev = carve<double>(h, (size_t)d->ld * (41 * (size_t)d->plev + 16 + (size_t)d->nx * d->ny));
   h->rnd_dev = carve<double>(h, (size_t)d->ncrms * 5 * d->nx * d->ny);
   h->gcol_dev = carve<int>(h, d->ld);
   ok = ok && p.kmin && p.kmax && p.ndamp && p.kprec && p.kqp && p.precsfc && p.precssfc && p.cfl_bits && p.flags && p.twc && p.tws && h->stage && h->esum &&
@@ -527,7 +527,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
     double **levs[] = {&eo.cldtop, &eo.qc_mean, &eo.qi_mean, &eo.qs_mean, &eo.qg_mean, &eo.qr_mean, &eo.sltend, &eo.qltend, &eo.qcltend,
                        &eo.qiltend, &eo.cld, &eo.gicewp, &eo.gliqwp, &eo.mctot, &eo.mcup, &eo.mcdn, &eo.mcuup, &eo.mcudn, &eo.mu_crm, &eo.md_crm,
                        &eo.du_crm, &eo.eu_crm, &eo.ed_crm, &eo.flux_qt, &eo.fluxsgs_qt, &eo.tkez, &eo.tkesgsz, &eo.tkz, &eo.flux_u, &eo.flux_v,
-                       &eo.flux_qp, &eo.precflux, &eo.qt_ls, &eo.qt_trans, &eo.qp_trans, &eo.qp_fall, &eo.qp_src, &eo.qp_evp, &eo.t_ls};
+                       &eo.flux_qp, &eo.precflux, &eo.qt_ls, &eo.qt_trans, &eo.qp_trans, &eo.qp_fall, &eo.qp_src, &eo.qp_evp, &eo.t_ls, &eo.ultend, &eo.vltend};
     for (double **c : levs) *c = take(plev);
     eo.prec_crm = take((size_t)nx * d->ny);
   }
@@ -555,13 +555,13 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
                     out->qiltend, out->cld, out->gicewp, out->gliqwp, out->mctot, out->mcup, out->mcdn, out->mcuup, out->mcudn, out->mu_crm,
                     out->md_crm, out->du_crm, out->eu_crm, out->ed_crm, out->flux_qt, out->fluxsgs_qt, out->tkez, out->tkesgsz, out->tkz,
                     out->flux_u, out->flux_v, out->flux_qp, out->precflux, out->qt_ls, out->qt_trans, out->qp_trans, out->qp_fall, out->qp_src,
-                    out->qp_evp, out->t_ls};
+                    out->qp_evp, out->t_ls, out->ultend, out->vltend};
     double *dl[] = {eo.cldtop, eo.qc_mean, eo.qi_mean, eo.qs_mean, eo.qg_mean, eo.qr_mean, eo.sltend, eo.qltend, eo.qcltend,
                     eo.qiltend, eo.cld, eo.gicewp, eo.gliqwp, eo.mctot, eo.mcup, eo.mcdn, eo.mcuup, eo.mcudn, eo.mu_crm,
                     eo.md_crm, eo.du_crm, eo.eu_crm, eo.ed_crm, eo.flux_qt, eo.fluxsgs_qt, eo.tkez, eo.tkesgsz, eo.tkz,
                     eo.flux_u, eo.flux_v, eo.flux_qp, eo.precflux, eo.qt_ls, eo.qt_trans, eo.qp_trans, eo.qp_fall, eo.qp_src,
-                    eo.qp_evp, eo.t_ls};
-    for (int q = 0; q < 39; q++) give(hl[q], dl[q], plev);
+                    eo.qp_evp, eo.t_ls, eo.ultend, eo.vltend};
+    for (int q = 0; q < 41; q++) give(hl[q], dl[q], plev);
     give(out->prec_crm, eo.prec_crm, (size_t)nx * d->ny);
   }
   auto store3 = [&](double *dst, const double *src, double scale) {

@@ -160,7 +160,7 @@ struct ExtOut {   // device staging of the (ld,plev) / (ld) outputs; same member
       *timing_factor;
   double *cldtop, *qc_mean, *qi_mean, *qs_mean, *qg_mean, *qr_mean, *sltend, *qltend, *qcltend, *qiltend, *cld, *gicewp, *gliqwp, *mctot,
       *mcup, *mcdn, *mcuup, *mcudn, *mu_crm, *md_crm, *du_crm, *eu_crm, *ed_crm, *flux_qt, *fluxsgs_qt, *tkez, *tkesgsz, *tkz, *flux_u,
-      *flux_v, *flux_qp, *precflux, *qt_ls, *qt_trans, *qp_trans, *qp_fall, *qp_src, *qp_evp, *t_ls;
+      *flux_v, *flux_qp, *precflux, *qt_ls, *qt_trans, *qp_trans, *qp_fall, *qp_src, *qp_evp, *t_ls, *ultend, *vltend;
   double *prec_crm;   // (ld,nx,ny)
 };
 
@@ -216,6 +216,8 @@ __global__ void k_epi_profiles(CrmP p, ExtIn in, ExtOut o, const double *esum, d
                     o.tkez, o.tkesgsz, o.tkz, o.flux_qp, o.precflux, o.qt_trans, o.qp_trans, o.qp_fall, o.qp_evp, o.qp_src, o.qt_ls, o.t_ls,
                     o.sltend, o.qltend, o.qcltend, o.qiltend};
     for (double *a : z0) O(a, l) = 0.;
+    // SPMOMTRANS (crm_module.F90:1200-1211): above the CRM top uln = ul, vln = vl (crm_module.F90:1110-1117) -> zero tendency
+    O(o.ultend, l) = 0.; O(o.vltend, l) = 0.;
   }
   double colprec = 0., colprecs = 0.;
   for (int k = 1; k <= nzm; k++) { colprec += ES(5, k); colprecs += ES(6, k); }
@@ -226,6 +228,8 @@ __global__ void k_epi_profiles(CrmP p, ExtIn in, ExtOut o, const double *esum, d
     O(o.qltend, l) = (qln - IN(in.ql, l)) * icrm_run_time;
     O(o.qcltend, l) = (qccln - IN(in.qccl, l)) * icrm_run_time;
     O(o.qiltend, l) = (qiiln - IN(in.qiil, l)) * icrm_run_time;
+    O(o.ultend, l) = (ES(4, k) * factor_xy - IN(in.ul, l)) * icrm_run_time;
+    O(o.vltend, l) = (0. * factor_xy - IN(in.vl, l)) * icrm_run_time;   // 2-D: v == 0 in the CRM (YES3D = 0)
     const double pdel = IN(in.pdel, l);
     O(o.cld, l) = dmin(1., PF(p.s_cld, k) * factor_xyt);
     O(o.cldtop, l) = dmin(1., PF(p.s_cldtop, k) * factor_xyt);
@@ -263,7 +267,7 @@ __global__ void k_epi_profiles(CrmP p, ExtIn in, ExtOut o, const double *esum, d
     O(o.qt_ls, l) = PF(p.qtend, k);
     O(o.t_ls, l) = PF(p.ttend, k);
   }
-  for (int l = ptop; l <= ptop + 1; l++) { O(o.sltend, l) = 0.; O(o.qltend, l) = 0.; O(o.qcltend, l) = 0.; O(o.qiltend, l) = 0.; }
+  for (int l = ptop; l <= ptop + 1; l++) { O(o.sltend, l) = 0.; O(o.qltend, l) = 0.; O(o.qcltend, l) = 0.; O(o.qiltend, l) = 0.; O(o.ultend, l) = 0.; O(o.vltend, l) = 0.; }
   o.prectend[icrm] = (colprec - p.colprec0[icrm]) / CRM_GGR * factor_xy * icrm_run_time;
   o.precstend[icrm] = (colprecs - p.colprecs0[icrm]) / CRM_GGR * factor_xy * icrm_run_time;
   o.z0m[icrm] = p.z0[icrm];

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CRM_B200_ABI_VERSION 1
+#define CRM_B200_ABI_VERSION 2
 
 /* Compile-time constants of the reference (PHYS/crmdims.F90:13-22, CRM/domain.F90:9-13) and the
  * hidden module inputs of crm() (time_manager:get_nstep, accelerate_crm_mod namelist). */
@@ -107,6 +107,9 @@ typedef struct crm_output_t {
   double *flux_qt, *fluxsgs_qt, *tkez, *tkesgsz, *tkz;
   double *flux_u, *flux_v, *flux_qp, *precflux;
   double *qt_ls, *qt_trans, *qp_trans, *qp_fall, *qp_src, *qp_evp, *t_ls;
+  /* (ld,plev), reference build option SPMOMTRANS (crm_output_module.F90:76-79, crm_module.F90:1200-1211): resolved
+   * convective momentum transport tendencies (uln - ul)/dt_gl, two top CRM levels zeroed; NULL = not wanted (ABI >= 2) */
+  double *ultend, *vltend;
 } crm_output_t;
 
 /* Run statistics (new: replaces the GPTL timers 'crm_gpu_region' etc.) */

@@ -443,6 +443,9 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
       if (out->qltend) OUT2(out->qltend, ic, k) = (c.qln(k) - P2(in->ql, ic, k)) * icrm_run_time;
       if (out->qcltend) OUT2(out->qcltend, ic, k) = (c.qccln(k) - P2(in->qccl, ic, k)) * icrm_run_time;
       if (out->qiltend) OUT2(out->qiltend, ic, k) = (c.qiiln(k) - P2(in->qiil, ic, k)) * icrm_run_time;
+      // SPMOMTRANS (crm_module.F90:1200-1211)
+      if (out->ultend) OUT2(out->ultend, ic, k) = (c.uln(k) - P2(in->ul, ic, k)) * icrm_run_time;
+      if (out->vltend) OUT2(out->vltend, ic, k) = (c.vln(k) - P2(in->vl, ic, k)) * icrm_run_time;
     }
     if (out->prectend) out->prectend[ic] = (c.colprec - c.prectend0) / ggr * factor_xy * icrm_run_time;
     if (out->precstend) out->precstend[ic] = (c.colprecs - c.precstend0) / ggr * factor_xy * icrm_run_time;
@@ -451,6 +454,8 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
       if (out->qltend) OUT2(out->qltend, ic, k) = 0.;
       if (out->qcltend) OUT2(out->qcltend, ic, k) = 0.;
       if (out->qiltend) OUT2(out->qiltend, ic, k) = 0.;
+      if (out->ultend) OUT2(out->ultend, ic, k) = 0.;
+      if (out->vltend) OUT2(out->vltend, ic, k) = 0.;
     }
     for (int k = 1; k <= nzm; k++)
       for (int j = 1; j <= ny; j++)

@@ -53,6 +53,7 @@ module crm_module
     type(c_ptr) :: mctot, mcup, mcdn, mcuup, mcudn, mu_crm, md_crm, du_crm, eu_crm, ed_crm
     type(c_ptr) :: flux_qt, fluxsgs_qt, tkez, tkesgsz, tkz, flux_u, flux_v, flux_qp, precflux
     type(c_ptr) :: qt_ls, qt_trans, qp_trans, qp_fall, qp_src, qp_evp, t_ls
+    type(c_ptr) :: ultend, vltend   ! SPMOMTRANS builds only, else c_null_ptr (ABI >= 2)
   end type
 
   interface
@@ -201,6 +202,11 @@ contains
     co%qt_ls = c_loc(crm_output%qt_ls);  co%qt_trans = c_loc(crm_output%qt_trans);  co%qp_trans = c_loc(crm_output%qp_trans)
     co%qp_fall = c_loc(crm_output%qp_fall);  co%qp_src = c_loc(crm_output%qp_src);  co%qp_evp = c_loc(crm_output%qp_evp)
     co%t_ls = c_loc(crm_output%t_ls)
+#if defined(SPMOMTRANS)
+    co%ultend = c_loc(crm_output%ultend);  co%vltend = c_loc(crm_output%vltend)
+#else
+    co%ultend = c_null_ptr;  co%vltend = c_null_ptr
+#endif
 
     rc = crm_b200_run(handle, d, ci, cs, cr, co)
     if (rc /= 0) then                               ! replaces task_abort()/endrun of kurant.F90:66-75, damping.F90:39-42
