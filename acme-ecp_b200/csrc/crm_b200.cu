@@ -74,7 +74,8 @@ struct Handle {
   size_t field_elems = 0, prof_elems = 0, col_elems = 0, slot_elems = 0, rad_elems = 0;
   std::vector<void *> allocs;
   CrmP p;                 // pointers filled at init; scalars per run
-  double *ubuf[4], *wbuf[4];
+  double *ubuf[4], *wbuf[4], *vbuf[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool d3 = false;        // 3-D CRM (ny > 1)
   double *stage = nullptr;            // one boundary-layout 3-D field (ld_max*nx*ny*nzm)
   double *esum = nullptr;
   double *in_dev = nullptr;           // packed device copy of the crm_input arrays
@@ -82,7 +83,7 @@ struct Handle {
   double *rnd_dev = nullptr;
   int *gcol_dev = nullptr;
   int ld_max = 0;
-  std::string err;
+  std::string err, launch_err;
   crm_run_stats_t stats;
   long long launches = 0;
   int precip_launches = 4;            // k_precip_b launches per sub-step (the last one runs any remaining sub-iterations)
@@ -112,6 +113,7 @@ static std::string kname(const char *s) { std::string n(s); while (!n.empty() &&
     CRM_LAUNCH(kern, grid, block, smem, 0, __VA_ARGS__);        \
     if ((h)->ktiming) ktime_add((h)->ktimes, #kern, (h)->ktimer.stop()); \
     (h)->launches++;                                            \
+    launch_check(h, #kern);                                     \
   } while (0)
 
 // Launch a kernel templated on the static tile geometry (NXT = nx when the tile uses the default CT of that nx, else 0).
@@ -120,11 +122,26 @@ static std::string kname(const char *s) { std::string n(s); while (!n.empty() &&
     switch ((h)->geo) {                                                                  \
       case 64: LAUNCH(h, kern<64>, grid, block, smem, __VA_ARGS__); break;               \
       case 32: LAUNCH(h, kern<32>, grid, block, smem, __VA_ARGS__); break;               \
+      case CRM_G3D: LAUNCH(h, kern<CRM_G3D>, grid, block, smem, __VA_ARGS__); break;     \
       default: LAUNCH(h, kern<0>, grid, block, smem, __VA_ARGS__); break;                \
     }                                                                                    \
   } while (0)
 
-int fail(Handle *h, int code, const std::string &msg) { h->err = msg; return code; }
+// a failed launch (bad configuration, too much shared memory ...) is recorded with the kernel's name and reported by the next fail()
+#ifdef CRM_EMU
+inline void launch_check(void *, const char *) {}
+#else
+#define launch_check(h, name)                                                                             \
+  do {                                                                                                    \
+    cudaError_t e_ = cudaPeekAtLastError();                                                               \
+    if (e_ != cudaSuccess && (h)->launch_err.empty()) (h)->launch_err = std::string(name) + ": " + cudaGetErrorString(e_); \
+  } while (0)
+#endif
+int fail(Handle *h, int code, const std::string &msg) {
+  h->err = msg;
+  if (!h->launch_err.empty()) { h->err += " [first failed launch: " + h->launch_err + "]"; h->launch_err.clear(); }
+  return code;
+}
 
 // copy rows [0,ncrms) of a boundary array (leading dim ld_src) into a device array with leading dim ld_dst
 int copy_rows(void *dst, int ld_dst, const void *src, int ld_src, int ncrms, size_t ncols) {
@@ -164,29 +181,38 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   g_init_err.clear();
   *handle = nullptr;
   if (d->micro != 0) { g_init_err = "crm_b200_init: only sam1mom (micro=0) is implemented on device (M2005: see DESIGN.md, out of round-1 scope)"; return 2; }
-  if (d->ny != 1 || d->yes3d != 0) { g_init_err = "crm_b200_init: 3-D CRM (ny>1) is not implemented on device yet (DESIGN.md)"; return 3; }
+  const bool d3 = d->ny > 1;
+  if (d->ny < 1 || (d3 && !d->yes3d) || (!d3 && d->yes3d)) { g_init_err = "crm_b200_init: RUN3D/YES3D mismatch: ny > 1 needs yes3d = 1, ny = 1 needs yes3d = 0 (setparm.F90:55-62)"; return 3; }
   if (d->nx < 8 || (d->nx & (d->nx - 1))) { g_init_err = "crm_b200_init: nx must be a power of two >= 8"; return 4; }
+  if (d3) {
+    const bool ok_geo = (d->nx == d->ny && (d->nx == 8 || d->nx == 16 || d->nx == 32)) || (d->nx == 16 && d->ny == 8);
+    if (!ok_geo) { g_init_err = "crm_b200_init: 3-D CRM geometries built into the library: 8x8, 16x16, 32x32, 16x8 (nx*ny <= 1024 columns per thread block)"; return 4; }
+  }
   if (d->nzm < 4 || d->plev < d->nzm) { g_init_err = "crm_b200_init: need 4 <= nzm <= plev"; return 5; }
-  if (d->nx_rad < 1 || d->nx % d->nx_rad != 0) { g_init_err = "crm_nx_rad must divide nx (crm_module.F90:686-692)"; return 6; }
+  if (d->nx_rad < 1 || d->nx % d->nx_rad != 0 || d->ny_rad < 1 || d->ny % d->ny_rad != 0) { g_init_err = "crm_nx_rad, crm_ny_rad must divide nx, ny (crm_module.F90:686-692)"; return 6; }
   if (d->ncrms < 1 || d->ld < d->ncrms) { g_init_err = "crm_b200_init: need 1 <= ncrms <= ld"; return 7; }
   if (dev_init(device)) { g_init_err = std::string("crm_b200_init: cannot select CUDA device: ") + dev_errstr(); return 8; }
   Handle *h = new Handle();
-  h->d0 = *d; h->device = device;
-  // CRM tile: P = nx*CT threads per block, at most CRM_MAX_P (kernels are compiled with __launch_bounds__(CRM_MAX_P))
-  int CT = CRM_MAX_P / d->nx;
+  h->d0 = *d; h->device = device; h->d3 = d3;
+  // CRM tile: P = nx*ny*CT threads per block, at most CRM_MAX_P (2-D) / CRM_MAX_P3 (3-D): the kernels are compiled with
+  // __launch_bounds__ of that size
+  const int nxy = d->nx * d->ny, maxp = d3 ? CRM_MAX_P3 : CRM_MAX_P;
+  int CT = CRM_MAX_P / nxy;
+  if (CT < 1) CT = 1;
   if (CT > 16) CT = 16;
   if (const char *e = getenv("CRM_B200_CT")) { int v = atoi(e); if (v >= 1 && v <= 32 && !(v & (v - 1))) CT = v; }
-  while (d->nx * CT > CRM_MAX_P && CT > 1) CT >>= 1;
-  while (d->nx * CT < 32) CT <<= 1;   // a block is at least one warp (warp-shuffle slab reductions)
-  if (CT < 1 || d->nx * CT > CRM_MAX_P) { g_init_err = "crm_b200_init: nx too large (nx <= 256)"; delete h; return 4; }
+  while (nxy * CT > maxp && CT > 1) CT >>= 1;
+  while (nxy * CT < 32) CT <<= 1;   // a block is at least one warp (warp-shuffle slab reductions)
+  if (CT < 1 || CT > 16 || nxy * CT > maxp) { g_init_err = "crm_b200_init: CRM too large for one thread block (nx <= 256 in 2-D, nx*ny <= 1024 in 3-D)"; delete h; return 4; }
   h->CT = CT;
   if (const char *e = getenv("CRM_B200_PRECIP_LAUNCHES")) { int v = atoi(e); if (v >= 1 && v <= 16) h->precip_launches = v; }
   h->geo = ((d->nx == 64 || d->nx == 32) && CT == crm_static_ct(d->nx)) ? d->nx : 0;
 #ifdef CRM_EMU
   h->geo = 0;
 #endif
+  if (d3) h->geo = CRM_G3D;
   h->ntiles = (d->ncrms + CT - 1) / CT;
-  h->P = d->nx * CT;
+  h->P = nxy * CT;
   const int nz = d->nzm + 1;
   h->nzp = nz + 1;
   h->tstride = (long long)nz * h->P;
@@ -194,19 +220,20 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   h->prof_elems = (size_t)h->ntiles * h->nzp * CT;
   h->col_elems = (size_t)h->ntiles * h->P;
   h->slot_elems = (size_t)h->ntiles * CT;
-  h->rad_elems = (size_t)h->ntiles * d->nzm * d->nx_rad * CT;
+  h->rad_elems = (size_t)h->ntiles * d->nzm * d->nx_rad * d->ny_rad * CT;
   h->ld_max = d->ld;
   CrmP &p = h->p;
   memset(&p, 0, sizeof(p));
-  p.ncrms = d->ncrms; p.ntiles = h->ntiles; p.CT = CT; p.nx = d->nx; p.ny = 1; p.nzm = d->nzm; p.nz = nz; p.nzp = h->nzp;
+  p.ncrms = d->ncrms; p.ntiles = h->ntiles; p.CT = CT; p.nx = d->nx; p.ny = d->ny; p.nzm = d->nzm; p.nz = nz; p.nzp = h->nzp;
   p.plev = d->plev; p.nx_rad = d->nx_rad; p.ny_rad = d->ny_rad; p.P = h->P; p.ld = d->ld; p.tstride = h->tstride;
   p.dx = d->dx; p.dy = d->dx;
   bool ok = true;
   auto F = [&](double *&ptr) { ptr = carve<double>(h, h->field_elems); ok = ok && ptr; };
   auto PRF = [&](double *&ptr) { ptr = carve<double>(h, h->prof_elems); ok = ok && ptr; };
   auto SL = [&](double *&ptr) { ptr = carve<double>(h, h->slot_elems); ok = ok && ptr; };
-  for (int n = 0; n < 4; n++) { F(h->ubuf[n]); F(h->wbuf[n]); }
+  for (int n = 0; n < 4; n++) { F(h->ubuf[n]); F(h->wbuf[n]); if (d3) F(h->vbuf[n]); }
   F(p.umf); F(p.wmf);
+  if (d3) { F(p.vmf); for (double **f : {&p.v0, &p.vtend, &p.vln, &p.vwle, &p.vwsb, &p.acc_v}) PRF(*f); }
   for (double **f : {&p.t, &p.qt, &p.qp, &p.qn, &p.tabs, &p.qv, &p.qcl, &p.qci, &p.qpl, &p.qpi, &p.tk, &p.tkh, &p.tke, &p.pbeta, &p.palfa, &p.wp}) F(*f);
   for (double **f : {&p.qrad, &p.rad_t, &p.rad_qv, &p.rad_qc, &p.rad_qi, &p.rad_cld}) { *f = carve<double>(h, h->rad_elems); ok = ok && *f; }
   for (double **f : {&p.z, &p.zi, &p.pres, &p.presi, &p.adz, &p.adzw, &p.rho, &p.rhow, &p.bet, &p.gamaz, &p.grdf_x, &p.grdf_z, &p.pdel, &p.tau,
@@ -224,7 +251,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   p.precsfc = carve<double>(h, h->col_elems); p.precssfc = carve<double>(h, h->col_elems);
   p.cfl_bits = carve<unsigned long long>(h, 2); p.prec_cfl_bits = p.cfl_bits ? p.cfl_bits + 1 : nullptr;
   p.flags = carve<int>(h, 4);
-  p.twc = carve<double>(h, d->nx); p.tws = carve<double>(h, d->nx);
+  p.twc = carve<double>(h, d->nx + d->ny); p.tws = carve<double>(h, d->nx + d->ny);   // x table, then y table
   h->stage = carve<double>(h, (size_t)d->ld * d->nx * d->ny * d->nzm);
   h->esum = carve<double>(h, (size_t)CRM_NESUM * h->prof_elems);
   h->in_dev = carve<double>(h, (size_t)d->ld * (11 * (size_t)(d->plev + 1) + 8));
@@ -241,18 +268,25 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   if (!micro_scalars(p.ms) || p.ms.csnow != 0.0625 || p.ms.cgrau != 0.125 || std::fabs(p.ms.crain - 0.2) > 1e-7) { g_init_err = "cannot compute gamma-function in precip_init"; crm_b200_free(h); return 10; }
 #ifndef CRM_EMU
   {
-    const int big = 200 * 1024;
-#define BIG(kern) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, big)
+    const int big = 226 * 1024;   // sm_100 allows 227 KB per block, static __shared__ included
+    bool attr_ok = true;
+#define BIG(kern) attr_ok = attr_ok && (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, big) == cudaSuccess)
 #define BIG_G(kern) BIG(kern<0>); BIG(kern<32>); BIG(kern<64>)
     BIG(k_epi_sums); BIG(k_prologue_fields);
     BIG_G(k_stats); BIG_G(k_p8_micro); BIG_G(k_mpdata); BIG_G(k_p7_diffuse); BIG_G(k_p3_mom); BIG_G(k_p1_forcing); BIG_G(k_p2_sgs);
     BIG_G(k_kurant); BIG_G(k_precip_a); BIG_G(k_precip_b);
+    BIG(k_stats<CRM_G3D>); BIG(k_p8_micro<CRM_G3D>); BIG(k_p7_diffuse<CRM_G3D>); BIG(k_p1_forcing<CRM_G3D>); BIG(k_kurant<CRM_G3D>);
+    BIG(k_precip_a<CRM_G3D>); BIG(k_precip_b<CRM_G3D>); BIG(k3_p2_sgs); BIG(k3_p3_mom); BIG(k3_mpdata); BIG(k_msa_a); BIG(k_msa_b); BIG(k_epi_precip);
+#define PRESS3_ATTR(NXV, NYV) BIG((k3_p4_press_fwd<NXV, NYV>)); BIG((k3_p5_press_bwd<NXV, NYV>));
+    PRESS3_ATTR(8, 8) PRESS3_ATTR(16, 16) PRESS3_ATTR(32, 32) PRESS3_ATTR(16, 8)
+#undef PRESS3_ATTR
 #define PRESS_ATTR(NXV) BIG((k_p4_press_fwd<NXV, 0>)); BIG((k_p5_press_bwd<NXV, 0>));
     PRESS_ATTR(8) PRESS_ATTR(16) PRESS_ATTR(32) PRESS_ATTR(64) PRESS_ATTR(128) PRESS_ATTR(256)
     BIG((k_p4_press_fwd<32, 32>)); BIG((k_p5_press_bwd<32, 32>)); BIG((k_p4_press_fwd<64, 64>)); BIG((k_p5_press_bwd<64, 64>));
 #undef PRESS_ATTR
 #undef BIG_G
 #undef BIG
+    if (!attr_ok) { g_init_err = std::string("crm_b200_init: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: ") + dev_errstr(); crm_b200_free(h); return 12; }
   }
 #endif
   if (dev_sync()) { g_init_err = std::string("crm_b200_init: ") + dev_errstr(); crm_b200_free(h); return 11; }
@@ -300,6 +334,8 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   h->ktimes.clear();
   CrmP &p = h->p;
   const int CT = h->CT, P = h->P, nx = d->nx, nzm = d->nzm, nz = nzm + 1, plev = d->plev, ld = d->ld, ncrms = d->ncrms;
+  const bool d3 = h->d3;
+  const int nxy = nx * d->ny, nrad = d->nx_rad * d->ny_rad;
   const int ntiles = (ncrms + CT - 1) / CT;
   p.ncrms = ncrms; p.ntiles = ntiles; p.ld = ld;
   p.dt = d->dt; p.dt_gl = d->dt_gl; p.igstep = d->igstep;
@@ -309,15 +345,17 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   auto red_bytes = [&](int nq) { return (size_t)CRM_RED_DOUBLES(nq, P, CT) * RED1; };
 
   // ---------------- cold start of the per-call state ----------------
-  for (int n = 0; n < 4; n++) { dev_zero(h->ubuf[n], fbytes); dev_zero(h->wbuf[n], fbytes); }
-  for (double *f : {p.umf, p.wmf, p.tk, p.tkh, p.tke, p.qv, p.qcl, p.qci, p.qpl, p.qpi}) dev_zero(f, fbytes);
-  for (double *f : {p.rad_t, p.rad_qv, p.rad_qc, p.rad_qi, p.rad_cld}) dev_zero(f, (size_t)ntiles * nzm * d->nx_rad * CT * 8);
+  int zrc = 0;   // any failed memset / copy of the input path is reported once, after the transfers
+  for (int n = 0; n < 4; n++) { zrc |= dev_zero(h->ubuf[n], fbytes); zrc |= dev_zero(h->wbuf[n], fbytes); if (d3) zrc |= dev_zero(h->vbuf[n], fbytes); }
+  for (double *f : {p.umf, p.wmf, p.tk, p.tkh, p.tke, p.qv, p.qcl, p.qci, p.qpl, p.qpi}) zrc |= dev_zero(f, fbytes);
+  if (d3) { zrc |= dev_zero(p.vmf, fbytes); zrc |= dev_zero(p.vwle, pbytes); zrc |= dev_zero(p.vwsb, pbytes); }
+  for (double *f : {p.rad_t, p.rad_qv, p.rad_qc, p.rad_qi, p.rad_cld}) zrc |= dev_zero(f, (size_t)ntiles * nzm * nrad * CT * 8);
   for (double *f : {p.precflux, p.qpfall, p.qpsrc, p.qpevp, p.uwle, p.uwsb, p.mkwle1, p.mkwle2, p.mkwsb1, p.mkwsb2, p.mkadv1, p.mkadv2, p.mkdiff1,
                     p.mkdiff2, p.s_cld, p.s_cldtop, p.s_gicewp, p.s_gliqwp, p.s_mcup, p.s_mcdn, p.s_mcuup, p.s_mcudn, p.s_mui, p.s_mdi})
-    dev_zero(f, pbytes);
-  for (double *f : {p.s_cltot, p.s_clhgh, p.s_clmed, p.s_cllow}) dev_zero(f, (size_t)ntiles * CT * 8);
-  dev_zero(p.precsfc, (size_t)ntiles * P * 8); dev_zero(p.precssfc, (size_t)ntiles * P * 8);
-  dev_zero(p.cfl_bits, 16); dev_zero(p.flags, 16);
+    zrc |= dev_zero(f, pbytes);
+  for (double *f : {p.s_cltot, p.s_clhgh, p.s_clmed, p.s_cllow}) zrc |= dev_zero(f, (size_t)ntiles * CT * 8);
+  zrc |= dev_zero(p.precsfc, (size_t)ntiles * P * 8); zrc |= dev_zero(p.precssfc, (size_t)ntiles * P * 8);
+  zrc |= dev_zero(p.cfl_bits, 16); zrc |= dev_zero(p.flags, 16);
 
   // ---------------- boundary inputs ----------------
   DevTimer tm;
@@ -328,8 +366,8 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
     double *q = h->in_dev;
     auto put = [&](const double *src, int ncols) -> const double * {
       double *dst = q; q += (size_t)ld * ncols;
-      if (is_dev_ptr(src)) { copy_rows(dst, ld, src, ld, ncrms, ncols); }
-      else { copy_rows(dst, ld, src, ld, ncrms, ncols); h2d += (long long)ncrms * ncols * 8; }
+      zrc |= copy_rows(dst, ld, src, ld, ncrms, ncols);
+      if (!is_dev_ptr(src)) h2d += (long long)ncrms * ncols * 8;
       return dst;
     };
     ei.zmid = put(in->zmid, plev); ei.zint = put(in->zint, plev + 1); ei.tl = put(in->tl, plev); ei.ql = put(in->ql, plev);
@@ -342,8 +380,14 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   {
     std::vector<double> c, s;
     twiddles(nx, d->twiddle_f32 != 0, c, s);
-    dev_copy2d(p.twc, nx * 8, c.data(), nx * 8, nx * 8, 1, 0);
-    dev_copy2d(p.tws, nx * 8, s.data(), nx * 8, nx * 8, 1, 0);
+    zrc |= dev_copy2d(p.twc, nx * 8, c.data(), nx * 8, nx * 8, 1, 0);
+    zrc |= dev_copy2d(p.tws, nx * 8, s.data(), nx * 8, nx * 8, 1, 0);
+    if (d3) {
+      const int ny = d->ny;
+      twiddles(ny, d->twiddle_f32 != 0, c, s);
+      zrc |= dev_copy2d(p.twc + nx, ny * 8, c.data(), ny * 8, ny * 8, 1, 0);
+      zrc |= dev_copy2d(p.tws + nx, ny * 8, s.data(), ny * 8, ny * 8, 1, 0);
+    }
   }
   // role assignment of the velocity buffers
   int iu = 0, ina = 1, inb = 2, inc = 3;
@@ -352,22 +396,24 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   auto load3 = [&](const double *src, double *dst, bool first_u) {
     const double *ext = src;
     int lde = ld;
-    if (!is_dev_ptr(src)) { copy_rows(h->stage, ld, src, ld, ncrms, ncols3); ext = h->stage; h2d += (long long)ncrms * ncols3 * 8; }
+    if (!is_dev_ptr(src)) { zrc |= copy_rows(h->stage, ld, src, ld, ncrms, ncols3); ext = h->stage; h2d += (long long)ncrms * ncols3 * 8; }
     if (first_u) LAUNCH(h, k_clamp_flag, 1, 32, 0, p, ext, lde);
-    LAUNCH(h, k_ext_to_int, ntiles * nzm, P, 0, p, ext, lde, nx, nzm, dst, h->tstride, P, 1.0);
+    LAUNCH(h, k_ext_to_int, ntiles * nzm, P, 0, p, ext, lde, nxy, nzm, dst, h->tstride, P, 1.0);
   };
   load3(st->u_wind, h->ubuf[iu], true);
+  if (d3) load3(st->v_wind, h->vbuf[iu], false);   // v * YES3D (crm_module.F90:390): in 2-D v is identically zero and not stored
   load3(st->w_wind, h->wbuf[iu], false);
   load3(st->temperature, p.tabs, false);
   load3(st->qt, p.qt, false);
   load3(st->qp, p.qp, false);
   load3(st->qn, p.qn, false);
   {
-    const size_t ncr = (size_t)d->nx_rad * d->ny_rad * nzm;
+    const size_t ncr = (size_t)nrad * nzm;
     const double *ext = rad->qrad;
-    if (!is_dev_ptr(ext)) { copy_rows(h->stage, ld, rad->qrad, ld, ncrms, ncr); ext = h->stage; h2d += (long long)ncrms * ncr * 8; }
-    LAUNCH(h, k_ext_to_int, ntiles * nzm, d->nx_rad * CT, 0, p, ext, ld, d->nx_rad, nzm, p.qrad, (long long)nzm * d->nx_rad * CT, d->nx_rad * CT, 1.0);
+    if (!is_dev_ptr(ext)) { zrc |= copy_rows(h->stage, ld, rad->qrad, ld, ncrms, ncr); ext = h->stage; h2d += (long long)ncrms * ncr * 8; }
+    LAUNCH(h, k_ext_to_int, ntiles * nzm, nrad * CT, 0, p, ext, ld, nrad, nzm, p.qrad, (long long)nzm * nrad * CT, nrad * CT, 1.0);
   }
+  if (zrc) return fail(h, 23, std::string("crm_b200_run: a memset or copy of the input path failed: ") + dev_errstr());
   if (dev_sync()) return fail(h, 23, std::string("crm_b200_run: input transfer failed: ") + dev_errstr());
   h->stats.ms_h2d = tm.stop();
   h->stats.h2d_bytes = h2d;
@@ -375,15 +421,18 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   DevTimer tk;
   tk.start();
   // ---------------- prologue ----------------
-  p.u = h->ubuf[iu]; p.w = h->wbuf[iu];
-  p.du_a = h->ubuf[ina]; p.du_b = h->ubuf[inb]; p.du_c = h->ubuf[inc];
-  p.dw_a = h->wbuf[ina]; p.dw_b = h->wbuf[inb]; p.dw_c = h->wbuf[inc];
+  auto set_roles = [&]() {
+    p.u = h->ubuf[iu]; p.w = h->wbuf[iu]; p.v = h->vbuf[iu];
+    p.du_a = h->ubuf[ina]; p.du_b = h->ubuf[inb]; p.du_c = h->ubuf[inc];
+    p.dv_a = h->vbuf[ina]; p.dv_b = h->vbuf[inb]; p.dv_c = h->vbuf[inc];
+    p.dw_a = h->wbuf[ina]; p.dw_b = h->wbuf[inb]; p.dw_c = h->wbuf[inc];
+  };
+  set_roles();
   const int slot_blocks = (ntiles * CT + 127) / 128;
   LAUNCH(h, k_prologue_grid, slot_blocks, 128, 0, p, ei);
   LAUNCH(h, k_prologue_fields, ntiles, P, red_bytes(9), p);
   LAUNCH(h, k_precip_init, (ntiles * nzm * CT + 127) / 128, 128, 0, p);
   if (d->igstep <= 1) {   // setperturb (crm_module.F90:677-681): RNG draws on the host like the reference
-    const int nxy = nx * d->ny;
     std::vector<double> rnd((size_t)ncrms * 5 * nxy);
     std::vector<int> gcol(ld);
     if (is_dev_ptr(in->gcol)) dev_copy2d(gcol.data(), ld * 4, in->gcol, ld * 4, (size_t)ncrms * 4, 1, 0);
@@ -395,7 +444,8 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
     dev_copy2d(h->rnd_dev, rnd.size() * 8, rnd.data(), rnd.size() * 8, rnd.size() * 8, 1, 0);
     LAUNCH(h, k_setperturb, slot_blocks, 128, 0, p, h->rnd_dev);
   }
-  LAUNCH(h, k_press_alfa, ntiles, P, 0, p);
+  if (d3) LAUNCH(h, k3_press_alfa, ntiles, P, 0, p);
+  else LAUNCH(h, k_press_alfa, ntiles, P, 0, p);
 
   int nstop = (int)(d->dt_gl / d->dt);   // crm_module.F90:712-713
   if (nstop < 1) return fail(h, 24, "crm_b200_run: dt_gl < crm_dt");
@@ -420,9 +470,10 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   while (nstep < nstop) {
     nstep++;
     dev_zero(p.cfl_bits, 8);
-    LAUNCH_G(h, k_kurant, ntiles, P, CRM_KURANT_SMEM(P, CT, h->nzp), p);
+    LAUNCH_G(h, k_kurant, ntiles, P, CRM_KURANT_SMEM(P, CT, h->nzp, d3), p);
     unsigned long long bits = 0;
     if (dev_copy2d(&bits, 8, p.cfl_bits, 8, 8, 1, 0)) return fail(h, 27, std::string("crm_b200_run: kurant readback failed: ") + dev_errstr());
+    if (!h->launch_err.empty()) return fail(h, 34, "crm_b200_run: a kernel launch failed");
     double cfl; memcpy(&cfl, &bits, 8);
     if (!(cfl == cfl) || cfl > 1e30) return fail(h, 28, "kurant(): non-finite CFL (model state blew up)");
     int ncycle = std::max(1, (int)std::ceil(cfl / R4(0.7)));
@@ -442,15 +493,22 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
       p.dtn = dtn; p.at = at; p.bt = bt; p.ct = ct; p.dt3na = dt3[na];
       p.nstep = nstep; p.icycle = icyc; p.ncycle = ncycle; p.nstop = nstop;
       p.last_substep = (nstep == nstop && icyc == ncycle) ? 1 : 0;   // statistics the reference overwrites every sub-step (mk*, uwle, qpsrc..)
-      p.u = h->ubuf[iu]; p.w = h->wbuf[iu];
-      p.du_a = h->ubuf[ina]; p.du_b = h->ubuf[inb]; p.du_c = h->ubuf[inc];
-      p.dw_a = h->wbuf[ina]; p.dw_b = h->wbuf[inb]; p.dw_c = h->wbuf[inc];
-      LAUNCH_G(h, k_p1_forcing, ntiles, P, CRM_P1_SMEM(P, CT, h->nzp), p);
+      set_roles();
+      LAUNCH_G(h, k_p1_forcing, ntiles, P, CRM_P1_SMEM(P, CT, h->nzp, d3), p);
       if (dbg_stop == 1) { dbg_break = true; break; }
-      LAUNCH_G(h, k_p2_sgs, ntiles, P, CRM_P2_SMEM(P, CT, h->nzp), p);
+      if (d3) LAUNCH(h, k3_p2_sgs, ntiles, P, CRM3_P2_SMEM(P, CT, h->nzp), p);
+      else LAUNCH_G(h, k_p2_sgs, ntiles, P, CRM_P2_SMEM(P, CT, h->nzp), p);
       if (dbg_stop == 2) { dbg_break = true; break; }
-      LAUNCH_G(h, k_p3_mom, ntiles, P, CRM_P3_SMEM(P, CT, h->nzp), p);
+      if (d3) LAUNCH(h, k3_p3_mom, ntiles, P, CRM3_P3_SMEM(P, CT, h->nzp), p);
+      else LAUNCH_G(h, k_p3_mom, ntiles, P, CRM_P3_SMEM(P, CT, h->nzp), p);
       if (dbg_stop == 3) { dbg_break = true; break; }
+#define PRESS3_CASE(NXV, NYV)                                                                          \
+  if (nx == NXV && d->ny == NYV) {                                                                     \
+    LAUNCH(h, (k3_p4_press_fwd<NXV, NYV>), ntiles, P, CRM3_P4_SMEM(P, CT, h->nzp, NXV, NYV), p);       \
+    LAUNCH(h, (k3_p5_press_bwd<NXV, NYV>), ntiles, P, CRM3_P5_SMEM(P, CT, h->nzp, NXV, NYV), p);       \
+  }
+      if (d3) { PRESS3_CASE(8, 8) PRESS3_CASE(16, 16) PRESS3_CASE(32, 32) PRESS3_CASE(16, 8) } else
+#undef PRESS3_CASE
 #define PRESS_CASE(NXV)                                                                           \
   case NXV:                                                                                       \
     LAUNCH(h, (k_p4_press_fwd<NXV, 0>), ntiles, P, CRM_P4_SMEM(P, CT, h->nzp, NXV), p);           \
@@ -467,9 +525,16 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
 #undef PRESS_CASE
       if (dbg_stop == 4) { dbg_break = true; break; }
       // advect_all_scalars.F90:32-64
-      LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, p.t, (double *)nullptr, (double *)nullptr, 0, (const int *)nullptr);
-      LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, p.qt, p.mkadv1, p.mkwle1, 1, (const int *)nullptr);
-      LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, p.qp, p.mkadv2, p.mkwle2, 1, (const int *)p.kqp);
+      if (d3) {
+        const size_t smem_mp3 = CRM3_MP_SMEM(P, CT, h->nzp);
+        LAUNCH(h, k3_mpdata, ntiles, P, smem_mp3, p, p.t, (double *)nullptr, (double *)nullptr, 0, (const int *)nullptr);
+        LAUNCH(h, k3_mpdata, ntiles, P, smem_mp3, p, p.qt, p.mkadv1, p.mkwle1, 1, (const int *)nullptr);
+        LAUNCH(h, k3_mpdata, ntiles, P, smem_mp3, p, p.qp, p.mkadv2, p.mkwle2, 1, (const int *)p.kqp);
+      } else {
+        LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, p.t, (double *)nullptr, (double *)nullptr, 0, (const int *)nullptr);
+        LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, p.qt, p.mkadv1, p.mkwle1, 1, (const int *)nullptr);
+        LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, p.qp, p.mkadv2, p.mkwle2, 1, (const int *)p.kqp);
+      }
       if (dbg_stop == 5) { dbg_break = true; break; }
       dev_zero(p.prec_cfl_bits, 8);
       LAUNCH_G(h, k_precip_a, ntiles, P, CRM_PRECIPA_SMEM(P, CT, h->nzp), p);
@@ -478,16 +543,16 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
         LAUNCH_G(h, k_precip_b, ntiles, P, CRM_PRECIPB_SMEM(P, CT, h->nzp), p, ip, ip == h->precip_launches ? 1 : 0);
       // uvw.F90: u <- dudt(nc) is a role rotation of the buffers (with the AB rotation of crm_module.F90:884-887)
       { int o_u = iu, o_a = ina, o_b = inb, o_c = inc; iu = o_c; ina = o_u; inb = o_a; inc = o_b; }
-      p.u = h->ubuf[iu]; p.w = h->wbuf[iu];
+      set_roles();
       if (dbg_stop == 6) { dbg_break = true; break; }
       LAUNCH_G(h, k_p7_diffuse, ntiles, P, CRM_P7_SMEM(P, CT, h->nzp), p);
       if (dbg_stop == 7) { dbg_break = true; break; }
       if (icyc == 1) LAUNCH(h, k_precip_init, (ntiles * nzm * CT + 127) / 128, 128, 0, p);
       LAUNCH(h, k_reset_kminmax, slot_blocks, 128, 0, p);
-      const size_t smem_p8 = CRM_P8_SMEM(P, CT);
+      const size_t smem_p8 = CRM_P8_SMEM(P, CT, d3);
       if (d->use_crm_accel && !ceaseflag) {
         LAUNCH_G(h, k_p8_micro, ntiles * ((nzm + CRM_P8_NL - 1) / CRM_P8_NL), P, smem_p8, p, 1, 0);
-        LAUNCH(h, k_msa_a, ntiles * nzm, P, red_bytes(3), p);
+        LAUNCH(h, k_msa_a, ntiles * nzm, P, red_bytes(4), p);
         int flags[4];
         if (dev_copy2d(flags, 16, p.flags, 16, 16, 1, 0)) return fail(h, 30, "crm_b200_run: MSA flag readback failed");
         if (flags[1]) {
@@ -505,7 +570,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
     }
     if (dbg_break) break;
     p.nstop = nstop;
-    LAUNCH_G(h, k_stats, ntiles, P, CRM_STATS_SMEM(P, CT, h->nzp, !(((nx / d->nx_rad) * CT <= 32) && !((nx / d->nx_rad) & ((nx / d->nx_rad) - 1)))), p);
+    LAUNCH_G(h, k_stats, ntiles, P, d3 ? CRM_STATS3_SMEM(P, CT, h->nzp) : CRM_STATS_SMEM(P, CT, h->nzp, !(((nx / d->nx_rad) * CT <= 32) && !((nx / d->nx_rad) & ((nx / d->nx_rad) - 1)))), p);
     // nprec statistic (device value of the last sub-step)
     if ((nstep & 15) == 0 || nstep == nstop) {
       unsigned long long pb2 = 0; dev_copy2d(&pb2, 8, p.prec_cfl_bits, 8, 8, 1, 0);
@@ -535,6 +600,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   LAUNCH(h, k_epi_precip, ntiles, P, red_bytes(4), p, eo, dt);
   LAUNCH(h, k_epi_profiles, (ncrms + 127) / 128, 128, 0, p, ei, eo, (const double *)h->esum, dt, dtn);
   if (dev_sync()) return fail(h, 31, std::string("crm_b200_run: kernel failure: ") + dev_errstr());
+  if (!h->launch_err.empty()) return fail(h, 34, "crm_b200_run: a kernel launch failed");
   h->stats.ms_kernels = tk.stop();
 
   // ---------------- boundary outputs ----------------
@@ -567,15 +633,16 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   auto store3 = [&](double *dst, const double *src, double scale) {
     if (!dst) return;
     if (is_dev_ptr(dst)) {
-      LAUNCH(h, k_int_to_ext, ntiles * nzm, P, 0, p, src, h->tstride, P, nx, nzm, dst, ld, scale);
+      LAUNCH(h, k_int_to_ext, ntiles * nzm, P, 0, p, src, h->tstride, P, nxy, nzm, dst, ld, scale);
     } else {
-      LAUNCH(h, k_int_to_ext, ntiles * nzm, P, 0, p, src, h->tstride, P, nx, nzm, h->stage, ld, scale);
+      LAUNCH(h, k_int_to_ext, ntiles * nzm, P, 0, p, src, h->tstride, P, nxy, nzm, h->stage, ld, scale);
       copy_rows(dst, ld, h->stage, ld, ncrms, ncols3);
       d2h += (long long)ncrms * ncols3 * 8;
     }
   };
   store3(st->u_wind, h->ubuf[iu], 1.0);
-  store3(st->v_wind, h->ubuf[iu], 0.0);   // 2-D: v == 0 (crm_module.F90:390, YES3D = 0)
+  if (d3) store3(st->v_wind, h->vbuf[iu], 1.0);
+  else store3(st->v_wind, h->ubuf[iu], 0.0);   // 2-D: v == 0 (crm_module.F90:390, YES3D = 0)
   store3(st->w_wind, h->wbuf[iu], 1.0);
   store3(st->temperature, p.tabs, 1.0);
   store3(st->qt, p.qt, 1.0); store3(st->qp, p.qp, 1.0); store3(st->qn, p.qn, 1.0);
@@ -583,14 +650,14 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   store3(out->qcl, p.qcl, 1.0); store3(out->qci, p.qci, 1.0); store3(out->qpl, p.qpl, 1.0); store3(out->qpi, p.qpi, 1.0);
   {
     const double tmp1 = ((double)d->nx_rad / (double)nx) * ((double)d->ny_rad / (double)d->ny) / (double)nstop;
-    const size_t ncr = (size_t)d->nx_rad * d->ny_rad * nzm;
+    const size_t ncr = (size_t)nrad * nzm;
     double *dsts[] = {rad->temperature, rad->qv, rad->qc, rad->qi, rad->cld};
     const double *srcs[] = {p.rad_t, p.rad_qv, p.rad_qc, p.rad_qi, p.rad_cld};
     for (int q = 0; q < 5; q++) {
       if (!dsts[q]) continue;
-      if (is_dev_ptr(dsts[q])) LAUNCH(h, k_epi_rad, ntiles * nzm, d->nx_rad * CT, 0, p, srcs[q], dsts[q], ld, tmp1);
+      if (is_dev_ptr(dsts[q])) LAUNCH(h, k_epi_rad, ntiles * nzm, nrad * CT, 0, p, srcs[q], dsts[q], ld, tmp1);
       else {
-        LAUNCH(h, k_epi_rad, ntiles * nzm, d->nx_rad * CT, 0, p, srcs[q], h->stage, ld, tmp1);
+        LAUNCH(h, k_epi_rad, ntiles * nzm, nrad * CT, 0, p, srcs[q], h->stage, ld, tmp1);
         copy_rows(dsts[q], ld, h->stage, ld, ncrms, ncr);
         d2h += (long long)ncrms * ncr * 8;
       }
@@ -604,8 +671,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   h->stats.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   h->last_nb_u = inb;
   // keep the role pointers of the final state for crm_b200_debug_fetch
-  p.u = h->ubuf[iu]; p.w = h->wbuf[iu]; p.du_a = h->ubuf[ina]; p.dw_a = h->wbuf[ina]; p.du_b = h->ubuf[inb]; p.dw_b = h->wbuf[inb];
-  p.du_c = h->ubuf[inc]; p.dw_c = h->wbuf[inc];
+  set_roles();
   return 0;
 }
 
@@ -693,7 +759,8 @@ extern "C" long long crm_b200_debug_fetch(void *handle, const char *name, double
   std::string nm(name);
   const double *src = nullptr;
   int nk = p.nzm;
-  if (nm == "u") src = p.u; else if (nm == "w") { src = p.w; nk = p.nz; } else if (nm == "t") src = p.t; else if (nm == "qt") src = p.qt;
+  if (nm == "u") src = p.u; else if (nm == "v" && p.v) src = p.v; else if (nm == "dvdt" && p.v) src = p.dv_b; else if (nm == "dvdt_a" && p.v) src = p.dv_a;
+  else if (nm == "vmf" && p.v) src = p.vmf; else if (nm == "w") { src = p.w; nk = p.nz; } else if (nm == "t") src = p.t; else if (nm == "qt") src = p.qt;
   else if (nm == "qp") src = p.qp; else if (nm == "qn") src = p.qn; else if (nm == "tabs") src = p.tabs; else if (nm == "qv") src = p.qv;
   else if (nm == "qcl") src = p.qcl; else if (nm == "qci") src = p.qci; else if (nm == "qpl") src = p.qpl; else if (nm == "qpi") src = p.qpi;
   else if (nm == "tk") src = p.tk; else if (nm == "tkh") src = p.tkh; else if (nm == "tke") src = p.tke;
@@ -708,14 +775,14 @@ extern "C" long long crm_b200_debug_fetch(void *handle, const char *name, double
     std::vector<double> tmp((size_t)h->field_elems);
     dev_copy2d(tmp.data(), tmp.size() * 8, src, tmp.size() * 8, (size_t)p.ntiles * h->tstride * 8, 1, 0);
     for (int k = 0; k < nk; k++)
-      for (int i = 0; i < p.nx; i++)
+      for (int i = 0; i < p.nx * p.ny; i++)
         for (int ic = 0; ic < p.ncrms; ic++) {
           int tile = ic / p.CT, lane = ic % p.CT;
-          host_buf[(size_t)ic + (size_t)p.ncrms * ((size_t)i + (size_t)p.nx * k)] = tmp[(size_t)tile * h->tstride + (size_t)k * p.P + i * p.CT + lane];
+          host_buf[(size_t)ic + (size_t)p.ncrms * ((size_t)i + (size_t)p.nx * p.ny * k)] = tmp[(size_t)tile * h->tstride + (size_t)k * p.P + i * p.CT + lane];
         }
     return (long long)need;
   }
-  LAUNCH(h, k_int_to_ext, p.ntiles * nk, p.P, 0, p, src, h->tstride, p.P, p.nx, nk, h->stage, p.ncrms, 1.0);
+  LAUNCH(h, k_int_to_ext, p.ntiles * nk, p.P, 0, p, src, h->tstride, p.P, p.nx * p.ny, nk, h->stage, p.ncrms, 1.0);
   if (dev_sync()) return -4;
   dev_copy2d(host_buf, need * 8, h->stage, need * 8, need * 8, 1, 0);
   return (long long)need;

@@ -24,7 +24,11 @@
 // REAL(4) literal promoted to double, as in the reference build without -r8
 #define R4(x) ((double)(x##f))
 
-#define CRM_MAX_P 256   // threads per block = nx * CT (one k-plane of one CRM tile)
+#define CRM_MAX_P 256   // threads per block = nx * CT (one k-plane of one CRM tile), 2-D CRMs
+#define CRM_MAX_P3 1024 // 3-D CRMs: threads per block = nx * ny * CT (kernels instantiated with NXT = CRM_G3D)
+#define CRM_G3D (-1)    // kernel template argument NXT: > 0 static 2-D tile geometry, 0 runtime 2-D geometry, CRM_G3D runtime 3-D geometry
+#define CRM_LB(NXT) ((NXT) < 0 ? CRM_MAX_P3 : CRM_MAX_P)
+#define CRM_LBMIN(NXT, nb) ((NXT) < 0 ? 1 : (nb))
 
 namespace crm {
 
@@ -76,6 +80,7 @@ struct CrmP {
   double *du_a, *du_b, *du_c;            // dudt(na,nb,nc)  (du_c receives the new u in adams)
   double *dw_a, *dw_b, *dw_c;
   double *umf, *wmf;                     // half-step mass-flux velocities (adams.F90:28-34)
+  double *v, *dv_a, *dv_b, *dv_c, *vmf;  // 3-D CRMs only (ny > 1); NULL in 2-D where v == 0 (crm_module.F90:390)
   double *t, *qt, *qp, *qn, *tabs, *qv, *qcl, *qci, *qpl, *qpi, *tk, *tkh, *tke;
   double *pbeta, *palfa;                 // tridiagonal scratch (pressure.F90:202-237)
   double *tri_a, *tri_c;                 // profiles: tridiagonal coefficients a(k), c(k) (pressure.F90:165-170)
@@ -87,6 +92,7 @@ struct CrmP {
   double *t0, *q0, *qv0, *tabs0, *u0, *qn0, *qp0, *t00;
   double *ttend, *qtend, *utend;
   double *tl, *ql, *qccl, *qiil, *uln;   // GCM profiles on CRM levels
+  double *v0, *vtend, *vln, *vwle, *vwsb, *acc_v;   // 3-D CRMs only
   double *accrsc, *accrsi, *accrrc, *coefice, *accrgc, *accrgi, *evaps1, *evaps2, *evapr1, *evapr2, *evapg1, *evapg2;
   double *precflux, *qpfall, *qpsrc, *qpevp, *uwle, *uwsb;
   double *mkwle1, *mkwle2, *mkwsb1, *mkwsb2, *mkadv1, *mkadv2, *mkdiff1, *mkdiff2;

@@ -40,26 +40,29 @@ __device__ __forceinline__ double ice_flux(const CrmP &p, const PipeQ &Q, const 
 // zero.F90, buoyancy.F90:17-36, forcing.F90:38-73, crm_module.F90:766-777, damping.F90:60-110, ice_fall.F90:34-165
 // Two TMA plane rings: qci (levels k..k+2 resident, 6 stages) and the nine single-level inputs (2 stages; three
 // blocks per SM keep enough loads in flight).
-#define CRM_P1_NPROF 13
-#define CRM_P1_SMEM(P, CT, nzp) \
-  (CRM_PIPE_BYTES(1, 6, P) + CRM_PIPE_BYTES(9, 2, P) + CRM_PROF_BYTES(CRM_P1_NPROF, nzp, CT) + (size_t)CRM_RED_DOUBLES(3, P, CT) * 8)
+#define CRM_P1_NPROF(d3) ((d3) ? 14 : 13)
+#define CRM_P1_SMEM(P, CT, nzp, d3) \
+  (CRM_PIPE_BYTES(1, 6, P) + CRM_PIPE_BYTES((d3) ? 10 : 9, 2, P) + CRM_PROF_BYTES(CRM_P1_NPROF(d3), nzp, CT) + (size_t)CRM_RED_DOUBLES(3, P, CT) * 8)
 template <int NXT>
-__global__ void __launch_bounds__(CRM_MAX_P) k_p1_forcing(CrmP p) {
+__global__ void __launch_bounds__(CRM_LB(NXT)) k_p1_forcing(CrmP p) {
   CRM_TILE_SETUP_T(NXT)
   CRM_DYN_SMEM(unsigned char, smraw);
   __shared__ int s_kd0;
   const int nzm = p.nzm, nz = p.nz, npf = p.nzp * CT;
+  constexpr int NFA = D3 ? 10 : 9;
   PlanePipe<1, 6> Q;
-  PlanePipe<9, 2> A;
+  PlanePipe<NFA, 2> A;
   Q.src[0] = p.qci + fb;
   A.src[0] = p.tabs + fb; A.src[1] = p.qv + fb; A.src[2] = p.qcl + fb; A.src[3] = p.qpl + fb; A.src[4] = p.qpi + fb;
   A.src[5] = p.t + fb; A.src[6] = p.qt + fb; A.src[7] = p.u + fb; A.src[8] = p.w + fb;
+  if (D3) A.src[NFA - 1] = p.v + fb;
   unsigned char *sm2 = smraw + CRM_PIPE_BYTES(1, 6, P);
-  double *sprof = (double *)(sm2 + CRM_PIPE_BYTES(9, 2, P));
-  double *red = sprof + CRM_P1_NPROF * npf;
+  double *sprof = (double *)(sm2 + CRM_PIPE_BYTES(NFA, 2, P));
+  double *red = sprof + CRM_P1_NPROF(D3) * npf;
   {
     const double *const g[11] = {p.rho, p.adz, p.tabs0, p.qv0, p.qn0, p.qp0, p.bet, p.ttend, p.qtend, p.utend, p.tau};
     stage_profiles<11>(sprof, g, tile, p.nzp, CT, tid, P);
+    if (D3) { const double *const gv[1] = {p.vtend}; stage_profiles<1>(sprof + 13 * npf, gv, tile, p.nzp, CT, tid, P); }
   }
   // per-(CRM, level) quotients evaluated once per block instead of once per cell (the FP64 divide runs on the MUFU pipe):
   // slot 6 = bet(k)*adz(k-1)/(adz(k)+adz(k-1)) (buoyancy.F90:27-28, replaces bet), 11 = bet(k-1)*adz(k)/(adz(k)+adz(k-1)),
@@ -88,8 +91,12 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p1_forcing(CrmP p) {
   const int kd0 = s_kd0;   // lowest level at which any CRM of the tile is in the sponge
   const int nxy = nx_ * p.ny;
   const double inxy = 1. / (double)nxy;
-  const int irad = i / (nx_ / p.nx_rad);
-  const long long rb = ((long long)tile * nzm) * (p.nx_rad * CT) + irad * CT + lane;
+  // radiation column of this CRM column (crm_module.F90:766-777): i_rad = (i-1)/(nx/nx_rad)+1, j_rad likewise
+  const int radp = p.nx_rad * p.ny_rad * CT;
+  int irad;
+  if (D3) { const int jy_ = i / nx_, ix_ = i - jy_ * nx_; irad = (jy_ / (p.ny / p.ny_rad)) * p.nx_rad + ix_ / (nx_ / p.nx_rad); }
+  else irad = i / (nx_ / p.nx_rad);
+  const long long rb = ((long long)tile * nzm) * radp + irad * CT + lane;
   double expr_km1 = 0.;
   double fz_k = ice_flux(p, Q, s_rho, s_adz, tid, lane, CT, 1, kmin, kmax, dz);
   double qrad_k = p.qrad[rb];
@@ -97,7 +104,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p1_forcing(CrmP p) {
     __syncthreads();
     CRM_PIPE_STEP(Q, k, nzm, 5, 2)
     CRM_PIPE_STEP(A, k, nzm, 1, 0)
-    const double qrad_next = (k < nzm) ? p.qrad[rb + (long long)k * (p.nx_rad * CT)] : 0.;   // software prefetch of the next level
+    const double qrad_next = (k < nzm) ? p.qrad[rb + (long long)k * radp] : 0.;   // software prefetch of the next level
     const double tabs = A.plane(0, k)[tid], qv = A.plane(1, k)[tid], qcl = A.plane(2, k)[tid], qci = Q.plane(0, k)[tid],
                  qpl = A.plane(3, k)[tid], qpi = A.plane(4, k)[tid];
     const double tabs0 = SPF(2, k), qv0 = SPF(3, k), qn0 = SPF(4, k), qp0 = SPF(5, k);
@@ -121,20 +128,36 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p1_forcing(CrmP p) {
       }
     }
     double du = 0. + SPF(9, k);
+    double dv = 0.;
+    if (D3) dv = 0. + SPF(13, k);
     // --- radiative heating
     t = t + qrad_k * dtn;
     qrad_k = qrad_next;
     // --- damping
     if (k >= kd0) {
       const double u = A.plane(7, k)[tid];
-      double v[2] = {u * inxy, t * inxy};   // == u/nxy, t/nxy exactly: nx*ny is a power of two
-      block_sum<2>(v, tid, P, CT, red);
-      if (k >= nzm - ndamp) {
-        const double tau = SPF(10, k);
-        du = du - (u - v[0]) * tau;
-        dw = dw - A.plane(8, k)[tid] * tau;
-        t = t - dtn * (t - v[1]) * tau;
-        qt = qt - dtn * (qv - qv0) * tau;
+      if (D3) {
+        const double vv = A.plane(NFA - 1, k)[tid];
+        double v[3] = {u * inxy, t * inxy, vv * inxy};
+        block_sum<3>(v, tid, P, CT, red);
+        if (k >= nzm - ndamp) {
+          const double tau = SPF(10, k);
+          du = du - (u - v[0]) * tau;
+          dv = dv - (vv - v[2]) * tau;
+          dw = dw - A.plane(8, k)[tid] * tau;
+          t = t - dtn * (t - v[1]) * tau;
+          qt = qt - dtn * (qv - qv0) * tau;
+        }
+      } else {
+        double v[2] = {u * inxy, t * inxy};   // == u/nxy, t/nxy exactly: nx*ny is a power of two
+        block_sum<2>(v, tid, P, CT, red);
+        if (k >= nzm - ndamp) {
+          const double tau = SPF(10, k);
+          du = du - (u - v[0]) * tau;
+          dw = dw - A.plane(8, k)[tid] * tau;
+          t = t - dtn * (t - v[1]) * tau;
+          qt = qt - dtn * (qv - qv0) * tau;
+        }
       }
     }
     // --- ice fall
@@ -155,6 +178,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p1_forcing(CrmP p) {
     }
     fz_k = fz_kp1;
     F3(p.t, k) = t; F3(p.qt, k) = qt; F3(p.du_a, k) = du; F3(p.dw_a, k) = dw;
+    if (D3) F3(p.dv_a, k) = dv;
   }
   F3(p.dw_a, nz) = 0.;
 #undef SPF

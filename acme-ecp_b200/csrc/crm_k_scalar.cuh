@@ -354,7 +354,7 @@ __device__ __forceinline__ double term_vel_qp(const MicroScalars &m, double qplo
 // k_precip_b is the identity and is skipped.
 #define CRM_PRECIPA_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(2, 3, P) + CRM_PROF_BYTES(4, nzp, CT) + (size_t)(P) * 8)
 template <int NXT>
-__global__ void __launch_bounds__(CRM_MAX_P) k_precip_a(CrmP p) {
+__global__ void __launch_bounds__(CRM_LB(NXT)) k_precip_a(CrmP p) {
   CRM_TILE_SETUP_T(NXT)
   CRM_DYN_SMEM(unsigned char, smraw);
   __shared__ int s_kt;
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_precip_a(CrmP p) {
 //    because 1/(rho*adz) is constant over the slab (microphysics.F90:772-776).
 #define CRM_PRECIPB_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(4, 6, P) + CRM_PROF_BYTES(5, nzp, CT) + (size_t)2 * CRM_RED_DOUBLES(1, P, CT) * 8)
 template <int NXT>
-__global__ void __launch_bounds__(CRM_MAX_P, 3) k_precip_b(CrmP p, int iprec0, int run_rest) {
+__global__ void __launch_bounds__(CRM_LB(NXT), CRM_LBMIN(NXT, 3)) k_precip_b(CrmP p, int iprec0, int run_rest) {
   CRM_TILE_SETUP_T(NXT)
   CRM_DYN_SMEM(unsigned char, smraw);
   const double prec_cfl = __longlong_as_double((long long)*p.prec_cfl_bits);
@@ -588,9 +588,9 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_precip_b(CrmP p, int iprec0, i
 // Inputs stream through a 4-stage TMA plane ring (tkh, t, qt, qp; levels k and k+1 resident, 2 levels of prefetch).
 #define CRM_P7_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(4, 4, P) + CRM_PROF_BYTES(6, nzp, CT) + (size_t)CRM_RED_DOUBLES(4, P, CT) * 8)
 template <int NXT>
-__global__ void __launch_bounds__(CRM_MAX_P) k_p7_diffuse(CrmP p) {
+__global__ void __launch_bounds__(CRM_LB(NXT)) k_p7_diffuse(CrmP p) {
   CRM_TILE_SETUP_T(NXT)
-  CRM_XNEIGH
+  CRM_XYNEIGH
   CRM_DYN_SMEM(unsigned char, smraw);
   const int nzm = p.nzm, npf = p.nzp * CT;
   PlanePipe<4, 4> pipe;
@@ -639,6 +639,11 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_p7_diffuse(CrmP p) {
       const double flx_i = -(rdx5 * (tkh_i + tkh_p)) * (f_p - f_i);
       const double flx_m = -(rdx5 * (tkh_m + tkh_i)) * (f_i - f_m);
       double dfdt = 0. - (flx_i - flx_m);
+      if (D3) {   // diffuse_scalar3D.F90:102-141 (dy == dx, grdf_y == grdf_x: rdy5 == rdx5)
+        const double fly_j = -(rdx5 * (tkh_i + tkh_k[tjp])) * (f_k[tjp] - f_i);
+        const double fly_b = -(rdx5 * (tkh_k[tjm] + tkh_i)) * (f_i - f_k[tjm]);
+        dfdt = dfdt - (fly_j - fly_b);
+      }
       flz[s] = (k <= nzm - 1) ? -tkz * (f_c[tid] - f_i) * rhoi : 0.;
       dfdt = p.dtn * (dfdt - (flz[s] - flz_km1[s]) * rhoi2);
       fold[s] = f_i;
@@ -805,10 +810,13 @@ __device__ inline void precip_proc_cell(const CrmP &p, int pb, int CT, int k, do
 // smem: X[8][NL*P]: cell exchange (5 inputs / 6 results in place), then each thread overwrites its own column with the 8
 // values of the transposed slab sums (quantity stride NL*P) + queue + flags.
 #define CRM_P8_NL 2
-#define CRM_P8_SMEM(P, CT) ((size_t)8 * CRM_P8_NL * (P) * 8 + (CRM_P8_NL * (P) + 64 + CRM_P8_NL * 40) * sizeof(int))
+#define CRM_P8_CNT(P) (2 * CRM_P8_NL * ((P) / 32) > 64 ? 2 * CRM_P8_NL * ((P) / 32) : 64)
+#define CRM_P8_SMEM(P, CT, d3) ((size_t)((d3) ? 9 : 8) * CRM_P8_NL * (P) * 8 + (CRM_P8_NL * (P) + CRM_P8_CNT(P) + CRM_P8_NL * 40) * sizeof(int))
 template <int NXT>
-__global__ void __launch_bounds__(CRM_MAX_P, 4) k_p8_micro(CrmP p, int do_micro, int do_diag) {
+__global__ void __launch_bounds__(CRM_LB(NXT), CRM_LBMIN(NXT, 4)) k_p8_micro(CrmP p, int do_micro, int do_diag) {
   constexpr int NL = CRM_P8_NL;
+  constexpr bool D3 = NXT < 0;
+  constexpr int NQ = D3 ? 9 : 8;   // slab sums: u, t, tabs, q, qn, qp, qpsrc, qpevp (+ v in 3-D)
   const int tid = threadIdx.x;
   const int CT = (NXT) > 0 ? crm_static_ct(NXT) : p.CT, P = (NXT) > 0 ? (NXT) * crm_static_ct(NXT) : p.P;
   const int nkb = (p.nzm + NL - 1) / NL;
@@ -819,9 +827,9 @@ __global__ void __launch_bounds__(CRM_MAX_P, 4) k_p8_micro(CrmP p, int do_micro,
   const int cb = tile * CT + lane;
   const int NC = NL * P;
   CRM_DYN_SMEM(double, X);                 // X[j*NC + cell], j = 0..7
-  int *qcell = (int *)(X + 8 * NC);        // NC queue entries
-  int *cnt = qcell + NC;                   // [2][NL*nw] class counts per (level, warp), NL*nw <= 32
-  int *sflag = cnt + 64;                   // [NL][2*CT+1 (<= 40)]
+  int *qcell = (int *)(X + NQ * NC);       // NC queue entries
+  int *cnt = qcell + NC;                   // [2][NL*nw] class counts per (level, warp)
+  int *sflag = cnt + CRM_P8_CNT(P);        // [NL][2*CT+1 (<= 40)]
   const int sub = tid & 31, wrp = tid >> 5, nw = P >> 5;
   double t[NL], q[NL], qp[NL];
 #pragma unroll
@@ -856,14 +864,14 @@ __global__ void __launch_bounds__(CRM_MAX_P, 4) k_p8_micro(CrmP p, int do_micro,
         }
       }
       mA[l] = __ballot_sync(0xffffffffu, isA[l]); mB[l] = __ballot_sync(0xffffffffu, isB[l]);
-      if (sub == 0) { cnt[l * nw + wrp] = __popc(mA[l]); cnt[32 + l * nw + wrp] = __popc(mB[l]); }
+      if (sub == 0) { cnt[l * nw + wrp] = __popc(mA[l]); cnt[NL * nw + l * nw + wrp] = __popc(mB[l]); }
     }
     __syncthreads();
     int offA[NL], offB[NL];
 #pragma unroll
     for (int l = 0; l < NL; l++) { offA[l] = 0; offB[l] = 0; }
     for (int g = 0; g < NL * nw; g++) {
-      const int a = cnt[g], b = cnt[32 + g];
+      const int a = cnt[g], b = cnt[NL * nw + g];
 #pragma unroll
       for (int l = 0; l < NL; l++) if (g < l * nw + wrp) { offA[l] += a; offB[l] += b; }
       nA += a; nB += b;
@@ -916,9 +924,10 @@ __global__ void __launch_bounds__(CRM_MAX_P, 4) k_p8_micro(CrmP p, int do_micro,
       F3(p.tabs, k) = tabs;
       if (qcl + qci > 0. && tabs < R4(273.15)) sf[lane] = 1;
     }
-    double v[8];
+    double v[NQ];
     v[0] = F3(p.u, k); v[1] = t[l]; v[2] = tabs; v[3] = qv + qcl + qci; v[4] = qcl + qci; v[5] = qpl + qpi; v[6] = dsrc; v[7] = devp;
-    tr_put<8>(v, tid, NC, X + l * P);   // own column of X: nobody else reads it after phase 1
+    if (D3) v[NQ - 1] = F3(p.v, k);
+    tr_put<NQ>(v, tid, NC, X + l * P);   // own column of X: nobody else reads it after phase 1
   }
   __syncthreads();
   for (int l = 0; l < NL; l++) {
@@ -926,9 +935,11 @@ __global__ void __launch_bounds__(CRM_MAX_P, 4) k_p8_micro(CrmP p, int do_micro,
     if (k > p.nzm) break;
     const double *trl = X + l * P;
     const int *sf = sflag + l * 40;
-    tr_get<8>(tid, P, CT, NC, trl, [&](int qq, int ln, double sum) {
+    tr_get<NQ>(tid, P, CT, NC, trl, [&](int qq, int ln, double sum) {
       const int o = tile * p.nzp * CT + k * CT + ln;
-      if (qq < 6) {
+      if (D3 && qq == 8) {
+        if (do_diag) p.v0[o] = sum * ((double)1.f / (double)(p.nx * p.ny));
+      } else if (qq < 6) {
         if (do_diag) {
           const double coef = (double)1.f / (double)(p.nx * p.ny);
           const double m = sum * coef;
@@ -961,7 +972,7 @@ __global__ void k_reset_kminmax(CrmP p) {
 
 // accelerate_crm.F90:166-225: horizontal means, MSA tendencies, batch-global ceaseflag.  Plane kernel.
 // smem: CRM_RED_DOUBLES(3,P,CT)
-__global__ void __launch_bounds__(CRM_MAX_P) k_msa_a(CrmP p) {
+__global__ void __launch_bounds__(CRM_MAX_P3) k_msa_a(CrmP p) {
   const int tid = threadIdx.x, P = p.P, CT = p.CT;
   const int tile = blockIdx.x / p.nzm, k = blockIdx.x - tile * p.nzm + 1;
   const int i = tid / CT, lane = tid - i * CT;
@@ -969,19 +980,20 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_msa_a(CrmP p) {
   const int pb = tile * p.nzp * CT + lane;
   CRM_DYN_SMEM(double, red);
   const double coef = 1. / (double)(p.nx * p.ny);
-  double v[3] = {F3(p.t, k) * coef, (F3(p.qcl, k) + F3(p.qci, k) + F3(p.qv, k)) * coef, F3(p.u, k) * coef};
-  block_sum_lead<3>(v, tid, P, CT, red);
+  double v[4] = {F3(p.t, k) * coef, (F3(p.qcl, k) + F3(p.qci, k) + F3(p.qv, k)) * coef, F3(p.u, k) * coef, p.v ? F3(p.v, k) * coef : 0.};
+  block_sum_lead<4>(v, tid, P, CT, red);
   if (i == 0) {
     const double ta = v[0] - PF(p.t0, k);
     PF(p.acc_t, k) = ta;
     PF(p.acc_q, k) = v[1] - PF(p.q0, k);
     PF(p.acc_u, k) = v[2] - PF(p.u0, k);
+    if (p.v) PF(p.acc_v, k) = v[3] - PF(p.v0, k);
     if (fabs(ta) > R4(5.) && tile * CT + lane < p.ncrms) atomicOr(&p.flags[1], 1);
   }
 }
 
 // accelerate_crm.F90:250-352: apply the tendencies, fix negative moisture.  Plane kernel.  smem: CRM_RED_DOUBLES(2,P,CT)
-__global__ void __launch_bounds__(CRM_MAX_P) k_msa_b(CrmP p) {
+__global__ void __launch_bounds__(CRM_MAX_P3) k_msa_b(CrmP p) {
   const int tid = threadIdx.x, P = p.P, CT = p.CT;
   const int tile = blockIdx.x / p.nzm, k = blockIdx.x - tile * p.nzm + 1;
   const int i = tid / CT, lane = tid - i * CT;
@@ -991,7 +1003,10 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_msa_b(CrmP p) {
   CRM_DYN_SMEM(double, red);
   const double fac = p.accel_factor;
   F3(p.t, k) = dmax(R4(50.), F3(p.t, k) + fac * PF(p.acc_t, k));
-  if (p.accel_uv) F3(p.u, k) = F3(p.u, k) + fac * PF(p.acc_u, k);
+  if (p.accel_uv) {
+    F3(p.u, k) = F3(p.u, k) + fac * PF(p.acc_u, k);
+    if (p.v) F3(p.v, k) = F3(p.v, k) + fac * PF(p.acc_v, k);
+  }
   double qt = F3(p.qt, k) + fac * PF(p.acc_q, k);
   double v[2] = {(qt < 0.) ? 0. : qt, (qt < 0.) ? qt : 0.};
   block_sum<2>(v, tid, P, CT, red);

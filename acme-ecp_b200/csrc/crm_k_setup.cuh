@@ -17,6 +17,7 @@ namespace crm {
 // index arithmetic folds into shifts/immediates.  NXT == 0: geometry from the parameter block.
 __host__ __device__ constexpr int crm_static_ct(int nx) { return nx <= 0 ? 0 : (CRM_MAX_P / nx > 16 ? 16 : (CRM_MAX_P / nx < 1 ? 1 : CRM_MAX_P / nx)); }
 #define CRM_TILE_SETUP_T(NXT)                                                 \
+  constexpr bool D3 = (NXT) < 0;                                              \
   const int tid = threadIdx.x, tile = blockIdx.x;                             \
   const int CT = (NXT) > 0 ? crm_static_ct(NXT) : p.CT;                       \
   const int nx_ = (NXT) > 0 ? (NXT) : p.nx;                                   \
@@ -25,7 +26,17 @@ __host__ __device__ constexpr int crm_static_ct(int nx) { return nx <= 0 ? 0 : (
   const long long fb = (long long)tile * p.tstride;                           \
   const int pb = tile * p.nzp * CT + lane;                                    \
   const int cb = tile * CT + lane;                                            \
-  (void)i; (void)fb; (void)pb; (void)cb; (void)nx_;
+  (void)i; (void)fb; (void)pb; (void)cb; (void)nx_; (void)D3;
+// In-plane neighbours of a 3-D tile: tid = ((jy*nx + ix)*CT + lane), periodic in x and y (index arithmetic instead of the
+// reference's halo exchanges).  Valid in 2-D too (ny = 1: tjm = tjp = tid).
+#define CRM_XYNEIGH                                                           \
+  const int ny_ = D3 ? p.ny : 1, rowl = nx_ * CT;                             \
+  const int jy = D3 ? i / nx_ : 0, ix = i - jy * nx_;                         \
+  const int tm1 = (ix == 0) ? tid + rowl - CT : tid - CT;                     \
+  const int tp1 = (ix == nx_ - 1) ? tid - rowl + CT : tid + CT;               \
+  const int tjm = (jy == 0) ? tid + P - rowl : tid - rowl;                    \
+  const int tjp = (jy == ny_ - 1) ? tid - P + rowl : tid + rowl;              \
+  (void)tm1; (void)tp1; (void)tjm; (void)tjp; (void)ix; (void)jy; (void)ny_;
 #define F3(a, k) a[fb + (long long)((k)-1) * P + tid]
 #define F3X(a, k, t2) a[fb + (long long)((k)-1) * P + (t2)]
 #define PF(a, k) a[pb + (k)*CT]
@@ -115,6 +126,7 @@ __global__ void k_prologue_grid(CrmP p, ExtIn in) {
     PF(p.pdel, k) = IN(in.pdel, l);
     PF(p.tl, k) = IN(in.tl, l); PF(p.ql, k) = IN(in.ql, l); PF(p.qccl, k) = IN(in.qccl, l); PF(p.qiil, k) = IN(in.qiil, l);
     PF(p.uln, k) = dmin(umax, dmax(-umax, IN(in.ul, l)));
+    if (p.vln) PF(p.vln, k) = dmin(umax, dmax(-umax, IN(in.vl, l))) * 1.;   // * YES3D (crm_module.F90:570); 2-D: vln == 0, not stored
   }
   PF(p.zi, nz) = IN(in.zint, plev - nz + 2) - IN(in.zint, plev + 1);
   PF(p.presi, nz) = IN(in.pint, plev - nz + 2) / R4(100.);
@@ -170,7 +182,7 @@ __device__ __forceinline__ void micro_diag_cell(const MicroScalars &ms, double q
 
 // crm_module.F90:400-417, 477-581: clamp, micro_init->micro_diagnose, t from tabs, slab means, LS tendencies.
 // Block per tile, k-march.  smem: CRM_RED_DOUBLES(10, P, CT).
-__global__ void __launch_bounds__(CRM_MAX_P) k_prologue_fields(CrmP p) {
+__global__ void __launch_bounds__(CRM_MAX_P3) k_prologue_fields(CrmP p) {
   CRM_TILE_SETUP
   CRM_DYN_SMEM(double, red);
   const int nzm = p.nzm;
@@ -182,8 +194,12 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_prologue_fields(CrmP p) {
   int kmin = nzm + 1, kmax = 0;
   if (tid == 0) p.kqp[tile] = nzm;   // no level skipping in the first sub-step of a call
   for (int k = 1; k <= nzm; k++) {
-    double u = F3(p.u, k);
+    double u = F3(p.u, k), vv = 0.;
     if (clamp) { u = dmin(umax, dmax(-umax, u)); F3(p.u, k) = u; }
+    if (p.v) {
+      vv = F3(p.v, k);
+      if (clamp) { vv = dmin(umax, dmax(-umax, vv)); F3(p.v, k) = vv; }
+    }
     double tabs = F3(p.tabs, k), qt = F3(p.qt, k), qn = F3(p.qn, k), qp = F3(p.qp, k);
     double qv, qcl, qci, qpl, qpi;
     micro_diag_cell(p.ms, qt, qn, qp, tabs, qv, qcl, qci, qpl, qpi);
@@ -196,7 +212,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_prologue_fields(CrmP p) {
     if (qcl + qci > 0. && tabs < R4(273.15)) { kmin = imin(kmin, k); kmax = imax(kmax, k); }
     double v[9];
     v[0] = u; v[1] = t; v[2] = t + CRM_FAC_COND * qpl + CRM_FAC_SUB * qpi; v[3] = tabs; v[4] = qv + qcl + qci;
-    v[5] = qv; v[6] = qcl + qci; v[7] = qpl + qpi; v[8] = 0.;
+    v[5] = qv; v[6] = qcl + qci; v[7] = qpl + qpi; v[8] = vv;
     block_sum_lead<9>(v, tid, P, CT, red);
     if (i == 0) {
       double u0 = v[0] * factor_xy, t0 = v[1] * factor_xy, t00 = v[2] * factor_xy, tabs0 = v[3] * factor_xy, q0 = v[4] * factor_xy;
@@ -206,6 +222,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_prologue_fields(CrmP p) {
       PF(p.ttend, k) = (tl + PF(p.gamaz, k) - CRM_FAC_COND * (qccl + qiil) - CRM_FAC_FUS * qiil - t00) * idt_gl;
       PF(p.qtend, k) = (ql + qccl + qiil - q0) * idt_gl;
       PF(p.utend, k) = (PF(p.uln, k) - u0) * idt_gl;
+      if (p.v) { const double v0 = v[8] * factor_xy; PF(p.v0, k) = v0; PF(p.vtend, k) = (PF(p.vln, k) - v0) * idt_gl; }
     }
   }
   double v[2] = {colprec, colprecs};
@@ -295,15 +312,17 @@ __global__ void k_setperturb(CrmP p, const double *rnd) {
 // kurant.F90:9-64 + sgs.F90:329-372.  max over i commutes with the per-level scaling, so every thread folds its own
 // column and only one block max + one atomicMax on the (non-negative) double bit pattern are needed.
 // u, w, tkh stream through a TMA plane ring (4 stages, levels k and k+1 resident).
-#define CRM_KURANT_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(3, 4, P) + CRM_PROF_BYTES(4, nzp, CT) + (size_t)(P) * 8)
+#define CRM_KURANT_SMEM(P, CT, nzp, d3) (CRM_PIPE_BYTES((d3) ? 4 : 3, 4, P) + CRM_PROF_BYTES(4, nzp, CT) + (size_t)(P) * 8)
 template <int NXT>
-__global__ void __launch_bounds__(CRM_MAX_P) k_kurant(CrmP p) {
+__global__ void __launch_bounds__(CRM_LB(NXT)) k_kurant(CrmP p) {
   CRM_TILE_SETUP_T(NXT)
   CRM_DYN_SMEM(unsigned char, smraw);
   const int nzm = p.nzm, nz = p.nz, npf = p.nzp * CT;
-  PlanePipe<3, 4> R;
+  constexpr int NF = D3 ? 4 : 3;
+  PlanePipe<NF, 4> R;
   R.src[0] = p.u + fb; R.src[1] = p.w + fb; R.src[2] = p.tkh + fb;
-  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(3, 4, P));
+  if (D3) R.src[NF - 1] = p.v + fb;
+  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(NF, 4, P));
   double *red = sprof + 4 * npf;
   {
     const double *const g[3] = {p.adzw, p.grdf_z, p.grdf_x};
@@ -312,8 +331,8 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_kurant(CrmP p) {
   }
   R.init(smraw, P, tid);
   CRM_PIPE_PROLOGUE(R, nz, 3, 1)
-  const double idx = 1. / p.dx;
-  const double sq = sqrt(idx * idx);
+  const double idx = 1. / p.dx, idy = 1. / p.dy;
+  const double sq = D3 ? sqrt(idx * idx + 1 * (idy * idy)) : sqrt(idx * idx);
   const double dz = p.dz[cb];
   const double idx2 = 1. / (p.dx * p.dx);
   double cfl = 0.;
@@ -329,6 +348,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_kurant(CrmP p) {
     double wk1 = fabs(R.plane(1, k + 1)[tid]);
     double u = R.plane(0, k)[tid];
     double uh = fabs(u);   // == sqrt(u*u) of kurant.F90:40 with v = 0
+    if (D3) { const double vv = R.plane(NF - 1, k)[tid]; uh = sqrt(u * u + 1 * (vv * vv)); }
     double adzw = sprof[0 * npf + k * CT + lane];
     cfl = dmax(cfl, uh * p.dt * sq);
     double tkh = R.plane(2, k)[tid];

@@ -1,7 +1,7 @@
 // crm_k_stats.cuh -- per-step statistics (crm_module.F90:896-1073) and the epilogue reductions / outputs
 // (crm_module.F90:1086-1594).  CF3D == 1 everywhere in the sam1mom/non-CLUBB build (vars.F90:456).
 #pragma once
-#include "crm_k_scalar.cuh"
+#include "crm_k_3d.cuh"
 
 namespace crm {
 
@@ -9,10 +9,14 @@ namespace crm {
 // the cloud-top hit at GCM level l(k), i.e. at CRM level k = nz-kk: quirk kept).
 // Descending TMA plane rings: A = qcl, qci, tabs, qpl, qpi (levels kk-1..kk+1 resident, 4 stages), B = w, qv (levels
 // kk, kk+1, 3 stages).  Radiation-group sums use warp shuffles when a group lies inside a warp.
+// 3-D tiles (NXT = CRM_G3D): w and qv are read in the own column with plain loads (no ring B), and the radiation groups are
+// (nx/nx_rad) x (ny/ny_rad) columns: x-sums by warp shuffles, y-sums through shared memory (5 * P/grpx doubles).
 #define CRM_STATS_SMEM(P, CT, nzp, need_srad) \
   (CRM_PIPE_BYTES(5, 4, P) + CRM_PIPE_BYTES(2, 3, P) + CRM_PROF_BYTES(4, nzp, CT) + (size_t)(2 * CRM_RED_DOUBLES(10, P, CT) + ((need_srad) ? 5 * (P) : 0)) * 8)
+#define CRM_STATS3_SMEM(P, CT, nzp) \
+  (CRM_PIPE_BYTES(5, 4, P) + 128 + CRM_PROF_BYTES(4, nzp, CT) + (size_t)(2 * CRM_RED_DOUBLES(10, P, CT) + 5 * (P)) * 8)
 template <int NXT>
-__global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
+__global__ void __launch_bounds__(CRM_LB(NXT)) k_stats(CrmP p) {
   CRM_TILE_SETUP_T(NXT)
   CRM_DYN_SMEM(unsigned char, smraw);
   const int nzm = p.nzm, nz = p.nz, npf = p.nzp * CT;
@@ -21,7 +25,7 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
   A.src[0] = p.qcl + fb; A.src[1] = p.qci + fb; A.src[2] = p.tabs + fb; A.src[3] = p.qpl + fb; A.src[4] = p.qpi + fb;
   B.src[0] = p.w + fb; B.src[1] = p.qv + fb;
   unsigned char *sm2 = smraw + CRM_PIPE_BYTES(5, 4, P);
-  double *sprof = (double *)(sm2 + CRM_PIPE_BYTES(2, 3, P));
+  double *sprof = (double *)(sm2 + (D3 ? 128 : CRM_PIPE_BYTES(2, 3, P)));
   double *red = sprof + 4 * npf, *srad = red + 2 * CRM_RED_DOUBLES(10, P, CT);
   const int RS = CRM_RED_DOUBLES(10, P, CT);
   {
@@ -30,18 +34,20 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
   }
 #define SPF(r, k) sprof[(r) * npf + (k) * CT + lane]
   A.init(smraw, P, tid);
-  B.init(sm2, P, tid);
+  if (!D3) B.init(sm2, P, tid);
   // top level nz of B (w(nz)) is needed by level nzm; A starts at nzm
   if (tid == 0) {
     A.issue(nzm); if (nzm >= 2) A.issue(nzm - 1);
-    B.issue(nz); B.issue(nzm);
+    if (!D3) { B.issue(nz); B.issue(nzm); }
   }
   A.wait_desc(nzm, nzm);
-  B.wait_desc(nz, nz);
+  if (!D3) B.wait_desc(nz, nz);
   const double dz = p.dz[cb];
   const double cwp_threshold = R4(0.001), wmin = R4(2.);
   const int grp = nx_ / p.nx_rad;
   const bool grp_in_warp = (grp * CT <= 32) && !(grp & (grp - 1));
+  const int jy3 = D3 ? i / nx_ : 0, ix3 = i - jy3 * nx_, grpy = D3 ? p.ny / p.ny_rad : 1;
+  double w_up = D3 ? F3(p.w, nz) : 0.;   // 3-D: w(kk+1) carried down the march
   double cwp = 0., cwph = 0., cwpm = 0., cwpl = 0., cltemp = 0., cmtemp = 0., chtemp = 0., cttemp = 0.;
   bool flag_top = true;
   // slab sum q of level lev -> its accumulator (cloud-top hits are booked at the mirrored level nz-lev)
@@ -52,10 +58,12 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
   };
   for (int kk = nzm; kk >= 1; kk--) {   // kk = nz-k of the reference's loop counter k
     __syncthreads();   // ring slots of level kk+2 are free; warp partials of level kk+1 are visible
-    if (tid == 0) { if (kk - 2 >= 1) A.issue(kk - 2); if (kk - 1 >= 1) B.issue(kk - 1); }
+    if (tid == 0) { if (kk - 2 >= 1) A.issue(kk - 2); if (!D3 && kk - 1 >= 1) B.issue(kk - 1); }
+    double w_own = 0., qv_own = 0.;
+    if (D3) { w_own = F3(p.w, kk); qv_own = F3(p.qv, kk); }
     if (kk < nzm) red_get<10>(tid, P, CT, red + ((kk + 1) & 1) * RS, [&](int q, int ln, double sum) { book(q, ln, sum, kk + 1); });
     if (kk - 1 >= 1) A.wait_desc(kk - 1, nzm);
-    B.wait_desc(kk, nz);
+    if (!D3) B.wait_desc(kk, nz);
     const double qcl = A.plane(0, kk)[tid], qci = A.plane(1, kk)[tid];
     const double rho = SPF(0, kk), adz = SPF(1, kk), pres = SPF(2, kk);
     double tmp1 = rho * adz * dz * (qcl + qci);
@@ -68,7 +76,8 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
     else { cwpm = cwpm + tmp1; cmtemp = dmax(1., cmtemp); }
     // level-local part, evaluated for level kk (sums over levels are order independent across k)
     tmp1 = rho * adz * dz;
-    const double w_k = B.plane(0, kk)[tid], w_kc = B.plane(0, kk + 1)[tid];
+    const double w_k = D3 ? w_own : B.plane(0, kk)[tid], w_kc = D3 ? w_up : B.plane(0, kk + 1)[tid];
+    w_up = w_k;
     const double wsum = w_kc + w_k;
     double cld = 0., mcup = 0., mcdn = 0., mcuup = 0., mcudn = 0.;
     if (tmp1 * (qcl + qci) > cwp_threshold) {
@@ -94,8 +103,37 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
     double v[10] = {cld, mcup, mcdn, mcuup, mcudn, qcl, qci, top_hit, mui, mdi};
     red_put<10>(v, tid, CT, red + (kk & 1) * RS);   // finished after the next barrier (deferred: one barrier per level)
     // radiation-group accumulators (crm_module.F90:979-1015): groups of nx/nx_rad adjacent columns
-    const double tabs = A.plane(2, kk)[tid], qv = B.plane(1, kk)[tid];
+    const double tabs = A.plane(2, kk)[tid], qv = D3 ? qv_own : B.plane(1, kk)[tid];
     double a[5] = {tabs, dmax(0., qv), qcl, qci, (qcl + qci > 0) ? 1. : 0.};
+    if (D3) {
+      const int nrx = p.nx_rad * CT;   // x-reduced values per row
+      if (grp_in_warp) {
+        for (int off = CT; off < grp * CT; off <<= 1) {
+#pragma unroll
+          for (int q = 0; q < 5; q++) a[q] += __shfl_xor_sync(0xffffffffu, a[q], off);
+        }
+        __syncthreads();
+        if (ix3 % grp == 0) {
+#pragma unroll
+          for (int q = 0; q < 5; q++) srad[q * (p.ny * nrx) + jy3 * nrx + (ix3 / grp) * CT + lane] = a[q];
+        }
+        __syncthreads();
+        if (ix3 % grp == 0 && jy3 % grpy == 0) {
+          const long long ro = ((long long)tile * nzm + (kk - 1)) * (p.nx_rad * p.ny_rad * CT) + ((jy3 / grpy) * p.nx_rad + ix3 / grp) * CT + lane;
+          double *dst[5] = {p.rad_t, p.rad_qv, p.rad_qc, p.rad_qi, p.rad_cld};
+#pragma unroll
+          for (int q = 0; q < 5; q++) {
+            double sacc = a[q];
+            for (int d = 1; d < grpy; d++) sacc += srad[q * (p.ny * nrx) + (jy3 + d) * nrx + (ix3 / grp) * CT + lane];
+            acc_add(dst[q] + ro, sacc);
+          }
+        }
+      } else {   // unusual group sizes: unordered atomics (sums then depend on the arrival order at the 1e-16 level)
+        const long long ro = ((long long)tile * nzm + (kk - 1)) * (p.nx_rad * p.ny_rad * CT) + ((jy3 / grpy) * p.nx_rad + ix3 / grp) * CT + lane;
+        acc_add(p.rad_t + ro, a[0]); acc_add(p.rad_qv + ro, a[1]); acc_add(p.rad_qc + ro, a[2]); acc_add(p.rad_qi + ro, a[3]); acc_add(p.rad_cld + ro, a[4]);
+      }
+      continue;
+    }
     if (grp_in_warp) {   // ascending-pair tree inside the warp
       for (int off = CT; off < grp * CT; off <<= 1) {
 #pragma unroll
@@ -133,8 +171,8 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_stats(CrmP p) {
 
 // Epilogue slab sums (crm_module.F90:1147-1183, 1314-1356, 1517-1584).  Plane kernel; results in the scratch
 // profile block esum (14 profiles).  smem: CRM_RED_DOUBLES(14,P,CT)
-#define CRM_NESUM 14
-__global__ void __launch_bounds__(CRM_MAX_P) k_epi_sums(CrmP p, double *esum) {
+#define CRM_NESUM 16
+__global__ void __launch_bounds__(CRM_MAX_P3) k_epi_sums(CrmP p, double *esum) {
   const int tid = threadIdx.x, P = p.P, CT = p.CT;
   const int tile = blockIdx.x / p.nzm, k = blockIdx.x - tile * p.nzm + 1;
   const int i = tid / CT, lane = tid - i * CT;
@@ -151,6 +189,8 @@ __global__ void __launch_bounds__(CRM_MAX_P) k_epi_sums(CrmP p, double *esum) {
   v[7] = qpl; v[8] = qpi * omg; v[9] = qpi * (1. - omg);
   v[10] = (u - u0) * (u - u0); v[11] = 0.5 * (w_kc * w_kc + w_k * w_k);
   v[12] = F3(p.tke, k); v[13] = F3(p.tk, k);
+  if (p.v) { const double vv = F3(p.v, k), v0 = PF(p.v0, k); v[14] = vv; v[15] = (vv - v0) * (vv - v0); }
+  else { v[14] = 0.; v[15] = 0.; }
   const size_t np = (size_t)p.ntiles * p.nzp * CT;
   block_sum_each<CRM_NESUM>(v, tid, P, CT, red, [&](int q, int ln, double sum) { esum[q * np + tile * p.nzp * CT + k * CT + ln] = sum; });
 }
@@ -165,7 +205,7 @@ struct ExtOut {   // device staging of the (ld,plev) / (ld) outputs; same member
 };
 
 // precsfc -> precc/precl split and prec_crm (crm_module.F90:1417-1481).  Block per tile.  smem: CRM_RED_DOUBLES(4,P,CT)
-__global__ void __launch_bounds__(CRM_MAX_P) k_epi_precip(CrmP p, ExtOut o, double dt_eff) {
+__global__ void __launch_bounds__(CRM_MAX_P3) k_epi_precip(CrmP p, ExtOut o, double dt_eff) {
   CRM_TILE_SETUP
   CRM_DYN_SMEM(double, red);
   const double dz = p.dz[cb];
@@ -228,8 +268,10 @@ __global__ void k_epi_profiles(CrmP p, ExtIn in, ExtOut o, const double *esum, d
     O(o.qltend, l) = (qln - IN(in.ql, l)) * icrm_run_time;
     O(o.qcltend, l) = (qccln - IN(in.qccl, l)) * icrm_run_time;
     O(o.qiltend, l) = (qiiln - IN(in.qiil, l)) * icrm_run_time;
-    O(o.ultend, l) = (ES(4, k) * factor_xy - IN(in.ul, l)) * icrm_run_time;
-    O(o.vltend, l) = (0. * factor_xy - IN(in.vl, l)) * icrm_run_time;   // 2-D: v == 0 in the CRM (YES3D = 0)
+    // SPMOMTRANS (crm_module.F90:1200-1211): the reference forms these tendencies BEFORE uln, vln are scaled by factor_xy
+    // (:1214-1224), i.e. from the raw slab sums; reproduced as is (reference quirks)
+    O(o.ultend, l) = (ES(4, k) - IN(in.ul, l)) * icrm_run_time;
+    O(o.vltend, l) = (ES(14, k) - IN(in.vl, l)) * icrm_run_time;
     const double pdel = IN(in.pdel, l);
     O(o.cld, l) = dmin(1., PF(p.s_cld, k) * factor_xyt);
     O(o.cldtop, l) = dmin(1., PF(p.s_cldtop, k) * factor_xyt);
@@ -250,7 +292,7 @@ __global__ void k_epi_profiles(CrmP p, ExtIn in, ExtOut o, const double *esum, d
     const double mkadv1 = PF(p.mkadv1, k) * factor_xy * icrm_run_time, mkadv2 = PF(p.mkadv2, k) * factor_xy * icrm_run_time;
     const double mkdiff1 = PF(p.mkdiff1, k) * factor_xy * icrm_run_time, mkdiff2 = PF(p.mkdiff2, k) * factor_xy * icrm_run_time;
     O(o.flux_u, l) = (PF(p.uwle, k) + PF(p.uwsb, k)) * tmp1 * factor_xy / nst;
-    O(o.flux_v, l) = (0. + 0.) * tmp1 * factor_xy / nst;
+    O(o.flux_v, l) = p.v ? (PF(p.vwle, k) + PF(p.vwsb, k)) * tmp1 * factor_xy / nst : (0. + 0.) * tmp1 * factor_xy / nst;
     O(o.flux_qt, l) = mkwle1 + mkwsb1;
     O(o.fluxsgs_qt, l) = mkwsb1;
     O(o.flux_qp, l) = mkwle2 + mkwsb2;
@@ -258,7 +300,7 @@ __global__ void k_epi_profiles(CrmP p, ExtIn in, ExtOut o, const double *esum, d
     O(o.qp_trans, l) = mkadv2 + mkdiff2;
     const double tkesgsz = rho * ES(12, k) * factor_xy;
     O(o.tkesgsz, l) = tkesgsz;
-    O(o.tkez, l) = rho * 0.5 * (ES(10, k) + 0. * 0 + ES(11, k)) * factor_xy + tkesgsz;
+    O(o.tkez, l) = rho * 0.5 * (ES(10, k) + ES(15, k) * (p.v ? 1 : 0) + ES(11, k)) * factor_xy + tkesgsz;
     O(o.tkz, l) = ES(13, k) * factor_xy;
     O(o.precflux, l) = (PF(p.precflux, k) * factor_xy * dz / dt_eff / nst) / R4(1000.);
     O(o.qp_fall, l) = PF(p.qpfall, k) * factor_xy * icrm_run_time;
@@ -298,13 +340,13 @@ __global__ void k_epi_profiles(CrmP p, ExtIn in, ExtOut o, const double *esum, d
 
 // crm_rad outputs scaled by nx_rad_fac*ny_rad_fac/nstop, written straight to the boundary layout (crm_module.F90:1086-1107).
 __global__ void k_epi_rad(CrmP p, const double *acc, double *ext, int ld, double scale) {
-  const int tid = threadIdx.x, CT = p.CT, Pd = p.nx_rad * CT;
+  const int tid = threadIdx.x, CT = p.CT, nr = p.nx_rad * p.ny_rad, Pd = nr * CT;
   const int tile = blockIdx.x / p.nzm, k = blockIdx.x - tile * p.nzm;
   if (tid >= Pd) return;
   const int ir = tid / CT, lane = tid - ir * CT;
   const int icrm = tile * CT + lane;
   if (icrm >= p.ncrms) return;
-  ext[(size_t)icrm + (size_t)ld * ((size_t)ir + (size_t)p.nx_rad * (size_t)k)] = acc[((long long)tile * p.nzm + k) * Pd + tid] * scale;
+  ext[(size_t)icrm + (size_t)ld * ((size_t)ir + (size_t)nr * (size_t)k)] = acc[((long long)tile * p.nzm + k) * Pd + tid] * scale;
 }
 
 // ---- crm_physics_tend glue (crm_physics.F90:1006-1011, 1160-1209): boundary layout (ld leading), one thread per element ----

@@ -434,6 +434,12 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
           c.uln(l) += c.u(i, j, k);
           c.vln(l) += c.v(i, j, k);
         }
+    // SPMOMTRANS (crm_module.F90:1200-1211): computed BEFORE the factor_xy scaling of uln, vln at :1214-1224, i.e. from the
+    // raw slab sums over nx*ny cells (a quirk of the reference, kept)
+    for (int k = 1; k <= plev; k++) {
+      if (out->ultend) OUT2(out->ultend, ic, k) = (c.uln(k) - P2(in->ul, ic, k)) * icrm_run_time;
+      if (out->vltend) OUT2(out->vltend, ic, k) = (c.vln(k) - P2(in->vl, ic, k)) * icrm_run_time;
+    }
     for (int k = ptop; k <= plev; k++) {
       c.tln(k) *= factor_xy; c.qln(k) *= factor_xy; c.qccln(k) *= factor_xy; c.qiiln(k) *= factor_xy;
       c.uln(k) *= factor_xy; c.vln(k) *= factor_xy;
@@ -443,9 +449,6 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
       if (out->qltend) OUT2(out->qltend, ic, k) = (c.qln(k) - P2(in->ql, ic, k)) * icrm_run_time;
       if (out->qcltend) OUT2(out->qcltend, ic, k) = (c.qccln(k) - P2(in->qccl, ic, k)) * icrm_run_time;
       if (out->qiltend) OUT2(out->qiltend, ic, k) = (c.qiiln(k) - P2(in->qiil, ic, k)) * icrm_run_time;
-      // SPMOMTRANS (crm_module.F90:1200-1211)
-      if (out->ultend) OUT2(out->ultend, ic, k) = (c.uln(k) - P2(in->ul, ic, k)) * icrm_run_time;
-      if (out->vltend) OUT2(out->vltend, ic, k) = (c.vln(k) - P2(in->vl, ic, k)) * icrm_run_time;
     }
     if (out->prectend) out->prectend[ic] = (c.colprec - c.prectend0) / ggr * factor_xy * icrm_run_time;
     if (out->precstend) out->precstend[ic] = (c.colprecs - c.precstend0) / ggr * factor_xy * icrm_run_time;

@@ -65,3 +65,20 @@ def test_emu_sedimentation_fallback_in_kernel(emu, monkeypatch):
 def test_emu_multi_warp_tiles_and_odd_levels(emu):
     # nx = 32 with a 4-column CRM tile: four warps per block (warp votes, compaction queue, transposed sums); odd crm_nz
     _check(emu, cm.small_dims(ncrms=5, nx=32, nzm=27, plev=30, nsteps=2), 30, 1e-11)
+
+
+def _dims3d(ncrms, nx, ny, nsteps, **kw):
+    return cm.pkg.CrmDims(ncrms=ncrms, nx=nx, ny=ny, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=20.0 * nsteps, igstep=kw.pop("igstep", 3),
+                          nx_rad=max(1, nx // 4), ny_rad=max(1, ny // 4), **kw)
+
+
+def test_emu_3d_ab3_and_padding(emu):
+    # 3-D CRM 8x8x28 (tile of 4 CRMs, 256 emulated threads), four steps (AB1..AB3), 5 CRMs -> padded second tile
+    ro, rg = _check(emu, _dims3d(5, 8, 8, 4), 40, 1e-11)
+    assert np.abs(rg[0].v_wind).max() > 0
+
+
+def test_emu_3d_rectangular_setperturb(emu, monkeypatch):
+    # 16x8 columns (different transform lengths in x and y), first call of a run (setperturb)
+    monkeypatch.setenv("CRM_B200_CT", "2")
+    _check(emu, _dims3d(3, 16, 8, 2, igstep=1), 0, 1e-11)

@@ -163,8 +163,8 @@ def test_sedimentation_fallback_single_launch(monkeypatch):
 def test_error_behaviour_matches_reference_aborts():
     """Unsupported builds are refused loudly at init (no CPU fallback); a bad crm_accel_factor/nstop pair returns the
     reference's abort message (accelerate_crm.F90:96-101) instead of calling endrun."""
-    d3 = cm.pkg.CrmDims(ncrms=4, nx=8, ny=8, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=40.0, igstep=3)
-    with pytest.raises(RuntimeError, match="3-D"):
+    d3 = cm.pkg.CrmDims(ncrms=4, nx=64, ny=64, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=40.0, igstep=3)
+    with pytest.raises(RuntimeError, match="3-D CRM geometries"):
         cm.libmod.CrmHandle(d3)
     dm = cm.small_dims(ncrms=4, nx=8, nsteps=2).copy(micro=1)
     with pytest.raises(RuntimeError, match="sam1mom"):
@@ -266,3 +266,85 @@ def test_odd_level_counts(nx, ncrms, nzm, plev, nsteps, spin):
     # crm_nz need not be even: k_p8_micro processes level pairs, the rings prefetch by fixed distances
     dims = cm.small_dims(ncrms=ncrms, nx=nx, nzm=nzm, plev=plev, nsteps=nsteps, igstep=1 if spin == 0 else 3)
     _check(dims, spin, 1e-9)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 3-D CRMs (ny > 1): shear_prod3D, diffuse_mom3D, advect_scalar3D, diffuse_scalar3D, the y-terms of advect2_mom_xy/z, the
+# 2-D spectral pressure solve, v_wind in and out.
+# ---------------------------------------------------------------------------------------------------------------------
+def dims3d(ncrms, nx, ny, nzm=28, plev=30, nsteps=3, igstep=3, **kw):
+    dx, dt = (4000.0, 20.0) if plev == 30 else (1000.0, 10.0)
+    return cm.pkg.CrmDims(ncrms=ncrms, nx=nx, ny=ny, nzm=nzm, plev=plev, dx=dx, dt=dt, dt_gl=dt * nsteps, igstep=igstep,
+                          nx_rad=max(1, nx // 4), ny_rad=max(1, ny // 4), **kw)
+
+
+def test_3d_small_three_steps():
+    # 8x8x28, CRM tile of 4 columns (256 threads per block); AB1..AB3; ncrms not a multiple of the tile
+    ro, rg = _check(dims3d(7, 8, 8, nsteps=3), 60, 1e-10)
+    assert np.abs(rg[0].v_wind).max() > 0
+
+
+def test_3d_cfg4_geometry_steps():
+    # BASELINE config 4 geometry: 32x32x58 (L72, dx 1 km, dt 10 s): one CRM per 1024-thread block, 20 steps after a spin-up
+    _check(dims3d(3, 32, 32, nzm=58, plev=72, nsteps=20), 40, 1e-7)
+
+
+@pytest.mark.parametrize("nx,ny,ncrms", [(16, 16, 3), (16, 8, 5)])
+def test_3d_other_geometries_setperturb(nx, ny, ncrms):
+    # first call of a run: setperturb noise on a cold state (igstep = 1); 16x16 = one CRM per 256-thread block, 16x8 rectangular
+    _check(dims3d(ncrms, nx, ny, nsteps=4, igstep=1), 0, 1e-10)
+
+
+def test_3d_mean_state_acceleration():
+    _check(dims3d(6, 8, 8, nsteps=8, use_crm_accel=True, crm_accel_factor=1.0, crm_accel_uv=True), 60, 1e-9)
+
+
+def test_golden_fixture_3d_on_device():
+    """tests/golden/sam1mom_3d_8x8x28.npz (oracle outputs) replayed through the C ABI."""
+    import os
+    import sys
+    gold = os.path.join(cm.ROOT, "tests", "golden")
+    if gold not in sys.path:
+        sys.path.insert(0, gold)
+    import make_golden as mg
+    z = np.load(os.path.join(gold, "sam1mom_3d_8x8x28.npz"))
+    dims, inp, st, rad = mg.build_case("sam1mom_3d_8x8x28")
+    h = cm.libmod.CrmHandle(dims)
+    out = h.run(dims, inp, st, rad)
+    assert h.stats()["ncycle_sum"] == int(z["ncycle_sum"])
+    h.close()
+    for n in cm.STATE:
+        ref = z["state_" + n]
+        assert np.abs(getattr(st, n) - ref).max() <= 1e-9 * max(1e-30, np.abs(ref).max()), n
+    for n in ("sltend", "qltend", "qcltend", "qiltend", "precc", "precl", "cld", "mcup", "flux_qt", "flux_u"):
+        ref = z["out_" + n]
+        assert np.abs(getattr(out, n) - ref).max() <= 1e-8 * max(1e-30, np.abs(ref).max()), n
+
+
+def test_3d_continuity_and_positivity_property_wide_batch():
+    """Size-independent properties on a batch that fills the GPU (no oracle): 300 CRMs of 32x32x58, 4 steps from a cold,
+    perturbed state: finite state, non-negative water, 3-D anelastic continuity to round-off."""
+    dims = dims3d(300, 32, 32, nzm=58, plev=72, nsteps=4, igstep=1)
+    dims, inp, st, rad = cm.pkg.synthetic.make_case(dims)
+    h = cm.libmod.CrmHandle(dims)
+    h.run(dims, inp, st, rad)
+    for n in cm.STATE:
+        assert np.isfinite(getattr(st, n)).all(), n
+    assert st.qt.min() >= 0 and st.qp.min() >= 0 and st.qn.min() >= 0
+    u, v, w = st.u_wind, st.v_wind, h.debug_fetch("w")
+    h.close()
+    nzm = dims.nzm
+    z = inp.zmid[:, ::-1][:, :nzm] - inp.zint[:, -1:]
+    zi = inp.zint[:, ::-1][:, :nzm + 1] - inp.zint[:, -1:]
+    dz = 0.5 * (z[:, 0] + z[:, 1])
+    adz = (zi[:, 1:] - zi[:, :-1]) / dz[:, None]
+    adzw = np.ones((dims.ld, nzm + 1)); adzw[:, 1:nzm] = (z[:, 1:] - z[:, :-1]) / dz[:, None]; adzw[:, nzm] = adzw[:, nzm - 1]
+    rho = inp.pdel[:, ::-1][:, :nzm] / 9.80616 / (adz * dz[:, None])
+    pm = inp.pmid[:, ::-1]
+    rhow = np.zeros((dims.ld, nzm + 1))
+    rhow[:, 1:nzm] = (pm[:, :nzm - 1] - pm[:, 1:nzm]) / 9.80616 / (adzw[:, 1:nzm] * dz[:, None])
+    rhow[:, 0] = 2 * rhow[:, 1] - rhow[:, 2]; rhow[:, nzm] = 2 * rhow[:, nzm - 1] - rhow[:, nzm - 2]
+    div = ((np.roll(u, -1, axis=1) - u) / dims.dx + (np.roll(v, -1, axis=2) - v) / dims.dx) * rho[:, None, None, :] + \
+        (w[..., 1:] * rhow[:, None, None, 1:] - w[..., :-1] * rhow[:, None, None, :-1]) / (adz[:, None, None, :] * dz[:, None, None, None])
+    scale = max(np.abs(u).max(), np.abs(v).max()) / dims.dx * rho.max()
+    assert np.abs(div).max() / scale < 1e-11
