@@ -30,18 +30,26 @@ static int dev_copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, 
   return 0;
 }
 static int dev_sync() { return 0; }
+static int t_launch = 0;
 static bool is_dev_ptr(const void *) { return false; }
 static const char *dev_errstr() { return "emu"; }
 struct DevTimer { void start() {} double stop() { return 0.; } };
 #else
+// Every handle owns a non-blocking stream: all of its copies, memsets and kernels are issued there and only that stream is
+// synchronised, so handles on different host threads (or GPUs) do not serialise each other ("different handles
+// are independent").  The API entry points select the calling handle's stream into these thread-local variables.
+static thread_local cudaStream_t t_stream = nullptr;   // the calling handle's main stream (copies, memsets, synchronisation)
+static thread_local cudaStream_t t_launch = nullptr;   // stream of the next kernel launches (main stream or one of its side streams)
 static int dev_init(int device) { return cudaSetDevice(device) == cudaSuccess ? 0 : 1; }
 static void *dev_alloc(size_t n) { void *p = nullptr; if (cudaMalloc(&p, n ? n : 1) != cudaSuccess) return nullptr; return p; }
 static void dev_free(void *p) { cudaFree(p); }
-static int dev_zero(void *p, size_t n) { return cudaMemsetAsync(p, 0, n, 0) == cudaSuccess ? 0 : 1; }
-static int dev_copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, int /*kind*/) {
-  return cudaMemcpy2D(dst, dpitch, src, spitch, width, height, cudaMemcpyDefault) == cudaSuccess ? 0 : 1;
+static int dev_zero(void *p, size_t n) { return cudaMemsetAsync(p, 0, n, t_stream) == cudaSuccess ? 0 : 1; }
+static int dev_sync() { return cudaStreamSynchronize(t_stream) == cudaSuccess ? 0 : 1; }
+// wait != 0: the host needs the destination (or drops the source) right after the call
+static int dev_copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, int wait) {
+  if (cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDefault, t_stream) != cudaSuccess) return 1;
+  return wait ? dev_sync() : 0;
 }
-static int dev_sync() { return cudaDeviceSynchronize() == cudaSuccess ? 0 : 1; }
 static bool is_dev_ptr(const void *p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -52,8 +60,8 @@ struct DevTimer {
   cudaEvent_t a, b;
   DevTimer() { cudaEventCreate(&a); cudaEventCreate(&b); }
   ~DevTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
-  void start() { cudaEventRecord(a, 0); }
-  double stop() { cudaEventRecord(b, 0); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+  void start() { cudaEventRecord(a, t_stream); }
+  double stop() { cudaEventRecord(b, t_stream); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 };
 #endif
 
@@ -84,6 +92,12 @@ struct Handle {
   int *gcol_dev = nullptr;
   int ld_max = 0;
   std::string err, launch_err;
+#ifndef CRM_EMU
+  cudaStream_t stream = nullptr, side[2] = {nullptr, nullptr};   // main stream; side streams for independent kernels of a sub-step
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  unsigned long long *pin = nullptr;                             // pinned host words for the per-step read-backs (cfl, flags)
+  int nsm = 148;
+#endif
   crm_run_stats_t stats;
   long long launches = 0;
   int precip_launches = 4;            // k_precip_b launches per sub-step (the last one runs any remaining sub-iterations)
@@ -110,7 +124,7 @@ static std::string kname(const char *s) { std::string n(s); while (!n.empty() &&
 #define LAUNCH(h, kern, grid, block, smem, ...)                 \
   do {                                                          \
     if ((h)->ktiming) (h)->ktimer.start();                      \
-    CRM_LAUNCH(kern, grid, block, smem, 0, __VA_ARGS__);        \
+    CRM_LAUNCH(kern, grid, block, smem, t_launch, __VA_ARGS__); \
     if ((h)->ktiming) ktime_add((h)->ktimes, #kern, (h)->ktimer.stop()); \
     (h)->launches++;                                            \
     launch_check(h, #kern);                                     \
@@ -137,6 +151,14 @@ inline void launch_check(void *, const char *) {}
     if (e_ != cudaSuccess && (h)->launch_err.empty()) (h)->launch_err = std::string(name) + ": " + cudaGetErrorString(e_); \
   } while (0)
 #endif
+// make `h` the calling thread's current handle: its device and its streams
+int select_handle(Handle *h) {
+  if (dev_init(h->device)) return 1;
+#ifndef CRM_EMU
+  t_stream = h->stream; t_launch = h->stream;
+#endif
+  return 0;
+}
 int fail(Handle *h, int code, const std::string &msg) {
   h->err = msg;
   if (!h->launch_err.empty()) { h->err += " [first failed launch: " + h->launch_err + "]"; h->launch_err.clear(); }
@@ -172,7 +194,18 @@ extern "C" const char *crm_b200_last_error(void *handle) {
 extern "C" int crm_b200_free(void *handle) {
   if (!handle) return 0;
   Handle *h = (Handle *)handle;
+  dev_init(h->device);
+#ifndef CRM_EMU
+  if (h->stream) { cudaStreamSynchronize(h->stream); }
+  for (int q = 0; q < 2; q++) { if (h->side[q]) cudaStreamDestroy(h->side[q]); if (h->ev_join[q]) cudaEventDestroy(h->ev_join[q]); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->pin) cudaFreeHost(h->pin);
+#endif
   for (void *q : h->allocs) dev_free(q);
+#ifndef CRM_EMU
+  if (h->stream) cudaStreamDestroy(h->stream);
+  t_stream = nullptr; t_launch = nullptr;
+#endif
   delete h;
   return 0;
 }
@@ -194,6 +227,19 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   if (dev_init(device)) { g_init_err = std::string("crm_b200_init: cannot select CUDA device: ") + dev_errstr(); return 8; }
   Handle *h = new Handle();
   h->d0 = *d; h->device = device; h->d3 = d3;
+#ifndef CRM_EMU
+  {
+    bool sok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int q = 0; q < 2; q++)
+      sok = sok && cudaStreamCreateWithFlags(&h->side[q], cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->ev_join[q], cudaEventDisableTiming) == cudaSuccess;
+    sok = sok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    sok = sok && cudaMallocHost((void **)&h->pin, 64) == cudaSuccess;
+    if (!sok) { g_init_err = std::string("crm_b200_init: cannot create the handle's streams / pinned words: ") + dev_errstr(); crm_b200_free(h); return 8; }
+    t_stream = h->stream; t_launch = h->stream;
+    cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, device);
+  }
+#endif
   // CRM tile: P = nx*ny*CT threads per block, at most CRM_MAX_P (2-D) / CRM_MAX_P3 (3-D): the kernels are compiled with
   // __launch_bounds__ of that size
   const int nxy = d->nx * d->ny, maxp = d3 ? CRM_MAX_P3 : CRM_MAX_P;
@@ -276,7 +322,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
     BIG_G(k_stats); BIG_G(k_p8_micro); BIG_G(k_mpdata); BIG_G(k_p7_diffuse); BIG_G(k_p3_mom); BIG_G(k_p1_forcing); BIG_G(k_p2_sgs);
     BIG_G(k_kurant); BIG_G(k_precip_a); BIG_G(k_precip_b);
     BIG(k_stats<CRM_G3D>); BIG(k_p8_micro<CRM_G3D>); BIG(k_p7_diffuse<CRM_G3D>); BIG(k_p1_forcing<CRM_G3D>); BIG(k_kurant<CRM_G3D>);
-    BIG(k_precip_a<CRM_G3D>); BIG(k_precip_b<CRM_G3D>); BIG(k3_p2_sgs); BIG(k3_p3_mom); BIG(k3_mpdata); BIG(k_msa_a); BIG(k_msa_b); BIG(k_epi_precip);
+    BIG(k_precip_a<CRM_G3D>); BIG(k_precip_b<CRM_G3D>); BIG(k3_p2_sgs); BIG(k3_p3_adv); BIG(k3_p3_dif); BIG(k3_mpdata); BIG(k_msa_a); BIG(k_msa_b); BIG(k_epi_precip);
 #define PRESS3_ATTR(NXV, NYV) BIG((k3_p4_press_fwd<NXV, NYV>)); BIG((k3_p5_press_bwd<NXV, NYV>));
     PRESS3_ATTR(8, 8) PRESS3_ATTR(16, 16) PRESS3_ATTR(32, 32) PRESS3_ATTR(16, 8)
 #undef PRESS3_ATTR
@@ -327,7 +373,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
       d->dx != d0.dx || d->dt != d0.dt || d->micro != d0.micro)
     return fail(h, 20, "crm_b200_run: geometry differs from crm_b200_init");
   if (d->ncrms < 1 || d->ncrms > d0.ncrms || d->ld < d->ncrms || d->ld > h->ld_max) return fail(h, 21, "crm_b200_run: need ncrms <= init ncrms and ncrms <= ld <= init ld");
-  if (dev_init(h->device)) return fail(h, 22, std::string("crm_b200_run: cannot select device: ") + dev_errstr());
+  if (select_handle(h)) return fail(h, 22, std::string("crm_b200_run: cannot select device: ") + dev_errstr());
   auto wall0 = std::chrono::steady_clock::now();
   memset(&h->stats, 0, sizeof(h->stats));
   h->launches = 0;
@@ -380,13 +426,13 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   {
     std::vector<double> c, s;
     twiddles(nx, d->twiddle_f32 != 0, c, s);
-    zrc |= dev_copy2d(p.twc, nx * 8, c.data(), nx * 8, nx * 8, 1, 0);
-    zrc |= dev_copy2d(p.tws, nx * 8, s.data(), nx * 8, nx * 8, 1, 0);
+    zrc |= dev_copy2d(p.twc, nx * 8, c.data(), nx * 8, nx * 8, 1, 1);
+    zrc |= dev_copy2d(p.tws, nx * 8, s.data(), nx * 8, nx * 8, 1, 1);
     if (d3) {
       const int ny = d->ny;
       twiddles(ny, d->twiddle_f32 != 0, c, s);
-      zrc |= dev_copy2d(p.twc + nx, ny * 8, c.data(), ny * 8, ny * 8, 1, 0);
-      zrc |= dev_copy2d(p.tws + nx, ny * 8, s.data(), ny * 8, ny * 8, 1, 0);
+      zrc |= dev_copy2d(p.twc + nx, ny * 8, c.data(), ny * 8, ny * 8, 1, 1);
+      zrc |= dev_copy2d(p.tws + nx, ny * 8, s.data(), ny * 8, ny * 8, 1, 1);
     }
   }
   // role assignment of the velocity buffers
@@ -435,13 +481,13 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   if (d->igstep <= 1) {   // setperturb (crm_module.F90:677-681): RNG draws on the host like the reference
     std::vector<double> rnd((size_t)ncrms * 5 * nxy);
     std::vector<int> gcol(ld);
-    if (is_dev_ptr(in->gcol)) dev_copy2d(gcol.data(), ld * 4, in->gcol, ld * 4, (size_t)ncrms * 4, 1, 0);
+    if (is_dev_ptr(in->gcol)) dev_copy2d(gcol.data(), ld * 4, in->gcol, ld * 4, (size_t)ncrms * 4, 1, 1);
     else memcpy(gcol.data(), in->gcol, (size_t)ncrms * 4);
     for (int ic = 0; ic < ncrms; ic++) {
       RngMT r; r.set_seed((int)((unsigned)gcol[ic] * 1000u));
       for (int q = 0; q < 5 * nxy; q++) rnd[(size_t)ic * 5 * nxy + q] = r.gen_rand();
     }
-    dev_copy2d(h->rnd_dev, rnd.size() * 8, rnd.data(), rnd.size() * 8, rnd.size() * 8, 1, 0);
+    dev_copy2d(h->rnd_dev, rnd.size() * 8, rnd.data(), rnd.size() * 8, rnd.size() * 8, 1, 1);
     LAUNCH(h, k_setperturb, slot_blocks, 128, 0, p, h->rnd_dev);
   }
   if (d3) LAUNCH(h, k3_press_alfa, ntiles, P, 0, p);
@@ -472,7 +518,14 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
     dev_zero(p.cfl_bits, 8);
     LAUNCH_G(h, k_kurant, ntiles, P, CRM_KURANT_SMEM(P, CT, h->nzp, d3), p);
     unsigned long long bits = 0;
-    if (dev_copy2d(&bits, 8, p.cfl_bits, 8, 8, 1, 0)) return fail(h, 27, std::string("crm_b200_run: kurant readback failed: ") + dev_errstr());
+#ifndef CRM_EMU
+    // 8-byte read-back into a pinned host word on the handle's stream (the only host<->device round trip of a CRM step)
+    if (cudaMemcpyAsync(h->pin, p.cfl_bits, 8, cudaMemcpyDeviceToHost, t_stream) != cudaSuccess || dev_sync())
+      return fail(h, 27, std::string("crm_b200_run: kurant readback failed: ") + dev_errstr());
+    bits = h->pin[0];
+#else
+    if (dev_copy2d(&bits, 8, p.cfl_bits, 8, 8, 1, 1)) return fail(h, 27, std::string("crm_b200_run: kurant readback failed: ") + dev_errstr());
+#endif
     if (!h->launch_err.empty()) return fail(h, 34, "crm_b200_run: a kernel launch failed");
     double cfl; memcpy(&cfl, &bits, 8);
     if (!(cfl == cfl) || cfl > 1e30) return fail(h, 28, "kurant(): non-finite CFL (model state blew up)");
@@ -499,7 +552,10 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
       if (d3) LAUNCH(h, k3_p2_sgs, ntiles, P, CRM3_P2_SMEM(P, CT, h->nzp), p);
       else LAUNCH_G(h, k_p2_sgs, ntiles, P, CRM_P2_SMEM(P, CT, h->nzp), p);
       if (dbg_stop == 2) { dbg_break = true; break; }
-      if (d3) LAUNCH(h, k3_p3_mom, ntiles, P, CRM3_P3_SMEM(P, CT, h->nzp), p);
+      if (d3) {
+        LAUNCH(h, k3_p3_adv, ntiles, P, CRM3_P3A_SMEM(P, CT, h->nzp), p);
+        LAUNCH(h, k3_p3_dif, ntiles, P, CRM3_P3B_SMEM(P, CT, h->nzp), p);
+      }
       else LAUNCH_G(h, k_p3_mom, ntiles, P, CRM_P3_SMEM(P, CT, h->nzp), p);
       if (dbg_stop == 3) { dbg_break = true; break; }
 #define PRESS3_CASE(NXV, NYV)                                                                          \
@@ -525,16 +581,37 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
 #undef PRESS_CASE
       if (dbg_stop == 4) { dbg_break = true; break; }
       // advect_all_scalars.F90:32-64
+      // the three advections are independent: on a batch that does not fill the GPU they run concurrently on the handle's side
+      // streams (fork / join by events; no effect on results)
+#ifndef CRM_EMU
+      const bool fork = !h->ktiming && ntiles < 4 * h->nsm;
+      if (fork) { cudaEventRecord(h->ev_fork, h->stream); for (int q = 0; q < 2; q++) cudaStreamWaitEvent(h->side[q], h->ev_fork, 0); }
+#define ON_SIDE(q) if (fork) t_launch = h->side[q]
+#define ON_MAIN() t_launch = h->stream
+#else
+#define ON_SIDE(q)
+#define ON_MAIN()
+#endif
       if (d3) {
         const size_t smem_mp3 = CRM3_MP_SMEM(P, CT, h->nzp);
         LAUNCH(h, k3_mpdata, ntiles, P, smem_mp3, p, p.t, (double *)nullptr, (double *)nullptr, 0, (const int *)nullptr);
+        ON_SIDE(0);
         LAUNCH(h, k3_mpdata, ntiles, P, smem_mp3, p, p.qt, p.mkadv1, p.mkwle1, 1, (const int *)nullptr);
+        ON_SIDE(1);
         LAUNCH(h, k3_mpdata, ntiles, P, smem_mp3, p, p.qp, p.mkadv2, p.mkwle2, 1, (const int *)p.kqp);
       } else {
         LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, p.t, (double *)nullptr, (double *)nullptr, 0, (const int *)nullptr);
+        ON_SIDE(0);
         LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, p.qt, p.mkadv1, p.mkwle1, 1, (const int *)nullptr);
+        ON_SIDE(1);
         LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, p.qp, p.mkadv2, p.mkwle2, 1, (const int *)p.kqp);
       }
+      ON_MAIN();
+#undef ON_SIDE
+#undef ON_MAIN
+#ifndef CRM_EMU
+      if (fork) for (int q = 0; q < 2; q++) { cudaEventRecord(h->ev_join[q], h->side[q]); cudaStreamWaitEvent(h->stream, h->ev_join[q], 0); }
+#endif
       if (dbg_stop == 5) { dbg_break = true; break; }
       dev_zero(p.prec_cfl_bits, 8);
       LAUNCH_G(h, k_precip_a, ntiles, P, CRM_PRECIPA_SMEM(P, CT, h->nzp), p);
@@ -554,7 +631,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
         LAUNCH_G(h, k_p8_micro, ntiles * ((nzm + CRM_P8_NL - 1) / CRM_P8_NL), P, smem_p8, p, 1, 0);
         LAUNCH(h, k_msa_a, ntiles * nzm, P, red_bytes(4), p);
         int flags[4];
-        if (dev_copy2d(flags, 16, p.flags, 16, 16, 1, 0)) return fail(h, 30, "crm_b200_run: MSA flag readback failed");
+        if (dev_copy2d(flags, 16, p.flags, 16, 16, 1, 1)) return fail(h, 30, "crm_b200_run: MSA flag readback failed");
         if (flags[1]) {
           ceaseflag = true;
           nstop = (int)(nstop + (nstop - nstep + 1) * d->crm_accel_factor);   // accelerate_crm.F90:243
@@ -573,7 +650,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
     LAUNCH_G(h, k_stats, ntiles, P, d3 ? CRM_STATS3_SMEM(P, CT, h->nzp) : CRM_STATS_SMEM(P, CT, h->nzp, !(((nx / d->nx_rad) * CT <= 32) && !((nx / d->nx_rad) & ((nx / d->nx_rad) - 1)))), p);
     // nprec statistic (device value of the last sub-step)
     if ((nstep & 15) == 0 || nstep == nstop) {
-      unsigned long long pb2 = 0; dev_copy2d(&pb2, 8, p.prec_cfl_bits, 8, 8, 1, 0);
+      unsigned long long pb2 = 0; dev_copy2d(&pb2, 8, p.prec_cfl_bits, 8, 8, 1, 1);
       double pc; memcpy(&pc, &pb2, 8);
       long long np_ = pc > R4(0.9) ? (long long)std::ceil(pc / R4(0.9)) : 1;
       nprec_max = std::max(nprec_max, np_);
@@ -696,7 +773,7 @@ int glue_check(Handle *h, const crm_dims_t *d) {
   const crm_dims_t &d0 = h->d0;
   if (d->plev != d0.plev || d->nzm != d0.nzm || d->nx_rad != d0.nx_rad || d->ny_rad != d0.ny_rad) return fail(h, 40, "crm_b200_physics_*: geometry differs from crm_b200_init");
   if (d->ncrms < 1 || d->ncrms > d0.ncrms || d->ld < d->ncrms || d->ld > h->ld_max) return fail(h, 41, "crm_b200_physics_*: need ncrms <= init ncrms and ncrms <= ld <= init ld");
-  if (dev_init(h->device)) return fail(h, 42, std::string("crm_b200_physics_*: cannot select device: ") + dev_errstr());
+  if (select_handle(h)) return fail(h, 42, std::string("crm_b200_physics_*: cannot select device: ") + dev_errstr());
   return 0;
 }
 int glue_qrad(Handle *h, const crm_dims_t *d, const double *pdel, double *qrad, int invert) {
@@ -710,6 +787,7 @@ int glue_qrad(Handle *h, const crm_dims_t *d, const double *pdel, double *qrad, 
   LAUNCH(h, k_glue_qrad, blocks, 256, 0, q.dev, pd.dev, d->ncrms, d->ld, ncr, d->nzm, d->plev, invert);
   if (dev_sync()) return fail(h, 44, std::string("crm_b200_physics_*: kernel failure: ") + dev_errstr());
   stage_out(q, d->ld, d->ncrms);
+  if (dev_sync()) return fail(h, 44, std::string("crm_b200_physics_*: copy failure: ") + dev_errstr());
   return 0;
 }
 }  // namespace
@@ -755,6 +833,7 @@ extern "C" int crm_b200_physics_post(void *handle, const crm_dims_t *d, const do
 extern "C" long long crm_b200_debug_fetch(void *handle, const char *name, double *host_buf, size_t n) {
   if (!handle) return -1;
   Handle *h = (Handle *)handle;
+  if (select_handle(h)) return -5;
   CrmP &p = h->p;
   std::string nm(name);
   const double *src = nullptr;
@@ -773,7 +852,7 @@ extern "C" long long crm_b200_debug_fetch(void *handle, const char *name, double
   if (n < need) return -2;
   if (nk > p.nzm) {   // staging buffer holds nzm levels only: fetch level by level through a small temporary
     std::vector<double> tmp((size_t)h->field_elems);
-    dev_copy2d(tmp.data(), tmp.size() * 8, src, tmp.size() * 8, (size_t)p.ntiles * h->tstride * 8, 1, 0);
+    dev_copy2d(tmp.data(), tmp.size() * 8, src, tmp.size() * 8, (size_t)p.ntiles * h->tstride * 8, 1, 1);
     for (int k = 0; k < nk; k++)
       for (int i = 0; i < p.nx * p.ny; i++)
         for (int ic = 0; ic < p.ncrms; ic++) {
@@ -784,7 +863,7 @@ extern "C" long long crm_b200_debug_fetch(void *handle, const char *name, double
   }
   LAUNCH(h, k_int_to_ext, p.ntiles * nk, p.P, 0, p, src, h->tstride, p.P, p.nx * p.ny, nk, h->stage, p.ncrms, 1.0);
   if (dev_sync()) return -4;
-  dev_copy2d(host_buf, need * 8, h->stage, need * 8, need * 8, 1, 0);
+  dev_copy2d(host_buf, need * 8, h->stage, need * 8, need * 8, 1, 1);
   return (long long)need;
 }
 

@@ -177,99 +177,85 @@ __global__ void __launch_bounds__(CRM_MAX_P3) k3_p2_sgs(CrmP p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// advect2_mom_xy.F90:25-62 (RUN3D), advect2_mom_z.F90:31-125, diffuse_mom3D.F90:38-203 (fluxb* = fluxt* = 0).
-// u, v, w, tk through a 3-stage TMA plane ring (levels k, k+1 resident, 1 level of prefetch); dudt, dvdt, dwdt(na) are
-// read-modify-write in the thread's own column (plain loads).
+// Momentum tendencies of the 3-D CRM in two kernels (one fused kernel needs ~40 live neighbour values and ten carried fluxes:
+// at the 64 registers per thread of a 1024-thread block it spilled 600 bytes per thread and level, 7x the DRAM write traffic):
+//   k3_p3_adv   advect2_mom_xy.F90:25-62 (RUN3D) + advect2_mom_z.F90:31-125
+//   k3_p3_dif   diffuse_mom3D.F90:38-203 (fluxb* = fluxt* = 0)
+// u, v, w (, tk) through a 3-stage TMA plane ring (levels k, k+1 resident, 1 level of prefetch); dudt, dvdt, dwdt(na) are
+// read-modify-write in the thread's own column (plain loads).  The order of the updates of dwdt is the reference's: xy-advection
+// (x, y), z-advection, horizontal diffusion (x, y), vertical diffusion.
 // ---------------------------------------------------------------------------------------------------------------
-#define CRM3_P3_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(4, 3, P) + CRM_PROF_BYTES(11, nzp, CT) + (size_t)CRM_RED_DOUBLES(4, P, CT) * 8)
-__global__ void __launch_bounds__(CRM_MAX_P3) k3_p3_mom(CrmP p) {
+#define CRM3_P3A_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(3, 3, P) + CRM_PROF_BYTES(5, nzp, CT) + (size_t)CRM_RED_DOUBLES(2, P, CT) * 8)
+__global__ void __launch_bounds__(CRM_MAX_P3) k3_p3_adv(CrmP p) {
   CRM_TILE_SETUP_T(CRM_G3D)
   CRM_XYNEIGH
-  CRM_DIAG
   CRM_DYN_SMEM(unsigned char, smraw);
   const int nzm = p.nzm, nz = p.nz, npf = p.nzp * CT;
-  PlanePipe<4, 3> R;
-  R.src[0] = p.u + fb; R.src[1] = p.v + fb; R.src[2] = p.w + fb; R.src[3] = p.tk + fb;
-  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(4, 3, P));
-  double *red = sprof + 11 * npf;
-  {
-    const double *const g[6] = {p.rho, p.adz, p.rhow, p.adzw, p.grdf_x, p.grdf_z};
-    stage_profiles<6>(sprof, g, tile, p.nzp, CT, tid, P);
-  }
-  // 6 1/(rhow adzw)  7 dx/(dz adzw)  8 1/(rho adz)  9 1/adz  10 1/adzw
+  PlanePipe<3, 3> R;
+  R.src[0] = p.u + fb; R.src[1] = p.v + fb; R.src[2] = p.w + fb;
+  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(3, 3, P));
+  double *red = sprof + 5 * npf;
+  // 0 rho*adz  1 rhow  2 1/(rhow adzw)  3 1/(rho adz)  4 -
   for (int q = tid; q < p.nz * CT; q += P) {
     const int k = q / CT + 1, ln = q - (k - 1) * CT;
     const int o = tile * p.nzp * CT + k * CT + ln, so = k * CT + ln;
-    const double dzq = p.dz[tile * CT + ln];
     const double rhow = p.rhow[o], adzw = p.adzw[o], rho = p.rho[o], adz = p.adz[o];
-    sprof[6 * npf + so] = 1. / (rhow * adzw);
-    sprof[7 * npf + so] = p.dx / (dzq * adzw);
-    sprof[8 * npf + so] = (k <= nzm) ? 1. / (rho * adz) : 0.;
-    sprof[9 * npf + so] = (k <= nzm) ? 1. / adz : 0.;
-    sprof[10 * npf + so] = 1. / adzw;
+    sprof[so] = rho; sprof[4 * npf + so] = adz;
+    sprof[npf + so] = rhow;
+    sprof[2 * npf + so] = 1. / (rhow * adzw);
+    sprof[3 * npf + so] = (k <= nzm) ? 1. / (rho * adz) : 0.;
   }
   R.init(smraw, P, tid);
-#define S_IRW(k) sprof[6 * npf + (k)*CT + lane]
-#define S_DXZ(k) sprof[7 * npf + (k)*CT + lane]
-#define S_IRS(k) sprof[8 * npf + (k)*CT + lane]
-#define S_IADZ(k) sprof[9 * npf + (k)*CT + lane]
-#define S_IADZW(k) sprof[10 * npf + (k)*CT + lane]
-#define S_RHO(k) sprof[0 * npf + (k)*CT + lane]
-#define S_ADZ(k) sprof[1 * npf + (k)*CT + lane]
-#define S_RHOW(k) sprof[2 * npf + (k)*CT + lane]
-#define S_GRDX(k) sprof[4 * npf + (k)*CT + lane]
-#define S_GRDZ(k) sprof[5 * npf + (k)*CT + lane]
+#define S_RHO(k) sprof[(k)*CT + lane]
+#define S_ADZ(k) sprof[4 * npf + (k)*CT + lane]
+#define S_RHOW(k) sprof[npf + (k)*CT + lane]
+#define S_IRW(k) sprof[2 * npf + (k)*CT + lane]
+#define S_IRS(k) sprof[3 * npf + (k)*CT + lane]
   CRM_PIPE_PROLOGUE(R, nz, 2, 1)
-  const double dz = p.dz[cb], dx = p.dx, dy = p.dy;
-  const double dx25 = 0.25 / dx, dy25 = 0.25 / dy, dz25 = 1. / (4. * dz);
-  const double rdx2 = 1. / (dx * dx), rdy2 = 1. / (dy * dy), rdx25 = 0.25 * rdx2, rdy25 = 0.25 * rdy2;
-  const double dxy = dx / dy, dyx = dy / dx;
-  const double rdz = 1. / dz, dzx = dz / dx, dzy = dz / dy;
-  double fuz_k = 0., fvz_k = 0., fwz_km1 = 0., fuv_k = 0., fvv_k = 0., fwv_k = 0.;
-  double dwa_x = 0., dwa_y = 0., dwd_x = 0., dwd_y = 0.;   // horizontal contributions to dwdt(k) computed while visiting level k-1
+  const double dz = p.dz[cb];
+  const double dx25 = 0.25 / p.dx, dy25 = 0.25 / p.dy, dz25 = 1. / (4. * dz);
+  const int t_pm = tjm + (tp1 - tid), t_mp = tjp + (tm1 - tid);
+  double fuz_k = 0., fvz_k = 0., fwz_km1 = 0., dwa_x = 0., dwa_y = 0.;
   for (int k = 1; k <= nzm; k++) {
     const int kc = k + 1, kcu = imin(kc, nzm);
     __syncthreads();
     CRM_PIPE_STEP(R, k, nz, 2, 1)
     double du = F3(p.du_a, k), dv = F3(p.dv_a, k);
     double dw = (k >= 2) ? F3(p.dw_a, k) : 0.;
-    const double *U = R.plane(0, k), *V = R.plane(1, k), *W = R.plane(2, k), *TK = R.plane(3, k);
-    const double *Uc = R.plane(0, kc), *Vc = R.plane(1, kc), *Wc = R.plane(2, kc), *TKc = R.plane(3, kc);
-    const double *Uu = R.plane(0, kcu), *Vu = R.plane(1, kcu), *TKu = R.plane(3, kcu);
-    const double u_c = U[tid], u_xm = U[tm1], u_xp = U[tp1], u_ym = U[tjm], u_yp = U[tjp], u_pm = U[t_pm];
-    const double v_c = V[tid], v_xm = V[tm1], v_xp = V[tp1], v_ym = V[tjm], v_yp = V[tjp], v_mp = V[t_mp];
-    const double w_c = W[tid], w_kc = Wc[tid], w_kc_xm = Wc[tm1], w_kc_xp = Wc[tp1], w_kc_ym = Wc[tjm], w_kc_yp = Wc[tjp];
-    const double rho_k = S_RHO(k), adz_k = S_ADZ(k);
-    const double rho_u = S_RHO(kcu), adz_u = S_ADZ(kcu);
-    // ---- advect2_mom_xy, x-direction
-    {
+    const double *U = R.plane(0, k), *V = R.plane(1, k), *W = R.plane(2, k);
+    const double *Uc = R.plane(0, kc), *Vc = R.plane(1, kc), *Wc = R.plane(2, kc);
+    const double *Uu = R.plane(0, kcu), *Vu = R.plane(1, kcu);
+    const double u_c = U[tid], u_xm = U[tm1], u_xp = U[tp1], u_ym = U[tjm], u_yp = U[tjp];
+    const double v_c = V[tid], v_xm = V[tm1], v_xp = V[tp1], v_ym = V[tjm], v_yp = V[tjp];
+    const double w_kc = Wc[tid], w_kc_xm = Wc[tm1], w_kc_ym = Wc[tjm];
+    {   // x-direction
       const double fu1 = dx25 * (u_c + u_xm) * (u_xm + u_c);
       const double fu2 = dx25 * (u_xp + u_c) * (u_c + u_xp);
       du = du - (fu2 - fu1);
       const double fv1 = dx25 * (u_c + u_ym) * (v_xm + v_c);
-      const double fv2 = dx25 * (u_xp + u_pm) * (v_c + v_xp);
+      const double fv2 = dx25 * (u_xp + U[t_pm]) * (v_c + v_xp);
       dv = dv - (fv2 - fv1);
     }
     double dwa_x_next, dwa_y_next;
     {
+      const double rho_k = S_RHO(k), adz_k = S_ADZ(k), rho_u = S_RHO(kcu), adz_u = S_ADZ(kcu);
       const double irho = S_IRW(kc);
       const double fw1 = dx25 * (u_c * rho_k * adz_k + Uu[tid] * rho_u * adz_u) * (w_kc_xm + w_kc);
-      const double fw2 = dx25 * (u_xp * rho_k * adz_k + Uu[tp1] * rho_u * adz_u) * (w_kc + w_kc_xp);
+      const double fw2 = dx25 * (u_xp * rho_k * adz_k + Uu[tp1] * rho_u * adz_u) * (w_kc + Wc[tp1]);
       dwa_x_next = irho * (fw2 - fw1);
       const double gw1 = dy25 * (v_c * rho_k * adz_k + Vu[tid] * rho_u * adz_u) * (w_kc_ym + w_kc);
-      const double gw2 = dy25 * (v_yp * rho_k * adz_k + Vu[tjp] * rho_u * adz_u) * (w_kc + w_kc_yp);
+      const double gw2 = dy25 * (v_yp * rho_k * adz_k + Vu[tjp] * rho_u * adz_u) * (w_kc + Wc[tjp]);
       dwa_y_next = irho * (gw2 - gw1);
     }
-    // ---- advect2_mom_xy, y-direction
-    {
+    {   // y-direction
       const double fu1 = dy25 * (v_c + v_xm) * (u_ym + u_c);
-      const double fu2 = dy25 * (v_yp + v_mp) * (u_c + u_yp);
+      const double fu2 = dy25 * (v_yp + V[t_mp]) * (u_c + u_yp);
       du = du - (fu2 - fu1);
       const double fv1 = dy25 * (v_c + v_ym) * (v_ym + v_c);
       const double fv2 = dy25 * (v_yp + v_c) * (v_c + v_yp);
       dv = dv - (fv2 - fv1);
     }
-    // ---- advect2_mom_z
+    // advect2_mom_z
     double fuz_kc = 0., fvz_kc = 0.;
     if (kc <= nzm) {
       const double rhoi = dz25 * S_RHOW(kc);
@@ -279,44 +265,120 @@ __global__ void __launch_bounds__(CRM_MAX_P3) k3_p3_mom(CrmP p) {
     const double rhoi_s = S_IRS(k);
     du = du - (fuz_kc - fuz_k) * rhoi_s;
     dv = dv - (fvz_kc - fvz_k) * rhoi_s;
+    const double w_c = W[tid];
     const double fwz_k = dz25 * (w_kc * S_RHOW(kc) + w_c * S_RHOW(k)) * (w_kc + w_c);
-    // ---- diffuse_mom3D: x-direction fluxes at i and i-1
-    const double tk_c = TK[tid], tk_xm = TK[tm1], tk_xp = TK[tp1], tk_ym = TK[tjm], tk_yp = TK[tjp];
-    const double tk_pm = TK[t_pm], tk_mm = TK[t_mm], tk_mp = TK[t_mp];
-    const double tku_c = TKu[tid];
+    F3(p.du_a, k) = du;
+    F3(p.dv_a, k) = dv;
+    if (k >= 2) {
+      dw = dw - dwa_x;
+      dw = dw - dwa_y;
+      dw = dw - (fwz_k - fwz_km1) * S_IRW(k);
+      F3(p.dw_a, k) = dw;
+    }
+    if (p.last_substep) {   // uwle, vwle (advect2_mom_z.F90:76-109)
+      double v[2] = {fuz_k, fvz_k};
+      block_sum_lead<2>(v, tid, P, CT, red);
+      if (i == 0) { PF(p.uwle, k) = v[0]; PF(p.vwle, k) = v[1]; }
+    }
+    fuz_k = fuz_kc; fvz_k = fvz_kc; fwz_km1 = fwz_k; dwa_x = dwa_x_next; dwa_y = dwa_y_next;
+  }
+#undef S_RHO
+#undef S_ADZ
+#undef S_RHOW
+#undef S_IRW
+#undef S_IRS
+}
+
+#define CRM3_P3B_SMEM(P, CT, nzp) (CRM_PIPE_BYTES(4, 3, P) + CRM_PROF_BYTES(9, nzp, CT) + (size_t)CRM_RED_DOUBLES(2, P, CT) * 8)
+__global__ void __launch_bounds__(CRM_MAX_P3) k3_p3_dif(CrmP p) {
+  CRM_TILE_SETUP_T(CRM_G3D)
+  CRM_XYNEIGH
+  CRM_DYN_SMEM(unsigned char, smraw);
+  const int nzm = p.nzm, nz = p.nz, npf = p.nzp * CT;
+  PlanePipe<4, 3> R;
+  R.src[0] = p.u + fb; R.src[1] = p.v + fb; R.src[2] = p.w + fb; R.src[3] = p.tk + fb;
+  double *sprof = (double *)(smraw + CRM_PIPE_BYTES(4, 3, P));
+  double *red = sprof + 9 * npf;
+  // 0 rho  1 adz  2 rhow  3 grdf_x  4 grdf_z  5 1/(rhow adzw)  6 dx/(dz adzw)  7 1/(rho adz)  8 1/adzw
+  {
+    const double *const g[5] = {p.rho, p.adz, p.rhow, p.grdf_x, p.grdf_z};
+    stage_profiles<5>(sprof, g, tile, p.nzp, CT, tid, P);
+  }
+  for (int q = tid; q < p.nz * CT; q += P) {
+    const int k = q / CT + 1, ln = q - (k - 1) * CT;
+    const int o = tile * p.nzp * CT + k * CT + ln, so = k * CT + ln;
+    const double dzq = p.dz[tile * CT + ln];
+    const double rhow = p.rhow[o], adzw = p.adzw[o], rho = p.rho[o], adz = p.adz[o];
+    sprof[5 * npf + so] = 1. / (rhow * adzw);
+    sprof[6 * npf + so] = p.dx / (dzq * adzw);
+    sprof[7 * npf + so] = (k <= nzm) ? 1. / (rho * adz) : 0.;
+    sprof[8 * npf + so] = 1. / adzw;
+  }
+  R.init(smraw, P, tid);
+#define S_RHO(k) sprof[0 * npf + (k)*CT + lane]
+#define S_ADZ(k) sprof[1 * npf + (k)*CT + lane]
+#define S_RHOW(k) sprof[2 * npf + (k)*CT + lane]
+#define S_GRDX(k) sprof[3 * npf + (k)*CT + lane]
+#define S_GRDZ(k) sprof[4 * npf + (k)*CT + lane]
+#define S_IRW(k) sprof[5 * npf + (k)*CT + lane]
+#define S_DXZ(k) sprof[6 * npf + (k)*CT + lane]
+#define S_IRS(k) sprof[7 * npf + (k)*CT + lane]
+#define S_IADZW(k) sprof[8 * npf + (k)*CT + lane]
+  CRM_PIPE_PROLOGUE(R, nz, 2, 1)
+  const double dz = p.dz[cb], dx = p.dx, dy = p.dy;
+  const double rdx2 = 1. / (dx * dx), rdy2 = 1. / (dy * dy), rdx25 = 0.25 * rdx2, rdy25 = 0.25 * rdy2;
+  const double dxy = dx / dy, dyx = dy / dx;
+  const double rdz = 1. / dz, dzx = dz / dx, dzy = dz / dy;
+  const int t_pm = tjm + (tp1 - tid), t_mp = tjp + (tm1 - tid), t_mm = tjm + (tm1 - tid);
+  double fuv_k = 0., fvv_k = 0., fwv_k = 0., dwd_x = 0., dwd_y = 0.;
+  for (int k = 1; k <= nzm; k++) {
+    const int kc = k + 1, kcu = imin(kc, nzm);
+    __syncthreads();
+    CRM_PIPE_STEP(R, k, nz, 2, 1)
+    double du = F3(p.du_a, k), dv = F3(p.dv_a, k);
+    double dw = (k >= 2) ? F3(p.dw_a, k) : 0.;
+    const double *U = R.plane(0, k), *V = R.plane(1, k), *W = R.plane(2, k), *TK = R.plane(3, k);
+    const double *Uc = R.plane(0, kc), *Vc = R.plane(1, kc), *Wc = R.plane(2, kc), *TKc = R.plane(3, kc);
+    const double *Uu = R.plane(0, kcu), *Vu = R.plane(1, kcu), *TKu = R.plane(3, kcu);
+    const double u_c = U[tid], u_xm = U[tm1], u_xp = U[tp1], u_ym = U[tjm], u_yp = U[tjp];
+    const double v_c = V[tid], v_xm = V[tm1], v_xp = V[tp1], v_ym = V[tjm], v_yp = V[tjp], v_mp = V[t_mp];
+    const double w_kc = Wc[tid], w_kc_xm = Wc[tm1], w_kc_ym = Wc[tjm];
+    const double tk_c = TK[tid], tk_xm = TK[tm1], tk_ym = TK[tjm], tk_mm = TK[t_mm], tku_c = TKu[tid];
     double dwd_x_next, dwd_y_next;
-    {
+    {   // x-direction fluxes at i and i-1
       const double rdx21 = rdx2 * S_GRDX(k), rdx251 = rdx25 * S_GRDX(k);
       const double dxz = S_DXZ(kc);
+      const double tk_xp = TK[tp1], u_pm = U[t_pm];
       const double fu_i = -2. * (rdx21 * tk_c) * (u_xp - u_c);
       const double fu_m = -2. * (rdx21 * tk_xm) * (u_c - u_xm);
       du = du - (fu_i - fu_m);
-      const double fv_i = -(rdx251 * (tk_c + tk_ym + tk_xp + tk_pm)) * (v_xp - v_c + (u_xp - u_pm) * dxy);
+      const double fv_i = -(rdx251 * (tk_c + tk_ym + tk_xp + TK[t_pm])) * (v_xp - v_c + (u_xp - u_pm) * dxy);
       const double fv_m = -(rdx251 * (tk_xm + tk_mm + tk_c + tk_ym)) * (v_c - v_xm + (u_c - u_ym) * dxy);
       dv = dv - (fv_i - fv_m);
-      const double fw_i = -(rdx251 * (tk_c + tk_xp + tku_c + TKu[tp1])) * (w_kc_xp - w_kc + (Uu[tp1] - u_xp) * dxz);
+      const double fw_i = -(rdx251 * (tk_c + tk_xp + tku_c + TKu[tp1])) * (Wc[tp1] - w_kc + (Uu[tp1] - u_xp) * dxz);
       const double fw_m = -(rdx251 * (tk_xm + tk_c + TKu[tm1] + tku_c)) * (w_kc - w_kc_xm + (Uu[tid] - u_c) * dxz);
       dwd_x_next = fw_i - fw_m;
     }
-    // ---- diffuse_mom3D: y-direction fluxes at j and j-1 (dy == dx: grdf_y == grdf_x, dyz == dxz)
-    {
+    {   // y-direction fluxes at j and j-1 (dy == dx: grdf_y == grdf_x, dyz == dxz)
       const double rdy21 = rdy2 * S_GRDX(k), rdy251 = rdy25 * S_GRDX(k);
       const double dyz = S_DXZ(kc);
+      const double tk_yp = TK[tjp];
       const double fv_j = -2. * (rdy21 * tk_c) * (v_yp - v_c);
       const double fv_b = -2. * (rdy21 * tk_ym) * (v_c - v_ym);
-      const double fu_j = -(rdy251 * (tk_c + tk_xm + tk_yp + tk_mp)) * (u_yp - u_c + (v_yp - v_mp) * dyx);
+      const double fu_j = -(rdy251 * (tk_c + tk_xm + tk_yp + TK[t_mp])) * (u_yp - u_c + (v_yp - v_mp) * dyx);
       const double fu_b = -(rdy251 * (tk_ym + tk_mm + tk_c + tk_xm)) * (u_c - u_ym + (v_c - v_xm) * dyx);
       du = du - (fu_j - fu_b);
       dv = dv - (fv_j - fv_b);
-      const double fw_j = -(rdy251 * (tk_c + tk_yp + tku_c + TKu[tjp])) * (w_kc_yp - w_kc + (Vu[tjp] - v_yp) * dyz);
+      const double fw_j = -(rdy251 * (tk_c + tk_yp + tku_c + TKu[tjp])) * (Wc[tjp] - w_kc + (Vu[tjp] - v_yp) * dyz);
       const double fw_b = -(rdy251 * (tk_ym + tk_c + TKu[tjm] + tku_c)) * (w_kc - w_kc_ym + (Vu[tid] - v_c) * dyz);
       dwd_y_next = fw_j - fw_b;
     }
-    // ---- diffuse_mom3D: vertical part
+    // vertical part
     double fuv_kc = 0., fvv_kc = 0., fwv_kc;
+    const double w_c = W[tid], rho_k = S_RHO(k);
     if (k <= nzm - 1) {
       const double rdz2 = rdz * rdz * S_GRDZ(k), rdz25 = 0.25 * rdz2;
-      const double iadz = S_IADZ(k), iadzw = S_IADZW(kc);
+      const double iadz = 1. / S_ADZ(k), iadzw = S_IADZW(kc);
       double tkz = rdz2 * tk_c;
       fwv_kc = -2. * tkz * (w_kc - w_c) * rho_k * iadz;
       tkz = rdz25 * (tk_c + tk_xm + TKc[tid] + TKc[tm1]);
@@ -326,29 +388,25 @@ __global__ void __launch_bounds__(CRM_MAX_P3) k3_p3_mom(CrmP p) {
     } else {   // k == nzm: fw(.,nz) (diffuse_mom3D.F90:159-163); fu, fv(.,nz) = fluxt*... = 0
       const double rdz2 = rdz * rdz * S_GRDZ(nzm - 1);
       const double tkz = rdz2 * S_GRDZ(nzm) * tk_c;
-      fwv_kc = -2. * tkz * (w_kc - w_c) / adz_k * rho_k;
+      fwv_kc = -2. * tkz * (w_kc - w_c) / S_ADZ(k) * rho_k;
     }
+    const double rhoi_s = S_IRS(k);
     du = du - (fuv_kc - fuv_k) * rhoi_s;
     dv = dv - (fvv_kc - fvv_k) * rhoi_s;
     F3(p.du_a, k) = du;
     F3(p.dv_a, k) = dv;
-    if (k >= 2) {   // reference order: xy-advection (x, y), z-advection, horizontal diffusion (x, y), vertical diffusion
-      dw = dw - dwa_x;
-      dw = dw - dwa_y;
-      const double rhoi_w = S_IRW(k);
-      dw = dw - (fwz_k - fwz_km1) * rhoi_w;
+    if (k >= 2) {
       dw = dw - dwd_x;
       dw = dw - dwd_y;
-      dw = dw - (fwv_kc - fwv_k) * rhoi_w;
+      dw = dw - (fwv_kc - fwv_k) * S_IRW(k);
       F3(p.dw_a, k) = dw;
     }
-    if (p.last_substep) {   // uwle, vwle (advect2_mom_z.F90:76-109), uwsb, vwsb (diffuse_mom3D.F90:140-173)
-      double v[4] = {fuz_k, fuv_k, fvz_k, fvv_k};
-      block_sum_lead<4>(v, tid, P, CT, red);
-      if (i == 0) { PF(p.uwle, k) = v[0]; PF(p.uwsb, k) = v[1]; PF(p.vwle, k) = v[2]; PF(p.vwsb, k) = v[3]; }
+    if (p.last_substep) {   // uwsb, vwsb (diffuse_mom3D.F90:140-173)
+      double v[2] = {fuv_k, fvv_k};
+      block_sum_lead<2>(v, tid, P, CT, red);
+      if (i == 0) { PF(p.uwsb, k) = v[0]; PF(p.vwsb, k) = v[1]; }
     }
-    fuz_k = fuz_kc; fvz_k = fvz_kc; fwz_km1 = fwz_k; fuv_k = fuv_kc; fvv_k = fvv_kc; fwv_k = fwv_kc;
-    dwa_x = dwa_x_next; dwa_y = dwa_y_next; dwd_x = dwd_x_next; dwd_y = dwd_y_next;
+    fuv_k = fuv_kc; fvv_k = fvv_kc; fwv_k = fwv_kc; dwd_x = dwd_x_next; dwd_y = dwd_y_next;
   }
 #undef S_RHO
 #undef S_ADZ
@@ -358,7 +416,6 @@ __global__ void __launch_bounds__(CRM_MAX_P3) k3_p3_mom(CrmP p) {
 #undef S_IRW
 #undef S_DXZ
 #undef S_IRS
-#undef S_IADZ
 #undef S_IADZW
 }
 

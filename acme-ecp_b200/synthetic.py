@@ -17,6 +17,7 @@ CONFIGS = {
     # name: ncrms, nx, ny, nzm, plev, dx, dt   (BASELINE.json configs)
     "cfg1": dict(ncrms=866, nx=32, ny=1, nzm=28, plev=30, dx=4000.0, dt=20.0),
     "cfg2": dict(ncrms=48602, nx=64, ny=1, nzm=58, plev=72, dx=1000.0, dt=10.0),
+    "cfg3": dict(ncrms=48602, nx=64, ny=1, nzm=58, plev=72, dx=1000.0, dt=10.0, micro=1),
     "cfg4": dict(ncrms=4096, nx=32, ny=32, nzm=58, plev=72, dx=1000.0, dt=10.0),
     "cfg5": dict(ncrms=194402, nx=32, ny=1, nzm=58, plev=72, dx=1000.0, dt=10.0),
 }
@@ -37,16 +38,33 @@ def _qsatw(T, p_pa):
     return 0.622 * es / (p_pa - es)
 
 
-def make_inputs(dims, seed=20260101, lat_range=(-1.0, 1.0)):
-    """Return (crm_input, crm_state, crm_rad) for ``dims``; rows ncrms..ld-1 are filled with copies of valid columns."""
+def make_inputs(dims, seed=20260101, lat_range=(-1.0, 1.0), rows=None, nglobal=None, sort_by_lat=False):
+    """Return (crm_input, crm_state, crm_rad) for ``dims``; rows ncrms..ld-1 are filled with copies of valid columns.
+
+    Column sharding (bench.py --config cfg5 --gpus N): with ``rows`` (global column indices owned by this rank) and
+    ``nglobal`` (size of the global batch) the per-column random draws are made for the whole global batch - every rank
+    draws the same numbers - optionally ordered by latitude like a GCM's column numbering, and only the columns ``rows``
+    are built (dims.ld == len(rows)); the 3-D state is never materialised for columns of other ranks."""
     rng = np.random.Generator(np.random.PCG64(seed))
     n, ld, plev, nzm = dims.ncrms, dims.ld, dims.plev, dims.nzm
     hyai, hybi, hyam, hybm = vcoord(plev)
     inp = crm_input_type().initialize(dims)
-    ps = 101325.0 + 300.0 * rng.standard_normal(ld)
-    sinlat = rng.uniform(lat_range[0], lat_range[1], ld)
+    ng = ld if rows is None else int(nglobal)
+    ps = 101325.0 + 300.0 * rng.standard_normal(ng)
+    sinlat = rng.uniform(lat_range[0], lat_range[1], ng)
+    lon = rng.uniform(0.0, 360.0, ng)
+    cloud_u = rng.uniform(0.0, 1.0, ng)
+    noise_u = rng.standard_normal((ng, plev))
+    noise_v = rng.standard_normal((ng, plev))
+    gcol = np.arange(1, ng + 1, dtype=np.int32)
+    if sort_by_lat:
+        order = np.argsort(sinlat, kind="stable")
+        ps, sinlat, lon, cloud_u, noise_u, noise_v = ps[order], sinlat[order], lon[order], cloud_u[order], noise_u[order], noise_v[order]
+    if rows is not None:
+        rows = np.asarray(rows)
+        assert len(rows) == ld, "dims.ld must equal the number of owned columns"
+        ps, sinlat, lon, cloud_u, noise_u, noise_v, gcol = ps[rows], sinlat[rows], lon[rows], cloud_u[rows], noise_u[rows], noise_v[rows], gcol[rows]
     lat = np.arcsin(sinlat)
-    lon = rng.uniform(0.0, 360.0, ld)
     pint = hyai[None, :] * 1.0e5 + hybi[None, :] * ps[:, None]
     pmid = hyam[None, :] * 1.0e5 + hybm[None, :] * ps[:, None]
     pdel = np.diff(pint, axis=1)
@@ -58,7 +76,7 @@ def make_inputs(dims, seed=20260101, lat_range=(-1.0, 1.0)):
     # (deviation from SURVEY.md 8(d), which has qccl=qiil=0 and leaves the CRM cloud-free for many calls).
     RH = np.clip(0.35 + 0.63 * ((sig - 0.3) / 0.6), 0.3, 0.98)
     ql = RH * _qsatw(T, pmid)
-    cloudy = (rng.uniform(0.0, 1.0, ld) < 0.7)[:, None]
+    cloudy = (cloud_u < 0.7)[:, None]
     qccl = np.where(cloudy & (sig > 0.55) & (sig < 0.9) & (T > 263.0), 1.6e-3 * np.sin(np.pi * (sig - 0.55) / 0.35) ** 2, 0.0)
     qiil = np.where(cloudy & (sig > 0.25) & (sig < 0.6) & (T < 258.0), 3.0e-4 * np.sin(np.pi * (sig - 0.25) / 0.35) ** 2, 0.0)
     Tv = T * (1.0 + 0.608 * ql)
@@ -69,8 +87,8 @@ def make_inputs(dims, seed=20260101, lat_range=(-1.0, 1.0)):
     zmid = np.zeros((ld, plev))
     for l in range(plev):
         zmid[:, l] = zint[:, l + 1] + RD * Tv[:, l] / G * np.log(pint[:, l + 1] / pmid[:, l])
-    ul = 30.0 * np.sin(2 * lat)[:, None] ** 2 * (1.0 - sig) + 2.0 * rng.standard_normal((ld, plev))
-    vl = 2.0 * rng.standard_normal((ld, plev))
+    ul = 30.0 * np.sin(2 * lat)[:, None] ** 2 * (1.0 - sig) + 2.0 * noise_u
+    vl = 2.0 * noise_v
     inp.zmid[...] = zmid; inp.zint[...] = zint; inp.tl[...] = T; inp.ql[...] = ql
     inp.qccl[...] = qccl; inp.qiil[...] = qiil
     inp.ps[...] = ps; inp.pmid[...] = pmid; inp.pint[...] = pint; inp.pdel[...] = pdel
@@ -78,7 +96,7 @@ def make_inputs(dims, seed=20260101, lat_range=(-1.0, 1.0)):
     inp.ocnfrac[...] = 1.0; inp.tau00[...] = 0.05; inp.bflxls[...] = 5.0e-3 * np.cos(lat)
     inp.wndls[...] = np.abs(ul[:, plev - 1])
     inp.lat_deg[...] = np.degrees(lat); inp.lon_deg[...] = lon
-    inp.gcol[...] = np.arange(1, ld + 1, dtype=np.int32)
+    inp.gcol[...] = gcol
 
     st = crm_state_type().initialize(dims)
     rad = crm_rad_type().initialize(dims)
@@ -108,3 +126,18 @@ def make_case(name_or_dims, seed=None, **over):
             seed = 20260101
     inp, st, rad = make_inputs(dims, seed)
     return dims, inp, st, rad
+
+
+def make_sharded_case(name, rank, world, mode="roundrobin", seed=None, ncrms=None, **over):
+    """This rank's share of a named config whose GLOBAL batch (ordered by latitude) is partitioned over ``world`` GPUs with
+    shard.shard_indices(mode) - "block" (contiguous gcol ranges, the reference's chunking) or "roundrobin"."""
+    from .shard import shard_indices
+    kw = dict(CONFIGS[name]); kw.update(over)
+    nglobal = int(ncrms or kw["ncrms"])
+    idx = shard_indices(nglobal, rank, world, mode)
+    kw["ncrms"] = len(idx)
+    dims = CrmDims(**kw)
+    if seed is None:
+        seed = 20260101 + int(name[3:])
+    inp, st, rad = make_inputs(dims, seed, rows=idx, nglobal=nglobal, sort_by_lat=True)
+    return dims, inp, st, rad, idx

@@ -26,11 +26,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-BYTES_PER_CELL_UPDATE = {"2d_sam1mom": 872.0}   # SURVEY.md 8(d) / App. C algorithmic traffic model
-# distinct 3-D arrays read + written per cell by each kernel of this implementation
-KERNEL_WORDS = {"k_p1_forcing": 14, "k_p2_sgs": 13, "k_p3_mom": 7, "k_p4_press_fwd": 9, "k_p5_press_bwd": 16,
-                "k_mpdata": 4, "k_precip_a": 3, "k_precip_b": 7, "k_p7_diffuse": 7, "k_p8_micro": 13, "k_stats": 7,
-                "k_kurant": 3}
+# SURVEY.md 8(d) / App. C algorithmic traffic model (fixed constants)
+BYTES_PER_CELL_UPDATE = {"2d_sam1mom": 872.0, "3d_sam1mom": 880.0, "2d_m2005": 1456.0}
+CONFIG_CLASS = {"cfg1": "2d_sam1mom", "cfg2": "2d_sam1mom", "cfg3": "2d_m2005", "cfg4": "3d_sam1mom", "cfg5": "2d_sam1mom"}
+# distinct 3-D arrays read + written per cell by each kernel of this implementation (same table there)
+KERNEL_WORDS = {
+    "2d": {"k_p1_forcing": 14, "k_p2_sgs": 14, "k_p3_mom": 7, "k_p4_press_fwd": 9, "k_p5_press_bwd": 15,
+           "k_mpdata": 4, "k_mpdata3": 8, "k_precip_a": 3, "k_precip_b": 7, "k_p7_diffuse": 7, "k_p8_micro": 13, "k_stats": 7,
+           "k_kurant": 3},
+    "3d": {"k_p1_forcing": 16, "k3_p2_sgs": 14, "k3_p3_adv": 9, "k3_p3_dif": 10, "k3_p4_press_fwd": 13, "k3_p5_press_bwd": 23,
+           "k3_mpdata": 5, "k_precip_a": 3, "k_precip_b": 7, "k_p7_diffuse": 7, "k_p8_micro": 14, "k_stats": 7, "k_kurant": 4},
+}
 
 
 def peaks():
@@ -103,8 +109,22 @@ def build_case(pkg, cfg, ncrms, seed):
     kw = dict(pkg.synthetic.CONFIGS[cfg])
     if ncrms:
         kw["ncrms"] = ncrms
+    if kw["ny"] > 1:
+        kw.update(nx_rad=kw["nx"] // 4, ny_rad=kw["ny"] // 4)
     dims = pkg.CrmDims(dt_gl=1800.0, igstep=1, **kw)
     return pkg.synthetic.make_case(dims, seed=seed)
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_sample_ncrms(args):
+    """The CPU arm parallelises over CRMs with a barrier per sub-step: at least 8 CRMs per host thread."""
+    return args.cpu_ncrms if args.cpu_ncrms > 0 else max(128, 8 * host_threads())
 
 
 def run_reference(args):
@@ -116,14 +136,11 @@ def run_reference(args):
         return
     pkg = importlib.import_module("acme-ecp_b200")
     import oracle_binding as ob
-    ncrms, nstop = args.cpu_ncrms, args.cpu_nstop
+    ncrms, nstop = cpu_sample_ncrms(args), args.cpu_nstop
     dims, inp, st, rad = build_case(pkg, args.config, ncrms, 20260101 + int(args.config[3:]))
     dims = dims.copy(dt_gl=dims.dt * nstop)
     # all host threads this process may use (torchrun sets OMP_NUM_THREADS=1 for its ranks; only rank 0 works here)
-    try:
-        navail = len(os.sched_getaffinity(0))
-    except AttributeError:
-        navail = os.cpu_count() or 1
+    navail = host_threads()
     ob.lib().crm_oracle_set_num_threads(int(navail))
     cores = ob.lib().crm_oracle_num_threads()
     for w in range(args.warmup):
@@ -135,19 +152,20 @@ def run_reference(args):
         upd += dims.cells * s["ncycle_sum"]
     dt = time.time() - t0
     val = upd / dt
-    sample = "%d CRMs x %d CRM steps per step of the %s geometry (same seed), all host threads" % (ncrms, nstop, args.config)
+    sample = "%d CRMs x %d CRM steps per step of the %s geometry (same seed), %d host threads (%d CRMs per thread)" % (
+        ncrms, nstop, args.config, cores, ncrms // max(1, cores))
     line = {"impl": "reference", "metric": "CRM cell-updates/s", "value": val, "unit": "cell-updates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args, dims), "sample": sample},
+            "config": {"workload": workload_name(args, dims) + "; CPU arm: %d host threads" % cores, "sample": sample},
             "cpu_baseline": {"value": val, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 def workload_name(args, dims):
-    return "%s: %d CRMs/GPU of %dx%dx%d sam1mom, crm_dt %g s, dt_gl %g s (nstop %d), synthetic aquaplanet columns" % (
-        args.config, dims.ncrms, dims.nx, dims.ny, dims.nzm, dims.dt, dims.dt_gl, int(dims.dt_gl / dims.dt))
+    return "%s: %d CRMs/GPU of %dx%dx%d %s, crm_dt %g s, dt_gl %g s (nstop %d), synthetic aquaplanet columns" % (
+        args.config, dims.ncrms, dims.nx, dims.ny, dims.nzm, "m2005" if dims.micro else "sam1mom", dims.dt, dims.dt_gl, int(dims.dt_gl / dims.dt))
 
 
 def run_e2e(args, pkg, abi, h, dims, inp, ci, st, rad, dstate, big, world, barrier, torch, dist, state_shape):
@@ -229,7 +247,13 @@ def run_ours(args):
     torch.cuda.set_device(lrank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
-    dims, inp, st, rad = build_case(pkg, args.config, args.ncrms, 20260101 + int(args.config[3:]) + 1000 * rank)
+    partition = args.partition
+    if partition == "auto":   # cfg5 is THE column-partition case (one global batch over the GPUs); the others weak-scale
+        partition = "roundrobin" if (args.config == "cfg5" and world > 1) else "replicate"
+    if partition == "replicate":
+        dims, inp, st, rad = build_case(pkg, args.config, args.ncrms, 20260101 + int(args.config[3:]) + 1000 * rank)
+    else:   # one global batch, ordered by latitude, partitioned with shard.shard_indices
+        dims, inp, st, rad, _ = pkg.synthetic.make_sharded_case(args.config, rank, world, partition, ncrms=args.ncrms or None, dt_gl=1800.0, igstep=1)
     if args.nstop:
         dims = dims.copy(dt_gl=dims.dt * args.nstop)
     h = libmod.CrmHandle(dims, device=lrank)
@@ -278,11 +302,18 @@ def run_ours(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms, float(upd), float(launches)], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, float(upd), float(launches), float(ncyc), float(dims.ncrms)], dtype=torch.float64, device="cuda")
+    per_rank = None
     if world > 1:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, upd_all, launches_all = float(tmax[0]), float(tsum[1]), int(tsum[2])
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        allt = torch.stack(allt).cpu().numpy()
+        ms_r = allt[:, 0]
+        ms, upd_all, launches_all = float(ms_r.max()), float(allt[:, 1].sum()), int(allt[:, 2].sum())
+        # load balance of the column partition: device time, sub-step count and idle share (waiting for the slowest rank) per rank
+        per_rank = {"ms": [round(float(x), 1) for x in ms_r], "ncycle_sum": [int(x) for x in allt[:, 3]], "ncrms": [int(x) for x in allt[:, 4]],
+                    "idle_frac": [round(float(1.0 - x / ms_r.max()), 4) for x in ms_r],
+                    "balance_efficiency": float(ms_r.mean() / ms_r.max())}
     else:
         upd_all, launches_all = float(upd), int(launches)
     value = upd_all / (ms * 1e-3)
@@ -296,17 +327,18 @@ def run_ours(args):
         kt = h.kernel_times()
         h.set_kernel_timing(False)
         tot = sum(v[0] for v in kt.values())
-        name = max((k for k in kt if k in KERNEL_WORDS), key=lambda k: kt[k][0])
+        kwords = KERNEL_WORDS["3d" if dims.ny > 1 else "2d"]
+        bpcu = BYTES_PER_CELL_UPDATE[CONFIG_CLASS.get(args.config, "2d_sam1mom")]
+        name = max((k for k in kt if k in kwords), key=lambda k: kt[k][0])
         ms_k, n_k = kt[name]
-        alg = KERNEL_WORDS[name] * 8.0 * dims.cells            # bytes per launch
+        alg = kwords[name] * 8.0 * dims.cells            # bytes per launch
         ach = alg / (ms_k / n_k * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": ncu_traffic(name, dims.ncrms),
                 "peak_source": peak_src, "kernel_share_of_step": ms_k / tot,
                 "algorithmic_bytes_per_launch": alg,
-                "whole_step": {"bytes_per_cell_update": BYTES_PER_CELL_UPDATE["2d_sam1mom"],
-                               "achieved": BYTES_PER_CELL_UPDATE["2d_sam1mom"] * (value / world) / 1e9,
-                               "frac": BYTES_PER_CELL_UPDATE["2d_sam1mom"] * (value / world) / 1e9 / peak},
+                "whole_step": {"bytes_per_cell_update": bpcu, "achieved": bpcu * (value / world) / 1e9, "frac": bpcu * (value / world) / 1e9 / peak},
+                "kernel_frac": {k: round(kwords[k] * 8.0 * dims.cells / (v[0] / v[1] * 1e-3) / 1e9 / peak, 3) for k, v in kt.items() if k in kwords},
                 "kernel_ms": {k: round(v[0], 3) for k, v in sorted(kt.items(), key=lambda kv: -kv[1][0])}}
 
     e2e = None
@@ -321,21 +353,26 @@ def run_ours(args):
             ob.lib().crm_oracle_set_num_threads(len(os.sched_getaffinity(0)))
         except AttributeError:
             pass
-        d2, i2, s2, r2 = build_case(pkg, args.config, args.cpu_ncrms, 20260101 + int(args.config[3:]))
+        d2, i2, s2, r2 = build_case(pkg, args.config, cpu_sample_ncrms(args), 20260101 + int(args.config[3:]))
         d2 = d2.copy(dt_gl=d2.dt * args.cpu_nstop)
         ob.run(d2.copy(igstep=1), i2, s2, r2)
         t0 = time.time()
         _, so = ob.run(d2.copy(igstep=3), i2, s2, r2)
         tc = time.time() - t0
         cpu = {"value": d2.cells * so["ncycle_sum"] / tc, "unit": "cell-updates/s", "cores": ob.lib().crm_oracle_num_threads(),
-               "kind": "port", "sample": "%d CRMs x %d CRM steps of the %s geometry after a %d-step spin-up, OpenMP over CRMs" %
-               (args.cpu_ncrms, args.cpu_nstop, args.config, args.cpu_nstop)}
+               "kind": "port", "sample": "%d CRMs x %d CRM steps of the %s geometry after a %d-step spin-up, OpenMP over CRMs (%d per thread)" %
+               (d2.ncrms, args.cpu_nstop, args.config, args.cpu_nstop, d2.ncrms // max(1, ob.lib().crm_oracle_num_threads()))}
     if rank == 0:
         line = {"metric": "CRM cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True,
+                "scaling": "weak" if partition == "replicate" else "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(args, dims), "l2": "inputs larger than L2 (44 GB of state per GPU)" if dims.cells > 2e7 else "small batch",
-                           "mean_ncycle": ncyc / max(1, args.steps * int(dims.dt_gl / dims.dt)), "partition": "columns block-partitioned, no collective"},
+                           "mean_ncycle": ncyc / max(1, args.steps * int(dims.dt_gl / dims.dt)),
+                           "partition": ("every GPU runs its own batch of this size (weak scaling), no collective" if partition == "replicate" else
+                                         "one global batch of %d columns ordered by latitude, %s-partitioned over %d GPUs (shard.shard_indices), no collective" %
+                                         (int(sum(per_rank["ncrms"])) if per_rank else dims.ncrms, partition, world)),
+                           "per_rank": per_rank},
                 "gpu_launches": launches_all, "kernel_ms_per_step": kms / max(args.steps, 1),
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks}
         print(json.dumps(line))
@@ -354,7 +391,10 @@ def main():
     ap.add_argument("--ncrms", type=int, default=0, help="override the batch size (testing only)")
     ap.add_argument("--nstop", type=int, default=0, help="override CRM steps per call (testing only)")
     ap.add_argument("--e2e-steps", type=int, default=1)
-    ap.add_argument("--cpu-ncrms", type=int, default=128)
+    ap.add_argument("--cpu-ncrms", type=int, default=0, help="CRMs of the CPU sample (default: max(128, 8 per host thread))")
+    ap.add_argument("--partition", default="auto", choices=["auto", "replicate", "block", "roundrobin"],
+                    help="replicate: every rank runs the config's batch (weak scaling); block/roundrobin: the config's batch is ONE global "
+                         "batch partitioned over the ranks (auto: roundrobin for cfg5 on several GPUs, else replicate)")
     ap.add_argument("--cpu-nstop", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
