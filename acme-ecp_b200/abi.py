@@ -62,8 +62,15 @@ OUTPUT_FIELDS = (
                           "qt_ls", "qt_trans", "qp_trans", "qp_fall", "qp_src", "qp_evp", "t_ls", "ultend", "vltend")])
 
 
+# m2005 members of crm_output_type (CRM/crm_output_module.F90:22-31, 60-74), appended to the struct (ABI 3)
+OUTPUT_FIELDS_M2005 = (
+    [(n, "crm3d") for n in ("wvar", "aut", "acc", "evpc", "evpr", "mlt", "sub", "dep", "con")] +
+    [(n, "lev") for n in ("nc_mean", "ni_mean", "ns_mean", "ng_mean", "nr_mean",
+                          "aut_a", "acc_a", "evpc_a", "evpr_a", "mlt_a", "sub_a", "dep_a", "con_a")])
+
+
 class crm_output_t(C.Structure):
-    _fields_ = [(n, c_dp) for n, _ in OUTPUT_FIELDS]
+    _fields_ = [(n, c_dp) for n, _ in OUTPUT_FIELDS + OUTPUT_FIELDS_M2005]
 
 
 class crm_run_stats_t(C.Structure):

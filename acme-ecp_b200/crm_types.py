@@ -73,22 +73,27 @@ class crm_input_type(_Bag):
 
 
 class crm_state_type(_Bag):
+    """crm_state_type; the m2005 members (nc, qr, nr, qi, ni, qs, ns, qg, ng, qc: crm_state_module.F90:34-45) exist when
+    initialize() is given dims with micro = 1 (qp and qn are then unused, as in the reference's m2005 build)."""
     _fields = [(n, "crm3d") for n in abi.STATE_FIELDS_SAM1MOM]
 
+    def names(self):
+        return list(abi.STATE_FIELDS_SAM1MOM) + [n for n in abi.STATE_FIELDS_M2005 if getattr(self, n, None) is not None]
+
     def initialize(self, dims):
-        for n in abi.STATE_FIELDS_SAM1MOM:
+        for n in abi.STATE_FIELDS_SAM1MOM + (abi.STATE_FIELDS_M2005 if getattr(dims, "micro", 0) == 1 else []):
             setattr(self, n, np.zeros(abi.shape_of("crm3d", dims), order="F"))
         return self
 
     def c_struct(self):
         s = abi.crm_state_t()
-        for n in abi.STATE_FIELDS_SAM1MOM:
+        for n in self.names():
             setattr(s, n, abi.dptr(getattr(self, n)))
         return s
 
     def copy(self):
         o = crm_state_type()
-        for n in abi.STATE_FIELDS_SAM1MOM:
+        for n in self.names():
             setattr(o, n, getattr(self, n).copy(order="F"))
         return o
 
@@ -96,20 +101,23 @@ class crm_state_type(_Bag):
 class crm_rad_type(_Bag):
     _fields = [(n, "rad") for n in abi.RAD_FIELDS_SAM1MOM]
 
+    def names(self):
+        return [n for n in abi.RAD_FIELDS if getattr(self, n, None) is not None]
+
     def initialize(self, dims):
-        for n in abi.RAD_FIELDS_SAM1MOM:
+        for n in (abi.RAD_FIELDS if getattr(dims, "micro", 0) == 1 else abi.RAD_FIELDS_SAM1MOM):
             setattr(self, n, np.zeros(abi.shape_of("rad", dims), order="F"))
         return self
 
     def c_struct(self):
         s = abi.crm_rad_t()
-        for n in abi.RAD_FIELDS_SAM1MOM:
+        for n in self.names():
             setattr(s, n, abi.dptr(getattr(self, n)))
         return s
 
     def copy(self):
         o = crm_rad_type()
-        for n in abi.RAD_FIELDS_SAM1MOM:
+        for n in self.names():
             setattr(o, n, getattr(self, n).copy(order="F"))
         return o
 
@@ -119,13 +127,13 @@ class crm_output_type(_Bag):
 
     def initialize(self, dims):
         """crm_output_initialize(output, ncol, nlev): allocate + zero (CRM/crm_output_module.F90:138-330)."""
-        for n, kind in abi.OUTPUT_FIELDS:
+        for n, kind in abi.OUTPUT_FIELDS + (abi.OUTPUT_FIELDS_M2005 if getattr(dims, "micro", 0) == 1 else []):
             setattr(self, n, np.zeros(abi.shape_of(kind, dims), order="F"))
         return self
 
     def c_struct(self):
         s = abi.crm_output_t()
-        for n, _ in abi.OUTPUT_FIELDS:
+        for n, _ in abi.OUTPUT_FIELDS + abi.OUTPUT_FIELDS_M2005:
             setattr(s, n, abi.dptr(getattr(self, n, None)))
         return s
 

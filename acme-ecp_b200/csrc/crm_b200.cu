@@ -13,6 +13,7 @@
 
 #include "../../include/crm_b200.h"
 #include "crm_k_stats.cuh"
+#include "crm_k_m2005.cuh"
 #include "crm_host_util.h"
 
 using namespace crm;
@@ -84,6 +85,9 @@ struct Handle {
   CrmP p;                 // pointers filled at init; scalars per run
   double *ubuf[4], *wbuf[4], *vbuf[4] = {nullptr, nullptr, nullptr, nullptr};
   bool d3 = false;        // 3-D CRM (ny > 1)
+  bool m25 = false;       // M2005 two-moment microphysics (micro = 1)
+  double *m25_scr = nullptr; int m25_chunk = 0;   // column work space of k_m2005_column for m25_chunk tiles
+  double *esum2 = nullptr;
   double *stage = nullptr;            // one boundary-layout 3-D field (ld_max*nx*ny*nzm)
   double *esum = nullptr;
   double *in_dev = nullptr;           // packed device copy of the crm_input arrays
@@ -213,7 +217,7 @@ extern "C" int crm_b200_free(void *handle) {
 extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   g_init_err.clear();
   *handle = nullptr;
-  if (d->micro != 0) { g_init_err = "crm_b200_init: only sam1mom (micro=0) is implemented on device (M2005: see DESIGN.md, out of round-1 scope)"; return 2; }
+  if (d->micro != 0 && d->micro != 1) { g_init_err = "crm_b200_init: micro must be 0 (sam1mom) or 1 (m2005)"; return 2; }
   const bool d3 = d->ny > 1;
   if (d->ny < 1 || (d3 && !d->yes3d) || (!d3 && d->yes3d)) { g_init_err = "crm_b200_init: RUN3D/YES3D mismatch: ny > 1 needs yes3d = 1, ny = 1 needs yes3d = 0 (setparm.F90:55-62)"; return 3; }
   if (d->nx < 8 || (d->nx & (d->nx - 1))) { g_init_err = "crm_b200_init: nx must be a power of two >= 8"; return 4; }
@@ -226,7 +230,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   if (d->ncrms < 1 || d->ld < d->ncrms) { g_init_err = "crm_b200_init: need 1 <= ncrms <= ld"; return 7; }
   if (dev_init(device)) { g_init_err = std::string("crm_b200_init: cannot select CUDA device: ") + dev_errstr(); return 8; }
   Handle *h = new Handle();
-  h->d0 = *d; h->device = device; h->d3 = d3;
+  h->d0 = *d; h->device = device; h->d3 = d3; h->m25 = d->micro == 1;
 #ifndef CRM_EMU
   {
     bool sok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -292,6 +296,24 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
                      &p.s_cld, &p.s_cldtop, &p.s_gicewp, &p.s_gliqwp, &p.s_mcup, &p.s_mcdn, &p.s_mcuup, &p.s_mcudn, &p.s_mui, &p.s_mdi})
     PRF(*f);
   for (double **f : {&p.dz, &p.z0, &p.colprec0, &p.colprecs0, &p.s_cltot, &p.s_clhgh, &p.s_clmed, &p.s_cllow}) SL(*f);
+  p.micro = d->micro;
+  if (h->m25) {
+    for (int n = 2; n <= 10; n++) F(p.mf[n]);
+    for (int q = 0; q < 8; q++) { F(p.m_rate[q]); F(p.m_ratea[q]); }
+    for (int q = 0; q < 4; q++) { p.m_rad[q] = carve<double>(h, h->rad_elems); ok = ok && p.m_rad[q]; }
+    for (int q = 0; q < 5; q++) PRF(p.m_stend[q]);
+    p.m_mkadv[0] = p.mkadv1; p.m_mkwle[0] = p.mkwle1; p.m_mkdiff[0] = p.mkdiff1; p.m_mkwsb[0] = p.mkwsb1;
+    for (int q = 1; q < 5; q++) { PRF(p.m_mkadv[q]); PRF(p.m_mkwle[q]); PRF(p.m_mkdiff[q]); PRF(p.m_mkwsb[q]); }
+    // column work space: NARR arrays of nzm levels per column; the batch is swept in chunks of tiles that fit ~6 GB
+    const size_t per_tile = (size_t)m2005::NARR * d->nzm * h->P * 8;
+    size_t chunk = (size_t)6e9 / per_tile;
+    if (const char *e = getenv("CRM_B200_M2005_CHUNK")) { int v = atoi(e); if (v >= 1) chunk = v; }
+    if (chunk < 1) chunk = 1;
+    if (chunk > (size_t)h->ntiles) chunk = h->ntiles;
+    h->m25_chunk = (int)chunk;
+    h->m25_scr = carve<double>(h, per_tile / 8 * chunk); ok = ok && h->m25_scr;
+    h->esum2 = carve<double>(h, (size_t)CRM_M25_NESUM * h->prof_elems); ok = ok && h->esum2;
+  }
   p.kmin = carve<int>(h, h->slot_elems); p.kmax = carve<int>(h, h->slot_elems); p.ndamp = carve<int>(h, h->slot_elems);
   p.kprec = carve<int>(h, h->ntiles); p.kqp = carve<int>(h, h->ntiles);
   p.precsfc = carve<double>(h, h->col_elems); p.precssfc = carve<double>(h, h->col_elems);
@@ -301,7 +323,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   h->stage = carve<double>(h, (size_t)d->ld * d->nx * d->ny * d->nzm);
   h->esum = carve<double>(h, (size_t)CRM_NESUM * h->prof_elems);
   h->in_dev = carve<double>(h, (size_t)d->ld * (11 * (size_t)(d->plev + 1) + 8));
-  h->out_dev = carve<double>(h, (size_t)d->ld * (41 * (size_t)d->plev + 16 + (size_t)d->nx * d->ny));
+  h->out_dev = carve<double>(h, (size_t)d->ld * ((41 + 13) * (size_t)d->plev + 16 + (size_t)d->nx * d->ny));
   h->rnd_dev = carve<double>(h, (size_t)d->ncrms * 5 * d->nx * d->ny);
   h->gcol_dev = carve<int>(h, d->ld);
   ok = ok && p.kmin && p.kmax && p.ndamp && p.kprec && p.kqp && p.precsfc && p.precssfc && p.cfl_bits && p.flags && p.twc && p.tws && h->stage && h->esum &&
@@ -329,11 +351,20 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
 #define PRESS_ATTR(NXV) BIG((k_p4_press_fwd<NXV, 0>)); BIG((k_p5_press_bwd<NXV, 0>));
     PRESS_ATTR(8) PRESS_ATTR(16) PRESS_ATTR(32) PRESS_ATTR(64) PRESS_ATTR(128) PRESS_ATTR(256)
     BIG((k_p4_press_fwd<32, 32>)); BIG((k_p5_press_bwd<32, 32>)); BIG((k_p4_press_fwd<64, 64>)); BIG((k_p5_press_bwd<64, 64>));
+    BIG(k_diffuse_set<0>); BIG(k_diffuse_set<32>); BIG(k_diffuse_set<64>); BIG(k_diffuse_set<CRM_G3D>); BIG(k_m2005_column); BIG(k_m2005_epi_sums);
+    if (h->m25) {
+      m2005::Const mc;
+      m2005::graupel_init(mc, CRM_RGAS, CRM_RV, CRM_CP, CRM_LCOND, CRM_LSUB);
+      attr_ok = attr_ok && cudaMemcpyToSymbol(c_m25, &mc, sizeof(mc)) == cudaSuccess;
+    }
 #undef PRESS_ATTR
 #undef BIG_G
 #undef BIG
     if (!attr_ok) { g_init_err = std::string("crm_b200_init: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: ") + dev_errstr(); crm_b200_free(h); return 12; }
   }
+#endif
+#ifdef CRM_EMU
+  if (h->m25) m2005::graupel_init(c_m25, CRM_RGAS, CRM_RV, CRM_CP, CRM_LCOND, CRM_LSUB);
 #endif
   if (dev_sync()) { g_init_err = std::string("crm_b200_init: ") + dev_errstr(); crm_b200_free(h); return 11; }
   *handle = h;
@@ -380,8 +411,11 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   h->ktimes.clear();
   CrmP &p = h->p;
   const int CT = h->CT, P = h->P, nx = d->nx, nzm = d->nzm, nz = nzm + 1, plev = d->plev, ld = d->ld, ncrms = d->ncrms;
-  const bool d3 = h->d3;
+  const bool d3 = h->d3, m25 = h->m25;
   const int nxy = nx * d->ny, nrad = d->nx_rad * d->ny_rad;
+  if (m25 && d->use_crm_accel) return fail(h, 35, "CRM time step relaxation is only compatible with sam1mom microphysics");   // accelerate_crm.F90:65-68
+  if (m25 && !(st->nc && st->qr && st->nr && st->qi && st->ni && st->qs && st->ns && st->qg && st->ng && st->qc))
+    return fail(h, 36, "crm_b200_run: m2005 needs the crm_state members nc, qr, nr, qi, ni, qs, ns, qg, ng, qc");
   const int ntiles = (ncrms + CT - 1) / CT;
   p.ncrms = ncrms; p.ntiles = ntiles; p.ld = ld;
   p.dt = d->dt; p.dt_gl = d->dt_gl; p.igstep = d->igstep;
@@ -402,6 +436,11 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   for (double *f : {p.s_cltot, p.s_clhgh, p.s_clmed, p.s_cllow}) zrc |= dev_zero(f, (size_t)ntiles * CT * 8);
   zrc |= dev_zero(p.precsfc, (size_t)ntiles * P * 8); zrc |= dev_zero(p.precssfc, (size_t)ntiles * P * 8);
   zrc |= dev_zero(p.cfl_bits, 16); zrc |= dev_zero(p.flags, 16);
+  if (m25) {
+    for (int q = 0; q < 8; q++) { zrc |= dev_zero(p.m_rate[q], fbytes); zrc |= dev_zero(p.m_ratea[q], fbytes); }
+    for (int q = 0; q < 4; q++) zrc |= dev_zero(p.m_rad[q], (size_t)ntiles * nzm * nrad * CT * 8);
+    for (int q = 1; q < 5; q++) for (double *f : {p.m_mkadv[q], p.m_mkwle[q], p.m_mkdiff[q], p.m_mkwsb[q]}) zrc |= dev_zero(f, pbytes);
+  }
 
   // ---------------- boundary inputs ----------------
   DevTimer tm;
@@ -451,8 +490,15 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   load3(st->w_wind, h->wbuf[iu], false);
   load3(st->temperature, p.tabs, false);
   load3(st->qt, p.qt, false);
-  load3(st->qp, p.qp, false);
-  load3(st->qn, p.qn, false);
+  if (m25) {   // crm_module.F90:432-445: micro_field(1..10) <- qt, nc, qr, nr, qi, ni, qs, ns, qg, ng; cloudliq <- qc
+    const double *src[11] = {nullptr, nullptr, st->nc, st->qr, st->nr, st->qi, st->ni, st->qs, st->ns, st->qg, st->ng};
+    for (int n = 2; n <= 10; n++) load3(src[n], p.mf[n], false);
+    load3(st->qc, p.qn, false);
+    zrc |= dev_zero(p.qp, fbytes);
+  } else {
+    load3(st->qp, p.qp, false);
+    load3(st->qn, p.qn, false);
+  }
   {
     const size_t ncr = (size_t)nrad * nzm;
     const double *ext = rad->qrad;
@@ -476,8 +522,9 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   set_roles();
   const int slot_blocks = (ntiles * CT + 127) / 128;
   LAUNCH(h, k_prologue_grid, slot_blocks, 128, 0, p, ei);
+  if (m25) LAUNCH(h, k_m2005_prologue, ntiles, P, 0, p);
   LAUNCH(h, k_prologue_fields, ntiles, P, red_bytes(9), p);
-  LAUNCH(h, k_precip_init, (ntiles * nzm * CT + 127) / 128, 128, 0, p);
+  if (!m25) LAUNCH(h, k_precip_init, (ntiles * nzm * CT + 127) / 128, 128, 0, p);   // crm_module.F90:672-674 (#ifdef sam1mom)
   if (d->igstep <= 1) {   // setperturb (crm_module.F90:677-681): RNG draws on the host like the reference
     std::vector<double> rnd((size_t)ncrms * 5 * nxy);
     std::vector<int> gcol(ld);
@@ -592,7 +639,17 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
 #define ON_SIDE(q)
 #define ON_MAIN()
 #endif
-      if (d3) {
+      if (m25) {   // advect_all_scalars.F90:32-49: t, then the ten micro fields; statistics for qt, qr, qi, qs, qg
+        const int slot_of[11] = {-1, 0, -1, 1, -1, 2, -1, 3, -1, 4, -1};
+        for (int n = 0; n <= 10; n++) {
+          double *f = (n == 0) ? p.t : (n == 1) ? p.qt : p.mf[n];
+          const int sl = (n == 0) ? -1 : slot_of[n];
+          double *fa = sl >= 0 ? p.m_mkadv[sl] : nullptr, *fl = sl >= 0 ? p.m_mkwle[sl] : nullptr;
+          if (n % 3 == 1) { ON_SIDE(0); } else if (n % 3 == 2) { ON_SIDE(1); } else { ON_MAIN(); }
+          if (d3) LAUNCH(h, k3_mpdata, ntiles, P, CRM3_MP_SMEM(P, CT, h->nzp), p, f, fa, fl, sl >= 0 ? 1 : 0, (const int *)nullptr);
+          else LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, f, fa, fl, sl >= 0 ? 1 : 0, (const int *)nullptr);
+        }
+      } else if (d3) {
         const size_t smem_mp3 = CRM3_MP_SMEM(P, CT, h->nzp);
         LAUNCH(h, k3_mpdata, ntiles, P, smem_mp3, p, p.t, (double *)nullptr, (double *)nullptr, 0, (const int *)nullptr);
         ON_SIDE(0);
@@ -613,20 +670,40 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
       if (fork) for (int q = 0; q < 2; q++) { cudaEventRecord(h->ev_join[q], h->side[q]); cudaStreamWaitEvent(h->stream, h->ev_join[q], 0); }
 #endif
       if (dbg_stop == 5) { dbg_break = true; break; }
-      dev_zero(p.prec_cfl_bits, 8);
-      LAUNCH_G(h, k_precip_a, ntiles, P, CRM_PRECIPA_SMEM(P, CT, h->nzp), p);
-      // one launch per sedimentation sub-iteration; nprec is only known on the device, launches beyond it return at once
-      for (int ip = 1; ip <= h->precip_launches; ip++)
-        LAUNCH_G(h, k_precip_b, ntiles, P, CRM_PRECIPB_SMEM(P, CT, h->nzp), p, ip, ip == h->precip_launches ? 1 : 0);
+      if (!m25) {   // m2005: micro_precip_fall is a no-op, sedimentation happens inside the column scheme (MICRO_M2005/microphysics.F90:1425-1429)
+        dev_zero(p.prec_cfl_bits, 8);
+        LAUNCH_G(h, k_precip_a, ntiles, P, CRM_PRECIPA_SMEM(P, CT, h->nzp), p);
+        // one launch per sedimentation sub-iteration; nprec is only known on the device, launches beyond it return at once
+        for (int ip = 1; ip <= h->precip_launches; ip++)
+          LAUNCH_G(h, k_precip_b, ntiles, P, CRM_PRECIPB_SMEM(P, CT, h->nzp), p, ip, ip == h->precip_launches ? 1 : 0);
+      }
       // uvw.F90: u <- dudt(nc) is a role rotation of the buffers (with the AB rotation of crm_module.F90:884-887)
       { int o_u = iu, o_a = ina, o_b = inb, o_c = inc; iu = o_c; ina = o_u; inb = o_a; inc = o_b; }
       set_roles();
       if (dbg_stop == 6) { dbg_break = true; break; }
+      if (m25) {   // sgs_scalars (sgs.F90:389-447): t, then every micro field
+        DiffSet sets[4];
+        memset(sets, 0, sizeof(sets));
+        sets[0].nf = 3; sets[0].f[0] = p.t; sets[0].f[1] = p.qt; sets[0].f[2] = p.mf[2]; sets[0].mkdiff[1] = p.m_mkdiff[0]; sets[0].mkwsb[1] = p.m_mkwsb[0];
+        sets[1].nf = 3; sets[1].f[0] = p.mf[3]; sets[1].f[1] = p.mf[4]; sets[1].f[2] = p.mf[5];
+        sets[1].mkdiff[0] = p.m_mkdiff[1]; sets[1].mkwsb[0] = p.m_mkwsb[1]; sets[1].mkdiff[2] = p.m_mkdiff[2]; sets[1].mkwsb[2] = p.m_mkwsb[2];
+        sets[2].nf = 3; sets[2].f[0] = p.mf[6]; sets[2].f[1] = p.mf[7]; sets[2].f[2] = p.mf[8]; sets[2].mkdiff[1] = p.m_mkdiff[3]; sets[2].mkwsb[1] = p.m_mkwsb[3];
+        sets[3].nf = 2; sets[3].f[0] = p.mf[9]; sets[3].f[1] = p.mf[10]; sets[3].mkdiff[0] = p.m_mkdiff[4]; sets[3].mkwsb[0] = p.m_mkwsb[4];
+        for (int q = 0; q < 4; q++) LAUNCH_G(h, k_diffuse_set, ntiles, P, CRM_DIFFSET_SMEM(P, CT, h->nzp), p, sets[q]);
+      } else
       LAUNCH_G(h, k_p7_diffuse, ntiles, P, CRM_P7_SMEM(P, CT, h->nzp), p);
       if (dbg_stop == 7) { dbg_break = true; break; }
-      if (icyc == 1) LAUNCH(h, k_precip_init, (ntiles * nzm * CT + 127) / 128, 128, 0, p);
+      if (icyc == 1 && !m25) LAUNCH(h, k_precip_init, (ntiles * nzm * CT + 127) / 128, 128, 0, p);
       LAUNCH(h, k_reset_kminmax, slot_blocks, 128, 0, p);
       const size_t smem_p8 = CRM_P8_SMEM(P, CT, d3);
+      if (m25) {   // micro_proc (column scheme, chunk by chunk) + diagnose; ice_fall of the next sub-step is a no-op: kmin > kmax
+        for (int t0 = 0; t0 < ntiles; t0 += h->m25_chunk) {
+          const int nt = std::min(h->m25_chunk, ntiles - t0);
+          LAUNCH(h, k_m2005_column, nt, P, red_bytes(5), p, h->m25_scr, t0, nt);
+        }
+        LAUNCH_G(h, k_p8_micro, ntiles * ((nzm + CRM_P8_NL - 1) / CRM_P8_NL), P, smem_p8, p, 0, 1);
+        LAUNCH(h, k_reset_kminmax, slot_blocks, 128, 0, p);
+      } else
       if (d->use_crm_accel && !ceaseflag) {
         LAUNCH_G(h, k_p8_micro, ntiles * ((nzm + CRM_P8_NL - 1) / CRM_P8_NL), P, smem_p8, p, 1, 0);
         LAUNCH(h, k_msa_a, ntiles * nzm, P, red_bytes(4), p);
@@ -648,8 +725,9 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
     if (dbg_break) break;
     p.nstop = nstop;
     LAUNCH_G(h, k_stats, ntiles, P, d3 ? CRM_STATS3_SMEM(P, CT, h->nzp) : CRM_STATS_SMEM(P, CT, h->nzp, !(((nx / d->nx_rad) * CT <= 32) && !((nx / d->nx_rad) & ((nx / d->nx_rad) - 1)))), p);
+    if (m25) LAUNCH(h, k_m2005_rad, ntiles * nzm, nrad * CT, 0, p);
     // nprec statistic (device value of the last sub-step)
-    if ((nstep & 15) == 0 || nstep == nstop) {
+    if (!m25 && ((nstep & 15) == 0 || nstep == nstop)) {
       unsigned long long pb2 = 0; dev_copy2d(&pb2, 8, p.prec_cfl_bits, 8, 8, 1, 1);
       double pc; memcpy(&pc, &pb2, 8);
       long long np_ = pc > R4(0.9) ? (long long)std::ceil(pc / R4(0.9)) : 1;
@@ -660,6 +738,8 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
 
   // ---------------- epilogue ----------------
   ExtOut eo;
+  M25Out mo;
+  memset(&mo, 0, sizeof(mo));
   {
     double *q = h->out_dev;
     auto take = [&](size_t ncols) { double *r = q; q += (size_t)ld * ncols; return r; };
@@ -672,10 +752,19 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
                        &eo.flux_qp, &eo.precflux, &eo.qt_ls, &eo.qt_trans, &eo.qp_trans, &eo.qp_fall, &eo.qp_src, &eo.qp_evp, &eo.t_ls, &eo.ultend, &eo.vltend};
     for (double **c : levs) *c = take(plev);
     eo.prec_crm = take((size_t)nx * d->ny);
+    if (m25) {
+      double **ml[] = {&mo.nc_mean, &mo.ni_mean, &mo.ns_mean, &mo.ng_mean, &mo.nr_mean, &mo.aut_a, &mo.acc_a, &mo.evpc_a, &mo.evpr_a, &mo.mlt_a, &mo.sub_a,
+                       &mo.dep_a, &mo.con_a};
+      for (double **c : ml) *c = take(plev);
+    }
   }
   LAUNCH(h, k_epi_sums, ntiles * nzm, P, red_bytes(CRM_NESUM), p, h->esum);
   LAUNCH(h, k_epi_precip, ntiles, P, red_bytes(4), p, eo, dt);
   LAUNCH(h, k_epi_profiles, (ncrms + 127) / 128, 128, 0, p, ei, eo, (const double *)h->esum, dt, dtn);
+  if (m25) {
+    LAUNCH(h, k_m2005_epi_sums, ntiles * nzm, P, red_bytes(CRM_M25_NESUM), p, h->esum2);
+    LAUNCH(h, k_m2005_epi_profiles, (ncrms + 127) / 128, 128, 0, p, eo, mo, (const double *)h->esum2, dt, dtn);
+  }
   if (dev_sync()) return fail(h, 31, std::string("crm_b200_run: kernel failure: ") + dev_errstr());
   if (!h->launch_err.empty()) return fail(h, 34, "crm_b200_run: a kernel launch failed");
   h->stats.ms_kernels = tk.stop();
@@ -706,6 +795,12 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
                     eo.qp_evp, eo.t_ls, eo.ultend, eo.vltend};
     for (int q = 0; q < 41; q++) give(hl[q], dl[q], plev);
     give(out->prec_crm, eo.prec_crm, (size_t)nx * d->ny);
+    if (m25) {
+      double *hm[] = {out->nc_mean, out->ni_mean, out->ns_mean, out->ng_mean, out->nr_mean, out->aut_a, out->acc_a, out->evpc_a, out->evpr_a, out->mlt_a,
+                      out->sub_a, out->dep_a, out->con_a};
+      double *dm[] = {mo.nc_mean, mo.ni_mean, mo.ns_mean, mo.ng_mean, mo.nr_mean, mo.aut_a, mo.acc_a, mo.evpc_a, mo.evpr_a, mo.mlt_a, mo.sub_a, mo.dep_a, mo.con_a};
+      for (int q = 0; q < 13; q++) give(hm[q], dm[q], plev);
+    }
   }
   auto store3 = [&](double *dst, const double *src, double scale) {
     if (!dst) return;
@@ -722,15 +817,24 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   else store3(st->v_wind, h->ubuf[iu], 0.0);   // 2-D: v == 0 (crm_module.F90:390, YES3D = 0)
   store3(st->w_wind, h->wbuf[iu], 1.0);
   store3(st->temperature, p.tabs, 1.0);
-  store3(st->qt, p.qt, 1.0); store3(st->qp, p.qp, 1.0); store3(st->qn, p.qn, 1.0);
+  store3(st->qt, p.qt, 1.0);
+  if (m25) {
+    double *dst[11] = {nullptr, nullptr, st->nc, st->qr, st->nr, st->qi, st->ni, st->qs, st->ns, st->qg, st->ng};
+    for (int n = 2; n <= 10; n++) store3(dst[n], p.mf[n], 1.0);
+    store3(st->qc, p.qn, 1.0);
+    double *o3[8] = {out->aut, out->acc, out->evpc, out->evpr, out->mlt, out->sub, out->dep, out->con};
+    for (int q = 0; q < 8; q++) store3(o3[q], p.m_rate[q], 1.0);
+    if (out->wvar) { LAUNCH(h, k_m2005_wvar, 148 * 8, 256, 0, p, p.wp); store3(out->wvar, p.wp, 1.0); }
+  } else { store3(st->qp, p.qp, 1.0); store3(st->qn, p.qn, 1.0); }
   store3(out->tk, p.tk, 1.0); store3(out->tkh, p.tkh, 1.0);
   store3(out->qcl, p.qcl, 1.0); store3(out->qci, p.qci, 1.0); store3(out->qpl, p.qpl, 1.0); store3(out->qpi, p.qpi, 1.0);
   {
     const double tmp1 = ((double)d->nx_rad / (double)nx) * ((double)d->ny_rad / (double)d->ny) / (double)nstop;
     const size_t ncr = (size_t)nrad * nzm;
-    double *dsts[] = {rad->temperature, rad->qv, rad->qc, rad->qi, rad->cld};
-    const double *srcs[] = {p.rad_t, p.rad_qv, p.rad_qc, p.rad_qi, p.rad_cld};
-    for (int q = 0; q < 5; q++) {
+    double *dsts[] = {rad->temperature, rad->qv, rad->qc, rad->qi, rad->cld, m25 ? rad->nc : nullptr, m25 ? rad->ni : nullptr, m25 ? rad->qs : nullptr,
+                      m25 ? rad->ns : nullptr};
+    const double *srcs[] = {p.rad_t, p.rad_qv, p.rad_qc, p.rad_qi, p.rad_cld, p.m_rad[0], p.m_rad[1], p.m_rad[2], p.m_rad[3]};
+    for (int q = 0; q < 9; q++) {
       if (!dsts[q]) continue;
       if (is_dev_ptr(dsts[q])) LAUNCH(h, k_epi_rad, ntiles * nzm, nrad * CT, 0, p, srcs[q], dsts[q], ld, tmp1);
       else {

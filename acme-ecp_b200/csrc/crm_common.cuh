@@ -93,6 +93,13 @@ struct CrmP {
   double *ttend, *qtend, *utend;
   double *tl, *ql, *qccl, *qiil, *uln;   // GCM profiles on CRM levels
   double *v0, *vtend, *vln, *vwle, *vwsb, *acc_v;   // 3-D CRMs only
+  // ---- m2005 (micro = 1): micro_field(:,:,:,:,n) = mf[n], n = 2..10 (nc, qr, nr, qi, ni, qs, ns, qg, ng); mf[1] = qt; cloudliq lives in qn ----
+  int micro;
+  double *mf[11];
+  double *m_rate[8], *m_ratea[8];        // aut1..con1 and their time integrals aut1a..con1a (3-D)
+  double *m_rad[4];                      // crm_rad nc, ni, qs, ns accumulators
+  double *m_stend[5];                    // profiles: slab sums of the sedimentation tendencies of qc, qr, qi, qs, qg
+  double *m_mkadv[5], *m_mkwle[5], *m_mkdiff[5], *m_mkwsb[5];   // statistics profiles of qt, qr, qi, qs, qg
   double *accrsc, *accrsi, *accrrc, *coefice, *accrgc, *accrgi, *evaps1, *evaps2, *evapr1, *evapr2, *evapg1, *evapg2;
   double *precflux, *qpfall, *qpsrc, *qpevp, *uwle, *uwsb;
   double *mkwle1, *mkwle2, *mkwsb1, *mkwsb2, *mkadv1, *mkadv2, *mkdiff1, *mkdiff2;

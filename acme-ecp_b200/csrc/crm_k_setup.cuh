@@ -202,7 +202,9 @@ __global__ void __launch_bounds__(CRM_MAX_P3) k_prologue_fields(CrmP p) {
     }
     double tabs = F3(p.tabs, k), qt = F3(p.qt, k), qn = F3(p.qn, k), qp = F3(p.qp, k);
     double qv, qcl, qci, qpl, qpi;
-    micro_diag_cell(p.ms, qt, qn, qp, tabs, qv, qcl, qci, qpl, qpi);
+    if (p.micro) {   // micro_diagnose of MICRO_M2005/microphysics.F90:1305-1345 (qn holds cloudliq)
+      qv = qt - qn; qcl = qn; qpl = F3(p.mf[3], k); qci = F3(p.mf[5], k); qpi = F3(p.mf[7], k) + F3(p.mf[9], k);
+    } else micro_diag_cell(p.ms, qt, qn, qp, tabs, qv, qcl, qci, qpl, qpi);
     F3(p.qv, k) = qv; F3(p.qcl, k) = qcl; F3(p.qci, k) = qci; F3(p.qpl, k) = qpl; F3(p.qpi, k) = qpi;
     double t = tabs + PF(p.gamaz, k) - CRM_FAC_COND * qcl - CRM_FAC_SUB * qci - CRM_FAC_COND * qpl - CRM_FAC_SUB * qpi;
     F3(p.t, k) = t;
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(CRM_MAX_P3) k_prologue_fields(CrmP p) {
   double v[2] = {colprec, colprecs};
   block_sum_lead<2>(v, tid, P, CT, red);
   if (i == 0) { p.colprec0[cb] = v[0]; p.colprecs0[cb] = v[1]; }
-  if (kmax > 0) { atomicMin(&p.kmin[cb], kmin); atomicMax(&p.kmax[cb], kmax); }
+  if (kmax > 0 && !p.micro) { atomicMin(&p.kmin[cb], kmin); atomicMax(&p.kmax[cb], kmax); }   // m2005: ice_fall is a no-op (ice_fall.F90:50-57)
 }
 
 // precip_init.F90:46-93; one thread per (tile, k, lane) profile slot.

@@ -105,8 +105,13 @@ def make_inputs(dims, seed=20260101, lat_range=(-1.0, 1.0), rows=None, nglobal=N
         st.u_wind[:, :, :, k] = ul[:, m][:, None, None]
         st.v_wind[:, :, :, k] = vl[:, m][:, None, None]
         st.temperature[:, :, :, k] = T[:, m][:, None, None]
-        st.qt[:, :, :, k] = (ql[:, m] + qccl[:, m] + qiil[:, m])[:, None, None]
-        st.qn[:, :, :, k] = (qccl[:, m] + qiil[:, m])[:, None, None]
+        if getattr(dims, "micro", 0) == 1:   # m2005 seeding (crm_physics.F90:926-938): qt = qv + cloud liquid, qi = cloud ice, qc = cloud liquid
+            st.qt[:, :, :, k] = (ql[:, m] + qccl[:, m])[:, None, None]
+            st.qi[:, :, :, k] = qiil[:, m][:, None, None]
+            st.qc[:, :, :, k] = qccl[:, m][:, None, None]
+        else:
+            st.qt[:, :, :, k] = (ql[:, m] + qccl[:, m] + qiil[:, m])[:, None, None]
+            st.qn[:, :, :, k] = (qccl[:, m] + qiil[:, m])[:, None, None]
         rad.qrad[:, :, :, k] = np.where(pmid[:, m] > 2.0e4, -1.5 / 86400.0, 0.0)[:, None, None]
         rad.temperature[:, :, :, k] = T[:, m][:, None, None]
         rad.qv[:, :, :, k] = ql[:, m][:, None, None]

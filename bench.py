@@ -33,7 +33,7 @@ CONFIG_CLASS = {"cfg1": "2d_sam1mom", "cfg2": "2d_sam1mom", "cfg3": "2d_m2005", 
 KERNEL_WORDS = {
     "2d": {"k_p1_forcing": 14, "k_p2_sgs": 14, "k_p3_mom": 7, "k_p4_press_fwd": 9, "k_p5_press_bwd": 15,
            "k_mpdata": 4, "k_mpdata3": 8, "k_precip_a": 3, "k_precip_b": 7, "k_p7_diffuse": 7, "k_p8_micro": 13, "k_stats": 7,
-           "k_kurant": 3},
+           "k_kurant": 3, "k_m2005_column": 54, "k_diffuse_set": 7},
     "3d": {"k_p1_forcing": 16, "k3_p2_sgs": 14, "k3_p3_adv": 9, "k3_p3_dif": 10, "k3_p4_press_fwd": 13, "k3_p5_press_bwd": 23,
            "k3_mpdata": 5, "k_precip_a": 3, "k_precip_b": 7, "k_p7_diffuse": 7, "k_p8_micro": 14, "k_stats": 7, "k_kurant": 4},
 }
@@ -168,7 +168,7 @@ def workload_name(args, dims):
         args.config, dims.ncrms, dims.nx, dims.ny, dims.nzm, "m2005" if dims.micro else "sam1mom", dims.dt, dims.dt_gl, int(dims.dt_gl / dims.dt))
 
 
-def run_e2e(args, pkg, abi, h, dims, inp, ci, st, rad, dstate, big, world, barrier, torch, dist, state_shape):
+def run_e2e(args, pkg, abi, h, dims, inp, ci, st, rad, dstate, big, world, barrier, torch, dist, state_shape, st_names):
     """End-to-end arm: HOST (pinned) buffers through the same C-ABI call (H2D of crm_state/crm_rad, D2H of the state
     and of every output inside the timed region)."""
     def pinned_like(a):
@@ -182,7 +182,7 @@ def run_e2e(args, pkg, abi, h, dims, inp, ci, st, rad, dstate, big, world, barri
     # smaller ncrms; the throughput of a batch of many thousand CRMs does not depend on its size) and says so.
     lworld = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     cell3 = dims.nx * dims.ny * dims.nzm * 8.0
-    per_crm = cell3 * (len(abi.STATE_FIELDS_SAM1MOM) + len(big) + 6.0 * dims.nx_rad * dims.ny_rad / (dims.nx * dims.ny)) + 45.0 * dims.plev * 8.0
+    per_crm = cell3 * (len(st_names) + len(big) + 6.0 * dims.nx_rad * dims.ny_rad / (dims.nx * dims.ny)) + 45.0 * dims.plev * 8.0
     try:
         avail = float([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024.0
     except Exception:
@@ -196,12 +196,13 @@ def run_e2e(args, pkg, abi, h, dims, inp, ci, st, rad, dstate, big, world, barri
     n_e2e = min(n_e2e, dims.ncrms)
     d_e = dims.copy(ncrms=n_e2e, ld=n_e2e) if n_e2e < dims.ncrms else dims
     hst = pkg.crm_state_type(); hrad = pkg.crm_rad_type(); hout = pkg.crm_output_type().initialize(d_e)
-    for n in abi.STATE_FIELDS_SAM1MOM:
+    hst.initialize(dims.copy(ncrms=1, ld=1)); hrad.initialize(dims.copy(ncrms=1, ld=1))   # creates the member set of this microphysics
+    for n in st_names:
         full = dstate[n].view(-1)
         src = full.view(dims.nx * dims.ny * dims.nzm, dims.ld)[:, :n_e2e].contiguous().cpu().numpy().reshape(-1)   # (ld fastest) -> leading CRMs
         tns, v = pinned_like(src.reshape((n_e2e,) + tuple(state_shape[1:]), order="F")); keep.append(tns); setattr(hst, n, v)
         del src
-    for n in abi.RAD_FIELDS_SAM1MOM:
+    for n in rad.names():
         tns, v = pinned_like(np.asfortranarray(getattr(rad, n)[:n_e2e])); keep.append(tns); setattr(hrad, n, v)
     for n in big:
         tns, v = pinned_like(getattr(hout, n)); keep.append(tns); setattr(hout, n, v)
@@ -258,17 +259,18 @@ def run_ours(args):
         dims = dims.copy(dt_gl=dims.dt * args.nstop)
     h = libmod.CrmHandle(dims, device=lrank)
     out = pkg.crm_output_type().initialize(dims)
-    big = ("qcl", "qci", "qpl", "qpi", "tk", "tkh")
+    big = ("qcl", "qci", "qpl", "qpi", "tk", "tkh") + (("wvar", "aut", "acc", "evpc", "evpr", "mlt", "sub", "dep", "con") if dims.micro == 1 else ())
+    st_names = st.names()
 
     # ---- device-resident arm: crm_state, crm_rad and the 3-D outputs live in HBM
     def to_dev(a):
         return torch.from_numpy(np.ascontiguousarray(a.ravel(order="F"))).cuda()
     dstate = {}
-    state_shape = getattr(st, abi.STATE_FIELDS_SAM1MOM[0]).shape
-    for n in abi.STATE_FIELDS_SAM1MOM:     # upload field by field and drop the host copy (8 ranks share one host's RAM)
+    state_shape = getattr(st, st_names[0]).shape
+    for n in st_names:     # upload field by field and drop the host copy (8 ranks share one host's RAM)
         dstate[n] = to_dev(getattr(st, n))
         setattr(st, n, None)
-    drad = {n: to_dev(getattr(rad, n)) for n in abi.RAD_FIELDS_SAM1MOM}
+    drad = {n: to_dev(getattr(rad, n)) for n in rad.names()}
     dout = {n: torch.zeros(dstate["qt"].numel(), dtype=torch.float64, device="cuda") for n in big}
     cs = abi.crm_state_t(); cr = abi.crm_rad_t(); co = out.c_struct(); ci = inp.c_struct()
     for n, tns in dstate.items():
@@ -343,7 +345,7 @@ def run_ours(args):
 
     e2e = None
     if args.e2e_steps > 0:
-        e2e = run_e2e(args, pkg, abi, h, dims, inp, ci, st, rad, dstate, big, world, barrier, torch, dist, state_shape)
+        e2e = run_e2e(args, pkg, abi, h, dims, inp, ci, st, rad, dstate, big, world, barrier, torch, dist, state_shape, st_names)
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on a bounded sample
     cpu = None

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CRM_B200_ABI_VERSION 2
+#define CRM_B200_ABI_VERSION 3
 
 /* Compile-time constants of the reference (PHYS/crmdims.F90:13-22, CRM/domain.F90:9-13) and the
  * hidden module inputs of crm() (time_manager:get_nstep, accelerate_crm_mod namelist). */
@@ -110,6 +110,12 @@ typedef struct crm_output_t {
   /* (ld,plev), reference build option SPMOMTRANS (crm_output_module.F90:76-79, crm_module.F90:1200-1211): resolved
    * convective momentum transport tendencies (uln - ul)/dt_gl, two top CRM levels zeroed; NULL = not wanted (ABI >= 2) */
   double *ultend, *vltend;
+  /* ---- m2005 members (crm_output_module.F90:22-31, 60-74; ABI >= 3); ignored for micro = 0, NULL = not wanted ---- */
+  /* (ld,nx,ny,nzm): sub-grid vertical velocity sqrt(tke/3) and the process rates of the last sub-step (crm_module.F90:1288-1298) */
+  double *wvar, *aut, *acc, *evpc, *evpr, *mlt, *sub, *dep, *con;
+  /* (ld,plev): mean number mixing ratios (crm_module.F90:1341-1350, 1379-1384) and time/domain mean process rates (:1386-1414) */
+  double *nc_mean, *ni_mean, *ns_mean, *ng_mean, *nr_mean;
+  double *aut_a, *acc_a, *evpc_a, *evpr_a, *mlt_a, *sub_a, *dep_a, *con_a;
 } crm_output_t;
 
 /* Run statistics (new: replaces the GPTL timers 'crm_gpu_region' etc.) */

@@ -53,7 +53,14 @@ void alloc_crm(const Geo &g, Crm &c) {
     p->alloc(1, nz);
   for (P1 *p : {&c.precflux, &c.uwle, &c.uwsb, &c.vwle, &c.vwsb, &c.tlat, &c.tlatqi, &c.qifall, &c.qpfall, &c.twsb, &c.tdiff, &c.qpsrc, &c.qpevp})
     p->alloc(1, nz);
-  for (int n = 1; n <= 2; n++) { c.mkwle[n].alloc(1, nz); c.mkwsb[n].alloc(1, nz); c.mkadv[n].alloc(1, nz); c.mkdiff[n].alloc(1, nz); }
+  for (int n = 1; n <= (g.m2005 ? 10 : 2); n++) { c.mkwle[n].alloc(1, nz); c.mkwsb[n].alloc(1, nz); c.mkadv[n].alloc(1, nz); c.mkdiff[n].alloc(1, nz); }
+  if (g.m2005) {
+    for (int n = 2; n <= 10; n++) c.mf[n].alloc(-2, nx + 3, 1 - 3 * Y, ny + 3 * Y, nzm);
+    for (F3 *f : {&c.wvar, &c.aut1, &c.acc1, &c.evpc1, &c.evpr1, &c.mlt1, &c.sub1, &c.dep1, &c.con1, &c.aut1a, &c.acc1a, &c.evpc1a, &c.evpr1a, &c.mlt1a,
+                  &c.sub1a, &c.dep1a, &c.con1a})
+      f->alloc(1, nx, 1, ny, nzm);
+    for (F3 *f : {&c.rad_nc, &c.rad_ni, &c.rad_qs, &c.rad_ns}) f->alloc(1, g.nx_rad, 1, g.ny_rad, nzm);
+  }
   for (P1 *p : {&c.accrsc, &c.accrsi, &c.accrrc, &c.coefice, &c.accrgc, &c.accrgi, &c.evaps1, &c.evaps2, &c.evapr1, &c.evapr2, &c.evapg1, &c.evapg2})
     p->alloc(1, nzm);
   for (P1 *p : {&c.tln, &c.qln, &c.qccln, &c.qiiln, &c.uln, &c.vln, &c.dd_crm}) p->alloc(1, plev);
@@ -70,8 +77,12 @@ extern "C" const char *crm_oracle_last_error(void) { return g_err.c_str(); }
 extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_state_t *st, crm_rad_t *rad, crm_output_t *out,
                               crm_run_stats_t *stats) {
   g_err.clear();
-  if (d->micro != 0) { g_err = "oracle: only sam1mom (micro=0) is restated"; return 2; }
+  if (d->micro != 0 && d->micro != 1) { g_err = "oracle: micro must be 0 (sam1mom) or 1 (m2005)"; return 2; }
+  const bool m25 = d->micro == 1;
+  if (m25 && d->use_crm_accel) { g_err = "CRM time step relaxation is only compatible with sam1mom microphysics"; return 2; }   // accelerate_crm.F90:65-68
+  if (m25 && !(st->nc && st->qr && st->nr && st->qi && st->ni && st->qs && st->ns && st->qg && st->ng && st->qc)) { g_err = "oracle: m2005 needs the crm_state members nc, qr, nr, qi, ni, qs, ns, qg, ng, qc"; return 2; }
   Geo g;
+  g.m2005 = m25;
   g.nx = d->nx; g.ny = d->ny; g.nzm = d->nzm; g.nz = d->nzm + 1; g.plev = d->plev; g.YES3D = d->yes3d;
   g.nx_rad = d->nx_rad; g.ny_rad = d->ny_rad; g.dx = d->dx; g.dy = d->dx; g.RUN3D = d->ny > 1;
   if ((g.RUN3D && !g.YES3D) || (!g.RUN3D && g.YES3D)) { g_err = "setparm: RUN3D/YES3D mismatch (setparm.F90:55-62)"; return 3; }
@@ -139,8 +150,15 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
           c.w(i, j, k) = st->w_wind[o];
           c.tabs(i, j, k) = st->temperature[o];
           c.qt(i, j, k) = st->qt[o];
-          c.qp(i, j, k) = st->qp[o];
-          c.qn(i, j, k) = st->qn[o];
+          if (m25) {   // crm_module.F90:432-445, 454-475
+            double *const src[11] = {nullptr, nullptr, st->nc, st->qr, st->nr, st->qi, st->ni, st->qs, st->ns, st->qg, st->ng};
+            for (int n = 2; n <= 10; n++) c.mf[n](i, j, k) = src[n][o];
+            c.qn(i, j, k) = st->qc[o];   // cloudliq
+            if (c.qn(i, j, k) > 0 && c.mf[2](i, j, k) == 0) c.mf[2](i, j, k) = R4(1.0e6) * R4(100.) / c.rho(k);   // 1.0e6*Nc0/rho
+          } else {
+            c.qp(i, j, k) = st->qp[o];
+            c.qn(i, j, k) = st->qn[o];
+          }
         }
     qrad[ic].alloc(1, g.nx_rad, 1, g.ny_rad, nzm);
     for (int k = 1; k <= nzm; k++)
@@ -167,7 +185,7 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
 #pragma omp parallel for schedule(static)
   for (int ic = 0; ic < ncrms; ic++) {
     Crm &c = crms[ic];
-    micro_diagnose(g, c, mc);   // micro_init -> micro_diagnose (microphysics.F90:155-226)
+    if (m25) micro_diagnose_m2005(g, c); else micro_diagnose(g, c, mc);   // micro_init -> micro_diagnose (microphysics.F90:155-226 / MICRO_M2005:476-597)
     // sgs_init (sgs.F90:174-226): tke, tk, tkh = 0 (alloc), grdf
     for (int k = 1; k <= nzm; k++) {
       double a2 = (c.adz(k) * c.dz) * (c.adz(k) * c.dz);
@@ -215,7 +233,7 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
     c.z0 = dmax(R4(0.00001), dmin(R4(1.), c.z0));
     c.o_timing = 0.;
     c.prectend0 = c.colprec; c.precstend0 = c.colprecs;
-    precip_init(g, c, mc);   // crm_module.F90:673
+    if (!m25) precip_init(g, c, mc);   // crm_module.F90:672-674 (#ifdef sam1mom)
     if (d->igstep <= 1) setperturb(g, c, in->gcol[ic] * 1000);   // :677-681, perturb_seed_scale = 1000
   }
 
@@ -262,7 +280,7 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
         forcing(g, c, s);
         rad_heating(g, c, s, qrad[ic]);
         fail += damping(g, c, s);
-        ice_fall(g, c, s);
+        if (!m25) ice_fall(g, c, s);   // m2005: index_cloud_ice = -1 -> early return (ice_fall.F90:50-57)
         if (dbg_stop == 1) continue;
         boundaries(g, c, 3);
         boundaries(g, c, 0);
@@ -280,9 +298,10 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
         // advect_all_scalars.F90:32-49
         advect_scalar(g, c, c.t, c.tdiff /*dummy*/, c.twsb /*dummy*/);
         advect_scalar(g, c, c.qt, c.mkadv[1], c.mkwle[1]);
-        advect_scalar(g, c, c.qp, c.mkadv[2], c.mkwle[2]);
+        if (m25) { for (int n = 2; n <= 10; n++) advect_scalar(g, c, c.mf[n], c.mkadv[n], c.mkwle[n]); }
+        else advect_scalar(g, c, c.qp, c.mkadv[2], c.mkwle[2]);
         if (dbg_stop == 5) continue;
-        prec_cfl = dmax(prec_cfl, precip_fall_part1(g, c, s, mc));
+        if (!m25) prec_cfl = dmax(prec_cfl, precip_fall_part1(g, c, s, mc));   // m2005: micro_precip_fall is a no-op (microphysics.F90:1425-1429)
       }
       if (dbg_stop >= 1 && dbg_stop <= 5) { dbg_break = true; break; }
       if (fail) { g_err = "Error: in damping() tau_min is too small!"; return 9; }
@@ -292,20 +311,25 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
 #pragma omp parallel for schedule(static) reduction(|| : cease_now)
       for (int ic = 0; ic < ncrms; ic++) {
         Crm &c = crms[ic];
-        precip_fall_part2(g, c, s, mc, prec_cfl);
+        if (!m25) precip_fall_part2(g, c, s, mc, prec_cfl);
         uvw(g, c, s);
         if (dbg_stop == 6) continue;
         boundaries(g, c, 3);
         // sgs_scalars (sgs.F90:389-447): t, then micro_flux (fluxbq=fluxtq=0), then qt, qp
         diffuse_scalar(g, c, s, c.t, c.fluxbt, c.fluxtt, c.tdiff, c.twsb);
         diffuse_scalar(g, c, s, c.qt, c.fluxbq, c.fluxtq, c.mkdiff[1], c.mkwsb[1]);
-        diffuse_scalar(g, c, s, c.qp, c.fluxbq /*=0*/, c.fluxtq /*=0*/, c.mkdiff[2], c.mkwsb[2]);
+        if (m25) { for (int n = 2; n <= 10; n++) diffuse_scalar(g, c, s, c.mf[n], c.fluxbq /*=0*/, c.fluxtq /*=0*/, c.mkdiff[n], c.mkwsb[n]); }
+        else diffuse_scalar(g, c, s, c.qp, c.fluxbq /*=0*/, c.fluxtq /*=0*/, c.mkdiff[2], c.mkwsb[2]);
         if (dbg_stop == 7) continue;
-        // micro_proc (microphysics.F90:292-329)
-        if (s.icycle == 1) precip_init(g, c, mc);
-        cloud(g, c);
-        precip_proc(g, c, s, mc);
-        micro_diagnose(g, c, mc);
+        if (m25) {
+          micro_proc_m2005(g, c, s);
+        } else {
+          // micro_proc (microphysics.F90:292-329)
+          if (s.icycle == 1) precip_init(g, c, mc);
+          cloud(g, c);
+          precip_proc(g, c, s, mc);
+          micro_diagnose(g, c, mc);
+        }
         if (use_accel && !ceaseflag) cease_now = cease_now || accelerate_part1(g, c, accel_uv);
       }
       if (dbg_stop == 6 || dbg_stop == 7) { dbg_break = true; break; }
@@ -376,6 +400,10 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
             c.rad_qc(i_rad, j_rad, k) += c.qcl(i, j, k);
             c.rad_qi(i_rad, j_rad, k) += c.qci(i, j, k);
             if (c.qcl(i, j, k) + c.qci(i, j, k) > 0) c.rad_cld(i_rad, j_rad, k) += c.cf3d(i, j, k);
+            if (m25) {   // crm_module.F90:1002-1011
+              c.rad_nc(i_rad, j_rad, k) += c.mf[2](i, j, k); c.rad_ni(i_rad, j_rad, k) += c.mf[6](i, j, k);
+              c.rad_qs(i_rad, j_rad, k) += c.mf[7](i, j, k); c.rad_ns(i_rad, j_rad, k) += c.mf[8](i, j, k);
+            }
           }
       for (int j = 1; j <= ny; j++)
         for (int i = 1; i <= nx; i++)
@@ -413,6 +441,12 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
           if (rad->qc) rad->qc[o] = c.rad_qc(i, j, k) * tmp1r;
           if (rad->qi) rad->qi[o] = c.rad_qi(i, j, k) * tmp1r;
           if (rad->cld) rad->cld[o] = c.rad_cld(i, j, k) * tmp1r;
+          if (m25) {
+            if (rad->nc) rad->nc[o] = c.rad_nc(i, j, k) * tmp1r;
+            if (rad->ni) rad->ni[o] = c.rad_ni(i, j, k) * tmp1r;
+            if (rad->qs) rad->qs[o] = c.rad_qs(i, j, k) * tmp1r;
+            if (rad->ns) rad->ns[o] = c.rad_ns(i, j, k) * tmp1r;
+          }
         }
     for (int k = 1; k <= ptop - 1; k++) {
       c.tln(k) = P2(in->tl, ic, k); c.qln(k) = P2(in->ql, ic, k); c.qccln(k) = P2(in->qccl, ic, k);
@@ -466,7 +500,15 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
           size_t o = e3.at(ic, i - 1, j - 1, k - 1);
           st->u_wind[o] = c.u(i, j, k); st->v_wind[o] = c.v(i, j, k); st->w_wind[o] = c.w(i, j, k);
           st->temperature[o] = c.tabs(i, j, k);
-          st->qt[o] = c.qt(i, j, k); st->qp[o] = c.qp(i, j, k); st->qn[o] = c.qn(i, j, k);
+          st->qt[o] = c.qt(i, j, k);
+          if (m25) {
+            double *const dst[11] = {nullptr, nullptr, st->nc, st->qr, st->nr, st->qi, st->ni, st->qs, st->ns, st->qg, st->ng};
+            for (int n = 2; n <= 10; n++) dst[n][o] = c.mf[n](i, j, k);
+            st->qc[o] = c.qn(i, j, k);
+            double *const o3[9] = {out->wvar, out->aut, out->acc, out->evpc, out->evpr, out->mlt, out->sub, out->dep, out->con};
+            const F3 *const s3[9] = {&c.wvar, &c.aut1, &c.acc1, &c.evpc1, &c.evpr1, &c.mlt1, &c.sub1, &c.dep1, &c.con1};
+            for (int n = 0; n < 9; n++) if (o3[n]) o3[n][o] = (*s3[n])(i, j, k);
+          } else { st->qp[o] = c.qp(i, j, k); st->qn[o] = c.qn(i, j, k); }
           if (out->tk) out->tk[o] = c.tk(i, j, k);
           if (out->tkh) out->tkh[o] = c.tkh(i, j, k);
           if (out->qcl) out->qcl[o] = c.qcl(i, j, k);
@@ -479,15 +521,40 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
     if (out->tauy) out->tauy[ic] = c.tauy0 / (double)nstop;
     // ---- diagnostics (:1314-1377)
     std::vector<double> qc_mean(plev + 1, 0.), qi_mean(plev + 1, 0.), qr_mean(plev + 1, 0.), qg_mean(plev + 1, 0.), qs_mean(plev + 1, 0.);
+    std::vector<double> nm[5];
+    for (auto &v : nm) v.assign(plev + 1, 0.);
     for (int k = 1; k <= nzm; k++)
       for (int j = 1; j <= ny; j++)
         for (int i = 1; i <= nx; i++) {
           int l = plev - k + 1;
           qc_mean[l] += c.qcl(i, j, k); qi_mean[l] += c.qci(i, j, k); qr_mean[l] += c.qpl(i, j, k);
-          double omg = dmax(0., dmin(1., (c.tabs(i, j, k) - tgrmin) * mc.a_gr));
-          qg_mean[l] += c.qpi(i, j, k) * omg;
-          qs_mean[l] += c.qpi(i, j, k) * (1. - omg);
+          if (m25) {   // crm_module.F90:1338-1350
+            qg_mean[l] += c.mf[9](i, j, k); qs_mean[l] += c.mf[7](i, j, k);
+            nm[0][l] += c.mf[2](i, j, k); nm[1][l] += c.mf[6](i, j, k); nm[4][l] += c.mf[4](i, j, k); nm[3][l] += c.mf[10](i, j, k); nm[2][l] += c.mf[8](i, j, k);
+          } else {
+            double omg = dmax(0., dmin(1., (c.tabs(i, j, k) - tgrmin) * mc.a_gr));
+            qg_mean[l] += c.qpi(i, j, k) * omg;
+            qs_mean[l] += c.qpi(i, j, k) * (1. - omg);
+          }
         }
+    if (m25) {   // crm_module.F90:1379-1414; nm: nc, ni, ns, ng, nr
+      double *const onm[5] = {out->nc_mean, out->ni_mean, out->ns_mean, out->ng_mean, out->nr_mean};
+      for (int q = 0; q < 5; q++) for (int k = 1; k <= plev; k++) if (onm[q]) OUT2(onm[q], ic, k) = nm[q][k] * factor_xy;
+      double *const oa[8] = {out->aut_a, out->acc_a, out->evpc_a, out->evpr_a, out->mlt_a, out->sub_a, out->dep_a, out->con_a};
+      const F3 *const sa[8] = {&c.aut1a, &c.acc1a, &c.evpc1a, &c.evpr1a, &c.mlt1a, &c.sub1a, &c.dep1a, &c.con1a};
+      for (int q = 0; q < 8; q++) {
+        if (!oa[q]) continue;
+        for (int k = 1; k <= plev; k++) OUT2(oa[q], ic, k) = 0.;
+        for (int k = 1; k <= nzm; k++) {
+          int l = plev - k + 1;
+          double acc = 0.;
+          for (int j = 1; j <= ny; j++)
+            for (int i = 1; i <= nx; i++) acc += (*sa[q])(i, j, k);
+          OUT2(oa[q], ic, l) = acc;
+        }
+        for (int k = 1; k <= plev; k++) OUT2(oa[q], ic, k) = OUT2(oa[q], ic, k) * factor_xyt / s.dt;
+      }
+    }
     for (int k = 1; k <= plev; k++) {
       double pdel = P2(in->pdel, ic, k);
       double cld = dmin(1., c.o_cld(k) * factor_xyt), cldtop = dmin(1., c.o_cldtop(k) * factor_xyt);
@@ -563,7 +630,7 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
         }
       double tmp1 = c.dz / c.rhow(k);
       double tmp2 = tmp1 / s.dtn;   // last dtn
-      for (int n = 1; n <= 2; n++) {
+      for (int n = 1; n <= (m25 ? 10 : 2); n++) {
         c.mkwsb[n](k) = c.mkwsb[n](k) * tmp1 * c.rhow(k) * factor_xy / nstop;
         c.mkwle[n](k) = c.mkwle[n](k) * tmp2 * c.rhow(k) * factor_xy / nstop;
         c.mkadv[n](k) = c.mkadv[n](k) * factor_xy * icrm_run_time;
@@ -576,11 +643,19 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
       int l = plev - k + 1;
       if (out->flux_u) OUT2(out->flux_u, ic, l) = (c.uwle(k) + c.uwsb(k)) * tmp1 * factor_xy / nstop;
       if (out->flux_v) OUT2(out->flux_v, ic, l) = (c.vwle(k) + c.vwsb(k)) * tmp1 * factor_xy / nstop;
+      if (m25) {   // crm_module.F90:1559-1569 (iqci = 5, iqr = 3, iqs = 7, iqg = 9)
+        if (out->flux_qt) OUT2(out->flux_qt, ic, l) = c.mkwle[1](k) + c.mkwsb[1](k) + c.mkwle[5](k) + c.mkwsb[5](k);
+        if (out->fluxsgs_qt) OUT2(out->fluxsgs_qt, ic, l) = c.mkwsb[1](k) + c.mkwsb[5](k);
+        if (out->flux_qp) OUT2(out->flux_qp, ic, l) = c.mkwle[3](k) + c.mkwsb[3](k) + c.mkwle[7](k) + c.mkwsb[7](k) + c.mkwle[9](k) + c.mkwsb[9](k);
+        if (out->qt_trans) OUT2(out->qt_trans, ic, l) = c.mkadv[1](k) + c.mkadv[5](k) + c.mkdiff[1](k) + c.mkdiff[5](k);
+        if (out->qp_trans) OUT2(out->qp_trans, ic, l) = c.mkadv[3](k) + c.mkadv[7](k) + c.mkadv[9](k) + c.mkdiff[3](k) + c.mkdiff[7](k) + c.mkdiff[9](k);
+      } else {
       if (out->flux_qt) OUT2(out->flux_qt, ic, l) = c.mkwle[1](k) + c.mkwsb[1](k);
       if (out->fluxsgs_qt) OUT2(out->fluxsgs_qt, ic, l) = c.mkwsb[1](k);
       if (out->flux_qp) OUT2(out->flux_qp, ic, l) = c.mkwle[2](k) + c.mkwsb[2](k);
       if (out->qt_trans) OUT2(out->qt_trans, ic, l) = c.mkadv[1](k) + c.mkdiff[1](k);
       if (out->qp_trans) OUT2(out->qp_trans, ic, l) = c.mkadv[2](k) + c.mkdiff[2](k);
+      }
       double tmp = 0;
       for (int j = 1; j <= ny; j++)
         for (int i = 1; i <= nx; i++) tmp += c.tke(i, j, k);

@@ -41,4 +41,7 @@ bool accelerate_part1(const Geo &g, Crm &c, bool accel_uv);   // returns local c
 void accelerate_part2(const Geo &g, Crm &c, bool accel_uv, double accel_factor);
 void setperturb(const Geo &g, Crm &c, int iseed);
 double z0_est(double z, double bflx, double wnd, double ustar);
+// crm_m2005.cpp
+void micro_diagnose_m2005(const Geo &g, Crm &c);
+void micro_proc_m2005(const Geo &g, Crm &c, const Step &s);
 }  // namespace orc

@@ -12,6 +12,7 @@ struct Geo {   // PHYS/crmdims.F90, CRM/domain.F90, CRM/grid.F90:14-46
   int nx_rad, ny_rad;
   double dx, dy;
   bool RUN3D;
+  bool m2005 = false;   // micro = 1
 };
 
 // Scalars shared by the whole batch (grid.F90:52-60, 101, 181)
@@ -31,6 +32,11 @@ struct Crm {
   F3 cf3d;
   // microphysics.F90:27-50 (sam1mom): micro_field(:,:,:,:,1)=qt, (..,2)=qp
   F3 qt, qp, qn;
+  // MICRO_M2005/microphysics.F90:57-121 (micro = 1): micro_field(:,:,:,:,n) = mf[n], n = 2..10 (nc, qr, nr, qi, ni, qs, ns, qg, ng);
+  // micro_field(..,1) = qt (total water vapour + cloud liquid); cloudliq lives in qn; qp is unused
+  F3 mf[11];
+  F3 wvar, aut1, acc1, evpc1, evpr1, mlt1, sub1, dep1, con1, aut1a, acc1a, evpc1a, evpr1a, mlt1a, sub1a, dep1a, con1a;
+  F3 rad_nc, rad_ni, rad_qs, rad_ns;
   // sgs.F90:40-54
   F3 tke, tk, tkh;
   P1 grdf_x, grdf_y, grdf_z;
@@ -40,7 +46,7 @@ struct Crm {
   P1 t0, q0, qv0, tabs0, u0, v0, tg0, qg0, ug0, vg0, tke0, t01, q01, qp0, qn0;
   P1 qtend, ttend, utend, vtend;
   P1 precflux, uwle, uwsb, vwle, vwsb, tlat, tlatqi, qifall, qpfall, twsb, tdiff;
-  P1 mkwle[3], mkwsb[3], mkadv[3], mkdiff[3];   // index 1,2 (micro fields)
+  P1 mkwle[11], mkwsb[11], mkadv[11], mkdiff[11];   // index = micro field (1,2 sam1mom; 1..10 m2005)
   P1 qpsrc, qpevp;
   // micro_params.F90:82-93
   P1 accrsc, accrsi, accrrc, coefice, accrgc, accrgi, evaps1, evaps2, evapr1, evapr2, evapg1, evapg2;

@@ -51,9 +51,11 @@ def compare_all(dims, res_o, res_g, tol, abs_floor=1e-18, skip=()):
     st_o, rad_o, out_o, _ = res_o
     st_g, rad_g, out_g, _ = res_g
     bad = []
-    items = [("state." + n, getattr(st_o, n), getattr(st_g, n)) for n in STATE]
-    items += [("rad." + n, getattr(rad_o, n), getattr(rad_g, n)) for n in RAD]
+    items = [("state." + n, getattr(st_o, n), getattr(st_g, n)) for n in st_o.names()]
+    items += [("rad." + n, getattr(rad_o, n), getattr(rad_g, n)) for n in rad_o.names() if n != "qrad"]
     items += [(n, getattr(out_o, n), getattr(out_g, n)) for n, _ in pkg.abi.OUTPUT_FIELDS]
+    if dims.micro == 1:
+        items += [(n, getattr(out_o, n), getattr(out_g, n)) for n, _ in pkg.abi.OUTPUT_FIELDS_M2005]
     for name, a, b in items:
         if name in skip:
             continue

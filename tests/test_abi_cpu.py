@@ -71,5 +71,5 @@ def test_product_path_fails_loudly_without_a_gpu():
     # unsupported builds are refused before any device work
     with pytest.raises(RuntimeError, match="3-D CRM geometries"):
         cm.libmod.CrmHandle(cm.pkg.CrmDims(ncrms=4, nx=64, ny=64, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=40.0, igstep=3))
-    with pytest.raises(RuntimeError, match="sam1mom"):
-        cm.libmod.CrmHandle(dims.copy(micro=1))
+    with pytest.raises(RuntimeError, match="micro must be"):
+        cm.libmod.CrmHandle(dims.copy(micro=2))

@@ -82,3 +82,10 @@ def test_emu_3d_rectangular_setperturb(emu, monkeypatch):
     # 16x8 columns (different transform lengths in x and y), first call of a run (setperturb)
     monkeypatch.setenv("CRM_B200_CT", "2")
     _check(emu, _dims3d(3, 16, 8, 2, igstep=1), 0, 1e-11)
+
+
+def test_emu_m2005_two_moment_microphysics(emu):
+    # micro = 1: ten advected/diffused micro fields, the column scheme of crm_m2005_col.h per thread, m2005 outputs
+    dims = cm.pkg.CrmDims(ncrms=5, nx=8, ny=1, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=20.0 * 3, igstep=3, micro=1)
+    ro, rg = _check(emu, dims, 90, 1e-11)
+    assert ro[2].qs_mean.max() > 0 and ro[2].nc_mean.max() > 0 and ro[0].qr.max() > 0   # rain, snow and droplets exist: the scheme is exercised

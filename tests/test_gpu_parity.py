@@ -166,8 +166,8 @@ def test_error_behaviour_matches_reference_aborts():
     d3 = cm.pkg.CrmDims(ncrms=4, nx=64, ny=64, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=40.0, igstep=3)
     with pytest.raises(RuntimeError, match="3-D CRM geometries"):
         cm.libmod.CrmHandle(d3)
-    dm = cm.small_dims(ncrms=4, nx=8, nsteps=2).copy(micro=1)
-    with pytest.raises(RuntimeError, match="sam1mom"):
+    dm = cm.small_dims(ncrms=4, nx=8, nsteps=2).copy(micro=2)
+    with pytest.raises(RuntimeError, match="micro must be"):
         cm.libmod.CrmHandle(dm)
     dims = cm.small_dims(ncrms=4, nx=8, nsteps=5, use_crm_accel=True, crm_accel_factor=1.0)
     dims, inp, st, rad = cm.make_case(dims, 0)
@@ -348,3 +348,39 @@ def test_3d_continuity_and_positivity_property_wide_batch():
         (w[..., 1:] * rhow[:, None, None, 1:] - w[..., :-1] * rhow[:, None, None, :-1]) / (adz[:, None, None, :] * dz[:, None, None, None])
     scale = max(np.abs(u).max(), np.abs(v).max()) / dims.dx * rho.max()
     assert np.abs(div).max() / scale < 1e-11
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# M2005 two-moment microphysics (micro = 1, BASELINE config 3)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_m2005_small_steps():
+    dims = cm.pkg.CrmDims(ncrms=9, nx=16, ny=1, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=20.0 * 4, igstep=3, micro=1)
+    ro, rg = _check(dims, 90, 1e-10)
+    assert ro[0].qr.max() > 0 and ro[0].qs.max() > 0 and ro[0].nc.max() > 0
+
+
+def test_m2005_cfg3_geometry_steps():
+    # BASELINE config 3 geometry (64x1x58, L72, dx 1 km, dt 10 s) with m2005, 24 CRMs, 12 steps after a spin-up
+    dims = cm.pkg.CrmDims(ncrms=24, nx=64, ny=1, nzm=58, plev=72, dx=1000.0, dt=10.0, dt_gl=10.0 * 12, igstep=3, micro=1)
+    _check(dims, 60, 1e-7)
+
+
+def test_m2005_first_call_and_chunked_sweep(monkeypatch):
+    # first call of a run (setperturb, all hydrometeors zero) and the column work space swept in chunks of 2 tiles
+    monkeypatch.setenv("CRM_B200_M2005_CHUNK", "2")
+    dims = cm.pkg.CrmDims(ncrms=21, nx=32, ny=1, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=20.0 * 5, igstep=1, micro=1)
+    _check(dims, 0, 1e-10, abs_floor=1e-13)   # t_ls of the uniform cold state is round-off noise (4e-15 K/s)
+
+
+def test_m2005_3d():
+    dims = cm.pkg.CrmDims(ncrms=5, nx=8, ny=8, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=20.0 * 3, igstep=3, micro=1)
+    _check(dims, 40, 1e-10)
+
+
+def test_m2005_refuses_mean_state_acceleration():
+    dims = cm.pkg.CrmDims(ncrms=4, nx=8, ny=1, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=40.0, igstep=3, micro=1, use_crm_accel=True, crm_accel_factor=1.0)
+    dims, inp, st, rad = cm.make_case(dims, 0)
+    h = cm.libmod.CrmHandle(dims)
+    with pytest.raises(RuntimeError, match="only compatible with sam1mom"):
+        h.run(dims, inp, st, rad)
+    h.close()

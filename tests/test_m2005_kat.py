@@ -1,0 +1,173 @@
+"""CPU known-answer tests that pin the transcription of the M2005 column scheme (acme-ecp_b200/csrc/crm_m2005_col.h, shared
+by the oracle and the CUDA kernel) against facts that do NOT come from that transcription: published function values
+(scipy.special.gamma / erf, Goff-Gratch saturation pressure), the closed-form Khairoutdinov-Kogan autoconversion rate,
+re-computation of GRAUPEL_INIT constants with numpy float32 arithmetic from the reference's literals
+(module_mp_graupel.F90:496-688), and conservation / positivity invariants of the scheme.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.special as sp
+
+import common as cm
+
+L = cm.ob.lib()
+for f, args in (("crm_oracle_m2005_polysvp", [C.c_double, C.c_int]), ("crm_oracle_m2005_gamma", [C.c_double]), ("crm_oracle_m2005_derf1", [C.c_double]),
+                ("crm_oracle_m2005_const", [C.c_int])):
+    getattr(L, f).restype = C.c_double
+    getattr(L, f).argtypes = args
+P = cm.pkg.abi.c_dp
+L.crm_oracle_m2005_satadj.argtypes = [P, P, P, C.c_double]
+L.crm_oracle_m2005_column.argtypes = [C.c_int, C.c_double, P, P, P, P, P]
+f32 = np.float32
+CP, LCOND, LSUB = 1.00464e3, 2.501e6, 2.501e6 + 3.337e5
+RGAS = 6.02214e26 * 1.38065e-23 / 28.966
+RV = 6.02214e26 * 1.38065e-23 / 18.016
+
+
+def is_f32(x):
+    return float(f32(x)) == x
+
+
+def test_polysvp_is_single_precision_flatau_and_close_to_goff_gratch():
+    T = np.linspace(200., 310., 56)
+    for t in T:
+        ew, ei = L.crm_oracle_m2005_polysvp(t, 0), L.crm_oracle_m2005_polysvp(t, 1)
+        assert is_f32(ew) and is_f32(ei)          # REAL FUNCTION POLYSVP: result rounded to single
+        # Goff-Gratch formulas quoted (commented out) in module_mp_graupel.F90:5653-5655, 5672-5676
+        gg_w = 10. ** (-7.90298 * (373.16 / t - 1.) + 5.02808 * np.log10(373.16 / t) - 1.3816e-7 * (10 ** (11.344 * (1. - t / 373.16)) - 1.) +
+                       8.1328e-3 * (10 ** (-3.49149 * (373.16 / t - 1.)) - 1.) + np.log10(1013.246)) * 100.
+        gg_i = 10. ** (-9.09718 * (273.16 / t - 1.) - 3.56654 * np.log10(273.16 / t) + 0.876793 * (1. - t / 273.16) + np.log10(6.1071)) * 100.
+        assert abs(ew / gg_w - 1.) < (4e-3 if t >= 250. else 8e-2), (t, ew, gg_w)   # supercooled water below -43 C: the two fits diverge
+        if t <= 273.16:
+            assert abs(ei / gg_i - 1.) < (4e-3 if t >= 215. else 2e-2), (t, ei, gg_i)
+    assert L.crm_oracle_m2005_polysvp(float(f32(273.16)), 0) == float(f32(float(f32(6.11239921)) * 100.))   # dt = 0 exactly: a0 * 100, rounded to single
+    assert L.crm_oracle_m2005_polysvp(150., 0) == L.crm_oracle_m2005_polysvp(193.16, 0)   # dt clamped at -80 K
+
+
+def test_gamma_against_scipy():
+    for x in list(np.linspace(0.3, 14.9, 74)) + [1., 2., 3., 4., 5.41, 3.8, 12., 20.5, -0.5, -1.5, -2.3]:
+        g = L.crm_oracle_m2005_gamma(float(x))
+        assert is_f32(g)
+        assert abs(g / sp.gamma(x) - 1.) < 3e-7, (x, g, sp.gamma(x))
+
+
+def test_derf1_against_scipy():
+    for x in np.linspace(-7.5, 7.5, 301):
+        y = L.crm_oracle_m2005_derf1(float(x))
+        assert is_f32(y) and abs(y - sp.erf(x)) < 1.2e-7, (x, y, sp.erf(x))
+
+
+def test_graupel_init_constants_recomputed_with_float32_literals():
+    pi = float(f32(3.1415926535897932384626434))
+    g = lambda x: L.crm_oracle_m2005_gamma(float(x))
+    BS, BR, BG = float(f32(0.41)), float(f32(0.8)), float(f32(0.37))
+    RHOW, RHOI, RHOSN, RHOG = 997., 500., 100., 400.
+    c = L.crm_oracle_m2005_const
+    assert c(1) == g(1. + 3.) * (RHOSN * pi / 6.)                      # CONS1 = GAMMA(1.+DS)*CS
+    assert c(4) == g(4. + BR) / 6.
+    assert c(26) == pi / 6. * RHOW
+    assert c(29) == float(f32(4.) / f32(3.)) * pi * RHOW * float(f32(25.e-6) * f32(25.e-6) * f32(25.e-6))
+    assert c(34) == 2.5 + BR / 2.
+    assert c(15) == -1108. * float(f32(0.1)) * pi ** ((1. - BS) / 3.) * RHOSN ** ((-2. - BS) / 3.) / 2880.
+    assert c(37) == 4. * pi * float(f32(1.38e-23)) / (6. * pi * float(f32(0.1e-6)))
+    assert c(100) == float(f32(4.) / f32(3.)) * pi * RHOI * float(f32(10.e-6) * f32(10.e-6) * f32(10.e-6))   # MI0
+    assert c(102) == 85000. / (RGAS * float(f32(273.15)))                # RHOSU
+    assert c(105) == 1. / (2. * float(f32(125.e-6)) + float(f32(100.e-6)))   # LAMMINI
+    assert c(106) == float(f32(1.) / f32(20.e-6))                         # LAMMAXR
+    assert abs(c(103) / (3. * 1. * 0.7 * 0.018 * 1777. / (0.132 * 997.)) - 1.) < 1e-6   # BACT
+    assert BG > 0
+
+
+def test_satadj_liquid_saturation_and_energy():
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        t0 = rng.uniform(255., 305.); pres = rng.uniform(5e4, 1.01e5)
+        es = L.crm_oracle_m2005_polysvp(t0, 0)
+        qs0 = 0.622 * es / (pres - es)
+        qt0 = qs0 * rng.uniform(0.5, 1.6)
+        t = C.c_double(t0); q = C.c_double(qt0); qc = C.c_double(-1.)
+        L.crm_oracle_m2005_satadj(C.byref(t), C.byref(q), C.byref(qc), pres)
+        if qt0 <= float(f32(0.622)) * es / (pres - es):
+            assert qc.value == 0. and t.value == t0 and q.value == qt0
+        else:
+            assert qc.value > 0.
+            assert abs((q.value + qc.value) - qt0) < 1e-18 + 1e-15 * qt0              # water conserved
+            assert abs((t.value - t0) - LCOND / CP * qc.value) < 1e-9                  # latent heating of the condensate
+            es1 = L.crm_oracle_m2005_polysvp(t.value, 0)
+            qs1 = float(f32(0.622)) * es1 / (pres - es1)
+            assert abs(q.value / qs1 - 1.) < 2e-3                                      # vapour left at saturation (Newton stops at 0.01 K)
+
+
+def _column(nz, dt, state, inp):
+    st = np.ascontiguousarray(state, dtype=np.float64); ip = np.ascontiguousarray(inp, dtype=np.float64)
+    sed = np.zeros((5, nz)); rates = np.zeros((8, nz)); prec = np.zeros(2)
+    L.crm_oracle_m2005_column(nz, dt, st.ctypes.data_as(P), ip.ctypes.data_as(P), sed.ctypes.data_as(P), rates.ctypes.data_as(P), prec.ctypes.data_as(P))
+    return st, sed, rates, prec
+
+
+QC, QI, QNI, QR, NC, NI, NS, NR, QG, NG, T3, QV = range(12)
+
+
+def _atmosphere(nz, rh=0.6):
+    z = (np.arange(nz) + 0.5) * 400.
+    T = 300. - 6.5e-3 * z
+    pres = 1.0e5 * (T / 300.) ** (9.80616 / (RGAS * 6.5e-3))
+    rho = pres / (RGAS * T)
+    es = np.array([L.crm_oracle_m2005_polysvp(float(t), 0) for t in T])
+    qvs = RGAS / RV * es / (pres - es)
+    st = np.zeros((12, nz)); st[T3] = T; st[QV] = rh * qvs
+    inp = np.stack([pres, rho, np.full(nz, 400.), np.zeros(nz), np.full(nz, 0.3)])
+    return st, inp, qvs
+
+
+def test_column_clear_subsaturated_air_is_untouched():
+    st, inp, _ = _atmosphere(30, rh=0.5)
+    out, sed, rates, prec = _column(30, 10., st.copy(), inp)
+    assert np.array_equal(out, st) and prec[0] == 0. and not sed.any() and not rates.any()
+
+
+def test_column_kk2000_autoconversion_known_answer():
+    """One warm saturated layer with cloud water and no rain: the only active processes are KK2000 autoconversion
+    PRC = 1350 qc^2.47 (Nc rho / 1e6)^-1.79 (module_mp_graupel.F90:2059-2060), droplet activation (number only) and sedimentation."""
+    nz, dt = 20, 10.
+    st, inp, qvs = _atmosphere(nz, rh=0.95)   # (below 90 % humidity the scheme evaporates traces of rain < 1e-8 at once, :5196-5201)
+    k = 5
+    st[QV, k] = qvs[k]; st[QC, k] = 1.5e-3; st[NC, k] = 80.e6
+    out, sed, rates, prec = _column(nz, dt, st.copy(), inp)
+    rho = inp[1, k]
+    prc = float(f32(1350.)) * st[QC, k] ** float(f32(2.47)) * (st[NC, k] / 1.e6 * rho) ** float(f32(-1.79))
+    assert abs(rates[0, k] / prc - 1.) < 1e-12                        # aut1d
+    assert rates[1, k] == 0.                                          # no accretion without rain
+    # rain appears in layer k (and, through sedimentation, below); column rain water + surface rain == autoconverted water
+    rain = (out[QR] * inp[1] * inp[2]).sum() + prec[0]
+    assert abs(rain / (prc * dt * rho * inp[2, k]) - 1.) < 1e-9
+    assert np.all(out[:10] >= 0.)
+
+
+def test_column_water_conservation_and_positivity_mixed_phase():
+    rng = np.random.default_rng(11)
+    nz, dt = 40, 10.
+    st, inp, qvs = _atmosphere(nz, rh=0.9)
+    inp[3] = rng.uniform(-0.5, 2.0, nz)
+    for name, amp, num in ((QC, 1e-3, (NC, 120e6)), (QR, 5e-4, (NR, 3e4)), (QI, 2e-4, (NI, 2e5)), (QNI, 6e-4, (NS, 5e3)), (QG, 8e-4, (NG, 2e3))):
+        m = rng.uniform(size=nz) < 0.5
+        st[name] = np.where(m, amp * rng.uniform(0.1, 1., nz), 0.)
+        st[num[0]] = np.where(m, num[1] * rng.uniform(0.3, 1.5, nz), 0.)
+    st[QV] = qvs * rng.uniform(0.7, 1.15, nz)
+    w = inp[1] * inp[2]
+    water0 = (w * (st[QV] + st[QC] + st[QR] + st[QI] + st[QNI] + st[QG])).sum()
+    out, sed, rates, prec = _column(nz, dt, st.copy(), inp)
+    water1 = (w * (out[QV] + out[QC] + out[QR] + out[QI] + out[QNI] + out[QG])).sum()
+    assert abs((water0 - water1) - prec[0]) < 1e-9 * water0, (water0 - water1, prec[0])
+    assert prec[0] > 0. and 0. <= prec[1] <= prec[0]
+    assert np.all(out[:10] >= 0.) and np.isfinite(out).all()
+    assert np.all(out[NI] <= 10.e6 / inp[1] * (1 + 1e-12))                # ice number cap (module_mp_graupel.F90:5576)
+    # ice nucleates in cold, ice-supersaturated clear air (Cooper, :3790-3802)
+    st2, inp2, qvs2 = _atmosphere(nz, rh=0.3)
+    kk = nz - 2
+    ei = L.crm_oracle_m2005_polysvp(float(st2[T3, kk]), 1)
+    st2[QV, kk] = 1.2 * RGAS / RV * ei / (inp2[0, kk] - ei)
+    out2, _, rates2, _ = _column(nz, dt, st2.copy(), inp2)
+    assert st2[T3, kk] < 265. and out2[NI, kk] > 0. and out2[QI, kk] > 0. and rates2[6, kk] > 0.
