@@ -48,7 +48,9 @@ def test_ctypes_mirror_has_the_compiled_struct_layout(lib):
     # every member of crm_output_type that the reference allocates (crm_output_module.F90:7-133, sam1mom build) is bound
     names = {n for n, _ in abi.OUTPUT_FIELDS}
     assert {"sltend", "qltend", "qcltend", "qiltend", "precc", "precl", "cld", "prec_crm", "timing_factor", "qp_evp"} <= names
-    assert names == {f[0] for f in abi.crm_output_t._fields_}
+    m2005 = {n for n, _ in abi.OUTPUT_FIELDS_M2005}   # crm_output_module.F90:22-31, 60-74 (m2005 build)
+    assert {"wvar", "aut", "con", "nc_mean", "nr_mean", "aut_a", "con_a"} <= m2005
+    assert names | m2005 == {f[0] for f in abi.crm_output_t._fields_}
 
 
 def test_fortran_shim_binds_the_same_entry_points():
