@@ -858,3 +858,55 @@ extern "C" int crm_oracle_physics_post(const crm_dims_t *d, const double *pdel, 
   }
   return 0;
 }
+
+// precip_proc (MICRO_SAM1MOM/precip_proc.F90:7-151) on n independent cells, each a one-level CRM whose coefficient profiles
+// come from precip_init with (rho, tabs0, pres) of the cell: q, qp, qn updated; dsrc / devp = the cell's qpsrc / qpevp.
+extern "C" int crm_oracle_test_precip_proc(int n, double dtn, const double *tabs, const double *pres, const double *rho, const double *tabs0,
+                                           double *q, double *qp, double *qn, double *dsrc, double *devp) {
+  MicroCoef mc; mc.init();
+  for (int m = 0; m < n; m++) {
+    Geo g; g.nx = 1; g.ny = 1; g.nzm = 1; g.nz = 2; g.plev = 1; g.YES3D = 0; g.RUN3D = false; g.nx_rad = 1; g.ny_rad = 1; g.dx = g.dy = 1000.;
+    Crm c; alloc_crm(g, c);
+    Step s; s.dtn = dtn; s.dt = dtn;
+    c.tabs(1, 1, 1) = tabs[m]; c.pres(1) = pres[m]; c.rho(1) = rho[m]; c.tabs0(1) = tabs0[m];
+    c.qt(1, 1, 1) = q[m]; c.qp(1, 1, 1) = qp[m]; c.qn(1, 1, 1) = qn[m];
+    precip_init(g, c, mc);
+    precip_proc(g, c, s, mc);
+    q[m] = c.qt(1, 1, 1); qp[m] = c.qp(1, 1, 1); qn[m] = c.qn(1, 1, 1); dsrc[m] = c.qpsrc(1); devp[m] = c.qpevp(1);
+  }
+  return 0;
+}
+
+// sgs_proc = shear_prod2D + tke_full (SGS_TKE/tke_full.F90:11-317, dosmagor) of one 2-D CRM: fields (nx, nzm[+1 for w]) in Fortran
+// order, profiles adz, bet, u0 (nzm), adzw, presi (nzm+1); tk in/out, tkh, tke out.
+extern "C" int crm_oracle_test_sgs(int nx, int nzm, double dx, double dt, double dz, const double *adz, const double *adzw, const double *bet,
+                                   const double *presi, const double *u0, const double *u, const double *w, const double *t, const double *tabs,
+                                   const double *qv, const double *qcl, const double *qci, const double *qpl, const double *qpi, double *tk, double *tkh,
+                                   double *tke) {
+  Geo g; g.nx = nx; g.ny = 1; g.nzm = nzm; g.nz = nzm + 1; g.plev = nzm; g.YES3D = 0; g.RUN3D = false; g.nx_rad = 1; g.ny_rad = 1; g.dx = g.dy = dx;
+  Crm c; alloc_crm(g, c);
+  Step s; s.dt = dt; s.dtn = dt;
+  c.dz = dz;
+  for (int k = 1; k <= nzm + 1; k++) { c.adzw(k) = adzw[k - 1]; c.presi(k) = presi[k - 1]; if (k <= nzm) { c.adz(k) = adz[k - 1]; c.bet(k) = bet[k - 1]; c.u0(k) = u0[k - 1]; } }
+  for (int k = 1; k <= nzm; k++) {
+    double a2 = (c.adz(k) * c.dz) * (c.adz(k) * c.dz);
+    c.grdf_x(k) = dmin(16., dx * dx / a2); c.grdf_y(k) = c.grdf_x(k); c.grdf_z(k) = 1.;
+  }
+  for (int k = 1; k <= nzm + 1; k++)
+    for (int i = 1; i <= nx; i++) {
+      const size_t o = (size_t)(i - 1) + (size_t)nx * (k - 1);
+      c.w(i, 1, k) = w[o];
+      if (k <= nzm) {
+        c.u(i, 1, k) = u[o]; c.t(i, 1, k) = t[o]; c.tabs(i, 1, k) = tabs[o]; c.qv(i, 1, k) = qv[o]; c.qcl(i, 1, k) = qcl[o]; c.qci(i, 1, k) = qci[o];
+        c.qpl(i, 1, k) = qpl[o]; c.qpi(i, 1, k) = qpi[o]; c.tk(i, 1, k) = tk[o]; c.tkh(i, 1, k) = tk[o];
+      }
+    }
+  boundaries(g, c, 0);
+  sgs_proc(g, c, s);
+  for (int k = 1; k <= nzm; k++)
+    for (int i = 1; i <= nx; i++) {
+      const size_t o = (size_t)(i - 1) + (size_t)nx * (k - 1);
+      tk[o] = c.tk(i, 1, k); tkh[o] = c.tkh(i, 1, k); tke[o] = c.tke(i, 1, k);
+    }
+  return 0;
+}

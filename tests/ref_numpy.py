@@ -1,0 +1,479 @@
+"""SECOND, independent restatement (numpy / plain Python) of five reference routines, written directly from the Fortran sources
+under /root/reference/components/cam/src/physics/crm (not from oracle/*.cpp), with another program structure than the C++
+oracle (periodic index arithmetic instead of halo arrays, cell-wise functions instead of field loops).  TEST INFRASTRUCTURE:
+tests/test_second_restatement.py checks the C++ oracle against it; agreement of two independent transcriptions is what stands in
+for the reference Fortran, which cannot be compiled in this environment (no Fortran compiler here or on the GPU box:
+profiles/r02_fortran_probe_gpu_box.txt).
+
+  sat.F90:12-139                          esatw/esati/dtesatw/dtesati/qsatw/qsati/dtqsatw/dtqsati
+  MICRO_SAM1MOM/precip_init.F90:23-93     precip_coefs
+  MICRO_SAM1MOM/cloud.F90:29-112          cloud_cell
+  MICRO_SAM1MOM/precip_proc.F90:47-148    precip_proc_cell
+  MICRO_SAM1MOM/microphysics.F90:453-830  term_vel_qp, precip_fall_column
+  ADV_MPDATA/advect_scalar2D.F90:93-234   advect_scalar2d
+  SGS_TKE/shear_prod2D.F90:20-94 + tke_full.F90:103-310   sgs_2d
+Unsuffixed literals are REAL(4) in the reference build (no -r8): f4() reproduces them; literal-only sub-expressions are evaluated in
+float32.
+"""
+import math
+
+import numpy as np
+
+F = np.float32
+
+
+def f4(x):
+    return float(F(x))
+
+
+# params.F90:49-69 / shr_const_mod.F90:22-54
+cp = 1.00464e3
+ggr = 9.80616
+lcond = 2.501e6
+lfus = 3.337e5
+lsub = lcond + lfus
+rv = 6.02214e26 * 1.38065e-23 / 18.016
+fac_cond, fac_fus, fac_sub = lcond / cp, lfus / cp, lsub / cp
+pi = f4(3.141592653589793)
+epsv = f4(0.61)
+diffelq, therco, muelq = f4(2.21e-05), f4(2.40e-02), f4(1.717e-05)
+# micro_params.F90:12-65
+rhor, rhos, rhog = f4(1000.), f4(100.), f4(400.)
+tbgmin, tbgmax, tprmin, tprmax, tgrmin, tgrmax = f4(253.16), f4(273.16), f4(268.16), f4(283.16), f4(223.16), f4(283.16)
+a_rain, b_rain, a_snow, b_snow, a_grau, b_grau = f4(842.), f4(0.8), f4(4.84), f4(0.25), f4(94.5), f4(0.5)
+qcw0, qci0, alphaelq, betaelq = f4(1.e-3), f4(1.e-4), f4(1.e-3), f4(1.e-3)
+erccoef, esccoef, esicoef, egccoef, egicoef = f4(1.0), f4(1.0), f4(0.1), f4(1.0), f4(0.1)
+nzeror, nzeros, nzerog = f4(8.e6), f4(3.e6), f4(4.e6)
+qp_threshold = f4(1.e-8)
+a_bg, a_pr, a_gr = 1. / (tbgmax - tbgmin), 1. / (tprmax - tprmin), 1. / (tgrmax - tgrmin)
+
+
+def _poly(c, dt):
+    a0, a1, a2, a3, a4, a5, a6, a7, a8 = (f4(v) for v in c)
+    return a0 + dt * (a1 + dt * (a2 + dt * (a3 + dt * (a4 + dt * (a5 + dt * (a6 + dt * (a7 + a8 * dt)))))))
+
+
+_EW = (6.105851, 0.4440316, 0.1430341e-1, 0.2641412e-3, 0.2995057e-5, 0.2031998e-7, 0.6936113e-10, 0.2564861e-13, -0.3704404e-15)
+_EI = (6.11147274, 0.503160820, 0.188439774e-1, 0.420895665e-3, 0.615021634e-5, 0.602588177e-7, 0.385852041e-9, 0.146898966e-11, 0.252751365e-14)
+_DW = (0.443956472, 0.285976452e-1, 0.794747212e-3, 0.121167162e-4, 0.103167413e-6, 0.385208005e-9, -0.604119582e-12, -0.792933209e-14, -0.599634321e-17)
+_DI = (0.503223089, 0.377174432e-1, 0.126710138e-2, 0.249065913e-4, 0.312668753e-6, 0.255653718e-8, 0.132073448e-10, 0.390204672e-13, 0.497275778e-16)
+
+
+def _cold(t):
+    return math.exp(f4(9.550426) - f4(5723.265) / t + f4(3.53068) * math.log(t) - f4(0.00728332) * t)
+
+
+def esatw(t):
+    dt = t - f4(273.16)
+    return _poly(_EW, dt) if dt > f4(-80.) else float(F(2.) * F(0.01)) * _cold(t)
+
+
+def esati(t):
+    dt = t - f4(273.16)
+    return _poly(_EI, dt) if dt > f4(-80.) else f4(0.01) * _cold(t)
+
+
+def dtesatw(t):
+    dt = t - f4(273.16)
+    return _poly(_DW, dt) if dt > f4(-80.) else esatw(t + 1) - esatw(t)
+
+
+def dtesati(t):
+    dt = t - f4(273.16)
+    return _poly(_DI, dt) if dt > f4(-80.) else esati(t + f4(1.)) - esati(t)
+
+
+def qsatw(t, p):
+    e = esatw(t)
+    return f4(0.622) * e / max(e, p - e)
+
+
+def qsati(t, p):
+    e = esati(t)
+    return f4(0.622) * e / max(e, p - e)
+
+
+def dtqsatw(t, p):
+    return f4(0.622) * dtesatw(t) / p
+
+
+def dtqsati(t, p):
+    return f4(0.622) * dtesati(t) / p
+
+
+def gammafff(x):   # gammafff.c:12 on a REAL*4 argument
+    return float(F(math.exp(math.lgamma(float(F(x))))))
+
+
+def _gams():
+    g = {}
+    g["gamr1"] = gammafff(F(3.) + F(0.8)); g["gamr2"] = gammafff((F(5.) + F(0.8)) / F(2.)); g["gamr3"] = gammafff(F(4.) + F(0.8))
+    g["gams1"] = gammafff(F(3.) + F(0.25)); g["gams2"] = gammafff((F(5.) + F(0.25)) / F(2.)); g["gams3"] = gammafff(F(4.) + F(0.25))
+    g["gamg1"] = gammafff(F(3.) + F(0.5)); g["gamg2"] = gammafff((F(5.) + F(0.5)) / F(2.)); g["gamg3"] = gammafff(F(4.) + F(0.5))
+    return g
+
+
+GAM = _gams()
+
+
+def precip_coefs(rho, tabs0, pres):
+    """precip_init.F90:46-93 for one level."""
+    g = GAM
+    c = {}
+    pratio = math.sqrt(f4(1.29) / rho)
+    rrr1 = f4(393.) / (tabs0 + f4(120.)) * (tabs0 / f4(273.)) ** f4(1.5)
+    rrr2 = (tabs0 / f4(273.)) ** f4(1.94) * (f4(1000.) / pres)
+    estw = f4(100.) * esatw(tabs0)
+    esti = f4(100.) * esati(tabs0)
+    coef1 = 0.25 * pi * nzeros * a_snow * g["gams1"] * pratio / (pi * rhos * nzeros / rho) ** ((3 + b_snow) / 4.)
+    coef2 = math.exp(f4(0.025) * (tabs0 - f4(273.15)))
+    c["accrsi"] = coef1 * coef2 * esicoef; c["accrsc"] = coef1 * esccoef; c["coefice"] = coef2
+    coef1 = (lsub / (tabs0 * rv) - 1.) * lsub / (therco * rrr1 * tabs0)
+    coef2 = rv * tabs0 / (diffelq * rrr2 * esti)
+    c["evaps1"] = float(F(0.65) * F(4.)) * nzeros / math.sqrt(pi * rhos * nzeros) / (coef1 + coef2) / math.sqrt(rho)
+    c["evaps2"] = float(F(0.49) * F(4.)) * nzeros * g["gams2"] * math.sqrt(a_snow / (muelq * rrr1)) / (pi * rhos * nzeros) ** ((5 + b_snow) / 8.) / \
+        (coef1 + coef2) * rho ** ((1 + b_snow) / 8.) * math.sqrt(pratio)
+    coef1 = 0.25 * pi * nzerog * a_grau * g["gamg1"] * pratio / (pi * rhog * nzerog / rho) ** ((3 + b_grau) / 4.)
+    coef2 = math.exp(f4(0.025) * (tabs0 - f4(273.15)))
+    c["accrgi"] = coef1 * coef2 * egicoef; c["accrgc"] = coef1 * egccoef
+    coef1 = (lsub / (tabs0 * rv) - 1.) * lsub / (therco * rrr1 * tabs0)
+    coef2 = rv * tabs0 / (diffelq * rrr2 * esti)
+    c["evapg1"] = float(F(0.65) * F(4.)) * nzerog / math.sqrt(pi * rhog * nzerog) / (coef1 + coef2) / math.sqrt(rho)
+    c["evapg2"] = float(F(0.49) * F(4.)) * nzerog * g["gamg2"] * math.sqrt(a_grau / (muelq * rrr1)) / (pi * rhog * nzerog) ** ((5 + b_grau) / 8.) / \
+        (coef1 + coef2) * rho ** ((1 + b_grau) / 8.) * math.sqrt(pratio)
+    c["accrrc"] = 0.25 * pi * nzeror * a_rain * g["gamr1"] * pratio / (pi * rhor * nzeror / rho) ** ((3 + b_rain) / 4.) * erccoef
+    coef1 = (lcond / (tabs0 * rv) - 1.) * lcond / (therco * rrr1 * tabs0)
+    coef2 = rv * tabs0 / (diffelq * rrr2 * estw)
+    c["evapr1"] = float(F(0.78) * F(2.)) * pi * nzeror / math.sqrt(pi * rhor * nzeror) / (coef1 + coef2) / math.sqrt(rho)
+    c["evapr2"] = float(F(0.31) * F(2.)) * pi * nzeror * g["gamr2"] * f4(0.89) * math.sqrt(a_rain / (muelq * rrr1)) / (pi * rhor * nzeror) ** ((5 + b_rain) / 8.) / \
+        (coef1 + coef2) * rho ** ((1 + b_rain) / 8.) * math.sqrt(pratio)
+    return c
+
+
+def cloud_cell(t, gamaz, pres, q, qp):
+    """cloud.F90:40-112 for one cell -> (q, qp, tabs, qn)."""
+    an = 1. / (tbgmax - tbgmin); bn = tbgmin * an
+    ap = 1. / (tprmax - tprmin); bp = tprmin * ap
+    fac1 = fac_cond + (1 + bp) * fac_fus
+    fac2 = fac_fus * ap
+    q = max(0., q)
+    tabs = t - gamaz
+    tabs1 = (tabs + fac1 * qp) / (1. + fac2 * qp)
+    if tabs1 >= tbgmax:
+        tabs1 = tabs + fac_cond * qp
+        qsatt = qsatw(tabs1, pres)
+    elif tabs1 <= tbgmin:
+        tabs1 = tabs + fac_sub * qp
+        qsatt = qsati(tabs1, pres)
+    else:
+        om = an * tabs1 - bn
+        qsatt = om * qsatw(tabs1, pres) + (1. - om) * qsati(tabs1, pres)
+    if q > qsatt:
+        niter = 0
+        dtabs = f4(100.)
+        while abs(dtabs) > f4(0.01) and niter < 10:
+            if tabs1 >= tbgmax:
+                om = 1.; lstarn = fac_cond; dlstarn = 0.
+                qsatt = qsatw(tabs1, pres); dqsat = dtqsatw(tabs1, pres)
+            elif tabs1 <= tbgmin:
+                om = 0.; lstarn = fac_sub; dlstarn = 0.
+                qsatt = qsati(tabs1, pres); dqsat = dtqsati(tabs1, pres)
+            else:
+                om = an * tabs1 - bn
+                lstarn = fac_cond + (1. - om) * fac_fus
+                dlstarn = an * fac_fus
+                qsatt = om * qsatw(tabs1, pres) + (1. - om) * qsati(tabs1, pres)
+                dqsat = om * dtqsatw(tabs1, pres) + (1. - om) * dtqsati(tabs1, pres)
+            if tabs1 >= tprmax:
+                lstarp = fac_cond; dlstarp = 0.
+            elif tabs1 <= tprmin:
+                lstarp = fac_sub; dlstarp = 0.
+            else:
+                omp = ap * tabs1 - bp
+                lstarp = fac_cond + (1. - omp) * fac_fus
+                dlstarp = ap * fac_fus
+            fff = tabs - tabs1 + lstarn * (q - qsatt) + lstarp * qp
+            dfff = dlstarn * (q - qsatt) + dlstarp * qp - lstarn * dqsat - 1.
+            dtabs = -fff / dfff
+            niter += 1
+            tabs1 = tabs1 + dtabs
+        qsatt = qsatt + dqsat * dtabs
+        qn = max(0., q - qsatt)
+    else:
+        qn = 0.
+    return q, max(0., qp), tabs1, qn
+
+
+def precip_proc_cell(dtn, tabs, pres, c, q, qp, qn):
+    """precip_proc.F90:47-148 for one cell with the level's coefficients c -> (q, qp, qn, dsrc, devp)."""
+    powr1 = (3 + b_rain) / 4.; powr2 = (5 + b_rain) / 8.
+    pows1 = (3 + b_snow) / 4.; pows2 = (5 + b_snow) / 8.
+    powg1 = (3 + b_grau) / 4.; powg2 = (5 + b_grau) / 8.
+    dsrc = devp = 0.
+    if qn + qp > 0.:
+        omn = max(0., min(1., (tabs - tbgmin) * a_bg))
+        omp = max(0., min(1., (tabs - tprmin) * a_pr))
+        omg = max(0., min(1., (tabs - tgrmin) * a_gr))
+        if qn > 0.:
+            qcc = qn * omn
+            qii = qn * (1. - omn)
+            autor = alphaelq if qcc > qcw0 else 0.
+            autos = betaelq * c["coefice"] if qii > qci0 else 0.
+            accrr = 0.
+            if omp > f4(0.001):
+                accrr = c["accrrc"] * (qp * omp) ** powr1
+            accrcs = accris = 0.
+            if omp < f4(0.999) and omg < f4(0.999):
+                tmp = (qp * (1. - omp) * (1. - omg)) ** pows1
+                accrcs = c["accrsc"] * tmp; accris = c["accrsi"] * tmp
+            accrcg = accrig = 0.
+            if omp < f4(0.999) and omg > f4(0.001):
+                tmp = (qp * (1. - omp) * omg) ** powg1
+                accrcg = c["accrgc"] * tmp; accrig = c["accrgi"] * tmp
+            qcc = (qcc + dtn * autor * qcw0) / (1. + dtn * (accrr + accrcs + accrcg + autor))
+            qii = (qii + dtn * autos * qci0) / (1. + dtn * (accris + accrig + autos))
+            dq = dtn * (accrr * qcc + autor * (qcc - qcw0) + (accris + accrig) * qii + (accrcs + accrcg) * qcc + autos * (qii - qci0))
+            dq = min(dq, qn)
+            qp += dq; q -= dq; qn -= dq; dsrc += dq
+        elif qp > qp_threshold and qn == 0.:
+            qsatt = 0.
+            if omn > f4(0.001):
+                qsatt += omn * qsatw(tabs, pres)
+            if omn < f4(0.999):
+                qsatt += (1. - omn) * qsati(tabs, pres)
+            dq = 0.
+            if omp > f4(0.001):
+                qrr = qp * omp
+                dq += c["evapr1"] * math.sqrt(qrr) + c["evapr2"] * qrr ** powr2
+            if omp < f4(0.999) and omg < f4(0.999):
+                qss = qp * (1. - omp) * (1. - omg)
+                dq += c["evaps1"] * math.sqrt(qss) + c["evaps2"] * qss ** pows2
+            if omp < f4(0.999) and omg > f4(0.001):
+                qgg = qp * (1. - omp) * omg
+                dq += c["evapg1"] * math.sqrt(qgg) + c["evapg2"] * qgg ** powg2
+            dq = dq * dtn * (q / qsatt - 1.)
+            dq = max(-0.5 * qp, dq)
+            qp += dq; q -= dq; devp += dq
+        else:
+            q += qp; devp -= qp; qp = 0.
+    dq = qp
+    qp = max(0., qp)
+    q = q + (dq - qp)
+    return q, qp, qn, dsrc, devp
+
+
+def _r(a, s):
+    """a(i+s) with periodic wrap along axis 0"""
+    return np.roll(a, -s, axis=0)
+
+
+def advect_scalar2d(f, u, w, rho, rhow, adz):
+    """advect_scalar2D.F90:93-234 + the flux statistic; f, u (nx, nzm), w (nx, nzm+1); periodic in x by index arithmetic.
+    Returns (f_new, flux(nzm))."""
+    nx, nzm = f.shape
+    eps = f4(1.e-10)
+    pp = lambda y: np.maximum(0., y)
+    pn = lambda y: -np.minimum(0., y)
+    andiff = lambda x1, x2, a, b: (np.abs(a) - a * a * b) * 0.5 * (x2 - x1)
+    across = lambda x1, a1, a2: 0.03125 * a1 * a2 * x1
+    kb = np.maximum(0, np.arange(nzm) - 1); kc = np.minimum(nzm - 1, np.arange(nzm) + 1)
+    irho = 1. / rho; iadz = 1. / adz; irhow = 1. / (rhow[:nzm] * adz)
+    mx = np.maximum.reduce([_r(f, -1), _r(f, 1), f[:, kb], f[:, kc], f])
+    mn = np.minimum.reduce([_r(f, -1), _r(f, 1), f[:, kb], f[:, kc], f])
+    uuu = np.maximum(0., u) * _r(f, -1) + np.minimum(0., u) * f
+    www = np.zeros((nx, nzm + 1))
+    www[:, :nzm] = np.maximum(0., w[:, :nzm]) * f[:, kb] + np.minimum(0., w[:, :nzm]) * f
+    flux = www[:, :nzm].sum(axis=0) * 0.
+    for k in range(nzm):
+        s = 0.
+        for i in range(nx):
+            s = s + www[i, k]
+        flux[k] = s
+    f = f - (_r(uuu, 1) - uuu + (www[:, 1:] - www[:, :nzm]) * iadz) * irho
+    dd = np.array([float(F(2.) / F(int(kc[k] - kb[k]))) / adz[k] for k in range(nzm)])
+    wk, wc = w[:, :nzm], w[:, kc]   # w(i,k), w(i,kc) with kc = min(nzm,k+1) (1-based) -> index kc of the (nzm+1) array is kc (0-based k+1 clipped to nzm-1)
+    uuu = andiff(_r(f, -1), f, u, irho) - across(dd * (_r(f, -1)[:, kc] + f[:, kc] - _r(f, -1)[:, kb] - f[:, kb]), u,
+                                                 _r(wk, -1) + _r(wc, -1) + wk + wc) * irho
+    www2 = andiff(f[:, kb], f, wk, irhow) - across(_r(f, 1)[:, kb] + _r(f, 1) - _r(f, -1)[:, kb] - _r(f, -1), wk,
+                                                   u[:, kb] + u + _r(u, 1) + _r(u, 1)[:, kb]) * irho
+    www = np.zeros((nx, nzm + 1)); www[:, :nzm] = www2
+    www[:, 0] = 0.
+    mx = np.maximum.reduce([_r(f, -1), _r(f, 1), f[:, kb], f[:, kc], f, mx])
+    mn = np.minimum.reduce([_r(f, -1), _r(f, 1), f[:, kb], f[:, kc], f, mn])
+    wkc = www[:, kc]   # www(i,kc), kc = min(nzm,k+1)
+    mxn = rho * (mx - f) / (pn(_r(uuu, 1)) + pp(uuu) + iadz * (pn(wkc) + pp(www[:, :nzm])) + eps)
+    mnn = rho * (f - mn) / (pp(_r(uuu, 1)) + pn(uuu) + iadz * (pp(wkc) + pn(www[:, :nzm])) + eps)
+    one = np.ones_like(f)
+    uuu = pp(uuu) * np.minimum.reduce([one, mxn, _r(mnn, -1)]) - pn(uuu) * np.minimum.reduce([one, _r(mxn, -1), mnn])
+    wl = pp(www[:, :nzm]) * np.minimum.reduce([one, mxn, mnn[:, kb]]) - pn(www[:, :nzm]) * np.minimum.reduce([one, mxn[:, kb], mnn])
+    for k in range(nzm):
+        s = flux[k]
+        for i in range(nx):
+            s = s + wl[i, k]
+        flux[k] = s
+    www = np.zeros((nx, nzm + 1)); www[:, :nzm] = wl
+    f = np.maximum(0., f - (_r(uuu, 1) - uuu + (www[:, 1:] - www[:, :nzm]) * iadz) * irho)
+    return f, flux
+
+
+def term_vel_qp(qploc, rho, tabs, v):
+    """microphysics.F90:453-486; v = (vrain, vsnow, vgrau, crain, csnow, cgrau)."""
+    vrain, vsnow, vgrau, crain, csnow, cgrau = v
+    term_vel = 0.
+    if qploc > qp_threshold:
+        omp = max(0., min(1., (tabs - tprmin) * a_pr))
+        if omp == 1.:
+            term_vel = vrain * (rho * qploc) ** crain
+        elif omp == 0.:
+            omg = max(0., min(1., (tabs - tgrmin) * a_gr))
+            qgg = omg * qploc; qss = qploc - qgg
+            term_vel = (omg * vgrau * (rho * qgg) ** cgrau + (1. - omg) * vsnow * (rho * qss) ** csnow)
+        else:
+            omg = max(0., min(1., (tabs - tgrmin) * a_gr))
+            qrr = omp * qploc; qss = qploc - qrr; qgg = omg * qss; qss = qss - qgg
+            term_vel = (omp * vrain * (rho * qrr) ** crain + (1. - omp) * (omg * vgrau * (rho * qgg) ** cgrau + (1. - omg) * vsnow * (rho * qss) ** csnow))
+    return term_vel
+
+
+def fall_coefs():
+    crain = b_rain / 4.; csnow = b_snow / 4.; cgrau = b_grau / 4.
+    vrain = a_rain * GAM["gamr3"] / 6. / (pi * rhor * nzeror) ** crain
+    vsnow = a_snow * GAM["gams3"] / 6. / (pi * rhos * nzeros) ** csnow
+    vgrau = a_grau * GAM["gamg3"] / 6. / (pi * rhog * nzerog) ** cgrau
+    return vrain, vsnow, vgrau, crain, csnow, cgrau
+
+
+def precip_fall_columns(dz, dtn, rho, rhow, adz, tabs, qp, t):
+    """micro_precip_fall / precip_fall (microphysics.F90:491-830, hydro_type 2) for columns (ncol, nzm) sharing one batch-global
+    nprec.  Returns (qp, t, precsfc(ncol), nprec)."""
+    ncol, nzm = qp.shape
+    v = fall_coefs()
+    eps = f4(1.e-10)
+    pp = lambda y: max(0., y)
+    pn = lambda y: -min(0., y)
+    omega = np.array([[max(0., min(1., (tabs[c, k] - tprmin) * a_pr)) for k in range(nzm)] for c in range(ncol)])
+    rhofac = np.sqrt(f4(1.29) / rho); irhoadz = 1. / (rho * adz)
+    iwmax = np.array([1. / (dz * adz[max(0, k - 1)] / dtn) for k in range(nzm)])
+    lfac = np.zeros((ncol, nzm + 1)); lfac[:, :nzm] = fac_cond + (1 - omega) * fac_fus
+    wp = np.zeros((ncol, nzm)); prec_cfl = 0.
+    for c in range(ncol):
+        for k in range(nzm):
+            w0 = rhofac[k] * term_vel_qp(qp[c, k], rho[k], tabs[c, k], v)
+            prec_cfl = max(prec_cfl, w0 * iwmax[k])
+            wp[c, k] = -w0 * rhow[k] * dtn / dz
+    if prec_cfl > f4(0.9):
+        nprec = int(math.ceil(prec_cfl / f4(0.9)))
+        wp = wp / float(nprec)
+    else:
+        nprec = 1
+    qp = qp.copy(); t = t.copy(); precsfc = np.zeros(ncol)
+    for iprec in range(1, nprec + 1):
+        for c in range(ncol):
+            q0 = qp[c].copy()
+            kb = [max(0, k - 1) for k in range(nzm)]; kc = [min(nzm - 1, k + 1) for k in range(nzm)]
+            mx = [max(q0[kb[k]], q0[kc[k]], q0[k]) for k in range(nzm)]
+            mn = [min(q0[kb[k]], q0[kc[k]], q0[k]) for k in range(nzm)]
+            fz = [q0[k] * wp[c, k] for k in range(nzm)] + [0.]
+            tq = [q0[k] - (fz[k + 1] - fz[k]) * irhoadz[k] for k in range(nzm)]
+            www = [0.5 * (1. + wp[c, k] * irhoadz[k]) * (tq[kb[k]] * wp[c, kb[k]] - tq[k] * wp[c, k]) for k in range(nzm)] + [0.]
+            mxn = [0.] * nzm; mnn = [0.] * nzm
+            for k in range(nzm):
+                m1 = max(tq[kb[k]], tq[kc[k]], tq[k], mx[k]); m2 = min(tq[kb[k]], tq[kc[k]], tq[k], mn[k])
+                mxn[k] = rho[k] * adz[k] * (m1 - tq[k]) / (pn(www[kc[k]]) + pp(www[k]) + eps)
+                mnn[k] = rho[k] * adz[k] * (tq[k] - m2) / (pp(www[kc[k]]) + pn(www[k]) + eps)
+            for k in range(nzm):
+                fz[k] = fz[k] + pp(www[k]) * min(1., mxn[k], mnn[kb[k]]) - pn(www[k]) * min(1., mxn[kb[k]], mnn[k])
+            for k in range(nzm):
+                qp[c, k] = qp[c, k] - (fz[k + 1] - fz[k]) * irhoadz[k]
+                lat_heat = -(lfac[c, k + 1] * fz[k + 1] - lfac[c, k] * fz[k]) * irhoadz[k]
+                t[c, k] = t[c, k] - lat_heat
+            precsfc[c] = precsfc[c] - fz[0] * 1.
+            if iprec < nprec:
+                for k in range(nzm):
+                    w0 = rhofac[k] * term_vel_qp(qp[c, k], rho[k], tabs[c, k], v)
+                    wp[c, k] = -w0 * rhow[k] * dtn / dz / float(nprec)
+    return qp, t, precsfc, nprec
+
+
+def sgs_2d(dx, dt, dz, adz, adzw, bet, presi, u0, u, w, t, tabs, qv, qcl, qci, qpl, qpi, tk):
+    """shear_prod2D.F90 + tke_full.F90 (dosmagor) for one 2-D CRM: fields (nx, nzm), w (nx, nzm+1), v == 0; periodic in x.
+    Returns (tk, tkh, tke); tk in = eddy viscosity of the previous sub-step."""
+    nx, nzm = u.shape
+    sq = lambda x: x * x
+    rdx0 = 1. / dx
+    def2 = np.zeros((nx, nzm))
+    up, wm = _r(u, 1), _r(w, -1)
+    wpl = _r(w, 1)
+    for k in range(nzm):
+        rdz = 1. / (dz * adz[k]); rdx = rdx0 * math.sqrt(dx * rdz)
+        base = 2. * (sq((up[:, k] - u[:, k]) * rdx) + sq((w[:, k + 1] - w[:, k]) * rdz))
+        upt = dnt = None
+        if k <= nzm - 2:
+            rdzw_up = 1. / (dz * adzw[k + 1]); rdx_up = rdx0 * math.sqrt(dx * rdzw_up)
+            upt = sq((up[:, k + 1] - u0[k + 1] - up[:, k] + u0[k]) * rdzw_up + (wpl[:, k + 1] - w[:, k + 1]) * rdx_up) + \
+                sq((u[:, k + 1] - u0[k + 1] - u[:, k] + u0[k]) * rdzw_up + (w[:, k + 1] - wm[:, k + 1]) * rdx_up)
+        if k >= 1:
+            rdzw_dn = 1. / (dz * adzw[k]); rdx_dn = rdx0 * math.sqrt(dx * rdzw_dn)
+            dnt = sq((up[:, k] - u0[k] - up[:, k - 1] + u0[k - 1]) * rdzw_dn + (wpl[:, k] - w[:, k]) * rdx_dn) + \
+                sq((u[:, k] - u0[k] - u[:, k - 1] + u0[k - 1]) * rdzw_dn + (w[:, k] - wm[:, k]) * rdx_dn)
+        if 1 <= k <= nzm - 2:
+            a1 = sq((up[:, k + 1] - u0[k + 1] - up[:, k] + u0[k]) * rdzw_up + (wpl[:, k + 1] - w[:, k + 1]) * rdx_up)
+            a2 = sq((u[:, k + 1] - u0[k + 1] - u[:, k] + u0[k]) * rdzw_up + (w[:, k + 1] - wm[:, k + 1]) * rdx_up)
+            a3 = sq((up[:, k] - u0[k] - up[:, k - 1] + u0[k - 1]) * rdzw_dn + (wpl[:, k] - w[:, k]) * rdx_dn)
+            a4 = sq((u[:, k] - u0[k] - u[:, k - 1] + u0[k - 1]) * rdzw_dn + (w[:, k] - wm[:, k]) * rdx_dn)
+            def2[:, k] = base + 0.5 * (0. + 0. + a1 + a2 + a3 + a4 + 0. + 0.)
+        elif k == 0:
+            def2[:, k] = base + 0.5 * (0. + 0.) + 0. + 0.5 * upt
+        else:
+            def2[:, k] = base + 0.5 * (0. + 0.) + 0. + 0.5 * dnt
+    Cs, Ck = f4(0.15), f4(0.1)
+    Ce = Ck * Ck * Ck / (Cs * Cs * Cs * Cs)
+    Pr = 1.
+    bsv = np.zeros((nx, nzm + 1))   # buoy_sgs_vert(0:nzm) -> index k (0 .. nzm)
+    for k in range(1, nzm):         # Fortran k = 1 .. nzm-1 : interface above level k; kb = k, kc = k+1 (1-based) -> 0-based kb = k-1, kc = k
+        b, c = k - 1, k
+        betdz = 0.5 * (bet[c] + bet[b]) / dz / adzw[k]
+        for i in range(nx):
+            tabs_i = 0.5 * (tabs[i, c] + fac_cond * qcl[i, c] + fac_sub * qci[i, c] + tabs[i, b] + fac_cond * qcl[i, b] + fac_sub * qci[i, b])
+            qtot_i = 0.5 * (qv[i, c] + qcl[i, c] + qci[i, c] + qv[i, b] + qcl[i, b] + qci[i, b])
+            qp_i = 0.5 * (qpl[i, c] + qpi[i, c] + qpl[i, b] + qpi[i, b])
+            bbb = 1. + epsv * qtot_i - qp_i
+            bs = betdz * (bbb * (t[i, c] - t[i, b]) + epsv * tabs_i * (qv[i, c] + qcl[i, c] + qci[i, c] - qv[i, b] - qcl[i, b] - qci[i, b]) +
+                          (bbb * fac_cond - tabs_i) * (qpl[i, c] - qpl[i, b]) + (bbb * fac_sub - tabs_i) * (qpi[i, c] - qpi[i, b]))
+            qctot = qcl[i, c] + qci[i, c] + qcl[i, b] + qci[i, b]
+            if qctot > 0.:
+                omn = (qcl[i, c] + qcl[i, b]) / (qctot + f4(1.e-20))
+                qsat_check = omn * qsatw(tabs_i, presi[k]) + (1. - omn) * qsati(tabs_i, presi[k])
+                if qtot_i > qsat_check:
+                    lstarn = fac_cond + (1. - omn) * fac_fus
+                    tabs_i = 0.5 * (tabs[i, c] + tabs[i, b])
+                    dqsat = omn * dtqsatw(tabs_i, presi[k]) + (1. - omn) * dtqsati(tabs_i, presi[k])
+                    qsatt = omn * qsatw(tabs_i, presi[k]) + (1. - omn) * qsati(tabs_i, presi[k])
+                    bbb = 1. + epsv * qsatt + qsatt - qtot_i - qp_i + f4(1.61) * tabs_i * dqsat
+                    bbb = bbb / (1. + lstarn * dqsat)
+                    bs = betdz * (bbb * (t[i, c] - t[i, b]) +
+                                  (bbb * lstarn - (1. + lstarn * dqsat) * tabs_i) * (qv[i, c] + qcl[i, c] + qci[i, c] - qv[i, b] - qcl[i, b] - qci[i, b]) +
+                                  (bbb * fac_cond - (1. + fac_cond * dqsat) * tabs[i, b]) * (qpl[i, c] - qpl[i, b]) +
+                                  (bbb * fac_sub - (1. + fac_sub * dqsat) * tabs[i, b]) * (qpi[i, c] - qpi[i, b]))
+            bsv[i, k] = bs
+    tk = tk.copy(); tkh = tk.copy(); tke = np.zeros((nx, nzm))
+    for k in range(nzm - 1):
+        grd = dz * adz[k]
+        Ce1 = Ce / f4(0.7) * f4(0.19); Ce2 = Ce / f4(0.7) * f4(0.51)
+        grdf_x = min(16., dx * dx / ((adz[k] * dz) * (adz[k] * dz)))
+        cx = dx ** 2 / dt / grdf_x; cy = dx ** 2 / dt / grdf_x
+        cz = (dz * min(adzw[k], adzw[k + 1])) ** 2 / dt / 1.
+        tkmax = f4(0.09) / (1. / cx + 1. / cy + 1. / cz)
+        for i in range(nx):
+            bs = 0.5 * (bsv[i, k] + bsv[i, k + 1])
+            if bs <= 0.:
+                smix = grd
+            else:
+                smix = min(grd, max(f4(0.1) * grd, math.sqrt(f4(0.76) * tk[i, k] / Ck / math.sqrt(bs + f4(1.e-10)))))
+            ratio = smix / grd
+            Cee = Ce1 + Ce2 * ratio
+            tkv = math.sqrt(Ck * Ck * Ck / Cee * max(0., def2[i, k] - Pr * bs)) * smix ** 2
+            tke[i, k] = (tkv / (Ck * smix)) ** 2
+            tkv = min(tkv, tkmax)
+            tk[i, k] = tkv; tkh[i, k] = Pr * tkv
+    return tk, tkh, tke

@@ -1,0 +1,117 @@
+"""The C++ oracle against the second, independent numpy restatement of tests/ref_numpy.py (written from the Fortran, not from the
+oracle): cloud, precip_proc (+ precip_init, sat.F90), advect_scalar2D, precip_fall, shear_prod2D + tke_full.  Two independent
+transcriptions agreeing to round-off is the strongest pin available without a Fortran compiler."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import common as cm
+import ref_numpy as rn
+
+L = cm.ob.lib()
+P = cm.pkg.abi.dptr
+
+
+def _close(a, b, tol=2e-13, floor=1e-300):
+    a = np.asarray(a, dtype=float); b = np.asarray(b, dtype=float)
+    scale = max(np.abs(a).max(), floor)
+    return np.abs(a - b).max() <= tol * scale
+
+
+def test_saturation_functions():
+    for t in np.linspace(185., 320., 136):
+        assert L.crm_oracle_esatw(float(t)) == rn.esatw(float(t)) and L.crm_oracle_esati(float(t)) == rn.esati(float(t))
+        assert L.crm_oracle_qsatw(float(t), 850.) == rn.qsatw(float(t), 850.) and L.crm_oracle_qsati(float(t), 300.) == rn.qsati(float(t), 300.)
+
+
+def test_cloud_against_second_restatement():
+    rng = np.random.default_rng(21)
+    n = 4000
+    tabs = rng.uniform(215., 305., n); pres = rng.uniform(150., 1010., n); gamaz = rng.uniform(0., 150., n)
+    qs = np.array([rn.qsatw(t, p) for t, p in zip(tabs, pres)])
+    q = qs * rng.uniform(0.2, 1.8, n); q[::17] = -1e-6
+    qp = np.where(rng.uniform(size=n) < 0.5, 0., rng.uniform(0., 3e-3, n)); qp[::23] = -1e-9
+    t = tabs + gamaz
+    q_o, qp_o, tabs_o, qn_o = q.copy(), qp.copy(), np.zeros(n), np.zeros(n)
+    assert L.crm_oracle_test_cloud(n, P(t), P(gamaz), P(pres), P(q_o), P(qp_o), P(tabs_o), P(qn_o)) == 0
+    ref = np.array([rn.cloud_cell(t[m], gamaz[m], pres[m], q[m], qp[m]) for m in range(n)])
+    assert (qn_o > 0).sum() > n // 4 and (qn_o == 0).sum() > n // 4
+    assert np.array_equal(ref[:, 0], q_o) and np.array_equal(ref[:, 1], qp_o)
+    assert _close(ref[:, 2], tabs_o, 1e-15) and _close(ref[:, 3], qn_o, 1e-12)
+
+
+def test_precip_proc_against_second_restatement():
+    rng = np.random.default_rng(22)
+    n = 4000
+    tabs = rng.uniform(215., 300., n); pres = rng.uniform(200., 1010., n); rho = pres * 100. / (287. * tabs); tabs0 = tabs + rng.uniform(-3., 3., n)
+    q = rng.uniform(1e-5, 1.5e-2, n)
+    qn = np.where(rng.uniform(size=n) < 0.5, 0., rng.uniform(0., 2.5e-3, n))
+    qp = np.where(rng.uniform(size=n) < 0.3, 0., rng.uniform(0., 3e-3, n)); qp[::29] = 5e-9
+    q_o, qp_o, qn_o, ds, de = q.copy(), qp.copy(), qn.copy(), np.zeros(n), np.zeros(n)
+    assert L.crm_oracle_test_precip_proc(n, C.c_double(10.), P(tabs), P(pres), P(rho), P(tabs0), P(q_o), P(qp_o), P(qn_o), P(ds), P(de)) == 0
+    ref = np.array([rn.precip_proc_cell(10., tabs[m], pres[m], rn.precip_coefs(rho[m], tabs0[m], pres[m]), q[m], qp[m], qn[m]) for m in range(n)])
+    assert (ds > 0).sum() > n // 5 and (de < 0).sum() > n // 10
+    for j, o in enumerate((q_o, qp_o, qn_o, ds, de)):
+        assert _close(ref[:, j], o, 5e-13), j
+
+
+def test_advect_scalar2d_against_second_restatement():
+    import test_oracle_kat as tk
+    rng = np.random.default_rng(23)
+    nx, nzm = 16, 24
+    adz = rng.uniform(0.6, 1.6, nzm); rho = np.linspace(1.15, 0.35, nzm) * rng.uniform(0.97, 1.03, nzm)
+    rhow = np.concatenate([[rho[0]], 0.5 * (rho[1:] + rho[:-1]), [rho[-1]]])
+    u, v, w = tk._nondivergent_flux(nx, 1, nzm, adz, rng, cmax=0.35)
+    u = u * rho[None, None, :] / rho.max(); w = w * rhow[None, None, :] / rho.max()
+    f0 = np.zeros((nx, 1, nzm)); f0[3:9, :, 4:11] = 1.0; f0 += 1e-3 * rng.uniform(size=f0.shape); f0[12:, :, 15:] = 0.
+    g, fadv, flux = tk._advect(nx, 1, nzm, u, v, w, rho, rhow, adz, f0)
+    f_ref, flux_ref = rn.advect_scalar2d(f0[:, 0, :].copy(), u[:, 0, :], w[:, 0, :], rho, rhow, adz)
+    assert np.abs(g[:, 0, :] - f0[:, 0, :]).max() > 1e-2          # the field really moves
+    assert _close(f_ref, g[:, 0, :], 5e-14) and _close(flux_ref, flux, 1e-12)
+    assert _close((f_ref - f0[:, 0, :]).sum(axis=0), fadv, 1e-10, floor=1e-3)
+
+
+def test_precip_fall_against_second_restatement():
+    rng = np.random.default_rng(24)
+    ncol, nzm, dz, dtn = 12, 30, 180., 10.
+    adz = np.concatenate([np.full(6, 0.35), np.linspace(0.5, 2.5, nzm - 6)])
+    z = np.cumsum(adz) * dz
+    tabs1 = 296. - 6.5e-3 * z
+    rho = 1.15 * np.exp(-z / 8000.); rhow = np.concatenate([[rho[0]], 0.5 * (rho[1:] + rho[:-1]), [rho[-1]]])
+    tabs = tabs1[None, :] + rng.uniform(-2., 2., (ncol, nzm))
+    qp = np.where(rng.uniform(size=(ncol, nzm)) < 0.6, rng.uniform(0., 4e-3, (ncol, nzm)), 0.); qp[:3] = 0.; qp[3, 10] = 5e-9
+    t = tabs + 9.8 / 1004. * z[None, :]
+    qo, to, ps = np.asfortranarray(qp.copy()), np.asfortranarray(t.copy()), np.zeros(ncol)
+    nprec = L.crm_oracle_test_precip_fall(ncol, nzm, C.c_double(dz), C.c_double(dtn), P(rho), P(rhow), P(adz), P(np.asfortranarray(tabs)), P(qo), P(to), P(ps))
+    q_ref, t_ref, ps_ref, nprec_ref = rn.precip_fall_columns(dz, dtn, rho, rhow, adz, tabs, qp, t)
+    assert nprec == nprec_ref and nprec >= 2                       # thin lowest layers: the sub-iterations are exercised
+    assert _close(q_ref, qo, 5e-13) and _close(t_ref, to, 1e-15) and _close(ps_ref, ps, 5e-13)
+
+
+def test_sgs_against_second_restatement():
+    rng = np.random.default_rng(25)
+    nx, nzm, dx, dt, dz = 16, 20, 1000., 10., 120.
+    adz = np.linspace(0.8, 2.2, nzm); adzw = np.concatenate([[1.], 0.5 * (adz[1:] + adz[:-1]), [adz[-1]]])
+    z = np.cumsum(adz) * dz
+    tabs = (295. - 6e-3 * z)[None, :] + rng.uniform(-1., 1., (nx, nzm))
+    presi = 1000. * np.exp(-np.concatenate([[0.], z]) / 8000.)
+    bet = 9.80616 / (295. - 6e-3 * z)
+    u = 5. + rng.standard_normal((nx, nzm)) * 2.; w = np.zeros((nx, nzm + 1)); w[:, 1:nzm] = rng.standard_normal((nx, nzm - 1))
+    u0 = u.mean(axis=0)
+    qs = np.array([[rn.qsatw(tabs[i, k], 0.5 * (presi[k] + presi[k + 1])) for k in range(nzm)] for i in range(nx)])
+    cloudy = rng.uniform(size=(nx, nzm)) < 0.4
+    qcl = np.where(cloudy & (tabs > 263.), rng.uniform(0., 1.5e-3, (nx, nzm)), 0.)
+    qci = np.where(cloudy & (tabs < 270.), rng.uniform(0., 4e-4, (nx, nzm)), 0.)
+    qv = qs * np.where(cloudy, 1.0, rng.uniform(0.3, 0.95, (nx, nzm)))
+    qpl = np.where(rng.uniform(size=(nx, nzm)) < 0.3, rng.uniform(0., 1e-3, (nx, nzm)), 0.); qpi = 0.3 * qpl[:, ::-1]
+    t = tabs + 9.80616 / 1004.64 * z[None, :] - rn.fac_cond * (qcl + qpl) - rn.fac_sub * (qci + qpi)
+    tk_in = rng.uniform(0., 20., (nx, nzm))
+    A = np.asfortranarray
+    tk, tkh, tke = A(tk_in.copy()), A(np.zeros((nx, nzm))), A(np.zeros((nx, nzm)))
+    rc = L.crm_oracle_test_sgs(nx, nzm, C.c_double(dx), C.c_double(dt), C.c_double(dz), P(adz), P(adzw), P(bet), P(presi), P(u0), P(A(u)), P(A(w)), P(A(t)),
+                               P(A(tabs)), P(A(qv)), P(A(qcl)), P(A(qci)), P(A(qpl)), P(A(qpi)), P(tk), P(tkh), P(tke))
+    assert rc == 0
+    tk_r, tkh_r, tke_r = rn.sgs_2d(dx, dt, dz, adz, adzw, bet, presi, u0, u, w, t, tabs, qv, qcl, qci, qpl, qpi, tk_in)
+    assert tk[:, :nzm - 1].max() > 0.1
+    assert _close(tk_r[:, :nzm - 1], tk[:, :nzm - 1], 5e-13) and _close(tkh_r[:, :nzm - 1], tkh[:, :nzm - 1], 5e-13) and _close(tke_r[:, :nzm - 1], tke[:, :nzm - 1], 5e-13)
