@@ -942,7 +942,7 @@ extern "C" long long crm_b200_debug_fetch(void *handle, const char *name, double
   std::string nm(name);
   const double *src = nullptr;
   int nk = p.nzm;
-  if (nm == "u") src = p.u; else if (nm == "v" && p.v) src = p.v; else if (nm == "dvdt" && p.v) src = p.dv_b; else if (nm == "dvdt_a" && p.v) src = p.dv_a;
+  if (nm == "u") src = p.u; else if (nm == "v" && p.v) src = p.v; else if (nm == "dvdt" && p.v) src = p.dv_b; else if (nm == "dvdt_a" && p.v) src = p.dv_a; else if (nm == "dvdt_c" && p.v) src = p.dv_c;
   else if (nm == "vmf" && p.v) src = p.vmf; else if (nm == "w") { src = p.w; nk = p.nz; } else if (nm == "t") src = p.t; else if (nm == "qt") src = p.qt;
   else if (nm == "qp") src = p.qp; else if (nm == "qn") src = p.qn; else if (nm == "tabs") src = p.tabs; else if (nm == "qv") src = p.qv;
   else if (nm == "qcl") src = p.qcl; else if (nm == "qci") src = p.qci; else if (nm == "qpl") src = p.qpl; else if (nm == "qpi") src = p.qpi;

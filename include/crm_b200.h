@@ -171,8 +171,15 @@ int crm_b200_get_stats(void *handle, crm_run_stats_t *stats);
 
 /* Test/diagnostic hook: copy an internal field, as left by the last run, into a host buffer
  * in the boundary layout (ncrms,nx,ny,nz[m]) with ld = ncrms.  Names: "u","w","t","qt","qp",
- * "qn","tabs","qv","qcl","qci","qpl","qpi","tk","tkh","tke","p","dudt","dwdt".  Returns the
- * number of doubles written, or <0 on error. */
+ * "qn","tabs","qv","qcl","qci","qpl","qpi","tk","tkh","tke", the Adams-Bashforth tendency slots
+ * "dudt","dwdt" (slot just computed), "dudt_a","dwdt_a" (na), "dudt_c","dwdt_c" (nc), the mass
+ * fluxes "umf","wmf", and for 3-D CRMs "v","dvdt","dvdt_a","dvdt_c","vmf".  (The pressure is not
+ * kept on the device: it lives in shared memory between the forward and backward solve kernels.)
+ * With the environment variable CRM_DEBUG_STOP=1..8 crm_b200_run stops inside the first sub-step
+ * after the phase of that number (forcing, sgs, momentum, pressure+adams, scalar advection,
+ * precipitation fall+uvw, scalar diffusion, microphysics) so the per-phase parity tests can fetch
+ * the intermediate state.  Returns the number of doubles written, or <0 on error
+ * (-3 unknown name, -2 buffer too small). */
 long long crm_b200_debug_fetch(void *handle, const char *name, double *host_buf, size_t n);
 
 /* Measurement hook: when on, every kernel launch of crm_b200_run is bracketed by CUDA events (this serialises the

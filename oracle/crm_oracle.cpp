@@ -703,6 +703,7 @@ extern "C" long long crm_oracle_debug_fetch(const char *name, double *buf, size_
     else if (nm == "tk") f = &c.tk; else if (nm == "tkh") f = &c.tkh; else if (nm == "tke") f = &c.tke; else if (nm == "p") f = &c.p;
     else if (nm == "dudt_a") f = &c.dudt[g_step.na]; else if (nm == "dwdt_a") f = &c.dwdt[g_step.na];
     else if (nm == "dudt_c") f = &c.dudt[g_step.nc]; else if (nm == "dwdt_c") f = &c.dwdt[g_step.nc];
+    else if (nm == "dvdt_a") f = &c.dvdt[g_step.na]; else if (nm == "dvdt_c") f = &c.dvdt[g_step.nc]; else if (nm == "dvdt") f = &c.dvdt[g_step.nb];
     else if (nm == "dudt") f = &c.dudt[g_step.nb]; else if (nm == "dwdt") f = &c.dwdt[g_step.nb];   // slot just computed (after rotation it is nb)
     else return -3;
     for (int k = 1; k <= nk; k++)

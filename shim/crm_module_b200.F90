@@ -5,7 +5,9 @@
 ! (components/cam/src/physics/cam/crm_physics.F90:1145-1156) compiles unchanged.  Build: replace crm_module.F90 by
 ! this file in the CRM Filepath and link -lcrm_b200 (see INTEGRATION.md).
 !
-! NOT compiled in the development image (no Fortran compiler there); kept deliberately trivial: it only takes the
+! NOT compiled in the development image (no Fortran compiler there or on the GPU box: profiles/r02_fortran_probe_gpu_box.txt);
+! tests/test_shim_static.py checks it statically against include/crm_b200.h (member order of every bind(C) type, every c_loc
+! target declared TARGET).  Kept deliberately trivial: it only takes the
 ! address of every member array of the derived types (c_loc) and forwards the hidden module inputs of the
 ! reference routine (phys_grid lookups, get_nstep, crmdims constants, accelerate_crm namelist) explicitly.
 ! The derived types are the reference's own, unmodified (crm_input_module, crm_state_module, crm_rad_module,
@@ -54,6 +56,9 @@ module crm_module
     type(c_ptr) :: flux_qt, fluxsgs_qt, tkez, tkesgsz, tkz, flux_u, flux_v, flux_qp, precflux
     type(c_ptr) :: qt_ls, qt_trans, qp_trans, qp_fall, qp_src, qp_evp, t_ls
     type(c_ptr) :: ultend, vltend   ! SPMOMTRANS builds only, else c_null_ptr (ABI >= 2)
+    type(c_ptr) :: wvar, aut, acc, evpc, evpr, mlt, sub, dep, con                       ! m2005 builds only (ABI >= 3)
+    type(c_ptr) :: nc_mean, ni_mean, ns_mean, ng_mean, nr_mean
+    type(c_ptr) :: aut_a, acc_a, evpc_a, evpr_a, mlt_a, sub_a, dep_a, con_a
   end type
 
   interface
@@ -98,7 +103,8 @@ contains
     integer , intent(in   ) :: icol(ncrms)
     integer , intent(in   ) :: plev
     real(r8), intent(in   ) :: dt_gl
-    type(crm_input_type),         intent(in   ) :: crm_input
+    type(crm_input_type), target, intent(in   ) :: crm_input        ! TARGET: c_loc() of its members (the caller's actual argument
+                                                                    ! needs no change: the interface is explicit, module procedure)
     type(crm_state_type), target, intent(inout) :: crm_state
     type(crm_rad_type),   target, intent(inout) :: crm_rad
     type(crm_ecpp_output_type),   intent(inout) :: crm_ecpp_output      ! untouched (no -DECPP)
@@ -206,6 +212,22 @@ contains
     co%ultend = c_loc(crm_output%ultend);  co%vltend = c_loc(crm_output%vltend)
 #else
     co%ultend = c_null_ptr;  co%vltend = c_null_ptr
+#endif
+
+    co%wvar = c_null_ptr; co%aut = c_null_ptr; co%acc = c_null_ptr; co%evpc = c_null_ptr; co%evpr = c_null_ptr
+    co%mlt = c_null_ptr; co%sub = c_null_ptr; co%dep = c_null_ptr; co%con = c_null_ptr
+    co%nc_mean = c_null_ptr; co%ni_mean = c_null_ptr; co%ns_mean = c_null_ptr; co%ng_mean = c_null_ptr; co%nr_mean = c_null_ptr
+    co%aut_a = c_null_ptr; co%acc_a = c_null_ptr; co%evpc_a = c_null_ptr; co%evpr_a = c_null_ptr
+    co%mlt_a = c_null_ptr; co%sub_a = c_null_ptr; co%dep_a = c_null_ptr; co%con_a = c_null_ptr
+#ifdef m2005
+    co%wvar = c_loc(crm_output%wvar);  co%aut = c_loc(crm_output%aut);  co%acc = c_loc(crm_output%acc)     ! crm_output_module.F90:22-31
+    co%evpc = c_loc(crm_output%evpc);  co%evpr = c_loc(crm_output%evpr);  co%mlt = c_loc(crm_output%mlt)
+    co%sub = c_loc(crm_output%sub);  co%dep = c_loc(crm_output%dep);  co%con = c_loc(crm_output%con)
+    co%nc_mean = c_loc(crm_output%nc_mean);  co%ni_mean = c_loc(crm_output%ni_mean);  co%ns_mean = c_loc(crm_output%ns_mean)   ! :60-74
+    co%ng_mean = c_loc(crm_output%ng_mean);  co%nr_mean = c_loc(crm_output%nr_mean)
+    co%aut_a = c_loc(crm_output%aut_a);  co%acc_a = c_loc(crm_output%acc_a);  co%evpc_a = c_loc(crm_output%evpc_a)
+    co%evpr_a = c_loc(crm_output%evpr_a);  co%mlt_a = c_loc(crm_output%mlt_a);  co%sub_a = c_loc(crm_output%sub_a)
+    co%dep_a = c_loc(crm_output%dep_a);  co%con_a = c_loc(crm_output%con_a)
 #endif
 
     rc = crm_b200_run(handle, d, ci, cs, cr, co)

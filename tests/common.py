@@ -63,3 +63,38 @@ def compare_all(dims, res_o, res_g, tol, abs_floor=1e-18, skip=()):
         if err > tol and err * scale > abs_floor:
             bad.append((name, err, scale))
     return bad
+
+
+# fields compared after each CRM_DEBUG_STOP phase: (oracle name, device name).  After phase 6 the device has already rotated the
+# roles of the u / AB-slot buffers (uvw.F90 is a pointer rotation there), the oracle rotates at the end of the sub-step.
+PHASE_FIELDS = {
+    1: [("dudt_a", "dudt_a"), ("dwdt_a", "dwdt_a"), ("t", "t"), ("qt", "qt"), ("qp", "qp")],            # zero .. damping, ice_fall
+    2: [("tk", "tk"), ("tkh", "tkh"), ("tke", "tke")],                                                   # shear_prod + tke_full
+    3: [("dudt_a", "dudt_a"), ("dwdt_a", "dwdt_a")],                                                     # advect_mom + sgs_mom
+    4: [("dudt_a", "dudt_a"), ("dwdt_a", "dwdt_a"), ("dudt_c", "dudt_c"), ("dwdt_c", "dwdt_c")],         # pressure + adams
+    5: [("t", "t"), ("qt", "qt"), ("qp", "qp")],                                                         # advect_all_scalars
+    6: [("t", "t"), ("qp", "qp"), ("dudt_c", "u"), ("dwdt_c", "w"), ("dudt_a", "dudt"), ("dwdt_a", "dwdt")],   # precip_fall, uvw
+    7: [("t", "t"), ("qt", "qt"), ("qp", "qp")],                                                         # sgs_scalars
+    8: [("t", "t"), ("qt", "qt"), ("qp", "qp"), ("qn", "qn"), ("tabs", "tabs"), ("qv", "qv"), ("qcl", "qcl"), ("qci", "qci"),
+        ("qpl", "qpl"), ("qpi", "qpi"), ("u", "u"), ("w", "w"), ("dudt", "dudt"), ("dwdt", "dwdt")],     # micro_proc + diagnose
+}
+PHASE_FIELDS_3D = {1: [("dvdt_a", "dvdt_a")], 3: [("dvdt_a", "dvdt_a")], 4: [("dvdt_a", "dvdt_a"), ("dvdt_c", "dvdt_c")],
+                   6: [("dvdt_c", "v"), ("dvdt_a", "dvdt")], 8: [("v", "v"), ("dvdt", "dvdt")]}
+
+
+def phase_errors(dims, inp, st, rad, stop, lib_path=None):
+    """Run oracle and device with CRM_DEBUG_STOP=stop (both stop inside the first sub-step after that phase) and return
+    [(field, rel. error, scale)] of the intermediate fields of that phase."""
+    os.environ["CRM_DEBUG_STOP"] = str(stop)
+    try:
+        ob.run(dims, inp, st.copy(), rad.copy())
+        h = libmod.CrmHandle(dims, lib_path=lib_path)
+        h.run(dims, inp, st.copy(), rad.copy())
+        res = []
+        for no, ng in PHASE_FIELDS[stop] + (PHASE_FIELDS_3D.get(stop, []) if dims.ny > 1 else []):
+            a, b = ob.debug_fetch(no, dims), h.debug_fetch(ng)
+            res.append((no,) + rel_err(a, b, dims.ncrms))
+        h.close()
+    finally:
+        del os.environ["CRM_DEBUG_STOP"]
+    return res

@@ -89,3 +89,20 @@ def test_emu_m2005_two_moment_microphysics(emu):
     dims = cm.pkg.CrmDims(ncrms=5, nx=8, ny=1, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=20.0 * 3, igstep=3, micro=1)
     ro, rg = _check(emu, dims, 90, 1e-11)
     assert ro[2].qs_mean.max() > 0 and ro[2].nc_mean.max() > 0 and ro[0].qr.max() > 0   # rain, snow and droplets exist: the scheme is exercised
+
+
+@pytest.mark.parametrize("stop", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_emu_per_phase_intermediate_state(emu, stop):
+    """CRM_DEBUG_STOP: oracle and device code stop after the same phase of the first sub-step; the intermediate fields of that phase
+    (tendency slots, eddy coefficients, advected / diffused scalars, microphysics diagnostics) agree to 1e-12 of the field maximum."""
+    dims, inp, st, rad = cm.make_case(cm.small_dims(ncrms=5, nx=8, nsteps=1), spinup_steps=90)
+    for name, err, scale in cm.phase_errors(dims, inp, st, rad, stop, lib_path=emu):
+        assert err <= 1e-12 or err * scale < 1e-18, (stop, name, err, scale)
+
+
+@pytest.mark.parametrize("stop", [1, 3, 4, 6, 8])
+def test_emu_per_phase_intermediate_state_3d(emu, stop):
+    dims = cm.pkg.CrmDims(ncrms=2, nx=8, ny=8, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=20.0, igstep=3, nx_rad=2, ny_rad=2)
+    dims, inp, st, rad = cm.make_case(dims, spinup_steps=40)
+    for name, err, scale in cm.phase_errors(dims, inp, st, rad, stop, lib_path=emu):
+        assert err <= 1e-12 or err * scale < 1e-18, (stop, name, err, scale)
