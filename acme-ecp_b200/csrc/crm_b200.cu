@@ -310,6 +310,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
     if (const char *e = getenv("CRM_B200_M2005_CHUNK")) { int v = atoi(e); if (v >= 1) chunk = v; }
     if (chunk < 1) chunk = 1;
     if (chunk > (size_t)h->ntiles) chunk = h->ntiles;
+    while (chunk > 1 && per_tile / 8 * chunk >= ((size_t)1 << 32)) chunk--;   // 32-bit element index of the work-space accessor
     h->m25_chunk = (int)chunk;
     h->m25_scr = carve<double>(h, per_tile / 8 * chunk); ok = ok && h->m25_scr;
     h->esum2 = carve<double>(h, (size_t)CRM_M25_NESUM * h->prof_elems); ok = ok && h->esum2;
@@ -351,7 +352,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
 #define PRESS_ATTR(NXV) BIG((k_p4_press_fwd<NXV, 0>)); BIG((k_p5_press_bwd<NXV, 0>));
     PRESS_ATTR(8) PRESS_ATTR(16) PRESS_ATTR(32) PRESS_ATTR(64) PRESS_ATTR(128) PRESS_ATTR(256)
     BIG((k_p4_press_fwd<32, 32>)); BIG((k_p5_press_bwd<32, 32>)); BIG((k_p4_press_fwd<64, 64>)); BIG((k_p5_press_bwd<64, 64>));
-    BIG(k_diffuse_set<0>); BIG(k_diffuse_set<32>); BIG(k_diffuse_set<64>); BIG(k_diffuse_set<CRM_G3D>); BIG(k_m2005_column); BIG(k_m2005_epi_sums);
+    BIG(k_diffuse_set<0>); BIG(k_diffuse_set<32>); BIG(k_diffuse_set<64>); BIG(k_diffuse_set<CRM_G3D>); BIG(k_m2005_scatter); BIG(k_m2005_epi_sums);
     if (h->m25) {
       m2005::Const mc;
       m2005::graupel_init(mc, CRM_RGAS, CRM_RV, CRM_CP, CRM_LCOND, CRM_LSUB);
@@ -699,7 +700,9 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
       if (m25) {   // micro_proc (column scheme, chunk by chunk) + diagnose; ice_fall of the next sub-step is a no-op: kmin > kmax
         for (int t0 = 0; t0 < ntiles; t0 += h->m25_chunk) {
           const int nt = std::min(h->m25_chunk, ntiles - t0);
-          LAUNCH(h, k_m2005_column, nt, P, red_bytes(5), p, h->m25_scr, t0, nt);
+          const int nb = (int)(((long long)nt * P + CRM_M25_COLS - 1) / CRM_M25_COLS);
+          LAUNCH(h, k_m2005_column<CRM_M25_MINB>, nb, CRM_M25_COLS, 0, p, h->m25_scr, t0, nt);
+          LAUNCH(h, k_m2005_scatter, nt, P, red_bytes(5), p, h->m25_scr, t0, nt);
         }
         LAUNCH_G(h, k_p8_micro, ntiles * ((nzm + CRM_P8_NL - 1) / CRM_P8_NL), P, smem_p8, p, 0, 1);
         LAUNCH(h, k_reset_kminmax, slot_blocks, 128, 0, p);

@@ -18,27 +18,37 @@ static m2005::Const c_m25;
 __constant__ m2005::Const c_m25;
 #endif
 
-struct M25Col {   // work-space accessor of one thread: a(id, k), k = 1..nz
-  double *s; size_t n; int nz; size_t col;
-  __device__ __forceinline__ double &operator()(int id, int k) { return s[((size_t)id * nz + (k - 1)) * n + col]; }
+struct M25Col {   // work-space accessor of one thread: a(id, k), k = 1..nz; 32-bit element index (the host sizes a chunk below 2^32 doubles)
+  double *s; unsigned n; int nz; unsigned col;
+  __device__ __forceinline__ double &operator()(int id, int k) { return s[(unsigned)(id * nz + (k - 1)) * n + col]; }
 };
 
-// grid: ntiles_chunk blocks of P threads (block = tile tile0 + blockIdx.x); scr: NARR*nzm*(ntiles_chunk*P) doubles.
-// smem: CRM_RED_DOUBLES(5, P, CT) doubles.
-__global__ void __launch_bounds__(CRM_MAX_P3) k_m2005_column(CrmP p, double *scr, int tile0, int ntiles_chunk) {
+// Column scheme: ONE THREAD PER COLUMN with a block size that is independent of the tile shape (CRM_M25_COLS threads, up to 255
+// registers: the scheme holds ~100 live doubles per level), columns numbered c = (tile - tile0) * P + cell*CT + lane over the chunk
+// of tiles [tile0, tile0 + ntiles_chunk).  scr: NARR*nzm*(ntiles_chunk*P) doubles.  Results stay in the work space; k_m2005_scatter
+// (one block per tile) writes them back to the fields and forms the slab sums.
+#define CRM_M25_COLS 128
+// resident blocks per SM asked from the compiler (register budget 65536 / (128 * MINB)); measured on B200 at 23 680 CRMs of cfg 3
+// (profiles/r02e_m2005_column_tuning.md): MINB 1 (255 regs) 26.2 ms/launch, 3 (168) 22.3, 4 (128) 20.6, 6 (80) 19.4, 8 (64) 28.5 (before the
+// out-of-line helpers): the kernel is bound by instruction issue and instruction-cache misses, occupancy hides both
+#define CRM_M25_MINB 6
+template <int MINB>
+__global__ void __launch_bounds__(CRM_M25_COLS, MINB) k_m2005_column(CrmP p, double *scr, int tile0, int ntiles_chunk) {
   using namespace m2005;
-  const int tid = threadIdx.x, tile = tile0 + blockIdx.x, P = p.P, CT = p.CT;
+  const int P = p.P, CT = p.CT;
+  const long long c = (long long)blockIdx.x * CRM_M25_COLS + threadIdx.x;
+  if (c >= (long long)ntiles_chunk * P) return;
+  const int tl = (int)(c / P), tid = (int)(c - (long long)tl * P), tile = tile0 + tl;
   const int i = tid / CT, lane = tid - i * CT;
+  (void)i;
   const long long fb = (long long)tile * p.tstride;
   const int pb = tile * p.nzp * CT + lane;
   const int cb = tile * CT + lane;
-  CRM_DYN_SMEM(double, red);
   const int nzm = p.nzm;
-  M25Col a; a.s = scr; a.n = (size_t)ntiles_chunk * P; a.nz = nzm; a.col = (size_t)blockIdx.x * P + tid;
+  M25Col a; a.s = scr; a.n = (unsigned)(ntiles_chunk * P); a.nz = nzm; a.col = (unsigned)c;
   const double dtn = p.dtn, dz = p.dz[cb];
   for (int k = 1; k <= nzm; k++) {
     const double qr = F3(p.mf[3], k), qi = F3(p.mf[5], k), qs = F3(p.mf[7], k), qg = F3(p.mf[9], k);
-    a(QV, k) = F3(p.qt, k);
     a(NC, k) = F3(p.mf[2], k); a(QR, k) = qr; a(NR, k) = F3(p.mf[4], k); a(QI, k) = qi; a(NI, k) = F3(p.mf[6], k);
     a(QNI, k) = qs; a(NS, k) = F3(p.mf[8], k); a(QG, k) = qg; a(NG, k) = F3(p.mf[10], k);
     double tabs = F3(p.t, k) - PF(p.gamaz, k) + CRM_FAC_COND * (qr) + CRM_FAC_SUB * (qi + qs + qg);
@@ -49,7 +59,7 @@ __global__ void __launch_bounds__(CRM_MAX_P3) k_m2005_column(CrmP p, double *scr
     const double pres = R4(100.) * PF(p.pres, k);
     a(PRES, k) = pres;
     a(RHO, k) = PF(p.rho, k);
-    double qv = a(QV, k), qc = 0.;
+    double qv = F3(p.qt, k), qc = 0.;
     satadj_liquid(c_m25, tabs, qv, qc, pres);
     a(T3, k) = tabs; a(QV, k) = qv; a(QC, k) = qc;
   }
@@ -60,6 +70,20 @@ __global__ void __launch_bounds__(CRM_MAX_P3) k_m2005_column(CrmP p, double *scr
     p.precsfc[c2] = p.precsfc[c2] + sfcpcp / dz;
     p.precssfc[c2] = p.precssfc[c2] + sfcicepcp / dz;
   }
+}
+
+// grid: ntiles_chunk blocks of P threads (block = tile tile0 + blockIdx.x).  smem: CRM_RED_DOUBLES(5, P, CT) doubles.
+__global__ void __launch_bounds__(CRM_MAX_P3) k_m2005_scatter(CrmP p, double *scr, int tile0, int ntiles_chunk) {
+  using namespace m2005;
+  const int tid = threadIdx.x, tile = tile0 + blockIdx.x, P = p.P, CT = p.CT;
+  const int i = tid / CT, lane = tid - i * CT;
+  const long long fb = (long long)tile * p.tstride;
+  const int pb = tile * p.nzp * CT + lane;
+  const int cb = tile * CT + lane;
+  CRM_DYN_SMEM(double, red);
+  const int nzm = p.nzm;
+  M25Col a; a.s = scr; a.n = (unsigned)(ntiles_chunk * P); a.nz = nzm; a.col = (unsigned)(blockIdx.x * P + tid);
+  const double dtn = p.dtn, dz = p.dz[cb];
   for (int k = 1; k <= nzm; k++) {
     const int rid[8] = {AUT, ACC, EVPC, EVPR, MLT, SUB, DEP, CON};
 #pragma unroll

@@ -18,10 +18,30 @@
 
 #ifdef __CUDACC__
 #define M25_HD __host__ __device__
+#define M25_NI __noinline__   // the big helpers are called out of line: the column kernel's code size decides its instruction-cache behaviour
 #else
 #define M25_HD
+#define M25_NI
 #endif
 #define F4(x) ((double)(x##f))
+// x**y of the scheme (positive bases, real exponents).  Host builds (oracle, emulator): libm pow.  Device: ONE out-of-line copy of
+// exp(y*log(x)) instead of 125 inlined copies of CUDA's pow (each ~250 instructions: 52 % of the kernel's instructions and an
+// instruction-cache footprint that stalled the schedulers 31 % of the time); relative error <= (|y ln x| + 2) * 2^-53 ~ 1e-14.
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ double m25_pow_dev(double x, double y) {
+  if (y == 0.) return 1.;
+  return exp(y * log(x));
+}
+__device__ __noinline__ double m25_exp_dev(double x) { return exp(x); }
+__device__ __noinline__ double m25_log_dev(double x) { return log(x); }
+#define M25_POW(x, y) m25_pow_dev(x, y)
+#define M25_EXP(x) m25_exp_dev(x)
+#define M25_LOG(x) m25_log_dev(x)
+#else
+#define M25_POW(x, y) pow(x, y)
+#define M25_EXP(x) exp(x)
+#define M25_LOG(x) log(x)
+#endif
 
 namespace m2005 {
 
@@ -53,7 +73,7 @@ struct Const {   // GRAUPEL_INIT (module_mp_graupel.F90:346-758)
 };
 
 // POLYSVP (module_mp_graupel.F90:5614-5681): Flatau et al. polynomials (coefficients REAL(4) literals), result REAL(4)
-M25_HD inline double polysvp(double T, int type) {
+M25_HD M25_NI inline double polysvp(double T, int type) {
   double dt = T - F4(273.16);
   if (dt < F4(-80.)) dt = F4(-80.);
   double p;
@@ -68,7 +88,7 @@ M25_HD inline double polysvp(double T, int type) {
 }
 
 // GAMMA (module_mp_graupel.F90:5685-5916): W. J. Cody's algorithm with REAL(4) DATA constants, result REAL(4)
-M25_HD inline double gamma_f(double X, double PI, double SQRTPI) {
+M25_HD M25_NI inline double gamma_f(double X, double PI, double SQRTPI) {
   const double ONE = 1., HALF = 0.5, TWELVE = 12., TWO = 2., ZERO = 0.;
   const double XBIG = F4(35.040E0), XMININ = F4(1.18E-38), EPS = F4(1.19E-7), XINF = F4(3.4E38);
   const double P[8] = {F4(-1.71618513886549492533811E+0), F4(2.47656508055759199108314E+1), F4(-3.79804256470945635097577E+2),
@@ -110,8 +130,8 @@ M25_HD inline double gamma_f(double X, double PI, double SQRTPI) {
       double SUM = C[6];
       for (int I = 0; I < 6; I++) SUM = SUM / YSQ + C[I];
       SUM = SUM / Y - Y + SQRTPI;
-      SUM = SUM + (Y - HALF) * log(Y);
-      RES = exp(SUM);
+      SUM = SUM + (Y - HALF) * M25_LOG(Y);
+      RES = M25_EXP(SUM);
     } else return (double)(float)XINF;
   }
   if (parity) RES = -RES;
@@ -120,8 +140,8 @@ M25_HD inline double gamma_f(double X, double PI, double SQRTPI) {
 }
 
 // DERF1 (module_mp_graupel.F90:5919-6030), REAL(4) DATA coefficients, result REAL(4)
-M25_HD inline double derf1(double X) {
-  const double A[65] = {
+M25_HD M25_NI inline double derf1(double X) {
+  static constexpr double A[65] = {
       F4(0.00000000005958930743E0), F4(-0.00000000113739022964E0), F4(0.00000001466005199839E0), F4(-0.00000016350354461960E0),
       F4(0.00000164610044809620E0), F4(-0.00001492559551950604E0), F4(0.00012055331122299265E0), F4(-0.00085483269811296660E0),
       F4(0.00522397762482322257E0), F4(-0.02686617064507733420E0), F4(0.11283791670954881569E0), F4(-0.37612638903183748117E0),
@@ -142,7 +162,7 @@ M25_HD inline double derf1(double X) {
       F4(0.00000005011915876293E0), F4(-0.00000048722516178974E0), F4(0.00000430683284629395E0), F4(-0.00003445026145385764E0),
       F4(0.00024879276133931664E0), F4(-0.00162940941748079288E0), F4(0.00988786373932350462E0), F4(-0.05962426839442303805E0),
       F4(0.49766113250947636708E0)};
-  const double B[65] = {
+  static constexpr double B[65] = {
       F4(-0.00000000029734388465E0), F4(0.00000000269776334046E0), F4(-0.00000000640788827665E0), F4(-0.00000001667820132100E0),
       F4(-0.00000021854388148686E0), F4(0.00000266246030457984E0), F4(0.00001612722157047886E0), F4(-0.00025616361025506629E0),
       F4(0.00015380842432375365E0), F4(0.00815533022524927908E0), F4(-0.01402283663896319337E0), F4(-0.19746892495383021487E0),
@@ -222,10 +242,10 @@ inline void graupel_init(Const &c, double rgas, double rv, double cp, double lco
   // micro_setparm (microphysics.F90:412-440): two log-normal aerosol modes, um -> m, cm-3 -> m-3
   c.RM1 = F4(1.e-6) * F4(0.052); c.SIG1 = F4(2.04); c.NANEW1 = F4(1.e6) * (double)2500;
   c.RM2 = F4(1.e-6) * F4(1.3); c.SIG2 = F4(2.5); c.NANEW2 = F4(1.e6) * F4(1.8);
-  c.F11 = F4(0.5) * exp(F4(2.5) * (log(c.SIG1) * log(c.SIG1)));
-  c.F21 = F4(1.) + F4(0.25) * log(c.SIG1);
-  c.F12 = F4(0.5) * exp(F4(2.5) * (log(c.SIG2) * log(c.SIG2)));
-  c.F22 = F4(1.) + F4(0.25) * log(c.SIG2);
+  c.F11 = F4(0.5) * M25_EXP(F4(2.5) * (M25_LOG(c.SIG1) * M25_LOG(c.SIG1)));
+  c.F21 = F4(1.) + F4(0.25) * M25_LOG(c.SIG1);
+  c.F12 = F4(0.5) * M25_EXP(F4(2.5) * (M25_LOG(c.SIG2) * M25_LOG(c.SIG2)));
+  c.F22 = F4(1.) + F4(0.25) * M25_LOG(c.SIG2);
   double *C = c.CONS;
   C[0] = 0.;
   C[1] = G_(F4(1.) + c.DS) * c.CS;
@@ -242,7 +262,7 @@ inline void graupel_init(Const &c, double rgas, double rv, double cp, double lco
   C[12] = G_(F4(1.) + c.DI) * c.CI;
   C[13] = G_(c.BS + F4(3.)) * c.PI / F4(4.) * c.ECI;
   C[14] = G_(c.BG + F4(3.)) * c.PI / F4(4.) * c.ECI;
-  C[15] = F4(-1108.) * c.EII * pow(c.PI, (F4(1.) - c.BS) / F4(3.)) * pow(c.RHOSN, (F4(-2.) - c.BS) / F4(3.)) / (double)(4.f * 720.f);
+  C[15] = F4(-1108.) * c.EII * M25_POW(c.PI, (F4(1.) - c.BS) / F4(3.)) * M25_POW(c.RHOSN, (F4(-2.) - c.BS) / F4(3.)) / (double)(4.f * 720.f);
   C[16] = G_(c.BI + F4(3.)) * c.PI / F4(4.) * c.ECI;
   C[17] = (double)(4.f * 2.f * 3.f) * c.RHOSU * c.PI * c.ECI * c.ECI * G_(F4(2.) * c.BS + F4(2.)) / (F4(8.) * (c.RHOG - c.RHOSN));
   C[18] = c.RHOSN * c.RHOSN;
@@ -317,16 +337,16 @@ M25_HD inline double activate2(const Cn &c, double DUM, double T, double EVS, do
   const double ALPHA = c.G * c.MW * c.XXLV / (c.CP * c.RR * (T * T)) - c.G * c.MA / (c.RR * T);
   const double GAMM = c.RR * T / (EVS * c.MW) + c.MW * (c.XXLV * c.XXLV) / (c.CP * PRES_ * c.MA * T);
   const double GG = F4(1.) / (c.RHOW * c.RR * T / (EVS * DV * c.MW) + c.XXLV * c.RHOW / (KAP * T) * (c.XXLV * c.MW / (T * c.RR) - F4(1.)));
-  const double PSI = (double)(2.f / 3.f) * pow(ALPHA * DUM / GG, F4(0.5)) * AACT;
-  const double ETA1 = pow(ALPHA * DUM / GG, F4(1.5)) / (F4(2.) * c.PI * c.RHOW * GAMM * c.NANEW1);
-  const double ETA2 = pow(ALPHA * DUM / GG, F4(1.5)) / (F4(2.) * c.PI * c.RHOW * GAMM * c.NANEW2);
-  const double SM1 = F4(2.) / pow(c.BACT, F4(0.5)) * pow(AACT / (F4(3.) * c.RM1), F4(1.5));
-  const double SM2 = F4(2.) / pow(c.BACT, F4(0.5)) * pow(AACT / (F4(3.) * c.RM2), F4(1.5));
-  double DUM1 = F4(1.) / (SM1 * SM1) * (c.F11 * pow(PSI / ETA1, F4(1.5)) + c.F21 * pow((SM1 * SM1) / (ETA1 + F4(3.) * PSI), F4(0.75)));
-  double DUM2 = F4(1.) / (SM2 * SM2) * (c.F12 * pow(PSI / ETA2, F4(1.5)) + c.F22 * pow((SM2 * SM2) / (ETA2 + F4(3.) * PSI), F4(0.75)));
-  const double SMAX = F4(1.) / pow(DUM1 + DUM2, F4(0.5));
-  const double UU1 = F4(2.) * log(SM1 / SMAX) / (F4(4.242) * log(c.SIG1));
-  const double UU2 = F4(2.) * log(SM2 / SMAX) / (F4(4.242) * log(c.SIG2));
+  const double PSI = (double)(2.f / 3.f) * M25_POW(ALPHA * DUM / GG, F4(0.5)) * AACT;
+  const double ETA1 = M25_POW(ALPHA * DUM / GG, F4(1.5)) / (F4(2.) * c.PI * c.RHOW * GAMM * c.NANEW1);
+  const double ETA2 = M25_POW(ALPHA * DUM / GG, F4(1.5)) / (F4(2.) * c.PI * c.RHOW * GAMM * c.NANEW2);
+  const double SM1 = F4(2.) / M25_POW(c.BACT, F4(0.5)) * M25_POW(AACT / (F4(3.) * c.RM1), F4(1.5));
+  const double SM2 = F4(2.) / M25_POW(c.BACT, F4(0.5)) * M25_POW(AACT / (F4(3.) * c.RM2), F4(1.5));
+  double DUM1 = F4(1.) / (SM1 * SM1) * (c.F11 * M25_POW(PSI / ETA1, F4(1.5)) + c.F21 * M25_POW((SM1 * SM1) / (ETA1 + F4(3.) * PSI), F4(0.75)));
+  double DUM2 = F4(1.) / (SM2 * SM2) * (c.F12 * M25_POW(PSI / ETA2, F4(1.5)) + c.F22 * M25_POW((SM2 * SM2) / (ETA2 + F4(3.) * PSI), F4(0.75)));
+  const double SMAX = F4(1.) / M25_POW(DUM1 + DUM2, F4(0.5));
+  const double UU1 = F4(2.) * M25_LOG(SM1 / SMAX) / (F4(4.242) * M25_LOG(c.SIG1));
+  const double UU2 = F4(2.) * M25_LOG(SM2 / SMAX) / (F4(4.242) * M25_LOG(c.SIG2));
   DUM1 = c.NANEW1 / F4(2.) * (F4(1.) - derf1(UU1));
   DUM2 = c.NANEW2 / F4(2.) * (F4(1.) - derf1(UU2));
   DUM2 = (DUM1 + DUM2) / RHO_;
@@ -384,9 +404,9 @@ M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, doub
     if (QNI3D < QSMALL) { QV3D = QV3D + QNI3D; T3D = T3D - QNI3D * XXLS / CPM; QNI3D = 0.; NS3D = 0.; }
     if (QG3D < QSMALL) { QV3D = QV3D + QG3D; T3D = T3D - QG3D * XXLS / CPM; QG3D = 0.; NG3D = 0.; }
     a(SQR, K) = 0.; a(SQI, K) = 0.; a(SQNI, K) = 0.; a(SQC, K) = 0.; a(SQG, K) = 0.;
-    const double MU = F4(1.496E-6) * pow(T3D, F4(1.5)) / (T3D + F4(120.));
-    double DUM = pow(RHOSU / RHOK, F4(0.54));
-    const double AIN = pow(RHOSU / RHOK, F4(0.35)) * c.AI;
+    const double MU = F4(1.496E-6) * M25_POW(T3D, F4(1.5)) / (T3D + F4(120.));
+    double DUM = M25_POW(RHOSU / RHOK, F4(0.54));
+    const double AIN = M25_POW(RHOSU / RHOK, F4(0.35)) * c.AI;
     const double ARN = DUM * c.AR, ASN = DUM * c.AS;
     const double ACN = c.G * RHOW / (F4(18.) * MU);
     const double AGN = DUM * c.AG;
@@ -399,7 +419,7 @@ M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, doub
     }
     if (!skip200) {
       const double KAP = F4(1.414E3) * MU;
-      const double DV = F4(8.794E-5) * pow(T3D, F4(1.81)) / PRESK;
+      const double DV = F4(8.794E-5) * M25_POW(T3D, F4(1.81)) / PRESK;
       const double SC = MU / (RHOK * DV);
       DUM = (RV * (T3D * T3D));
       DQSDT = XXLV * QVS / DUM;
@@ -409,7 +429,7 @@ M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, doub
       // size-distribution parameters shared by both temperature branches
       auto rain_dist = [&]() {
         if (QR3D >= QSMALL) {
-          LAMR = pow(PI * RHOW * NR3D / QR3D, third);
+          LAMR = M25_POW(PI * RHOW * NR3D / QR3D, third);
           N0RR = NR3D * LAMR;
           if (LAMR < c.LAMMINR) { LAMR = c.LAMMINR; N0RR = p4_(LAMR) * QR3D / (PI * RHOW); NR3D = N0RR / LAMR; }
           else if (LAMR > c.LAMMAXR) { LAMR = c.LAMMAXR; N0RR = p4_(LAMR) * QR3D / (PI * RHOW); NR3D = N0RR / LAMR; }
@@ -421,45 +441,45 @@ M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, doub
           PGAM = F4(1.) / (PGAM * PGAM) - F4(1.);
           PGAM = mx_(PGAM, 2.);
           PGAM = mn_(PGAM, 10.);
-          LAMC = pow(CONS[26] * NC3D * GAM(PGAM + F4(4.)) / (QC3D * GAM(PGAM + F4(1.))), third);
+          LAMC = M25_POW(CONS[26] * NC3D * GAM(PGAM + F4(4.)) / (QC3D * GAM(PGAM + F4(1.))), third);
           const double LAMMIN = (PGAM + F4(1.)) / F4(60.E-6), LAMMAX = (PGAM + F4(1.)) / F4(1.E-6);
           if (LAMC < LAMMIN) {
             LAMC = LAMMIN;
-            NC3D = exp(F4(3.) * log(LAMC) + log(QC3D) + log(GAM(PGAM + F4(1.))) - log(GAM(PGAM + F4(4.)))) / CONS[26];
+            NC3D = M25_EXP(F4(3.) * M25_LOG(LAMC) + M25_LOG(QC3D) + M25_LOG(GAM(PGAM + F4(1.))) - M25_LOG(GAM(PGAM + F4(4.)))) / CONS[26];
           } else if (LAMC > LAMMAX) {
             LAMC = LAMMAX;
-            NC3D = exp(F4(3.) * log(LAMC) + log(QC3D) + log(GAM(PGAM + F4(1.))) - log(GAM(PGAM + F4(4.)))) / CONS[26];
+            NC3D = M25_EXP(F4(3.) * M25_LOG(LAMC) + M25_LOG(QC3D) + M25_LOG(GAM(PGAM + F4(1.))) - M25_LOG(GAM(PGAM + F4(4.)))) / CONS[26];
           }
         }
       };
       auto snow_dist = [&]() {
         if (QNI3D >= QSMALL) {
-          LAMS = pow(CONS[1] * NS3D / QNI3D, F4(1.) / DS);
+          LAMS = M25_POW(CONS[1] * NS3D / QNI3D, F4(1.) / DS);
           N0S = NS3D * LAMS;
-          if (LAMS < c.LAMMINS) { LAMS = c.LAMMINS; N0S = pow(LAMS, DS + F4(1.)) * QNI3D / CONS[1]; NS3D = N0S / LAMS; }
-          else if (LAMS > c.LAMMAXS) { LAMS = c.LAMMAXS; N0S = pow(LAMS, DS + F4(1.)) * QNI3D / CONS[1]; NS3D = N0S / LAMS; }
+          if (LAMS < c.LAMMINS) { LAMS = c.LAMMINS; N0S = M25_POW(LAMS, DS + F4(1.)) * QNI3D / CONS[1]; NS3D = N0S / LAMS; }
+          else if (LAMS > c.LAMMAXS) { LAMS = c.LAMMAXS; N0S = M25_POW(LAMS, DS + F4(1.)) * QNI3D / CONS[1]; NS3D = N0S / LAMS; }
         }
       };
       auto graupel_dist = [&]() {
         if (QG3D >= QSMALL) {
-          LAMG = pow(CONS[2] * NG3D / QG3D, F4(1.) / DG);
+          LAMG = M25_POW(CONS[2] * NG3D / QG3D, F4(1.) / DG);
           N0G = NG3D * LAMG;
-          if (LAMG < c.LAMMING) { LAMG = c.LAMMING; N0G = pow(LAMG, DG + F4(1.)) * QG3D / CONS[2]; NG3D = N0G / LAMG; }
-          else if (LAMG > c.LAMMAXG) { LAMG = c.LAMMAXG; N0G = pow(LAMG, DG + F4(1.)) * QG3D / CONS[2]; NG3D = N0G / LAMG; }
+          if (LAMG < c.LAMMING) { LAMG = c.LAMMING; N0G = M25_POW(LAMG, DG + F4(1.)) * QG3D / CONS[2]; NG3D = N0G / LAMG; }
+          else if (LAMG > c.LAMMAXG) { LAMG = c.LAMMAXG; N0G = M25_POW(LAMG, DG + F4(1.)) * QG3D / CONS[2]; NG3D = N0G / LAMG; }
         }
       };
       // rain-snow / rain-graupel fall-speed pairs (3337-3348, 3395-3406)
       double UMS, UMR, UNS, UNR, UMG, UNG;
       auto epsr_of = [&]() {
         if (QR3D >= QSMALL)
-          EPSR = F4(2.) * PI * N0RR * RHOK * DV * (F1R / (LAMR * LAMR) + F2R * pow(ARN * RHOK / MU, F4(0.5)) * pow(SC, third) * CONS[9] / pow(LAMR, CONS[34]));
+          EPSR = F4(2.) * PI * N0RR * RHOK * DV * (F1R / (LAMR * LAMR) + F2R * M25_POW(ARN * RHOK / MU, F4(0.5)) * M25_POW(SC, third) * CONS[9] / M25_POW(LAMR, CONS[34]));
         else EPSR = 0.;
       };
       auto epss_val = [&]() {
-        return F4(2.) * PI * N0S * RHOK * DV * (F1S / (LAMS * LAMS) + F2S * pow(ASN * RHOK / MU, F4(0.5)) * pow(SC, third) * CONS[10] / pow(LAMS, CONS[35]));
+        return F4(2.) * PI * N0S * RHOK * DV * (F1S / (LAMS * LAMS) + F2S * M25_POW(ASN * RHOK / MU, F4(0.5)) * M25_POW(SC, third) * CONS[10] / M25_POW(LAMS, CONS[35]));
       };
       auto epsg_val = [&]() {
-        return F4(2.) * PI * N0G * RHOK * DV * (F1S / (LAMG * LAMG) + F2S * pow(AGN * RHOK / MU, F4(0.5)) * pow(SC, third) * CONS[11] / pow(LAMG, CONS[36]));
+        return F4(2.) * PI * N0G * RHOK * DV * (F1S / (LAMG * LAMG) + F2S * M25_POW(AGN * RHOK / MU, F4(0.5)) * M25_POW(SC, third) * CONS[11] / M25_POW(LAMG, CONS[36]));
       };
       bool do_act = true;   // the activation block follows both branches (2517-2845, 4287-4636)
       double wmin_act;
@@ -473,40 +493,40 @@ M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, doub
           NS3D = mx_(0., NS3D); NC3D = mx_(0., NC3D); NR3D = mx_(0., NR3D); NG3D = mx_(0., NG3D);
           rain_dist(); cloud_dist(); snow_dist(); graupel_dist();
           if (QC3D >= F4(1.E-6)) {   // autoconversion, KK2000 (IRAIN = 0)
-            PRC = F4(1350.) * pow(QC3D, F4(2.47)) * pow(NC3D / F4(1.e6) * RHOK, F4(-1.79));
+            PRC = F4(1350.) * M25_POW(QC3D, F4(2.47)) * M25_POW(NC3D / F4(1.e6) * RHOK, F4(-1.79));
             NPRC1 = PRC / CONS[29];
             NPRC = PRC / (QC3D / NC3D);
             NPRC = mn_(NPRC, NC3D / DT);
           }
           if (QR3D >= F4(1.E-8) && QNI3D >= F4(1.E-8)) {
-            UMS = ASN * CONS[3] / pow(LAMS, BS); UMR = ARN * CONS[4] / pow(LAMR, BR);
-            UNS = ASN * CONS[5] / pow(LAMS, BS); UNR = ARN * CONS[6] / pow(LAMR, BR);
-            DUM = pow(RHOSU / RHOK, F4(0.54));
+            UMS = ASN * CONS[3] / M25_POW(LAMS, BS); UMR = ARN * CONS[4] / M25_POW(LAMR, BR);
+            UNS = ASN * CONS[5] / M25_POW(LAMS, BS); UNR = ARN * CONS[6] / M25_POW(LAMR, BR);
+            DUM = M25_POW(RHOSU / RHOK, F4(0.54));
             UMS = mn_(UMS, F4(1.2) * DUM); UNS = mn_(UNS, F4(1.2) * DUM); UMR = mn_(UMR, F4(9.1) * DUM); UNR = mn_(UNR, F4(9.1) * DUM);
-            PRACS = CONS[31] * (pow(p2_(F4(1.2) * UMR - F4(0.95) * UMS) + F4(0.08) * UMS * UMR, F4(0.5)) * RHOK * N0RR * N0S / p3_(LAMS) *
+            PRACS = CONS[31] * (M25_POW(p2_(F4(1.2) * UMR - F4(0.95) * UMS) + F4(0.08) * UMS * UMR, F4(0.5)) * RHOK * N0RR * N0S / p3_(LAMS) *
                                 (F4(5.) / (p3_(LAMS) * LAMR) + F4(2.) / (p2_(LAMS) * p2_(LAMR)) + F4(0.5) / (LAMS * p3_(LAMR))));
           }
           if (QR3D >= F4(1.E-8) && QG3D >= F4(1.E-8)) {
-            UMG = AGN * CONS[7] / pow(LAMG, BG); UMR = ARN * CONS[4] / pow(LAMR, BR);
-            UNG = AGN * CONS[8] / pow(LAMG, BG); UNR = ARN * CONS[6] / pow(LAMR, BR);
-            DUM = pow(RHOSU / RHOK, F4(0.54));
+            UMG = AGN * CONS[7] / M25_POW(LAMG, BG); UMR = ARN * CONS[4] / M25_POW(LAMR, BR);
+            UNG = AGN * CONS[8] / M25_POW(LAMG, BG); UNR = ARN * CONS[6] / M25_POW(LAMR, BR);
+            DUM = M25_POW(RHOSU / RHOK, F4(0.54));
             UMG = mn_(UMG, F4(20.) * DUM); UNG = mn_(UNG, F4(20.) * DUM); UMR = mn_(UMR, F4(9.1) * DUM); UNR = mn_(UNR, F4(9.1) * DUM);
-            PRACG = CONS[41] * (pow(p2_(F4(1.2) * UMR - F4(0.95) * UMG) + F4(0.08) * UMG * UMR, F4(0.5)) * RHOK * N0RR * N0G / p3_(LAMR) *
+            PRACG = CONS[41] * (M25_POW(p2_(F4(1.2) * UMR - F4(0.95) * UMG) + F4(0.08) * UMG * UMR, F4(0.5)) * RHOK * N0RR * N0G / p3_(LAMR) *
                                 (F4(5.) / (p3_(LAMR) * LAMG) + F4(2.) / (p2_(LAMR) * p2_(LAMG)) + F4(0.5) / (LAMR * p3_(LAMG))));
             DUM = PRACG / F4(5.2E-7);
-            NPRACG = CONS[32] * RHOK * pow(F4(1.7) * p2_(UNR - UNG) + F4(0.3) * UNR * UNG, F4(0.5)) * N0RR * N0G *
+            NPRACG = CONS[32] * RHOK * M25_POW(F4(1.7) * p2_(UNR - UNG) + F4(0.3) * UNR * UNG, F4(0.5)) * N0RR * N0G *
                      (F4(1.) / (p3_(LAMR) * LAMG) + F4(1.) / (p2_(LAMR) * p2_(LAMG)) + F4(1.) / (LAMR * p3_(LAMG)));
             NPRACG = mx_(NPRACG - DUM, 0.);
           }
           if (QR3D >= F4(1.E-8) && QC3D >= F4(1.E-8)) {
             DUM = (QC3D * QR3D);
-            PRA = F4(67.) * pow(DUM, F4(1.15));
+            PRA = F4(67.) * M25_POW(DUM, F4(1.15));
             NPRA = PRA / (QC3D / NC3D);
           }
           if (QR3D >= F4(1.E-8)) {
             const double dum1 = F4(300.e-6);
             if (F4(1.) / LAMR < dum1) DUM = 1.;
-            else DUM = F4(2.) - exp(F4(2300.) * (F4(1.) / LAMR - dum1));
+            else DUM = F4(2.) - M25_EXP(F4(2300.) * (F4(1.) / LAMR - dum1));
             NRAGG = F4(-5.78) * DUM * NR3D * QR3D * RHOK;
           }
           epsr_of();
@@ -514,7 +534,7 @@ M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, doub
           if (QNI3D >= F4(1.E-8)) {
             DUM = -CPW / XLF * mx_(T3D - TMELT, 0.) * PRACS;
             PSMLT = F4(2.) * PI * N0S * KAP * mn_(TMELT - T3D, 0.) / XLF * RHOK *
-                        (F1S / (LAMS * LAMS) + F2S * pow(ASN * RHOK / MU, F4(0.5)) * pow(SC, third) * CONS[10] / pow(LAMS, CONS[35])) + DUM;
+                        (F1S / (LAMS * LAMS) + F2S * M25_POW(ASN * RHOK / MU, F4(0.5)) * M25_POW(SC, third) * CONS[10] / M25_POW(LAMS, CONS[35])) + DUM;
             if (QVQVS < F4(1.)) {
               EPSS = epss_val();
               EVPMS = (QV3D - QVS) * EPSS / AB;
@@ -525,7 +545,7 @@ M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, doub
           if (QG3D >= F4(1.E-8)) {
             DUM = -CPW / XLF * mx_(T3D - TMELT, 0.) * PRACG;
             PGMLT = F4(2.) * PI * N0G * KAP * (TMELT - T3D) / XLF * RHOK *
-                        (F1S / (LAMG * LAMG) + F2S * pow(AGN * RHOK / MU, F4(0.5)) * pow(SC, third) * CONS[11] / pow(LAMG, CONS[36])) + DUM;
+                        (F1S / (LAMG * LAMG) + F2S * M25_POW(AGN * RHOK / MU, F4(0.5)) * M25_POW(SC, third) * CONS[11] / M25_POW(LAMG, CONS[36])) + DUM;
             if (QVQVS < F4(1.)) {
               EPSG = epsg_val();
               EVPMG = (QV3D - QVS) * EPSG / AB;
@@ -577,68 +597,68 @@ M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, doub
                PSACR = 0., PSACWG = 0., PGSACW = 0., PGRACS = 0., PRDG = 0., EPRDG = 0., NPSACWG = 0., NSCNG = 0., NGRACS = 0., NSUBG = 0.;
         NI3D = mx_(0., NI3D); NS3D = mx_(0., NS3D); NC3D = mx_(0., NC3D); NR3D = mx_(0., NR3D); NG3D = mx_(0., NG3D);
         if (QI3D >= QSMALL) {
-          LAMI = pow(CONS[12] * NI3D / QI3D, F4(1.) / DI);
+          LAMI = M25_POW(CONS[12] * NI3D / QI3D, F4(1.) / DI);
           N0I = NI3D * LAMI;
-          if (LAMI < c.LAMMINI) { LAMI = c.LAMMINI; N0I = pow(LAMI, DI + F4(1.)) * QI3D / CONS[12]; NI3D = N0I / LAMI; }
-          else if (LAMI > c.LAMMAXI) { LAMI = c.LAMMAXI; N0I = pow(LAMI, DI + F4(1.)) * QI3D / CONS[12]; NI3D = N0I / LAMI; }
+          if (LAMI < c.LAMMINI) { LAMI = c.LAMMINI; N0I = M25_POW(LAMI, DI + F4(1.)) * QI3D / CONS[12]; NI3D = N0I / LAMI; }
+          else if (LAMI > c.LAMMAXI) { LAMI = c.LAMMAXI; N0I = M25_POW(LAMI, DI + F4(1.)) * QI3D / CONS[12]; NI3D = N0I / LAMI; }
         }
         rain_dist(); cloud_dist();
         if (QC3D >= QSMALL) CDIST1 = NC3D / GAM(PGAM + F4(1.));
         snow_dist(); graupel_dist();
         if (QC3D >= QSMALL && T3D < F4(269.15)) {   // contact + immersion freezing of droplets (3145-3192)
-          const double NACNT = exp(F4(-2.80) + F4(0.262) * (TMELT - T3D)) * F4(1000.);
+          const double NACNT = M25_EXP(F4(-2.80) + F4(0.262) * (TMELT - T3D)) * F4(1000.);
           DUM = F4(7.37) * T3D / (F4(288.) * F4(10.) * PRESK) / F4(100.);
           const double DAP = CONS[37] * T3D * (F4(1.) + DUM / c.RIN) / MU;
-          MNUCCC = CONS[38] * DAP * NACNT * exp(log(CDIST1) + log(GAM(PGAM + F4(5.))) - F4(4.) * log(LAMC));
+          MNUCCC = CONS[38] * DAP * NACNT * M25_EXP(M25_LOG(CDIST1) + M25_LOG(GAM(PGAM + F4(5.))) - F4(4.) * M25_LOG(LAMC));
           NNUCCC = F4(2.) * PI * DAP * NACNT * CDIST1 * GAM(PGAM + F4(2.)) / LAMC;
-          MNUCCC = MNUCCC + CONS[39] * exp(log(CDIST1) + log(GAM(F4(7.) + PGAM)) - F4(6.) * log(LAMC)) * exp(AIMM * (TMELT - T3D));
-          NNUCCC = NNUCCC + CONS[40] * exp(log(CDIST1) + log(GAM(PGAM + F4(4.))) - F4(3.) * log(LAMC)) * exp(AIMM * (TMELT - T3D));
+          MNUCCC = MNUCCC + CONS[39] * M25_EXP(M25_LOG(CDIST1) + M25_LOG(GAM(F4(7.) + PGAM)) - F4(6.) * M25_LOG(LAMC)) * M25_EXP(AIMM * (TMELT - T3D));
+          NNUCCC = NNUCCC + CONS[40] * M25_EXP(M25_LOG(CDIST1) + M25_LOG(GAM(PGAM + F4(4.))) - F4(3.) * M25_LOG(LAMC)) * M25_EXP(AIMM * (TMELT - T3D));
           NNUCCC = mn_(NNUCCC, NC3D / DT);
         }
         if (QC3D >= F4(1.E-6)) {
-          PRC = F4(1350.) * pow(QC3D, F4(2.47)) * pow(NC3D / F4(1.e6) * RHOK, F4(-1.79));
+          PRC = F4(1350.) * M25_POW(QC3D, F4(2.47)) * M25_POW(NC3D / F4(1.e6) * RHOK, F4(-1.79));
           NPRC1 = PRC / CONS[29];
           NPRC = PRC / (QC3D / NC3D);
           NPRC = mn_(NPRC, NC3D / DT);
         }
         if (QNI3D >= F4(1.E-8))
-          NSAGG = CONS[15] * ASN * pow(RHOK, (F4(2.) + BS) / F4(3.)) * pow(QNI3D, (F4(2.) + BS) / F4(3.)) * pow(NS3D * RHOK, (F4(4.) - BS) / F4(3.)) / (RHOK);
+          NSAGG = CONS[15] * ASN * M25_POW(RHOK, (F4(2.) + BS) / F4(3.)) * M25_POW(QNI3D, (F4(2.) + BS) / F4(3.)) * M25_POW(NS3D * RHOK, (F4(4.) - BS) / F4(3.)) / (RHOK);
         if (QNI3D >= F4(1.E-8) && QC3D >= QSMALL) {
-          PSACWS = CONS[13] * ASN * QC3D * RHOK * N0S / pow(LAMS, BS + F4(3.));
-          NPSACWS = CONS[13] * ASN * NC3D * RHOK * N0S / pow(LAMS, BS + F4(3.));
+          PSACWS = CONS[13] * ASN * QC3D * RHOK * N0S / M25_POW(LAMS, BS + F4(3.));
+          NPSACWS = CONS[13] * ASN * NC3D * RHOK * N0S / M25_POW(LAMS, BS + F4(3.));
         }
         if (QG3D >= F4(1.E-8) && QC3D >= QSMALL) {
-          PSACWG = CONS[14] * AGN * QC3D * RHOK * N0G / pow(LAMG, BG + F4(3.));
-          NPSACWG = CONS[14] * AGN * NC3D * RHOK * N0G / pow(LAMG, BG + F4(3.));
+          PSACWG = CONS[14] * AGN * QC3D * RHOK * N0G / M25_POW(LAMG, BG + F4(3.));
+          NPSACWG = CONS[14] * AGN * NC3D * RHOK * N0G / M25_POW(LAMG, BG + F4(3.));
         }
         if (QI3D >= F4(1.E-8) && QC3D >= QSMALL) {
           if (F4(1.) / LAMI >= F4(100.E-6)) {
-            PSACWI = CONS[16] * AIN * QC3D * RHOK * N0I / pow(LAMI, BI + F4(3.));
-            NPSACWI = CONS[16] * AIN * NC3D * RHOK * N0I / pow(LAMI, BI + F4(3.));
+            PSACWI = CONS[16] * AIN * QC3D * RHOK * N0I / M25_POW(LAMI, BI + F4(3.));
+            NPSACWI = CONS[16] * AIN * NC3D * RHOK * N0I / M25_POW(LAMI, BI + F4(3.));
           }
         }
         if (QR3D >= F4(1.E-8) && QNI3D >= F4(1.E-8)) {
-          UMS = ASN * CONS[3] / pow(LAMS, BS); UMR = ARN * CONS[4] / pow(LAMR, BR);
-          UNS = ASN * CONS[5] / pow(LAMS, BS); UNR = ARN * CONS[6] / pow(LAMR, BR);
-          DUM = pow(RHOSU / RHOK, F4(0.54));
+          UMS = ASN * CONS[3] / M25_POW(LAMS, BS); UMR = ARN * CONS[4] / M25_POW(LAMR, BR);
+          UNS = ASN * CONS[5] / M25_POW(LAMS, BS); UNR = ARN * CONS[6] / M25_POW(LAMR, BR);
+          DUM = M25_POW(RHOSU / RHOK, F4(0.54));
           UMS = mn_(UMS, F4(1.2) * DUM); UNS = mn_(UNS, F4(1.2) * DUM); UMR = mn_(UMR, F4(9.1) * DUM); UNR = mn_(UNR, F4(9.1) * DUM);
-          PRACS = CONS[41] * (pow(p2_(F4(1.2) * UMR - F4(0.95) * UMS) + F4(0.08) * UMS * UMR, F4(0.5)) * RHOK * N0RR * N0S / p3_(LAMR) *
+          PRACS = CONS[41] * (M25_POW(p2_(F4(1.2) * UMR - F4(0.95) * UMS) + F4(0.08) * UMS * UMR, F4(0.5)) * RHOK * N0RR * N0S / p3_(LAMR) *
                               (F4(5.) / (p3_(LAMR) * LAMS) + F4(2.) / (p2_(LAMR) * p2_(LAMS)) + F4(0.5) / (LAMR * p3_(LAMS))));
-          NPRACS = CONS[32] * RHOK * pow(F4(1.7) * p2_(UNR - UNS) + F4(0.3) * UNR * UNS, F4(0.5)) * N0RR * N0S *
+          NPRACS = CONS[32] * RHOK * M25_POW(F4(1.7) * p2_(UNR - UNS) + F4(0.3) * UNR * UNS, F4(0.5)) * N0RR * N0S *
                    (F4(1.) / (p3_(LAMR) * LAMS) + F4(1.) / (p2_(LAMR) * p2_(LAMS)) + F4(1.) / (LAMR * p3_(LAMS)));
           PRACS = mn_(PRACS, QR3D / DT);
           if (QNI3D >= F4(0.1E-3) && QR3D >= F4(0.1E-3))
-            PSACR = CONS[31] * (pow(p2_(F4(1.2) * UMR - F4(0.95) * UMS) + F4(0.08) * UMS * UMR, F4(0.5)) * RHOK * N0RR * N0S / p3_(LAMS) *
+            PSACR = CONS[31] * (M25_POW(p2_(F4(1.2) * UMR - F4(0.95) * UMS) + F4(0.08) * UMS * UMR, F4(0.5)) * RHOK * N0RR * N0S / p3_(LAMS) *
                                 (F4(5.) / (p3_(LAMS) * LAMR) + F4(2.) / (p2_(LAMS) * p2_(LAMR)) + F4(0.5) / (LAMS * p3_(LAMR))));
         }
         if (QR3D >= F4(1.E-8) && QG3D >= F4(1.E-8)) {
-          UMG = AGN * CONS[7] / pow(LAMG, BG); UMR = ARN * CONS[4] / pow(LAMR, BR);
-          UNG = AGN * CONS[8] / pow(LAMG, BG); UNR = ARN * CONS[6] / pow(LAMR, BR);
-          DUM = pow(RHOSU / RHOK, F4(0.54));
+          UMG = AGN * CONS[7] / M25_POW(LAMG, BG); UMR = ARN * CONS[4] / M25_POW(LAMR, BR);
+          UNG = AGN * CONS[8] / M25_POW(LAMG, BG); UNR = ARN * CONS[6] / M25_POW(LAMR, BR);
+          DUM = M25_POW(RHOSU / RHOK, F4(0.54));
           UMG = mn_(UMG, F4(20.) * DUM); UNG = mn_(UNG, F4(20.) * DUM); UMR = mn_(UMR, F4(9.1) * DUM); UNR = mn_(UNR, F4(9.1) * DUM);
-          PRACG = CONS[41] * (pow(p2_(F4(1.2) * UMR - F4(0.95) * UMG) + F4(0.08) * UMG * UMR, F4(0.5)) * RHOK * N0RR * N0G / p3_(LAMR) *
+          PRACG = CONS[41] * (M25_POW(p2_(F4(1.2) * UMR - F4(0.95) * UMG) + F4(0.08) * UMG * UMR, F4(0.5)) * RHOK * N0RR * N0G / p3_(LAMR) *
                               (F4(5.) / (p3_(LAMR) * LAMG) + F4(2.) / (p2_(LAMR) * p2_(LAMG)) + F4(0.5) / (LAMR * p3_(LAMG))));
-          NPRACG = CONS[32] * RHOK * pow(F4(1.7) * p2_(UNR - UNG) + F4(0.3) * UNR * UNG, F4(0.5)) * N0RR * N0G *
+          NPRACG = CONS[32] * RHOK * M25_POW(F4(1.7) * p2_(UNR - UNG) + F4(0.3) * UNR * UNG, F4(0.5)) * N0RR * N0G *
                    (F4(1.) / (p3_(LAMR) * LAMG) + F4(1.) / (p2_(LAMR) * p2_(LAMG)) + F4(1.) / (LAMR * p3_(LAMG)));
           PRACG = mn_(PRACG, QR3D / DT);
         }
@@ -676,7 +696,7 @@ M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, doub
         // conversion of rimed snow to graupel (3567-3612)
         if (PSACWS > 0.) {
           if (QNI3D >= F4(0.1E-3) && QC3D >= F4(0.5E-3)) {
-            PGSACW = mn_(PSACWS, CONS[17] * DT * N0S * QC3D * QC3D * ASN * ASN / (RHOK * pow(LAMS, F4(2.) * BS + F4(2.))));
+            PGSACW = mn_(PSACWS, CONS[17] * DT * N0S * QC3D * QC3D * ASN * ASN / (RHOK * M25_POW(LAMS, F4(2.) * BS + F4(2.))));
             DUM = mx_(c.RHOSN / (c.RHOG - c.RHOSN) * PGSACW, 0.);
             NSCNG = DUM / c.MG0 * RHOK;
             NSCNG = mn_(NSCNG, NS3D / DT);
@@ -697,47 +717,47 @@ M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, doub
           }
         }
         if (T3D < F4(269.15) && QR3D >= QSMALL) {   // freezing of rain (3619-3630)
-          MNUCCR = CONS[20] * NR3D * exp(AIMM * (TMELT - T3D)) / p3_(LAMR) / p3_(LAMR);
-          NNUCCR = PI * NR3D * c.BIMM * exp(AIMM * (TMELT - T3D)) / p3_(LAMR);
+          MNUCCR = CONS[20] * NR3D * M25_EXP(AIMM * (TMELT - T3D)) / p3_(LAMR) / p3_(LAMR);
+          NNUCCR = PI * NR3D * c.BIMM * M25_EXP(AIMM * (TMELT - T3D)) / p3_(LAMR);
           NNUCCR = mn_(NNUCCR, NR3D / DT);
         }
         if (QR3D >= F4(1.E-8) && QC3D >= F4(1.E-8)) {
           DUM = (QC3D * QR3D);
-          PRA = F4(67.) * pow(DUM, F4(1.15));
+          PRA = F4(67.) * M25_POW(DUM, F4(1.15));
           NPRA = PRA / (QC3D / NC3D);
         }
         if (QR3D >= F4(1.E-8)) {
           const double dum1 = F4(300.e-6);
           if (F4(1.) / LAMR < dum1) DUM = 1.;
-          else DUM = F4(2.) - exp(F4(2300.) * (F4(1.) / LAMR - dum1));
+          else DUM = F4(2.) - M25_EXP(F4(2300.) * (F4(1.) / LAMR - dum1));
           NRAGG = F4(-5.78) * DUM * NR3D * QR3D * RHOK;
         }
         if (QI3D >= F4(1.E-8) && QVQVSI >= F4(1.)) {   // autoconversion of cloud ice to snow (3693-3703)
-          NPRCI = CONS[21] * (QV3D - QVI) * RHOK * N0I * exp(-LAMI * DCS) * DV / ABI;
+          NPRCI = CONS[21] * (QV3D - QVI) * RHOK * N0I * M25_EXP(-LAMI * DCS) * DV / ABI;
           PRCI = CONS[22] * NPRCI;
           NPRCI = mn_(NPRCI, NI3D / DT);
         }
         if (QNI3D >= F4(1.E-8) && QI3D >= QSMALL) {
-          PRAI = CONS[23] * ASN * QI3D * RHOK * N0S / pow(LAMS, BS + F4(3.));
-          NPRAI = CONS[23] * ASN * NI3D * RHOK * N0S / pow(LAMS, BS + F4(3.));
+          PRAI = CONS[23] * ASN * QI3D * RHOK * N0S / M25_POW(LAMS, BS + F4(3.));
+          NPRAI = CONS[23] * ASN * NI3D * RHOK * N0S / M25_POW(LAMS, BS + F4(3.));
           NPRAI = mn_(NPRAI, NI3D / DT);
         }
         if (QR3D >= F4(1.E-8) && QI3D >= F4(1.E-8) && T3D <= TMELT) {
           if (QR3D >= F4(0.1E-3)) {
-            NIACR = CONS[24] * NI3D * N0RR * ARN / pow(LAMR, BR + F4(3.)) * RHOK;
-            PIACR = CONS[25] * NI3D * N0RR * ARN / pow(LAMR, BR + F4(3.)) / p3_(LAMR) * RHOK;
-            PRACI = CONS[24] * QI3D * N0RR * ARN / pow(LAMR, BR + F4(3.)) * RHOK;
+            NIACR = CONS[24] * NI3D * N0RR * ARN / M25_POW(LAMR, BR + F4(3.)) * RHOK;
+            PIACR = CONS[25] * NI3D * N0RR * ARN / M25_POW(LAMR, BR + F4(3.)) / p3_(LAMR) * RHOK;
+            PRACI = CONS[24] * QI3D * N0RR * ARN / M25_POW(LAMR, BR + F4(3.)) * RHOK;
             NIACR = mn_(NIACR, NR3D / DT); NIACR = mn_(NIACR, NI3D / DT);
           } else {
-            NIACRS = CONS[24] * NI3D * N0RR * ARN / pow(LAMR, BR + F4(3.)) * RHOK;
-            PIACRS = CONS[25] * NI3D * N0RR * ARN / pow(LAMR, BR + F4(3.)) / p3_(LAMR) * RHOK;
-            PRACIS = CONS[24] * QI3D * N0RR * ARN / pow(LAMR, BR + F4(3.)) * RHOK;
+            NIACRS = CONS[24] * NI3D * N0RR * ARN / M25_POW(LAMR, BR + F4(3.)) * RHOK;
+            PIACRS = CONS[25] * NI3D * N0RR * ARN / M25_POW(LAMR, BR + F4(3.)) / p3_(LAMR) * RHOK;
+            PRACIS = CONS[24] * QI3D * N0RR * ARN / M25_POW(LAMR, BR + F4(3.)) * RHOK;
             NIACRS = mn_(NIACRS, NR3D / DT); NIACRS = mn_(NIACRS, NI3D / DT);
           }
         }
         // ice nucleation, Cooper (INUC = 0, 3782-3804)
         if ((QVQVS >= F4(0.999) && T3D <= F4(265.15)) || QVQVSI >= F4(1.08)) {
-          double kc2 = F4(0.005) * exp(F4(0.304) * (TMELT - T3D)) * F4(1000.);
+          double kc2 = F4(0.005) * M25_EXP(F4(0.304) * (TMELT - T3D)) * F4(1000.);
           kc2 = mn_(kc2, F4(500.e3));
           kc2 = mx_(kc2 / RHOK, 0.);
           if (kc2 > NI3D + NS3D + NG3D) { NNUCCD = (kc2 - NI3D - NS3D - NG3D) / DT; MNUCCD = NNUCCD * c.MI0; }
@@ -748,7 +768,7 @@ M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, doub
         if (QG3D >= QSMALL) EPSG = epsg_val(); else EPSG = 0.;
         epsr_of();
         if (QI3D >= QSMALL) {
-          DUM = (F4(1.) - exp(-LAMI * DCS) * (F4(1.) + LAMI * DCS));
+          DUM = (F4(1.) - M25_EXP(-LAMI * DCS) * (F4(1.) + LAMI * DCS));
           PRD = EPSI * (QV3D - QVI) / ABI * DUM;
         } else DUM = 0.;
         if (QNI3D >= QSMALL) PRDS = EPSS * (QV3D - QVI) / ABI + EPSI * (QV3D - QVI) / ABI * (F4(1.) - DUM);
@@ -856,31 +876,31 @@ M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, doub
     double DUMC = a(QC, K) + a(TQC, K) * DT, DUMFNC = a(NC, K) + a(TNC, K) * DT, DUMG = a(QG, K) + a(TQG, K) * DT, DUMFNG = a(NG, K) + a(TNG, K) * DT;
     DUMFNI = mx_(0., DUMFNI); DUMFNS = mx_(0., DUMFNS); DUMFNC = mx_(0., DUMFNC); DUMFNR = mx_(0., DUMFNR); DUMFNG = mx_(0., DUMFNG);
     double DLAMI = 0., DLAMR = 0., DLAMC = 0., DLAMS = 0., DLAMG = 0., PGAM = 0.;
-    if (DUMI >= QSMALL) { DLAMI = pow(CONS[12] * DUMFNI / DUMI, F4(1.) / DI); DLAMI = mx_(DLAMI, c.LAMMINI); DLAMI = mn_(DLAMI, c.LAMMAXI); }
-    if (DUMR >= QSMALL) { DLAMR = pow(PI * RHOW * DUMFNR / DUMR, third); DLAMR = mx_(DLAMR, c.LAMMINR); DLAMR = mn_(DLAMR, c.LAMMAXR); }
+    if (DUMI >= QSMALL) { DLAMI = M25_POW(CONS[12] * DUMFNI / DUMI, F4(1.) / DI); DLAMI = mx_(DLAMI, c.LAMMINI); DLAMI = mn_(DLAMI, c.LAMMAXI); }
+    if (DUMR >= QSMALL) { DLAMR = M25_POW(PI * RHOW * DUMFNR / DUMR, third); DLAMR = mx_(DLAMR, c.LAMMINR); DLAMR = mn_(DLAMR, c.LAMMAXR); }
     if (DUMC >= QSMALL) {
       PGAM = F4(0.0005714) * (a(NC, K) / F4(1.E6) * RHOK) + F4(0.2714);
       PGAM = F4(1.) / (PGAM * PGAM) - F4(1.);
       PGAM = mx_(PGAM, 2.); PGAM = mn_(PGAM, 10.);
-      DLAMC = pow(CONS[26] * DUMFNC * GAM(PGAM + F4(4.)) / (DUMC * GAM(PGAM + F4(1.))), third);
+      DLAMC = M25_POW(CONS[26] * DUMFNC * GAM(PGAM + F4(4.)) / (DUMC * GAM(PGAM + F4(1.))), third);
       const double LAMMIN = (PGAM + F4(1.)) / F4(60.E-6), LAMMAX = (PGAM + F4(1.)) / F4(1.E-6);
       DLAMC = mx_(DLAMC, LAMMIN); DLAMC = mn_(DLAMC, LAMMAX);
     }
-    if (DUMQS >= QSMALL) { DLAMS = pow(CONS[1] * DUMFNS / DUMQS, F4(1.) / DS); DLAMS = mx_(DLAMS, c.LAMMINS); DLAMS = mn_(DLAMS, c.LAMMAXS); }
-    if (DUMG >= QSMALL) { DLAMG = pow(CONS[2] * DUMFNG / DUMG, F4(1.) / DG); DLAMG = mx_(DLAMG, c.LAMMING); DLAMG = mn_(DLAMG, c.LAMMAXG); }
+    if (DUMQS >= QSMALL) { DLAMS = M25_POW(CONS[1] * DUMFNS / DUMQS, F4(1.) / DS); DLAMS = mx_(DLAMS, c.LAMMINS); DLAMS = mn_(DLAMS, c.LAMMAXS); }
+    if (DUMG >= QSMALL) { DLAMG = M25_POW(CONS[2] * DUMFNG / DUMG, F4(1.) / DG); DLAMG = mx_(DLAMG, c.LAMMING); DLAMG = mn_(DLAMG, c.LAMMAXG); }
     const double ACN = a(ACN_, K), AIN = a(AIN_, K), ARN = a(ARN_, K), ASN = a(ASN_, K), AGN = a(AGN_, K);
     double UNC, UMC, UNI, UMI, UNR, UMR, UMS, UNS, UMG, UNG;
     if (DUMC >= QSMALL) {
-      UNC = ACN * GAM(F4(1.) + BC + PGAM) / (pow(DLAMC, BC) * GAM(PGAM + F4(1.)));
-      UMC = ACN * GAM(F4(4.) + BC + PGAM) / (pow(DLAMC, BC) * GAM(PGAM + F4(4.)));
+      UNC = ACN * GAM(F4(1.) + BC + PGAM) / (M25_POW(DLAMC, BC) * GAM(PGAM + F4(1.)));
+      UMC = ACN * GAM(F4(4.) + BC + PGAM) / (M25_POW(DLAMC, BC) * GAM(PGAM + F4(4.)));
     } else { UMC = 0.; UNC = 0.; }
-    if (DUMI >= QSMALL) { UNI = AIN * CONS[27] / pow(DLAMI, BI); UMI = AIN * CONS[28] / (pow(DLAMI, BI)); } else { UMI = 0.; UNI = 0.; }
-    if (DUMR >= QSMALL) { UNR = ARN * CONS[6] / pow(DLAMR, BR); UMR = ARN * CONS[4] / (pow(DLAMR, BR)); } else { UMR = 0.; UNR = 0.; }
-    if (DUMQS >= QSMALL) { UMS = ASN * CONS[3] / (pow(DLAMS, BS)); UNS = ASN * CONS[5] / pow(DLAMS, BS); } else { UMS = 0.; UNS = 0.; }
-    if (DUMG >= QSMALL) { UMG = AGN * CONS[7] / (pow(DLAMG, BG)); UNG = AGN * CONS[8] / pow(DLAMG, BG); } else { UMG = 0.; UNG = 0.; }
-    const double dum = pow(RHOSU / RHOK, F4(0.54));
+    if (DUMI >= QSMALL) { UNI = AIN * CONS[27] / M25_POW(DLAMI, BI); UMI = AIN * CONS[28] / (M25_POW(DLAMI, BI)); } else { UMI = 0.; UNI = 0.; }
+    if (DUMR >= QSMALL) { UNR = ARN * CONS[6] / M25_POW(DLAMR, BR); UMR = ARN * CONS[4] / (M25_POW(DLAMR, BR)); } else { UMR = 0.; UNR = 0.; }
+    if (DUMQS >= QSMALL) { UMS = ASN * CONS[3] / (M25_POW(DLAMS, BS)); UNS = ASN * CONS[5] / M25_POW(DLAMS, BS); } else { UMS = 0.; UNS = 0.; }
+    if (DUMG >= QSMALL) { UMG = AGN * CONS[7] / (M25_POW(DLAMG, BG)); UNG = AGN * CONS[8] / M25_POW(DLAMG, BG); } else { UMG = 0.; UNG = 0.; }
+    const double dum = M25_POW(RHOSU / RHOK, F4(0.54));
     UMS = mn_(UMS, F4(1.2) * dum); UNS = mn_(UNS, F4(1.2) * dum);
-    UMI = mn_(UMI, F4(1.2) * pow(RHOSU / RHOK, F4(0.35))); UNI = mn_(UNI, F4(1.2) * pow(RHOSU / RHOK, F4(0.35)));
+    UMI = mn_(UMI, F4(1.2) * M25_POW(RHOSU / RHOK, F4(0.35))); UNI = mn_(UNI, F4(1.2) * M25_POW(RHOSU / RHOK, F4(0.35)));
     UMR = mn_(UMR, F4(9.1) * dum); UNR = mn_(UNR, F4(9.1) * dum);
     UMG = mn_(UMG, F4(20.) * dum); UNG = mn_(UNG, F4(20.) * dum);
     double fr = UMR, fi = UMI, fni = UNI, fs = UMS, fns = UNS, fnr = UNR, fc = UMC, fnc = UNC, fg = UMG, fng = UNG;
@@ -990,12 +1010,12 @@ M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, doub
       if (T3D <= F4(233.15) && QR3D >= QSMALL) { QG3D = QG3D + QR3D; T3D = T3D + QR3D * XLF / CPM; QR3D = 0.; NG3D = NG3D + NR3D; NR3D = 0.; }
       NI3D = mx_(0., NI3D); NS3D = mx_(0., NS3D); NC3D = mx_(0., NC3D); NR3D = mx_(0., NR3D); NG3D = mx_(0., NG3D);
       if (QI3D >= QSMALL) {
-        LAMI = pow(CONS[12] * NI3D / QI3D, F4(1.) / DI);
-        if (LAMI < c.LAMMINI) { LAMI = c.LAMMINI; const double N0I = pow(LAMI, DI + F4(1.)) * QI3D / CONS[12]; NI3D = N0I / LAMI; }
-        else if (LAMI > c.LAMMAXI) { LAMI = c.LAMMAXI; const double N0I = pow(LAMI, DI + F4(1.)) * QI3D / CONS[12]; NI3D = N0I / LAMI; }
+        LAMI = M25_POW(CONS[12] * NI3D / QI3D, F4(1.) / DI);
+        if (LAMI < c.LAMMINI) { LAMI = c.LAMMINI; const double N0I = M25_POW(LAMI, DI + F4(1.)) * QI3D / CONS[12]; NI3D = N0I / LAMI; }
+        else if (LAMI > c.LAMMAXI) { LAMI = c.LAMMAXI; const double N0I = M25_POW(LAMI, DI + F4(1.)) * QI3D / CONS[12]; NI3D = N0I / LAMI; }
       }
       if (QR3D >= QSMALL) {
-        double LAMR = pow(PI * RHOW * NR3D / QR3D, third);
+        double LAMR = M25_POW(PI * RHOW * NR3D / QR3D, third);
         if (LAMR < c.LAMMINR) { LAMR = c.LAMMINR; const double N0RR = p4_(LAMR) * QR3D / (PI * RHOW); NR3D = N0RR / LAMR; }
         else if (LAMR > c.LAMMAXR) { LAMR = c.LAMMAXR; const double N0RR = p4_(LAMR) * QR3D / (PI * RHOW); NR3D = N0RR / LAMR; }
       }
@@ -1003,20 +1023,20 @@ M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, doub
         double PGAM = F4(0.0005714) * (NC3D / F4(1.E6) * RHOK) + F4(0.2714);
         PGAM = F4(1.) / (PGAM * PGAM) - F4(1.);
         PGAM = mx_(PGAM, 2.); PGAM = mn_(PGAM, 10.);
-        double LAMC = pow(CONS[26] * NC3D * GAM(PGAM + F4(4.)) / (QC3D * GAM(PGAM + F4(1.))), third);
+        double LAMC = M25_POW(CONS[26] * NC3D * GAM(PGAM + F4(4.)) / (QC3D * GAM(PGAM + F4(1.))), third);
         const double LAMMIN = (PGAM + F4(1.)) / F4(60.E-6), LAMMAX = (PGAM + F4(1.)) / F4(1.E-6);
-        if (LAMC < LAMMIN) { LAMC = LAMMIN; NC3D = exp(F4(3.) * log(LAMC) + log(QC3D) + log(GAM(PGAM + F4(1.))) - log(GAM(PGAM + F4(4.)))) / CONS[26]; }
-        else if (LAMC > LAMMAX) { LAMC = LAMMAX; NC3D = exp(F4(3.) * log(LAMC) + log(QC3D) + log(GAM(PGAM + F4(1.))) - log(GAM(PGAM + F4(4.)))) / CONS[26]; }
+        if (LAMC < LAMMIN) { LAMC = LAMMIN; NC3D = M25_EXP(F4(3.) * M25_LOG(LAMC) + M25_LOG(QC3D) + M25_LOG(GAM(PGAM + F4(1.))) - M25_LOG(GAM(PGAM + F4(4.)))) / CONS[26]; }
+        else if (LAMC > LAMMAX) { LAMC = LAMMAX; NC3D = M25_EXP(F4(3.) * M25_LOG(LAMC) + M25_LOG(QC3D) + M25_LOG(GAM(PGAM + F4(1.))) - M25_LOG(GAM(PGAM + F4(4.)))) / CONS[26]; }
       }
       if (QNI3D >= QSMALL) {
-        double LAMS = pow(CONS[1] * NS3D / QNI3D, F4(1.) / DS);
-        if (LAMS < c.LAMMINS) { LAMS = c.LAMMINS; const double N0S = pow(LAMS, DS + F4(1.)) * QNI3D / CONS[1]; NS3D = N0S / LAMS; }
-        else if (LAMS > c.LAMMAXS) { LAMS = c.LAMMAXS; const double N0S = pow(LAMS, DS + F4(1.)) * QNI3D / CONS[1]; NS3D = N0S / LAMS; }
+        double LAMS = M25_POW(CONS[1] * NS3D / QNI3D, F4(1.) / DS);
+        if (LAMS < c.LAMMINS) { LAMS = c.LAMMINS; const double N0S = M25_POW(LAMS, DS + F4(1.)) * QNI3D / CONS[1]; NS3D = N0S / LAMS; }
+        else if (LAMS > c.LAMMAXS) { LAMS = c.LAMMAXS; const double N0S = M25_POW(LAMS, DS + F4(1.)) * QNI3D / CONS[1]; NS3D = N0S / LAMS; }
       }
       if (QG3D >= QSMALL) {
-        double LAMG = pow(CONS[2] * NG3D / QG3D, F4(1.) / DG);
-        if (LAMG < c.LAMMING) { LAMG = c.LAMMING; const double N0G = pow(LAMG, DG + F4(1.)) * QG3D / CONS[2]; NG3D = N0G / LAMG; }
-        else if (LAMG > c.LAMMAXG) { LAMG = c.LAMMAXG; const double N0G = pow(LAMG, DG + F4(1.)) * QG3D / CONS[2]; NG3D = N0G / LAMG; }
+        double LAMG = M25_POW(CONS[2] * NG3D / QG3D, F4(1.) / DG);
+        if (LAMG < c.LAMMING) { LAMG = c.LAMMING; const double N0G = M25_POW(LAMG, DG + F4(1.)) * QG3D / CONS[2]; NG3D = N0G / LAMG; }
+        else if (LAMG > c.LAMMAXG) { LAMG = c.LAMMAXG; const double N0G = M25_POW(LAMG, DG + F4(1.)) * QG3D / CONS[2]; NG3D = N0G / LAMG; }
       }
     }
     // 500 CONTINUE
