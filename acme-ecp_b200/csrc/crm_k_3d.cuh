@@ -843,8 +843,8 @@ __global__ void __launch_bounds__(CRM_MAX_P3) k3_mpdata(CrmP p, double *f, doubl
       const double rho = S_RHO(kb_), iadz = S_IADZ(kb_);
       const double WWk = WW_prev;
       const double WWkc = (kb_ == nzm) ? WW_prev : WW_ka;
-      ratio2(rho * (mxr - F1c), pn_(UUp) + pp_(UU) + pn_(VVp) + pp_(VV) + iadz * (pn_(WWkc) + pp_(WWk)) + eps,
-             rho * (F1c - mnr), pp_(UUp) + pn_(UU) + pp_(VVp) + pn_(VV) + iadz * (pp_(WWkc) + pn_(WWk)) + eps, mx_new, mn_new);
+      ratio2(rho * (mxr - F1c), fma(0.5, fma(iadz, pn2_(WWkc) + pp2_(WWk), pn2_(UUp) + pp2_(UU) + pn2_(VVp) + pp2_(VV)), eps),
+             rho * (F1c - mnr), fma(0.5, fma(iadz, pp2_(WWkc) + pn2_(WWk), pp2_(UUp) + pn2_(UU) + pp2_(VVp) + pn2_(VV)), eps), mx_new, mn_new);
       smx[(kb_ & 1) * P + tid] = mx_new;
       smn[(kb_ & 1) * P + tid] = mn_new;
     }
@@ -854,14 +854,14 @@ __global__ void __launch_bounds__(CRM_MAX_P3) k3_mpdata(CrmP p, double *f, doubl
     double WWlim_kp1 = 0.;
     if (vB && kb_ >= 2) {
       const double WWl = WW_prev;
-      WWlim_kp1 = pp_(WWl) * dmin(dmin(1., mx_new), mn_prev) - pn_(WWl) * dmin(dmin(1., mx_prev), mn_new);
+      WWlim_kp1 = lim_flux(WWl, mx_new, mn_prev, mx_prev, mn_new);
     }
     double ULim = 0., VLim = 0.;
     if (vC) {
       const double *MX = smx + (kc_ & 1) * P, *MN = smn + (kc_ & 1) * P;
       const double mx_c = MX[tid], mn_c = MN[tid];
-      ULim = pp_(UU_prev) * dmin(dmin(1., mx_c), MN[tm1]) - pn_(UU_prev) * dmin(dmin(1., MX[tm1]), mn_c);
-      VLim = pp_(VV_prev) * dmin(dmin(1., mx_c), MN[tjm]) - pn_(VV_prev) * dmin(dmin(1., MX[tjm]), mn_c);
+      ULim = lim_flux(UU_prev, mx_c, MN[tm1], MX[tm1], mn_c);
+      VLim = lim_flux(VV_prev, mx_c, MN[tjm], MX[tjm], mn_c);
       sUL[tid] = ULim; sVL[tid] = VLim;
     }
     __syncthreads();   // (4)

@@ -37,9 +37,20 @@ __device__ __forceinline__ void ratio2(double n1, double d1, double n2, double d
   q1 = 1.; q2 = 1.;
   if (a1 || a2) {
     const double r = 1. / (d1 * d2);
-    if (a1) q1 = n1 * d2 * r;
-    if (a2) q2 = n2 * d1 * r;
+    if (a1) q1 = dmin(1., n1 * d2 * r);   // n1 < d1, but the 2-ulp quotient may round to 1 + ulp: every ratio leaves here <= 1
+    if (a2) q2 = dmin(1., n2 * d1 * r);
   }
+}
+// FP64 max / min cost three issue slots each (DSETP + 2 FSEL: there is no DMNMX on sm_100), and they were 29 % of k_mpdata's
+// instructions (profiles/r02f).  Two exact rewrites of the FCT formulas remove a third of them:
+//  * 2*max(0,x) = |x| + x and 2*(-min(0,x)) = |x| - x exactly (|x| is a free operand modifier), so the out/in-flux sums
+//    pn(a) + pp(b) + .. = 0.5 * ((|a| - a) + (|b| + b) + ..): same roundings (scaling by 2 is exact), fma(0.5, s, eps) = s/2 + eps;
+//  * with every ratio <= 1 (ratio2), pp(v)*min(1,mxP,mnP) - pn(v)*min(1,mxN,mnN) = v * min(v > 0 ? mxP : mxN, v > 0 ? mnP : mnN).
+__device__ __forceinline__ double pp2_(double x) { return fabs(x) + x; }   // 2*max(0,x)
+__device__ __forceinline__ double pn2_(double x) { return fabs(x) - x; }   // 2*(-min(0,x))
+__device__ __forceinline__ double lim_flux(double v, double mxP, double mnP, double mxN, double mnN) {
+  const bool pos = v > 0.;
+  return v * dmin(pos ? mxP : mxN, pos ? mnP : mnN);
 }
 template <int NXT>
 __global__ void __launch_bounds__(CRM_MAX_P, 3) k_mpdata(CrmP p, double *f, double *fadv, double *flux, int stats, const int *ktop) {
@@ -167,8 +178,8 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_mpdata(CrmP p, double *f, doub
       const double WWk = WW_prev;                                  // WW(kb_)
       const double WWkc = (kb_ == nzm) ? WW_prev : WW_ka;           // WW(min(nzm,kb_+1))
       // zero numerators give exactly +0 (denominators >= eps > 0): no division where the field is locally uniform (qp = 0 ...)
-      ratio2(rho * (mxr - F1c), pn_(UUp) + pp_(UU) + iadz * (pn_(WWkc) + pp_(WWk)) + eps,
-             rho * (F1c - mnr), pp_(UUp) + pn_(UU) + iadz * (pp_(WWkc) + pn_(WWk)) + eps, mx_new, mn_new);
+      ratio2(rho * (mxr - F1c), fma(0.5, fma(iadz, pn2_(WWkc) + pp2_(WWk), pn2_(UUp) + pp2_(UU)), eps),
+             rho * (F1c - mnr), fma(0.5, fma(iadz, pp2_(WWkc) + pn2_(WWk), pp2_(UUp) + pn2_(UU)), eps), mx_new, mn_new);
       smx[(kb_ & 1) * P + tid] = mx_new;
       smn[(kb_ & 1) * P + tid] = mn_new;
     }
@@ -180,13 +191,13 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_mpdata(CrmP p, double *f, doub
     double WWlim_kp1 = 0.;
     if (vB && kb_ >= 2) {
       const double WWl = WW_prev;
-      WWlim_kp1 = pp_(WWl) * dmin(dmin(1., mx_new), mn_prev) - pn_(WWl) * dmin(dmin(1., mx_prev), mn_new);
+      WWlim_kp1 = lim_flux(WWl, mx_new, mn_prev, mx_prev, mn_new);
     }
     double ULim = 0.;
     if (vC) {
       const double mx_c = smx[(kc_ & 1) * P + tid], mx_m = smx[(kc_ & 1) * P + tm1];
       const double mn_c = smn[(kc_ & 1) * P + tid], mn_m = smn[(kc_ & 1) * P + tm1];
-      ULim = pp_(UU_prev) * dmin(dmin(1., mx_c), mn_m) - pn_(UU_prev) * dmin(dmin(1., mx_m), mn_c);
+      ULim = lim_flux(UU_prev, mx_c, mn_m, mx_m, mn_c);
       sUL[tid] = ULim;
     }
     __syncthreads();   // (4)
@@ -263,15 +274,15 @@ __global__ void __launch_bounds__(CRM_MAX_P, 3) k_mpdata(CrmP p, double *f, doub
     const double UUp = sUU[tp1];
     const double rho_b = pr[-2 * CT], iadz_b = pr[-4 * CT];
     double mx_new, mn_new;
-    ratio2(rho_b * (mxr - c_F1b), pn_(UUp) + pp_(UU) + iadz_b * (pn_(WW_ka) + pp_(WW_prev)) + eps,
-           rho_b * (c_F1b - mnr), pp_(UUp) + pn_(UU) + iadz_b * (pp_(WW_ka) + pn_(WW_prev)) + eps, mx_new, mn_new);
+    ratio2(rho_b * (mxr - c_F1b), fma(0.5, fma(iadz_b, pn2_(WW_ka) + pp2_(WW_prev), pn2_(UUp) + pp2_(UU)), eps),
+           rho_b * (c_F1b - mnr), fma(0.5, fma(iadz_b, pp2_(WW_ka) + pn2_(WW_prev), pp2_(UUp) + pn2_(UU)), eps), mx_new, mn_new);
     smx[X_B * P + tid] = mx_new;
     smn[X_B * P + tid] = mn_new;
     __syncthreads();   // (3)
     // ---- stage C: level ka-2
-    const double WWlim_kp1 = WW_prev * (WW_prev > 0. ? dmin(dmin(1., mx_new), mn_prev) : dmin(dmin(1., mx_prev), mn_new));
+    const double WWlim_kp1 = lim_flux(WW_prev, mx_new, mn_prev, mx_prev, mn_new);
     const double mx_m = smx[X_C * P + tm1], mn_m = smn[X_C * P + tm1];
-    const double ULim = UU_prev * (UU_prev > 0. ? dmin(dmin(1., mx_prev), mn_m) : dmin(dmin(1., mx_m), mn_prev));
+    const double ULim = lim_flux(UU_prev, mx_prev, mn_m, mx_m, mn_prev);
     sUL[tid] = ULim;
     __syncthreads();   // (4)
     const double ULp = sUL[tp1];
@@ -534,14 +545,14 @@ __global__ void __launch_bounds__(CRM_LB(NXT), CRM_LBMIN(NXT, 3)) k_precip_b(Crm
         const double wwc = (k2 == nzm) ? ww1 : ww2;   // www(min(nzm,k2+1))
         const double ra = S_RA(k2);
         // a zero numerator gives exactly +0 (the denominators are >= eps > 0): skip the two divisions in precipitation-free air
-        ratio2(ra * (mx - tq1), pn_(wwc) + pp_(ww1) + eps, ra * (tq1 - mn), pp_(wwc) + pn_(ww1) + eps, mxn1, mnn1);
+        ratio2(ra * (mx - tq1), fma(0.5, pn2_(wwc) + pp2_(ww1), eps), ra * (tq1 - mn), fma(0.5, pp2_(wwc) + pn2_(ww1), eps), mxn1, mnn1);
       } else { mxn1 = 0.; mnn1 = 0.; }
       // ---- limited flux at k2: fz(k2) + pp(www)*min(1,mx(k2),mn(kb)) - pn(www)*min(1,mx(kb),mn(k2))
       fzl0 = fzl1;
       if (k2 >= 1 && k2 <= nzm) {
         const double mxb = (k2 == 1) ? mxn1 : mxn0, mnb = (k2 == 1) ? mnn1 : mnn0;
         const double fzk2 = q1 * w1;
-        fzl1 = fzk2 + pp_(ww1) * dmin(dmin(1., mxn1), mnb) - pn_(ww1) * dmin(dmin(1., mxb), mnn1);
+        fzl1 = fzk2 + lim_flux(ww1, mxn1, mnb, mxb, mnn1);
       } else fzl1 = 0.;   // fz(nz) = 0
       // ---- final update at k3 = s-3
       if (k3 >= 1) {   // k3 <= KT by the loop bound
@@ -831,12 +842,12 @@ __global__ void __launch_bounds__(CRM_LB(NXT), CRM_LBMIN(NXT, 4)) k_p8_micro(Crm
   int *cnt = qcell + NC;                   // [2][NL*nw] class counts per (level, warp)
   int *sflag = cnt + CRM_P8_CNT(P);        // [NL][2*CT+1 (<= 40)]
   const int sub = tid & 31, wrp = tid >> 5, nw = P >> 5;
-  double t[NL], q[NL], qp[NL];
+  double t[NL], q[NL], qp[NL], uu[NL];   // uu: only needed by the slab sums at the end, but loaded here so that its latency is not exposed there
 #pragma unroll
   for (int l = 0; l < NL; l++) {
     const int k = k0 + l;
-    if (k <= p.nzm) { t[l] = F3(p.t, k); q[l] = F3(p.qt, k); qp[l] = F3(p.qp, k); }
-    else { t[l] = 0.; q[l] = 0.; qp[l] = 0.; }
+    if (k <= p.nzm) { t[l] = F3(p.t, k); q[l] = F3(p.qt, k); qp[l] = F3(p.qp, k); uu[l] = F3(p.u, k); }
+    else { t[l] = 0.; q[l] = 0.; qp[l] = 0.; uu[l] = 0.; }
   }
   for (int f = tid; f < NL * 40; f += P) sflag[f] = 0;
   int nA = 0, nB = 0;
@@ -925,7 +936,7 @@ __global__ void __launch_bounds__(CRM_LB(NXT), CRM_LBMIN(NXT, 4)) k_p8_micro(Crm
       if (qcl + qci > 0. && tabs < R4(273.15)) sf[lane] = 1;
     }
     double v[NQ];
-    v[0] = F3(p.u, k); v[1] = t[l]; v[2] = tabs; v[3] = qv + qcl + qci; v[4] = qcl + qci; v[5] = qpl + qpi; v[6] = dsrc; v[7] = devp;
+    v[0] = uu[l]; v[1] = t[l]; v[2] = tabs; v[3] = qv + qcl + qci; v[4] = qcl + qci; v[5] = qpl + qpi; v[6] = dsrc; v[7] = devp;
     if (D3) v[NQ - 1] = F3(p.v, k);
     tr_put<NQ>(v, tid, NC, X + l * P);   // own column of X: nobody else reads it after phase 1
   }
