@@ -297,6 +297,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
     PRF(*f);
   for (double **f : {&p.dz, &p.z0, &p.colprec0, &p.colprecs0, &p.s_cltot, &p.s_clhgh, &p.s_clmed, &p.s_cllow}) SL(*f);
   p.micro = d->micro;
+  p.m25_order = getenv("CRM_B200_M25_ORDER") ? atoi(getenv("CRM_B200_M25_ORDER")) : 1;
   if (h->m25) {
     for (int n = 2; n <= 10; n++) F(p.mf[n]);
     for (int q = 0; q < 8; q++) { F(p.m_rate[q]); F(p.m_ratea[q]); }
@@ -318,7 +319,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   p.kmin = carve<int>(h, h->slot_elems); p.kmax = carve<int>(h, h->slot_elems); p.ndamp = carve<int>(h, h->slot_elems);
   p.kprec = carve<int>(h, h->ntiles); p.kqp = carve<int>(h, h->ntiles);
   p.precsfc = carve<double>(h, h->col_elems); p.precssfc = carve<double>(h, h->col_elems);
-  p.cfl_bits = carve<unsigned long long>(h, 2); p.prec_cfl_bits = p.cfl_bits ? p.cfl_bits + 1 : nullptr;
+  p.cfl_bits = carve<unsigned long long>(h, 3); p.prec_cfl_bits = p.cfl_bits ? p.cfl_bits + 1 : nullptr;   // [2]: max of prec_cfl over the call
   p.flags = carve<int>(h, 4);
   p.twc = carve<double>(h, d->nx + d->ny); p.tws = carve<double>(h, d->nx + d->ny);   // x table, then y table
   h->stage = carve<double>(h, (size_t)d->ld * d->nx * d->ny * d->nzm);
@@ -436,7 +437,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
     zrc |= dev_zero(f, pbytes);
   for (double *f : {p.s_cltot, p.s_clhgh, p.s_clmed, p.s_cllow}) zrc |= dev_zero(f, (size_t)ntiles * CT * 8);
   zrc |= dev_zero(p.precsfc, (size_t)ntiles * P * 8); zrc |= dev_zero(p.precssfc, (size_t)ntiles * P * 8);
-  zrc |= dev_zero(p.cfl_bits, 16); zrc |= dev_zero(p.flags, 16);
+  zrc |= dev_zero(p.cfl_bits, 24); zrc |= dev_zero(p.flags, 16);
   if (m25) {
     for (int q = 0; q < 8; q++) { zrc |= dev_zero(p.m_rate[q], fbytes); zrc |= dev_zero(p.m_ratea[q], fbytes); }
     for (int q = 0; q < 4; q++) zrc |= dev_zero(p.m_rad[q], (size_t)ntiles * nzm * nrad * CT * 8);
@@ -729,15 +730,14 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
     p.nstop = nstop;
     LAUNCH_G(h, k_stats, ntiles, P, d3 ? CRM_STATS3_SMEM(P, CT, h->nzp) : CRM_STATS_SMEM(P, CT, h->nzp, !(((nx / d->nx_rad) * CT <= 32) && !((nx / d->nx_rad) & ((nx / d->nx_rad) - 1)))), p);
     if (m25) LAUNCH(h, k_m2005_rad, ntiles * nzm, nrad * CT, 0, p);
-    // nprec statistic (device value of the last sub-step)
-    if (!m25 && ((nstep & 15) == 0 || nstep == nstop)) {
-      unsigned long long pb2 = 0; dev_copy2d(&pb2, 8, p.prec_cfl_bits, 8, 8, 1, 1);
-      double pc; memcpy(&pc, &pb2, 8);
-      long long np_ = pc > R4(0.9) ? (long long)std::ceil(pc / R4(0.9)) : 1;
-      nprec_max = std::max(nprec_max, np_);
-    }
   }
   p.nstop = nstop;
+  if (!m25 && !dbg_break) {   // nprec statistic: the maximum of prec_cfl over every sub-step of the call, accumulated on the device (k_precip_a)
+    unsigned long long pb2 = 0;
+    if (dev_copy2d(&pb2, 8, p.prec_cfl_bits + 1, 8, 8, 1, 1)) return fail(h, 31, "crm_b200_run: nprec readback failed");
+    double pc; memcpy(&pc, &pb2, 8);
+    nprec_max = pc > R4(0.9) ? (long long)std::ceil(pc / R4(0.9)) : 1;
+  }
 
   // ---------------- epilogue ----------------
   ExtOut eo;

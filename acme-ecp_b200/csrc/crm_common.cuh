@@ -94,7 +94,7 @@ struct CrmP {
   double *tl, *ql, *qccl, *qiil, *uln;   // GCM profiles on CRM levels
   double *v0, *vtend, *vln, *vwle, *vwsb, *acc_v;   // 3-D CRMs only
   // ---- m2005 (micro = 1): micro_field(:,:,:,:,n) = mf[n], n = 2..10 (nc, qr, nr, qi, ni, qs, ns, qg, ng); mf[1] = qt; cloudliq lives in qn ----
-  int micro;
+  int micro, m25_order;
   double *mf[11];
   double *m_rate[8], *m_ratea[8];        // aut1..con1 and their time integrals aut1a..con1a (3-D)
   double *m_rad[4];                      // crm_rad nc, ni, qs, ns accumulators

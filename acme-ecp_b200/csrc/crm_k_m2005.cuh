@@ -38,9 +38,11 @@ __global__ void __launch_bounds__(CRM_M25_COLS, MINB) k_m2005_column(CrmP p, dou
   const int P = p.P, CT = p.CT;
   const long long c = (long long)blockIdx.x * CRM_M25_COLS + threadIdx.x;
   if (c >= (long long)ntiles_chunk * P) return;
-  const int tl = (int)(c / P), tid = (int)(c - (long long)tl * P), tile = tile0 + tl;
-  const int i = tid / CT, lane = tid - i * CT;
-  (void)i;
+  // column order inside a tile: (lane, cell), i.e. a warp holds 32 ADJACENT columns of ONE CRM (clouds span several columns of a
+  // CRM, different CRMs are unrelated: fewer warps that have to execute both the active and the clear-air paths of a level)
+  const int tl = (int)(c / P), r = (int)(c - (long long)tl * P), tile = tile0 + tl;
+  const int ncell = P / CT;
+  const int lane = p.m25_order ? r / ncell : r % CT, i = p.m25_order ? r - lane * ncell : r / CT, tid = i * CT + lane;
   const long long fb = (long long)tile * p.tstride;
   const int pb = tile * p.nzp * CT + lane;
   const int cb = tile * CT + lane;
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(CRM_MAX_P3) k_m2005_scatter(CrmP p, double *sc
   const int cb = tile * CT + lane;
   CRM_DYN_SMEM(double, red);
   const int nzm = p.nzm;
-  M25Col a; a.s = scr; a.n = (unsigned)(ntiles_chunk * P); a.nz = nzm; a.col = (unsigned)(blockIdx.x * P + tid);
+  M25Col a; a.s = scr; a.n = (unsigned)(ntiles_chunk * P); a.nz = nzm; a.col = (unsigned)(blockIdx.x * P + (p.m25_order ? lane * (P / CT) + i : tid));   // k_m2005_column's column order
   const double dtn = p.dtn, dz = p.dz[cb];
   for (int k = 1; k <= nzm; k++) {
     const int rid[8] = {AUT, ACC, EVPC, EVPR, MLT, SUB, DEP, CON};

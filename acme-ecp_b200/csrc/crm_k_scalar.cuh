@@ -416,7 +416,8 @@ __global__ void __launch_bounds__(CRM_LB(NXT)) k_precip_a(CrmP p) {
   if (kt > 0) atomicMax(&s_kt, kt);
   const double m = block_max_all(cfl, tid, P, red);
   if (tid == 0) {
-    atomicMax(p.prec_cfl_bits, (unsigned long long)__double_as_longlong(m));
+    atomicMax(p.prec_cfl_bits, (unsigned long long)__double_as_longlong(m));       // this sub-step (reset by the host before the launch)
+    atomicMax(p.prec_cfl_bits + 1, (unsigned long long)__double_as_longlong(m));   // whole call (crm_run_stats_t.nprec_max)
     p.kprec[tile] = s_kt;
   }
 }
@@ -476,8 +477,7 @@ __global__ void __launch_bounds__(CRM_LB(NXT), CRM_LBMIN(NXT, 3)) k_precip_b(Crm
       // the ring re-reads what this block has just written with ordinary stores: order them before the bulk copies
       asm volatile("fence.proxy.async;" ::: "memory");
 #endif
-      __syncthreads();
-      R.init(smraw, P, tid);   // fresh barrier phases
+      R.reinit(tid);   // barrier, invalidate + re-initialise the mbarriers (fresh phases), barrier
     }
     CRM_PIPE_PROLOGUE(R, KT, 2, 0)
     const bool scale_wp = (iprec == 1 && nprec > 1);   // wp = wp/nprec (microphysics.F90:648-660); later iterations read scaled wp

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(CRM_LB(NXT)) k_stats(CrmP p) {
     if (tid == 0) { if (kk - 2 >= 1) A.issue(kk - 2); if (!D3 && kk - 1 >= 1) B.issue(kk - 1); }
     double w_own = 0., qv_own = 0.;
     if (D3) { w_own = F3(p.w, kk); qv_own = F3(p.qv, kk); }
-    if (kk < nzm) red_get<10>(tid, P, CT, red + ((kk + 1) & 1) * RS, [&](int q, int ln, double sum) { book(q, ln, sum, kk + 1); });
+    if (!D3 && kk < nzm) red_get<10>(tid, P, CT, red + ((kk + 1) & 1) * RS, [&](int q, int ln, double sum) { book(q, ln, sum, kk + 1); });
     if (kk - 1 >= 1) A.wait_desc(kk - 1, nzm);
     if (!D3) B.wait_desc(kk, nz);
     const double qcl = A.plane(0, kk)[tid], qci = A.plane(1, kk)[tid];
@@ -101,7 +101,20 @@ __global__ void __launch_bounds__(CRM_LB(NXT)) k_stats(CrmP p) {
       else if (A.plane(3, kx)[tid] + A.plane(4, kx)[tid] > R4(1.0e-4)) mdi = SPF(3, kk) * w_k;
     }
     double v[10] = {cld, mcup, mcdn, mcuup, mcudn, qcl, qci, top_hit, mui, mdi};
-    red_put<10>(v, tid, CT, red + (kk & 1) * RS);   // finished after the next barrier (deferred: one barrier per level)
+    if (!D3) red_put<10>(v, tid, CT, red + (kk & 1) * RS);   // finished after the next barrier (deferred: one barrier per level)
+    else {
+      // 3-D tiles (up to 32 warps, CT = 1 at 32x32): ten shuffle trees per thread were 45 % of the kernel's instructions
+      // (profiles/r02b).  Transposed slab sums through the 5*P doubles of srad instead, five statistics per round: every thread
+      // stores its values, warp q adds the P values of statistic q (fixed order) - ~40 instead of ~250 instructions per thread.
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        __syncthreads();   // srad is free (radiation sums of the previous level / reads of the previous round)
+        const double vv[5] = {v[5 * r], v[5 * r + 1], v[5 * r + 2], v[5 * r + 3], v[5 * r + 4]};
+        tr_put<5>(vv, tid, P, srad);
+        __syncthreads();
+        tr_get<5>(tid, P, CT, P, srad, [&](int q, int ln, double sum) { book(q + 5 * r, ln, sum, kk); });
+      }
+    }
     // radiation-group accumulators (crm_module.F90:979-1015): groups of nx/nx_rad adjacent columns
     const double tabs = A.plane(2, kk)[tid], qv = D3 ? qv_own : B.plane(1, kk)[tid];
     double a[5] = {tabs, dmax(0., qv), qcl, qci, (qcl + qci > 0) ? 1. : 0.};
@@ -159,7 +172,7 @@ __global__ void __launch_bounds__(CRM_LB(NXT)) k_stats(CrmP p) {
     }
   }
   __syncthreads();
-  red_get<10>(tid, P, CT, red + (1 & 1) * RS, [&](int q, int ln, double sum) { book(q, ln, sum, 1); });
+  if (!D3) red_get<10>(tid, P, CT, red + (1 & 1) * RS, [&](int q, int ln, double sum) { book(q, ln, sum, 1); });
   // w-level nz (k = nzm+1 of crm_module.F90:1023): w(nz) = 0 -> no contribution.
   double v[4];
   v[0] = (cwp > cwp_threshold) ? cttemp : 0.; v[1] = (cwph > cwp_threshold) ? chtemp : 0.;

@@ -24,6 +24,9 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)_
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_inval(unsigned long long *bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -67,6 +70,20 @@ struct PlanePipe {
     if (tid == 0) {
 #pragma unroll
       for (int s = 0; s < NS; s++) mbar_init(bar + s, 1);
+      mbar_fence_init();
+    }
+#endif
+    __syncthreads();
+  }
+  // Start a new march over the same shared memory (fresh barrier phases).  All waits of the previous march must have completed;
+  // the live mbarrier objects are invalidated before they are initialised again (PTX: mbarrier.init on a location that holds a
+  // valid mbarrier object is undefined behaviour without mbarrier.inval).
+  __device__ __forceinline__ void reinit(int tid) {
+    __syncthreads();
+#ifndef CRM_EMU
+    if (tid == 0) {
+#pragma unroll
+      for (int s = 0; s < NS; s++) { mbar_inval(bar + s); mbar_init(bar + s, 1); }
       mbar_fence_init();
     }
 #endif

@@ -22,6 +22,8 @@ def _check(emu, dims, spin, tol):
     dims, inp, st, rad = cm.make_case(dims, spinup_steps=spin)
     ro, rg = cm.run_both(dims, inp, st, rad, lib_path=emu)
     assert rg[3]["nstop"] == ro[3]["nstop"] and rg[3]["ncycle_sum"] == ro[3]["ncycle_sum"]
+    if dims.micro == 0:
+        assert rg[3]["nprec_max"] == ro[3]["nprec_max"]          # maximum over every sub-step of the call, accumulated on the device
     bad = cm.compare_all(dims, ro, rg, tol)
     assert not bad, bad
     return ro, rg

@@ -19,6 +19,8 @@ def _check(dims, spin, tol, **kw):
     ro, rg = cm.run_both(dims, inp, st, rad)
     assert rg[3]["kernel_launches"] > 0
     assert rg[3]["nstop"] == ro[3]["nstop"] and rg[3]["ncycle_sum"] == ro[3]["ncycle_sum"]
+    if dims.micro == 0:
+        assert rg[3]["nprec_max"] == ro[3]["nprec_max"]          # maximum over every sub-step of the call, accumulated on the device
     bad = cm.compare_all(dims, ro, rg, tol, **kw)
     assert not bad, "fields beyond tolerance %g: %s" % (tol, bad)
     return ro, rg

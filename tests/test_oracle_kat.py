@@ -315,3 +315,23 @@ def test_precip_fall_conserves_water_and_only_moves_it_down():
     assert np.all(qp[:8] == 0.0) and np.all(prec[:8] == 0.0) and np.array_equal(t[:8], t0[:8])
     assert np.all(qp[:, top:] == 0.0)                     # sedimentation never moves water upward
     assert np.abs(qp - qp0).max() > 1e-5                  # and it did move
+
+
+def test_spmomtrans_tendencies_use_the_raw_slab_sum():
+    """crm_module.F90:1200-1211 forms ultend/vltend BEFORE uln/vln are scaled by factor_xy (:1214-1224): the reference's tendency is
+    (SUM over the nx*ny columns of u  -  ul) / dt_gl, not (mean - ul) / dt_gl.  Quirk reproduced (INTEGRATION.md
+    section 4); this test pins the chosen behaviour from the returned state alone."""
+    dims = cm.pkg.CrmDims(ncrms=3, nx=8, ny=8, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=40.0, igstep=3, nx_rad=2, ny_rad=2)
+    dims, inp, st, rad = cm.make_case(dims, spinup_steps=0)
+    out, _ = ob.run(dims, inp, st, rad)
+    n, plev, nzm = dims.ncrms, dims.plev, dims.nzm
+    ptop = plev - nzm + 1                                         # 1-based GCM level of the CRM top
+    for name, fld, gcm in (("ultend", st.u_wind, inp.ul), ("vltend", st.v_wind, inp.vl)):
+        got = getattr(out, name)[:n]
+        exp = np.zeros((n, plev))
+        for k in range(nzm):
+            l = plev - 1 - k
+            exp[:, l] = (fld[:n, :, :, k].reshape(n, -1).sum(axis=1) - gcm[:n, l]) / dims.dt_gl
+        exp[:, ptop - 1:ptop + 1] = 0.0                           # "don't use tendencies from two top levels"
+        assert np.abs(got[:, ptop - 1:]).max() > 1.0                  # sums of 64 columns: far from a mean-based tendency
+        assert np.abs(got - exp).max() <= 1e-12 * np.abs(exp).max(), name
