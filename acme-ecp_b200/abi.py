@@ -18,7 +18,7 @@ class crm_dims_t(C.Structure):
                 ("dx", C.c_double), ("dt", C.c_double), ("dt_gl", C.c_double),
                 ("igstep", C.c_int), ("micro", C.c_int),
                 ("use_crm_accel", C.c_int), ("crm_accel_uv", C.c_int), ("crm_accel_factor", C.c_double),
-                ("twiddle_f32", C.c_int)]
+                ("twiddle_f32", C.c_int), ("esmt", C.c_int)]
 
 
 # (name, shape-kind): "lev"=(ld,plev) "ilev"=(ld,plev+1) "col"=(ld)
@@ -30,8 +30,11 @@ INPUT_FIELDS = [("zmid", "lev"), ("zint", "ilev"), ("tl", "lev"), ("ql", "lev"),
                 ("lat_deg", "col"), ("lon_deg", "col")]
 
 
+INPUT_FIELDS_ESMT = [("ul_esmt", "lev"), ("vl_esmt", "lev")]   # SP_ESMT builds (crm_input_module.F90:39-42), ABI 4
+
+
 class crm_input_t(C.Structure):
-    _fields_ = [(n, c_dp) for n, _ in INPUT_FIELDS] + [("gcol", c_ip)]
+    _fields_ = [(n, c_dp) for n, _ in INPUT_FIELDS] + [("gcol", c_ip)] + [(n, c_dp) for n, _ in INPUT_FIELDS_ESMT]
 
 
 STATE_FIELDS_SAM1MOM = ["u_wind", "v_wind", "w_wind", "temperature", "qt", "qp", "qn"]
@@ -69,8 +72,11 @@ OUTPUT_FIELDS_M2005 = (
                           "aut_a", "acc_a", "evpc_a", "evpr_a", "mlt_a", "sub_a", "dep_a", "con_a")])
 
 
+OUTPUT_FIELDS_ESMT = [("u_tend_esmt", "lev"), ("v_tend_esmt", "lev")]   # SP_ESMT builds (crm_output_module.F90:81-84), ABI 4
+
+
 class crm_output_t(C.Structure):
-    _fields_ = [(n, c_dp) for n, _ in OUTPUT_FIELDS + OUTPUT_FIELDS_M2005]
+    _fields_ = [(n, c_dp) for n, _ in OUTPUT_FIELDS + OUTPUT_FIELDS_M2005 + OUTPUT_FIELDS_ESMT]
 
 
 class crm_run_stats_t(C.Structure):

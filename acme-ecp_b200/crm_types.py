@@ -18,7 +18,7 @@ class CrmDims:
     """Compile-time constants of the reference (PHYS/crmdims.F90:13-22) + hidden module inputs of crm()."""
 
     def __init__(self, ncrms, nx, ny, nzm, plev, dx, dt, dt_gl=1800.0, ld=None, nx_rad=None, ny_rad=None,
-                 igstep=3, micro=0, use_crm_accel=False, crm_accel_uv=False, crm_accel_factor=0.0, twiddle_f32=False):
+                 igstep=3, micro=0, use_crm_accel=False, crm_accel_uv=False, crm_accel_factor=0.0, twiddle_f32=False, esmt=False):
         self.ncrms, self.nx, self.ny, self.nzm, self.plev = int(ncrms), int(nx), int(ny), int(nzm), int(plev)
         self.ld = int(ld if ld is not None else ncrms)
         self.nx_rad = int(nx_rad if nx_rad is not None else max(1, nx // 4))
@@ -29,6 +29,7 @@ class CrmDims:
         self.use_crm_accel, self.crm_accel_uv = bool(use_crm_accel), bool(crm_accel_uv)
         self.crm_accel_factor = float(crm_accel_factor)
         self.twiddle_f32 = bool(twiddle_f32)
+        self.esmt = bool(esmt)   # -DSP_ESMT: explicit scalar momentum transport (scalar_momentum.F90)
 
     def c_struct(self):
         d = abi.crm_dims_t()
@@ -62,13 +63,21 @@ class crm_input_type(_Bag):
         for n, kind in abi.INPUT_FIELDS:
             setattr(self, n, np.zeros(abi.shape_of(kind, dims), order="F"))
         self.gcol = np.zeros(dims.ld, dtype=np.int32)
+        if getattr(dims, "esmt", False):   # crm_input_module.F90:110-113 (allocated only in SP_ESMT builds)
+            for n, kind in abi.INPUT_FIELDS_ESMT:
+                setattr(self, n, np.zeros(abi.shape_of(kind, dims), order="F"))
         return self
+
+    def names(self):
+        return [n for n, _ in abi.INPUT_FIELDS] + ["gcol"] + [n for n, _ in abi.INPUT_FIELDS_ESMT if getattr(self, n, None) is not None]
 
     def c_struct(self):
         s = abi.crm_input_t()
         for n, _ in abi.INPUT_FIELDS:
             setattr(s, n, abi.dptr(getattr(self, n)))
         s.gcol = abi.iptr(self.gcol)
+        for n, _ in abi.INPUT_FIELDS_ESMT:
+            setattr(s, n, abi.dptr(getattr(self, n, None)))
         return s
 
 
@@ -127,13 +136,14 @@ class crm_output_type(_Bag):
 
     def initialize(self, dims):
         """crm_output_initialize(output, ncol, nlev): allocate + zero (CRM/crm_output_module.F90:138-330)."""
-        for n, kind in abi.OUTPUT_FIELDS + (abi.OUTPUT_FIELDS_M2005 if getattr(dims, "micro", 0) == 1 else []):
+        for n, kind in (abi.OUTPUT_FIELDS + (abi.OUTPUT_FIELDS_M2005 if getattr(dims, "micro", 0) == 1 else []) +
+                        (abi.OUTPUT_FIELDS_ESMT if getattr(dims, "esmt", False) else [])):
             setattr(self, n, np.zeros(abi.shape_of(kind, dims), order="F"))
         return self
 
     def c_struct(self):
         s = abi.crm_output_t()
-        for n, _ in abi.OUTPUT_FIELDS + abi.OUTPUT_FIELDS_M2005:
+        for n, _ in abi.OUTPUT_FIELDS + abi.OUTPUT_FIELDS_M2005 + abi.OUTPUT_FIELDS_ESMT:
             setattr(s, n, abi.dptr(getattr(self, n, None)))
         return s
 

@@ -14,6 +14,7 @@
 #include "../../include/crm_b200.h"
 #include "crm_k_stats.cuh"
 #include "crm_k_m2005.cuh"
+#include "crm_k_esmt.cuh"
 #include "crm_host_util.h"
 
 using namespace crm;
@@ -218,6 +219,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   g_init_err.clear();
   *handle = nullptr;
   if (d->micro != 0 && d->micro != 1) { g_init_err = "crm_b200_init: micro must be 0 (sam1mom) or 1 (m2005)"; return 2; }
+  if (d->esmt != 0 && d->esmt != 1) { g_init_err = "crm_b200_init: esmt must be 0 or 1"; return 2; }
   const bool d3 = d->ny > 1;
   if (d->ny < 1 || (d3 && !d->yes3d) || (!d3 && d->yes3d)) { g_init_err = "crm_b200_init: RUN3D/YES3D mismatch: ny > 1 needs yes3d = 1, ny = 1 needs yes3d = 0 (setparm.F90:55-62)"; return 3; }
   if (d->nx < 8 || (d->nx & (d->nx - 1))) { g_init_err = "crm_b200_init: nx must be a power of two >= 8"; return 4; }
@@ -297,6 +299,12 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
     PRF(*f);
   for (double **f : {&p.dz, &p.z0, &p.colprec0, &p.colprecs0, &p.s_cltot, &p.s_clhgh, &p.s_clmed, &p.s_cllow}) SL(*f);
   p.micro = d->micro;
+  p.esmt = d->esmt;
+  if (d->esmt) {
+    F(p.u_esmt); F(p.v_esmt); F(p.esmt_s1); F(p.esmt_s2); SL(p.esmt_off);
+    double *tw = carve<double>(h, 2 * (size_t)d->nx); ok = ok && tw;
+    p.esmt_tw = tw;
+  }
   p.m25_order = getenv("CRM_B200_M25_ORDER") ? atoi(getenv("CRM_B200_M25_ORDER")) : 1;
   if (h->m25) {
     for (int n = 2; n <= 10; n++) F(p.mf[n]);
@@ -324,8 +332,8 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   p.twc = carve<double>(h, d->nx + d->ny); p.tws = carve<double>(h, d->nx + d->ny);   // x table, then y table
   h->stage = carve<double>(h, (size_t)d->ld * d->nx * d->ny * d->nzm);
   h->esum = carve<double>(h, (size_t)CRM_NESUM * h->prof_elems);
-  h->in_dev = carve<double>(h, (size_t)d->ld * (11 * (size_t)(d->plev + 1) + 8));
-  h->out_dev = carve<double>(h, (size_t)d->ld * ((41 + 13) * (size_t)d->plev + 16 + (size_t)d->nx * d->ny));
+  h->in_dev = carve<double>(h, (size_t)d->ld * ((11 + 2) * (size_t)(d->plev + 1) + 8));
+  h->out_dev = carve<double>(h, (size_t)d->ld * ((41 + 13 + 2) * (size_t)d->plev + 16 + (size_t)d->nx * d->ny));
   h->rnd_dev = carve<double>(h, (size_t)d->ncrms * 5 * d->nx * d->ny);
   h->gcol_dev = carve<int>(h, d->ld);
   ok = ok && p.kmin && p.kmax && p.ndamp && p.kprec && p.kqp && p.precsfc && p.precssfc && p.cfl_bits && p.flags && p.twc && p.tws && h->stage && h->esum &&
@@ -403,8 +411,10 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   h->err.clear();
   const crm_dims_t &d0 = h->d0;
   if (d->nx != d0.nx || d->ny != d0.ny || d->nzm != d0.nzm || d->plev != d0.plev || d->nx_rad != d0.nx_rad || d->ny_rad != d0.ny_rad ||
-      d->dx != d0.dx || d->dt != d0.dt || d->micro != d0.micro)
+      d->dx != d0.dx || d->dt != d0.dt || d->micro != d0.micro || d->esmt != d0.esmt)
     return fail(h, 20, "crm_b200_run: geometry differs from crm_b200_init");
+  if (d->esmt && !(in->ul_esmt && in->vl_esmt && out->u_tend_esmt && out->v_tend_esmt))
+    return fail(h, 23, "crm_b200_run: esmt = 1 needs crm_input ul_esmt, vl_esmt and crm_output u_tend_esmt, v_tend_esmt");
   if (d->ncrms < 1 || d->ncrms > d0.ncrms || d->ld < d->ncrms || d->ld > h->ld_max) return fail(h, 21, "crm_b200_run: need ncrms <= init ncrms and ncrms <= ld <= init ld");
   if (select_handle(h)) return fail(h, 22, std::string("crm_b200_run: cannot select device: ") + dev_errstr());
   auto wall0 = std::chrono::steady_clock::now();
@@ -448,6 +458,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   DevTimer tm;
   tm.start();
   long long h2d = 0;
+  const double *esmt_ul = nullptr, *esmt_vl = nullptr;   // staged crm_input%ul_esmt, vl_esmt
   ExtIn ei;
   {
     double *q = h->in_dev;
@@ -462,6 +473,13 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
     ei.pdel = put(in->pdel, plev); ei.ul = put(in->ul, plev); ei.vl = put(in->vl, plev);
     ei.tau00 = put(in->tau00, 1); ei.wndls = put(in->wndls, 1); ei.bflxls = put(in->bflxls, 1);
     ei.gcol = h->gcol_dev;
+    if (d->esmt) { esmt_ul = put(in->ul_esmt, plev); esmt_vl = put(in->vl_esmt, plev); }
+  }
+  if (d->esmt) {   // FP64 cos / sin table of the ESMT x-transform (independent of twiddle_f32: FFTPACK 5.1 builds its own tables in real(crm_rknd))
+    std::vector<double> c, s;
+    twiddles(nx, false, c, s);
+    zrc |= dev_copy2d(const_cast<double *>(p.esmt_tw), nx * 8, c.data(), nx * 8, nx * 8, 1, 1);
+    zrc |= dev_copy2d(const_cast<double *>(p.esmt_tw) + nx, nx * 8, s.data(), nx * 8, nx * 8, 1, 1);
   }
   // twiddles
   {
@@ -526,6 +544,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   LAUNCH(h, k_prologue_grid, slot_blocks, 128, 0, p, ei);
   if (m25) LAUNCH(h, k_m2005_prologue, ntiles, P, 0, p);
   LAUNCH(h, k_prologue_fields, ntiles, P, red_bytes(9), p);
+  if (d->esmt) LAUNCH(h, k_esmt_init, ntiles * nzm, P, 0, p, esmt_ul, esmt_vl);
   if (!m25) LAUNCH(h, k_precip_init, (ntiles * nzm * CT + 127) / 128, 128, 0, p);   // crm_module.F90:672-674 (#ifdef sam1mom)
   if (d->igstep <= 1) {   // setperturb (crm_module.F90:677-681): RNG draws on the host like the reference
     std::vector<double> rnd((size_t)ncrms * 5 * nxy);
@@ -671,6 +690,14 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
 #ifndef CRM_EMU
       if (fork) for (int q = 0; q < 2; q++) { cudaEventRecord(h->ev_join[q], h->side[q]); cudaStreamWaitEvent(h->stream, h->ev_join[q], 0); }
 #endif
+      if (d->esmt) {   // advect_all_scalars.F90:74-88: scalar momentum, made positive definite by a per-CRM offset around the advection
+        LAUNCH(h, k_esmt_offset, ntiles, P, (size_t)P * 8, p, 1);
+        for (double *f : {p.u_esmt, p.v_esmt}) {
+          if (d3) LAUNCH(h, k3_mpdata, ntiles, P, CRM3_MP_SMEM(P, CT, h->nzp), p, f, (double *)nullptr, (double *)nullptr, 0, (const int *)nullptr);
+          else LAUNCH_G(h, k_mpdata, ntiles, P, smem_mp, p, f, (double *)nullptr, (double *)nullptr, 0, (const int *)nullptr);
+        }
+        LAUNCH(h, k_esmt_offset, ntiles, P, (size_t)P * 8, p, -1);
+      }
       if (dbg_stop == 5) { dbg_break = true; break; }
       if (!m25) {   // m2005: micro_precip_fall is a no-op, sedimentation happens inside the column scheme (MICRO_M2005/microphysics.F90:1425-1429)
         dev_zero(p.prec_cfl_bits, 8);
@@ -694,6 +721,14 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
         for (int q = 0; q < 4; q++) LAUNCH_G(h, k_diffuse_set, ntiles, P, CRM_DIFFSET_SMEM(P, CT, h->nzp), p, sets[q]);
       } else
       LAUNCH_G(h, k_p7_diffuse, ntiles, P, CRM_P7_SMEM(P, CT, h->nzp), p);
+      if (d->esmt) {   // sgs_scalars (sgs.F90:442-448) then scalar_momentum_tend (crm_module.F90:856-860)
+        DiffSet es;
+        memset(&es, 0, sizeof(es));
+        es.nf = 2; es.f[0] = p.u_esmt; es.f[1] = p.v_esmt;
+        LAUNCH_G(h, k_diffuse_set, ntiles, P, CRM_DIFFSET_SMEM(P, CT, h->nzp), p, es);
+        LAUNCH(h, k_esmt_pgf, ntiles, P, CRM_ESMT_SMEM(P, CT, nzm, d->ny), p, p.u_esmt);
+        LAUNCH(h, k_esmt_pgf, ntiles, P, CRM_ESMT_SMEM(P, CT, nzm, d->ny), p, p.v_esmt);
+      }
       if (dbg_stop == 7) { dbg_break = true; break; }
       if (icyc == 1 && !m25) LAUNCH(h, k_precip_init, (ntiles * nzm * CT + 127) / 128, 128, 0, p);
       LAUNCH(h, k_reset_kminmax, slot_blocks, 128, 0, p);
@@ -740,6 +775,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   }
 
   // ---------------- epilogue ----------------
+  double *esmt_ou = nullptr, *esmt_ov = nullptr;
   ExtOut eo;
   M25Out mo;
   memset(&mo, 0, sizeof(mo));
@@ -760,6 +796,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
                        &mo.dep_a, &mo.con_a};
       for (double **c : ml) *c = take(plev);
     }
+    if (d->esmt) { esmt_ou = take(plev); esmt_ov = take(plev); }
   }
   LAUNCH(h, k_epi_sums, ntiles * nzm, P, red_bytes(CRM_NESUM), p, h->esum);
   LAUNCH(h, k_epi_precip, ntiles, P, red_bytes(4), p, eo, dt);
@@ -768,6 +805,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
     LAUNCH(h, k_m2005_epi_sums, ntiles * nzm, P, red_bytes(CRM_M25_NESUM), p, h->esum2);
     LAUNCH(h, k_m2005_epi_profiles, (ncrms + 127) / 128, 128, 0, p, eo, mo, (const double *)h->esum2, dt, dtn);
   }
+  if (d->esmt) LAUNCH(h, k_esmt_epi, ntiles * nzm, P, red_bytes(2), p, esmt_ul, esmt_vl, esmt_ou, esmt_ov);
   if (dev_sync()) return fail(h, 31, std::string("crm_b200_run: kernel failure: ") + dev_errstr());
   if (!h->launch_err.empty()) return fail(h, 34, "crm_b200_run: a kernel launch failed");
   h->stats.ms_kernels = tk.stop();
@@ -798,6 +836,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
                     eo.qp_evp, eo.t_ls, eo.ultend, eo.vltend};
     for (int q = 0; q < 41; q++) give(hl[q], dl[q], plev);
     give(out->prec_crm, eo.prec_crm, (size_t)nx * d->ny);
+    if (d->esmt) { give(out->u_tend_esmt, esmt_ou, plev); give(out->v_tend_esmt, esmt_ov, plev); }
     if (m25) {
       double *hm[] = {out->nc_mean, out->ni_mean, out->ns_mean, out->ng_mean, out->nr_mean, out->aut_a, out->acc_a, out->evpc_a, out->evpr_a, out->mlt_a,
                       out->sub_a, out->dep_a, out->con_a};
@@ -947,6 +986,7 @@ extern "C" long long crm_b200_debug_fetch(void *handle, const char *name, double
   int nk = p.nzm;
   if (nm == "u") src = p.u; else if (nm == "v" && p.v) src = p.v; else if (nm == "dvdt" && p.v) src = p.dv_b; else if (nm == "dvdt_a" && p.v) src = p.dv_a; else if (nm == "dvdt_c" && p.v) src = p.dv_c;
   else if (nm == "vmf" && p.v) src = p.vmf; else if (nm == "w") { src = p.w; nk = p.nz; } else if (nm == "t") src = p.t; else if (nm == "qt") src = p.qt;
+  else if (nm == "u_esmt" && p.esmt) src = p.u_esmt; else if (nm == "v_esmt" && p.esmt) src = p.v_esmt;
   else if (nm == "qp") src = p.qp; else if (nm == "qn") src = p.qn; else if (nm == "tabs") src = p.tabs; else if (nm == "qv") src = p.qv;
   else if (nm == "qcl") src = p.qcl; else if (nm == "qci") src = p.qci; else if (nm == "qpl") src = p.qpl; else if (nm == "qpi") src = p.qpi;
   else if (nm == "tk") src = p.tk; else if (nm == "tkh") src = p.tkh; else if (nm == "tke") src = p.tke;

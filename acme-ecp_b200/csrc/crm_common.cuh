@@ -95,6 +95,11 @@ struct CrmP {
   double *v0, *vtend, *vln, *vwle, *vwsb, *acc_v;   // 3-D CRMs only
   // ---- m2005 (micro = 1): micro_field(:,:,:,:,n) = mf[n], n = 2..10 (nc, qr, nr, qi, ni, qs, ns, qg, ng); mf[1] = qt; cloudliq lives in qn ----
   int micro, m25_order;
+  // explicit scalar momentum transport (-DSP_ESMT): the two scalars, two field-sized scratch arrays of the tridiagonal sweep, the
+  // per-CRM advection offset, and the FP64 cos / sin table of the x-transform (FFTPACK's own tables are real(crm_rknd))
+  int esmt;
+  double *u_esmt, *v_esmt, *esmt_s1, *esmt_s2, *esmt_off;
+  const double *esmt_tw;
   double *mf[11];
   double *m_rate[8], *m_ratea[8];        // aut1..con1 and their time integrals aut1a..con1a (3-D)
   double *m_rad[4];                      // crm_rad nc, ni, qs, ns accumulators

@@ -122,7 +122,9 @@ struct PlanePipe {
 // March boilerplate.  NPRE = NS-1-back levels are issued ahead; FWD = highest level above k that iteration k reads.
 #define CRM_PIPE_PROLOGUE(pipe, nlev, NPRE, FWD)                                   \
   if (tid == 0) for (int L_ = 1; L_ <= imin((nlev), (NPRE)); L_++) (pipe).issue(L_); \
-  for (int L_ = 1; L_ <= imin((nlev), (FWD)); L_++) (pipe).wait(L_);
+  if ((FWD) >= 1 && (nlev) >= 1) (pipe).wait(1);                                     \
+  if ((FWD) >= 2 && (nlev) >= 2) (pipe).wait(2);                                     \
+  static_assert((FWD) <= 2, "CRM_PIPE_PROLOGUE waits for at most two levels");
 // top of iteration k (after the caller's __syncthreads()): refill the freed slot, wait for level k+FWD
 #define CRM_PIPE_STEP(pipe, k, nlev, NPRE, FWD)                        \
   if (tid == 0 && (k) + (NPRE) <= (nlev)) (pipe).issue((k) + (NPRE)); \

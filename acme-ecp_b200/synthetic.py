@@ -97,6 +97,8 @@ def make_inputs(dims, seed=20260101, lat_range=(-1.0, 1.0), rows=None, nglobal=N
     inp.wndls[...] = np.abs(ul[:, plev - 1])
     inp.lat_deg[...] = np.degrees(lat); inp.lon_deg[...] = lon
     inp.gcol[...] = gcol
+    if getattr(dims, "esmt", False):   # crm_physics.F90:1126-1127: the transported scalar momentum starts from the GCM wind
+        inp.ul_esmt[...] = ul; inp.vl_esmt[...] = vl
 
     st = crm_state_type().initialize(dims)
     rad = crm_rad_type().initialize(dims)

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CRM_B200_ABI_VERSION 3
+#define CRM_B200_ABI_VERSION 4
 
 /* Compile-time constants of the reference (PHYS/crmdims.F90:13-22, CRM/domain.F90:9-13) and the
  * hidden module inputs of crm() (time_manager:get_nstep, accelerate_crm_mod namelist). */
@@ -55,6 +55,7 @@ typedef struct crm_dims_t {
   int crm_accel_uv;
   double crm_accel_factor;
   int twiddle_f32;      /* 1: REAL(4) FFT trig tables like CRM/fft.F90; 0: FP64 */
+  int esmt;             /* 1: explicit scalar momentum transport (-DSP_ESMT, scalar_momentum.F90); ABI >= 4 */
 } crm_dims_t;
 
 /* crm_input_type (CRM/crm_input_module.F90:10-47) + phys_grid lookups (crm_module.F90:287-288,679) */
@@ -69,6 +70,7 @@ typedef struct crm_input_t {
   const double *fluxu00, *fluxv00, *fluxt00, *fluxq00;   /* (ld) */
   const double *lat_deg, *lon_deg;      /* (ld) get_rlat_p/get_rlon_p * 57.296 */
   const int    *gcol;                   /* (ld) get_gcol_p: seed of setperturb */
+  const double *ul_esmt, *vl_esmt;      /* (ld,plev) SP_ESMT builds only (crm_input_module.F90:39-42); NULL otherwise (ABI >= 4) */
 } crm_input_t;
 
 /* crm_state_type (CRM/crm_state_module.F90:12-56); all (ld,nx,ny,nzm), in/out */
@@ -116,6 +118,9 @@ typedef struct crm_output_t {
   /* (ld,plev): mean number mixing ratios (crm_module.F90:1341-1350, 1379-1384) and time/domain mean process rates (:1386-1414) */
   double *nc_mean, *ni_mean, *ns_mean, *ng_mean, *nr_mean;
   double *aut_a, *acc_a, *evpc_a, *evpr_a, *mlt_a, *sub_a, *dep_a, *con_a;
+  /* (ld,plev), SP_ESMT builds (crm_output_module.F90:81-84, crm_module.F90:1185-1192): (mean of the transported scalar momentum -
+   * ul_esmt) / dt_gl; required when dims.esmt = 1 (ABI >= 4) */
+  double *u_tend_esmt, *v_tend_esmt;
 } crm_output_t;
 
 /* Run statistics (new: replaces the GPTL timers 'crm_gpu_region' etc.) */

@@ -45,11 +45,13 @@ void boundaries(const Geo &g, Crm &c, int flag) {
     bound_exchange(g, c.qt, nzm, 3, 3, 3, 3);
     if (g.m2005) { for (int n = 2; n <= 10; n++) bound_exchange(g, c.mf[n], nzm, 3, 3, 3, 3); }
     else bound_exchange(g, c.qp, nzm, 3, 3, 3, 3);
+    if (g.esmt) { bound_exchange(g, c.u_esmt, nzm, 3, 3, 3, 3); bound_exchange(g, c.v_esmt, nzm, 3, 3, 3, 3); }   // periodic.F90:87-90
   } else if (flag == 3) {
     bound_exchange(g, c.t, nzm, 1, 1, 1, 1);
     bound_exchange(g, c.qt, nzm, 1, 1, 1, 1);
     if (g.m2005) { for (int n = 2; n <= 10; n++) bound_exchange(g, c.mf[n], nzm, 1, 1, 1, 1); }
     else bound_exchange(g, c.qp, nzm, 1, 1, 1, 1);
+    if (g.esmt) { bound_exchange(g, c.u_esmt, nzm, 1, 1, 1, 1); bound_exchange(g, c.v_esmt, nzm, 1, 1, 1, 1); }   // periodic.F90:120-123
   } else if (flag == 4) {
     // sgs_field_diag: dimx1_d=0 -> 1+dimx1_d = 1 cell west, dimx2_d-nx = 1 east; y: YES3D each side
     bound_exchange(g, c.tk, nzm, 1, 1, g.YES3D, g.YES3D);

@@ -53,6 +53,7 @@ void alloc_crm(const Geo &g, Crm &c) {
     p->alloc(1, nz);
   for (P1 *p : {&c.precflux, &c.uwle, &c.uwsb, &c.vwle, &c.vwsb, &c.tlat, &c.tlatqi, &c.qifall, &c.qpfall, &c.twsb, &c.tdiff, &c.qpsrc, &c.qpevp})
     p->alloc(1, nz);
+  if (g.esmt) { c.u_esmt.alloc(-2, nx + 3, 1 - 3 * Y, ny + 3 * Y, nzm); c.v_esmt.alloc(-2, nx + 3, 1 - 3 * Y, ny + 3 * Y, nzm); }   // dimx1_s:dimx2_s (scalar_momentum.F90:62-63)
   for (int n = 1; n <= (g.m2005 ? 10 : 2); n++) { c.mkwle[n].alloc(1, nz); c.mkwsb[n].alloc(1, nz); c.mkadv[n].alloc(1, nz); c.mkdiff[n].alloc(1, nz); }
   if (g.m2005) {
     for (int n = 2; n <= 10; n++) c.mf[n].alloc(-2, nx + 3, 1 - 3 * Y, ny + 3 * Y, nzm);
@@ -81,8 +82,11 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
   const bool m25 = d->micro == 1;
   if (m25 && d->use_crm_accel) { g_err = "CRM time step relaxation is only compatible with sam1mom microphysics"; return 2; }   // accelerate_crm.F90:65-68
   if (m25 && !(st->nc && st->qr && st->nr && st->qi && st->ni && st->qs && st->ns && st->qg && st->ng && st->qc)) { g_err = "oracle: m2005 needs the crm_state members nc, qr, nr, qi, ni, qs, ns, qg, ng, qc"; return 2; }
+  const bool esmt = d->esmt != 0;
+  if (esmt && !(in->ul_esmt && in->vl_esmt && out->u_tend_esmt && out->v_tend_esmt)) { g_err = "oracle: esmt needs crm_input ul_esmt, vl_esmt and crm_output u_tend_esmt, v_tend_esmt"; return 2; }
   Geo g;
   g.m2005 = m25;
+  g.esmt = esmt;
   g.nx = d->nx; g.ny = d->ny; g.nzm = d->nzm; g.nz = d->nzm + 1; g.plev = d->plev; g.YES3D = d->yes3d;
   g.nx_rad = d->nx_rad; g.ny_rad = d->ny_rad; g.dx = d->dx; g.dy = d->dx; g.RUN3D = d->ny > 1;
   if ((g.RUN3D && !g.YES3D) || (!g.RUN3D && g.YES3D)) { g_err = "setparm: RUN3D/YES3D mismatch (setparm.F90:55-62)"; return 3; }
@@ -185,6 +189,14 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
 #pragma omp parallel for schedule(static)
   for (int ic = 0; ic < ncrms; ic++) {
     Crm &c = crms[ic];
+    if (esmt) {
+      // crm_module.F90:419-424: u_esmt(:,:,:,k) = crm_input%ul_esmt(icrm,plev-k+1).  In the reference this statement sits OUTSIDE any
+      // icrm loop and reads row ncrms+1 of ul_esmt for EVERY CRM (icrm is left at ncrms+1 by the preceding loop nest): an
+      // out-of-range leftover of the single-CRM code.  Restated with the evident intent - every CRM starts from its own column.
+      for (int k = 1; k <= nzm; k++)
+        for (int j = 1; j <= ny; j++)
+          for (int i = 1; i <= nx; i++) { c.u_esmt(i, j, k) = P2(in->ul_esmt, ic, plev - k + 1); c.v_esmt(i, j, k) = P2(in->vl_esmt, ic, plev - k + 1); }
+    }
     if (m25) micro_diagnose_m2005(g, c); else micro_diagnose(g, c, mc);   // micro_init -> micro_diagnose (microphysics.F90:155-226 / MICRO_M2005:476-597)
     // sgs_init (sgs.F90:174-226): tke, tk, tkh = 0 (alloc), grdf
     for (int k = 1; k <= nzm; k++) {
@@ -300,6 +312,7 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
         advect_scalar(g, c, c.qt, c.mkadv[1], c.mkwle[1]);
         if (m25) { for (int n = 2; n <= 10; n++) advect_scalar(g, c, c.mf[n], c.mkadv[n], c.mkwle[n]); }
         else advect_scalar(g, c, c.qp, c.mkadv[2], c.mkwle[2]);
+        if (esmt) esmt_advect(g, c);   // advect_all_scalars.F90:74-88
         if (dbg_stop == 5) continue;
         if (!m25) prec_cfl = dmax(prec_cfl, precip_fall_part1(g, c, s, mc));   // m2005: micro_precip_fall is a no-op (microphysics.F90:1425-1429)
       }
@@ -320,6 +333,7 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
         diffuse_scalar(g, c, s, c.qt, c.fluxbq, c.fluxtq, c.mkdiff[1], c.mkwsb[1]);
         if (m25) { for (int n = 2; n <= 10; n++) diffuse_scalar(g, c, s, c.mf[n], c.fluxbq /*=0*/, c.fluxtq /*=0*/, c.mkdiff[n], c.mkwsb[n]); }
         else diffuse_scalar(g, c, s, c.qp, c.fluxbq /*=0*/, c.fluxtq /*=0*/, c.mkdiff[2], c.mkwsb[2]);
+        if (esmt) { esmt_diffuse(g, c, s); scalar_momentum_tend(g, c, s); }   // sgs.F90:442-448, crm_module.F90:856-860
         if (dbg_stop == 7) continue;
         if (m25) {
           micro_proc_m2005(g, c, s);
@@ -486,6 +500,21 @@ extern "C" int crm_oracle_run(const crm_dims_t *d, const crm_input_t *in, crm_st
     }
     if (out->prectend) out->prectend[ic] = (c.colprec - c.prectend0) / ggr * factor_xy * icrm_run_time;
     if (out->precstend) out->precstend[ic] = (c.colprecs - c.precstend0) / ggr * factor_xy * icrm_run_time;
+    if (esmt) {   // crm_module.F90:1140-1145, 1174-1179, 1185-1197
+      for (int l = 1; l <= plev; l++) {
+        double su = P2(in->ul_esmt, ic, l), sv = P2(in->vl_esmt, ic, l);
+        if (l >= ptop) {
+          su = 0.; sv = 0.;
+          const int k = plev - l + 1;
+          for (int i = 1; i <= nx; i++)
+            for (int j = 1; j <= ny; j++) { su += c.u_esmt(i, j, k); sv += c.v_esmt(i, j, k); }
+          su *= factor_xy; sv *= factor_xy;
+        }
+        OUT2(out->u_tend_esmt, ic, l) = (su - P2(in->ul_esmt, ic, l)) * icrm_run_time;
+        OUT2(out->v_tend_esmt, ic, l) = (sv - P2(in->vl_esmt, ic, l)) * icrm_run_time;
+      }
+      for (int k = ptop; k <= ptop + 1; k++) { OUT2(out->u_tend_esmt, ic, k) = 0.; OUT2(out->v_tend_esmt, ic, k) = 0.; }
+    }
     for (int k = ptop; k <= ptop + 1; k++) {
       if (out->sltend) OUT2(out->sltend, ic, k) = 0.;
       if (out->qltend) OUT2(out->qltend, ic, k) = 0.;
@@ -698,6 +727,7 @@ extern "C" long long crm_oracle_debug_fetch(const char *name, double *buf, size_
     F3 *f = nullptr;
     if (nm == "u") f = &c.u; else if (nm == "v") f = &c.v; else if (nm == "w") f = &c.w; else if (nm == "t") f = &c.t;
     else if (nm == "qt") f = &c.qt; else if (nm == "qp") f = &c.qp; else if (nm == "qn") f = &c.qn;
+    else if (nm == "u_esmt" && g.esmt) f = &c.u_esmt; else if (nm == "v_esmt" && g.esmt) f = &c.v_esmt;
     else if (nm == "tabs") f = &c.tabs; else if (nm == "qv") f = &c.qv; else if (nm == "qcl") f = &c.qcl;
     else if (nm == "qci") f = &c.qci; else if (nm == "qpl") f = &c.qpl; else if (nm == "qpi") f = &c.qpi;
     else if (nm == "tk") f = &c.tk; else if (nm == "tkh") f = &c.tkh; else if (nm == "tke") f = &c.tke; else if (nm == "p") f = &c.p;

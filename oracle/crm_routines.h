@@ -23,6 +23,10 @@ void advect_scalar(const Geo &g, const Crm &c, F3 &f, P1 &fadv, P1 &flux);
 void diffuse_scalar(const Geo &g, const Crm &c, const Step &s, F3 &f, const std::vector<double> &fluxb,
                     const std::vector<double> &fluxt, P1 &fdiff, P1 &flux);
 double kurant_cfl(const Geo &g, const Crm &c, const Step &s);
+// crm_esmt.cpp (-DSP_ESMT)
+void esmt_advect(const Geo &g, Crm &c);
+void esmt_diffuse(const Geo &g, Crm &c, const Step &s);
+void scalar_momentum_tend(const Geo &g, Crm &c, const Step &s);
 // crm_micro.cpp
 struct MicroCoef {   // micro_params.F90:70-97 + microphysics.F90:32 scalars
   float gam3, gams1, gams2, gams3, gamg1, gamg2, gamg3, gamr1, gamr2, gamr3;

@@ -13,6 +13,7 @@ struct Geo {   // PHYS/crmdims.F90, CRM/domain.F90, CRM/grid.F90:14-46
   double dx, dy;
   bool RUN3D;
   bool m2005 = false;   // micro = 1
+  bool esmt = false;    // -DSP_ESMT
 };
 
 // Scalars shared by the whole batch (grid.F90:52-60, 101, 181)
@@ -35,6 +36,7 @@ struct Crm {
   // MICRO_M2005/microphysics.F90:57-121 (micro = 1): micro_field(:,:,:,:,n) = mf[n], n = 2..10 (nc, qr, nr, qi, ni, qs, ns, qg, ng);
   // micro_field(..,1) = qt (total water vapour + cloud liquid); cloudliq lives in qn; qp is unused
   F3 mf[11];
+  F3 u_esmt, v_esmt;   // scalar_momentum.F90:27-28 (SP_ESMT)
   F3 wvar, aut1, acc1, evpc1, evpr1, mlt1, sub1, dep1, con1, aut1a, acc1a, evpc1a, evpr1a, mlt1a, sub1a, dep1a, con1a;
   F3 rad_nc, rad_ni, rad_qs, rad_ns;
   // sgs.F90:40-54

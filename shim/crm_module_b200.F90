@@ -32,11 +32,13 @@ module crm_module
     integer(c_int) :: igstep, micro, use_crm_accel, crm_accel_uv
     real(c_double) :: crm_accel_factor
     integer(c_int) :: twiddle_f32
+    integer(c_int) :: esmt
   end type
   type, bind(C) :: crm_input_t
     type(c_ptr) :: zmid, zint, tl, ql, qccl, qiil, ps, pmid, pint, pdel, phis, ul, vl
     type(c_ptr) :: ocnfrac, tau00, wndls, bflxls, fluxu00, fluxv00, fluxt00, fluxq00
     type(c_ptr) :: lat_deg, lon_deg, gcol
+    type(c_ptr) :: ul_esmt, vl_esmt      ! SP_ESMT builds only (ABI >= 4)
   end type
   type, bind(C) :: crm_state_t
     type(c_ptr) :: u_wind, v_wind, w_wind, temperature, qt, qp, qn
@@ -59,6 +61,7 @@ module crm_module
     type(c_ptr) :: wvar, aut, acc, evpc, evpr, mlt, sub, dep, con                       ! m2005 builds only (ABI >= 3)
     type(c_ptr) :: nc_mean, ni_mean, ns_mean, ng_mean, nr_mean
     type(c_ptr) :: aut_a, acc_a, evpc_a, evpr_a, mlt_a, sub_a, dep_a, con_a
+    type(c_ptr) :: u_tend_esmt, v_tend_esmt   ! SP_ESMT builds only (ABI >= 4)
   end type
 
   interface
@@ -144,6 +147,11 @@ contains
     d%crm_accel_uv  = merge(1, 0, crm_accel_uv)
     d%crm_accel_factor = crm_accel_factor
     d%twiddle_f32 = 1                              ! reproduce CRM/fft.F90's implicit REAL(4) trig tables
+#if defined(SP_ESMT)
+    d%esmt = 1
+#else
+    d%esmt = 0
+#endif
 
     if (.not. c_associated(handle) .or. ncrms > handle_ncrms) then
       d%ncrms = pcols                              ! size the arena for the largest chunk
@@ -163,6 +171,12 @@ contains
     ci%bflxls = c_loc(crm_input%bflxls);  ci%fluxu00 = c_loc(crm_input%fluxu00);  ci%fluxv00 = c_loc(crm_input%fluxv00)
     ci%fluxt00 = c_loc(crm_input%fluxt00);  ci%fluxq00 = c_loc(crm_input%fluxq00)
     ci%lat_deg = c_loc(lat_deg);  ci%lon_deg = c_loc(lon_deg);  ci%gcol = c_loc(gcol)
+    ci%ul_esmt = c_null_ptr;  ci%vl_esmt = c_null_ptr
+    co%u_tend_esmt = c_null_ptr;  co%v_tend_esmt = c_null_ptr
+#if defined(SP_ESMT)
+    ci%ul_esmt = c_loc(crm_input%ul_esmt);  ci%vl_esmt = c_loc(crm_input%vl_esmt)          ! crm_input_module.F90:39-42
+    co%u_tend_esmt = c_loc(crm_output%u_tend_esmt);  co%v_tend_esmt = c_loc(crm_output%v_tend_esmt)   ! crm_output_module.F90:81-84
+#endif
 
     cs%u_wind = c_loc(crm_state%u_wind);  cs%v_wind = c_loc(crm_state%v_wind);  cs%w_wind = c_loc(crm_state%w_wind)
     cs%temperature = c_loc(crm_state%temperature);  cs%qt = c_loc(crm_state%qt)

@@ -56,6 +56,8 @@ def compare_all(dims, res_o, res_g, tol, abs_floor=1e-18, skip=()):
     items += [(n, getattr(out_o, n), getattr(out_g, n)) for n, _ in pkg.abi.OUTPUT_FIELDS]
     if dims.micro == 1:
         items += [(n, getattr(out_o, n), getattr(out_g, n)) for n, _ in pkg.abi.OUTPUT_FIELDS_M2005]
+    if getattr(dims, "esmt", False):
+        items += [(n, getattr(out_o, n), getattr(out_g, n)) for n, _ in pkg.abi.OUTPUT_FIELDS_ESMT]
     for name, a, b in items:
         if name in skip:
             continue

@@ -477,3 +477,39 @@ def sgs_2d(dx, dt, dz, adz, adzw, bet, presi, u0, u, w, t, tabs, qv, qcl, qci, q
             tkv = min(tkv, tkmax)
             tk[i, k] = tkv; tkh[i, k] = Pr * tkv
     return tk, tkh, tke
+
+
+def esmt_pgf(u_s, w, zi, z, rho, dx):
+    """scalar_momentum_pgf (scalar_momentum.F90:156-320) for one 2-D CRM, written with numpy.fft and a dense linear solve (the reference
+    uses FFTPACK 5.1 rfft1f / rfft1b and Gaussian elimination): u_s (nx, nzm), w (nx, nzm+1) -> tend (nx, nzm)."""
+    nx, nzm = u_s.shape
+    pi = float(F(2.) * np.arcsin(F(1.)))                       # pi = 2.*asin(1.0) in REAL(4)
+    dz = np.empty(nzm + 1); dz[:nzm] = zi[1:nzm + 1] - zi[:nzm]; dz[nzm] = dz[nzm - 1]
+    avg = u_s.sum(axis=0) / nx
+    shr = np.zeros(nzm)
+    shr[0] = (avg[1] - avg[0]) / (z[1] - z[0])
+    shr[1:nzm - 1] = (avg[2:] - avg[:nzm - 2]) / (z[2:nzm] - z[:nzm - 2])
+    w_i = 0.5 * (w[:, :nzm] + w[:, 1:nzm + 1])
+    W = np.fft.rfft(w_i, axis=0)                               # W[m] = sum_x w e^{-2 pi i m x / n}
+    P_hat = np.zeros_like(W)
+    for m in range(1, nx // 2 + 1):
+        kw = 2. * pi * m / (nx * dx) if m < nx // 2 else 2. * pi / (2. * dx)
+        A = np.zeros((nzm, nzm))
+        for k in range(nzm):
+            a = dz[k + 1] / (dz[k + 1] + dz[k]); c = dz[k] / (dz[k + 1] + dz[k])
+            b = -0.5 * 1.25 * kw ** 2 * dz[k] * dz[k + 1] - 1.0
+            if k == 0: b += a
+            else: A[k, k - 1] = a
+            if k == nzm - 1: b += c
+            else: A[k, k + 1] = c
+            A[k, k] = b
+        r = kw ** 2 * W[m] * shr * dz[:nzm] * dz[1:nzm + 1]    # the system is real: real and imaginary parts solve separately
+        P_hat[m] = np.linalg.solve(A, r.real) + 1j * np.linalg.solve(A, r.imag)
+    # FFTPACK's Nyquist coefficient is sum (-1)^x w / n and the reference halves the solution at that coefficient (:283-289); in the
+    # rfft convention the Nyquist term enters irfft once, with weight 1/n
+    if nx % 2 == 0:
+        P_hat[nx // 2] *= 0.5
+    pgf = np.fft.irfft(P_hat, n=nx, axis=0)
+    tend = -pgf * rho[None, :]
+    tend[:, 0] = 0.
+    return tend

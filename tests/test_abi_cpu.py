@@ -50,7 +50,10 @@ def test_ctypes_mirror_has_the_compiled_struct_layout(lib):
     assert {"sltend", "qltend", "qcltend", "qiltend", "precc", "precl", "cld", "prec_crm", "timing_factor", "qp_evp"} <= names
     m2005 = {n for n, _ in abi.OUTPUT_FIELDS_M2005}   # crm_output_module.F90:22-31, 60-74 (m2005 build)
     assert {"wvar", "aut", "con", "nc_mean", "nr_mean", "aut_a", "con_a"} <= m2005
-    assert names | m2005 == {f[0] for f in abi.crm_output_t._fields_}
+    esmt = {n for n, _ in abi.OUTPUT_FIELDS_ESMT}     # crm_output_module.F90:81-84 (SP_ESMT build)
+    assert esmt == {"u_tend_esmt", "v_tend_esmt"}
+    assert names | m2005 | esmt == {f[0] for f in abi.crm_output_t._fields_}
+    assert [f[0] for f in abi.crm_input_t._fields_][-2:] == ["ul_esmt", "vl_esmt"] and abi.crm_dims_t._fields_[-1][0] == "esmt"
 
 
 def test_fortran_shim_binds_the_same_entry_points():

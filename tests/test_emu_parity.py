@@ -108,3 +108,16 @@ def test_emu_per_phase_intermediate_state_3d(emu, stop):
     dims, inp, st, rad = cm.make_case(dims, spinup_steps=40)
     for name, err, scale in cm.phase_errors(dims, inp, st, rad, stop, lib_path=emu):
         assert err <= 1e-12 or err * scale < 1e-18, (stop, name, err, scale)
+
+
+def test_emu_esmt_2d(emu):
+    # explicit scalar momentum transport (-DSP_ESMT): offset advection, diffusion, spectral pressure-gradient force, outputs
+    dims = cm.small_dims(ncrms=5, nx=8, nsteps=3, esmt=True)
+    ro, rg = _check(emu, dims, 60, 1e-10)
+    assert np.abs(ro[2].u_tend_esmt).max() > 1e-7
+
+
+def test_emu_esmt_3d(emu):
+    dims = cm.pkg.CrmDims(ncrms=2, nx=8, ny=8, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=40.0, igstep=3, nx_rad=2, ny_rad=2, esmt=True)
+    ro, rg = _check(emu, dims, 30, 1e-10)
+    assert np.abs(ro[2].v_tend_esmt).max() > 1e-7

@@ -516,3 +516,33 @@ def test_ensemble_kolmogorov_smirnov_equivalence():
         assert abs(a.mean() - b.mean()) <= 3.0 * np.sqrt((a.var(ddof=1) + b.var(ddof=1)) / M) + 1e-300, (k, a.mean(), b.mean())
     for k in ("prec", "lwp", "iwp", "mcup"):
         assert ks_2samp(stats["oracle"][k], stats["control"][k]).pvalue < 0.01, ("the test cannot tell a 3 % drier column apart", k)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Explicit scalar momentum transport (-DSP_ESMT, scalar_momentum.F90): dims.esmt = 1
+# ---------------------------------------------------------------------------------------------------------------------
+def test_esmt_2d_cfg2_geometry():
+    dims = cm.small_dims(ncrms=19, nx=64, nzm=58, plev=72, nsteps=10, esmt=True)
+    ro, rg = _check(dims, 60, 1e-9)
+    assert np.abs(ro[2].u_tend_esmt).max() > 1e-6 and np.all(ro[2].u_tend_esmt[:, :dims.plev - dims.nzm + 2] == 0.0)
+
+
+def test_esmt_small_tile_and_padding():
+    dims = cm.small_dims(ncrms=21, nx=32, nsteps=4, ld=24, esmt=True)
+    ro, rg = _check(dims, 60, 1e-9)
+    assert np.all(rg[2].u_tend_esmt[dims.ncrms:] == 0.0)
+
+
+def test_esmt_3d():
+    dims = dims3d(3, 16, 16, nsteps=3, esmt=True)
+    _check(dims, 30, 1e-9)
+
+
+def test_esmt_needs_its_arrays():
+    dims = cm.small_dims(ncrms=4, nx=8, nsteps=1, esmt=True)
+    dims, inp, st, rad = cm.make_case(dims, 0)
+    h = cm.libmod.CrmHandle(dims)
+    inp.ul_esmt = None
+    with pytest.raises(cm.libmod.CrmB200Error, match="esmt = 1 needs"):
+        h.run(dims, inp, st, rad)
+    h.close()

@@ -115,3 +115,21 @@ def test_sgs_against_second_restatement():
     tk_r, tkh_r, tke_r = rn.sgs_2d(dx, dt, dz, adz, adzw, bet, presi, u0, u, w, t, tabs, qv, qcl, qci, qpl, qpi, tk_in)
     assert tk[:, :nzm - 1].max() > 0.1
     assert _close(tk_r[:, :nzm - 1], tk[:, :nzm - 1], 5e-13) and _close(tkh_r[:, :nzm - 1], tkh[:, :nzm - 1], 5e-13) and _close(tke_r[:, :nzm - 1], tke[:, :nzm - 1], 5e-13)
+
+
+def test_esmt_pressure_gradient_force_against_second_restatement():
+    """scalar_momentum_pgf: the oracle's direct real DFT (FFTPACK 5.1 coefficient layout) + Thomas algorithm against numpy.fft.rfft/irfft +
+    a dense solve.  Pins the coefficient <-> wavenumber mapping, the 1/n - 2/n normalisation pair and the halved Nyquist coefficient."""
+    rng = np.random.default_rng(26)
+    for nx in (8, 32, 64):
+        nzm, dx = 24, 1000.
+        adz = np.linspace(0.6, 2.4, nzm + 1); zi = np.concatenate([[0.], np.cumsum(adz * 150.)]); z = 0.5 * (zi[1:] + zi[:-1])
+        rho = 1.15 * np.exp(-z[:nzm] / 8000.)
+        w = np.zeros((nx, nzm + 1)); w[:, 1:nzm] = rng.standard_normal((nx, nzm - 1)) * 2.
+        u_s = (10. * np.tanh(z[:nzm] / 3000.))[None, :] + rng.standard_normal((nx, nzm))
+        tend = np.zeros((nx, nzm), order="F")
+        A = np.asfortranarray
+        assert L.crm_oracle_test_esmt_pgf(nx, nzm, C.c_double(dx), P(zi[:nzm + 1].copy()), P(z[:nzm + 1].copy()), P(rho), P(A(w)), P(A(u_s)), P(tend)) == 0
+        ref = rn.esmt_pgf(u_s, w, zi, z, rho, dx)
+        assert np.abs(tend[:, 1:]).max() > 1e-4 and np.all(tend[:, 0] == 0.)
+        assert _close(ref, tend, 2e-12), (nx, np.abs(ref - tend).max() / np.abs(tend).max())

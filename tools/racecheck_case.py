@@ -12,6 +12,11 @@ if which in ("2d", "all"):
 if which in ("3d", "all"):
     cases.append(("3d", cm.pkg.CrmDims(ncrms=2, nx=32, ny=32, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=40.0, igstep=3, nx_rad=8, ny_rad=8), 6))
     cases.append(("3d-16x8", cm.pkg.CrmDims(ncrms=5, nx=16, ny=8, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=40.0, igstep=3, nx_rad=4, ny_rad=2), 6))
+if which in ("2drt", "all"):   # runtime-geometry kernel variants (nx = 128: CRM tile of 2)
+    cases.append(("2d-runtime-geometry", cm.small_dims(ncrms=3, nx=128, nsteps=2), 6))
+if which in ("esmt", "all"):
+    cases.append(("esmt", cm.small_dims(ncrms=8, nx=32, nsteps=2, esmt=True), 10))
+    cases.append(("esmt-3d", cm.pkg.CrmDims(ncrms=3, nx=16, ny=16, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=40.0, igstep=3, nx_rad=4, ny_rad=4, esmt=True), 6))
 if which in ("m2005", "all"):
     cases.append(("m2005", cm.small_dims(ncrms=8, nx=32, nsteps=2, micro=1), 10))
 for name, dims, spin in cases:
