@@ -737,7 +737,9 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
         for (int t0 = 0; t0 < ntiles; t0 += h->m25_chunk) {
           const int nt = std::min(h->m25_chunk, ntiles - t0);
           const int nb = (int)(((long long)nt * P + CRM_M25_COLS - 1) / CRM_M25_COLS);
-          LAUNCH(h, k_m2005_column<CRM_M25_MINB>, nb, CRM_M25_COLS, 0, p, h->m25_scr, t0, nt);
+          LAUNCH(h, (k_m2005_column<CRM_M25_MINB, 1>), nb, CRM_M25_COLS, 0, p, h->m25_scr, t0, nt);
+          LAUNCH(h, (k_m2005_column<CRM_M25_MINB, 2>), nb, CRM_M25_COLS, 0, p, h->m25_scr, t0, nt);
+          LAUNCH(h, (k_m2005_column<CRM_M25_MINB, 3>), nb, CRM_M25_COLS, 0, p, h->m25_scr, t0, nt);
           LAUNCH(h, k_m2005_scatter, nt, P, red_bytes(5), p, h->m25_scr, t0, nt);
         }
         LAUNCH_G(h, k_p8_micro, ntiles * ((nzm + CRM_P8_NL - 1) / CRM_P8_NL), P, smem_p8, p, 0, 1);

@@ -32,7 +32,8 @@ struct M25Col {   // work-space accessor of one thread: a(id, k), k = 1..nz; 32-
 // (profiles/r02e_m2005_column_tuning.md): MINB 1 (255 regs) 26.2 ms/launch, 3 (168) 22.3, 4 (128) 20.6, 6 (80) 19.4, 8 (64) 28.5 (before the
 // out-of-line helpers): the kernel is bound by instruction issue and instruction-cache misses, occupancy hides both
 #define CRM_M25_MINB 6
-template <int MINB>
+// PH = 1: gather + satadj_liquid + process rates; 2: sedimentation; 3: final update + surface precipitation (three launches per chunk).
+template <int MINB, int PH>
 __global__ void __launch_bounds__(CRM_M25_COLS, MINB) k_m2005_column(CrmP p, double *scr, int tile0, int ntiles_chunk) {
   using namespace m2005;
   const int P = p.P, CT = p.CT;
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(CRM_M25_COLS, MINB) k_m2005_column(CrmP p, dou
   const int nzm = p.nzm;
   M25Col a; a.s = scr; a.n = (unsigned)(ntiles_chunk * P); a.nz = nzm; a.col = (unsigned)c;
   const double dtn = p.dtn, dz = p.dz[cb];
+  if (PH == 1)
   for (int k = 1; k <= nzm; k++) {
     const double qr = F3(p.mf[3], k), qi = F3(p.mf[5], k), qs = F3(p.mf[7], k), qg = F3(p.mf[9], k);
     a(NC, k) = F3(p.mf[2], k); a(QR, k) = qr; a(NR, k) = F3(p.mf[4], k); a(QI, k) = qi; a(NI, k) = F3(p.mf[6], k);
@@ -66,8 +68,8 @@ __global__ void __launch_bounds__(CRM_M25_COLS, MINB) k_m2005_column(CrmP p, dou
     a(T3, k) = tabs; a(QV, k) = qv; a(QC, k) = qc;
   }
   double sfcpcp = 0., sfcicepcp = 0.;
-  m2005::column(a, c_m25, nzm, dtn, sfcpcp, sfcicepcp);
-  {
+  m2005::column_ph<PH>(a, c_m25, nzm, dtn, sfcpcp, sfcicepcp);
+  if (PH == 3) {
     const long long c2 = (long long)tile * P + tid;
     p.precsfc[c2] = p.precsfc[c2] + sfcpcp / dz;
     p.precssfc[c2] = p.precssfc[c2] + sfcicepcp / dz;

@@ -357,8 +357,12 @@ M25_HD inline double activate2(const Cn &c, double DUM, double T, double EVS, do
 // M2005MICRO_GRAUPEL for one column of nz levels (k = 1 bottom).  `a(id, k)` is the work space (ids above); on entry the state
 // (QC..NG, T3, QV) and the inputs (PRES [Pa], RHO, DZQ, W3, WVAR) are filled, on return the state is updated, the sedimentation
 // tendencies SQ* and the rate outputs AUT..CON are set.  PRECRT / SNOWRT: surface precipitation of the step (mm).
-template <class A, class Cn>
-M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, double &PRECRT, double &SNOWRT) {
+// PH = 0: the whole scheme (oracle, emulator).  PH = 1, 2, 3: the three sections as separate passes over the work space (process rates /
+// sedimentation / final update); the device runs them as three kernels because the scheme's code size (20 k instructions) thrashes the
+// instruction cache.  Between the passes the column's LTRUE flag and the two surface precipitation sums travel in levels 1-3 of the W3
+// array (an input that only the first section reads).
+template <int PH, class A, class Cn>
+M25_HD inline void column_ph(A &a, const Cn &c, const int nz, const double DT, double &PRECRT, double &SNOWRT) {
   const double PI = c.PI, QSMALL = c.QSMALL, TMELT = c.TMELT, RHOW = c.RHOW, RHOSU = c.RHOSU;
   const double BS = c.BS, BR = c.BR, BG = c.BG, BI = c.BI, BC = c.BC, DS = c.DS, DG = c.DG, DI = c.DI, DCS = c.DCS;
   const double F1S = c.F1S, F2S = c.F2S, F1R = c.F1R, F2R = c.F2R, CPW = c.CPW, AIMM = c.AIMM, MMULT = c.MMULT, RV = c.RV;
@@ -369,8 +373,9 @@ M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, doub
   auto GAM = [&](double x) { return gamma_f(x, c.PI, c.SQRTPI); };
   int LTRUE = 0;
   double EPSR = 0., EPSI = 0., EPSS = 0., EPSG = 0., DQSDT = 0.;   // SAVE-less locals of the reference keep their last value across levels
-  (void)EPSI; (void)EPSS; (void)EPSG; (void)DQSDT; (void)BC;
+  (void)EPSI; (void)EPSS; (void)EPSG; (void)DQSDT; (void)BC; (void)CPW; (void)AIMM; (void)MMULT; (void)XLF; (void)DCS; (void)F1S; (void)F2S; (void)F1R; (void)F2R;
 
+  if (PH == 0 || PH == 1) {
   for (int K = 1; K <= nz; K++) {
     double QC3D = a(QC, K), QI3D = a(QI, K), QNI3D = a(QNI, K), QR3D = a(QR, K), NC3D = a(NC, K), NI3D = a(NI, K), NS3D = a(NS, K),
            NR3D = a(NR, K), QG3D = a(QG, K), NG3D = a(NG, K), T3D = a(T3, K), QV3D = a(QV, K);
@@ -867,8 +872,16 @@ M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, doub
     a(AUT, K) = aut1d; a(ACC, K) = acc1d; a(EVPC, K) = evpc1d; a(EVPR, K) = evpr1d; a(MLT, K) = mlt1d; a(SUB, K) = sub1d; a(DEP, K) = dep1d; a(CON, K) = con1d;
   }
 
-  PRECRT = 0.; SNOWRT = 0.;
-  if (LTRUE == 0) return;   // GOTO 400
+  if (PH == 1) { a(W3, 1) = (double)LTRUE; return; }
+  }   // PH 0 / 1
+  if (PH >= 2) LTRUE = (int)a(W3, 1);
+  if (PH == 0 || PH == 2) { PRECRT = 0.; SNOWRT = 0.; }
+  if (PH == 3) { PRECRT = a(W3, 2); SNOWRT = a(W3, 3); }
+  if (LTRUE == 0) {   // GOTO 400
+    if (PH == 2) { a(W3, 2) = 0.; a(W3, 3) = 0.; }
+    return;
+  }
+  if (PH == 0 || PH == 2) {
 
   // ------------------------------------------------------------------- sedimentation (4796-5127)
   int NSTEP = 1;
@@ -958,6 +971,8 @@ M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, doub
     SNOWRT = SNOWRT + (fout1[3] + fout1[1] + fout1[8]) * DT / rn;
   }
 
+  if (PH == 2) { a(W3, 2) = PRECRT; a(W3, 3) = SNOWRT; return; }
+  }   // PH 0 / 2
   // ------------------------------------------------------------------- final update (5129-5604)
   for (int K = 1; K <= nz; K++) {
     const double PRESK = a(PRES, K), RHOK = a(RHO, K);
@@ -1049,6 +1064,10 @@ M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, doub
     a(QC, K) = QC3D; a(QI, K) = QI3D; a(QNI, K) = QNI3D; a(QR, K) = QR3D; a(NC, K) = NC3D; a(NI, K) = NI3D; a(NS, K) = NS3D; a(NR, K) = NR3D;
     a(QG, K) = QG3D; a(NG, K) = NG3D; a(T3, K) = T3D; a(QV, K) = QV3D; a(MLT, K) = mlt1d;
   }
+}
+template <class A, class Cn>
+M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, double &PRECRT, double &SNOWRT) {
+  column_ph<0>(a, c, nz, DT, PRECRT, SNOWRT);
 }
 
 }  // namespace m2005

@@ -31,6 +31,8 @@ for l in out.splitlines():
     m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\w+\s+)?([A-Z0-9_]+)", l)
     if m and fn:
         op = m.group(1)
+        if op.startswith("ATOM"): op = "ATOM"      # ATOMG / ATOMS
+        elif op.startswith("RED"): op = "RED"      # REDG / REDS / REDUX
         cnt[fn][op] += 1; cnt[fn]["_total"] += 1
         if op in TENSOR: tens[op] += 1
 def short(f):
