@@ -125,7 +125,18 @@ static void ktime_add(std::vector<KTime> &v, const char *name, double ms) {
   for (auto &k : v) if (k.name == name || !strcmp(k.name, name)) { k.ms += ms; k.n++; return; }
   v.push_back({name, ms, 1});
 }
-static std::string kname(const char *s) { std::string n(s); while (!n.empty() && n[0] == '(') n.erase(0, 1); size_t q = n.find('<'); return q == std::string::npos ? n : n.substr(0, q); }
+static std::string kname(const char *s) {
+  std::string n(s);
+  while (!n.empty() && n[0] == '(') n.erase(0, 1);
+  const size_t q = n.find('<');
+  if (q == std::string::npos) return n;
+  std::string base = n.substr(0, q);
+  if (base == "k_m2005_column") {   // the three passes of the column scheme are timed separately: k_m2005_column_p1 / _p2 / _p3
+    const size_t c = n.rfind(','), e = n.rfind('>');
+    if (c != std::string::npos && e != std::string::npos && e > c) { std::string ph = n.substr(c + 1, e - c - 1); ph.erase(0, ph.find_first_not_of(' ')); base += "_p" + ph; }
+  }
+  return base;
+}
 #define LAUNCH(h, kern, grid, block, smem, ...)                 \
   do {                                                          \
     if ((h)->ktiming) (h)->ktimer.start();                      \

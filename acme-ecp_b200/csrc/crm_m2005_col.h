@@ -946,6 +946,46 @@ M25_HD inline void column_ph(A &a, const Cn &c, const int nz, const double DT, d
   const int FID[10] = {FR, FI, FNI, FS, FNS, FNR, FC, FNC, FG, FNG};
   // species order of DID: mass tendencies -> SQ* (+ nothing else), number tendencies -> *3DTEN (the N*STEN arrays of the reference feed nothing)
   const int TID[10] = {SQR, SQI, TNI, SQNI, TNS, TNR, SQC, TNC, SQG, TNG};
+#if defined(__CUDA_ARCH__) || defined(CRM_EMU)
+  // Device order of the same arithmetic: species outermost, then levels from the top, then the NSTEP sub-steps of that level with the
+  // level's density and tendency in registers (the fallout of the level above is kept per sub-step: fprev[n]).  Every (species, level,
+  // sub-step) update is the reference's expression on the same operands, executed in another order of INDEPENDENT updates, so the
+  // results are bit-identical; the work space is read and written once per species and level instead of once per sub-step.
+  constexpr int NMAX = 8;
+  if (NSTEP <= NMAX) {
+    double f1[5][NMAX];   // fallout at the surface of rain, cloud water, snow, cloud ice, graupel (the terms of PRECRT / SNOWRT)
+    for (int s = 0; s < 10; s++) {
+      // fallout of the level above, per sub-step.  Starting from +0 makes the top level the general case: (0 - fout)/dzq = -(fout/dzq)
+      // and T + (-x) = T - x exactly, which is the reference's K = NZ branch.
+      double fprev[NMAX];
+#pragma unroll
+      for (int n = 0; n < NMAX; n++) fprev[n] = 0.;
+      const int slot = (s == 0) ? 0 : (s == 6) ? 1 : (s == 3) ? 2 : (s == 1) ? 3 : (s == 8) ? 4 : -1;
+      for (int K = nz; K >= 1; K--) {
+        const double dzq = a(DZQ, K), RHOK = a(RHO, K), Fk = a(FID[s], K);
+        double Dk = a(DID[s], K), Tk = a(TID[s], K);
+#pragma unroll
+        for (int n = 0; n < NMAX; n++) {
+          if (n < NSTEP) {
+            const double fout = Fk * Dk;
+            const double FALTND = (fprev[n] - fout) / dzq;
+            Tk = Tk + FALTND / rn / RHOK; Dk = Dk + FALTND * DT / rn;
+            fprev[n] = fout;
+          }
+        }
+        a(TID[s], K) = Tk; a(DID[s], K) = Dk;
+      }
+      if (slot >= 0) {
+#pragma unroll
+        for (int n = 0; n < NMAX; n++) f1[slot][n] = fprev[n];   // after the last level fprev holds the fallout of level 1
+      }
+    }
+    for (int n = 0; n < NSTEP; n++) {
+      PRECRT = PRECRT + (f1[0][n] + f1[1][n] + f1[2][n] + f1[3][n] + f1[4][n]) * DT / rn;
+      SNOWRT = SNOWRT + (f1[2][n] + f1[3][n] + f1[4][n]) * DT / rn;
+    }
+  } else
+#endif
   for (int N = 1; N <= NSTEP; N++) {
     double fout_up[10];   // FALOUT*(K+1) of this sub-step (values before the update of level K+1)
     double fout1[10];

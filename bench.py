@@ -33,13 +33,13 @@ CONFIG_CLASS = {"cfg1": "2d_sam1mom", "cfg2": "2d_sam1mom", "cfg3": "2d_m2005", 
 KERNEL_WORDS = {
     "2d": {"k_p1_forcing": 14, "k_p2_sgs": 14, "k_p3_mom": 7, "k_p4_press_fwd": 9, "k_p5_press_bwd": 15,
            "k_mpdata": 4, "k_mpdata3": 8, "k_precip_a": 3, "k_precip_b": 7, "k_p7_diffuse": 7, "k_p8_micro": 13, "k_stats": 9.5,
-           "k_kurant": 3, "k_m2005_column": 13, "k_m2005_scatter": 42, "k_diffuse_set": 7},
+           "k_kurant": 3, "k_m2005_column_p1": 13, "k_m2005_column_p2": 0, "k_m2005_column_p3": 0, "k_m2005_scatter": 42, "k_diffuse_set": 7},
     "3d": {"k_p1_forcing": 16, "k3_p2_sgs": 14, "k3_p3_adv": 9, "k3_p3_dif": 10, "k3_p4_press_fwd": 13, "k3_p5_press_bwd": 23,
            "k3_mpdata": 5, "k_precip_a": 3, "k_precip_b": 7, "k_p7_diffuse": 7, "k_p8_micro": 14, "k_stats": 9.5, "k_kurant": 4},
 }
 
 
-CHUNKED_KERNELS = ("k_m2005_column", "k_m2005_scatter")
+CHUNKED_KERNELS = ("k_m2005_column_p1", "k_m2005_column_p2", "k_m2005_column_p3", "k_m2005_scatter")
 
 
 def peaks():
