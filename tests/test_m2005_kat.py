@@ -5,6 +5,7 @@ re-computation of GRAUPEL_INIT constants with numpy float32 arithmetic from the 
 (module_mp_graupel.F90:496-688), and conservation / positivity invariants of the scheme.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -171,3 +172,36 @@ def test_column_water_conservation_and_positivity_mixed_phase():
     st2[QV, kk] = 1.2 * RGAS / RV * ei / (inp2[0, kk] - ei)
     out2, _, rates2, _ = _column(nz, dt, st2.copy(), inp2)
     assert st2[T3, kk] < 265. and out2[NI, kk] > 0. and out2[QI, kk] > 0. and rates2[6, kk] > 0.
+
+
+def test_device_order_of_the_sedimentation_is_bit_identical(tmp_path):
+    """The device runs the sub-stepped sedimentation of the column scheme in another order (species outermost, the sub-steps of a level with
+    its density and tendency in registers; crm_m2005_col.h under __CUDA_ARCH__ / CRM_EMU).  Every update is the reference's expression on
+    the same operands, only INDEPENDENT updates are reordered, so the results must be bit-identical: the column hook compiled both ways
+    (-DCRM_EMU selects the device order on the host) is compared on random mixed-phase columns with fast-falling rain and graupel."""
+    import subprocess
+    src = [os.path.join(cm.ROOT, "oracle", f) for f in ("crm_oracle.cpp", "crm_dycore.cpp", "crm_micro.cpp", "crm_m2005.cpp", "crm_esmt.cpp", "oracle_util.cpp")]
+    alt = str(tmp_path / "liboracle_devorder.so")
+    subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-fopenmp", "-fPIC", "-std=c++17", "-DCRM_EMU", "-shared", "-o", alt] + src)
+    L2 = C.CDLL(alt)
+    rng = np.random.default_rng(12)
+    nsub = 0
+    for trial in range(6):
+        nz, dt = 40, 10.
+        st, inp, qvs = _atmosphere(nz, rh=0.9)
+        inp[2] = np.where(np.arange(nz) < 8, 40., 400.)          # thin lowest layers -> several sedimentation sub-steps
+        inp[3] = rng.uniform(-0.5, 2.0, nz)
+        for name, amp, num in ((QC, 1e-3, (NC, 120e6)), (QR, 2e-3, (NR, 3e4)), (QI, 2e-4, (NI, 2e5)), (QNI, 6e-4, (NS, 5e3)), (QG, 3e-3, (NG, 2e3))):
+            m = rng.uniform(size=nz) < 0.6
+            st[name] = np.where(m, amp * rng.uniform(0.1, 1., nz), 0.)
+            st[num[0]] = np.where(m, num[1] * rng.uniform(0.3, 1.5, nz), 0.)
+        st[QV] = qvs * rng.uniform(0.7, 1.15, nz)
+        res = []
+        for lib in (L, L2):
+            s2 = np.ascontiguousarray(st.copy()); ip = np.ascontiguousarray(inp)
+            sed = np.zeros((5, nz)); rates = np.zeros((8, nz)); prec = np.zeros(2)
+            lib.crm_oracle_m2005_column(nz, C.c_double(dt), s2.ctypes.data_as(P), ip.ctypes.data_as(P), sed.ctypes.data_as(P), rates.ctypes.data_as(P), prec.ctypes.data_as(P))
+            res.append((s2, sed, rates, prec))
+        for x, y in zip(res[0], res[1]):
+            assert np.array_equal(x, y)
+        assert res[0][3][0] > 0. and np.abs(res[0][1]).max() > 0.
