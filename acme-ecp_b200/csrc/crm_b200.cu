@@ -105,7 +105,8 @@ struct Handle {
 #endif
   crm_run_stats_t stats;
   long long launches = 0;
-  int precip_launches = 4;            // k_precip_b launches per sub-step (the last one runs any remaining sub-iterations)
+  int precip_launches = 8;            // upper bound of k_precip_b launches per sub-step (the last one runs any remaining sub-iterations in-kernel)
+  bool precip_adapt = true;           // launch nprec(previous step) + 1 passes instead of the upper bound (off when CRM_B200_PRECIP_LAUNCHES is set)
   int last_nb_u = 1;                  // buffer index holding dudt(nb) after the last run (debug fetch)
 };
 
@@ -268,7 +269,7 @@ extern "C" int crm_b200_init(int device, const crm_dims_t *d, void **handle) {
   while (nxy * CT < 32) CT <<= 1;   // a block is at least one warp (warp-shuffle slab reductions)
   if (CT < 1 || CT > 16 || nxy * CT > maxp) { g_init_err = "crm_b200_init: CRM too large for one thread block (nx <= 256 in 2-D, nx*ny <= 1024 in 3-D)"; delete h; return 4; }
   h->CT = CT;
-  if (const char *e = getenv("CRM_B200_PRECIP_LAUNCHES")) { int v = atoi(e); if (v >= 1 && v <= 16) h->precip_launches = v; }
+  if (const char *e = getenv("CRM_B200_PRECIP_LAUNCHES")) { int v = atoi(e); if (v >= 1 && v <= 16) { h->precip_launches = v; h->precip_adapt = false; } }
   h->geo = ((d->nx == 64 || d->nx == 32) && CT == crm_static_ct(d->nx)) ? d->nx : 0;
 #ifdef CRM_EMU
   h->geo = 0;
@@ -596,15 +597,26 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
     nstep++;
     dev_zero(p.cfl_bits, 8);
     LAUNCH_G(h, k_kurant, ntiles, P, CRM_KURANT_SMEM(P, CT, h->nzp, d3), p);
-    unsigned long long bits = 0;
+    unsigned long long bits = 0, pbits = 0;   // cfl of this step; prec_cfl of the previous step's last sub-step (next word)
 #ifndef CRM_EMU
-    // 8-byte read-back into a pinned host word on the handle's stream (the only host<->device round trip of a CRM step)
-    if (cudaMemcpyAsync(h->pin, p.cfl_bits, 8, cudaMemcpyDeviceToHost, t_stream) != cudaSuccess || dev_sync())
+    // 16-byte read-back into pinned host words on the handle's stream (the only host<->device round trip of a CRM step)
+    if (cudaMemcpyAsync(h->pin, p.cfl_bits, 16, cudaMemcpyDeviceToHost, t_stream) != cudaSuccess || dev_sync())
       return fail(h, 27, std::string("crm_b200_run: kurant readback failed: ") + dev_errstr());
-    bits = h->pin[0];
+    bits = h->pin[0]; pbits = h->pin[1];
 #else
-    if (dev_copy2d(&bits, 8, p.cfl_bits, 8, 8, 1, 1)) return fail(h, 27, std::string("crm_b200_run: kurant readback failed: ") + dev_errstr());
+    { unsigned long long two[2] = {0, 0};
+      if (dev_copy2d(two, 16, p.cfl_bits, 16, 16, 1, 1)) return fail(h, 27, std::string("crm_b200_run: kurant readback failed: ") + dev_errstr());
+      bits = two[0]; pbits = two[1]; }
 #endif
+    // sedimentation passes to launch in this step: one more than the previous step needed (nprec is only known on the device; passes
+    // beyond it return at once, passes missing are run inside the last launch), so neither empty launches nor the slower in-kernel
+    // loop are paid when nprec changes slowly, which it does
+    int precip_passes = h->precip_launches;
+    if (h->precip_adapt && nstep > 1) {
+      double pc; memcpy(&pc, &pbits, 8);
+      const int np_prev = (pc > R4(0.9)) ? (int)std::ceil(pc / R4(0.9)) : 1;
+      precip_passes = std::min(h->precip_launches, np_prev + 1);
+    }
     if (!h->launch_err.empty()) return fail(h, 34, "crm_b200_run: a kernel launch failed");
     double cfl; memcpy(&cfl, &bits, 8);
     if (!(cfl == cfl) || cfl > 1e30) return fail(h, 28, "kurant(): non-finite CFL (model state blew up)");
@@ -714,8 +726,8 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
         dev_zero(p.prec_cfl_bits, 8);
         LAUNCH_G(h, k_precip_a, ntiles, P, CRM_PRECIPA_SMEM(P, CT, h->nzp), p);
         // one launch per sedimentation sub-iteration; nprec is only known on the device, launches beyond it return at once
-        for (int ip = 1; ip <= h->precip_launches; ip++)
-          LAUNCH_G(h, k_precip_b, ntiles, P, CRM_PRECIPB_SMEM(P, CT, h->nzp), p, ip, ip == h->precip_launches ? 1 : 0);
+        for (int ip = 1; ip <= precip_passes; ip++)
+          LAUNCH_G(h, k_precip_b, ntiles, P, CRM_PRECIPB_SMEM(P, CT, h->nzp), p, ip, ip == precip_passes ? 1 : 0);
       }
       // uvw.F90: u <- dudt(nc) is a role rotation of the buffers (with the AB rotation of crm_module.F90:884-887)
       { int o_u = iu, o_a = ina, o_b = inb, o_c = inc; iu = o_c; ina = o_u; inb = o_a; inc = o_b; }
