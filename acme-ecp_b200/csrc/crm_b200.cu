@@ -133,8 +133,10 @@ static std::string kname(const char *s) {
   if (q == std::string::npos) return n;
   std::string base = n.substr(0, q);
   if (base == "k_m2005_column") {   // the three passes of the column scheme are timed separately: k_m2005_column_p1 / _p2 / _p3
-    const size_t c = n.rfind(','), e = n.rfind('>');
-    if (c != std::string::npos && e != std::string::npos && e > c) { std::string ph = n.substr(c + 1, e - c - 1); ph.erase(0, ph.find_first_not_of(' ')); base += "_p" + ph; }
+    // template arguments <COLS, MINB, PH, LSYNC>: the third one is the pass
+    size_t a = q + 1;
+    for (int skip = 0; skip < 2 && a != std::string::npos; skip++) { a = n.find(',', a); if (a != std::string::npos) a++; }
+    if (a != std::string::npos) { while (a < n.size() && n[a] == ' ') a++; if (a < n.size()) base += std::string("_p") + n[a]; }
   }
   return base;
 }
@@ -759,10 +761,11 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
       if (m25) {   // micro_proc (column scheme, chunk by chunk) + diagnose; ice_fall of the next sub-step is a no-op: kmin > kmax
         for (int t0 = 0; t0 < ntiles; t0 += h->m25_chunk) {
           const int nt = std::min(h->m25_chunk, ntiles - t0);
-          const int nb = (int)(((long long)nt * P + CRM_M25_COLS - 1) / CRM_M25_COLS);
-          LAUNCH(h, (k_m2005_column<CRM_M25_MINB, 1>), nb, CRM_M25_COLS, 0, p, h->m25_scr, t0, nt);
-          LAUNCH(h, (k_m2005_column<CRM_M25_MINB, 2>), nb, CRM_M25_COLS, 0, p, h->m25_scr, t0, nt);
-          LAUNCH(h, (k_m2005_column<CRM_M25_MINB, 3>), nb, CRM_M25_COLS, 0, p, h->m25_scr, t0, nt);
+          const long long ncol = (long long)nt * P;
+          if (P % 256 == 0) LAUNCH(h, (k_m2005_column<256, 3, 1, true>), (int)(ncol / 256), 256, 0, p, h->m25_scr, t0, nt);
+          else LAUNCH(h, (k_m2005_column<128, 6, 1, false>), (int)((ncol + 127) / 128), 128, 0, p, h->m25_scr, t0, nt);   // small test tiles (CRM_B200_CT)
+          LAUNCH(h, (k_m2005_column<128, 6, 2, false>), (int)((ncol + 127) / 128), 128, 0, p, h->m25_scr, t0, nt);
+          LAUNCH(h, (k_m2005_column<128, 6, 3, false>), (int)((ncol + 127) / 128), 128, 0, p, h->m25_scr, t0, nt);
           LAUNCH(h, k_m2005_scatter, nt, P, red_bytes(5), p, h->m25_scr, t0, nt);
         }
         LAUNCH_G(h, k_p8_micro, ntiles * ((nzm + CRM_P8_NL - 1) / CRM_P8_NL), P, smem_p8, p, 0, 1);

@@ -33,12 +33,15 @@ struct M25Col {   // work-space accessor of one thread: a(id, k), k = 1..nz; 32-
 // out-of-line helpers): the kernel is bound by instruction issue and instruction-cache misses, occupancy hides both
 #define CRM_M25_MINB 6
 // PH = 1: gather + satadj_liquid + process rates; 2: sedimentation; 3: final update + surface precipitation (three launches per chunk).
-template <int MINB, int PH>
-__global__ void __launch_bounds__(CRM_M25_COLS, MINB) k_m2005_column(CrmP p, double *scr, int tile0, int ntiles_chunk) {
+// COLS threads per block, MINB blocks per SM (COLS * MINB = 768 threads at 80 registers).  The process-rate pass runs 256-thread blocks:
+// its warps start every level together (M25_LEVEL_SYNC), and fewer, larger blocks mean fewer distinct code positions per SM for a pass
+// that is bound by instruction-cache misses (p1 5.66 -> 4.97 ms with the level barrier, -> 4.60 with 256 threads; p2 prefers 128).
+template <int COLS, int MINB, int PH, bool LSYNC>
+__global__ void __launch_bounds__(COLS, MINB) k_m2005_column(CrmP p, double *scr, int tile0, int ntiles_chunk) {
   using namespace m2005;
   const int P = p.P, CT = p.CT;
-  const long long c = (long long)blockIdx.x * CRM_M25_COLS + threadIdx.x;
-  if (c >= (long long)ntiles_chunk * P) return;
+  const long long c = (long long)blockIdx.x * COLS + threadIdx.x;
+  if (c >= (long long)ntiles_chunk * P) return;   // never taken when LSYNC (the host picks LSYNC only if P is a multiple of COLS)
   // column order inside a tile: (lane, cell), i.e. a warp holds 32 ADJACENT columns of ONE CRM (clouds span several columns of a
   // CRM, different CRMs are unrelated: fewer warps that have to execute both the active and the clear-air paths of a level)
   const int tl = (int)(c / P), r = (int)(c - (long long)tl * P), tile = tile0 + tl;
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(CRM_M25_COLS, MINB) k_m2005_column(CrmP p, dou
     a(T3, k) = tabs; a(QV, k) = qv; a(QC, k) = qc;
   }
   double sfcpcp = 0., sfcicepcp = 0.;
-  m2005::column_ph<PH>(a, c_m25, nzm, dtn, sfcpcp, sfcicepcp);
+  m2005::column_ph<PH, LSYNC>(a, c_m25, nzm, dtn, sfcpcp, sfcicepcp);
   if (PH == 3) {
     const long long c2 = (long long)tile * P + tid;
     p.precsfc[c2] = p.precsfc[c2] + sfcpcp / dz;

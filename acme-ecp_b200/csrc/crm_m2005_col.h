@@ -35,10 +35,14 @@ __device__ __noinline__ double m25_pow_dev(double x, double y) {
 __device__ __noinline__ double m25_exp_dev(double x) { return exp(x); }
 __device__ __noinline__ double m25_log_dev(double x) { return log(x); }
 #define M25_POW(x, y) m25_pow_dev(x, y)
+// the warps of a block start every level of the process-rate pass together: they then fetch the same instructions at about the same
+// time (the pass is bound by instruction-cache misses); the launch guarantees that every thread of the block runs the loop
+#define M25_LEVEL_SYNC() __syncthreads()
 #define M25_EXP(x) m25_exp_dev(x)
 #define M25_LOG(x) m25_log_dev(x)
 #else
 #define M25_POW(x, y) pow(x, y)
+#define M25_LEVEL_SYNC()
 #define M25_EXP(x) exp(x)
 #define M25_LOG(x) log(x)
 #endif
@@ -361,7 +365,7 @@ M25_HD inline double activate2(const Cn &c, double DUM, double T, double EVS, do
 // sedimentation / final update); the device runs them as three kernels because the scheme's code size (20 k instructions) thrashes the
 // instruction cache.  Between the passes the column's LTRUE flag and the two surface precipitation sums travel in levels 1-3 of the W3
 // array (an input that only the first section reads).
-template <int PH, class A, class Cn>
+template <int PH, bool LSYNC, class A, class Cn>
 M25_HD inline void column_ph(A &a, const Cn &c, const int nz, const double DT, double &PRECRT, double &SNOWRT) {
   const double PI = c.PI, QSMALL = c.QSMALL, TMELT = c.TMELT, RHOW = c.RHOW, RHOSU = c.RHOSU;
   const double BS = c.BS, BR = c.BR, BG = c.BG, BI = c.BI, BC = c.BC, DS = c.DS, DG = c.DG, DI = c.DI, DCS = c.DCS;
@@ -377,6 +381,7 @@ M25_HD inline void column_ph(A &a, const Cn &c, const int nz, const double DT, d
 
   if (PH == 0 || PH == 1) {
   for (int K = 1; K <= nz; K++) {
+    if (LSYNC) { M25_LEVEL_SYNC(); }   // only when the launch runs whole blocks
     double QC3D = a(QC, K), QI3D = a(QI, K), QNI3D = a(QNI, K), QR3D = a(QR, K), NC3D = a(NC, K), NI3D = a(NI, K), NS3D = a(NS, K),
            NR3D = a(NR, K), QG3D = a(QG, K), NG3D = a(NG, K), T3D = a(T3, K), QV3D = a(QV, K);
     const double PRESK = a(PRES, K), RHOK = a(RHO, K);
@@ -1107,7 +1112,7 @@ M25_HD inline void column_ph(A &a, const Cn &c, const int nz, const double DT, d
 }
 template <class A, class Cn>
 M25_HD inline void column(A &a, const Cn &c, const int nz, const double DT, double &PRECRT, double &SNOWRT) {
-  column_ph<0>(a, c, nz, DT, PRECRT, SNOWRT);
+  column_ph<0, false>(a, c, nz, DT, PRECRT, SNOWRT);
 }
 
 }  // namespace m2005
