@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -71,6 +72,18 @@ namespace {
 
 struct KTime { const char *name; double ms; long long n; };
 
+// crm_state / crm_rad of one physics chunk kept in HBM across GCM steps (crm_b200_resident_*): one allocation, boundary layout
+constexpr int RES_NST = 17, RES_NRAD = 10;
+struct Resident {
+  int ncrms = 0, ld = 0;
+  double *base = nullptr;
+  size_t bytes = 0;
+  double *st[RES_NST] = {};    // member order of crm_state_t
+  double *rad[RES_NRAD] = {};  // member order of crm_rad_t (qrad first)
+};
+static_assert(sizeof(crm_state_t) == RES_NST * sizeof(double *) && sizeof(crm_rad_t) == RES_NRAD * sizeof(double *),
+              "crm_state_t / crm_rad_t are plain arrays of pointers");
+
 struct Handle {
   bool ktiming = false;
   DevTimer ktimer;
@@ -108,6 +121,8 @@ struct Handle {
   int precip_launches = 8;            // upper bound of k_precip_b launches per sub-step (the last one runs any remaining sub-iterations in-kernel)
   bool precip_adapt = true;           // launch nprec(previous step) + 1 passes instead of the upper bound (off when CRM_B200_PRECIP_LAUNCHES is set)
   int last_nb_u = 1;                  // buffer index holding dudt(nb) after the last run (debug fetch)
+  std::map<int, Resident> resident;   // device-resident crm_state / crm_rad by physics chunk
+  int last_lchnk = 0; bool last_is_resident = false;   // chunk whose outputs the workspace holds (crm_b200_history_field)
 };
 
 std::string g_init_err;
@@ -221,6 +236,7 @@ extern "C" int crm_b200_free(void *handle) {
   if (h->pin) cudaFreeHost(h->pin);
 #endif
   for (void *q : h->allocs) dev_free(q);
+  for (auto &r : h->resident) dev_free(r.second.base);
 #ifndef CRM_EMU
   if (h->stream) cudaStreamDestroy(h->stream);
   t_stream = nullptr; t_launch = nullptr;
@@ -423,6 +439,7 @@ extern "C" int crm_b200_run(void *handle, const crm_dims_t *d, const crm_input_t
   if (!handle) return 1;
   Handle *h = (Handle *)handle;
   h->err.clear();
+  h->last_is_resident = false;
   const crm_dims_t &d0 = h->d0;
   if (d->nx != d0.nx || d->ny != d0.ny || d->nzm != d0.nzm || d->plev != d0.plev || d->nx_rad != d0.nx_rad || d->ny_rad != d0.ny_rad ||
       d->dx != d0.dx || d->dt != d0.dt || d->micro != d0.micro || d->esmt != d0.esmt)
@@ -1002,6 +1019,209 @@ extern "C" int crm_b200_physics_post(void *handle, const crm_dims_t *d, const do
   if (dev_sync()) return fail(h, 47, std::string("crm_b200_physics_post: kernel failure: ") + dev_errstr());
   for (const Staged *v : {&pc, &pl, &sc, &sn, &ts, &tv, &tl, &ti, &tc, &pdp, &sdp}) stage_out(*v, ld, n);
   return glue_qrad(h, d, pdel, qrad, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident crm_state / crm_rad keyed by the physics chunk, and the CRM-level history fields (include/crm_b200.h).
+// ------------------------------------------------------------------------------------------------
+namespace {
+const char *const kStateNames[RES_NST] = {"u_wind", "v_wind", "w_wind", "temperature", "qt", "qp", "qn", "nc", "qr", "nr", "qi", "ni", "qs", "ns",
+                                          "qg", "ng", "qc"};
+const char *const kRadNames[RES_NRAD] = {"qrad", "rad_temperature", "rad_qv", "rad_qc", "rad_qi", "rad_cld", "rad_nc", "rad_ni", "rad_qs", "rad_ns"};
+int resident_check(Handle *h, const crm_dims_t *d, const char *who) {
+  const crm_dims_t &d0 = h->d0;
+  if (d->nx != d0.nx || d->ny != d0.ny || d->nzm != d0.nzm || d->plev != d0.plev || d->nx_rad != d0.nx_rad || d->ny_rad != d0.ny_rad || d->micro != d0.micro)
+    return fail(h, 50, std::string(who) + ": geometry differs from crm_b200_init");
+  if (d->ncrms < 1 || d->ncrms > d0.ncrms || d->ld < d->ncrms || d->ld > h->ld_max) return fail(h, 51, std::string(who) + ": need ncrms <= init ncrms and ncrms <= ld <= init ld");
+  if (select_handle(h)) return fail(h, 52, std::string(who) + ": cannot select device: " + dev_errstr());
+  return 0;
+}
+Resident *resident_find(Handle *h, int lchnk, const crm_dims_t *d, const char *who, int &rc) {
+  auto it = h->resident.find(lchnk);
+  if (it == h->resident.end()) { rc = fail(h, 53, std::string(who) + ": chunk " + std::to_string(lchnk) + " has no resident state (crm_b200_resident_put first)"); return nullptr; }
+  if (d && (it->second.ncrms != d->ncrms || it->second.ld != d->ld)) { rc = fail(h, 51, std::string(who) + ": ncrms / ld differ from crm_b200_resident_put"); return nullptr; }
+  rc = 0;
+  return &it->second;
+}
+}  // namespace
+
+extern "C" int crm_b200_resident_put(void *handle, int lchnk, const crm_dims_t *d, const crm_state_t *st, const crm_rad_t *rad) {
+  if (!handle) return 1;
+  Handle *h = (Handle *)handle;
+  h->err.clear();
+  if (lchnk < 0) return fail(h, 55, "crm_b200_resident_put: lchnk must be >= 0");
+  if (int rc = resident_check(h, d, "crm_b200_resident_put")) return rc;
+  const size_t n3 = (size_t)d->ld * d->nx * d->ny * d->nzm, nr = (size_t)d->ld * d->nx_rad * d->ny_rad * d->nzm;
+  const int nst = h->m25 ? RES_NST : 7, nrad = h->m25 ? RES_NRAD : 6;
+  auto it = h->resident.find(lchnk);
+  if (it != h->resident.end() && (it->second.ncrms != d->ncrms || it->second.ld != d->ld)) { dev_free(it->second.base); h->resident.erase(it); it = h->resident.end(); }
+  if (it == h->resident.end()) {
+    Resident r;
+    r.ncrms = d->ncrms; r.ld = d->ld;
+    r.bytes = ((size_t)nst * n3 + (size_t)nrad * nr) * 8;
+    r.base = (double *)dev_alloc(r.bytes);
+    if (!r.base) return fail(h, 56, "crm_b200_resident_put: device allocation failed (" + std::to_string(r.bytes >> 20) + " MiB)");
+    if (dev_zero(r.base, r.bytes)) { dev_free(r.base); return fail(h, 56, std::string("crm_b200_resident_put: memset failed: ") + dev_errstr()); }
+    double *q = r.base;
+    for (int m = 0; m < nst; m++) { r.st[m] = q; q += n3; }
+    for (int m = 0; m < nrad; m++) { r.rad[m] = q; q += nr; }
+    it = h->resident.emplace(lchnk, r).first;
+  }
+  Resident &r = it->second;
+  int zrc = 0;
+  if (st) {
+    double *src[RES_NST];
+    memcpy(src, st, sizeof(src));
+    for (int m = 0; m < nst; m++) if (src[m]) zrc |= copy_rows(r.st[m], r.ld, src[m], d->ld, d->ncrms, (size_t)d->nx * d->ny * d->nzm);
+  }
+  if (rad) {
+    double *src[RES_NRAD];
+    memcpy(src, rad, sizeof(src));
+    for (int m = 0; m < nrad; m++) if (src[m]) zrc |= copy_rows(r.rad[m], r.ld, src[m], d->ld, d->ncrms, (size_t)d->nx_rad * d->ny_rad * d->nzm);
+  }
+  if (zrc || dev_sync()) return fail(h, 57, std::string("crm_b200_resident_put: copy failed: ") + dev_errstr());
+  if (h->last_is_resident && h->last_lchnk == lchnk) h->last_is_resident = false;   // the workspace no longer matches this chunk's state
+  return 0;
+}
+
+extern "C" int crm_b200_resident_run(void *handle, int lchnk, const crm_dims_t *d, const crm_input_t *in, crm_rad_t *rad, crm_output_t *out) {
+  if (!handle) return 1;
+  Handle *h = (Handle *)handle;
+  h->err.clear();
+  if (int rc = resident_check(h, d, "crm_b200_resident_run")) return rc;
+  int rc = 0;
+  Resident *r = resident_find(h, lchnk, d, "crm_b200_resident_run", rc);
+  if (!r) return rc;
+  const size_t ncr = (size_t)d->nx_rad * d->ny_rad * d->nzm;
+  long long h2d = 0, d2h = 0;
+  if (rad && rad->qrad) {
+    if (copy_rows(r->rad[0], r->ld, rad->qrad, d->ld, d->ncrms, ncr)) return fail(h, 57, std::string("crm_b200_resident_run: qrad copy failed: ") + dev_errstr());
+    if (!is_dev_ptr(rad->qrad)) h2d += (long long)d->ncrms * ncr * 8;
+  }
+  crm_state_t cs;
+  crm_rad_t cr;
+  memcpy(&cs, r->st, sizeof(cs));
+  memcpy(&cr, r->rad, sizeof(cr));
+  rc = crm_b200_run(handle, d, in, &cs, &cr, out);
+  if (rc) return rc;
+  if (rad) {
+    double *dst[RES_NRAD];
+    memcpy(dst, rad, sizeof(dst));
+    const int nrad = h->m25 ? RES_NRAD : 6;
+    for (int m = 1; m < nrad; m++) {
+      if (!dst[m]) continue;
+      copy_rows(dst[m], d->ld, r->rad[m], r->ld, d->ncrms, ncr);
+      if (!is_dev_ptr(dst[m])) d2h += (long long)d->ncrms * ncr * 8;
+    }
+    if (dev_sync()) return fail(h, 57, std::string("crm_b200_resident_run: crm_rad copy failed: ") + dev_errstr());
+  }
+  h->stats.h2d_bytes += h2d; h->stats.d2h_bytes += d2h;
+  h->last_lchnk = lchnk; h->last_is_resident = true;
+  return 0;
+}
+
+extern "C" int crm_b200_resident_get(void *handle, int lchnk, const crm_dims_t *d, crm_state_t *st, crm_rad_t *rad) {
+  if (!handle) return 1;
+  Handle *h = (Handle *)handle;
+  h->err.clear();
+  if (int rc = resident_check(h, d, "crm_b200_resident_get")) return rc;
+  int rc = 0;
+  Resident *r = resident_find(h, lchnk, d, "crm_b200_resident_get", rc);
+  if (!r) return rc;
+  int zrc = 0;
+  if (st) {
+    double *dst[RES_NST];
+    memcpy(dst, st, sizeof(dst));
+    for (int m = 0; m < (h->m25 ? RES_NST : 7); m++) if (dst[m]) zrc |= copy_rows(dst[m], d->ld, r->st[m], r->ld, d->ncrms, (size_t)d->nx * d->ny * d->nzm);
+  }
+  if (rad) {
+    double *dst[RES_NRAD];
+    memcpy(dst, rad, sizeof(dst));
+    for (int m = 0; m < (h->m25 ? RES_NRAD : 6); m++) if (dst[m]) zrc |= copy_rows(dst[m], d->ld, r->rad[m], r->ld, d->ncrms, (size_t)d->nx_rad * d->ny_rad * d->nzm);
+  }
+  if (zrc || dev_sync()) return fail(h, 57, std::string("crm_b200_resident_get: copy failed: ") + dev_errstr());
+  return 0;
+}
+
+extern "C" double *crm_b200_resident_field(void *handle, int lchnk, const char *name) {
+  if (!handle || !name) return nullptr;
+  Handle *h = (Handle *)handle;
+  auto it = h->resident.find(lchnk);
+  if (it == h->resident.end()) return nullptr;
+  for (int m = 0; m < RES_NST; m++) if (!strcmp(name, kStateNames[m])) return it->second.st[m];
+  for (int m = 0; m < RES_NRAD; m++) if (!strcmp(name, kRadNames[m])) return it->second.rad[m];
+  return nullptr;
+}
+
+extern "C" int crm_b200_resident_drop(void *handle, int lchnk) {
+  if (!handle) return 1;
+  Handle *h = (Handle *)handle;
+  h->err.clear();
+  if (dev_init(h->device)) return fail(h, 52, "crm_b200_resident_drop: cannot select device");
+  if (lchnk < 0) {
+    for (auto &r : h->resident) dev_free(r.second.base);
+    h->resident.clear();
+    h->last_is_resident = false;
+    return 0;
+  }
+  auto it = h->resident.find(lchnk);
+  if (it == h->resident.end()) return fail(h, 53, "crm_b200_resident_drop: chunk " + std::to_string(lchnk) + " has no resident state");
+  dev_free(it->second.base);
+  h->resident.erase(it);
+  if (h->last_lchnk == lchnk) h->last_is_resident = false;
+  return 0;
+}
+
+extern "C" long long crm_b200_resident_bytes(void *handle) {
+  if (!handle) return -1;
+  long long n = 0;
+  for (auto &r : ((Handle *)handle)->resident) n += (long long)r.second.bytes;
+  return n;
+}
+
+extern "C" int crm_b200_history_field(void *handle, int lchnk, const crm_dims_t *d, const char *name, double *buf) {
+  if (!handle) return 1;
+  Handle *h = (Handle *)handle;
+  h->err.clear();
+  if (!name || !buf) return fail(h, 58, "crm_b200_history_field: name and buf must not be NULL");
+  if (int rc = resident_check(h, d, "crm_b200_history_field")) return rc;
+  int rc = 0;
+  Resident *r = resident_find(h, lchnk, d, "crm_b200_history_field", rc);
+  if (!r) return rc;
+  CrmP &p = h->p;
+  const size_t ncols3 = (size_t)d->nx * d->ny * d->nzm;
+  const std::string nm(name);
+  // (1) members of crm_state: straight from the resident copy
+  static const struct { const char *hist; int member; bool m25; } kState[] = {
+      {"CRM_U", 0, false}, {"CRM_V", 1, false}, {"CRM_W", 2, false}, {"CRM_T", 3, false}, {"CRM_NC", 7, true}, {"CRM_QR", 8, true}, {"CRM_NR", 9, true},
+      {"CRM_NI", 11, true}, {"CRM_QS", 12, true}, {"CRM_NS", 13, true}, {"CRM_QG", 14, true}, {"CRM_NG", 15, true}};
+  for (const auto &e : kState)
+    if (nm == e.hist) {
+      if (e.m25 && !h->m25) return fail(h, 59, "crm_b200_history_field: " + nm + " exists only with m2005 microphysics");
+      if (copy_rows(buf, d->ld, r->st[e.member], r->ld, d->ncrms, ncols3) || dev_sync()) return fail(h, 57, std::string("crm_b200_history_field: copy failed: ") + dev_errstr());
+      return 0;
+    }
+  // (2) crm_output fields: the workspace of the last run, which must have been this chunk's
+  const double *src = nullptr;
+  bool qv = false;
+  if (nm == "CRM_QV") qv = true;
+  else if (nm == "CRM_QC") src = p.qcl; else if (nm == "CRM_QI") src = p.qci; else if (nm == "CRM_QPC") src = p.qpl; else if (nm == "CRM_QPI") src = p.qpi;
+  else if (nm == "CRM_TK") src = p.tk; else if (nm == "CRM_TKH") src = p.tkh;
+  else if (h->m25) {
+    static const char *const kRate[8] = {"CRM_AUT", "CRM_ACC", "CRM_EVPC", "CRM_EVPR", "CRM_MLT", "CRM_SUB", "CRM_DEP", "CRM_CON"};
+    for (int q = 0; q < 8; q++) if (nm == kRate[q]) src = p.m_rate[q];
+  }
+  if (!qv && !src) return fail(h, 59, "crm_b200_history_field: unknown field " + nm);
+  if (!h->last_is_resident || h->last_lchnk != lchnk)
+    return fail(h, 54, "crm_b200_history_field: " + nm + " is a crm_output field and the last crm_b200_resident_run on this handle was not on chunk " + std::to_string(lchnk));
+  double *ext = is_dev_ptr(buf) ? buf : h->stage;
+  const int nxy = d->nx * d->ny;
+  if (qv) LAUNCH(h, k_hist_qv, p.ntiles * d->nzm, p.P, 0, p, p.qt, p.qcl, h->m25 ? (const double *)nullptr : p.qci, h->tstride, p.P, nxy, d->nzm, ext, d->ld);
+  else LAUNCH(h, k_int_to_ext, p.ntiles * d->nzm, p.P, 0, p, src, h->tstride, p.P, nxy, d->nzm, ext, d->ld, 1.0);
+  if (ext != buf) copy_rows(buf, d->ld, ext, d->ld, d->ncrms, ncols3);
+  if (dev_sync()) return fail(h, 57, std::string("crm_b200_history_field: kernel or copy failed: ") + dev_errstr());
+  if (!h->launch_err.empty()) return fail(h, 34, "crm_b200_history_field: a kernel launch failed");
+  return 0;
 }
 
 extern "C" long long crm_b200_debug_fetch(void *handle, const char *name, double *host_buf, size_t n) {

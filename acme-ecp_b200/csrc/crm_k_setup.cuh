@@ -73,6 +73,22 @@ __global__ void k_int_to_ext(CrmP p, const double *src, long long src_tstride, i
   ext[(size_t)icrm + (size_t)ld * ((size_t)i + (size_t)nxe * (size_t)k)] = src[(long long)tile * src_tstride + (long long)k * Pd + tid] * scale;
 }
 
+// History field CRM_QV (PHYS/crm_physics.F90:1219-1223): (crm_state%qt - crm_output%qcl) - crm_output%qci for sam1mom,
+// crm_state%qt - crm_output%qcl for m2005 (qci == nullptr), from the internal fields of the last run to the boundary layout.
+__global__ void k_hist_qv(CrmP p, const double *qt, const double *qcl, const double *qci, long long src_tstride, int Pd, int nxe, int nk,
+                          double *ext, int ld) {
+  const int tid = threadIdx.x, CT = p.CT;
+  const int tile = blockIdx.x / nk, k = blockIdx.x - tile * nk;
+  if (tid >= Pd) return;
+  const int i = tid / CT, lane = tid - i * CT;
+  const int icrm = tile * CT + lane;
+  if (icrm >= p.ncrms) return;
+  const long long s = (long long)tile * src_tstride + (long long)k * Pd + tid;
+  double v = qt[s] - qcl[s];
+  if (qci) v = v - qci[s];
+  ext[(size_t)icrm + (size_t)ld * ((size_t)i + (size_t)nxe * (size_t)k)] = v;
+}
+
 __global__ void k_fill(double *a, long long n, double v) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < n) a[idx] = v;

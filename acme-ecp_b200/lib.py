@@ -47,6 +47,21 @@ def load(path=None):
     lib.crm_b200_physics_post.restype = C.c_int
     lib.crm_b200_physics_post.argtypes = [C.c_void_p, C.POINTER(abi.crm_dims_t), abi.c_dp, abi.c_dp, C.POINTER(abi.crm_output_t),
                                           C.POINTER(abi.crm_ptend_t)]
+    lib.crm_b200_resident_put.restype = C.c_int
+    lib.crm_b200_resident_put.argtypes = [C.c_void_p, C.c_int, C.POINTER(abi.crm_dims_t), C.POINTER(abi.crm_state_t), C.POINTER(abi.crm_rad_t)]
+    lib.crm_b200_resident_run.restype = C.c_int
+    lib.crm_b200_resident_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(abi.crm_dims_t), C.POINTER(abi.crm_input_t), C.POINTER(abi.crm_rad_t),
+                                          C.POINTER(abi.crm_output_t)]
+    lib.crm_b200_resident_get.restype = C.c_int
+    lib.crm_b200_resident_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(abi.crm_dims_t), C.POINTER(abi.crm_state_t), C.POINTER(abi.crm_rad_t)]
+    lib.crm_b200_resident_field.restype = C.c_void_p
+    lib.crm_b200_resident_field.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+    lib.crm_b200_resident_drop.restype = C.c_int
+    lib.crm_b200_resident_drop.argtypes = [C.c_void_p, C.c_int]
+    lib.crm_b200_resident_bytes.restype = C.c_longlong
+    lib.crm_b200_resident_bytes.argtypes = [C.c_void_p]
+    lib.crm_b200_history_field.restype = C.c_int
+    lib.crm_b200_history_field.argtypes = [C.c_void_p, C.c_int, C.POINTER(abi.crm_dims_t), C.c_char_p, abi.c_dp]
     _libs[path] = lib
     return lib
 
@@ -95,6 +110,54 @@ class CrmHandle:
         if rc != 0:
             raise CrmB200Error("crm_b200_physics_post failed (%d): %s" % (rc, self.lib.crm_b200_last_error(self.h).decode()))
         return pt
+
+    # ---- device-resident crm_state / crm_rad keyed by the physics chunk (crm_b200_resident_*) ----
+    def _chk(self, rc, what):
+        if rc != 0:
+            raise CrmB200Error("%s failed (%d): %s" % (what, rc, self.lib.crm_b200_last_error(self.h).decode()))
+
+    def resident_put(self, lchnk, dims, state=None, rad=None):
+        """Upload (members of) the chunk's crm_state / crm_rad: the pbuf fields of crm_physics.F90:126-147 now live in HBM."""
+        d = dims.c_struct()
+        cs = state.c_struct() if state is not None else None
+        cr = rad.c_struct() if rad is not None else None
+        self._chk(self.lib.crm_b200_resident_put(self.h, int(lchnk), C.byref(d), C.byref(cs) if cs is not None else None,
+                                                 C.byref(cr) if cr is not None else None), "crm_b200_resident_put")
+
+    def resident_run(self, lchnk, dims, inp, rad=None, out=None):
+        """crm() on the chunk's resident state; ``rad`` (optional) supplies qrad and receives copies of the crm_rad results."""
+        if out is None:
+            out = crm_output_type().initialize(dims)
+        d = dims.c_struct()
+        ci, co = inp.c_struct(), out.c_struct()
+        cr = rad.c_struct() if rad is not None else None
+        self._chk(self.lib.crm_b200_resident_run(self.h, int(lchnk), C.byref(d), C.byref(ci), C.byref(cr) if cr is not None else None,
+                                                 C.byref(co)), "crm_b200_resident_run")
+        return out
+
+    def resident_get(self, lchnk, dims, state=None, rad=None):
+        d = dims.c_struct()
+        cs = state.c_struct() if state is not None else None
+        cr = rad.c_struct() if rad is not None else None
+        self._chk(self.lib.crm_b200_resident_get(self.h, int(lchnk), C.byref(d), C.byref(cs) if cs is not None else None,
+                                                 C.byref(cr) if cr is not None else None), "crm_b200_resident_get")
+
+    def resident_field(self, lchnk, name):
+        """Device address (int) of one resident member, or None."""
+        return self.lib.crm_b200_resident_field(self.h, int(lchnk), name.encode())
+
+    def resident_drop(self, lchnk=-1):
+        self._chk(self.lib.crm_b200_resident_drop(self.h, int(lchnk)), "crm_b200_resident_drop")
+
+    def resident_bytes(self):
+        return int(self.lib.crm_b200_resident_bytes(self.h))
+
+    def history_field(self, lchnk, dims, name):
+        """One `outfld('CRM_*')` field of crm_physics.F90:1214-1273 for a resident chunk, boundary layout (ld, nx, ny, nzm)."""
+        buf = np.zeros(abi.shape_of("crm3d", dims), order="F")
+        d = dims.c_struct()
+        self._chk(self.lib.crm_b200_history_field(self.h, int(lchnk), C.byref(d), name.encode(), abi.dptr(buf)), "crm_b200_history_field")
+        return buf
 
     def stats(self):
         s = abi.crm_run_stats_t()

@@ -238,6 +238,40 @@ def run_e2e(args, pkg, abi, h, dims, inp, ci, st, rad, dstate, big, world, barri
            "steps": e2e_steps, "host_buffers": "pinned", "ncrms_per_gpu": int(n_e2e)}
     if n_e2e < dims_full.ncrms:
         res["note"] = "host RAM share of this rank holds the pinned boundary arrays of %d of %d CRMs" % (n_e2e, dims_full.ncrms)
+    if args.e2e_resident:
+        # Same call with crm_state / crm_rad resident in HBM keyed by the physics chunk (crm_b200_resident_*):
+        # per step only crm_input + qrad go in and crm_output + the crm_rad results come out (host buffers, pinned).  The one-off
+        # upload of the chunk's state (crm_b200_resident_put, the first GCM step) is outside the timed region.
+        import ctypes as C
+        dstate.clear()                 # the device-pointer arm is finished: give its state (10-22 GB) back before the resident copy is made
+        torch.cuda.empty_cache()
+        d3 = dims.copy(igstep=3)
+        h.resident_put(0, d3, hst, hrad)
+        cd = d3.c_struct()
+
+        def rrun():
+            rc = h.lib.crm_b200_resident_run(h.h, 0, C.byref(cd), C.byref(ci), C.byref(hcr), C.byref(hco))
+            if rc != 0:
+                raise RuntimeError("crm_b200_resident_run failed (%d): %s" % (rc, h.lib.crm_b200_last_error(h.h).decode()))
+        rrun()
+        barrier()
+        t0 = time.time()
+        upd_r, h2d, d2h = 0, 0, 0
+        for _ in range(e2e_steps):
+            rrun()
+            s = h.stats()
+            upd_r += dims.cells * s["ncycle_sum"]; h2d = s["h2d_bytes"]; d2h = s["d2h_bytes"]
+        barrier()
+        tr = time.time() - t0
+        t = torch.tensor([tr, float(upd_r)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            tr, upd_r = float(tmax[0]), float(tsum[1])
+        res["resident"] = {"value": upd_r / tr, "unit": "cell-updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                           "steps": e2e_steps, "resident_bytes": h.resident_bytes(),
+                           "what": "crm_state/crm_rad kept in HBM by crm_b200_resident_run; crm_input, qrad in, crm_output and crm_rad results out"}
+        h.resident_drop(-1)
     return res
 
 
@@ -400,6 +434,7 @@ def main():
     ap.add_argument("--ncrms", type=int, default=0, help="override the batch size (testing only)")
     ap.add_argument("--nstop", type=int, default=0, help="override CRM steps per call (testing only)")
     ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--e2e-resident", type=int, default=1, help="also time the end-to-end call with the state resident in HBM (0 = skip)")
     ap.add_argument("--cpu-ncrms", type=int, default=0, help="CRMs of the CPU sample (default: max(128, 8 per host thread))")
     ap.add_argument("--partition", default="auto", choices=["auto", "replicate", "block", "roundrobin"],
                     help="replicate: every rank runs the config's batch (weak scaling); block/roundrobin: the config's batch is ONE global "

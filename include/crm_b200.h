@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CRM_B200_ABI_VERSION 4
+#define CRM_B200_ABI_VERSION 5
 
 /* Compile-time constants of the reference (PHYS/crmdims.F90:13-22, CRM/domain.F90:9-13) and the
  * hidden module inputs of crm() (time_manager:get_nstep, accelerate_crm_mod namelist). */
@@ -167,6 +167,39 @@ int crm_b200_physics_pre(void *handle, const crm_dims_t *dims, const double *pde
  * for precsc/precsl, updated in place in `out`), CLD, and qrad *= pdel (:1160-1209).  NULL members of ptend are skipped. */
 int crm_b200_physics_post(void *handle, const crm_dims_t *dims, const double *pdel, double *qrad, crm_output_t *out,
                           crm_ptend_t *ptend);
+
+/* ---- device-resident crm_state / crm_rad across GCM steps, keyed by the physics chunk (ABI >= 5) -----------------------
+ * SURVEY.md 8(f) items 1 and 3.  In the reference crm_state%* and crm_rad%* are pointers into the physics buffer of chunk
+ * `lchnk` (PHYS/crm_physics.F90:126-147 pbuf_add_field, :811-828 pbuf_get_field): they persist from one GCM step to the
+ * next and nothing but crm() (and the radiation, for crm_rad) touches them, yet every call moves them across the host
+ * boundary (7 x 1.44 GB each way at BASELINE config 2).  Here the handle keeps one copy per chunk in HBM, in the boundary
+ * layout with the leading dimension given at `put`:
+ *   put   after the caller has seeded the state on the first step (crm_physics.F90:912-939) or read a restart file;
+ *         NULL members are zero on creation and left alone on later puts;
+ *   run   one crm() call on the resident state: only crm_input, (optionally) qrad and the outputs cross the boundary.
+ *         `rad` may be NULL; a non-NULL rad->qrad replaces the resident qrad before the call, non-NULL output members of
+ *         `rad` receive copies of the resident results after it.  dims->ncrms and dims->ld must equal those of `put`;
+ *   get   copies resident members into the caller's arrays (restart write; NULL members skipped; either struct may be NULL);
+ *   field device pointer of one resident member for callers that run their own device code on it (a GPU radiation
+ *         reading crm_rad%*, crm_b200_physics_pre/post on "qrad"): crm_state member names, crm_rad members prefixed
+ *         "rad_" ("rad_temperature", ...) and "qrad"; NULL if unknown;
+ *   drop  frees one chunk, or all of them with lchnk < 0 (crm_b200_free drops them too).
+ * Several chunks may share one handle (one workspace arena): calls on a handle are serialised anyway. */
+int crm_b200_resident_put(void *handle, int lchnk, const crm_dims_t *dims, const crm_state_t *state, const crm_rad_t *rad);
+int crm_b200_resident_run(void *handle, int lchnk, const crm_dims_t *dims, const crm_input_t *in, crm_rad_t *rad,
+                          crm_output_t *out);
+int crm_b200_resident_get(void *handle, int lchnk, const crm_dims_t *dims, crm_state_t *state, crm_rad_t *rad);
+double *crm_b200_resident_field(void *handle, int lchnk, const char *name);
+int crm_b200_resident_drop(void *handle, int lchnk);
+long long crm_b200_resident_bytes(void *handle);   /* HBM held by resident chunks of this handle */
+
+/* CRM-level history stream of crm_physics_tend (PHYS/crm_physics.F90:1214-1273, the `outfld('CRM_*')` calls) for a resident
+ * chunk: writes the named field in the boundary layout (dims->ld, nx, ny, nzm) into `buf` (host or device).  State fields
+ * "CRM_U","CRM_V","CRM_W","CRM_T" (+ m2005 "CRM_NC","CRM_NI","CRM_NR","CRM_NS","CRM_NG","CRM_QR","CRM_QS","CRM_QG") come
+ * from the resident copy; "CRM_QV" (= qt - qcl - qci, m2005: qt - qcl, formed on the device), "CRM_QC","CRM_QI","CRM_QPC",
+ * "CRM_QPI","CRM_TK","CRM_TKH" (+ m2005 "CRM_AUT","CRM_ACC","CRM_EVPC","CRM_EVPR","CRM_MLT","CRM_SUB","CRM_DEP","CRM_CON")
+ * come from the workspace of the last crm_b200_resident_run and are refused (rc 54) if that run was not on `lchnk`. */
+int crm_b200_history_field(void *handle, int lchnk, const crm_dims_t *dims, const char *name, double *buf);
 
 /* Message of the last failure on this handle (or of a failed init if handle==NULL). */
 const char *crm_b200_last_error(void *handle);

@@ -24,6 +24,16 @@ module crm_module
   implicit none
   private
   public :: crm
+  public :: crm_b200_resident, crm_b200_sync_host
+
+  ! Device-resident mode (SURVEY 8(f) item 1; include/crm_b200.h crm_b200_resident_*): crm_state stays in HBM keyed by lchnk.  The first
+  ! crm() call of a chunk uploads the pbuf copy (seeded on the first step, crm_physics.F90:912-939, or read from a restart file);
+  ! later calls move only crm_input, crm_rad (the host radiation reads / writes it) and crm_output.  The pbuf copy of crm_state is then
+  ! stale until crm_b200_sync_host(lchnk, ...) is called -- the integration patch calls it before restart writes and before the
+  ! CRM_U/CRM_W/CRM_T/... outfld calls (crm_physics.F90:1214-1231) on history steps (INTEGRATION.md).
+  logical, save :: crm_b200_resident = .false.
+  integer, parameter :: max_chunks = 4096
+  integer, save :: seen_chunk(max_chunks) = -1, nseen = 0
 
   ! ---- mirrors of the C structs of include/crm_b200.h (member order and types must match exactly) ----
   type, bind(C) :: crm_dims_t
@@ -79,6 +89,31 @@ module crm_module
       type(crm_state_t),  intent(inout) :: cstate
       type(crm_rad_t),    intent(inout) :: crad
       type(crm_output_t), intent(inout) :: cout
+    end function
+    integer(c_int) function crm_b200_resident_put(handle, lchnk, dims, cstate, crad) bind(C, name="crm_b200_resident_put")
+      import :: c_int, c_ptr, crm_dims_t, crm_state_t, crm_rad_t
+      type(c_ptr), value :: handle
+      integer(c_int), value :: lchnk
+      type(crm_dims_t),   intent(in) :: dims
+      type(crm_state_t),  intent(in) :: cstate
+      type(crm_rad_t),    intent(in) :: crad
+    end function
+    integer(c_int) function crm_b200_resident_run(handle, lchnk, dims, cin, crad, cout) bind(C, name="crm_b200_resident_run")
+      import :: c_int, c_ptr, crm_dims_t, crm_input_t, crm_rad_t, crm_output_t
+      type(c_ptr), value :: handle
+      integer(c_int), value :: lchnk
+      type(crm_dims_t),   intent(in)    :: dims
+      type(crm_input_t),  intent(in)    :: cin
+      type(crm_rad_t),    intent(inout) :: crad
+      type(crm_output_t), intent(inout) :: cout
+    end function
+    integer(c_int) function crm_b200_resident_get(handle, lchnk, dims, cstate, crad) bind(C, name="crm_b200_resident_get")
+      import :: c_int, c_ptr, crm_dims_t, crm_state_t, crm_rad_t
+      type(c_ptr), value :: handle
+      integer(c_int), value :: lchnk
+      type(crm_dims_t),   intent(in)    :: dims
+      type(crm_state_t),  intent(inout) :: cstate
+      type(crm_rad_t),    intent(inout) :: crad
     end function
     function crm_b200_last_error(handle) bind(C, name="crm_b200_last_error") result(msg)
       import :: c_ptr
@@ -244,13 +279,64 @@ contains
     co%dep_a = c_loc(crm_output%dep_a);  co%con_a = c_loc(crm_output%con_a)
 #endif
 
-    rc = crm_b200_run(handle, d, ci, cs, cr, co)
+    if (crm_b200_resident) then
+      if (.not. any(seen_chunk(1:nseen) == lchnk)) then        ! first crm() call of this chunk: upload the pbuf copy once
+        if (nseen >= max_chunks) call endrun('crm (B200): more than max_chunks resident chunks')
+        rc = crm_b200_resident_put(handle, int(lchnk, c_int), d, cs, cr)
+        if (rc /= 0) call endrun('crm_b200_resident_put: '//trim(c_message(handle)))
+        nseen = nseen + 1
+        seen_chunk(nseen) = lchnk
+      end if
+      rc = crm_b200_resident_run(handle, int(lchnk, c_int), d, ci, cr, co)
+    else
+      rc = crm_b200_run(handle, d, ci, cs, cr, co)
+    end if
     if (rc /= 0) then                               ! replaces task_abort()/endrun of kurant.F90:66-75, damping.F90:39-42
       msg = c_message(handle)
       call endrun('crm (B200): '//trim(msg))
     end if
     deallocate(lat_deg, lon_deg, gcol)
   end subroutine crm
+
+  ! Resident mode: refresh the host (pbuf) copy of crm_state of chunk lchnk before it is written to a restart file or to history.
+  subroutine crm_b200_sync_host(lchnk, ncrms, crm_state)
+    use ppgrid,          only: pver
+    use crmdims,         only: crm_nx, crm_ny, crm_nz, crm_nx_rad, crm_ny_rad, crm_dx, crm_dt
+    use cam_abortutils,  only: endrun
+    integer, intent(in) :: lchnk, ncrms
+    type(crm_state_type), target, intent(inout) :: crm_state
+    type(crm_dims_t)  :: d
+    type(crm_state_t) :: cs
+    type(crm_rad_t)   :: cr
+    integer :: rc
+    if (.not. crm_b200_resident .or. .not. c_associated(handle)) return
+    if (.not. any(seen_chunk(1:nseen) == lchnk)) return
+    d%ncrms = ncrms;  d%ld = size(crm_state%u_wind, 1);  d%plev = pver
+    d%nx = crm_nx;  d%ny = crm_ny;  d%nzm = crm_nz;  d%nx_rad = crm_nx_rad;  d%ny_rad = crm_ny_rad
+    d%yes3d = merge(1, 0, crm_ny > 1);  d%dx = crm_dx;  d%dt = crm_dt;  d%dt_gl = crm_dt
+    d%igstep = 2;  d%use_crm_accel = 0;  d%crm_accel_uv = 0;  d%crm_accel_factor = 0;  d%twiddle_f32 = 1;  d%esmt = 0
+#ifdef m2005
+    d%micro = 1
+#else
+    d%micro = 0
+#endif
+    cs%u_wind = c_loc(crm_state%u_wind);  cs%v_wind = c_loc(crm_state%v_wind);  cs%w_wind = c_loc(crm_state%w_wind)
+    cs%temperature = c_loc(crm_state%temperature);  cs%qt = c_loc(crm_state%qt)
+    cs%nc = c_null_ptr; cs%qr = c_null_ptr; cs%nr = c_null_ptr; cs%qi = c_null_ptr; cs%ni = c_null_ptr
+    cs%qs = c_null_ptr; cs%ns = c_null_ptr; cs%qg = c_null_ptr; cs%ng = c_null_ptr; cs%qc = c_null_ptr
+    cs%qp = c_null_ptr; cs%qn = c_null_ptr
+#ifdef m2005
+    cs%nc = c_loc(crm_state%nc);  cs%qr = c_loc(crm_state%qr);  cs%nr = c_loc(crm_state%nr);  cs%qi = c_loc(crm_state%qi)
+    cs%ni = c_loc(crm_state%ni);  cs%qs = c_loc(crm_state%qs);  cs%ns = c_loc(crm_state%ns);  cs%qg = c_loc(crm_state%qg)
+    cs%ng = c_loc(crm_state%ng);  cs%qc = c_loc(crm_state%qc)
+#else
+    cs%qp = c_loc(crm_state%qp);  cs%qn = c_loc(crm_state%qn)
+#endif
+    cr%qrad = c_null_ptr; cr%temperature = c_null_ptr; cr%qv = c_null_ptr; cr%qc = c_null_ptr; cr%qi = c_null_ptr; cr%cld = c_null_ptr
+    cr%nc = c_null_ptr; cr%ni = c_null_ptr; cr%qs = c_null_ptr; cr%ns = c_null_ptr      ! crm_rad is copied out by every resident run
+    rc = crm_b200_resident_get(handle, int(lchnk, c_int), d, cs, cr)
+    if (rc /= 0) call endrun('crm_b200_resident_get: '//trim(c_message(handle)))
+  end subroutine crm_b200_sync_host
 
   function c_message(h) result(s)
     type(c_ptr), intent(in) :: h

@@ -100,3 +100,82 @@ def phase_errors(dims, inp, st, rad, stop, lib_path=None):
     finally:
         del os.environ["CRM_DEBUG_STOP"]
     return res
+
+
+def resident_case(dims, lib_path=None, device=0, ncalls=2):
+    """crm_b200_resident_* (SURVEY 8(f) items 1, 3): `ncalls` chained crm() calls on a chunk whose crm_state / crm_rad stay on the
+    device must give exactly what the same calls give with the state crossing the host boundary every time, and the oracle's
+    result within the parity tolerance; the CRM-level history fields must be the outfld expressions of crm_physics.F90:1214-1231.
+    Returns (host-path results, resident results, oracle results, history dict, handle statistics)."""
+    dims, inp, st, rad = make_case(dims, 90)
+    st_o, rad_o, st_h, rad_h = st.copy(), rad.copy(), st.copy(), rad.copy()
+    for _ in range(ncalls):
+        out_o, stats_o = ob.run(dims, inp, st_o, rad_o)
+    h = libmod.CrmHandle(dims, device=device, lib_path=lib_path)
+    for _ in range(ncalls):
+        out_h = h.run(dims, inp, st_h, rad_h)
+    lchnk = 7
+    assert h.resident_bytes() == 0
+    h.resident_put(lchnk, dims, st, rad)
+    assert h.resident_bytes() > 0
+    rad_r = rad.copy()
+    for call in range(ncalls):
+        # qrad travels with the first call only (later calls use the resident copy); results are copied out every call
+        rr = rad_r if call == 0 else _rad_without_qrad(rad_r)
+        out_r = h.resident_run(lchnk, dims, inp, rr)
+    stats_r = h.stats()
+    hist = {n: h.history_field(lchnk, dims, n) for n in ("CRM_U", "CRM_W", "CRM_T", "CRM_QV", "CRM_QC", "CRM_QI", "CRM_QPC", "CRM_QPI",
+                                                         "CRM_TK", "CRM_TKH")}
+    st_r = pkg.crm_state_type().initialize(dims)
+    rad_g = pkg.crm_rad_type().initialize(dims)
+    h.resident_get(lchnk, dims, st_r, rad_g)
+    # a second chunk on the same handle: its crm_output history is refused until it has run
+    h.resident_put(lchnk + 1, dims, st, rad)
+    refused = False
+    try:
+        h.history_field(lchnk + 1, dims, "CRM_QC")
+    except libmod.CrmB200Error as e:
+        refused = "54" in str(e)
+    assert refused, "history of a chunk that did not run last must be refused"
+    assert h.history_field(lchnk + 1, dims, "CRM_T").shape == st.temperature.shape        # state fields are always available
+    h.resident_drop(lchnk + 1)
+    assert h.resident_field(lchnk + 1, "qt") is None and h.resident_field(lchnk, "qrad")
+    h.resident_drop(-1)
+    assert h.resident_bytes() == 0
+    h.close()
+    return (st_h, rad_h, out_h), (st_r, rad_r, rad_g, out_r), (st_o, rad_o, out_o, stats_o), hist, stats_r
+
+
+def _rad_without_qrad(rad):
+    o = pkg.crm_rad_type()
+    for n in rad.names():
+        if n != "qrad":
+            setattr(o, n, getattr(rad, n))
+    return o
+
+
+def check_resident(dims, host, res, orc, hist, tol):
+    st_h, rad_h, out_h = host
+    st_r, rad_r, rad_g, out_r = res
+    st_o, rad_o, out_o, _ = orc
+    n = dims.ncrms
+    for name in st_h.names():                      # identical code path, identical inputs: bit-identical
+        assert np.array_equal(getattr(st_h, name)[:n], getattr(st_r, name)[:n]), name
+    for name in rad_h.names():
+        if name == "qrad":
+            continue
+        assert np.array_equal(getattr(rad_h, name)[:n], getattr(rad_r, name)[:n]), name
+        assert np.array_equal(getattr(rad_h, name)[:n], getattr(rad_g, name)[:n]), name
+    assert np.array_equal(rad_g.qrad[:n], rad_h.qrad[:n])
+    for name, _ in pkg.abi.OUTPUT_FIELDS:
+        assert np.array_equal(getattr(out_h, name)[:n], getattr(out_r, name)[:n]), name
+    bad = compare_all(dims, (st_o, rad_o, out_o, None), (st_r, rad_g, out_r, None), tol)
+    assert not bad, bad
+    # history stream
+    assert np.array_equal(hist["CRM_U"][:n], st_r.u_wind[:n]) and np.array_equal(hist["CRM_W"][:n], st_r.w_wind[:n])
+    assert np.array_equal(hist["CRM_T"][:n], st_r.temperature[:n])
+    for hn, on in (("CRM_QC", "qcl"), ("CRM_QI", "qci"), ("CRM_QPC", "qpl"), ("CRM_QPI", "qpi"), ("CRM_TK", "tk"), ("CRM_TKH", "tkh")):
+        assert np.array_equal(hist[hn][:n], getattr(out_r, on)[:n]), hn
+    qv = (st_r.qt - out_r.qcl) - out_r.qci if dims.micro == 0 else st_r.qt - out_r.qcl
+    assert np.array_equal(hist["CRM_QV"][:n], qv[:n])
+    assert float(hist["CRM_QV"][:n].min()) > 0.0

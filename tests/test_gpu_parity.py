@@ -546,3 +546,31 @@ def test_esmt_needs_its_arrays():
     with pytest.raises(cm.libmod.CrmB200Error, match="esmt = 1 needs"):
         h.run(dims, inp, st, rad)
     h.close()
+
+
+@pytest.mark.gpu
+def test_resident_state_and_history_stream():
+    """crm_state / crm_rad resident in HBM keyed by the physics chunk (crm_b200_resident_*) and the
+    CRM-level history fields (crm_physics.F90:1214-1231).  Two chained crm() calls on the resident chunk are bit-identical to the
+    same calls with the state crossing the host boundary, and within 1e-9 of two oracle calls; the resident path moves no
+    crm_state bytes (d2h of the second call = crm_output + crm_rad only)."""
+    dims = cm.small_dims(ncrms=37, nx=32, nsteps=4, ld=40)
+    host, res, orc, hist, stats = cm.resident_case(dims)
+    cm.check_resident(dims, host, res, orc, hist, 1e-9)
+    n3 = dims.ncrms * dims.nx * dims.ny * dims.nzm * 8
+    nrad = dims.ncrms * dims.nx_rad * dims.ny_rad * dims.nzm * 8
+    # 6 three-dimensional crm_output members + 5 crm_rad results + profiles; the 7 crm_state members would add 7 * n3
+    assert 6 * n3 + 5 * nrad < stats["d2h_bytes"] < 6 * n3 + 5 * nrad + n3
+    assert stats["h2d_bytes"] < n3                 # crm_input profiles only (qrad stayed resident on the second call)
+
+
+@pytest.mark.gpu
+def test_resident_m2005_and_3d():
+    """The resident path with the m2005 members of crm_state / crm_rad, and for a 3-D CRM (v_wind round trip)."""
+    d2 = cm.small_dims(ncrms=9, nx=16, nzm=28, plev=30, nsteps=2, micro=1)
+    host, res, orc, hist, _ = cm.resident_case(d2)
+    cm.check_resident(d2, host, res, orc, hist, 1e-8)
+    d3 = cm.pkg.CrmDims(ncrms=5, nx=8, ny=8, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=40.0, igstep=3)
+    host, res, orc, hist, _ = cm.resident_case(d3)
+    cm.check_resident(d3, host, res, orc, hist, 1e-9)
+    assert float(np.abs(res[0].v_wind).max()) > 0.0

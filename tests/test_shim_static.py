@@ -76,3 +76,43 @@ def test_every_struct_member_is_assigned_before_the_run_call():
     for var, tname in (("d", "crm_dims_t"), ("ci", "crm_input_t"), ("cs", "crm_state_t"), ("cr", "crm_rad_t"), ("co", "crm_output_t")):
         for member, _ in f[tname]:
             assert re.search(r"\b%s%%%s\s*=" % (var, member), body), (var, member)
+
+
+def _c_prototypes():
+    src = re.sub(r"/\*.*?\*/", "", open(HDR).read(), flags=re.S)
+    out = {}
+    for name, args in re.findall(r"\b(crm_b200_\w+)\s*\(([^)]*)\)\s*;", src):
+        args = [a.strip() for a in args.split(",") if a.strip() and a.strip() != "void"]
+        out[name] = args
+    return out
+
+
+def test_every_bind_c_interface_matches_a_header_prototype():
+    """Each interface block of the shim names a function the header declares, with the same number of arguments, `value` on
+    exactly the by-value C parameters (int lchnk / int device / void *handle) and references for the struct pointers."""
+    src = open(SHIM).read()
+    protos = _c_prototypes()
+    blocks = re.findall(r"function\s+(\w+)\s*\(([^)]*)\)\s*bind\(C,\s*name=\"(\w+)\"\)(.*?)end function", src, flags=re.S | re.I)
+    assert len(blocks) >= 6
+    for fname, fargs, cname, body in blocks:
+        assert fname == cname and cname in protos, cname
+        fargs = [a.strip() for a in fargs.split(",") if a.strip()]
+        assert len(fargs) == len(protos[cname]), (cname, fargs, protos[cname])
+        for fa, ca in zip(fargs, protos[cname]):
+            decl = [ln for ln in body.splitlines() if re.search(r"::\s*%s\b" % fa, ln)]
+            assert decl, (cname, fa)
+            by_value = "value" in decl[0].split("::")[0].lower()
+            c_by_value = ("*" not in ca) or (ca.startswith("void *") and not ca.startswith("void **"))
+            assert by_value == c_by_value, (cname, fa, ca)
+
+
+def test_sync_host_assigns_every_member_and_uses_targets():
+    src = open(SHIM).read()
+    body = src[src.index("subroutine crm_b200_sync_host("):src.index("end subroutine crm_b200_sync_host")]
+    f = _f_types()
+    for var, tname in (("d", "crm_dims_t"), ("cs", "crm_state_t"), ("cr", "crm_rad_t")):
+        for member, _ in f[tname]:
+            assert re.search(r"\b%s%%%s\s*=" % (var, member), body), (var, member)
+    used = {m.split("%")[0] for m in re.findall(r"c_loc\(\s*([\w%]+)\s*\)", body)}
+    assert used == {"crm_state"}
+    assert re.search(r"type\(crm_state_type\),\s*target", body)
