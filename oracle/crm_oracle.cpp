@@ -908,6 +908,85 @@ extern "C" int crm_oracle_test_precip_proc(int n, double dtn, const double *tabs
   return 0;
 }
 
+// Momentum tendencies of one 2-D CRM from zero tendencies (test hook for tests/test_second_restatement.py): which = 1 advect_mom
+// (advect2_mom_xy.F90 + advect2_mom_z.F90), 2 sgs_mom (diffuse_mom2D.F90), 3 buoyancy (buoyancy.F90; u/tk unused, the six thermodynamic
+// fields and four reference profiles in `thermo`).  u, tk (nx, nzm), w (nx, nzm+1) in Fortran order; dudt (nx, nzm), dwdt (nx, nzm+1),
+// prof (nzm+1) = uwle (which = 1) or uwsb (which = 2) out.
+extern "C" int crm_oracle_test_mom2d(int which, int nx, int nzm, double dx, double dz, const double *adz, const double *adzw, const double *rho,
+                                     const double *rhow, const double *u, const double *w, const double *tk, const double *thermo, double *dudt,
+                                     double *dwdt, double *prof) {
+  Geo g; g.nx = nx; g.ny = 1; g.nzm = nzm; g.nz = nzm + 1; g.plev = nzm; g.YES3D = 0; g.RUN3D = false; g.nx_rad = 1; g.ny_rad = 1; g.dx = g.dy = dx;
+  Crm c; alloc_crm(g, c);
+  Step s; s.na = 1; s.nb = 2; s.nc = 3;
+  c.dz = dz;
+  for (int k = 1; k <= nzm + 1; k++) { c.adzw(k) = adzw[k - 1]; c.rhow(k) = rhow[k - 1]; if (k <= nzm) { c.adz(k) = adz[k - 1]; c.rho(k) = rho[k - 1]; } }
+  for (int k = 1; k <= nzm; k++) {
+    double a2 = (c.adz(k) * c.dz) * (c.adz(k) * c.dz);
+    c.grdf_x(k) = dmin(16., dx * dx / a2); c.grdf_y(k) = c.grdf_x(k); c.grdf_z(k) = 1.;
+  }
+  const size_t n2 = (size_t)nx * nzm;
+  for (int k = 1; k <= nzm + 1; k++)
+    for (int i = 1; i <= nx; i++) {
+      const size_t o = (size_t)(i - 1) + (size_t)nx * (k - 1);
+      c.w(i, 1, k) = w[o];
+      if (k <= nzm) {
+        c.u(i, 1, k) = u[o]; c.tk(i, 1, k) = tk[o];
+        if (which == 3) {
+          c.tabs(i, 1, k) = thermo[o]; c.qv(i, 1, k) = thermo[n2 + o]; c.qcl(i, 1, k) = thermo[2 * n2 + o]; c.qci(i, 1, k) = thermo[3 * n2 + o];
+          c.qpl(i, 1, k) = thermo[4 * n2 + o]; c.qpi(i, 1, k) = thermo[5 * n2 + o];
+        }
+      }
+    }
+  if (which == 3)
+    for (int k = 1; k <= nzm; k++) {
+      const double *pr = thermo + 6 * n2;
+      c.tabs0(k) = pr[k - 1]; c.qv0(k) = pr[nzm + k - 1]; c.qn0(k) = pr[2 * nzm + k - 1]; c.qp0(k) = pr[3 * nzm + k - 1]; c.bet(k) = pr[4 * nzm + k - 1];
+    }
+  boundaries(g, c, 0);
+  boundaries(g, c, 4);
+  if (which == 1) advect_mom(g, c, s);
+  else if (which == 2) sgs_mom(g, c, s);
+  else buoyancy(g, c, s);
+  for (int k = 1; k <= nzm + 1; k++) {
+    if (which == 1) prof[k - 1] = c.uwle(k);
+    else if (which == 2) prof[k - 1] = (k <= nzm) ? c.uwsb(k) : 0.;
+    for (int i = 1; i <= nx; i++) {
+      const size_t o = (size_t)(i - 1) + (size_t)nx * (k - 1);
+      dwdt[o] = c.dwdt[s.na](i, 1, k);
+      if (k <= nzm) dudt[o] = c.dudt[s.na](i, 1, k);
+    }
+  }
+  return 0;
+}
+
+// diffuse_scalar2D (SGS_TKE/diffuse_scalar2D.F90) of one 2-D CRM: f in/out (nx, nzm), tkh (nx, nzm), fluxb / fluxt (nx); flux (nzm+1) out.
+extern "C" int crm_oracle_test_diffuse_scalar2d(int nx, int nzm, double dx, double dz, double dtn, const double *adz, const double *adzw, const double *rho,
+                                                const double *rhow, const double *tkh, const double *fluxb, const double *fluxt, double *f, double *flux) {
+  Geo g; g.nx = nx; g.ny = 1; g.nzm = nzm; g.nz = nzm + 1; g.plev = nzm; g.YES3D = 0; g.RUN3D = false; g.nx_rad = 1; g.ny_rad = 1; g.dx = g.dy = dx;
+  Crm c; alloc_crm(g, c);
+  Step s; s.dtn = dtn; s.dt = dtn;
+  c.dz = dz;
+  for (int k = 1; k <= nzm + 1; k++) { c.adzw(k) = adzw[k - 1]; c.rhow(k) = rhow[k - 1]; if (k <= nzm) { c.adz(k) = adz[k - 1]; c.rho(k) = rho[k - 1]; } }
+  for (int k = 1; k <= nzm; k++) {
+    double a2 = (c.adz(k) * c.dz) * (c.adz(k) * c.dz);
+    c.grdf_x(k) = dmin(16., dx * dx / a2); c.grdf_y(k) = c.grdf_x(k); c.grdf_z(k) = 1.;
+  }
+  for (int k = 1; k <= nzm; k++)
+    for (int i = 1; i <= nx; i++) {
+      const size_t o = (size_t)(i - 1) + (size_t)nx * (k - 1);
+      c.t(i, 1, k) = f[o]; c.tkh(i, 1, k) = tkh[o];
+    }
+  boundaries(g, c, 3);
+  boundaries(g, c, 4);
+  std::vector<double> fb(fluxb, fluxb + nx), ft(fluxt, fluxt + nx);
+  P1 fdiff = c.tdiff, fl = c.twsb;
+  diffuse_scalar(g, c, s, c.t, fb, ft, fdiff, fl);
+  for (int k = 1; k <= nzm + 1; k++) flux[k - 1] = (k <= nzm) ? fl(k) : 0.;
+  for (int k = 1; k <= nzm; k++)
+    for (int i = 1; i <= nx; i++) f[(size_t)(i - 1) + (size_t)nx * (k - 1)] = c.t(i, 1, k);
+  return 0;
+}
+
 // sgs_proc = shear_prod2D + tke_full (SGS_TKE/tke_full.F90:11-317, dosmagor) of one 2-D CRM: fields (nx, nzm[+1 for w]) in Fortran
 // order, profiles adz, bet, u0 (nzm), adzw, presi (nzm+1); tk in/out, tkh, tke out.
 extern "C" int crm_oracle_test_sgs(int nx, int nzm, double dx, double dt, double dz, const double *adz, const double *adzw, const double *bet,

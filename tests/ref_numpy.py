@@ -1,4 +1,4 @@
-"""SECOND, independent restatement (numpy / plain Python) of five reference routines, written directly from the Fortran sources
+"""SECOND, independent restatement (numpy / plain Python) of reference routines, written directly from the Fortran sources
 under /root/reference/components/cam/src/physics/crm (not from oracle/*.cpp), with another program structure than the C++
 oracle (periodic index arithmetic instead of halo arrays, cell-wise functions instead of field loops).  TEST INFRASTRUCTURE:
 tests/test_second_restatement.py checks the C++ oracle against it; agreement of two independent transcriptions is what stands in
@@ -12,6 +12,10 @@ profiles/r02_fortran_probe_gpu_box.txt).
   MICRO_SAM1MOM/microphysics.F90:453-830  term_vel_qp, precip_fall_column
   ADV_MPDATA/advect_scalar2D.F90:93-234   advect_scalar2d
   SGS_TKE/shear_prod2D.F90:20-94 + tke_full.F90:103-310   sgs_2d
+  advect2_mom_xy.F90:74-96 + advect2_mom_z.F90:26-123     advect_mom_2d
+  SGS_TKE/diffuse_mom2D.F90:38-156        diffuse_mom_2d
+  SGS_TKE/diffuse_scalar2D.F90:81-139     diffuse_scalar_2d
+  buoyancy.F90:16-36                      buoyancy_2d
 Unsuffixed literals are REAL(4) in the reference build (no -r8): f4() reproduces them; literal-only sub-expressions are evaluated in
 float32.
 """
@@ -513,3 +517,166 @@ def esmt_pgf(u_s, w, zi, z, rho, dx):
     tend = -pgf * rho[None, :]
     tend[:, 0] = 0.
     return tend
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Momentum tendencies and SGS scalar diffusion of one 2-D CRM (second restatement, round 2 addition).  Arrays (nx, nzm) with w
+# (nx, nzm+1), periodic in x through np.roll; Fortran level k (1-based) is column k-1.  Flux arrays are built whole-field and
+# differenced, where the oracle loops cell by cell over halo arrays.
+# ---------------------------------------------------------------------------------------------------------------------------
+def advect_mom_2d(u, w, dx, dz, rho, rhow, adz, adzw):
+    """advect2_mom_xy.F90:74-96 (2-D branch, v == 0) + advect2_mom_z.F90:26-123.  Returns (dudt, dwdt, uwle): the increments to
+    dudt(:,:,:,na) (nx, nzm), dwdt (nx, nzm+1) and the resolved momentum flux profile uwle (nzm+1)."""
+    nx, nzm = u.shape
+    nz = nzm + 1
+    dudt = np.zeros((nx, nzm)); dwdt = np.zeros((nx, nz))
+    dx25 = 0.25 / dx
+    # ---- x: fu at the u-point pair (i-1, i): fu1 uses (u(i) + u(i-1)), fu2 (u(i+1) + u(i))
+    um, up = _r(u, -1), _r(u, 1)
+    fu1 = dx25 * (u + um) * (um + u)
+    fu2 = dx25 * (up + u) * (u + up)
+    dudt = dudt - (fu2 - fu1)
+    ra = rho * adz                                     # rho(k)*adz(k)
+    for k in range(nzm):                               # Fortran k = k+1, kc = k+2 -> w index k+1; kcu = min(kc, nzm)
+        kcu = min(k + 1, nzm - 1)
+        irho = 1. / (rhow[k + 1] * adzw[k + 1])
+        wk = w[:, k + 1]
+        f1 = dx25 * (u[:, k] * rho[k] * adz[k] + u[:, kcu] * rho[kcu] * adz[kcu]) * (np.roll(wk, 1) + wk)
+        ukp, ukcp = np.roll(u[:, k], -1), np.roll(u[:, kcu], -1)
+        f2 = dx25 * (ukp * rho[k] * adz[k] + ukcp * rho[kcu] * adz[kcu]) * (wk + np.roll(wk, -1))
+        dwdt[:, k + 1] = dwdt[:, k + 1] - irho * (f2 - f1)
+    # ---- z
+    dz25 = 1. / (4. * dz)
+    fuz = np.zeros((nx, nz)); fwz = np.zeros((nx, nzm))
+    uwle = np.zeros(nz)
+    for k in range(1, nzm):                            # Fortran k = 2..nzm
+        rhoi = dz25 * rhow[k]
+        www = rhoi * (w[:, k] + np.roll(w[:, k], 1))
+        fuz[:, k] = www * (u[:, k] + u[:, k - 1])
+        s = 0.
+        for i in range(nx):
+            s = s + fuz[i, k]
+        uwle[k] = s
+    for k in range(nzm):
+        rhoi = 1. / (rho[k] * adz[k])
+        dudt[:, k] = dudt[:, k] - (fuz[:, k + 1] - fuz[:, k]) * rhoi
+        fwz[:, k] = dz25 * (w[:, k + 1] * rhow[k + 1] + w[:, k] * rhow[k]) * (w[:, k + 1] + w[:, k])
+    for k in range(1, nzm):
+        rhoi = 1. / (rhow[k] * adzw[k])
+        dwdt[:, k] = dwdt[:, k] - (fwz[:, k] - fwz[:, k - 1]) * rhoi
+    return dudt, dwdt, uwle
+
+
+def diffuse_mom_2d(u, w, tk, dx, dz, rho, rhow, adz, adzw, grdf_x, grdf_z):
+    """SGS_TKE/diffuse_mom2D.F90:38-156 with zero surface / top momentum fluxes (fluxbu = fluxtu = 0: the reference's defaults) and
+    v == 0.  Returns (dudt, dwdt, uwsb)."""
+    nx, nzm = u.shape
+    nz = nzm + 1
+    dudt = np.zeros((nx, nzm)); dwdt = np.zeros((nx, nz))
+    rdx2 = 1. / dx / dx
+    rdx25 = 0.25 * rdx2
+    up = _r(u, 1)
+    tkp = _r(tk, 1)
+    # horizontal fluxes at the right face of column i (the Fortran's i = 0 column is the periodic image of i = nx)
+    fu = np.zeros((nx, nzm)); fw = np.zeros((nx, nzm))
+    for k in range(nzm):
+        kcu = min(k + 1, nzm - 1)
+        dxz = dx / (dz * adzw[k + 1])
+        rdx21 = rdx2 * grdf_x[k]
+        rdx251 = rdx25 * grdf_x[k]
+        tkx = rdx21 * tk[:, k]
+        fu[:, k] = -2. * tkx * (up[:, k] - u[:, k])
+        tkx = rdx251 * (tk[:, k] + tkp[:, k] + tk[:, kcu] + tkp[:, kcu])
+        wk = w[:, k + 1]
+        fw[:, k] = -tkx * (np.roll(wk, -1) - wk + (up[:, kcu] - up[:, k]) * dxz)
+    dudt = dudt - (fu - np.roll(fu, 1, axis=0))
+    dwdt[:, 1:] = dwdt[:, 1:] - (fw - np.roll(fw, 1, axis=0))
+    # vertical fluxes
+    fuz = np.zeros((nx, nz)); fwz = np.zeros((nx, nz + 1))   # fwz index: Fortran fw(:,kc) with kc up to nz
+    uwsb = np.zeros(nz)
+    rdz = 1. / dz
+    dzx = dz / dx
+    for k in range(nzm - 1):
+        kc = k + 1
+        rdz2 = rdz * rdz * grdf_z[k]
+        rdz25 = 0.25 * rdz2
+        iadz = 1. / adz[k]
+        iadzw = 1. / adzw[kc]
+        tkz = rdz2 * tk[:, k]
+        fwz[:, kc] = -2. * tkz * (w[:, kc] - w[:, k]) * rho[k] * iadz
+        tkz = rdz25 * (tk[:, k] + np.roll(tk[:, k], 1) + tk[:, kc] + np.roll(tk[:, kc], 1))
+        fuz[:, kc] = -tkz * ((u[:, kc] - u[:, k]) * iadzw + (w[:, kc] - np.roll(w[:, kc], 1)) * dzx) * rhow[kc]
+        s = 0.
+        for i in range(nx):
+            s = s + fuz[i, kc]
+        uwsb[kc] = s
+    rdz2 = rdz * rdz * grdf_z[nzm - 2]
+    tkz = rdz2 * grdf_z[nzm - 1] * tk[:, nzm - 1]
+    fwz[:, nzm] = -2. * tkz * (w[:, nzm] - w[:, nzm - 1]) / adz[nzm - 1] * rho[nzm - 1]
+    # fu(:,1) = fluxbu*rdz*rhow(1) = 0, fu(:,nz) = fluxtu*rdz*rhow(nz) = 0
+    for k in range(nzm):
+        rhoi = 1. / (rho[k] * adz[k])
+        dudt[:, k] = dudt[:, k] - (fuz[:, k + 1] - fuz[:, k]) * rhoi
+    for k in range(1, nzm):
+        rhoi = 1. / (rhow[k] * adzw[k])
+        dwdt[:, k] = dwdt[:, k] - (fwz[:, k + 1] - fwz[:, k]) * rhoi
+    return dudt, dwdt, uwsb
+
+
+def diffuse_scalar_2d(f, tkh, dx, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_z, fluxb, fluxt):
+    """SGS_TKE/diffuse_scalar2D.F90:81-139: returns (f_new, flux(nzm+1)) with flux(k) the slab sum of the SGS flux through the
+    lower face of level k (flux(1) from the surface flux)."""
+    nx, nzm = f.shape
+    nz = nzm + 1
+    rdx2 = 1. / (dx * dx)
+    dfdt = np.zeros((nx, nzm))
+    for k in range(nzm):
+        rdx5 = 0.5 * rdx2 * grdf_x[k]
+        tkx = rdx5 * (tkh[:, k] + np.roll(tkh[:, k], -1))
+        flx = -tkx * (np.roll(f[:, k], -1) - f[:, k])
+        dfdt[:, k] = dfdt[:, k] - (flx - np.roll(flx, 1))
+    flxz = np.zeros((nx, nz))                           # flxz[:, k] = Fortran flx(:,k) for k = 0..nzm
+    flux = np.zeros(nz)
+    for k in range(nzm - 1):                            # Fortran k = k+1, kc = k+2
+        kc = k + 1
+        rhoi = rhow[kc] / adzw[kc]
+        rdz2 = 1. / (dz * dz)
+        rdz5 = 0.5 * rdz2 * grdf_z[k]
+        tkz = rdz5 * (tkh[:, k] + tkh[:, kc])
+        flxz[:, k + 1] = -tkz * (f[:, kc] - f[:, k]) * rhoi
+        s = 0.
+        for i in range(nx):
+            s = s + flxz[i, k + 1]
+        flux[kc] = s
+    tmp = 1. / adzw[nz - 1]
+    rdz = 1. / dz
+    flxz[:, 0] = fluxb * rdz * rhow[0]
+    flxz[:, nzm] = fluxt * rdz * tmp * rhow[nz - 1]
+    s = 0.
+    for i in range(nx):
+        s = s + flxz[i, 0]
+    flux[0] = s
+    out = f.copy()
+    for k in range(nzm):
+        rhoi = 1. / (adz[k] * rho[k])
+        d = dtn * (dfdt[:, k] - (flxz[:, k + 1] - flxz[:, k]) * rhoi)
+        out[:, k] = f[:, k] + d
+    return out, flux
+
+
+def buoyancy_2d(tabs, qv, qcl, qci, qpl, qpi, tabs0, qv0, qn0, qp0, bet, adz):
+    """buoyancy.F90:16-36: increment of dwdt(:,:,k,na) on w-levels 2..nzm; returns (nx, nzm+1)."""
+    nx, nzm = tabs.shape
+    dwdt = np.zeros((nx, nzm + 1))
+
+    def term(k):
+        return bet[k] * 1.0, (tabs0[k] * (epsv * (qv[:, k] - qv0[k]) - (qcl[:, k] + qci[:, k] - qn0[k] + qpl[:, k] + qpi[:, k] - qp0[k]))
+                              + (tabs[:, k] - tabs0[k]) * (1. + epsv * qv0[k] - qn0[k] - qp0[k]))
+    for k in range(1, nzm):
+        kb = k - 1
+        betu = adz[kb] / (adz[k] + adz[kb])
+        betd = adz[k] / (adz[k] + adz[kb])
+        bk, tk_ = term(k)
+        bb, tb = term(kb)
+        dwdt[:, k] = dwdt[:, k] + bet[k] * betu * tk_ + bet[kb] * betd * tb
+    return dwdt

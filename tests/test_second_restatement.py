@@ -1,5 +1,6 @@
 """The C++ oracle against the second, independent numpy restatement of tests/ref_numpy.py (written from the Fortran, not from the
-oracle): cloud, precip_proc (+ precip_init, sat.F90), advect_scalar2D, precip_fall, shear_prod2D + tke_full.  Two independent
+oracle): cloud, precip_proc (+ precip_init, sat.F90), advect_scalar2D, precip_fall, shear_prod2D + tke_full, advect2_mom_xy/z,
+diffuse_mom2D, diffuse_scalar2D, buoyancy.  Two independent
 transcriptions agreeing to round-off is the strongest pin available without a Fortran compiler."""
 import ctypes as C
 
@@ -133,3 +134,72 @@ def test_esmt_pressure_gradient_force_against_second_restatement():
         ref = rn.esmt_pgf(u_s, w, zi, z, rho, dx)
         assert np.abs(tend[:, 1:]).max() > 1e-4 and np.all(tend[:, 0] == 0.)
         assert _close(ref, tend, 2e-12), (nx, np.abs(ref - tend).max() / np.abs(tend).max())
+
+
+def _grid_2d(rng, nx=16, nzm=20, dx=1000., dz=120.):
+    adz = np.linspace(0.8, 2.2, nzm); adzw = np.concatenate([[1.], 0.5 * (adz[1:] + adz[:-1]), [adz[-1]]])
+    z = np.cumsum(adz) * dz
+    rho = 1.16 * np.exp(-z / 8500.); rhow = np.concatenate([[1.2], 0.5 * (rho[1:] + rho[:-1]), [2 * rho[-1] - 0.5 * (rho[-1] + rho[-2])]])
+    grdf_x = np.minimum(16., dx * dx / ((adz * dz) * (adz * dz))); grdf_z = np.ones(nzm)
+    return nx, nzm, dx, dz, adz, adzw, z, rho, rhow, grdf_x, grdf_z
+
+
+def test_momentum_advection_and_diffusion_against_second_restatement():
+    """advect2_mom_xy + advect2_mom_z (2-D branch), diffuse_mom2D: tendencies from zero, and the uwle / uwsb profiles."""
+    rng = np.random.default_rng(31)
+    nx, nzm, dx, dz, adz, adzw, z, rho, rhow, grdf_x, grdf_z = _grid_2d(rng)
+    u = 6. + 3. * rng.standard_normal((nx, nzm)); w = np.zeros((nx, nzm + 1)); w[:, 1:nzm] = rng.standard_normal((nx, nzm - 1))
+    tk = rng.uniform(0., 30., (nx, nzm)); tk[:, nzm - 1] = rng.uniform(0., 5., nx)
+    A = np.asfortranarray
+    for which, fn in ((1, lambda: rn.advect_mom_2d(u, w, dx, dz, rho, rhow, adz, adzw)),
+                      (2, lambda: rn.diffuse_mom_2d(u, w, tk, dx, dz, rho, rhow, adz, adzw, grdf_x, grdf_z))):
+        du, dw, pr = A(np.zeros((nx, nzm))), A(np.zeros((nx, nzm + 1))), np.zeros(nzm + 1)
+        rc = L.crm_oracle_test_mom2d(which, nx, nzm, C.c_double(dx), C.c_double(dz), P(adz), P(adzw), P(rho), P(rhow), P(A(u)), P(A(w)), P(A(tk)), None,
+                                     P(du), P(dw), P(pr))
+        assert rc == 0
+        du_r, dw_r, pr_r = fn()
+        assert np.abs(du).max() > 1e-4 and np.abs(dw[:, 1:nzm]).max() > 1e-5 and np.abs(pr).max() > 0
+        assert _close(du_r, du, 5e-14), which
+        assert _close(dw_r[:, 1:nzm], dw[:, 1:nzm], 5e-14), which
+        assert _close(pr_r[:nzm], pr[:nzm], 5e-14), which
+
+
+def test_buoyancy_against_second_restatement():
+    rng = np.random.default_rng(32)
+    nx, nzm, dx, dz, adz, adzw, z, rho, rhow, grdf_x, grdf_z = _grid_2d(rng)
+    tabs0 = 296. - 6e-3 * z; bet = 9.80616 / tabs0
+    tabs = tabs0[None, :] + rng.uniform(-2., 2., (nx, nzm))
+    qv0 = 1.5e-2 * np.exp(-z / 2500.); qv = qv0[None, :] * rng.uniform(0.7, 1.3, (nx, nzm))
+    qcl = np.where(rng.uniform(size=(nx, nzm)) < 0.3, rng.uniform(0., 1e-3, (nx, nzm)), 0.); qci = 0.2 * qcl[::-1]
+    qpl = np.where(rng.uniform(size=(nx, nzm)) < 0.2, rng.uniform(0., 2e-3, (nx, nzm)), 0.); qpi = 0.5 * qpl[::-1]
+    qn0 = (qcl + qci).mean(axis=0); qp0 = (qpl + qpi).mean(axis=0)
+    A = np.asfortranarray
+    thermo = np.concatenate([A(x).ravel(order="F") for x in (tabs, qv, qcl, qci, qpl, qpi)] + [tabs0, qv0, qn0, qp0, bet])
+    zero2, zero3 = A(np.zeros((nx, nzm))), A(np.zeros((nx, nzm + 1)))
+    du, dw, pr = A(np.zeros((nx, nzm))), A(np.zeros((nx, nzm + 1))), np.zeros(nzm + 1)
+    rc = L.crm_oracle_test_mom2d(3, nx, nzm, C.c_double(dx), C.c_double(dz), P(adz), P(adzw), P(rho), P(rhow), P(zero2), P(zero3), P(zero2), P(thermo),
+                                 P(du), P(dw), P(pr))
+    assert rc == 0
+    dw_r = rn.buoyancy_2d(tabs, qv, qcl, qci, qpl, qpi, tabs0, qv0, qn0, qp0, bet, adz)
+    assert np.abs(dw).max() > 1e-3 and np.all(dw[:, 0] == 0.) and np.all(dw[:, nzm] == 0.)
+    assert np.array_equal(dw_r, dw)            # same expression, same order: bit-identical
+
+
+def test_diffuse_scalar2d_against_second_restatement():
+    rng = np.random.default_rng(33)
+    nx, nzm, dx, dz, adz, adzw, z, rho, rhow, grdf_x, grdf_z = _grid_2d(rng)
+    f = 300. + 4e-3 * z[None, :] + rng.standard_normal((nx, nzm))
+    tkh = rng.uniform(0., 40., (nx, nzm))
+    fluxb = rng.uniform(0., 0.05, nx); fluxt = rng.uniform(-0.01, 0.01, nx)
+    A = np.asfortranarray
+    f_o, flux_o = A(f.copy()), np.zeros(nzm + 1)
+    rc = L.crm_oracle_test_diffuse_scalar2d(nx, nzm, C.c_double(dx), C.c_double(dz), C.c_double(10.), P(adz), P(adzw), P(rho), P(rhow), P(A(tkh)),
+                                            P(fluxb), P(fluxt), P(f_o), P(flux_o))
+    assert rc == 0
+    f_r, flux_r = rn.diffuse_scalar_2d(f, tkh, dx, dz, 10., rho, rhow, adz, adzw, grdf_x, grdf_z, fluxb, fluxt)
+    assert np.abs(f_o - f).max() > 1e-3
+    assert _close(f_r - f, f_o - f, 2e-12) and _close(f_r, f_o, 1e-15)
+    assert _close(flux_r[:nzm], flux_o[:nzm], 5e-14)
+    # the scheme is conservative: the rho*adz-weighted domain sum changes by the boundary fluxes only
+    tot = float(((f_o - f) * (rho * adz)[None, :]).sum())
+    assert abs(tot - 10. * float((fluxb * rhow[0] - fluxt * rhow[nzm] / adzw[nzm]).sum()) / dz) < 1e-9 * np.abs((f_o - f) * (rho * adz)[None, :]).sum()
