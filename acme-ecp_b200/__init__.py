@@ -6,7 +6,7 @@ no CPU fallback: importing .crm and calling crm() without the CUDA library raise
 """
 from .crm_types import (CrmDims, crm_input_type, crm_state_type, crm_rad_type, crm_output_type,
                         crm_ecpp_output_type)
-from . import abi, synthetic, shard
+from . import abi, synthetic, shard, replay
 
 __all__ = ["CrmDims", "crm_input_type", "crm_state_type", "crm_rad_type", "crm_output_type",
-           "crm_ecpp_output_type", "abi", "synthetic", "shard"]
+           "crm_ecpp_output_type", "abi", "synthetic", "shard", "replay"]
