@@ -908,6 +908,42 @@ extern "C" int crm_oracle_test_precip_proc(int n, double dtn, const double *tabs
   return 0;
 }
 
+// ice_fall (ice_fall.F90) and damping (damping.F90) of one 2-D CRM (test hook for tests/test_second_restatement.py).
+// which = 1 ice_fall: reads qcl, qci, tabs; qt, t in/out; prof = [qifall(nzm), tlatqi(nzm)], col = precsfc (nx).
+// which = 2 damping:  reads u, w, qv, qv0, z; qt, t in/out; dudt (nx, nzm), dwdt (nx, nzm+1) out (from zero).
+extern "C" int crm_oracle_test_column_physics(int which, int nx, int nzm, double dz, double dt, double dtn, const double *z, const double *adz,
+                                              const double *rho, const double *qv0, const double *u, const double *w, const double *qv, const double *qcl,
+                                              const double *qci, const double *tabs, double *qt, double *t, double *dudt, double *dwdt, double *prof,
+                                              double *col) {
+  Geo g; g.nx = nx; g.ny = 1; g.nzm = nzm; g.nz = nzm + 1; g.plev = nzm; g.YES3D = 0; g.RUN3D = false; g.nx_rad = 1; g.ny_rad = 1; g.dx = g.dy = 1000.;
+  Crm c; alloc_crm(g, c);
+  Step s; s.na = 1; s.nb = 2; s.nc = 3; s.dt = dt; s.dtn = dtn;
+  c.dz = dz;
+  for (int k = 1; k <= nzm; k++) { c.adz(k) = adz[k - 1]; c.rho(k) = rho[k - 1]; c.z(k) = z[k - 1]; c.qv0(k) = qv0[k - 1]; }
+  for (int k = 1; k <= nzm + 1; k++)
+    for (int i = 1; i <= nx; i++) {
+      const size_t o = (size_t)(i - 1) + (size_t)nx * (k - 1);
+      c.w(i, 1, k) = w[o];
+      if (k <= nzm) {
+        c.u(i, 1, k) = u[o]; c.qv(i, 1, k) = qv[o]; c.qcl(i, 1, k) = qcl[o]; c.qci(i, 1, k) = qci[o]; c.tabs(i, 1, k) = tabs[o];
+        c.qt(i, 1, k) = qt[o]; c.t(i, 1, k) = t[o];
+      }
+    }
+  int rc = 0;
+  if (which == 1) ice_fall(g, c, s); else rc = damping(g, c, s);
+  for (int k = 1; k <= nzm + 1; k++)
+    for (int i = 1; i <= nx; i++) {
+      const size_t o = (size_t)(i - 1) + (size_t)nx * (k - 1);
+      dwdt[o] = c.dwdt[s.na](i, 1, k);
+      if (k <= nzm) { qt[o] = c.qt(i, 1, k); t[o] = c.t(i, 1, k); dudt[o] = c.dudt[s.na](i, 1, k); }
+    }
+  if (which == 1) {
+    for (int k = 1; k <= nzm; k++) { prof[k - 1] = c.qifall(k); prof[nzm + k - 1] = c.tlatqi(k); }
+    for (int i = 1; i <= nx; i++) col[i - 1] = c.precsfc[i - 1];
+  }
+  return rc;
+}
+
 // Momentum tendencies of one 2-D CRM from zero tendencies (test hook for tests/test_second_restatement.py): which = 1 advect_mom
 // (advect2_mom_xy.F90 + advect2_mom_z.F90), 2 sgs_mom (diffuse_mom2D.F90), 3 buoyancy (buoyancy.F90; u/tk unused, the six thermodynamic
 // fields and four reference profiles in `thermo`).  u, tk (nx, nzm), w (nx, nzm+1) in Fortran order; dudt (nx, nzm), dwdt (nx, nzm+1),

@@ -680,3 +680,69 @@ def buoyancy_2d(tabs, qv, qcl, qci, qpl, qpi, tabs0, qv0, qn0, qp0, bet, adz):
         bb, tb = term(kb)
         dwdt[:, k] = dwdt[:, k] + bet[k] * betu * tk_ + bet[kb] * betd * tb
     return dwdt
+
+
+def ice_fall_2d(qcl, qci, tabs, qt, t, dz, dtn, adz, rho):
+    """ice_fall.F90:29-164 for one 2-D CRM, fields (nx, nzm).  Returns (qt_new, t_new, qifall(nzm), tlatqi(nzm), precsfc increment (nx)).
+    Unsuffixed literals (273.15, 0.4, 8.66, 1.e-10, 0.24, 1.0e-25) are REAL(4)."""
+    nx, nzm = qci.shape
+    nz = nzm + 1
+    cold = (qcl + qci > 0.) & (tabs < f4(273.15))
+    levels = np.nonzero(cold.any(axis=0))[0]
+    kmin = int(levels.min()) + 1 if levels.size else nzm + 1        # 1-based like the Fortran
+    kmax = int(levels.max()) + 1 if levels.size else 0
+    qt = qt.copy(); t = t.copy()
+    qifall = np.zeros(nzm); tlatqi = np.zeros(nzm)
+    fz = np.zeros((nx, nz + 1))                                    # fz[:, k-1] = Fortran fz(k); one spare level for fz(k+1) at k = nz
+    for k in range(max(1, kmin - 1), kmax + 1):                    # 1-based k
+        kc = min(nzm, k + 1); kb = max(1, k - 1)
+        coef = dtn / (0.5 * (adz[kb - 1] + adz[k - 1]) * dz)
+        qiu = rho[kc - 1] * qci[:, kc - 1]
+        qic = rho[k - 1] * qci[:, k - 1]
+        qid = rho[kb - 1] * qci[:, kb - 1]
+        vt_ice = np.minimum(f4(0.4), f4(8.66) * (np.maximum(0., qic) + f4(1.e-10)) ** f4(0.24))
+        same = np.abs(qic - qid) < f4(1.0e-25)
+        den = np.where(same, 1., qic - qid)
+        theta = (qiu - qic) / den
+        phi = np.where(same, 0., np.maximum(0., np.minimum(np.minimum(0.5 * (1. + theta), 2.), 2. * theta)))
+        fz[:, k - 1] = -vt_ice * (qic - 0.5 * (1. - coef * vt_ice) * phi * (qic - qid))
+    fz[:, nz - 1] = 0.
+    for k in range(max(1, kmin - 2), kmax + 1):
+        coef = dtn / (dz * adz[k - 1] * rho[k - 1])
+        dqi = coef * (fz[:, k - 1] - fz[:, k])
+        qt[:, k - 1] = qt[:, k - 1] + dqi
+        lat_heat = (fac_cond + fac_fus) * dqi
+        t[:, k - 1] = t[:, k - 1] - lat_heat
+        s1 = 0.; s2 = 0.
+        for i in range(nx):
+            s1 = s1 + dqi[i]; s2 = s2 - lat_heat[i]
+        qifall[k - 1] = s1; tlatqi[k - 1] = s2
+    prec = -(dtn / dz) * fz[:, 0]
+    return qt, t, qifall, tlatqi, prec
+
+
+def damping_2d(u, w, t, qt, qv, qv0, z, dt, dtn):
+    """damping.F90:40-112 for one 2-D CRM (v == 0).  Returns (dudt, dwdt, t_new, qt_new): tendencies from zero."""
+    nx, nzm = u.shape
+    tau_min, tau_max, damp_depth = f4(60.), f4(450.), f4(0.4)
+    assert not tau_min < 2 * dt
+    n_damp = 0
+    for k in range(nzm, 0, -1):
+        if z[nzm - 1] - z[k - 1] < damp_depth * z[nzm - 1]:
+            n_damp = nzm - k + 1
+    dudt = np.zeros((nx, nzm)); dwdt = np.zeros((nx, nzm + 1))
+    t = t.copy(); qt = qt.copy()
+    for k in range(1, nzm + 1):
+        if not (k >= nzm - n_damp):
+            continue
+        tau = tau_min * (tau_max / tau_min) ** ((z[nzm - 1] - z[k - 1]) / (z[nzm - 1] - z[nzm - n_damp - 1]))
+        tau = 1. / tau
+        u0 = 0.; t0 = 0.
+        for i in range(nx):
+            u0 = u0 + u[i, k - 1] / (nx * 1)
+            t0 = t0 + t[i, k - 1] / (nx * 1)
+        dudt[:, k - 1] = dudt[:, k - 1] - (u[:, k - 1] - u0) * tau
+        dwdt[:, k - 1] = dwdt[:, k - 1] - w[:, k - 1] * tau
+        t[:, k - 1] = t[:, k - 1] - dtn * (t[:, k - 1] - t0) * tau
+        qt[:, k - 1] = qt[:, k - 1] - dtn * (qv[:, k - 1] - qv0[k - 1]) * tau
+    return dudt, dwdt, t, qt

@@ -203,3 +203,39 @@ def test_diffuse_scalar2d_against_second_restatement():
     # the scheme is conservative: the rho*adz-weighted domain sum changes by the boundary fluxes only
     tot = float(((f_o - f) * (rho * adz)[None, :]).sum())
     assert abs(tot - 10. * float((fluxb * rhow[0] - fluxt * rhow[nzm] / adzw[nzm]).sum()) / dz) < 1e-9 * np.abs((f_o - f) * (rho * adz)[None, :]).sum()
+
+
+def test_ice_fall_and_damping_against_second_restatement():
+    rng = np.random.default_rng(34)
+    nx, nzm, dx, dz, adz, adzw, z, rho, rhow, grdf_x, grdf_z = _grid_2d(rng, nzm=24, dz=450.)
+    tabs = (299. - 6.2e-3 * z)[None, :] + rng.uniform(-1., 1., (nx, nzm))
+    cloudy = rng.uniform(size=(nx, nzm)) < 0.35
+    qci = np.where(cloudy & (tabs < 268.), rng.uniform(0., 6e-4, (nx, nzm)), 0.)
+    qci[3, :] = np.where(tabs[3] < 268., 2e-4, 0.)            # a column with equal neighbours: the |qic - qid| < 1e-25 branch
+    qcl = np.where(cloudy & (tabs > 255.), rng.uniform(0., 8e-4, (nx, nzm)), 0.)
+    qv = 1.4e-2 * np.exp(-z / 2600.)[None, :] * rng.uniform(0.6, 1.2, (nx, nzm)); qv0 = qv.mean(axis=0)
+    qt = qv + qcl + qci
+    t = tabs + 9.80616 / 1004.64 * z[None, :] - rn.fac_cond * qcl - rn.fac_sub * qci
+    u = 8. + 3. * rng.standard_normal((nx, nzm)); w = np.zeros((nx, nzm + 1)); w[:, 1:nzm] = rng.standard_normal((nx, nzm - 1))
+    A = np.asfortranarray
+    for which in (1, 2):
+        qt_o, t_o = A(qt.copy()), A(t.copy())
+        du, dw, prof, col = A(np.zeros((nx, nzm))), A(np.zeros((nx, nzm + 1))), np.zeros(2 * nzm), np.zeros(nx)
+        rc = L.crm_oracle_test_column_physics(which, nx, nzm, C.c_double(dz), C.c_double(10.), C.c_double(5.), P(z), P(adz), P(rho), P(qv0), P(A(u)), P(A(w)),
+                                              P(A(qv)), P(A(qcl)), P(A(qci)), P(A(tabs)), P(qt_o), P(t_o), P(du), P(dw), P(prof), P(col))
+        assert rc == 0
+        if which == 1:
+            qt_r, t_r, qif_r, tl_r, prec_r = rn.ice_fall_2d(qcl, qci, tabs, qt, t, dz, 5., adz, rho)
+            assert np.abs(qt_o - qt).max() > 1e-7 and np.abs(prof[:nzm]).max() > 0
+            assert _close(qt_r - qt, qt_o - qt, 1e-11) and _close(t_r - t, t_o - t, 1e-11)
+            assert _close(qif_r, prof[:nzm], 1e-11) and _close(tl_r, prof[nzm:], 1e-11)
+            assert _close(prec_r, col, 1e-12) or np.abs(col).max() == 0.
+            # sedimentation only moves ice: rho*adz*dz-weighted column water + what reached the surface is conserved
+            colsum = ((qt_o - qt) * (rho * adz)[None, :]).sum(axis=1) * dz + col * dz
+            assert np.abs(colsum).max() < 1e-12 * np.abs((qt_o - qt) * (rho * adz)[None, :] * dz).sum(axis=1).max()
+        else:
+            du_r, dw_r, t_r, qt_r = rn.damping_2d(u, w, t, qt, qv, qv0, z, 10., 5.)
+            assert np.abs(du).max() > 1e-4 and np.abs(t_o - t).max() > 1e-4
+            assert _close(du_r, du, 1e-13) and _close(dw_r, dw, 1e-13)
+            assert _close(t_r - t, t_o - t, 1e-10) and _close(qt_r - qt, qt_o - qt, 1e-10)
+            assert np.all(du[:, :nzm // 2] == 0.)               # the sponge is the upper 40 % of the domain only
