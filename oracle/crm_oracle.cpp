@@ -908,6 +908,73 @@ extern "C" int crm_oracle_test_precip_proc(int n, double dtn, const double *tabs
   return 0;
 }
 
+// 3-D versions of the two hooks above (BASELINE config 4): which = 1 advect_mom (advect2_mom_xy / _z, RUN3D branches), 2 sgs_mom
+// (diffuse_mom3D.F90); fields (nx, ny, nzm[+1]) in Fortran order, dx == dy; prof = [uwle | uwsb (nzm+1), vwle | vwsb (nzm+1)].
+extern "C" int crm_oracle_test_mom3d(int which, int nx, int ny, int nzm, double dx, double dz, const double *adz, const double *adzw, const double *rho,
+                                     const double *rhow, const double *u, const double *v, const double *w, const double *tk, double *dudt, double *dvdt,
+                                     double *dwdt, double *prof) {
+  Geo g; g.nx = nx; g.ny = ny; g.nzm = nzm; g.nz = nzm + 1; g.plev = nzm; g.YES3D = 1; g.RUN3D = true; g.nx_rad = 1; g.ny_rad = 1; g.dx = g.dy = dx;
+  Crm c; alloc_crm(g, c);
+  Step s; s.na = 1; s.nb = 2; s.nc = 3;
+  c.dz = dz;
+  for (int k = 1; k <= nzm + 1; k++) { c.adzw(k) = adzw[k - 1]; c.rhow(k) = rhow[k - 1]; if (k <= nzm) { c.adz(k) = adz[k - 1]; c.rho(k) = rho[k - 1]; } }
+  for (int k = 1; k <= nzm; k++) {
+    double a2 = (c.adz(k) * c.dz) * (c.adz(k) * c.dz);
+    c.grdf_x(k) = dmin(16., dx * dx / a2); c.grdf_y(k) = c.grdf_x(k); c.grdf_z(k) = 1.;
+  }
+  for (int k = 1; k <= nzm + 1; k++)
+    for (int j = 1; j <= ny; j++)
+      for (int i = 1; i <= nx; i++) {
+        const size_t o = (size_t)(i - 1) + (size_t)nx * ((j - 1) + (size_t)ny * (k - 1));
+        c.w(i, j, k) = w[o];
+        if (k <= nzm) { c.u(i, j, k) = u[o]; c.v(i, j, k) = v[o]; c.tk(i, j, k) = tk[o]; }
+      }
+  boundaries(g, c, 0);
+  boundaries(g, c, 4);
+  if (which == 1) advect_mom(g, c, s); else sgs_mom(g, c, s);
+  for (int k = 1; k <= nzm + 1; k++) {
+    prof[k - 1] = which == 1 ? c.uwle(k) : (k <= nzm ? c.uwsb(k) : 0.);
+    prof[nzm + 1 + k - 1] = which == 1 ? c.vwle(k) : (k <= nzm ? c.vwsb(k) : 0.);
+    for (int j = 1; j <= ny; j++)
+      for (int i = 1; i <= nx; i++) {
+        const size_t o = (size_t)(i - 1) + (size_t)nx * ((j - 1) + (size_t)ny * (k - 1));
+        dwdt[o] = c.dwdt[s.na](i, j, k);
+        if (k <= nzm) { dudt[o] = c.dudt[s.na](i, j, k); dvdt[o] = c.dvdt[s.na](i, j, k); }
+      }
+  }
+  return 0;
+}
+
+extern "C" int crm_oracle_test_diffuse_scalar3d(int nx, int ny, int nzm, double dx, double dz, double dtn, const double *adz, const double *adzw,
+                                                const double *rho, const double *rhow, const double *tkh, const double *fluxb, const double *fluxt,
+                                                double *f, double *flux) {
+  Geo g; g.nx = nx; g.ny = ny; g.nzm = nzm; g.nz = nzm + 1; g.plev = nzm; g.YES3D = 1; g.RUN3D = true; g.nx_rad = 1; g.ny_rad = 1; g.dx = g.dy = dx;
+  Crm c; alloc_crm(g, c);
+  Step s; s.dtn = dtn; s.dt = dtn;
+  c.dz = dz;
+  for (int k = 1; k <= nzm + 1; k++) { c.adzw(k) = adzw[k - 1]; c.rhow(k) = rhow[k - 1]; if (k <= nzm) { c.adz(k) = adz[k - 1]; c.rho(k) = rho[k - 1]; } }
+  for (int k = 1; k <= nzm; k++) {
+    double a2 = (c.adz(k) * c.dz) * (c.adz(k) * c.dz);
+    c.grdf_x(k) = dmin(16., dx * dx / a2); c.grdf_y(k) = c.grdf_x(k); c.grdf_z(k) = 1.;
+  }
+  for (int k = 1; k <= nzm; k++)
+    for (int j = 1; j <= ny; j++)
+      for (int i = 1; i <= nx; i++) {
+        const size_t o = (size_t)(i - 1) + (size_t)nx * ((j - 1) + (size_t)ny * (k - 1));
+        c.t(i, j, k) = f[o]; c.tkh(i, j, k) = tkh[o];
+      }
+  boundaries(g, c, 3);
+  boundaries(g, c, 4);
+  std::vector<double> fb(fluxb, fluxb + (size_t)nx * ny), ft(fluxt, fluxt + (size_t)nx * ny);
+  P1 fdiff = c.tdiff, fl = c.twsb;
+  diffuse_scalar(g, c, s, c.t, fb, ft, fdiff, fl);
+  for (int k = 1; k <= nzm + 1; k++) flux[k - 1] = (k <= nzm) ? fl(k) : 0.;
+  for (int k = 1; k <= nzm; k++)
+    for (int j = 1; j <= ny; j++)
+      for (int i = 1; i <= nx; i++) f[(size_t)(i - 1) + (size_t)nx * ((j - 1) + (size_t)ny * (k - 1))] = c.t(i, j, k);
+  return 0;
+}
+
 // ice_fall (ice_fall.F90) and damping (damping.F90) of one 2-D CRM (test hook for tests/test_second_restatement.py).
 // which = 1 ice_fall: reads qcl, qci, tabs; qt, t in/out; prof = [qifall(nzm), tlatqi(nzm)], col = precsfc (nx).
 // which = 2 damping:  reads u, w, qv, qv0, z; qt, t in/out; dudt (nx, nzm), dwdt (nx, nzm+1) out (from zero).

@@ -746,3 +746,237 @@ def damping_2d(u, w, t, qt, qv, qv0, z, dt, dtn):
         t[:, k - 1] = t[:, k - 1] - dtn * (t[:, k - 1] - t0) * tau
         qt[:, k - 1] = qt[:, k - 1] - dtn * (qv[:, k - 1] - qv0[k - 1]) * tau
     return dudt, dwdt, t, qt
+
+
+def advect_scalar3d(f, u, v, w, rho, rhow, adz):
+    """ADV_MPDATA/advect_scalar3D.F90:126-330 (MPDATA + FCT, nonos) + the flux statistic, for one 3-D CRM: f, u, v (nx, ny, nzm), w
+    (nx, ny, nzm+1), periodic in x and y through np.roll (the Fortran's halo cells are periodic images).  Returns (f_new, flux(nzm))."""
+    nx, ny, nzm = f.shape
+    eps = f4(1.e-10)
+    pp = lambda a: np.maximum(0., a)
+    pn = lambda a: -np.minimum(0., a)
+    andiff = lambda x1, x2, a, b: (np.abs(a) - a * a * b) * 0.5 * (x2 - x1)
+    across = lambda x1, a1, a2: 0.03125 * a1 * a2 * x1
+    X = lambda a, s: np.roll(a, -s, axis=0)        # a(i+s)
+    Y = lambda a, s: np.roll(a, -s, axis=1)        # a(j+s)
+    ks = np.arange(nzm)
+    kb = np.maximum(0, ks - 1); kc = np.minimum(nzm - 1, ks + 1)
+    irho = (1. / rho)[None, None, :]; iadz = (1. / adz)[None, None, :]; irhow = (1. / (rhow[:nzm] * adz))[None, None, :]
+    rho3 = rho[None, None, :]
+
+    def slab_sum(a3):                              # Fortran order of flux(k) = flux(k) + www(i,j,k): j outer, i inner
+        out = np.zeros(nzm)
+        for k in range(nzm):
+            s = 0.
+            for j in range(ny):
+                for i in range(nx):
+                    s = s + a3[i, j, k]
+            out[k] = s
+        return out
+
+    def extrema(g):
+        return [X(g, -1), X(g, 1), Y(g, -1), Y(g, 1), g[:, :, kb], g[:, :, kc], g]
+    mx = np.maximum.reduce(extrema(f)); mn = np.minimum.reduce(extrema(f))
+    wk = w[:, :, :nzm]
+    uuu = np.maximum(0., u) * X(f, -1) + np.minimum(0., u) * f
+    vvv = np.maximum(0., v) * Y(f, -1) + np.minimum(0., v) * f
+    www = np.zeros((nx, ny, nzm + 1))
+    www[:, :, :nzm] = np.maximum(0., wk) * f[:, :, kb] + np.minimum(0., wk) * f
+    flux = slab_sum(www)
+    f = f - (X(uuu, 1) - uuu + Y(vvv, 1) - vvv + (www[:, :, 1:] - www[:, :, :nzm]) * iadz) * irho
+    dd = np.array([float(F(2.) / F(int(kc[k] - kb[k]))) / adz[k] for k in range(nzm)])[None, None, :]
+    wc = w[:, :, kc]                               # w(i,j,kc), kc = min(nzm, k+1)
+    fkb, fkc = f[:, :, kb], f[:, :, kc]
+    uuu = andiff(X(f, -1), f, u, irho) - (
+        across(Y(X(f, -1), 1) + Y(f, 1) - Y(X(f, -1), -1) - Y(f, -1), u, X(v, -1) + Y(X(v, -1), 1) + Y(v, 1) + v) +
+        across(dd * (X(fkc, -1) + fkc - X(fkb, -1) - fkb), u, X(wk, -1) + X(wc, -1) + wk + wc)) * irho
+    vvv = andiff(Y(f, -1), f, v, irho) - (
+        across(Y(X(f, 1), -1) + X(f, 1) - Y(X(f, -1), -1) - X(f, -1), v, Y(u, -1) + u + X(u, 1) + Y(X(u, 1), -1)) +
+        across(dd * (Y(fkc, -1) + fkc - Y(fkb, -1) - fkb), v, Y(wk, -1) + wk + wc + Y(wc, -1))) * irho
+    ukb, vkb = u[:, :, kb], v[:, :, kb]
+    ww2 = andiff(fkb, f, wk, irhow) - (
+        across(X(fkb, 1) + X(f, 1) - X(fkb, -1) - X(f, -1), wk, ukb + u + X(u, 1) + X(ukb, 1)) +
+        across(Y(f, 1) + Y(fkb, 1) - Y(f, -1) - Y(fkb, -1), wk, vkb + Y(vkb, 1) + Y(v, 1) + v)) * irho
+    www = np.zeros((nx, ny, nzm + 1)); www[:, :, :nzm] = ww2
+    www[:, :, 0] = 0.
+    mx = np.maximum.reduce(extrema(f) + [mx]); mn = np.minimum.reduce(extrema(f) + [mn])
+    wkc = www[:, :, kc]; wk0 = www[:, :, :nzm]
+    mxn = rho3 * (mx - f) / (pn(X(uuu, 1)) + pp(uuu) + pn(Y(vvv, 1)) + pp(vvv) + (pn(wkc) + pp(wk0)) * iadz + eps)
+    mnn = rho3 * (f - mn) / (pp(X(uuu, 1)) + pn(uuu) + pp(Y(vvv, 1)) + pn(vvv) + (pp(wkc) + pn(wk0)) * iadz + eps)
+    one = np.ones_like(f)
+    uuu = pp(uuu) * np.minimum.reduce([one, mxn, X(mnn, -1)]) - pn(uuu) * np.minimum.reduce([one, X(mxn, -1), mnn])
+    vvv = pp(vvv) * np.minimum.reduce([one, mxn, Y(mnn, -1)]) - pn(vvv) * np.minimum.reduce([one, Y(mxn, -1), mnn])
+    wl = pp(wk0) * np.minimum.reduce([one, mxn, mnn[:, :, kb]]) - pn(wk0) * np.minimum.reduce([one, mxn[:, :, kb], mnn])
+    for k in range(nzm):                           # flux(k) keeps accumulating cell by cell in the Fortran
+        s = flux[k]
+        for j in range(ny):
+            for i in range(nx):
+                s = s + wl[i, j, k]
+        flux[k] = s
+    www = np.zeros((nx, ny, nzm + 1)); www[:, :, :nzm] = wl
+    f = np.maximum(0., f - (X(uuu, 1) - uuu + Y(vvv, 1) - vvv + (www[:, :, 1:] - www[:, :, :nzm]) * iadz) * irho)
+    return f, flux
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# 3-D CRM (BASELINE config 4): momentum advection / diffusion and scalar diffusion.  Arrays (nx, ny, nzm), w (nx, ny, nzm+1), periodic in
+# x and y; dx == dy and grdf_y == grdf_x in the reference's set-up (crmdims / sgs_init), both are kept as separate arguments here.
+# ---------------------------------------------------------------------------------------------------------------------------
+def _X(a, s):
+    return np.roll(a, -s, axis=0)
+
+
+def _Y(a, s):
+    return np.roll(a, -s, axis=1)
+
+
+def _slab(a2):
+    """Fortran accumulation order of a slab sum: j outer, i inner."""
+    s = 0.
+    for j in range(a2.shape[1]):
+        for i in range(a2.shape[0]):
+            s = s + a2[i, j]
+    return s
+
+
+def advect_mom_3d(u, v, w, dx, dy, dz, rho, rhow, adz, adzw):
+    """advect2_mom_xy.F90:22-58 (RUN3D branch) + advect2_mom_z.F90:26-123 (RUN3D branch).  Returns (dudt, dvdt, dwdt, uwle, vwle)."""
+    nx, ny, nzm = u.shape
+    nz = nzm + 1
+    dudt = np.zeros((nx, ny, nzm)); dvdt = np.zeros((nx, ny, nzm)); dwdt = np.zeros((nx, ny, nz))
+    dx25, dy25 = 0.25 / dx, 0.25 / dy
+    um, up, vm, vp = _X(u, -1), _X(u, 1), _Y(v, -1), _Y(v, 1)
+    # x-fluxes
+    fu1 = dx25 * (u + um) * (um + u); fu2 = dx25 * (up + u) * (u + up)
+    dudt = dudt - (fu2 - fu1)
+    fv1 = dx25 * (u + _Y(u, -1)) * (_X(v, -1) + v); fv2 = dx25 * (up + _Y(up, -1)) * (v + _X(v, 1))
+    dvdt = dvdt - (fv2 - fv1)
+    # y-fluxes (second group of the Fortran loop body)
+    gu1 = dy25 * (v + _X(v, -1)) * (_Y(u, -1) + u); gu2 = dy25 * (vp + _X(vp, -1)) * (u + _Y(u, 1))
+    dudt = dudt - (gu2 - gu1)
+    gv1 = dy25 * (v + vm) * (vm + v); gv2 = dy25 * (vp + v) * (v + vp)
+    dvdt = dvdt - (gv2 - gv1)
+    for k in range(nzm):
+        kcu = min(k + 1, nzm - 1)
+        irho = 1. / (rhow[k + 1] * adzw[k + 1])
+        wk = w[:, :, k + 1]
+        ru = u[:, :, k] * rho[k] * adz[k] + u[:, :, kcu] * rho[kcu] * adz[kcu]
+        fw1 = dx25 * ru * (_X(wk, -1) + wk); fw2 = dx25 * _X(ru, 1) * (wk + _X(wk, 1))
+        dwdt[:, :, k + 1] = dwdt[:, :, k + 1] - irho * (fw2 - fw1)
+        rv = v[:, :, k] * rho[k] * adz[k] + v[:, :, kcu] * rho[kcu] * adz[kcu]
+        gw1 = dy25 * rv * (_Y(wk, -1) + wk); gw2 = dy25 * _Y(rv, 1) * (wk + _Y(wk, 1))
+        dwdt[:, :, k + 1] = dwdt[:, :, k + 1] - irho * (gw2 - gw1)
+    dz25 = 1. / (4. * dz)
+    fuz = np.zeros((nx, ny, nz)); fvz = np.zeros((nx, ny, nz)); fwz = np.zeros((nx, ny, nzm))
+    uwle = np.zeros(nz); vwle = np.zeros(nz)
+    for k in range(1, nzm):
+        rhoi = dz25 * rhow[k]
+        wk = w[:, :, k]
+        fuz[:, :, k] = rhoi * (wk + _X(wk, -1)) * (u[:, :, k] + u[:, :, k - 1])
+        fvz[:, :, k] = rhoi * (wk + _Y(wk, -1)) * (v[:, :, k] + v[:, :, k - 1])
+        uwle[k] = _slab(fuz[:, :, k]); vwle[k] = _slab(fvz[:, :, k])
+    for k in range(nzm):
+        rhoi = 1. / (rho[k] * adz[k])
+        dudt[:, :, k] = dudt[:, :, k] - (fuz[:, :, k + 1] - fuz[:, :, k]) * rhoi
+        dvdt[:, :, k] = dvdt[:, :, k] - (fvz[:, :, k + 1] - fvz[:, :, k]) * rhoi
+        fwz[:, :, k] = dz25 * (w[:, :, k + 1] * rhow[k + 1] + w[:, :, k] * rhow[k]) * (w[:, :, k + 1] + w[:, :, k])
+    for k in range(1, nzm):
+        rhoi = 1. / (rhow[k] * adzw[k])
+        dwdt[:, :, k] = dwdt[:, :, k] - (fwz[:, :, k] - fwz[:, :, k - 1]) * rhoi
+    return dudt, dvdt, dwdt, uwle, vwle
+
+
+def diffuse_mom_3d(u, v, w, tk, dx, dy, dz, rho, rhow, adz, adzw, grdf_x, grdf_y, grdf_z):
+    """SGS_TKE/diffuse_mom3D.F90:40-200 with zero surface / top momentum fluxes.  Returns (dudt, dvdt, dwdt, uwsb, vwsb)."""
+    nx, ny, nzm = u.shape
+    nz = nzm + 1
+    dudt = np.zeros((nx, ny, nzm)); dvdt = np.zeros((nx, ny, nzm)); dwdt = np.zeros((nx, ny, nz))
+    rdx2, rdy2 = 1. / (dx * dx), 1. / (dy * dy)
+    rdx25, rdy25 = 0.25 * rdx2, 0.25 * rdy2
+    dxy, dyx = dx / dy, dy / dx
+    for k in range(nzm):
+        kcu = min(k + 1, nzm - 1)
+        tkk, tkc = tk[:, :, k], tk[:, :, kcu]
+        uk, vk, wk = u[:, :, k], v[:, :, k], w[:, :, k + 1]
+        ukc, vkc = u[:, :, kcu], v[:, :, kcu]
+        # x-direction fluxes at the right face of column i
+        dxz = dx / (dz * adzw[k + 1])
+        rdx21 = rdx2 * grdf_x[k]; rdx251 = rdx25 * grdf_x[k]
+        fu = -2. * (rdx21 * tkk) * (_X(uk, 1) - uk)
+        tkx = rdx251 * (tkk + _Y(tkk, -1) + _X(tkk, 1) + _Y(_X(tkk, 1), -1))
+        fv = -tkx * (_X(vk, 1) - vk + (_X(uk, 1) - _Y(_X(uk, 1), -1)) * dxy)
+        tkx = rdx251 * (tkk + _X(tkk, 1) + tkc + _X(tkc, 1))
+        fw = -tkx * (_X(wk, 1) - wk + (_X(ukc, 1) - _X(uk, 1)) * dxz)
+        dudt[:, :, k] = dudt[:, :, k] - (fu - _X(fu, -1))
+        dvdt[:, :, k] = dvdt[:, :, k] - (fv - _X(fv, -1))
+        dwdt[:, :, k + 1] = dwdt[:, :, k + 1] - (fw - _X(fw, -1))
+        # y-direction fluxes at the far face of row j
+        dyz = dy / (dz * adzw[k + 1])
+        rdy21 = rdy2 * grdf_y[k]; rdy251 = rdy25 * grdf_y[k]
+        gv = -2. * (rdy21 * tkk) * (_Y(vk, 1) - vk)
+        tky = rdy251 * (tkk + _X(tkk, -1) + _Y(tkk, 1) + _X(_Y(tkk, 1), -1))
+        gu = -tky * (_Y(uk, 1) - uk + (_Y(vk, 1) - _X(_Y(vk, 1), -1)) * dyx)
+        tky = rdy251 * (tkk + _Y(tkk, 1) + tkc + _Y(tkc, 1))
+        gw = -tky * (_Y(wk, 1) - wk + (_Y(vkc, 1) - _Y(vk, 1)) * dyz)
+        dudt[:, :, k] = dudt[:, :, k] - (gu - _Y(gu, -1))
+        dvdt[:, :, k] = dvdt[:, :, k] - (gv - _Y(gv, -1))
+        dwdt[:, :, k + 1] = dwdt[:, :, k + 1] - (gw - _Y(gw, -1))
+    fuz = np.zeros((nx, ny, nz)); fvz = np.zeros((nx, ny, nz)); fwz = np.zeros((nx, ny, nz + 1))
+    uwsb = np.zeros(nz); vwsb = np.zeros(nz)
+    rdz = 1. / dz
+    dzx, dzy = dz / dx, dz / dy
+    for k in range(nzm - 1):
+        kc = k + 1
+        rdz2 = rdz * rdz * grdf_z[k]; rdz25 = 0.25 * rdz2
+        iadz = 1. / adz[k]; iadzw = 1. / adzw[kc]
+        tkk, tkc = tk[:, :, k], tk[:, :, kc]
+        fwz[:, :, kc] = -2. * (rdz2 * tkk) * (w[:, :, kc] - w[:, :, k]) * rho[k] * iadz
+        tkz = rdz25 * (tkk + _X(tkk, -1) + tkc + _X(tkc, -1))
+        fuz[:, :, kc] = -tkz * ((u[:, :, kc] - u[:, :, k]) * iadzw + (w[:, :, kc] - _X(w[:, :, kc], -1)) * dzx) * rhow[kc]
+        tkz = rdz25 * (tkk + _Y(tkk, -1) + tkc + _Y(tkc, -1))
+        fvz[:, :, kc] = -tkz * ((v[:, :, kc] - v[:, :, k]) * iadzw + (w[:, :, kc] - _Y(w[:, :, kc], -1)) * dzy) * rhow[kc]
+        uwsb[kc] = _slab(fuz[:, :, kc]); vwsb[kc] = _slab(fvz[:, :, kc])
+    rdz2 = rdz * rdz * grdf_z[nzm - 2]
+    tkz = rdz2 * grdf_z[nzm - 1] * tk[:, :, nzm - 1]
+    fwz[:, :, nzm] = -2. * tkz * (w[:, :, nzm] - w[:, :, nzm - 1]) / adz[nzm - 1] * rho[nzm - 1]
+    for k in range(nzm):
+        rhoi = 1. / (rho[k] * adz[k])
+        dudt[:, :, k] = dudt[:, :, k] - (fuz[:, :, k + 1] - fuz[:, :, k]) * rhoi
+        dvdt[:, :, k] = dvdt[:, :, k] - (fvz[:, :, k + 1] - fvz[:, :, k]) * rhoi
+    for k in range(1, nzm):
+        rhoi = 1. / (rhow[k] * adzw[k])
+        dwdt[:, :, k] = dwdt[:, :, k] - (fwz[:, :, k + 1] - fwz[:, :, k]) * rhoi
+    return dudt, dvdt, dwdt, uwsb, vwsb
+
+
+def diffuse_scalar_3d(f, tkh, dx, dy, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_y, grdf_z, fluxb, fluxt):
+    """SGS_TKE/diffuse_scalar3D.F90:118-205.  f, tkh (nx, ny, nzm), fluxb / fluxt (nx, ny).  Returns (f_new, flux(nzm+1))."""
+    nx, ny, nzm = f.shape
+    nz = nzm + 1
+    rdx2, rdy2 = 1. / (dx * dx), 1. / (dy * dy)
+    dfdt = np.zeros((nx, ny, nzm))
+    for k in range(nzm):
+        fk, tkk = f[:, :, k], tkh[:, :, k]
+        flx = -(0.5 * rdx2 * grdf_x[k] * (tkk + _X(tkk, 1))) * (_X(fk, 1) - fk)
+        fly = -(0.5 * rdy2 * grdf_y[k] * (tkk + _Y(tkk, 1))) * (_Y(fk, 1) - fk)
+        dfdt[:, :, k] = dfdt[:, :, k] - (flx - _X(flx, -1))
+        dfdt[:, :, k] = dfdt[:, :, k] - (fly - _Y(fly, -1))
+    flz = np.zeros((nx, ny, nz))                    # flz[:, :, k] = Fortran flx_z(:,:,k), k = 0..nzm
+    flux = np.zeros(nz)
+    for k in range(nzm - 1):
+        kc = k + 1
+        rhoi = rhow[kc] / adzw[kc]
+        rdz5 = 0.5 * (1. / (dz * dz)) * grdf_z[k]
+        tkz = rdz5 * (tkh[:, :, k] + tkh[:, :, kc])
+        flz[:, :, k + 1] = -tkz * (f[:, :, kc] - f[:, :, k]) * rhoi
+        flux[kc] = _slab(flz[:, :, k + 1])
+    tmp = 1. / adzw[nz - 1]
+    rdz = 1. / dz
+    flz[:, :, 0] = fluxb * rdz * rhow[0]
+    flz[:, :, nzm] = fluxt * rdz * tmp * rhow[nz - 1]
+    flux[0] = _slab(flz[:, :, 0])
+    out = f.copy()
+    for k in range(nzm):
+        rhoi = 1. / (adz[k] * rho[k])
+        out[:, :, k] = f[:, :, k] + dtn * (dfdt[:, :, k] - (flz[:, :, k + 1] - flz[:, :, k]) * rhoi)
+    return out, flux

@@ -239,3 +239,51 @@ def test_ice_fall_and_damping_against_second_restatement():
             assert _close(du_r, du, 1e-13) and _close(dw_r, dw, 1e-13)
             assert _close(t_r - t, t_o - t, 1e-10) and _close(qt_r - qt, qt_o - qt, 1e-10)
             assert np.all(du[:, :nzm // 2] == 0.)               # the sponge is the upper 40 % of the domain only
+
+
+def test_advect_scalar3d_against_second_restatement():
+    """advect_scalar3D.F90 (MPDATA + FCT in three dimensions): the 3-D CRM of BASELINE config 4."""
+    import test_oracle_kat as tk
+    rng = np.random.default_rng(41)
+    nx, ny, nzm = 8, 8, 14
+    adz = rng.uniform(0.6, 1.6, nzm); rho = np.linspace(1.15, 0.35, nzm) * rng.uniform(0.97, 1.03, nzm)
+    rhow = np.concatenate([[rho[0]], 0.5 * (rho[1:] + rho[:-1]), [rho[-1]]])
+    u, v, w = tk._nondivergent_flux(nx, ny, nzm, adz, rng, cmax=0.3)
+    u = u * rho[None, None, :] / rho.max(); v = v * rho[None, None, :] / rho.max(); w = w * rhow[None, None, :] / rho.max()
+    f0 = np.zeros((nx, ny, nzm)); f0[2:5, 3:7, 3:8] = 1.0; f0 += 1e-3 * rng.uniform(size=f0.shape); f0[6:, :, 10:] = 0.
+    g, fadv, flux = tk._advect(nx, ny, nzm, u, v, w, rho, rhow, adz, f0)
+    f_ref, flux_ref = rn.advect_scalar3d(f0.copy(), u, v, w, rho, rhow, adz)
+    assert np.abs(g - f0).max() > 1e-2 and np.abs(v).max() > 0
+    assert _close(f_ref, g, 1e-13) and _close(flux_ref, flux, 1e-12)
+    assert _close((f_ref - f0).sum(axis=(0, 1)), fadv, 1e-10, floor=1e-3)
+
+
+def test_3d_momentum_and_scalar_diffusion_against_second_restatement():
+    """The 3-D CRM (config 4): advect2_mom_xy / advect2_mom_z (RUN3D branches), diffuse_mom3D, diffuse_scalar3D."""
+    rng = np.random.default_rng(42)
+    nx, nzm, dx, dz, adz, adzw, z, rho, rhow, grdf_x, grdf_z = _grid_2d(rng, nx=8, nzm=14)
+    ny = 8
+    u = 6. + 3. * rng.standard_normal((nx, ny, nzm)); v = -2. + 3. * rng.standard_normal((nx, ny, nzm))
+    w = np.zeros((nx, ny, nzm + 1)); w[:, :, 1:nzm] = rng.standard_normal((nx, ny, nzm - 1))
+    tk = rng.uniform(0., 30., (nx, ny, nzm)); tk[:, :, nzm - 1] = rng.uniform(0., 5., (nx, ny))
+    A = np.asfortranarray
+    for which, fn in ((1, lambda: rn.advect_mom_3d(u, v, w, dx, dx, dz, rho, rhow, adz, adzw)),
+                      (2, lambda: rn.diffuse_mom_3d(u, v, w, tk, dx, dx, dz, rho, rhow, adz, adzw, grdf_x, grdf_x, grdf_z))):
+        du, dv, dw, pr = A(np.zeros((nx, ny, nzm))), A(np.zeros((nx, ny, nzm))), A(np.zeros((nx, ny, nzm + 1))), np.zeros(2 * (nzm + 1))
+        rc = L.crm_oracle_test_mom3d(which, nx, ny, nzm, C.c_double(dx), C.c_double(dz), P(adz), P(adzw), P(rho), P(rhow), P(A(u)), P(A(v)), P(A(w)),
+                                     P(A(tk)), P(du), P(dv), P(dw), P(pr))
+        assert rc == 0
+        du_r, dv_r, dw_r, pu_r, pv_r = fn()
+        assert min(np.abs(du).max(), np.abs(dv).max(), np.abs(dw[:, :, 1:nzm]).max()) > 1e-5
+        assert _close(du_r, du, 1e-13) and _close(dv_r, dv, 1e-13) and _close(dw_r[:, :, 1:nzm], dw[:, :, 1:nzm], 1e-13), which
+        assert _close(pu_r[:nzm], pr[:nzm], 1e-13) and _close(pv_r[:nzm], pr[nzm + 1:2 * nzm + 1], 1e-13), which
+    f = 300. + 4e-3 * z[None, None, :] + rng.standard_normal((nx, ny, nzm))
+    tkh = rng.uniform(0., 40., (nx, ny, nzm))
+    fluxb = rng.uniform(0., 0.05, (nx, ny)); fluxt = rng.uniform(-0.01, 0.01, (nx, ny))
+    f_o, flux_o = A(f.copy()), np.zeros(nzm + 1)
+    rc = L.crm_oracle_test_diffuse_scalar3d(nx, ny, nzm, C.c_double(dx), C.c_double(dz), C.c_double(10.), P(adz), P(adzw), P(rho), P(rhow), P(A(tkh)),
+                                            P(A(fluxb)), P(A(fluxt)), P(f_o), P(flux_o))
+    assert rc == 0
+    f_r, flux_r = rn.diffuse_scalar_3d(f, tkh, dx, dx, dz, 10., rho, rhow, adz, adzw, grdf_x, grdf_x, grdf_z, fluxb, fluxt)
+    assert np.abs(f_o - f).max() > 1e-3
+    assert _close(f_r - f, f_o - f, 2e-12) and _close(f_r, f_o, 1e-15) and _close(flux_r[:nzm], flux_o[:nzm], 1e-13)
