@@ -908,6 +908,44 @@ extern "C" int crm_oracle_test_precip_proc(int n, double dtn, const double *tabs
   return 0;
 }
 
+// sgs_proc of one 3-D CRM (shear_prod3D.F90 + tke_full.F90): as crm_oracle_test_sgs with v, v0 and fields (nx, ny, nzm[+1]).
+extern "C" int crm_oracle_test_sgs3d(int nx, int ny, int nzm, double dx, double dt, double dz, const double *adz, const double *adzw, const double *bet,
+                                     const double *presi, const double *u0, const double *v0, const double *u, const double *v, const double *w,
+                                     const double *t, const double *tabs, const double *qv, const double *qcl, const double *qci, const double *qpl,
+                                     const double *qpi, double *tk, double *tkh, double *tke) {
+  Geo g; g.nx = nx; g.ny = ny; g.nzm = nzm; g.nz = nzm + 1; g.plev = nzm; g.YES3D = 1; g.RUN3D = true; g.nx_rad = 1; g.ny_rad = 1; g.dx = g.dy = dx;
+  Crm c; alloc_crm(g, c);
+  Step s; s.dt = dt; s.dtn = dt;
+  c.dz = dz;
+  for (int k = 1; k <= nzm + 1; k++) {
+    c.adzw(k) = adzw[k - 1]; c.presi(k) = presi[k - 1];
+    if (k <= nzm) { c.adz(k) = adz[k - 1]; c.bet(k) = bet[k - 1]; c.u0(k) = u0[k - 1]; c.v0(k) = v0[k - 1]; }
+  }
+  for (int k = 1; k <= nzm; k++) {
+    double a2 = (c.adz(k) * c.dz) * (c.adz(k) * c.dz);
+    c.grdf_x(k) = dmin(16., dx * dx / a2); c.grdf_y(k) = c.grdf_x(k); c.grdf_z(k) = 1.;
+  }
+  for (int k = 1; k <= nzm + 1; k++)
+    for (int j = 1; j <= ny; j++)
+      for (int i = 1; i <= nx; i++) {
+        const size_t o = (size_t)(i - 1) + (size_t)nx * ((j - 1) + (size_t)ny * (k - 1));
+        c.w(i, j, k) = w[o];
+        if (k <= nzm) {
+          c.u(i, j, k) = u[o]; c.v(i, j, k) = v[o]; c.t(i, j, k) = t[o]; c.tabs(i, j, k) = tabs[o]; c.qv(i, j, k) = qv[o]; c.qcl(i, j, k) = qcl[o];
+          c.qci(i, j, k) = qci[o]; c.qpl(i, j, k) = qpl[o]; c.qpi(i, j, k) = qpi[o]; c.tk(i, j, k) = tk[o]; c.tkh(i, j, k) = tk[o];
+        }
+      }
+  boundaries(g, c, 0);
+  sgs_proc(g, c, s);
+  for (int k = 1; k <= nzm; k++)
+    for (int j = 1; j <= ny; j++)
+      for (int i = 1; i <= nx; i++) {
+        const size_t o = (size_t)(i - 1) + (size_t)nx * ((j - 1) + (size_t)ny * (k - 1));
+        tk[o] = c.tk(i, j, k); tkh[o] = c.tkh(i, j, k); tke[o] = c.tke(i, j, k);
+      }
+  return 0;
+}
+
 // 3-D versions of the two hooks above (BASELINE config 4): which = 1 advect_mom (advect2_mom_xy / _z, RUN3D branches), 2 sgs_mom
 // (diffuse_mom3D.F90); fields (nx, ny, nzm[+1]) in Fortran order, dx == dy; prof = [uwle | uwsb (nzm+1), vwle | vwsb (nzm+1)].
 extern "C" int crm_oracle_test_mom3d(int which, int nx, int ny, int nzm, double dx, double dz, const double *adz, const double *adzw, const double *rho,

@@ -399,37 +399,9 @@ def precip_fall_columns(dz, dtn, rho, rhow, adz, tabs, qp, t):
     return qp, t, precsfc, nprec
 
 
-def sgs_2d(dx, dt, dz, adz, adzw, bet, presi, u0, u, w, t, tabs, qv, qcl, qci, qpl, qpi, tk):
-    """shear_prod2D.F90 + tke_full.F90 (dosmagor) for one 2-D CRM: fields (nx, nzm), w (nx, nzm+1), v == 0; periodic in x.
-    Returns (tk, tkh, tke); tk in = eddy viscosity of the previous sub-step."""
-    nx, nzm = u.shape
-    sq = lambda x: x * x
-    rdx0 = 1. / dx
-    def2 = np.zeros((nx, nzm))
-    up, wm = _r(u, 1), _r(w, -1)
-    wpl = _r(w, 1)
-    for k in range(nzm):
-        rdz = 1. / (dz * adz[k]); rdx = rdx0 * math.sqrt(dx * rdz)
-        base = 2. * (sq((up[:, k] - u[:, k]) * rdx) + sq((w[:, k + 1] - w[:, k]) * rdz))
-        upt = dnt = None
-        if k <= nzm - 2:
-            rdzw_up = 1. / (dz * adzw[k + 1]); rdx_up = rdx0 * math.sqrt(dx * rdzw_up)
-            upt = sq((up[:, k + 1] - u0[k + 1] - up[:, k] + u0[k]) * rdzw_up + (wpl[:, k + 1] - w[:, k + 1]) * rdx_up) + \
-                sq((u[:, k + 1] - u0[k + 1] - u[:, k] + u0[k]) * rdzw_up + (w[:, k + 1] - wm[:, k + 1]) * rdx_up)
-        if k >= 1:
-            rdzw_dn = 1. / (dz * adzw[k]); rdx_dn = rdx0 * math.sqrt(dx * rdzw_dn)
-            dnt = sq((up[:, k] - u0[k] - up[:, k - 1] + u0[k - 1]) * rdzw_dn + (wpl[:, k] - w[:, k]) * rdx_dn) + \
-                sq((u[:, k] - u0[k] - u[:, k - 1] + u0[k - 1]) * rdzw_dn + (w[:, k] - wm[:, k]) * rdx_dn)
-        if 1 <= k <= nzm - 2:
-            a1 = sq((up[:, k + 1] - u0[k + 1] - up[:, k] + u0[k]) * rdzw_up + (wpl[:, k + 1] - w[:, k + 1]) * rdx_up)
-            a2 = sq((u[:, k + 1] - u0[k + 1] - u[:, k] + u0[k]) * rdzw_up + (w[:, k + 1] - wm[:, k + 1]) * rdx_up)
-            a3 = sq((up[:, k] - u0[k] - up[:, k - 1] + u0[k - 1]) * rdzw_dn + (wpl[:, k] - w[:, k]) * rdx_dn)
-            a4 = sq((u[:, k] - u0[k] - u[:, k - 1] + u0[k - 1]) * rdzw_dn + (w[:, k] - wm[:, k]) * rdx_dn)
-            def2[:, k] = base + 0.5 * (0. + 0. + a1 + a2 + a3 + a4 + 0. + 0.)
-        elif k == 0:
-            def2[:, k] = base + 0.5 * (0. + 0.) + 0. + 0.5 * upt
-        else:
-            def2[:, k] = base + 0.5 * (0. + 0.) + 0. + 0.5 * dnt
+def _tke_full(def2, dx, dy, dt, dz, adz, adzw, bet, presi, t, tabs, qv, qcl, qci, qpl, qpi, tk):
+    """tke_full.F90:103-310 (dosmagor) on independent columns: every array (ncol, nzm); def2 from shear_prod2D / shear_prod3D."""
+    nx, nzm = def2.shape
     Cs, Ck = f4(0.15), f4(0.1)
     Ce = Ck * Ck * Ck / (Cs * Cs * Cs * Cs)
     Pr = 1.
@@ -465,7 +437,7 @@ def sgs_2d(dx, dt, dz, adz, adzw, bet, presi, u0, u, w, t, tabs, qv, qcl, qci, q
         grd = dz * adz[k]
         Ce1 = Ce / f4(0.7) * f4(0.19); Ce2 = Ce / f4(0.7) * f4(0.51)
         grdf_x = min(16., dx * dx / ((adz[k] * dz) * (adz[k] * dz)))
-        cx = dx ** 2 / dt / grdf_x; cy = dx ** 2 / dt / grdf_x
+        cx = dx ** 2 / dt / grdf_x; cy = dy ** 2 / dt / grdf_x
         cz = (dz * min(adzw[k], adzw[k + 1])) ** 2 / dt / 1.
         tkmax = f4(0.09) / (1. / cx + 1. / cy + 1. / cz)
         for i in range(nx):
@@ -481,6 +453,40 @@ def sgs_2d(dx, dt, dz, adz, adzw, bet, presi, u0, u, w, t, tabs, qv, qcl, qci, q
             tkv = min(tkv, tkmax)
             tk[i, k] = tkv; tkh[i, k] = Pr * tkv
     return tk, tkh, tke
+
+
+def sgs_2d(dx, dt, dz, adz, adzw, bet, presi, u0, u, w, t, tabs, qv, qcl, qci, qpl, qpi, tk):
+    """shear_prod2D.F90 + tke_full.F90 (dosmagor) for one 2-D CRM: fields (nx, nzm), w (nx, nzm+1), v == 0; periodic in x.
+    Returns (tk, tkh, tke); tk in = eddy viscosity of the previous sub-step."""
+    nx, nzm = u.shape
+    sq = lambda x: x * x
+    rdx0 = 1. / dx
+    def2 = np.zeros((nx, nzm))
+    up, wm = _r(u, 1), _r(w, -1)
+    wpl = _r(w, 1)
+    for k in range(nzm):
+        rdz = 1. / (dz * adz[k]); rdx = rdx0 * math.sqrt(dx * rdz)
+        base = 2. * (sq((up[:, k] - u[:, k]) * rdx) + sq((w[:, k + 1] - w[:, k]) * rdz))
+        upt = dnt = None
+        if k <= nzm - 2:
+            rdzw_up = 1. / (dz * adzw[k + 1]); rdx_up = rdx0 * math.sqrt(dx * rdzw_up)
+            upt = sq((up[:, k + 1] - u0[k + 1] - up[:, k] + u0[k]) * rdzw_up + (wpl[:, k + 1] - w[:, k + 1]) * rdx_up) + \
+                sq((u[:, k + 1] - u0[k + 1] - u[:, k] + u0[k]) * rdzw_up + (w[:, k + 1] - wm[:, k + 1]) * rdx_up)
+        if k >= 1:
+            rdzw_dn = 1. / (dz * adzw[k]); rdx_dn = rdx0 * math.sqrt(dx * rdzw_dn)
+            dnt = sq((up[:, k] - u0[k] - up[:, k - 1] + u0[k - 1]) * rdzw_dn + (wpl[:, k] - w[:, k]) * rdx_dn) + \
+                sq((u[:, k] - u0[k] - u[:, k - 1] + u0[k - 1]) * rdzw_dn + (w[:, k] - wm[:, k]) * rdx_dn)
+        if 1 <= k <= nzm - 2:
+            a1 = sq((up[:, k + 1] - u0[k + 1] - up[:, k] + u0[k]) * rdzw_up + (wpl[:, k + 1] - w[:, k + 1]) * rdx_up)
+            a2 = sq((u[:, k + 1] - u0[k + 1] - u[:, k] + u0[k]) * rdzw_up + (w[:, k + 1] - wm[:, k + 1]) * rdx_up)
+            a3 = sq((up[:, k] - u0[k] - up[:, k - 1] + u0[k - 1]) * rdzw_dn + (wpl[:, k] - w[:, k]) * rdx_dn)
+            a4 = sq((u[:, k] - u0[k] - u[:, k - 1] + u0[k - 1]) * rdzw_dn + (w[:, k] - wm[:, k]) * rdx_dn)
+            def2[:, k] = base + 0.5 * (0. + 0. + a1 + a2 + a3 + a4 + 0. + 0.)
+        elif k == 0:
+            def2[:, k] = base + 0.5 * (0. + 0.) + 0. + 0.5 * upt
+        else:
+            def2[:, k] = base + 0.5 * (0. + 0.) + 0. + 0.5 * dnt
+    return _tke_full(def2, dx, dx, dt, dz, adz, adzw, bet, presi, t, tabs, qv, qcl, qci, qpl, qpi, tk)
 
 
 def esmt_pgf(u_s, w, zi, z, rho, dx):
@@ -980,3 +986,56 @@ def diffuse_scalar_3d(f, tkh, dx, dy, dz, dtn, rho, rhow, adz, adzw, grdf_x, grd
         rhoi = 1. / (adz[k] * rho[k])
         out[:, :, k] = f[:, :, k] + dtn * (dfdt[:, :, k] - (flz[:, :, k + 1] - flz[:, :, k]) * rhoi)
     return out, flux
+
+
+def shear_prod3d(u, v, w, u0, v0, dx, dy, dz, adz, adzw):
+    """SGS_TKE/shear_prod3D.F90:19-135: def2 (nx, ny, nzm) of one 3-D CRM; the bottom / top levels use the one-sided forms."""
+    nx, ny, nzm = u.shape
+    sq = lambda x: x * x
+    rdx0, rdy0 = 1. / dx, 1. / dy
+    def2 = np.zeros((nx, ny, nzm))
+    for k in range(nzm):
+        rdz = 1. / (dz * adz[k])
+        rdx = rdx0 * math.sqrt(dx * rdz); rdy = rdy0 * math.sqrt(dy * rdz)
+        uk, vk, wk, wc = u[:, :, k], v[:, :, k], w[:, :, k], w[:, :, k + 1]
+        ic = lambda a: _X(a, 1); ib = lambda a: _X(a, -1); jc = lambda a: _Y(a, 1); jb = lambda a: _Y(a, -1)
+        d = 2. * (sq((ic(uk) - uk) * rdx) + sq((jc(vk) - vk) * rdy) + sq((wc - wk) * rdz)) + 0.25 * (
+            sq((jc(ic(uk)) - ic(uk)) * rdy + (jc(ic(vk)) - jc(vk)) * rdx) +
+            sq((jc(uk) - uk) * rdy + (jc(vk) - ib(jc(vk))) * rdx) +
+            sq((ic(uk) - jb(ic(uk))) * rdy + (ic(vk) - vk) * rdx) +
+            sq((uk - jb(uk)) * rdy + (vk - ib(vk)) * rdx))
+        up = dn = None
+        if k <= nzm - 2:
+            rdzw_up = 1. / (dz * adzw[k + 1])
+            rdx_up = rdx0 * math.sqrt(dx * rdzw_up); rdy_up = rdy0 * math.sqrt(dy * rdzw_up)
+            un, vn = u[:, :, k + 1], v[:, :, k + 1]
+            up_u = (sq((ic(un) - u0[k + 1] - ic(uk) + u0[k]) * rdzw_up + (ic(wc) - wc) * rdx_up) +
+                    sq((un - u0[k + 1] - uk + u0[k]) * rdzw_up + (wc - ib(wc)) * rdx_up))
+            up_v = (sq((jc(vn) - v0[k + 1] - jc(vk) + v0[k]) * rdzw_up + (jc(wc) - wc) * rdy_up) +
+                    sq((vn - v0[k + 1] - vk + v0[k]) * rdzw_up + (wc - jb(wc)) * rdy_up))
+        if k >= 1:
+            rdzw_dn = 1. / (dz * adzw[k])
+            rdx_dn = rdx0 * math.sqrt(dx * rdzw_dn); rdy_dn = rdy0 * math.sqrt(dy * rdzw_dn)
+            ub, vb = u[:, :, k - 1], v[:, :, k - 1]
+            dn_u = (sq((ic(uk) - u0[k] - ic(ub) + u0[k - 1]) * rdzw_dn + (ic(wk) - wk) * rdx_dn) +
+                    sq((uk - u0[k] - ub + u0[k - 1]) * rdzw_dn + (wk - ib(wk)) * rdx_dn))
+            dn_v = (sq((jc(vk) - v0[k] - jc(vb) + v0[k - 1]) * rdzw_dn + (jc(wk) - wk) * rdy_dn) +
+                    sq((vk - v0[k] - vb + v0[k - 1]) * rdzw_dn + (wk - jb(wk)) * rdy_dn))
+        if 1 <= k <= nzm - 2:
+            d = d + 0.25 * (up_u + dn_u)
+            d = d + 0.25 * (up_v + dn_v)
+        elif k == 0:
+            d = d + 0.5 * up_v + 0.5 * up_u
+        else:
+            d = d + 0.5 * dn_v + 0.5 * dn_u
+        def2[:, :, k] = d
+    return def2
+
+
+def sgs_3d(dx, dt, dz, adz, adzw, bet, presi, u0, v0, u, v, w, t, tabs, qv, qcl, qci, qpl, qpi, tk):
+    """shear_prod3D.F90 + tke_full.F90 for one 3-D CRM (dx == dy): fields (nx, ny, nzm), w (nx, ny, nzm+1).  Returns (tk, tkh, tke)."""
+    nx, ny, nzm = u.shape
+    def2 = shear_prod3d(u, v, w, u0, v0, dx, dx, dz, adz, adzw)
+    flat = lambda a: a.reshape(nx * ny, nzm)
+    out = _tke_full(flat(def2), dx, dx, dt, dz, adz, adzw, bet, presi, flat(t), flat(tabs), flat(qv), flat(qcl), flat(qci), flat(qpl), flat(qpi), flat(tk))
+    return tuple(a.reshape(nx, ny, nzm) for a in out)

@@ -287,3 +287,35 @@ def test_3d_momentum_and_scalar_diffusion_against_second_restatement():
     f_r, flux_r = rn.diffuse_scalar_3d(f, tkh, dx, dx, dz, 10., rho, rhow, adz, adzw, grdf_x, grdf_x, grdf_z, fluxb, fluxt)
     assert np.abs(f_o - f).max() > 1e-3
     assert _close(f_r - f, f_o - f, 2e-12) and _close(f_r, f_o, 1e-15) and _close(flux_r[:nzm], flux_o[:nzm], 1e-13)
+
+
+def test_3d_sgs_against_second_restatement():
+    """shear_prod3D + tke_full for the 3-D CRM."""
+    rng = np.random.default_rng(43)
+    nx, ny, nzm, dx, dt, dz = 8, 8, 16, 1000., 10., 120.
+    adz = np.linspace(0.8, 2.2, nzm); adzw = np.concatenate([[1.], 0.5 * (adz[1:] + adz[:-1]), [adz[-1]]])
+    z = np.cumsum(adz) * dz
+    sh = (nx, ny, nzm)
+    tabs = (295. - 6e-3 * z)[None, None, :] + rng.uniform(-1., 1., sh)
+    presi = 1000. * np.exp(-np.concatenate([[0.], z]) / 8000.)
+    bet = 9.80616 / (295. - 6e-3 * z)
+    u = 5. + 2. * rng.standard_normal(sh); v = -1. + 2. * rng.standard_normal(sh)
+    w = np.zeros((nx, ny, nzm + 1)); w[:, :, 1:nzm] = rng.standard_normal((nx, ny, nzm - 1))
+    u0 = u.mean(axis=(0, 1)); v0 = v.mean(axis=(0, 1))
+    qs = np.vectorize(rn.qsatw)(tabs, (0.5 * (presi[:-1] + presi[1:]))[None, None, :])
+    cloudy = rng.uniform(size=sh) < 0.4
+    qcl = np.where(cloudy & (tabs > 263.), rng.uniform(0., 1.5e-3, sh), 0.)
+    qci = np.where(cloudy & (tabs < 270.), rng.uniform(0., 4e-4, sh), 0.)
+    qv = qs * np.where(cloudy, 1.0, rng.uniform(0.3, 0.95, sh))
+    qpl = np.where(rng.uniform(size=sh) < 0.3, rng.uniform(0., 1e-3, sh), 0.); qpi = 0.3 * qpl[:, ::-1]
+    t = tabs + 9.80616 / 1004.64 * z[None, None, :] - rn.fac_cond * (qcl + qpl) - rn.fac_sub * (qci + qpi)
+    tk_in = rng.uniform(0., 20., sh)
+    A = np.asfortranarray
+    tk, tkh, tke = A(tk_in.copy()), A(np.zeros(sh)), A(np.zeros(sh))
+    rc = L.crm_oracle_test_sgs3d(nx, ny, nzm, C.c_double(dx), C.c_double(dt), C.c_double(dz), P(adz), P(adzw), P(bet), P(presi), P(u0), P(v0), P(A(u)), P(A(v)),
+                                 P(A(w)), P(A(t)), P(A(tabs)), P(A(qv)), P(A(qcl)), P(A(qci)), P(A(qpl)), P(A(qpi)), P(tk), P(tkh), P(tke))
+    assert rc == 0
+    tk_r, tkh_r, tke_r = rn.sgs_3d(dx, dt, dz, adz, adzw, bet, presi, u0, v0, u, v, w, t, tabs, qv, qcl, qci, qpl, qpi, tk_in)
+    m = nzm - 1
+    assert tk[:, :, :m].max() > 0.1
+    assert _close(tk_r[:, :, :m], tk[:, :, :m], 5e-13) and _close(tkh_r[:, :, :m], tkh[:, :, :m], 5e-13) and _close(tke_r[:, :, :m], tke[:, :, :m], 5e-13)
