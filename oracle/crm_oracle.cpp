@@ -1016,6 +1016,8 @@ extern "C" int crm_oracle_test_diffuse_scalar3d(int nx, int ny, int nzm, double 
 // ice_fall (ice_fall.F90) and damping (damping.F90) of one 2-D CRM (test hook for tests/test_second_restatement.py).
 // which = 1 ice_fall: reads qcl, qci, tabs; qt, t in/out; prof = [qifall(nzm), tlatqi(nzm)], col = precsfc (nx).
 // which = 2 damping:  reads u, w, qv, qv0, z; qt, t in/out; dudt (nx, nzm), dwdt (nx, nzm+1) out (from zero).
+// which = 3 forcing:  prof in = [ttend | qtend | utend]; qt, t in/out, dudt out.   which = 4 kurant (+ kurant_sgs): u, w, tkh (in qv), prof in = adzw;
+// col[0] = cfl out (dx = 1000).
 extern "C" int crm_oracle_test_column_physics(int which, int nx, int nzm, double dz, double dt, double dtn, const double *z, const double *adz,
                                               const double *rho, const double *qv0, const double *u, const double *w, const double *qv, const double *qcl,
                                               const double *qci, const double *tabs, double *qt, double *t, double *dudt, double *dwdt, double *prof,
@@ -1035,7 +1037,18 @@ extern "C" int crm_oracle_test_column_physics(int which, int nx, int nzm, double
       }
     }
   int rc = 0;
-  if (which == 1) ice_fall(g, c, s); else rc = damping(g, c, s);
+  if (which == 3) {   // forcing.F90: prof in = [ttend, qtend, utend (nzm each)]
+    for (int k = 1; k <= nzm; k++) { c.ttend(k) = prof[k - 1]; c.qtend(k) = prof[nzm + k - 1]; c.utend(k) = prof[2 * nzm + k - 1]; c.vtend(k) = 0.; }
+    forcing(g, c, s);
+  } else if (which == 4) {   // kurant.F90 + kurant_sgs: tkh is passed in qv; col[0] = cfl
+    for (int k = 1; k <= nzm + 1; k++) c.adzw(k) = prof[k - 1];
+    for (int k = 1; k <= nzm; k++) {
+      double a2 = (c.adz(k) * c.dz) * (c.adz(k) * c.dz);
+      c.grdf_x(k) = dmin(16., g.dx * g.dx / a2); c.grdf_y(k) = c.grdf_x(k); c.grdf_z(k) = 1.;
+      for (int i = 1; i <= nx; i++) c.tkh(i, 1, k) = c.qv(i, 1, k);
+    }
+    col[0] = kurant_cfl(g, c, s);
+  } else if (which == 1) ice_fall(g, c, s); else rc = damping(g, c, s);
   for (int k = 1; k <= nzm + 1; k++)
     for (int i = 1; i <= nx; i++) {
       const size_t o = (size_t)(i - 1) + (size_t)nx * (k - 1);

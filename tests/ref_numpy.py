@@ -1039,3 +1039,37 @@ def sgs_3d(dx, dt, dz, adz, adzw, bet, presi, u0, v0, u, v, w, t, tabs, qv, qcl,
     flat = lambda a: a.reshape(nx * ny, nzm)
     out = _tke_full(flat(def2), dx, dx, dt, dz, adz, adzw, bet, presi, flat(t), flat(tabs), flat(qv), flat(qcl), flat(qci), flat(qpl), flat(qpi), flat(tk))
     return tuple(a.reshape(nx, ny, nzm) for a in out)
+
+
+def forcing_2d(t, qt, ttend, qtend, utend, dtn):
+    """forcing.F90:27-62 for one 2-D CRM: large-scale tendencies and the negative-moisture fix.  Returns (t, qt, dudt increment)."""
+    nx, nzm = t.shape
+    t = t + ttend[None, :] * dtn
+    qt = qt + qtend[None, :] * dtn
+    dudt = np.zeros((nx, nzm)) + utend[None, :]
+    for k in range(nzm):
+        nneg = 0; qneg = 0.; qpoz = 0.
+        for i in range(nx):
+            if qt[i, k] < 0.:
+                nneg += 1; qneg = qneg + qt[i, k]
+            else:
+                qpoz = qpoz + qt[i, k]
+        if nneg > 0 and qpoz + qneg > 0.:
+            factor = 1. + qneg / qpoz
+            qt[:, k] = np.maximum(0., qt[:, k] * factor)
+    return t, qt, dudt
+
+
+def kurant_2d(u, w, tkh, dx, dz, dt, adz, adzw):
+    """kurant.F90:31-55 + sgs.F90:343-365 (kurant_sgs) for one 2-D CRM (YES3D = 0): the CFL number behind ncycle = ceiling(cfl/0.7)."""
+    nx, nzm = u.shape
+    wm = np.zeros(nzm + 2); wm[:nzm] = np.abs(w[:, :nzm]).max(axis=0)
+    uhm = np.sqrt(u ** 2).max(axis=0)
+    cfl = 0.
+    for k in range(nzm):
+        cfl = max(cfl, max(uhm[k] * dt * math.sqrt((1. / dx) ** 2), max(wm[k], wm[k + 1]) * dt / (dz * adzw[k])))
+    tkhmax = tkh.max(axis=0)
+    for k in range(nzm):
+        grdf_x = min(16., dx * dx / ((adz[k] * dz) * (adz[k] * dz)))
+        cfl = max(cfl, max(0.5 * tkhmax[k] * 1. * dt / (dz * adzw[k]) ** 2, 0.5 * tkhmax[k] * grdf_x * dt / dx ** 2, 0.))
+    return cfl

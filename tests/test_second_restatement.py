@@ -319,3 +319,35 @@ def test_3d_sgs_against_second_restatement():
     m = nzm - 1
     assert tk[:, :, :m].max() > 0.1
     assert _close(tk_r[:, :, :m], tk[:, :, :m], 5e-13) and _close(tkh_r[:, :, :m], tkh[:, :, :m], 5e-13) and _close(tke_r[:, :, :m], tke[:, :, :m], 5e-13)
+
+
+def test_forcing_and_kurant_against_second_restatement():
+    rng = np.random.default_rng(35)
+    nx, nzm, dx, dz, adz, adzw, z, rho, rhow, grdf_x, grdf_z = _grid_2d(rng, nzm=24, dz=300.)
+    t = 300. + 4e-3 * z[None, :] + rng.standard_normal((nx, nzm))
+    qt = 1.2e-2 * np.exp(-z / 2500.)[None, :] * rng.uniform(0.5, 1.5, (nx, nzm))
+    qt[:, -3:] = rng.uniform(-2e-7, 6e-7, (nx, 3))                         # levels where the negative-moisture fix acts
+    qt[:, -1] = -1e-7                                                      # all negative: qpoz + qneg <= 0, left alone
+    ttend = rng.uniform(-3e-5, 3e-5, nzm); qtend = rng.uniform(-2e-8, 2e-8, nzm); utend = rng.uniform(-1e-4, 1e-4, nzm)
+    A = np.asfortranarray
+    zero2, zero3 = A(np.zeros((nx, nzm))), A(np.zeros((nx, nzm + 1)))
+    qt_o, t_o = A(qt.copy()), A(t.copy())
+    du, dw, col = A(np.zeros((nx, nzm))), A(np.zeros((nx, nzm + 1))), np.zeros(nx)
+    prof = np.concatenate([ttend, qtend, utend])
+    rc = L.crm_oracle_test_column_physics(3, nx, nzm, C.c_double(dz), C.c_double(10.), C.c_double(5.), P(z), P(adz), P(rho), P(np.zeros(nzm)), P(zero2), P(zero3),
+                                          P(zero2), P(zero2), P(zero2), P(zero2), P(qt_o), P(t_o), P(du), P(dw), P(prof), P(col))
+    assert rc == 0
+    t_r, qt_r, du_r = rn.forcing_2d(t, qt, ttend, qtend, utend, 5.)
+    assert np.array_equal(t_r, t_o) and np.array_equal(du_r, du)
+    assert (qt_o[:, -3:-1] == 0.).any() and qt_o[:, -3:-1].min() >= 0. and np.all(qt_o[:, -1] < 0.)
+    assert _close(qt_r, qt_o, 1e-15)
+    # kurant
+    u = 12. * rng.standard_normal((nx, nzm)); w = np.zeros((nx, nzm + 1)); w[:, 1:nzm] = 3. * rng.standard_normal((nx, nzm - 1))
+    for scale in (1., 400.):                                               # advective limit, then the SGS (tkh) limit
+        tkh = scale * rng.uniform(0., 30., (nx, nzm))
+        col = np.zeros(nx)
+        rc = L.crm_oracle_test_column_physics(4, nx, nzm, C.c_double(dz), C.c_double(10.), C.c_double(10.), P(z), P(adz), P(rho), P(np.zeros(nzm)), P(A(u)),
+                                              P(A(w)), P(A(tkh)), P(zero2), P(zero2), P(zero2), P(A(qt.copy())), P(A(t.copy())), P(du), P(dw), P(adzw.copy()), P(col))
+        assert rc == 0
+        cfl = rn.kurant_2d(u, w, tkh, 1000., dz, 10., adz, adzw)
+        assert abs(cfl - col[0]) <= 1e-15 * cfl and cfl > 0.1
