@@ -1073,3 +1073,175 @@ def kurant_2d(u, w, tkh, dx, dz, dt, adz, adzw):
         grdf_x = min(16., dx * dx / ((adz[k] * dz) * (adz[k] * dz)))
         cfl = max(cfl, max(0.5 * tkhmax[k] * 1. * dt / (dz * adzw[k]) ** 2, 0.5 * tkhmax[k] * grdf_x * dt / dx ** 2, 0.))
     return cfl
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# crm_module.F90 itself: the vertical grid of the prologue (:338-372), the per-step statistics (:896-1073) and the epilogue outputs that
+# are functions of the FINAL fields of a call (:1086-1135, 1139-1170, 1212-1243, 1311-1378, 1464-1512), for a call of ONE CRM step
+# (nstop = 1: every accumulator holds one sample).  Inputs are what a caller sees: crm_input, crm_state before / after, crm_output's 3-D
+# members; nothing comes from the oracle's internals.
+# ---------------------------------------------------------------------------------------------------------------------------
+def crm_grid(zmid, zint, pmid, pint, pdel, nzm):
+    """crm_module.F90:338-372 for one column: returns dict(z, pres, dz, adz, adzw, rho, rhow); GCM arrays are top-down (plev / plev+1)."""
+    plev = zmid.shape[0]
+    nz = nzm + 1
+    z = np.array([zmid[plev - k] - zint[plev] for k in range(1, nzm + 1)])
+    zi = np.array([zint[plev - k + 1] - zint[plev] for k in range(1, nz + 1)])
+    pres = np.array([pmid[plev - k] / 100. for k in range(1, nzm + 1)])
+    dz = 0.5 * (z[0] + z[1])
+    adzw = np.zeros(nz)
+    adzw[1:nzm] = (z[1:] - z[:-1]) / dz
+    adzw[0] = 1.; adzw[nz - 1] = adzw[nzm - 1]
+    adz = (zi[1:] - zi[:-1]) / dz
+    rho = np.array([pdel[plev - k] / ggr / (adz[k - 1] * dz) for k in range(1, nzm + 1)])
+    rhow = np.zeros(nz)
+    for k in range(2, nzm + 1):
+        rhow[k - 1] = (pmid[plev - k + 1] - pmid[plev - k]) / ggr / (adzw[k - 1] * dz)
+    rhow[0] = 2. * rhow[1] - rhow[2]
+    rhow[nz - 1] = 2. * rhow[nzm - 1] - rhow[nzm - 2]
+    return dict(z=z, pres=pres, dz=dz, adz=adz, adzw=adzw, rho=rho, rhow=rhow)
+
+
+def crm_outputs_one_step(g, plev, dt_gl, inp, tabs_in, qp_in, u, v, w, tabs, qv, qcl, qci, qpl, qpi, nx_rad, ny_rad):
+    """Outputs of a one-step crm() call (nstop = 1) of ONE sam1mom CRM from its final fields (nx, ny, nzm) [w: (nx, ny, nzm+1)].
+    `inp` = dict of this column's crm_input profiles (tl, ql, qccl, qiil, pdel), tabs_in / qp_in the crm_state before the call.
+    Returns a dict of (plev) profiles, scalars and the (nx_rad, ny_rad, nzm) radiation means."""
+    nx, ny, nzm = tabs.shape
+    nz = nzm + 1
+    rho, rhow, adz, dz, pres = g["rho"], g["rhow"], g["adz"], g["dz"], g["pres"]
+    cwp_threshold, wmin = f4(0.001), 2.
+    factor_xy = 1. / float(nx * ny); factor_xyt = factor_xy / 1.
+    o = {n: np.zeros(plev) for n in ("cld", "cldtop", "gicewp", "gliqwp", "mcup", "mcdn", "mcuup", "mcudn", "qc_mean", "qi_mean", "qr_mean", "qg_mean",
+                                     "qs_mean", "tln", "qln", "qccln", "qiiln")}
+    mui = np.zeros(plev + 2); mdi = np.zeros(plev + 2)          # 1-based l up to plev+1
+    cl = dict(cltot=0., clhgh=0., clmed=0., cllow=0.)
+    for j in range(ny):
+        for i in range(nx):
+            cwp = cwph = cwpm = cwpl = 0.
+            flag_top = True
+            ct = ch = cm_ = cl_ = 0.
+            for k in range(1, nzm + 1):
+                l = plev - k + 1
+                kk = nz - k                                     # 1-based level counted from the top
+                tmp1 = rho[kk - 1] * adz[kk - 1] * dz * (qcl[i, j, kk - 1] + qci[i, j, kk - 1])
+                cwp = cwp + tmp1
+                ct = max(1., ct)                                # cf3d == 1 (CF3D default of vars.F90)
+                if cwp > cwp_threshold and flag_top:
+                    o["cldtop"][l - 1] += 1; flag_top = False
+                if pres[kk - 1] >= f4(700.):
+                    cwpl = cwpl + tmp1; cl_ = max(1., cl_)
+                elif pres[kk - 1] < f4(400.):
+                    cwph = cwph + tmp1; ch = max(1., ch)
+                else:
+                    cwpm = cwpm + tmp1; cm_ = max(1., cm_)
+                tmp1 = rho[k - 1] * adz[k - 1] * dz
+                ws = w[i, j, k] + w[i, j, k - 1]
+                if tmp1 * (qcl[i, j, k - 1] + qci[i, j, k - 1]) > cwp_threshold:
+                    o["cld"][l - 1] += 1.
+                    if ws > 2 * wmin:
+                        o["mcup"][l - 1] += rho[k - 1] * 0.5 * ws * 1.
+                        o["mcuup"][l - 1] += rho[k - 1] * 0.5 * ws * (f4(1.0) - 1.)
+                    if ws < -2 * wmin:
+                        o["mcdn"][l - 1] += rho[k - 1] * 0.5 * ws * 1.
+                        o["mcudn"][l - 1] += rho[k - 1] * 0.5 * ws * (1. - 1.)
+                else:
+                    if ws > 2 * wmin:
+                        o["mcuup"][l - 1] += rho[k - 1] * 0.5 * ws
+                    if ws < -2 * wmin:
+                        o["mcudn"][l - 1] += rho[k - 1] * 0.5 * ws
+                o["gliqwp"][l - 1] += qcl[i, j, k - 1]
+                o["gicewp"][l - 1] += qci[i, j, k - 1]
+            if cwp > cwp_threshold: cl["cltot"] += ct
+            if cwph > cwp_threshold: cl["clhgh"] += ch
+            if cwpm > cwp_threshold: cl["clmed"] += cm_
+            if cwpl > cwp_threshold: cl["cllow"] += cl_
+            for k in range(1, nzm + 2):                         # mass fluxes on w-levels
+                l = plev + 1 - k + 1
+                wk = w[i, j, k - 1]
+                if wk > 0.:
+                    kx = max(1, k - 1)
+                    qs = qsatw(tabs[i, j, kx - 1], pres[kx - 1])
+                    if qcl[i, j, kx - 1] + qci[i, j, kx - 1] > min(f4(1.e-5), f4(0.01) * qs):
+                        mui[l] += rhow[k - 1] * wk
+                elif wk < 0.:
+                    kx = min(k + 1, nzm)
+                    qs = qsatw(tabs[i, j, kx - 1], pres[kx - 1])
+                    if qcl[i, j, kx - 1] + qci[i, j, kx - 1] > min(f4(1.e-5), f4(0.01) * qs):
+                        mdi[l] += rhow[k - 1] * wk
+                    elif qpl[i, j, kx - 1] + qpi[i, j, kx - 1] > f4(1.0e-4):
+                        mdi[l] += rhow[k - 1] * wk
+    # radiation column-group means (:979-1003, 1086-1108)
+    rad = {n: np.zeros((nx_rad, ny_rad, nzm)) for n in ("temperature", "qv", "qc", "qi", "cld")}
+    for k in range(nzm):
+        for j in range(ny):
+            for i in range(nx):
+                ir, jr = i // (nx // nx_rad), j // (ny // ny_rad)
+                rad["temperature"][ir, jr, k] += tabs[i, j, k]
+                rad["qv"][ir, jr, k] += max(0., qv[i, j, k])
+                rad["qc"][ir, jr, k] += qcl[i, j, k]
+                rad["qi"][ir, jr, k] += qci[i, j, k]
+                if qcl[i, j, k] + qci[i, j, k] > 0:
+                    rad["cld"][ir, jr, k] += 1.
+    tmp1 = (float(nx_rad) / float(nx)) * (float(ny_rad) / float(ny)) / 1.
+    for n in rad:
+        rad[n] = rad[n] * tmp1
+    # epilogue: horizontal means and tendencies (:1139-1170, 1212-1243)
+    ptop = plev - nzm + 1
+    colprec = colprecs = 0.
+    colprec0 = colprecs0 = 0.
+    a_pr = 1. / (tprmax - tprmin); a_grc = 1. / (tgrmax - tgrmin)
+    pdel = inp["pdel"]
+    for k in range(1, nzm + 1):
+        l = plev - k + 1
+        for i in range(nx):
+            for j in range(ny):
+                colprec = colprec + (qpl[i, j, k - 1] + qpi[i, j, k - 1]) * pdel[plev - k]
+                colprecs = colprecs + qpi[i, j, k - 1] * pdel[plev - k]
+                o["tln"][l - 1] += tabs[i, j, k - 1]; o["qln"][l - 1] += qv[i, j, k - 1]
+                o["qccln"][l - 1] += qcl[i, j, k - 1]; o["qiiln"][l - 1] += qci[i, j, k - 1]
+        for j in range(ny):                                     # the prologue's colprec (:503-517) from the state before the call
+            for i in range(nx):
+                omp = max(0., min(1., (tabs_in[i, j, k - 1] - tprmin) * a_pr))
+                qpl0 = qp_in[i, j, k - 1] * omp; qpi0 = qp_in[i, j, k - 1] * (1. - omp)
+                colprec0 = colprec0 + (qpl0 + qpi0) * pdel[plev - k]
+                colprecs0 = colprecs0 + qpi0 * pdel[plev - k]
+        for j in range(ny):
+            for i in range(nx):
+                o["qc_mean"][l - 1] += qcl[i, j, k - 1]; o["qi_mean"][l - 1] += qci[i, j, k - 1]; o["qr_mean"][l - 1] += qpl[i, j, k - 1]
+                omg = max(0., min(1., (tabs[i, j, k - 1] - tgrmin) * a_grc))
+                o["qg_mean"][l - 1] += qpi[i, j, k - 1] * omg
+                o["qs_mean"][l - 1] += qpi[i, j, k - 1] * (1. - omg)
+    res = {}
+    irt = 1. / dt_gl
+    for n, src, ref in (("sltend", "tln", "tl"), ("qltend", "qln", "ql"), ("qcltend", "qccln", "qccl"), ("qiltend", "qiiln", "qiil")):
+        mean = inp[ref].copy()
+        mean[ptop - 1:] = o[src][ptop - 1:] * factor_xy
+        res[n] = (cp if n == "sltend" else 1.) * (mean - inp[ref]) * irt
+        res[n][ptop - 1:ptop + 1] = 0.
+    res["prectend"] = (colprec - colprec0) / ggr * factor_xy * irt
+    res["precstend"] = (colprecs - colprecs0) / ggr * factor_xy * irt
+    res["cld"] = np.minimum(1., o["cld"] * factor_xyt); res["cldtop"] = np.minimum(1., o["cldtop"] * factor_xyt)
+    res["gicewp"] = o["gicewp"] * pdel * f4(1000.) / ggr * factor_xyt; res["gliqwp"] = o["gliqwp"] * pdel * f4(1000.) / ggr * factor_xyt
+    for n in ("mcup", "mcdn", "mcuup", "mcudn"):
+        res[n] = o[n] * factor_xyt
+    res["mctot"] = res["mcup"] + res["mcdn"] + res["mcuup"] + res["mcudn"]
+    for n in ("qc_mean", "qi_mean", "qs_mean", "qg_mean", "qr_mean"):
+        res[n] = o[n] * factor_xy
+    for n in cl:
+        res[n] = cl[n] * factor_xyt
+    mu = np.zeros(plev); md = np.zeros(plev); eu = np.zeros(plev); du = np.zeros(plev); ed = np.zeros(plev)
+    jt, mx = plev * f4(1.0), f4(1.0)
+    for k in range(1, plev + 1):
+        mu[k - 1] = 0.5 * (mui[k] + mui[k + 1]) * ggr / f4(100.)
+        md[k - 1] = 0.5 * (mdi[k] + mdi[k + 1]) * ggr / f4(100.)
+        if mui[k] - mui[k + 1] > 0:
+            eu[k - 1] = (mui[k] - mui[k + 1]) * ggr / pdel[k - 1]
+        else:
+            du[k - 1] = f4(-1.0) * (mui[k] - mui[k + 1]) * ggr / pdel[k - 1]
+        if mdi[k + 1] - mdi[k] < 0:
+            ed[k - 1] = (mdi[k] - mdi[k + 1]) * ggr / pdel[k - 1]
+        if abs(mu[k - 1]) > f4(1.0e-15) or abs(md[k - 1]) > f4(1.0e-15):
+            jt = min(float(k), jt); mx = max(float(k), mx)
+    res.update(mu_crm=mu, md_crm=md, eu_crm=eu, du_crm=du, ed_crm=ed, jt_crm=jt, mx_crm=mx)
+    res["rad"] = rad
+    return res

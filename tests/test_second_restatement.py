@@ -351,3 +351,40 @@ def test_forcing_and_kurant_against_second_restatement():
         assert rc == 0
         cfl = rn.kurant_2d(u, w, tkh, 1000., dz, 10., adz, adzw)
         assert abs(cfl - col[0]) <= 1e-15 * cfl and cfl > 0.1
+
+
+@pytest.mark.parametrize("ny", [1, 8])
+def test_crm_module_grid_statistics_and_epilogue_against_second_restatement(ny):
+    """crm_module.F90 itself: vertical grid (:338-372), per-step statistics (:896-1073) and the epilogue outputs (:1086-1512) recomputed in numpy
+    from what a caller sees (crm_input, crm_state before / after, crm_output's 3-D members) for a call of ONE CRM step, 2-D and 3-D."""
+    if ny == 1:
+        dims = cm.small_dims(ncrms=4, nx=16, nsteps=1)
+        spin = 120
+    else:
+        dims = cm.pkg.CrmDims(ncrms=2, nx=8, ny=8, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=20.0, igstep=3, nx_rad=2, ny_rad=2)
+        spin = 60
+    dims, inp, st, rad = cm.make_case(dims, spin)
+    st0 = st.copy()
+    out, stats = cm.ob.run(dims, inp, st, rad)
+    assert stats["nstop"] == 1
+    plev, nzm = dims.plev, dims.nzm
+    checked = 0
+    for ic in range(dims.ncrms):
+        g = rn.crm_grid(inp.zmid[ic], inp.zint[ic], inp.pmid[ic], inp.pint[ic], inp.pdel[ic], nzm)
+        w = np.zeros((dims.nx, dims.ny, nzm + 1)); w[:, :, :nzm] = st.w_wind[ic]
+        qv = st.qt[ic] - st.qn[ic]
+        col = dict(tl=inp.tl[ic], ql=inp.ql[ic], qccl=inp.qccl[ic], qiil=inp.qiil[ic], pdel=inp.pdel[ic])
+        r = rn.crm_outputs_one_step(g, plev, dims.dt_gl, col, st0.temperature[ic], st0.qp[ic], st.u_wind[ic], st.v_wind[ic], w, st.temperature[ic], qv,
+                                    out.qcl[ic], out.qci[ic], out.qpl[ic], out.qpi[ic], dims.nx_rad, dims.ny_rad)
+        for n in ("sltend", "qltend", "qcltend", "qiltend", "cld", "cldtop", "gicewp", "gliqwp", "mcup", "mcdn", "mcuup", "mcudn", "mctot", "qc_mean",
+                  "qi_mean", "qs_mean", "qg_mean", "qr_mean", "mu_crm", "md_crm", "eu_crm", "du_crm", "ed_crm"):
+            a = getattr(out, n)[ic]
+            assert _close(r[n], a, 1e-11, floor=1e-30), (ic, n, np.abs(r[n] - a).max(), np.abs(a).max())
+            checked += int(np.abs(a).max() > 0)
+        for n in ("prectend", "precstend", "cltot", "clhgh", "clmed", "cllow", "jt_crm", "mx_crm"):
+            a = float(getattr(out, n)[ic])
+            assert abs(r[n] - a) <= 1e-9 * max(abs(a), 1e-30) + 1e-30, (ic, n, r[n], a)
+        for n in ("temperature", "qv", "qc", "qi", "cld"):
+            assert _close(r["rad"][n], getattr(rad, n)[ic], 1e-13, floor=1e-30), (ic, n)
+    assert checked > 10 * dims.ncrms          # clouds, updraughts and precipitation are present in the spun-up state
+    assert float(out.cld.max()) > 0 and float(np.abs(out.mu_crm).max()) > 0
