@@ -118,7 +118,10 @@ __global__ void __launch_bounds__(CRM_LB(NXT)) k_p1_forcing(CrmP p) {
     // --- forcing
     double t = A.plane(5, k)[tid] + SPF(7, k) * dtn;
     double qt = A.plane(6, k)[tid] + SPF(8, k) * dtn;
-    {
+    // forcing.F90:46-61, the negative-moisture fix: it acts only on levels that hold a negative qt, which is rare.  One barrier with an
+    // OR-reduction decides for the whole tile; the three slab sums (a serial sum over the block's warps in every thread: 18 % of this
+    // kernel's instructions in 2-D, half of them for a 32x32 CRM) are formed only then.  Results are identical: nneg == 0 leaves qt alone.
+    if (__syncthreads_or(qt < 0.)) {
       double v[3];
       v[0] = (qt < 0.) ? 1. : 0.; v[1] = (qt < 0.) ? qt : 0.; v[2] = (qt < 0.) ? 0. : qt;
       block_sum<3>(v, tid, P, CT, red);

@@ -878,14 +878,28 @@ __global__ void __launch_bounds__(CRM_LB(NXT), CRM_LBMIN(NXT, 4)) k_p8_micro(Crm
       if (sub == 0) { cnt[l * nw + wrp] = __popc(mA[l]); cnt[NL * nw + l * nw + wrp] = __popc(mB[l]); }
     }
     __syncthreads();
+    // Exclusive prefix of the NE = NL*nw (<= 64) per-(level, warp) counts of both classes: every warp scans them with shuffles, two
+    // entries per lane.  (Every thread used to sum them serially: 10 instructions per entry, 640 per thread for a 32x32 CRM.)
     int offA[NL], offB[NL];
+    {
+      const int NE = NL * nw;
+      int a0 = sub < NE ? cnt[sub] : 0, a1 = sub + 32 < NE ? cnt[sub + 32] : 0;
+      int b0 = sub < NE ? cnt[NE + sub] : 0, b1 = sub + 32 < NE ? cnt[NE + sub + 32] : 0;
 #pragma unroll
-    for (int l = 0; l < NL; l++) { offA[l] = 0; offB[l] = 0; }
-    for (int g = 0; g < NL * nw; g++) {
-      const int a = cnt[g], b = cnt[NL * nw + g];
+      for (int d = 1; d < 32; d <<= 1) {
+        const int ta0 = __shfl_up_sync(0xffffffffu, a0, d), ta1 = __shfl_up_sync(0xffffffffu, a1, d);
+        const int tb0 = __shfl_up_sync(0xffffffffu, b0, d), tb1 = __shfl_up_sync(0xffffffffu, b1, d);
+        if (sub >= d) { a0 += ta0; a1 += ta1; b0 += tb0; b1 += tb1; }
+      }
+      a1 += __shfl_sync(0xffffffffu, a0, 31); b1 += __shfl_sync(0xffffffffu, b0, 31);
+      nA = __shfl_sync(0xffffffffu, a1, 31); nB = __shfl_sync(0xffffffffu, b1, 31);
 #pragma unroll
-      for (int l = 0; l < NL; l++) if (g < l * nw + wrp) { offA[l] += a; offB[l] += b; }
-      nA += a; nB += b;
+      for (int l = 0; l < NL; l++) {
+        const int e = l * nw + wrp;   // warp-uniform
+        const int ia = e < 32 ? __shfl_sync(0xffffffffu, a0, e) : __shfl_sync(0xffffffffu, a1, e - 32);
+        const int ib = e < 32 ? __shfl_sync(0xffffffffu, b0, e) : __shfl_sync(0xffffffffu, b1, e - 32);
+        offA[l] = ia - cnt[e]; offB[l] = ib - cnt[NE + e];
+      }
     }
     const unsigned lt = (1u << sub) - 1u;
 #pragma unroll

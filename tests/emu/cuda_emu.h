@@ -43,6 +43,22 @@ static inline double __shfl_xor_sync(unsigned, double v, int lanemask) {
   pthread_barrier_wait(wb);
   return r;
 }
+// integer shuffles (k_p8_micro's count scan); lanes outside the block keep their own value like an out-of-range source on the device
+static inline int emu_shfl_int(int v, int src_lane) {
+  pthread_barrier_t *wb = &emu_warp_barrier[threadIdx.x >> 5];
+  emu_vote_buf[threadIdx.x] = v;
+  pthread_barrier_wait(wb);
+  const unsigned w0 = threadIdx.x & ~31u;
+  int r = v;
+  if (src_lane >= 0 && src_lane < 32 && w0 + (unsigned)src_lane < blockDim.x) r = emu_vote_buf[w0 + (unsigned)src_lane];
+  pthread_barrier_wait(wb);
+  return r;
+}
+static inline int __shfl_sync(unsigned, int v, int src_lane) { return emu_shfl_int(v, src_lane & 31); }
+static inline int __shfl_up_sync(unsigned, int v, unsigned delta) {
+  const int lane = (int)(threadIdx.x & 31u);
+  return emu_shfl_int(v, lane - (int)delta >= 0 ? lane - (int)delta : lane);
+}
 static inline unsigned __ballot_sync(unsigned, int pred) {
   pthread_barrier_t *wb = &emu_warp_barrier[threadIdx.x >> 5];
   emu_vote_buf[threadIdx.x] = pred != 0;
@@ -51,6 +67,14 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
   const unsigned w0 = threadIdx.x & ~31u;
   for (unsigned l = 0; l < 32 && w0 + l < blockDim.x; l++) r |= (unsigned)emu_vote_buf[w0 + l] << l;
   pthread_barrier_wait(wb);
+  return r;
+}
+static inline int __syncthreads_or(int pred) {   // barrier + OR over the block (k_p1_forcing's negative-moisture vote)
+  emu_vote_buf[threadIdx.x] = pred != 0;
+  pthread_barrier_wait(&emu_barrier);
+  int r = 0;
+  for (unsigned t = 0; t < blockDim.x; t++) r |= emu_vote_buf[t];
+  pthread_barrier_wait(&emu_barrier);
   return r;
 }
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
