@@ -179,3 +179,27 @@ def check_resident(dims, host, res, orc, hist, tol):
     qv = (st_r.qt - out_r.qcl) - out_r.qci if dims.micro == 0 else st_r.qt - out_r.qcl
     assert np.array_equal(hist["CRM_QV"][:n], qv[:n])
     assert float(hist["CRM_QV"][:n].min()) > 0.0
+
+
+def negative_moisture_case(dims, lib_path=None, spin=60):
+    """forcing.F90:46-61: drive qt negative in part of the domain -- every second column of SOME CRMs holds 2 % of its moisture and the
+    large-scale tendency dries (crm_input%ql = 0.3 x the GCM value, one CRM step per call) -- so that both the skipped and the taken
+    branch of the device's per-tile vote are exercised; compare the state right after the forcing phase (CRM_DEBUG_STOP = 1).
+    Returns (errors, qt device, mask of the drying CRMs)."""
+    dims, inp, st, rad = make_case(dims, spin)
+    dry = np.arange(dims.ncrms) % 3 == 1                       # every third CRM: tiles hold CRMs with and without negative cells
+    for f in (st.qt, st.qn):
+        sub = f[dry]
+        sub[:, ::2] *= 0.02
+        f[dry] = sub
+    inp.ql[dry] *= 0.3
+    res = phase_errors(dims, inp, st, rad, 1, lib_path=lib_path)
+    os.environ["CRM_DEBUG_STOP"] = "1"
+    try:
+        h = libmod.CrmHandle(dims, lib_path=lib_path)
+        h.run(dims, inp, st.copy(), rad.copy())
+        qt = h.debug_fetch("qt")
+        h.close()
+    finally:
+        del os.environ["CRM_DEBUG_STOP"]
+    return res, qt, dry

@@ -138,3 +138,13 @@ def test_emu_resident_3d(emu):
     host, res, orc, hist, _ = cm.resident_case(d3, lib_path=emu, ncalls=1)
     cm.check_resident(d3, host, res, orc, hist, 1e-10)
     assert float(np.abs(res[0].v_wind).max()) > 0.0
+
+
+def test_emu_negative_moisture_fix(emu):
+    """The forcing phase with negative qt in some CRMs of a tile (k_p1_forcing forms the three slab sums only when the tile's vote finds a
+    negative cell): identical to the oracle, and the fix really acted (clipped cells are exactly zero in the drying CRMs only)."""
+    dims = cm.small_dims(ncrms=6, nx=8, nsteps=1)
+    res, qt, dry = cm.negative_moisture_case(dims, lib_path=emu)
+    for name, err, scale in res:
+        assert err <= 1e-12 or err * scale < 1e-18, (name, err, scale)
+    assert (qt[dry] == 0.).sum() > 10 and (qt[~dry] == 0.).sum() == 0

@@ -576,3 +576,18 @@ def test_resident_m2005_and_3d():
     host, res, orc, hist, _ = cm.resident_case(d3)
     cm.check_resident(d3, host, res, orc, hist, 1e-9)
     assert float(np.abs(res[0].v_wind).max()) > 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geo", ["2d", "3d"])
+def test_negative_moisture_fix_in_forcing(geo):
+    """forcing.F90:46-61 with negative qt in some CRMs of a tile (the device forms the slab sums of the fix only when the tile's vote finds a
+    negative cell): the state after the forcing phase equals the oracle's, clipped cells are exactly zero in the drying CRMs only."""
+    if geo == "2d":
+        dims = cm.small_dims(ncrms=22, nx=64, nzm=58, plev=72, nsteps=1)
+    else:
+        dims = cm.pkg.CrmDims(ncrms=5, nx=16, ny=16, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=20.0, igstep=3)
+    res, qt, dry = cm.negative_moisture_case(dims, spin=40)
+    for name, err, scale in res:
+        assert err <= 1e-12 or err * scale < 1e-18, (name, err, scale)
+    assert (qt[dry] == 0.).sum() > 10 and (qt[~dry] == 0.).sum() == 0
