@@ -349,19 +349,11 @@ __device__ __forceinline__ void block_sum_impl(double (&v)[NQ], int tid, int P, 
     for (int q = 0; q < NQ; q++) red[(w * NQ + q) * CT + lane] = v[q];
   }
   __syncthreads();
-  // second stage: the nw*CT warp partials of a quantity are summed by a whole warp -- lane `sub` adds the partials sub, sub+32, ... (all of
-  // its own CRM lane, since CT divides 32; ascending order) and an xor-shuffle tree over the warp-index bits finishes -- instead of a serial
-  // chain of nw loads and adds per quantity in every thread (ALL) or in the CT leader threads: nw*CT/32 loads + log2(32/CT) shuffles.
-  if (ALL || tid < 32) {
-    const int sub = tid & 31, nv = nw * CT;
+  if (ALL || tid < CT) {
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
-      double s = 0.;
-      for (int t = sub; t < nv; t += 32) {
-        const int g = t / CT;   // warp index of partial t (its CRM lane is t % CT == sub % CT)
-        s += red[(g * NQ + q) * CT + lane];
-      }
-      for (int off = CT; off < 32; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      double s = red[q * CT + lane];
+      for (int g = 1; g < nw; g++) s += red[(g * NQ + q) * CT + lane];
       v[q] = s;
     }
   }
