@@ -205,3 +205,62 @@ def test_device_order_of_the_sedimentation_is_bit_identical(tmp_path):
         for x, y in zip(res[0], res[1]):
             assert np.array_equal(x, y)
         assert res[0][3][0] > 0. and np.abs(res[0][1]).max() > 0.
+
+
+def _polysvp_np(t, kind):
+    """module_mp_graupel.F90:5614-5673 written out with numpy: REAL(4) literals, FP64 Horner on dt = max(-80, t - 273.16), result of the
+    REAL FUNCTION rounded to single."""
+    a_i = [6.11147274, 0.503160820, 0.188439774e-1, 0.420895665e-3, 0.615021634e-5, 0.602588177e-7, 0.385852041e-9, 0.146898966e-11, 0.252751365e-14]
+    a_w = [6.11239921, 0.443987641, 0.142986287e-1, 0.264847430e-3, 0.302950461e-5, 0.206739458e-7, 0.640689451e-10, -0.952447341e-13,
+           -0.976195544e-15]
+    a = [float(f32(x)) for x in (a_i if kind == 1 else a_w)]
+    dt = max(float(f32(-80.)), t - float(f32(273.16)))
+    p = a[7] + a[8] * dt
+    for c in a[6::-1]:
+        p = c + dt * p
+    return float(f32(p * float(f32(100.))))
+
+
+def _satadj_np(tabs, qt, pres):
+    """MICRO_M2005/microphysics.F90:1435-1508 (satadj_liquid) for one level, from the Fortran.  Returns (tabs, qv, qc)."""
+    fac_cond = LCOND / CP
+    c622, c001 = float(f32(0.622)), float(f32(0.01))
+    tabs1 = tabs
+    esat1 = _polysvp_np(tabs1, 0)
+    qsat1 = c622 * esat1 / (pres - esat1)
+    if not qt > qsat1:
+        return tabs, qt, 0.
+    dtabs = fac_cond * max(0., qt - qsat1) / (1. + LCOND ** 2 * qsat1 / (CP * RV * tabs1 ** 2))
+    tabs1 = tabs1 + dtabs
+    niter = 1
+    thresh = min(c001, c001 * fac_cond * qsat1)
+    while abs(dtabs) > thresh and niter < 20:
+        esat1 = _polysvp_np(tabs1, 0)
+        qsat1 = c622 * esat1 / (pres - esat1)
+        fff = tabs - tabs1 + fac_cond * max(0., qt - qsat1)
+        dfff = 1. + LCOND ** 2 * qsat1 / (CP * RV * tabs1 ** 2)
+        dtabs = fff / dfff
+        tabs1 = tabs1 + dtabs
+        niter += 1
+    qc = max(0., tabs1 - tabs) / fac_cond
+    return tabs1, qt - qc, qc
+
+
+def test_polysvp_and_satadj_liquid_against_a_second_restatement():
+    """POLYSVP and satadj_liquid restated a second time in numpy from the Fortran: the shared C++ transcription (crm_m2005_col.h, used by
+    oracle AND device) must agree -- bit-identical for POLYSVP, to round-off for the Newton iteration of satadj_liquid."""
+    for t in np.linspace(180., 320., 281):
+        for kind in (0, 1):
+            assert L.crm_oracle_m2005_polysvp(float(t), kind) == _polysvp_np(float(t), kind), (t, kind)
+    rng = np.random.default_rng(7)
+    nsat = 0
+    for _ in range(400):
+        t0 = rng.uniform(245., 305.); pres = rng.uniform(3e4, 1.01e5)
+        qs0 = 0.622 * _polysvp_np(t0, 0) / (pres - _polysvp_np(t0, 0))
+        qt0 = qs0 * rng.uniform(0.4, 1.8)
+        t = C.c_double(t0); q = C.c_double(qt0); qc = C.c_double(-1.)
+        L.crm_oracle_m2005_satadj(C.byref(t), C.byref(q), C.byref(qc), pres)
+        t_r, q_r, qc_r = _satadj_np(t0, qt0, pres)
+        nsat += qc_r > 0.
+        assert abs(t.value - t_r) <= 1e-13 * t_r and abs(q.value - q_r) <= 1e-12 * q_r + 1e-20 and abs(qc.value - qc_r) <= 1e-10 * qc_r + 1e-18, (t0, qt0, pres)
+    assert 100 < nsat < 350
