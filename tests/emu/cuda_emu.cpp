@@ -5,8 +5,10 @@ thread_local emu_dim3 threadIdx, blockIdx;
 emu_dim3 blockDim, gridDim;
 pthread_barrier_t emu_barrier;
 char *emu_dyn_smem = nullptr;
-double emu_shfl_buf[2048];
-int emu_vote_buf[2048];
+double emu_shfl_buf[2][2048];
+int emu_vote_buf[2][2048];
+int emu_block_vote[2048];
+thread_local unsigned emu_xchg_phase = 0;
 pthread_barrier_t emu_warp_barrier[64];
 
 void emu_launch(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body) {

@@ -32,26 +32,26 @@ static inline void __syncthreads() { pthread_barrier_wait(&emu_barrier); }
 
 // warp primitives: emulated per warp of 32 consecutive threads (one pthread barrier per warp), so that warp-uniform
 // branches around shuffles/votes behave as on the device
-extern double emu_shfl_buf[2048];
-extern int emu_vote_buf[2048];
+// Exchange buffers are double-buffered by a per-thread phase counter, so one warp barrier per shuffle / vote suffices: a lane can only
+// overwrite a buffer two exchanges later, after every lane of the warp has passed the barrier of the exchange in between.
+extern double emu_shfl_buf[2][2048];
+extern int emu_vote_buf[2][2048];
 extern pthread_barrier_t emu_warp_barrier[64];
+extern thread_local unsigned emu_xchg_phase;
 static inline double __shfl_xor_sync(unsigned, double v, int lanemask) {
-  pthread_barrier_t *wb = &emu_warp_barrier[threadIdx.x >> 5];
-  emu_shfl_buf[threadIdx.x] = v;
-  pthread_barrier_wait(wb);
-  double r = emu_shfl_buf[threadIdx.x ^ (unsigned)lanemask];
-  pthread_barrier_wait(wb);
-  return r;
+  const unsigned ph = emu_xchg_phase++ & 1u;
+  emu_shfl_buf[ph][threadIdx.x] = v;
+  pthread_barrier_wait(&emu_warp_barrier[threadIdx.x >> 5]);
+  return emu_shfl_buf[ph][threadIdx.x ^ (unsigned)lanemask];
 }
 // integer shuffles (k_p8_micro's count scan); lanes outside the block keep their own value like an out-of-range source on the device
 static inline int emu_shfl_int(int v, int src_lane) {
-  pthread_barrier_t *wb = &emu_warp_barrier[threadIdx.x >> 5];
-  emu_vote_buf[threadIdx.x] = v;
-  pthread_barrier_wait(wb);
+  const unsigned ph = emu_xchg_phase++ & 1u;
+  emu_vote_buf[ph][threadIdx.x] = v;
+  pthread_barrier_wait(&emu_warp_barrier[threadIdx.x >> 5]);
   const unsigned w0 = threadIdx.x & ~31u;
   int r = v;
-  if (src_lane >= 0 && src_lane < 32 && w0 + (unsigned)src_lane < blockDim.x) r = emu_vote_buf[w0 + (unsigned)src_lane];
-  pthread_barrier_wait(wb);
+  if (src_lane >= 0 && src_lane < 32 && w0 + (unsigned)src_lane < blockDim.x) r = emu_vote_buf[ph][w0 + (unsigned)src_lane];
   return r;
 }
 static inline int __shfl_sync(unsigned, int v, int src_lane) { return emu_shfl_int(v, src_lane & 31); }
@@ -60,20 +60,20 @@ static inline int __shfl_up_sync(unsigned, int v, unsigned delta) {
   return emu_shfl_int(v, lane - (int)delta >= 0 ? lane - (int)delta : lane);
 }
 static inline unsigned __ballot_sync(unsigned, int pred) {
-  pthread_barrier_t *wb = &emu_warp_barrier[threadIdx.x >> 5];
-  emu_vote_buf[threadIdx.x] = pred != 0;
-  pthread_barrier_wait(wb);
+  const unsigned ph = emu_xchg_phase++ & 1u;
+  emu_vote_buf[ph][threadIdx.x] = pred != 0;
+  pthread_barrier_wait(&emu_warp_barrier[threadIdx.x >> 5]);
   unsigned r = 0;
   const unsigned w0 = threadIdx.x & ~31u;
-  for (unsigned l = 0; l < 32 && w0 + l < blockDim.x; l++) r |= (unsigned)emu_vote_buf[w0 + l] << l;
-  pthread_barrier_wait(wb);
+  for (unsigned l = 0; l < 32 && w0 + l < blockDim.x; l++) r |= (unsigned)emu_vote_buf[ph][w0 + l] << l;
   return r;
 }
+extern int emu_block_vote[2048];
 static inline int __syncthreads_or(int pred) {   // barrier + OR over the block (k_p1_forcing's negative-moisture vote)
-  emu_vote_buf[threadIdx.x] = pred != 0;
+  emu_block_vote[threadIdx.x] = pred != 0;
   pthread_barrier_wait(&emu_barrier);
   int r = 0;
-  for (unsigned t = 0; t < blockDim.x; t++) r |= emu_vote_buf[t];
+  for (unsigned t = 0; t < blockDim.x; t++) r |= emu_block_vote[t];
   pthread_barrier_wait(&emu_barrier);
   return r;
 }

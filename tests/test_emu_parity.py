@@ -59,7 +59,7 @@ def test_emu_sedimentation_subiterations(emu):
 def test_emu_sedimentation_fallback_in_kernel(emu, monkeypatch):
     # sub-iterations beyond the host's series of launches run inside the last launch
     monkeypatch.setenv("CRM_B200_PRECIP_LAUNCHES", "1")
-    dims = cm.small_dims(ncrms=6, nx=8, nzm=58, plev=72, nsteps=3)
+    dims = cm.small_dims(ncrms=6, nx=8, nzm=58, plev=72, nsteps=2)
     ro, rg = _check(emu, dims, 120, 1e-11)
     assert ro[3]["nprec_max"] >= 2
 
@@ -75,8 +75,8 @@ def _dims3d(ncrms, nx, ny, nsteps, **kw):
 
 
 def test_emu_3d_ab3_and_padding(emu):
-    # 3-D CRM 8x8x28 (tile of 4 CRMs, 256 emulated threads), four steps (AB1..AB3), 5 CRMs -> padded second tile
-    ro, rg = _check(emu, _dims3d(5, 8, 8, 4), 40, 1e-11)
+    # 3-D CRM 8x8x28 (tile of 4 CRMs, 256 emulated threads), three steps (AB1..AB3), 5 CRMs -> padded second tile
+    ro, rg = _check(emu, _dims3d(5, 8, 8, 3), 40, 1e-11)
     assert np.abs(rg[0].v_wind).max() > 0
 
 
@@ -88,7 +88,7 @@ def test_emu_3d_rectangular_setperturb(emu, monkeypatch):
 
 def test_emu_m2005_two_moment_microphysics(emu):
     # micro = 1: ten advected/diffused micro fields, the column scheme of crm_m2005_col.h per thread, m2005 outputs
-    dims = cm.pkg.CrmDims(ncrms=5, nx=8, ny=1, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=20.0 * 3, igstep=3, micro=1)
+    dims = cm.pkg.CrmDims(ncrms=5, nx=8, ny=1, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=20.0 * 2, igstep=3, micro=1)
     ro, rg = _check(emu, dims, 90, 1e-11)
     assert ro[2].qs_mean.max() > 0 and ro[2].nc_mean.max() > 0 and ro[0].qr.max() > 0   # rain, snow and droplets exist: the scheme is exercised
 
@@ -102,7 +102,7 @@ def test_emu_per_phase_intermediate_state(emu, stop):
         assert err <= 1e-12 or err * scale < 1e-18, (stop, name, err, scale)
 
 
-@pytest.mark.parametrize("stop", [1, 3, 4, 6, 8])
+@pytest.mark.parametrize("stop", [3, 4, 8])      # the GPU suite runs 1, 3, 4, 6, 8
 def test_emu_per_phase_intermediate_state_3d(emu, stop):
     dims = cm.pkg.CrmDims(ncrms=2, nx=8, ny=8, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=20.0, igstep=3, nx_rad=2, ny_rad=2)
     dims, inp, st, rad = cm.make_case(dims, spinup_steps=40)
