@@ -1013,6 +1013,28 @@ extern "C" int crm_oracle_test_diffuse_scalar3d(int nx, int ny, int nzm, double 
   return 0;
 }
 
+// Mean-state acceleration (accelerate_crm.F90:109-352) of one 2-D CRM: means t0, q0, u0 (nzm) from the start of the step; t, qt, u, qv, qcl,
+// qci (nx, nzm) in/out.  Returns 1 if the |dT| > 5 K guard fired (nothing applied), else 0.
+extern "C" int crm_oracle_test_accelerate(int nx, int nzm, int accel_uv, double accel_factor, const double *t0, const double *q0, const double *u0,
+                                          double *t, double *qt, double *u, double *qv, double *qcl, double *qci) {
+  Geo g; g.nx = nx; g.ny = 1; g.nzm = nzm; g.nz = nzm + 1; g.plev = nzm; g.YES3D = 0; g.RUN3D = false; g.nx_rad = 1; g.ny_rad = 1; g.dx = g.dy = 1000.;
+  Crm c; alloc_crm(g, c);
+  for (int k = 1; k <= nzm; k++) { c.t0(k) = t0[k - 1]; c.q0(k) = q0[k - 1]; c.u0(k) = u0[k - 1]; c.v0(k) = 0.; }
+  for (int k = 1; k <= nzm; k++)
+    for (int i = 1; i <= nx; i++) {
+      const size_t o = (size_t)(i - 1) + (size_t)nx * (k - 1);
+      c.t(i, 1, k) = t[o]; c.qt(i, 1, k) = qt[o]; c.u(i, 1, k) = u[o]; c.qv(i, 1, k) = qv[o]; c.qcl(i, 1, k) = qcl[o]; c.qci(i, 1, k) = qci[o];
+    }
+  if (accelerate_part1(g, c, accel_uv != 0)) return 1;
+  accelerate_part2(g, c, accel_uv != 0, accel_factor);
+  for (int k = 1; k <= nzm; k++)
+    for (int i = 1; i <= nx; i++) {
+      const size_t o = (size_t)(i - 1) + (size_t)nx * (k - 1);
+      t[o] = c.t(i, 1, k); qt[o] = c.qt(i, 1, k); u[o] = c.u(i, 1, k); qv[o] = c.qv(i, 1, k); qcl[o] = c.qcl(i, 1, k); qci[o] = c.qci(i, 1, k);
+    }
+  return 0;
+}
+
 // ice_fall (ice_fall.F90) and damping (damping.F90) of one 2-D CRM (test hook for tests/test_second_restatement.py).
 // which = 1 ice_fall: reads qcl, qci, tabs; qt, t in/out; prof = [qifall(nzm), tlatqi(nzm)], col = precsfc (nx).
 // which = 2 damping:  reads u, w, qv, qv0, z; qt, t in/out; dudt (nx, nzm), dwdt (nx, nzm+1) out (from zero).

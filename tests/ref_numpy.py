@@ -1245,3 +1245,48 @@ def crm_outputs_one_step(g, plev, dt_gl, inp, tabs_in, qp_in, u, v, w, tabs, qv,
     res.update(mu_crm=mu, md_crm=md, eu_crm=eu, du_crm=du, ed_crm=ed, jt_crm=jt, mx_crm=mx)
     res["rad"] = rad
     return res
+
+
+def accelerate_crm_2d(t, qt, u, qv, qcl, qci, t0, q0, u0, accel_uv, accel_factor):
+    """accelerate_crm.F90:166-345 (mean-state acceleration, Jones et al. 2015) for one 2-D CRM; arrays (nx, nzm).  Returns
+    (ceaseflag, t, qt, u, qv, qcl, qci)."""
+    nx, nzm = t.shape
+    coef = 1. / float(nx)
+    t, qt, u, qv, qcl, qci = (a.copy() for a in (t, qt, u, qv, qcl, qci))
+    tt = np.zeros(nzm); qq = np.zeros(nzm); uu = np.zeros(nzm)
+    for k in range(nzm):
+        tb = qb = ub = 0.
+        for i in range(nx):
+            tb = tb + t[i, k] * coef
+            qb = qb + (qcl[i, k] + qci[i, k] + qv[i, k]) * coef
+            ub = ub + u[i, k] * coef
+        tt[k] = tb - t0[k]; qq[k] = qb - q0[k]; uu[k] = ub - u0[k]
+    if (np.abs(tt) > f4(5.)).any():
+        return True, t, qt, u, qv, qcl, qci
+    for k in range(nzm):
+        t[:, k] = np.maximum(f4(50.), t[:, k] + accel_factor * tt[k])
+        if accel_uv:
+            u[:, k] = u[:, k] + accel_factor * uu[k]
+        qt[:, k] = qt[:, k] + accel_factor * qq[k]
+        qpoz = qneg = 0.
+        for i in range(nx):
+            if qt[i, k] < 0.:
+                qneg = qneg + qt[i, k]
+            else:
+                qpoz = qpoz + qt[i, k]
+        for i in range(nx):
+            if qpoz + qneg <= 0.:
+                qt[i, k] = 0.; qv[i, k] = 0.; qcl[i, k] = 0.; qci[i, k] = 0.
+            else:
+                factor = 1. + qneg / qpoz
+                qt[i, k] = max(0., qt[i, k] * factor)
+                if qt[i, k] <= 0.:
+                    qv[i, k] = 0.; qcl[i, k] = 0.; qci[i, k] = 0.
+                else:
+                    qt_res = qt[i, k] - qcl[i, k] - qci[i, k]
+                    qv[i, k] = max(0., qt_res)
+                    if qt_res < 0.:
+                        factor = 1. + qt_res / (qcl[i, k] + qci[i, k])
+                        qcl[i, k] = qcl[i, k] * factor
+                        qci[i, k] = qci[i, k] * factor
+    return False, t, qt, u, qv, qcl, qci

@@ -388,3 +388,38 @@ def test_crm_module_grid_statistics_and_epilogue_against_second_restatement(ny):
             assert _close(r["rad"][n], getattr(rad, n)[ic], 1e-13, floor=1e-30), (ic, n)
     assert checked > 10 * dims.ncrms          # clouds, updraughts and precipitation are present in the spun-up state
     assert float(out.cld.max()) > 0 and float(np.abs(out.mu_crm).max()) > 0
+
+
+def test_accelerate_crm_against_second_restatement():
+    """Mean-state acceleration (accelerate_crm.F90): tendencies of the horizontal means applied crm_accel_factor times, the moisture
+    redistribution with all of its branches (level emptied, cell clipped, condensate rescaled), and the |dT| > 5 K guard."""
+    rng = np.random.default_rng(51)
+    nx, nzm = 16, 20
+    z = np.linspace(100., 14000., nzm)
+    t = 300. + 3e-3 * z[None, :] + rng.standard_normal((nx, nzm))
+    qv = 1.2e-2 * np.exp(-z / 2500.)[None, :] * rng.uniform(0.4, 1.6, (nx, nzm))
+    qcl = np.where(rng.uniform(size=(nx, nzm)) < 0.3, rng.uniform(0., 1e-3, (nx, nzm)), 0.); qci = 0.3 * qcl[::-1]
+    qt = qv + qcl + qci
+    u = 5. + rng.standard_normal((nx, nzm))
+    t0 = t.mean(axis=0) - rng.uniform(-0.2, 0.2, nzm)
+    q0 = (qv + qcl + qci).mean(axis=0) * rng.uniform(0.9, 1.1, nzm)
+    q0[-1] = 5. * (qv + qcl + qci)[:, -1].mean()              # strong drying at the top level: the whole level is emptied
+    m2 = qt[:, -2].mean()                                     # level nzm-1: half of the cells hold 0.2 m, half 1.8 m -> the dry half goes negative
+    qt[:, -2] = np.where(np.arange(nx) % 2 == 0, 0.2, 1.8) * m2
+    qci[:, -2] = 0.; qcl[:, -2] = 0.9 * qt[:, -2]; qv[:, -2] = qt[:, -2] - qcl[:, -2]
+    q0[-2] = 1.25 * m2                                        # redistribution + condensate rescaling (qt_res < 0 in the kept cells)
+    u0 = u.mean(axis=0) + 0.1
+    A = np.asfortranarray
+    for uv, fac, t0x, expect in ((1, 2., t0, 0), (0, 3., t0, 0), (1, 2., t0 + 6., 1)):
+        arrs = [A(a.copy()) for a in (t, qt, u, qv, qcl, qci)]
+        rc = L.crm_oracle_test_accelerate(nx, nzm, uv, C.c_double(fac), P(t0x), P(q0), P(u0), *[P(a) for a in arrs])
+        cease, *ref = rn.accelerate_crm_2d(t, qt, u, qv, qcl, qci, t0x, q0, u0, bool(uv), fac)
+        assert rc == expect == int(cease)
+        if not cease:
+            for a, b, n in zip(arrs, ref, "t qt u qv qcl qci".split()):
+                assert _close(b, a, 1e-14), (uv, n)
+            assert np.all(arrs[1][:, -1] == 0.) and np.all(arrs[3][:, -1] == 0.)        # emptied level
+            assert (arrs[1][:, -2] == 0.).any() and (arrs[1][:, -2] > 0.).any()           # clipped cells next to kept ones
+            assert (arrs[4][:, -2] < qcl[:, -2] - 1e-9).any()                             # condensate rescaled where qt_res < 0
+            if not uv:
+                assert np.array_equal(arrs[2], u)
