@@ -1013,6 +1013,23 @@ extern "C" int crm_oracle_test_diffuse_scalar3d(int nx, int ny, int nzm, double 
   return 0;
 }
 
+// setperturb (setperturb.F90:7-79) of one CRM: t (nx, ny, nzm) in/out, t0 (nzm) the level means before the perturbation, seeded like
+// crm_module.F90:679 (iseed = gcol * 1000 is the caller's business).
+extern "C" int crm_oracle_test_setperturb(int nx, int ny, int nzm, int iseed, const double *t0, double *t) {
+  Geo g; g.nx = nx; g.ny = ny; g.nzm = nzm; g.nz = nzm + 1; g.plev = nzm; g.YES3D = ny > 1 ? 1 : 0; g.RUN3D = ny > 1; g.nx_rad = 1; g.ny_rad = 1; g.dx = g.dy = 1000.;
+  Crm c; alloc_crm(g, c);
+  for (int k = 1; k <= nzm; k++) {
+    c.t0(k) = t0[k - 1];
+    for (int j = 1; j <= ny; j++)
+      for (int i = 1; i <= nx; i++) c.t(i, j, k) = t[(size_t)(i - 1) + (size_t)nx * ((j - 1) + (size_t)ny * (k - 1))];
+  }
+  setperturb(g, c, iseed);
+  for (int k = 1; k <= nzm; k++)
+    for (int j = 1; j <= ny; j++)
+      for (int i = 1; i <= nx; i++) t[(size_t)(i - 1) + (size_t)nx * ((j - 1) + (size_t)ny * (k - 1))] = c.t(i, j, k);
+  return 0;
+}
+
 // Mean-state acceleration (accelerate_crm.F90:109-352) of one 2-D CRM: means t0, q0, u0 (nzm) from the start of the step; t, qt, u, qv, qcl,
 // qci (nx, nzm) in/out.  Returns 1 if the |dT| > 5 K guard fired (nothing applied), else 0.
 extern "C" int crm_oracle_test_accelerate(int nx, int nzm, int accel_uv, double accel_factor, const double *t0, const double *q0, const double *u0,

@@ -423,3 +423,32 @@ def test_accelerate_crm_against_second_restatement():
             assert (arrs[4][:, -2] < qcl[:, -2] - 1e-9).any()                             # condensate rescaled where qt_res < 0
             if not uv:
                 assert np.array_equal(arrs[2], u)
+
+
+@pytest.mark.parametrize("ny", [1, 8])
+def test_setperturb_against_second_restatement(ny):
+    """setperturb.F90: Mersenne-Twister noise (the Python restatement of RNG_MT.F90) on the five lowest levels, amplitude decreasing with
+    height, j outer / i inner draw order, level means restored by the t0/t02 scaling."""
+    import test_oracle_kat as tk
+    rng = np.random.default_rng(61)
+    nx, nzm, seed = 16, 12, 48602 * 1000
+    t = 300. + rng.standard_normal((nx, ny, nzm)) + np.linspace(0., 30., nzm)[None, None, :]
+    t0 = t.mean(axis=(0, 1))
+    t_o = np.asfortranarray(t.copy())
+    assert L.crm_oracle_test_setperturb(nx, ny, nzm, seed, P(t0), P(t_o)) == 0
+    r = tk._rng_mt_python(seed, 5 * nx * ny)
+    ref = t.copy()
+    factor_xy = 1. / float(nx * ny)
+    n = 0
+    for k in range(5):
+        scal = float(5 + 1 - (k + 1)) / float(5)
+        t02 = 0.
+        for j in range(ny):
+            for i in range(nx):
+                ref[i, j, k] = ref[i, j, k] + 1 * (1. - 2. * r[n]) * scal
+                n += 1
+                t02 = t02 + ref[i, j, k] * factor_xy
+        ref[:, :, k] = ref[:, :, k] * t0[k] / t02
+    assert np.array_equal(ref, t_o)
+    assert np.array_equal(t_o[:, :, 5:], t[:, :, 5:]) and np.abs(t_o[:, :, 0] - t[:, :, 0]).max() > 0.5
+    assert np.abs(t_o[:, :, :5].mean(axis=(0, 1)) - t0[:5]).max() < 1e-12
