@@ -264,3 +264,58 @@ def test_polysvp_and_satadj_liquid_against_a_second_restatement():
         nsat += qc_r > 0.
         assert abs(t.value - t_r) <= 1e-13 * t_r and abs(q.value - q_r) <= 1e-12 * q_r + 1e-20 and abs(qc.value - qc_r) <= 1e-10 * qc_r + 1e-18, (t0, qt0, pres)
     assert 100 < nsat < 350
+
+
+def test_column_kk2000_accretion_known_answer():
+    """A warm saturated layer with cloud water AND rain: accretion PRA = 67 (qc qr)^1.15 (module_mp_graupel.F90:2187-2188, Khairoutdinov and
+    Kogan 2000) next to the autoconversion of the previous test; REAL(4) literals 67. and 1.15."""
+    nz, dt = 20, 10.
+    st, inp, qvs = _atmosphere(nz, rh=0.95)
+    k = 5
+    st[QV, k] = qvs[k]; st[QC, k] = 8e-4; st[NC, k] = 100.e6; st[QR, k] = 3e-4; st[NR, k] = 2.e4
+    out, sed, rates, prec = _column(nz, dt, st.copy(), inp)
+    pra = float(f32(67.)) * (st[QC, k] * st[QR, k]) ** float(f32(1.15))
+    rho = inp[1, k]
+    prc = float(f32(1350.)) * st[QC, k] ** float(f32(2.47)) * (st[NC, k] / 1.e6 * rho) ** float(f32(-1.79))
+    assert abs(rates[1, k] / pra - 1.) < 1e-12 and abs(rates[0, k] / prc - 1.) < 1e-12
+    assert pra > 10. * prc                                              # rain collects far faster than droplets coalesce here
+    # cloud water of the layer: only autoconversion + accretion remove it (saturated, no sedimentation of droplets out of a 400 m layer in 10 s
+    # beyond the flux the scheme reports in sed[]) -- total water is conserved
+    w = inp[1] * inp[2]
+    water0 = (w * (st[QV] + st[QC] + st[QR])).sum(); water1 = (w * (out[QV] + out[QC] + out[QR] + out[QI] + out[QNI] + out[QG])).sum()
+    assert abs((water0 - water1) - prec[0]) < 1e-9 * water0
+
+
+def test_column_instantaneous_melting_and_homogeneous_freezing():
+    """The instantaneous processes at the end of the scheme (module_mp_graupel.F90:5284-5335): cloud ice in air warmer than TMELT melts to rain
+    completely (mass to QR, number to NR, the melted mass is what the MLT diagnostic reports); cloud water colder than 233.15 K freezes to
+    cloud ice completely (QC = NC = 0)."""
+    nz, dt = 40, 10.
+    st, inp, qvs = _atmosphere(nz, rh=0.9)
+    warm = np.nonzero(st[T3] > 276.)[0]
+    kw = warm[-3:]                                                       # three warm levels well above the ground
+    st[QI, kw] = 2e-4; st[NI, kw] = 5e4
+    out, sed, rates, prec = _column(nz, dt, st.copy(), inp)
+    w = inp[1] * inp[2]
+    assert np.all(out[QI, warm] == 0.) and np.all(out[NI, warm] == 0.)  # (cold, ice-supersaturated levels far above nucleate their own ice)
+    melted = (rates[4, warm] * w[warm]).sum() * dt
+    assert abs(melted / (st[QI] * w).sum() - 1.) < 1e-9                  # every gram of ice shows up in the melting diagnostic
+    assert abs(((out[QR] + out[QV] - st[QV])[warm] * w[warm]).sum() + prec[0] - (st[QI] * w).sum()) < 1e-9 * (st[QI] * w).sum()   # then as rain / vapour
+    assert out[T3, kw[1]] < st[T3, kw[1]]                                # latent cooling
+    # homogeneous freezing
+    st2, inp2, qvs2 = _atmosphere(nz, rh=0.9)
+    cold = np.nonzero(st2[T3] < 232.)[0]
+    if cold.size == 0:                                                   # the 16 km column of _atmosphere does not reach 232 K: cool its top
+        st2[T3, -4:] = 230.
+        cold = np.arange(nz - 4, nz)
+    kc = cold[:2]
+    for kk in kc:
+        es = L.crm_oracle_m2005_polysvp(float(st2[T3, kk]), 0)
+        st2[QV, kk] = RGAS / RV * es / (inp2[0, kk] - es)
+    st2[QC, kc] = 1e-5; st2[NC, kc] = 5e6
+    out2, _, rates2, _ = _column(nz, dt, st2.copy(), inp2)
+    assert np.all(out2[QC, kc] == 0.) and np.all(out2[NC, kc] == 0.)
+    assert np.all(out2[QI, kc] + out2[QNI, kc] > 0.)
+    w2 = inp2[1] * inp2[2]
+    tot0 = (w2 * (st2[QV] + st2[QC])).sum(); tot1 = (w2 * (out2[QV] + out2[QC] + out2[QI] + out2[QNI] + out2[QG] + out2[QR])).sum()
+    assert abs(tot0 - tot1) < 1e-9 * tot0
