@@ -319,3 +319,47 @@ def test_column_instantaneous_melting_and_homogeneous_freezing():
     w2 = inp2[1] * inp2[2]
     tot0 = (w2 * (st2[QV] + st2[QC])).sum(); tot1 = (w2 * (out2[QV] + out2[QC] + out2[QI] + out2[QNI] + out2[QG] + out2[QR])).sum()
     assert abs(tot0 - tot1) < 1e-9 * tot0
+
+
+def test_column_rain_sedimentation_at_the_fall_speed_cap():
+    """Big drops (few, heavy): the mass-weighted rain fall speed ARN CONS4 / LAMR^BR exceeds its cap, so it IS the cap 9.1 (RHOSU/rho)^0.54
+    (module_mp_graupel.F90:2111-2113, 4905-4943), and one sedimentation sub-step (:5009-5075) moves FR rho qr dt / dz out of the layer into
+    the one below -- a closed form independent of the size-distribution code.  Saturated air: no evaporation; no cloud water: no accretion."""
+    nz, dt = 20, 10.
+    st, inp, qvs = _atmosphere(nz, rh=0.95)
+    k = 6
+    for kk in (k - 1, k):
+        st[QV, kk] = qvs[kk]
+    qr = 1.0e-3
+    st[QR, k] = qr; st[NR, k] = 100.
+    out, sed, rates, prec = _column(nz, dt, st.copy(), inp)
+    rho, dz = inp[1], inp[2]
+    rhosu = float(f32(85000.)) / (RGAS * float(f32(273.15)))
+    assert abs(L.crm_oracle_m2005_const(102) / rhosu - 1.) < 1e-15
+    fr = float(f32(9.1)) * (rhosu / rho[k]) ** float(f32(0.54))
+    assert fr * dt / dz[k] < 1.                                          # one sub-step (NSTEP = 1)
+    assert abs(out[QR, k] / (qr * (1. - fr * dt / dz[k])) - 1.) < 1e-12
+    assert abs(out[QR, k - 1] / (fr * rho[k] * qr * dt / (dz[k - 1] * rho[k - 1])) - 1.) < 1e-12
+    assert prec[0] == 0. and np.all(out[QR, :k - 1] == 0.) and np.all(out[QR, k + 1:] == 0.)
+    assert abs(((out[QR] - st[QR]) * rho * dz).sum()) < 1e-12 * qr * rho[k] * dz[k]      # rain mass conserved by the flux form
+    assert out[QV, k] == st[QV, k] and rates[3, k] == 0.                # no evaporation in saturated air
+
+
+def test_column_snow_sedimentation_at_the_fall_speed_cap():
+    """The same for snow: few large flakes (slope parameter at its lower bound) fall at the cap 1.2 (RHOSU/rho)^0.54 (module_mp_graupel.F90:
+    2108-2110); in ice-saturated air without cloud water, cloud ice or rain nothing else changes the snow mass."""
+    nz, dt = 30, 10.
+    st, inp, qvs = _atmosphere(nz, rh=0.3)
+    k = int(np.nonzero(st[T3] < 255.)[0][0]) + 1
+    for kk in (k - 1, k):
+        ei = L.crm_oracle_m2005_polysvp(float(st[T3, kk]), 1)
+        st[QV, kk] = RGAS / RV * ei / (inp[0, kk] - ei)
+    qs = 8.0e-4
+    st[QNI, k] = qs; st[NS, k] = 20.
+    out, sed, rates, prec = _column(nz, dt, st.copy(), inp)
+    rho, dz = inp[1], inp[2]
+    rhosu = float(f32(85000.)) / (RGAS * float(f32(273.15)))
+    fs = float(f32(1.2)) * (rhosu / rho[k]) ** float(f32(0.54))
+    assert abs(out[QNI, k] / (qs * (1. - fs * dt / dz[k])) - 1.) < 1e-9, (out[QNI, k], qs * (1. - fs * dt / dz[k]))
+    assert abs(out[QNI, k - 1] / (fs * rho[k] * qs * dt / (dz[k - 1] * rho[k - 1])) - 1.) < 1e-9
+    assert abs(((out[QNI] - st[QNI]) * rho * dz).sum()) < 1e-9 * qs * rho[k] * dz[k]
