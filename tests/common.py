@@ -140,6 +140,16 @@ def resident_case(dims, lib_path=None, device=0, ncalls=2):
     assert h.history_field(lchnk + 1, dims, "CRM_T").shape == st.temperature.shape        # state fields are always available
     h.resident_drop(lchnk + 1)
     assert h.resident_field(lchnk + 1, "qt") is None and h.resident_field(lchnk, "qrad")
+    # error behaviour: every refusal names its reason and leaves the resident chunks alone
+    for call, code in ((lambda: h.resident_put(-3, dims, st, rad), "(55)"), (lambda: h.resident_run(lchnk + 1, dims, inp), "(53)"),
+                       (lambda: h.resident_get(99, dims, st_r, None), "(53)"), (lambda: h.history_field(lchnk, dims, "CRM_XYZ"), "(59)"),
+                       (lambda: h.resident_run(lchnk, dims.copy(ncrms=dims.ncrms - 1), inp), "(51)"), (lambda: h.resident_drop(99), "(53)")):
+        try:
+            call()
+            raise AssertionError("expected a refusal " + code)
+        except libmod.CrmB200Error as e:
+            assert code in str(e), (code, str(e))
+    assert h.resident_bytes() > 0
     h.resident_drop(-1)
     assert h.resident_bytes() == 0
     h.close()
