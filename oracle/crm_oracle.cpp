@@ -1013,6 +1013,40 @@ extern "C" int crm_oracle_test_diffuse_scalar3d(int nx, int ny, int nzm, double 
   return 0;
 }
 
+// pressure (press_rhs.F90 + pressure.F90 + press_grad.F90) of one 2-D CRM with FP64 trig tables: u (nx, nzm), w (nx, nzm+1), the three
+// Adams-Bashforth tendency slots dudt[3] (nx, nzm) and dwdt[3] (nx, nzm+1) in the order na, nb, nc (slot na in/out), coef = {at, bt, ct,
+// dt3(na)}; p (nx, nzm) out.
+extern "C" int crm_oracle_test_pressure2d(int nx, int nzm, double dx, double dz, const double *adz, const double *adzw, const double *rho,
+                                          const double *rhow, const double *coef, const double *u, const double *w, double *dudt, double *dwdt,
+                                          double *pout) {
+  Geo g; g.nx = nx; g.ny = 1; g.nzm = nzm; g.nz = nzm + 1; g.plev = nzm; g.YES3D = 0; g.RUN3D = false; g.nx_rad = 1; g.ny_rad = 1; g.dx = g.dy = dx;
+  Crm c; alloc_crm(g, c);
+  Step s; s.na = 1; s.nb = 2; s.nc = 3; s.at = coef[0]; s.bt = coef[1]; s.ct = coef[2]; s.dt3[1] = coef[3]; s.dt3[2] = coef[3]; s.dt3[3] = coef[3];
+  c.dz = dz;
+  for (int k = 1; k <= nzm + 1; k++) { c.adzw(k) = adzw[k - 1]; c.rhow(k) = rhow[k - 1]; if (k <= nzm) { c.adz(k) = adz[k - 1]; c.rho(k) = rho[k - 1]; } }
+  const size_t n2 = (size_t)nx * nzm, n3 = (size_t)nx * (nzm + 1);
+  for (int k = 1; k <= nzm + 1; k++)
+    for (int i = 1; i <= nx; i++) {
+      const size_t o = (size_t)(i - 1) + (size_t)nx * (k - 1);
+      c.w(i, 1, k) = w[o];
+      for (int q = 0; q < 3; q++) c.dwdt[q + 1](i, 1, k) = dwdt[q * n3 + o];
+      if (k <= nzm) { c.u(i, 1, k) = u[o]; for (int q = 0; q < 3; q++) c.dudt[q + 1](i, 1, k) = dudt[q * n2 + o]; }
+    }
+  boundaries(g, c, 0);
+  // the nb / nc slots carry the periodic image dudt(nx+1) = dudt(1) that bound_duvdt gave them when they were the na slot of earlier steps
+  for (int q = 2; q <= 3; q++)
+    for (int k = 1; k <= nzm; k++) c.dudt[q](nx + 1, 1, k) = c.dudt[q](1, 1, k);
+  FftPlan fx, fy; fx.init(nx, false); fy.init(2, false);
+  pressure(g, c, s, fx, fy);
+  for (int k = 1; k <= nzm + 1; k++)
+    for (int i = 1; i <= nx; i++) {
+      const size_t o = (size_t)(i - 1) + (size_t)nx * (k - 1);
+      dwdt[o] = c.dwdt[1](i, 1, k);
+      if (k <= nzm) { dudt[o] = c.dudt[1](i, 1, k); pout[o] = c.p(i, 1, k); }
+    }
+  return 0;
+}
+
 // setperturb (setperturb.F90:7-79) of one CRM: t (nx, ny, nzm) in/out, t0 (nzm) the level means before the perturbation, seeded like
 // crm_module.F90:679 (iseed = gcol * 1000 is the caller's business).
 extern "C" int crm_oracle_test_setperturb(int nx, int ny, int nzm, int iseed, const double *t0, double *t) {

@@ -1290,3 +1290,47 @@ def accelerate_crm_2d(t, qt, u, qv, qcl, qci, t0, q0, u0, accel_uv, accel_factor
                         qcl[i, k] = qcl[i, k] * factor
                         qci[i, k] = qci[i, k] * factor
     return False, t, qt, u, qv, qcl, qci
+
+
+def pressure_2d(u, w, dudt, dwdt, coef, dx, dz, rho, rhow, adz, adzw):
+    """press_rhs.F90:85-105 + the Poisson problem of pressure.F90:152-262 + press_grad.F90:19-42 for one 2-D CRM -- solved ANOTHER way: the
+    reference transforms in x (FFT99) and solves one tridiagonal system per wavenumber (Thomas); here the same discrete operator is
+    assembled in physical space as one dense (nx*nzm)^2 matrix and handed to numpy.linalg.solve.  The mean mode's regularisation of the
+    Fortran (the extra -a(1) on the diagonal of level 1 for wavenumber 0, :209-213) is the rank-one term on the x-mean of level 1.
+    dudt, dwdt: lists of the three Adams-Bashforth slots [na, nb, nc]; coef = (at, bt, ct, dt3(na)).  Returns (dudt_na, dwdt_na, p'/1 * rho)."""
+    nx, nzm = u.shape
+    at, bt, ct, dt3 = coef
+    rdx = 1. / dx
+    btat, ctat = bt / at, ct / at
+    dta = 1. / dt3 / at
+    rhs = np.zeros((nx, nzm))
+    for k in range(nzm):
+        rdz = 1. / (adz[k] * dz)
+        rup = rhow[k + 1] / rho[k] * rdz; rdn = rhow[k] / rho[k] * rdz
+        div = lambda uu, ww: rdx * (np.roll(uu[:, k], -1) - uu[:, k]) + (ww[:, k + 1] * rup - ww[:, k] * rdn)
+        rhs[:, k] = (div(u, w) * dta + div(dudt[0], dwdt[0]) + btat * div(dudt[1], dwdt[1]) + ctat * div(dudt[2], dwdt[2])) * rho[k]
+    a = rhow[:nzm] / (adz * adzw[:nzm] * dz * dz)
+    c = rhow[1:] / (adz * adzw[1:] * dz * dz)
+    n = nx * nzm
+    A = np.zeros((n, n))
+    idx = lambda i, k: (i % nx) + nx * k
+    ddx2 = 1. / (dx * dx)
+    for k in range(nzm):
+        for i in range(nx):
+            r = idx(i, k)
+            A[r, idx(i + 1, k)] += rho[k] * ddx2; A[r, idx(i - 1, k)] += rho[k] * ddx2; A[r, r] += -2. * rho[k] * ddx2
+            if k > 0:
+                A[r, idx(i, k - 1)] += a[k]; A[r, r] -= a[k]
+            if k < nzm - 1:
+                A[r, idx(i, k + 1)] += c[k]; A[r, r] -= c[k]
+            if k == 0:                                         # wavenumber 0 only: -a(1) on the diagonal
+                for ii in range(nx):
+                    A[r, idx(ii, 0)] -= a[0] / nx
+    p = np.linalg.solve(A, rhs.ravel(order="F")).reshape((nx, nzm), order="F")
+    du = dudt[0].copy(); dw = dwdt[0].copy()
+    for k in range(nzm):
+        kb = max(0, k - 1)
+        rdz = 1. / (dz * adzw[k])
+        du[:, k] = du[:, k] - (p[:, k] - np.roll(p[:, k], 1)) * rdx
+        dw[:, k] = dw[:, k] - (p[:, k] - p[:, kb]) * rdz
+    return du, dw, p * rho[None, :]

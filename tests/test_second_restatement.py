@@ -452,3 +452,25 @@ def test_setperturb_against_second_restatement(ny):
     assert np.array_equal(ref, t_o)
     assert np.array_equal(t_o[:, :, 5:], t[:, :, 5:]) and np.abs(t_o[:, :, 0] - t[:, :, 0]).max() > 0.5
     assert np.abs(t_o[:, :, :5].mean(axis=(0, 1)) - t0[:5]).max() < 1e-12
+
+
+def test_pressure_solve_against_a_dense_physical_space_solve():
+    """press_rhs + pressure + press_grad: the oracle's FFT99 + Thomas solution against numpy.linalg.solve on the same discrete operator assembled
+    in physical space (no transform, no tridiagonal sweep), AB3 coefficients, stretched grid."""
+    rng = np.random.default_rng(71)
+    nx, nzm, dx, dz, adz, adzw, z, rho, rhow, grdf_x, grdf_z = _grid_2d(rng, nx=16, nzm=18)
+    u = 5. + 2. * rng.standard_normal((nx, nzm)); w = np.zeros((nx, nzm + 1)); w[:, 1:nzm] = rng.standard_normal((nx, nzm - 1))
+    dudt = [1e-2 * rng.standard_normal((nx, nzm)) for _ in range(3)]
+    dwdt = []
+    for _ in range(3):
+        d = np.zeros((nx, nzm + 1)); d[:, 1:nzm] = 1e-2 * rng.standard_normal((nx, nzm - 1)); dwdt.append(d)
+    coef = np.array([23. / 12., -16. / 12., 5. / 12., 10.])
+    A = np.asfortranarray
+    du_o = np.concatenate([A(x).ravel(order="F") for x in dudt]); dw_o = np.concatenate([A(x).ravel(order="F") for x in dwdt])
+    p_o = A(np.zeros((nx, nzm)))
+    rc = L.crm_oracle_test_pressure2d(nx, nzm, C.c_double(dx), C.c_double(dz), P(adz), P(adzw), P(rho), P(rhow), P(coef), P(A(u)), P(A(w)), P(du_o), P(dw_o), P(p_o))
+    assert rc == 0
+    du_r, dw_r, p_r = rn.pressure_2d(u, w, dudt, dwdt, tuple(coef), dx, dz, rho, rhow, adz, adzw)
+    du = du_o[:nx * nzm].reshape((nx, nzm), order="F"); dw = dw_o[:nx * (nzm + 1)].reshape((nx, nzm + 1), order="F")
+    assert np.abs(du - dudt[0]).max() > 1e-3                      # the pressure gradient really acts
+    assert _close(p_r, p_o, 1e-9) and _close(du_r, du, 1e-9) and _close(dw_r[:, 1:nzm], dw[:, 1:nzm], 1e-9)
