@@ -16,6 +16,14 @@ profiles/r02_fortran_probe_gpu_box.txt).
   SGS_TKE/diffuse_mom2D.F90:38-156        diffuse_mom_2d
   SGS_TKE/diffuse_scalar2D.F90:81-139     diffuse_scalar_2d
   buoyancy.F90:16-36                      buoyancy_2d
+  ice_fall.F90:29-164, damping.F90:40-112, forcing.F90:27-62, kurant.F90:31-55 + sgs.F90:343-365
+                                          ice_fall_2d, damping_2d, forcing_2d, kurant_2d
+  accelerate_crm.F90:166-345              accelerate_crm_2d
+  press_rhs.F90 + pressure.F90 + press_grad.F90   pressure_2d (dense physical-space solve instead of FFT99 + Thomas)
+  ADV_MPDATA/advect_scalar3D.F90, advect2_mom_xy/z (RUN3D), SGS_TKE/diffuse_mom3D.F90, diffuse_scalar3D.F90, shear_prod3D.F90
+                                          advect_scalar3d, advect_mom_3d, diffuse_mom_3d, diffuse_scalar_3d, shear_prod3d / sgs_3d
+  crm_module.F90:338-372, 896-1073, 1086-1512     crm_grid, crm_outputs_one_step (vertical grid, statistics, epilogue)
+  scalar_momentum.F90:156-320             esmt_pgf
 Unsuffixed literals are REAL(4) in the reference build (no -r8): f4() reproduces them; literal-only sub-expressions are evaluated in
 float32.
 """
