@@ -1107,7 +1107,8 @@ def crm_grid(zmid, zint, pmid, pint, pdel, nzm):
         rhow[k - 1] = (pmid[plev - k + 1] - pmid[plev - k]) / ggr / (adzw[k - 1] * dz)
     rhow[0] = 2. * rhow[1] - rhow[2]
     rhow[nz - 1] = 2. * rhow[nzm - 1] - rhow[nzm - 2]
-    return dict(z=z, pres=pres, dz=dz, adz=adz, adzw=adzw, rho=rho, rhow=rhow)
+    presi = np.array([pint[plev - k + 1] / 100. for k in range(1, nz + 1)])
+    return dict(z=z, pres=pres, presi=presi, dz=dz, adz=adz, adzw=adzw, rho=rho, rhow=rhow)
 
 
 def crm_outputs_one_step(g, plev, dt_gl, inp, tabs_in, qp_in, u, v, w, tabs, qv, qcl, qci, qpl, qpi, nx_rad, ny_rad):
@@ -1342,3 +1343,111 @@ def pressure_2d(u, w, dudt, dwdt, coef, dx, dz, rho, rhow, adz, adzw):
         du[:, k] = du[:, k] - (p[:, k] - np.roll(p[:, k], 1)) * rdx
         dw[:, k] = dw[:, k] - (p[:, k] - p[:, kb]) * rdz
     return du, dw, p * rho[None, :]
+
+
+def crm_first_substep(g, plev, dx, dt, dt_gl, ncycle, inp, u, w, tabs, qt, qp, qn, qrad, upto=8):
+    """THE SEQUENCING of crm_module.F90 for one 2-D sam1mom CRM, composed from the routine restatements above: the prologue (:380-594: state
+    load, micro_init -> micro_diagnose, t from tabs, horizontal means, large-scale tendencies, precip_init) and the first sub-step of the
+    first CRM step (:743-888, Adams-Bashforth order 1, cold-start tk = 0), phase by phase in the reference's order:
+      1 zero, buoyancy, forcing, radiative heating, damping, ice_fall      5 advect_all_scalars (t, qt, qp)
+      2 sgs_proc (shear_prod2D + tke_full)                                 6 micro_precip_fall, uvw
+      3 advect_mom, sgs_mom                                                7 sgs_scalars
+      4 pressure, adams                                                    8 micro_proc (cloud, precip_proc, micro_diagnose), diagnose
+    inp: this column's crm_input profiles (tl, ql, qccl, qiil, ul); qrad (nx_rad, nzm).  Returns the list of state dicts after each phase
+    1..upto (what CRM_DEBUG_STOP = n exposes)."""
+    nx, nzm = tabs.shape
+    a_bg_ = 1. / (tbgmax - tbgmin); a_pr_ = 1. / (tprmax - tprmin)
+    z, dz, adz, adzw, rho, rhow, pres, presi = g["z"], g["dz"], g["adz"], g["adzw"], g["rho"], g["rhow"], g["pres"], g["presi"]
+    gamaz = ggr / cp * z
+    bet = np.array([ggr / inp["tl"][plev - k] for k in range(1, nzm + 1)])
+    # ---- prologue: micro_diagnose on the state as loaded, t, means, large-scale tendencies
+    qv = qt - qn
+    omn = np.maximum(0., np.minimum(1., (tabs - tbgmin) * a_bg_)); omp = np.maximum(0., np.minimum(1., (tabs - tprmin) * a_pr_))
+    qcl = qn * omn; qci = qn * (1. - omn); qpl = qp * omp; qpi = qp * (1. - omp)
+    t = tabs + gamaz[None, :] - fac_cond * qcl - fac_sub * qci - fac_cond * qpl - fac_sub * qpi
+    factor_xy = 1. / float(nx)
+
+    def mean(a):
+        out = np.zeros(nzm)
+        for k in range(nzm):
+            s_ = 0.
+            for i in range(nx):
+                s_ = s_ + a[i, k]
+            out[k] = s_ * factor_xy
+        return out
+    u0 = mean(u); t00 = mean(t + fac_cond * qpl + fac_sub * qpi); tabs0 = mean(tabs)
+    q0 = mean(qv + qcl + qci); qv0 = mean(qv); qn0 = mean(qcl + qci); qp0 = mean(qpl + qpi)
+    idt_gl = 1. / dt_gl
+    ttend = np.zeros(nzm); qtend = np.zeros(nzm); utend = np.zeros(nzm)
+    for k in range(1, nzm + 1):
+        l = plev - k
+        ttend[k - 1] = (inp["tl"][l] + gamaz[k - 1] - fac_cond * (inp["qccl"][l] + inp["qiil"][l]) - fac_fus * inp["qiil"][l] - t00[k - 1]) * idt_gl
+        qtend[k - 1] = (inp["ql"][l] + inp["qccl"][l] + inp["qiil"][l] - q0[k - 1]) * idt_gl
+        utend[k - 1] = (inp["ul"][l] - u0[k - 1]) * idt_gl
+    coefs = [precip_coefs(rho[k], tabs0[k], pres[k]) for k in range(nzm)]     # precip_init (crm_module.F90:672-674) with the prologue's tabs0
+    out = []
+    snap = lambda **kw: out.append({k_: (v_.copy() if hasattr(v_, "copy") else v_) for k_, v_ in kw.items()})
+    # ---- phase 1
+    dtn = dt / ncycle
+    wf = np.zeros((nx, nzm + 1)); wf[:, :nzm] = w
+    dwdt = buoyancy_2d(tabs, qv, qcl, qci, qpl, qpi, tabs0, qv0, qn0, qp0, bet, adz)
+    t, qt, dudt = forcing_2d(t, qt, ttend, qtend, utend, dtn)
+    nxr = qrad.shape[0]
+    for i in range(nx):
+        t[i, :] = t[i, :] + qrad[i // (nx // nxr), :] * dtn
+    du_d, dw_d, t, qt = damping_2d(u, wf, t, qt, qv, qv0, z, dt, dtn)
+    dudt = dudt + du_d; dwdt = dwdt + dw_d
+    qt, t, _, _, _ = ice_fall_2d(qcl, qci, tabs, qt, t, dz, dtn, adz, rho)
+    snap(t=t, qt=qt, qp=qp, dudt_a=dudt, dwdt_a=dwdt)
+    if upto == 1: return out
+    # ---- phase 2: sgs_proc (tk = tkh = 0 at the start of a call)
+    tk, tkh, tke = sgs_2d(dx, dt, dz, adz, adzw, bet, presi, u0, u, wf, t, tabs, qv, qcl, qci, qpl, qpi, np.zeros((nx, nzm)))
+    snap(tk=tk, tkh=tkh, tke=tke)
+    if upto == 2: return out
+    # ---- phase 3: advect_mom, sgs_mom
+    grdf_x = np.minimum(16., dx * dx / ((adz * dz) * (adz * dz))); grdf_z = np.ones(nzm)
+    da, dwa, _ = advect_mom_2d(u, wf, dx, dz, rho, rhow, adz, adzw)
+    dd, dwd, _ = diffuse_mom_2d(u, wf, tk, dx, dz, rho, rhow, adz, adzw, grdf_x, grdf_z)
+    dudt = dudt + da + dd; dwdt = dwdt + dwa + dwd
+    snap(dudt_a=dudt, dwdt_a=dwdt)
+    if upto == 3: return out
+    # ---- phase 4: pressure (AB1: at = 1, bt = ct = 0, dt3(na) = dtn), adams
+    zero2, zero3 = np.zeros((nx, nzm)), np.zeros((nx, nzm + 1))
+    dudt, dwdt, _ = pressure_2d(u, wf, [dudt, zero2, zero2], [dwdt, zero3, zero3], (1., 0., 0., dtn), dx, dz, rho, rhow, adz, adzw)
+    dudt_c = u + dtn * (1. * dudt + 0. * zero2 + 0. * zero2)
+    dwdt_c = wf + dtn * (1. * dwdt + 0. * zero3 + 0. * zero3)
+    umf = 0.5 * (u + dudt_c) * (rho * (dtn / dx))[None, :]
+    wmf = 0.5 * (wf + dwdt_c) * (rhow * (dtn / dz))[None, :]
+    snap(dudt_a=dudt, dwdt_a=dwdt, dudt_c=dudt_c, dwdt_c=dwdt_c)
+    if upto == 4: return out
+    # ---- phase 5: advect_all_scalars
+    t, _ = advect_scalar2d(t, umf, wmf, rho, rhow, adz)
+    qt, _ = advect_scalar2d(qt, umf, wmf, rho, rhow, adz)
+    qp, _ = advect_scalar2d(qp, umf, wmf, rho, rhow, adz)
+    snap(t=t, qt=qt, qp=qp)
+    if upto == 5: return out
+    # ---- phase 6: micro_precip_fall (tabs of the previous diagnose), uvw
+    qp, t, precsfc, nprec = precip_fall_columns(dz, dtn, rho, rhow, adz, tabs, qp, t)
+    u = dudt_c; wf = dwdt_c
+    snap(t=t, qp=qp, u=u, w=wf, nprec=nprec)
+    if upto == 6: return out
+    # ---- phase 7: sgs_scalars (no surface / top fluxes)
+    zf = np.zeros(nx)
+    t, _ = diffuse_scalar_2d(t, tkh, dx, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_z, zf, zf)
+    qt, _ = diffuse_scalar_2d(qt, tkh, dx, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_z, zf, zf)
+    qp, _ = diffuse_scalar_2d(qp, tkh, dx, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_z, zf, zf)
+    snap(t=t, qt=qt, qp=qp)
+    if upto == 7: return out
+    # ---- phase 8: micro_proc (cloud, precip_proc, micro_diagnose) and diagnose's tabs
+    qn = np.zeros((nx, nzm)); tabs = tabs.copy()
+    for k in range(nzm):
+        for i in range(nx):
+            q_, qp_, tb, qn_ = cloud_cell(t[i, k], gamaz[k], pres[k], qt[i, k], qp[i, k])
+            q_, qp_, qn_, _, _ = precip_proc_cell(dtn, tb, pres[k], coefs[k], q_, qp_, qn_)
+            qt[i, k] = q_; qp[i, k] = qp_; qn[i, k] = qn_; tabs[i, k] = tb
+    qv = qt - qn
+    omn = np.maximum(0., np.minimum(1., (tabs - tbgmin) * a_bg_)); omp = np.maximum(0., np.minimum(1., (tabs - tprmin) * a_pr_))
+    qcl = qn * omn; qci = qn * (1. - omn); qpl = qp * omp; qpi = qp * (1. - omp)
+    tabs = t - gamaz[None, :] + fac_cond * (qcl + qpl) + fac_sub * (qci + qpi)        # diagnose.F90
+    snap(t=t, qt=qt, qp=qp, qn=qn, tabs=tabs, qv=qv, qcl=qcl, qci=qci, qpl=qpl, qpi=qpi, u=u, w=wf)
+    return out

@@ -474,3 +474,48 @@ def test_pressure_solve_against_a_dense_physical_space_solve():
     du = du_o[:nx * nzm].reshape((nx, nzm), order="F"); dw = dw_o[:nx * (nzm + 1)].reshape((nx, nzm + 1), order="F")
     assert np.abs(du - dudt[0]).max() > 1e-3                      # the pressure gradient really acts
     assert _close(p_r, p_o, 1e-9) and _close(du_r, du, 1e-9) and _close(dw_r[:, 1:nzm], dw[:, 1:nzm], 1e-9)
+
+
+@pytest.mark.parametrize("stop", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_first_substep_composition_phase_by_phase(stop):
+    """The SEQUENCING of crm_module.F90, not only its routines: prologue (:380-594) + the first sub-step (:743-888) composed in numpy from
+    the restated routines (ref_numpy.crm_first_substep) and compared with the oracle stopped after each phase (CRM_DEBUG_STOP = stop).
+    The numpy side uses a dense pressure solve, periodic index arithmetic and cell functions: nothing of the oracle's structure."""
+    import os
+    dims = cm.small_dims(ncrms=2, nx=16, nsteps=1)
+    dims, inp, st, rad = cm.make_case(dims, 120)
+    st_in = st.copy()
+    _, stats = cm.ob.run(dims, inp, st.copy(), rad.copy())
+    ncycle = stats["ncycle_sum"]                                 # one CRM step: ncycle of that step
+    os.environ["CRM_DEBUG_STOP"] = str(stop)
+    try:
+        cm.ob.run(dims, inp, st.copy(), rad.copy())
+        got = {no: cm.ob.debug_fetch(no, dims) for no, _ in cm.PHASE_FIELDS[stop]}
+    finally:
+        del os.environ["CRM_DEBUG_STOP"]
+    alias = {"dudt_c": "dudt_c", "dwdt_c": "dwdt_c"}
+    if stop == 6:                                                # after uvw the oracle's nc slot IS the velocity
+        alias = {"dudt_c": "u", "dwdt_c": "w"}
+    tol = {1: 1e-14, 2: 1e-13, 3: 1e-13, 4: 1e-11, 5: 1e-12, 6: 1e-12, 7: 1e-12, 8: 1e-11}[stop]   # measured: <= 3e-16 (1-3), 1e-13 (pressure), 5e-14 (qn)
+    checked = 0
+    for ic in range(dims.ncrms):
+        g = rn.crm_grid(inp.zmid[ic], inp.zint[ic], inp.pmid[ic], inp.pint[ic], inp.pdel[ic], dims.nzm)
+        col = dict(tl=inp.tl[ic], ql=inp.ql[ic], qccl=inp.qccl[ic], qiil=inp.qiil[ic], ul=inp.ul[ic])
+        r = rn.crm_first_substep(g, dims.plev, dims.dx, dims.dt, dims.dt_gl, ncycle, col, st_in.u_wind[ic][:, 0, :], st_in.w_wind[ic][:, 0, :],
+                                 st_in.temperature[ic][:, 0, :], st_in.qt[ic][:, 0, :], st_in.qp[ic][:, 0, :], st_in.qn[ic][:, 0, :],
+                                 rad.qrad[ic][:, 0, :], upto=stop)[-1]
+        for no, _ in cm.PHASE_FIELDS[stop]:
+            key = alias.get(no, no)
+            if key not in r or (stop == 6 and no in ("dudt_a", "dwdt_a")):
+                continue
+            a = got[no][ic][:, 0, :]; b = r[key]
+            n = min(a.shape[1], b.shape[1])
+            if no.startswith("dwdt") or no == "w":
+                a, b = a[:, 1:dims.nzm], b[:, 1:dims.nzm]
+            else:
+                a, b = a[:, :n], b[:, :n]
+            if no in ("tk", "tkh", "tke"):
+                a, b = a[:, :dims.nzm - 1], b[:, :dims.nzm - 1]
+            assert _close(b, a, tol, floor=1e-30), (stop, ic, no, float(np.abs(a - b).max()), float(np.abs(a).max()))
+            checked += 1
+    assert checked >= 2 * dims.ncrms
