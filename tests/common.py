@@ -213,3 +213,18 @@ def negative_moisture_case(dims, lib_path=None, spin=60):
     finally:
         del os.environ["CRM_DEBUG_STOP"]
     return res, qt, dry
+
+
+def single_crm_case(dims, inp, st, rad, ic):
+    """CRM `ic` of a batch as a batch of its own (its ncycle / nprec are then its own maxima, not the batch's)."""
+    d1 = dims.copy(ncrms=1, ld=1)
+    i1 = pkg.crm_input_type().initialize(d1)
+    for n, _ in pkg.abi.INPUT_FIELDS:
+        getattr(i1, n)[...] = getattr(inp, n)[ic:ic + 1]
+    i1.gcol[...] = inp.gcol[ic:ic + 1]
+    s1 = pkg.crm_state_type().initialize(d1); r1 = pkg.crm_rad_type().initialize(d1)
+    for n in s1.names():
+        getattr(s1, n)[...] = getattr(st, n)[ic:ic + 1]
+    for n in r1.names():
+        getattr(r1, n)[...] = getattr(rad, n)[ic:ic + 1]
+    return d1, i1, s1, r1

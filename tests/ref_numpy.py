@@ -1111,19 +1111,26 @@ def crm_grid(zmid, zint, pmid, pint, pdel, nzm):
     return dict(z=z, pres=pres, presi=presi, dz=dz, adz=adz, adzw=adzw, rho=rho, rhow=rhow)
 
 
-def crm_outputs_one_step(g, plev, dt_gl, inp, tabs_in, qp_in, u, v, w, tabs, qv, qcl, qci, qpl, qpi, nx_rad, ny_rad):
+def crm_outputs_one_step(g, plev, dt_gl, inp, tabs_in, qp_in, u, v, w, tabs, qv, qcl, qci, qpl, qpi, nx_rad, ny_rad, nstop=1, acc=None, finalize=True):
     """Outputs of a one-step crm() call (nstop = 1) of ONE sam1mom CRM from its final fields (nx, ny, nzm) [w: (nx, ny, nzm+1)].
     `inp` = dict of this column's crm_input profiles (tl, ql, qccl, qiil, pdel), tabs_in / qp_in the crm_state before the call.
-    Returns a dict of (plev) profiles, scalars and the (nx_rad, ny_rad, nzm) radiation means."""
+    Returns a dict of (plev) profiles, scalars and the (nx_rad, ny_rad, nzm) radiation means.
+    Calls of several CRM steps: pass the per-step statistics of every step but the last with finalize=False (the accumulators come back and
+    go into the next call as `acc`), the last one with finalize=True and nstop = the number of steps."""
     nx, ny, nzm = tabs.shape
     nz = nzm + 1
     rho, rhow, adz, dz, pres = g["rho"], g["rhow"], g["adz"], g["dz"], g["pres"]
     cwp_threshold, wmin = f4(0.001), 2.
-    factor_xy = 1. / float(nx * ny); factor_xyt = factor_xy / 1.
+    factor_xy = 1. / float(nx * ny); factor_xyt = factor_xy / float(nstop)
     o = {n: np.zeros(plev) for n in ("cld", "cldtop", "gicewp", "gliqwp", "mcup", "mcdn", "mcuup", "mcudn", "qc_mean", "qi_mean", "qr_mean", "qg_mean",
                                      "qs_mean", "tln", "qln", "qccln", "qiiln")}
     mui = np.zeros(plev + 2); mdi = np.zeros(plev + 2)          # 1-based l up to plev+1
     cl = dict(cltot=0., clhgh=0., clmed=0., cllow=0.)
+    rad = {n: np.zeros((nx_rad, ny_rad, nzm)) for n in ("temperature", "qv", "qc", "qi", "cld")}
+    if acc is not None:                                         # accumulators of the earlier steps of this call
+        for n in ("cld", "cldtop", "gicewp", "gliqwp", "mcup", "mcdn", "mcuup", "mcudn"):
+            o[n] = acc["o"][n]
+        mui, mdi, cl, rad = acc["mui"], acc["mdi"], acc["cl"], acc["rad"]
     for j in range(ny):
         for i in range(nx):
             cwp = cwph = cwpm = cwpl = 0.
@@ -1180,7 +1187,6 @@ def crm_outputs_one_step(g, plev, dt_gl, inp, tabs_in, qp_in, u, v, w, tabs, qv,
                     elif qpl[i, j, kx - 1] + qpi[i, j, kx - 1] > f4(1.0e-4):
                         mdi[l] += rhow[k - 1] * wk
     # radiation column-group means (:979-1003, 1086-1108)
-    rad = {n: np.zeros((nx_rad, ny_rad, nzm)) for n in ("temperature", "qv", "qc", "qi", "cld")}
     for k in range(nzm):
         for j in range(ny):
             for i in range(nx):
@@ -1191,9 +1197,10 @@ def crm_outputs_one_step(g, plev, dt_gl, inp, tabs_in, qp_in, u, v, w, tabs, qv,
                 rad["qi"][ir, jr, k] += qci[i, j, k]
                 if qcl[i, j, k] + qci[i, j, k] > 0:
                     rad["cld"][ir, jr, k] += 1.
-    tmp1 = (float(nx_rad) / float(nx)) * (float(ny_rad) / float(ny)) / 1.
-    for n in rad:
-        rad[n] = rad[n] * tmp1
+    if not finalize:
+        return dict(o=o, mui=mui, mdi=mdi, cl=cl, rad=rad)
+    tmp1 = (float(nx_rad) / float(nx)) * (float(ny_rad) / float(ny)) / float(nstop)
+    rad = {n: rad[n] * tmp1 for n in rad}
     # epilogue: horizontal means and tendencies (:1139-1170, 1212-1243)
     ptop = plev - nzm + 1
     colprec = colprecs = 0.
@@ -1451,3 +1458,136 @@ def crm_first_substep(g, plev, dx, dt, dt_gl, ncycle, inp, u, w, tabs, qt, qp, q
     tabs = t - gamaz[None, :] + fac_cond * (qcl + qpl) + fac_sub * (qci + qpi)        # diagnose.F90
     snap(t=t, qt=qt, qp=qp, qn=qn, tabs=tabs, qv=qv, qcl=qcl, qci=qci, qpl=qpl, qpi=qpi, u=u, w=wf)
     return out
+
+
+def abcoefs(nstep, dt3, na, nb, nc):
+    """abcoefs.F90:13-27 (nadams = 3, no restart): Adams-Bashforth coefficients for variable time steps."""
+    if nstep >= 3:
+        alpha = dt3[nb] / dt3[na]; beta = dt3[nc] / dt3[na]
+        ct = (2. + 3. * alpha) / (6. * (alpha + beta) * beta)
+        bt = -(1. + 2. * (alpha + beta) * ct) / (2. * alpha)
+        at = 1. - bt - ct
+    elif nstep >= 2:
+        at, bt, ct = 3. / 2., -1. / 2., 0.
+    else:
+        at, bt, ct = 1., 0., 0.
+    return at, bt, ct
+
+
+def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad):
+    """A complete crm() call (crm_module.F90:286-1594) of ONE 2-D sam1mom CRM in numpy, composed from the routine restatements of this file:
+    prologue, the step loop with the CFL sub-cycling of kurant (ncycle) and the variable-step Adams-Bashforth rotation of the tendency slots,
+    per-step statistics, epilogue.  No mean-state acceleration, no setperturb (igstep > 1).  Returns dict(state=..., out=...)."""
+    nx, nzm = tabs.shape
+    u, w, tabs, qt, qp, qn = (a.copy() for a in (u, w, tabs, qt, qp, qn))
+    tabs_in, qp_in = tabs.copy(), qp.copy()
+    a_bg_ = 1. / (tbgmax - tbgmin); a_pr_ = 1. / (tprmax - tprmin)
+    z, dz, adz, adzw, rho, rhow, pres, presi = g["z"], g["dz"], g["adz"], g["adzw"], g["rho"], g["rhow"], g["pres"], g["presi"]
+    gamaz = ggr / cp * z
+    bet = np.array([ggr / inp["tl"][plev - k] for k in range(1, nzm + 1)])
+    factor_xy = 1. / float(nx)
+
+    def mean(a):
+        out = np.zeros(nzm)
+        for k in range(nzm):
+            s_ = 0.
+            for i in range(nx):
+                s_ = s_ + a[i, k]
+            out[k] = s_ * factor_xy
+        return out
+
+    def diagnose_micro(tabs_):
+        omn = np.maximum(0., np.minimum(1., (tabs_ - tbgmin) * a_bg_)); omp = np.maximum(0., np.minimum(1., (tabs_ - tprmin) * a_pr_))
+        return qt - qn, qn * omn, qn * (1. - omn), qp * omp, qp * (1. - omp)
+    # ---- prologue
+    qv, qcl, qci, qpl, qpi = diagnose_micro(tabs)
+    t = tabs + gamaz[None, :] - fac_cond * qcl - fac_sub * qci - fac_cond * qpl - fac_sub * qpi
+    u0 = mean(u); t00 = mean(t + fac_cond * qpl + fac_sub * qpi); tabs0 = mean(tabs)
+    q0 = mean(qv + qcl + qci); qv0 = mean(qv); qn0 = mean(qcl + qci); qp0 = mean(qpl + qpi)
+    idt_gl = 1. / dt_gl
+    ttend = np.zeros(nzm); qtend = np.zeros(nzm); utend = np.zeros(nzm)
+    for k in range(1, nzm + 1):
+        l = plev - k
+        ttend[k - 1] = (inp["tl"][l] + gamaz[k - 1] - fac_cond * (inp["qccl"][l] + inp["qiil"][l]) - fac_fus * inp["qiil"][l] - t00[k - 1]) * idt_gl
+        qtend[k - 1] = (inp["ql"][l] + inp["qccl"][l] + inp["qiil"][l] - q0[k - 1]) * idt_gl
+        utend[k - 1] = (inp["ul"][l] - u0[k - 1]) * idt_gl
+    coefs = [precip_coefs(rho[k], tabs0[k], pres[k]) for k in range(nzm)]
+    grdf_x = np.minimum(16., dx * dx / ((adz * dz) * (adz * dz))); grdf_z = np.ones(nzm)
+    nstop = int(dt_gl / dt)
+    dt = dt_gl / nstop
+    wf = np.zeros((nx, nzm + 1)); wf[:, :nzm] = w
+    du = [np.zeros((nx, nzm)) for _ in range(3)]; dw = [np.zeros((nx, nzm + 1)) for _ in range(3)]
+    na, nb, nc = 0, 1, 2
+    dt3 = [0., 0., 0.]
+    tk = np.zeros((nx, nzm)); tkh = np.zeros((nx, nzm))
+    precsfc = np.zeros(nx)
+    acc = None
+    ncycle_sum = 0
+    nxr = qrad.shape[0]
+    zf = np.zeros(nx)
+    for nstep in range(1, nstop + 1):
+        cfl = kurant_2d(u, wf, tkh, dx, dz, dt, adz, adzw)
+        ncycle = max(1, int(math.ceil(cfl / f4(0.7))))
+        ncycle_sum += ncycle
+        for icyc in range(1, ncycle + 1):
+            dtn = dt / ncycle
+            dt3[na] = dtn
+            at, bt, ct = abcoefs(nstep, dt3, na, nb, nc)
+            # zero, buoyancy, forcing, radiative heating, damping, ice_fall
+            du[na] = np.zeros((nx, nzm))
+            dw[na] = buoyancy_2d(tabs, qv, qcl, qci, qpl, qpi, tabs0, qv0, qn0, qp0, bet, adz)
+            t, qt, dfu = forcing_2d(t, qt, ttend, qtend, utend, dtn)
+            du[na] = du[na] + dfu
+            for i in range(nx):
+                t[i, :] = t[i, :] + qrad[i // (nx // nxr), :] * dtn
+            du_d, dw_d, t, qt = damping_2d(u, wf, t, qt, qv, qv0, z, dt, dtn)
+            du[na] = du[na] + du_d; dw[na] = dw[na] + dw_d
+            qt, t, _, _, pice = ice_fall_2d(qcl, qci, tabs, qt, t, dz, dtn, adz, rho)
+            precsfc = precsfc + pice
+            # sgs_proc, advect_mom, sgs_mom
+            tk, tkh, _ = sgs_2d(dx, dt, dz, adz, adzw, bet, presi, u0, u, wf, t, tabs, qv, qcl, qci, qpl, qpi, tk)
+            da, dwa, _ = advect_mom_2d(u, wf, dx, dz, rho, rhow, adz, adzw)
+            dd, dwd, _ = diffuse_mom_2d(u, wf, tk, dx, dz, rho, rhow, adz, adzw, grdf_x, grdf_z)
+            du[na] = du[na] + da + dd; dw[na] = dw[na] + dwa + dwd
+            # pressure, adams
+            du[na], dw[na], _ = pressure_2d(u, wf, [du[na], du[nb], du[nc]], [dw[na], dw[nb], dw[nc]], (at, bt, ct, dt3[na]), dx, dz, rho, rhow, adz, adzw)
+            du[nc] = u + dt3[na] * (at * du[na] + bt * du[nb] + ct * du[nc])
+            dw[nc] = wf + dt3[na] * (at * dw[na] + bt * dw[nb] + ct * dw[nc])
+            umf = 0.5 * (u + du[nc]) * (rho * (dtn / dx))[None, :]
+            wmf = 0.5 * (wf + dw[nc]) * (rhow * (dtn / dz))[None, :]
+            # advect_all_scalars (incl. micro_precip_fall), uvw
+            t, _ = advect_scalar2d(t, umf, wmf, rho, rhow, adz)
+            qt, _ = advect_scalar2d(qt, umf, wmf, rho, rhow, adz)
+            qp, _ = advect_scalar2d(qp, umf, wmf, rho, rhow, adz)
+            qp, t, pfall, _ = precip_fall_columns(dz, dtn, rho, rhow, adz, tabs, qp, t)
+            precsfc = precsfc + pfall
+            u = du[nc]; wf = dw[nc]
+            # sgs_scalars
+            t, _ = diffuse_scalar_2d(t, tkh, dx, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_z, zf, zf)
+            qt, _ = diffuse_scalar_2d(qt, tkh, dx, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_z, zf, zf)
+            qp, _ = diffuse_scalar_2d(qp, tkh, dx, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_z, zf, zf)
+            # micro_proc: the bulk coefficients are refreshed with the current tabs0 on the first sub-step of every CRM step
+            # (MICRO_SAM1MOM/microphysics.F90:309)
+            if icyc == 1:
+                coefs = [precip_coefs(rho[k], tabs0[k], pres[k]) for k in range(nzm)]
+            qn = np.zeros((nx, nzm)); tabs = tabs.copy()
+            for k in range(nzm):
+                for i in range(nx):
+                    q_, qp_, tb, qn_ = cloud_cell(t[i, k], gamaz[k], pres[k], qt[i, k], qp[i, k])
+                    q_, qp_, qn_, _, _ = precip_proc_cell(dtn, tb, pres[k], coefs[k], q_, qp_, qn_)
+                    qt[i, k] = q_; qp[i, k] = qp_; qn[i, k] = qn_; tabs[i, k] = tb
+            qv, qcl, qci, qpl, qpi = diagnose_micro(tabs)
+            # diagnose
+            tabs = t - gamaz[None, :] + fac_cond * (qcl + qpl) + fac_sub * (qci + qpi)
+            u0 = mean(u); tabs0 = mean(tabs); q0 = mean(qv + qcl + qci); qn0 = mean(qcl + qci); qp0 = mean(qpl + qpi)
+            qv0 = q0 - qn0
+            na, nb, nc = nc, na, nb                                  # nn = na; na = nc; nc = nb; nb = nn
+        last = nstep == nstop
+        acc = crm_outputs_one_step(g, plev, dt_gl, inp, tabs_in[:, None, :], qp_in[:, None, :], u[:, None, :], None, wf[:, None, :], tabs[:, None, :],
+                                   qv[:, None, :], qcl[:, None, :], qci[:, None, :], qpl[:, None, :], qpi[:, None, :], nxr, 1, nstop=nstop, acc=acc,
+                                   finalize=last)
+    out = acc
+    out["prec_crm"] = precsfc * dz / dt / float(nstop) / f4(1000.)
+    out["tk"] = tk; out["tkh"] = tkh; out["qcl"] = qcl; out["qci"] = qci; out["qpl"] = qpl; out["qpi"] = qpi
+    out["ncycle_sum"] = ncycle_sum
+    return dict(state=dict(u_wind=u, w_wind=wf[:, :nzm], temperature=tabs, qt=qt, qp=qp, qn=qn), out=out)

@@ -519,3 +519,50 @@ def test_first_substep_composition_phase_by_phase(stop):
             assert _close(b, a, tol, floor=1e-30), (stop, ic, no, float(np.abs(a - b).max()), float(np.abs(a).max()))
             checked += 1
     assert checked >= 2 * dims.ncrms
+
+
+@pytest.mark.parametrize("nzm,plev,spin,nsteps,wind", [(58, 72, 200, 4, 1.), (28, 30, 300, 5, 1.), (58, 72, 200, 3, 5.)])
+def test_whole_crm_call_against_the_numpy_composition(nzm, plev, spin, nsteps, wind):
+    """A complete crm() call of several CRM steps (Adams-Bashforth orders 1, 2, 3 with variable sub-steps, CFL sub-cycling, sub-iterated
+    precipitation fall, per-step statistics, epilogue) computed by ref_numpy.crm_call_numpy -- an independent numpy implementation composed
+    from the routine restatements, written from the Fortran -- against the C++ oracle: final crm_state, crm_output (3-D members, tendencies,
+    cloud statistics, mass fluxes, precipitation) and crm_rad.  The most strongly precipitating CRM of a spun-up batch is used; `wind`
+    scales its horizontal wind so that kurant() sub-cycles (ncycle > 1)."""
+    dims = cm.small_dims(ncrms=6, nx=16, nzm=nzm, plev=plev, nsteps=nsteps)
+    dims, inp, st, rad = cm.make_case(dims, spin)
+    ic = int(np.argmax(st.qp.reshape(dims.ncrms, -1).max(axis=1)))
+    dims, inp, st, rad = cm.single_crm_case(dims, inp, st, rad, ic)
+    st.u_wind *= wind
+    st_in = st.copy()
+    out, stats = cm.ob.run(dims, inp, st, rad)
+    ic = 0
+    g = rn.crm_grid(inp.zmid[ic], inp.zint[ic], inp.pmid[ic], inp.pint[ic], inp.pdel[ic], dims.nzm)
+    col = dict(tl=inp.tl[ic], ql=inp.ql[ic], qccl=inp.qccl[ic], qiil=inp.qiil[ic], ul=inp.ul[ic], pdel=inp.pdel[ic])
+    r = rn.crm_call_numpy(g, dims.plev, dims.dx, dims.dt, dims.dt_gl, col, st_in.u_wind[ic][:, 0, :], st_in.w_wind[ic][:, 0, :],
+                          st_in.temperature[ic][:, 0, :], st_in.qt[ic][:, 0, :], st_in.qp[ic][:, 0, :], st_in.qn[ic][:, 0, :], rad.qrad[ic][:, 0, :])
+    assert r["out"]["ncycle_sum"] == stats["ncycle_sum"] and stats["nstop"] == nsteps
+    if wind > 1.:
+        assert stats["ncycle_sum"] > nsteps                       # sub-cycling happened
+    else:
+        assert float(out.prec_crm.max()) > 0. and float(out.cld.max()) > 0.
+    if nzm == 58 and wind == 1.:
+        assert stats["nprec_max"] >= 2                            # sub-iterated sedimentation on the thin L72 layers
+    worst = {}
+    for n in ("u_wind", "w_wind", "temperature", "qt", "qp", "qn"):
+        a = getattr(st, n)[ic][:, 0, :]; b = r["state"][n]
+        worst["state." + n] = float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-300))
+    for n in ("qcl", "qci", "qpl", "qpi", "tk", "tkh"):
+        a = getattr(out, n)[ic][:, 0, :]; b = r["out"][n]
+        worst[n] = float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-300))
+    for n in ("sltend", "qltend", "qcltend", "qiltend", "cld", "cldtop", "gicewp", "gliqwp", "mcup", "mcdn", "mcuup", "mcudn", "mctot", "qc_mean", "qi_mean",
+              "qs_mean", "qg_mean", "qr_mean", "mu_crm", "md_crm", "eu_crm", "du_crm", "ed_crm"):
+        a = getattr(out, n)[ic]; b = r["out"][n]
+        worst[n] = float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-300)) if np.abs(a).max() > 0 else float(np.abs(b).max())
+    worst["prec_crm"] = float(np.abs(out.prec_crm[ic][:, 0] - r["out"]["prec_crm"]).max() / max(np.abs(out.prec_crm[ic]).max(), 1e-300))
+    for n in ("temperature", "qv", "qc", "qi", "cld"):
+        a = getattr(rad, n)[ic][:, 0, :]; b = r["out"]["rad"][n][:, 0, :]
+        worst["rad." + n] = float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-300)) if np.abs(a).max() > 0 else float(np.abs(b).max())
+    for n in ("cltot", "clhgh", "clmed", "cllow", "prectend", "precstend"):
+        a = float(getattr(out, n)[ic]); worst[n] = abs(a - r["out"][n]) / max(abs(a), 1e-300) if a != 0 else abs(r["out"][n])
+    bad = {k: v for k, v in worst.items() if v > 1e-10}
+    assert not bad, bad
