@@ -148,3 +148,20 @@ def test_emu_negative_moisture_fix(emu):
     for name, err, scale in res:
         assert err <= 1e-12 or err * scale < 1e-18, (name, err, scale)
     assert (qt[dry] == 0.).sum() > 10 and (qt[~dry] == 0.).sum() == 0
+
+
+def test_emu_device_code_matches_the_numpy_golden_fixture(emu):
+    """The device code path (emulated) against a fixture computed by the independent numpy crm() (tests/golden/make_golden_numpy.py): no C++
+    oracle between the CUDA sources and the restatement written from the Fortran."""
+    import sys
+    gold = os.path.join(cm.ROOT, "tests", "golden")
+    if gold not in sys.path:
+        sys.path.insert(0, gold)
+    import make_golden_numpy as mgn
+    dims, inp, st, rad, z = mgn.load_case("numpy_2d_16x28")
+    h = cm.libmod.CrmHandle(dims, lib_path=emu)
+    out = h.run(dims, inp, st, rad)
+    assert h.stats()["ncycle_sum"] == int(z["ncycle_sum"])
+    h.close()
+    bad = mgn.compare(dims, st, rad, out, z, 1e-9)
+    assert not bad, bad

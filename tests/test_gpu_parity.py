@@ -591,3 +591,24 @@ def test_negative_moisture_fix_in_forcing(geo):
     for name, err, scale in res:
         assert err <= 1e-12 or err * scale < 1e-18, (name, err, scale)
     assert (qt[dry] == 0.).sum() > 10 and (qt[~dry] == 0.).sum() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["numpy_2d_16x58_precip", "numpy_2d_16x58_subcycling", "numpy_2d_16x28"])
+def test_numpy_golden_fixture_on_device(name):
+    """Device vs the independent numpy crm() written from the Fortran (tests/golden/numpy_2d_*.npz, generated by make_golden_numpy.py from
+    ref_numpy.crm_call_numpy): complete single-CRM calls with clouds, sub-iterated precipitation fall and -- in the sub-cycling case --
+    ncycle > 1, replayed through the C ABI from the file alone.  No C++ oracle is involved in this comparison."""
+    import os
+    import sys
+    gold = os.path.join(cm.ROOT, "tests", "golden")
+    if gold not in sys.path:
+        sys.path.insert(0, gold)
+    import make_golden_numpy as mgn
+    dims, inp, st, rad, z = mgn.load_case(name)
+    h = cm.libmod.CrmHandle(dims)
+    out = h.run(dims, inp, st, rad)
+    assert h.stats()["ncycle_sum"] == int(z["ncycle_sum"])
+    h.close()
+    bad = mgn.compare(dims, st, rad, out, z, 1e-9)
+    assert not bad, bad

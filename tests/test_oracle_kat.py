@@ -335,3 +335,29 @@ def test_spmomtrans_tendencies_use_the_raw_slab_sum():
         exp[:, ptop - 1:ptop + 1] = 0.0                           # "don't use tendencies from two top levels"
         assert np.abs(got[:, ptop - 1:]).max() > 1.0                  # sums of 64 columns: far from a mean-based tendency
         assert np.abs(got - exp).max() <= 1e-12 * np.abs(exp).max(), name
+
+
+# ---------------------------------------------------------------- fixtures from the independent numpy crm()
+NUMPY_GOLDEN = ("numpy_2d_16x58_precip", "numpy_2d_16x58_subcycling", "numpy_2d_16x28")
+
+
+def _numpy_golden():
+    import sys
+    gold = os.path.join(cm.ROOT, "tests", "golden")
+    if gold not in sys.path:
+        sys.path.insert(0, gold)
+    import make_golden_numpy as mgn
+    return mgn
+
+
+@pytest.mark.parametrize("name", NUMPY_GOLDEN)
+def test_oracle_matches_the_numpy_golden_fixture(name):
+    """tests/golden/numpy_2d_*.npz hold complete single-CRM crm() calls whose outputs were computed by ref_numpy.crm_call_numpy (written from
+    the Fortran, no C++ involved).  The oracle replays the stored arguments and must reproduce the stored results (<= 1e-10)."""
+    mgn = _numpy_golden()
+    dims, inp, st, rad, z = mgn.load_case(name)
+    out, stats = ob.run(dims, inp, st, rad)
+    assert stats["ncycle_sum"] == int(z["ncycle_sum"])
+    bad = mgn.compare(dims, st, rad, out, z, 1e-10)
+    assert not bad, bad
+    assert float(z["out_prec_crm"].max()) > 0 and float(z["out_cld"].max()) > 0
