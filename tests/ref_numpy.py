@@ -1591,3 +1591,185 @@ def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad):
     out["tk"] = tk; out["tkh"] = tkh; out["qcl"] = qcl; out["qci"] = qci; out["qpl"] = qpl; out["qpi"] = qpi
     out["ncycle_sum"] = ncycle_sum
     return dict(state=dict(u_wind=u, w_wind=wf[:, :nzm], temperature=tabs, qt=qt, qp=qp, qn=qn), out=out)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The 3-D CRM (BASELINE config 4) as a whole call.  Column-wise routines (buoyancy, forcing, damping, ice_fall, precip_fall, the tke_full
+# part of sgs, microphysics) run on the columns flattened with i fastest (the Fortran's j-outer / i-inner summation order).
+# ---------------------------------------------------------------------------------------------------------------------------
+def pressure_3d(u, v, w, dudt, dvdt, dwdt, coef, dx, dy, dz, rho, rhow, adz, adzw):
+    """press_rhs.F90:57-83 (RUN3D) + the Poisson problem of pressure.F90 + press_grad.F90, the operator assembled densely in physical
+    space like pressure_2d (periodic in x and y).  Slots [na, nb, nc]; returns (dudt_na, dvdt_na, dwdt_na)."""
+    nx, ny, nzm = u.shape
+    at, bt, ct, dt3 = coef
+    rdx, rdy = 1. / dx, 1. / dy
+    btat, ctat = bt / at, ct / at
+    dta = 1. / dt3 / at
+    rhs = np.zeros((nx, ny, nzm))
+    for k in range(nzm):
+        rdz = 1. / (adz[k] * dz)
+        rup = rhow[k + 1] / rho[k] * rdz; rdn = rhow[k] / rho[k] * rdz
+        div = lambda uu, vv, ww: (rdx * (_X(uu[:, :, k], 1) - uu[:, :, k]) + rdy * (_Y(vv[:, :, k], 1) - vv[:, :, k]) +
+                                  (ww[:, :, k + 1] * rup - ww[:, :, k] * rdn))
+        rhs[:, :, k] = (div(u, v, w) * dta + div(dudt[0], dvdt[0], dwdt[0]) + btat * div(dudt[1], dvdt[1], dwdt[1]) +
+                        ctat * div(dudt[2], dvdt[2], dwdt[2])) * rho[k]
+    a = rhow[:nzm] / (adz * adzw[:nzm] * dz * dz)
+    c = rhow[1:] / (adz * adzw[1:] * dz * dz)
+    nh = nx * ny
+    n = nh * nzm
+    A = np.zeros((n, n))
+    idx = lambda i, j, k: (i % nx) + nx * (j % ny) + nh * k
+    ddx2, ddy2 = 1. / (dx * dx), 1. / (dy * dy)
+    for k in range(nzm):
+        for j in range(ny):
+            for i in range(nx):
+                r = idx(i, j, k)
+                A[r, idx(i + 1, j, k)] += rho[k] * ddx2; A[r, idx(i - 1, j, k)] += rho[k] * ddx2
+                A[r, idx(i, j + 1, k)] += rho[k] * ddy2; A[r, idx(i, j - 1, k)] += rho[k] * ddy2
+                A[r, r] += -2. * rho[k] * (ddx2 + ddy2)
+                if k > 0:
+                    A[r, idx(i, j, k - 1)] += a[k]; A[r, r] -= a[k]
+                if k < nzm - 1:
+                    A[r, idx(i, j, k + 1)] += c[k]; A[r, r] -= c[k]
+        if k == 0:                                             # wavenumber (0, 0) only: -a(1) on the diagonal
+            A[:nh, :nh] -= a[0] / nh
+    p = np.linalg.solve(A, rhs.ravel(order="F")).reshape((nx, ny, nzm), order="F")
+    du = dudt[0].copy(); dv = dvdt[0].copy(); dw = dwdt[0].copy()
+    for k in range(nzm):
+        kb = max(0, k - 1)
+        rdz = 1. / (dz * adzw[k])
+        du[:, :, k] = du[:, :, k] - (p[:, :, k] - _X(p[:, :, k], -1)) * rdx
+        dv[:, :, k] = dv[:, :, k] - (p[:, :, k] - _Y(p[:, :, k], -1)) * rdy
+        dw[:, :, k] = dw[:, :, k] - (p[:, :, k] - p[:, :, kb]) * rdz
+    return du, dv, dw
+
+
+def crm_call_numpy_3d(g, plev, dx, dt, dt_gl, inp, u, v, w, tabs, qt, qp, qn, qrad):
+    """crm_call_numpy for a 3-D CRM (nx, ny, nzm): RUN3D branches of the momentum routines, advect_scalar3D, diffuse_scalar3D, shear_prod3D,
+    the 3-D pressure problem, v everywhere; dx == dy.  qrad (nx_rad, ny_rad, nzm)."""
+    nx, ny, nzm = tabs.shape
+    nc_ = nx * ny
+    col = lambda a: a.reshape((nc_, a.shape[2]), order="F")
+    box = lambda a: a.reshape((nx, ny, a.shape[1]), order="F")
+    u, v, w, tabs, qt, qp, qn = (a.copy() for a in (u, v, w, tabs, qt, qp, qn))
+    tabs_in, qp_in = tabs.copy(), qp.copy()
+    a_bg_ = 1. / (tbgmax - tbgmin); a_pr_ = 1. / (tprmax - tprmin)
+    z, dz, adz, adzw, rho, rhow, pres, presi = g["z"], g["dz"], g["adz"], g["adzw"], g["rho"], g["rhow"], g["pres"], g["presi"]
+    dy = dx
+    gamaz = ggr / cp * z
+    bet = np.array([ggr / inp["tl"][plev - k] for k in range(1, nzm + 1)])
+    factor_xy = 1. / float(nc_)
+
+    def mean(a3):
+        a = col(a3)
+        out = np.zeros(nzm)
+        for k in range(nzm):
+            s_ = 0.
+            for c in range(nc_):
+                s_ = s_ + a[c, k]
+            out[k] = s_ * factor_xy
+        return out
+
+    def diagnose_micro(tabs_):
+        omn = np.maximum(0., np.minimum(1., (tabs_ - tbgmin) * a_bg_)); omp = np.maximum(0., np.minimum(1., (tabs_ - tprmin) * a_pr_))
+        return qt - qn, qn * omn, qn * (1. - omn), qp * omp, qp * (1. - omp)
+    qv, qcl, qci, qpl, qpi = diagnose_micro(tabs)
+    t = tabs + gamaz[None, None, :] - fac_cond * qcl - fac_sub * qci - fac_cond * qpl - fac_sub * qpi
+    u0 = mean(u); v0 = mean(v); t00 = mean(t + fac_cond * qpl + fac_sub * qpi); tabs0 = mean(tabs)
+    q0 = mean(qv + qcl + qci); qv0 = mean(qv); qn0 = mean(qcl + qci); qp0 = mean(qpl + qpi)
+    idt_gl = 1. / dt_gl
+    ttend = np.zeros(nzm); qtend = np.zeros(nzm); utend = np.zeros(nzm); vtend = np.zeros(nzm)
+    for k in range(1, nzm + 1):
+        l = plev - k
+        ttend[k - 1] = (inp["tl"][l] + gamaz[k - 1] - fac_cond * (inp["qccl"][l] + inp["qiil"][l]) - fac_fus * inp["qiil"][l] - t00[k - 1]) * idt_gl
+        qtend[k - 1] = (inp["ql"][l] + inp["qccl"][l] + inp["qiil"][l] - q0[k - 1]) * idt_gl
+        utend[k - 1] = (inp["ul"][l] - u0[k - 1]) * idt_gl
+        vtend[k - 1] = (inp["vl"][l] - v0[k - 1]) * idt_gl
+    grdf_x = np.minimum(16., dx * dx / ((adz * dz) * (adz * dz))); grdf_z = np.ones(nzm)
+    nstop = int(dt_gl / dt)
+    dt = dt_gl / nstop
+    wf = np.zeros((nx, ny, nzm + 1)); wf[:, :, :nzm] = w
+    du = [np.zeros((nx, ny, nzm)) for _ in range(3)]; dv = [np.zeros((nx, ny, nzm)) for _ in range(3)]; dw = [np.zeros((nx, ny, nzm + 1)) for _ in range(3)]
+    na, nb, nc = 0, 1, 2
+    dt3 = [0., 0., 0.]
+    tk = np.zeros((nx, ny, nzm)); tkh = np.zeros((nx, ny, nzm))
+    precsfc = np.zeros(nc_)
+    acc = None
+    ncycle_sum = 0
+    nxr, nyr = qrad.shape[0], qrad.shape[1]
+    zf = np.zeros((nx, ny))
+    coefs = None
+    for nstep in range(1, nstop + 1):
+        # kurant.F90 + kurant_sgs with YES3D = 1
+        wm = np.zeros(nzm + 2); wm[:nzm] = np.abs(wf[:, :, :nzm]).max(axis=(0, 1))
+        uhm = np.sqrt(u ** 2 + 1 * v ** 2).max(axis=(0, 1))
+        cfl = 0.
+        for k in range(nzm):
+            cfl = max(cfl, max(uhm[k] * dt * math.sqrt((1. / dx) ** 2 + 1 * (1. / dy) ** 2), max(wm[k], wm[k + 1]) * dt / (dz * adzw[k])))
+        tkhmax = tkh.max(axis=(0, 1))
+        for k in range(nzm):
+            cfl = max(cfl, max(0.5 * tkhmax[k] * 1. * dt / (dz * adzw[k]) ** 2, 0.5 * tkhmax[k] * grdf_x[k] * dt / dx ** 2,
+                               1 * 0.5 * tkhmax[k] * grdf_x[k] * dt / dy ** 2))
+        ncycle = max(1, int(math.ceil(cfl / f4(0.7))))
+        ncycle_sum += ncycle
+        for icyc in range(1, ncycle + 1):
+            dtn = dt / ncycle
+            dt3[na] = dtn
+            at, bt, ct = abcoefs(nstep, dt3, na, nb, nc)
+            dw[na] = box(buoyancy_2d(col(tabs), col(qv), col(qcl), col(qci), col(qpl), col(qpi), tabs0, qv0, qn0, qp0, bet, adz))
+            t_c, qt_c, dfu = forcing_2d(col(t), col(qt), ttend, qtend, utend, dtn)
+            du[na] = box(dfu); dv[na] = np.zeros((nx, ny, nzm)) + vtend[None, None, :]
+            t = box(t_c); qt = box(qt_c)
+            for j in range(ny):
+                for i in range(nx):
+                    t[i, j, :] = t[i, j, :] + qrad[i // (nx // nxr), j // (ny // nyr), :] * dtn
+            du_d, dw_d, t_c, qt_c = damping_2d(col(u), col(wf), col(t), col(qt), col(qv), qv0, z, dt, dtn)
+            dv_d, _, _, _ = damping_2d(col(v), col(wf), col(t), col(qt), col(qv), qv0, z, dt, dtn)
+            du[na] = du[na] + box(du_d); dv[na] = dv[na] + box(dv_d); dw[na] = dw[na] + box(dw_d)
+            t = box(t_c); qt = box(qt_c)
+            qt_c, t_c, _, _, pice = ice_fall_2d(col(qcl), col(qci), col(tabs), col(qt), col(t), dz, dtn, adz, rho)
+            qt = box(qt_c); t = box(t_c)
+            precsfc = precsfc + pice
+            tk, tkh, _ = sgs_3d(dx, dt, dz, adz, adzw, bet, presi, u0, v0, u, v, wf, t, tabs, qv, qcl, qci, qpl, qpi, tk)
+            da, dva, dwa, _, _ = advect_mom_3d(u, v, wf, dx, dy, dz, rho, rhow, adz, adzw)
+            dd, dvd, dwd, _, _ = diffuse_mom_3d(u, v, wf, tk, dx, dy, dz, rho, rhow, adz, adzw, grdf_x, grdf_x, grdf_z)
+            du[na] = du[na] + da + dd; dv[na] = dv[na] + dva + dvd; dw[na] = dw[na] + dwa + dwd
+            du[na], dv[na], dw[na] = pressure_3d(u, v, wf, [du[na], du[nb], du[nc]], [dv[na], dv[nb], dv[nc]], [dw[na], dw[nb], dw[nc]],
+                                                 (at, bt, ct, dt3[na]), dx, dy, dz, rho, rhow, adz, adzw)
+            du[nc] = u + dt3[na] * (at * du[na] + bt * du[nb] + ct * du[nc])
+            dv[nc] = v + dt3[na] * (at * dv[na] + bt * dv[nb] + ct * dv[nc])
+            dw[nc] = wf + dt3[na] * (at * dw[na] + bt * dw[nb] + ct * dw[nc])
+            umf = 0.5 * (u + du[nc]) * (rho * (dtn / dx))[None, None, :]
+            vmf = 0.5 * (v + dv[nc]) * (rho * (dtn / dy))[None, None, :]
+            wmf = 0.5 * (wf + dw[nc]) * (rhow * (dtn / dz))[None, None, :]
+            t, _ = advect_scalar3d(t, umf, vmf, wmf, rho, rhow, adz)
+            qt, _ = advect_scalar3d(qt, umf, vmf, wmf, rho, rhow, adz)
+            qp, _ = advect_scalar3d(qp, umf, vmf, wmf, rho, rhow, adz)
+            qp_c, t_c, pfall, _ = precip_fall_columns(dz, dtn, rho, rhow, adz, col(tabs), col(qp), col(t))
+            qp = box(qp_c); t = box(t_c)
+            precsfc = precsfc + pfall
+            u = du[nc]; v = dv[nc]; wf = dw[nc]
+            t, _ = diffuse_scalar_3d(t, tkh, dx, dy, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_x, grdf_z, zf, zf)
+            qt, _ = diffuse_scalar_3d(qt, tkh, dx, dy, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_x, grdf_z, zf, zf)
+            qp, _ = diffuse_scalar_3d(qp, tkh, dx, dy, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_x, grdf_z, zf, zf)
+            if icyc == 1:
+                coefs = [precip_coefs(rho[k], tabs0[k], pres[k]) for k in range(nzm)]
+            qn = np.zeros((nx, ny, nzm)); tabs = tabs.copy()
+            for k in range(nzm):
+                for j in range(ny):
+                    for i in range(nx):
+                        q_, qp_, tb, qn_ = cloud_cell(t[i, j, k], gamaz[k], pres[k], qt[i, j, k], qp[i, j, k])
+                        q_, qp_, qn_, _, _ = precip_proc_cell(dtn, tb, pres[k], coefs[k], q_, qp_, qn_)
+                        qt[i, j, k] = q_; qp[i, j, k] = qp_; qn[i, j, k] = qn_; tabs[i, j, k] = tb
+            qv, qcl, qci, qpl, qpi = diagnose_micro(tabs)
+            tabs = t - gamaz[None, None, :] + fac_cond * (qcl + qpl) + fac_sub * (qci + qpi)
+            u0 = mean(u); v0 = mean(v); tabs0 = mean(tabs); q0 = mean(qv + qcl + qci); qn0 = mean(qcl + qci); qp0 = mean(qpl + qpi)
+            qv0 = q0 - qn0
+            na, nb, nc = nc, na, nb
+        acc = crm_outputs_one_step(g, plev, dt_gl, inp, tabs_in, qp_in, u, v, wf, tabs, qv, qcl, qci, qpl, qpi, nxr, nyr, nstop=nstop, acc=acc,
+                                   finalize=nstep == nstop)
+    out = acc
+    out["prec_crm"] = box(precsfc[:, None])[:, :, 0] * dz / dt / float(nstop) / f4(1000.)
+    out["tk"] = tk; out["tkh"] = tkh; out["qcl"] = qcl; out["qci"] = qci; out["qpl"] = qpl; out["qpi"] = qpi
+    out["ncycle_sum"] = ncycle_sum
+    return dict(state=dict(u_wind=u, v_wind=v, w_wind=wf[:, :, :nzm], temperature=tabs, qt=qt, qp=qp, qn=qn), out=out)

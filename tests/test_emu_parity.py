@@ -165,3 +165,20 @@ def test_emu_device_code_matches_the_numpy_golden_fixture(emu):
     h.close()
     bad = mgn.compare(dims, st, rad, out, z, 1e-9)
     assert not bad, bad
+
+
+def test_emu_device_code_matches_the_numpy_golden_fixture_3d(emu, monkeypatch):
+    """The 3-D device code path (emulated) against the fixture of the independent numpy 3-D crm()."""
+    import sys
+    gold = os.path.join(cm.ROOT, "tests", "golden")
+    if gold not in sys.path:
+        sys.path.insert(0, gold)
+    import make_golden_numpy as mgn
+    monkeypatch.setenv("CRM_B200_CT", "1")
+    dims, inp, st, rad, z = mgn.load_case_3d()
+    h = cm.libmod.CrmHandle(dims, lib_path=emu)
+    out = h.run(dims, inp, st, rad)
+    assert h.stats()["ncycle_sum"] == int(z["ncycle_sum"])
+    h.close()
+    bad = mgn.compare_3d(dims, st, rad, out, z, 1e-9)
+    assert not bad, bad

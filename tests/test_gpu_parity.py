@@ -612,3 +612,22 @@ def test_numpy_golden_fixture_on_device(name):
     h.close()
     bad = mgn.compare(dims, st, rad, out, z, 1e-9)
     assert not bad, bad
+
+
+@pytest.mark.gpu
+def test_numpy_golden_fixture_3d_on_device():
+    """Device vs the independent numpy 3-D crm() (tests/golden/numpy_3d_8x8x28.npz, ref_numpy.crm_call_numpy_3d): a complete 3-step call of a
+    3-D CRM with clouds and precipitation replayed through the C ABI from the file alone -- no C++ oracle in this comparison."""
+    import os
+    import sys
+    gold = os.path.join(cm.ROOT, "tests", "golden")
+    if gold not in sys.path:
+        sys.path.insert(0, gold)
+    import make_golden_numpy as mgn
+    dims, inp, st, rad, z = mgn.load_case_3d()
+    h = cm.libmod.CrmHandle(dims)
+    out = h.run(dims, inp, st, rad)
+    assert h.stats()["ncycle_sum"] == int(z["ncycle_sum"])
+    h.close()
+    bad = mgn.compare_3d(dims, st, rad, out, z, 1e-9)
+    assert not bad, bad

@@ -361,3 +361,15 @@ def test_oracle_matches_the_numpy_golden_fixture(name):
     bad = mgn.compare(dims, st, rad, out, z, 1e-10)
     assert not bad, bad
     assert float(z["out_prec_crm"].max()) > 0 and float(z["out_cld"].max()) > 0
+
+
+def test_oracle_matches_the_numpy_golden_fixture_3d():
+    """The 3-D fixture (tests/golden/numpy_3d_8x8x28.npz): a complete 3-step call of a 3-D CRM computed by ref_numpy.crm_call_numpy_3d (RUN3D
+    momentum routines, advect_scalar3D, diffuse_scalar3D, shear_prod3D, a dense 3-D pressure solve)."""
+    mgn = _numpy_golden()
+    dims, inp, st, rad, z = mgn.load_case_3d()
+    out, stats = ob.run(dims, inp, st, rad)
+    assert stats["ncycle_sum"] == int(z["ncycle_sum"])
+    bad = mgn.compare_3d(dims, st, rad, out, z, 1e-10)
+    assert not bad, bad
+    assert float(z["out_prec_crm"].max()) > 0 and float(z["out_cld"].max()) > 0 and float(np.abs(z["state_v_wind"]).max()) > 0
