@@ -1474,10 +1474,14 @@ def abcoefs(nstep, dt3, na, nb, nc):
     return at, bt, ct
 
 
-def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad):
+def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad, igstep=3, gcol=0, rng=None, use_accel=False, accel_uv=False,
+                   accel_factor=0.):
     """A complete crm() call (crm_module.F90:286-1594) of ONE 2-D sam1mom CRM in numpy, composed from the routine restatements of this file:
     prologue, the step loop with the CFL sub-cycling of kurant (ncycle) and the variable-step Adams-Bashforth rotation of the tendency slots,
-    per-step statistics, epilogue.  No mean-state acceleration, no setperturb (igstep > 1).  Returns dict(state=..., out=...)."""
+    per-step statistics, epilogue; optionally the first-step noise of setperturb.F90 (igstep <= 1: `rng(seed, n)` must return the Mersenne-Twister
+    draws of RNG_MT.F90, seed = gcol * 1000, crm_module.F90:677-681) and mean-state acceleration (accelerate_crm.F90: nstop reduced by
+    1 + crm_accel_factor, acceleration after micro_proc of every sub-step, nstop extended once if the 5 K guard fires).
+    Returns dict(state=..., out=...)."""
     nx, nzm = tabs.shape
     u, w, tabs, qt, qp, qn = (a.copy() for a in (u, w, tabs, qt, qp, qn))
     tabs_in, qp_in = tabs.copy(), qp.copy()
@@ -1502,7 +1506,7 @@ def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad):
     # ---- prologue
     qv, qcl, qci, qpl, qpi = diagnose_micro(tabs)
     t = tabs + gamaz[None, :] - fac_cond * qcl - fac_sub * qci - fac_cond * qpl - fac_sub * qpi
-    u0 = mean(u); t00 = mean(t + fac_cond * qpl + fac_sub * qpi); tabs0 = mean(tabs)
+    u0 = mean(u); t0 = mean(t); t00 = mean(t + fac_cond * qpl + fac_sub * qpi); tabs0 = mean(tabs)
     q0 = mean(qv + qcl + qci); qv0 = mean(qv); qn0 = mean(qcl + qci); qp0 = mean(qpl + qpi)
     idt_gl = 1. / dt_gl
     ttend = np.zeros(nzm); qtend = np.zeros(nzm); utend = np.zeros(nzm)
@@ -1515,6 +1519,21 @@ def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad):
     grdf_x = np.minimum(16., dx * dx / ((adz * dz) * (adz * dz))); grdf_z = np.ones(nzm)
     nstop = int(dt_gl / dt)
     dt = dt_gl / nstop
+    if igstep <= 1:                                                 # setperturb.F90:34-75 (setperturb_sgs does nothing with dosmagor)
+        r_ = rng(int(gcol) * 1000, 5 * nx)
+        n_ = 0
+        for k in range(5):
+            scal = float(5 + 1 - (k + 1)) / float(5)
+            t02 = 0.
+            for i in range(nx):
+                t[i, k] = t[i, k] + 1 * (1. - 2. * r_[n_]) * scal
+                n_ += 1
+                t02 = t02 + t[i, k] * factor_xy
+            t[:, k] = t[:, k] * t0[k] / t02
+    cease = False
+    if use_accel:
+        assert nstop % int(1 + accel_factor) == 0
+        nstop = int(nstop / (1 + accel_factor))
     wf = np.zeros((nx, nzm + 1)); wf[:, :nzm] = w
     du = [np.zeros((nx, nzm)) for _ in range(3)]; dw = [np.zeros((nx, nzm + 1)) for _ in range(3)]
     na, nb, nc = 0, 1, 2
@@ -1525,7 +1544,9 @@ def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad):
     ncycle_sum = 0
     nxr = qrad.shape[0]
     zf = np.zeros(nx)
-    for nstep in range(1, nstop + 1):
+    nstep = 0
+    while nstep < nstop:
+        nstep += 1
         cfl = kurant_2d(u, wf, tkh, dx, dz, dt, adz, adzw)
         ncycle = max(1, int(math.ceil(cfl / f4(0.7))))
         ncycle_sum += ncycle
@@ -1577,9 +1598,15 @@ def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad):
                     q_, qp_, qn_, _, _ = precip_proc_cell(dtn, tb, pres[k], coefs[k], q_, qp_, qn_)
                     qt[i, k] = q_; qp[i, k] = qp_; qn[i, k] = qn_; tabs[i, k] = tb
             qv, qcl, qci, qpl, qpi = diagnose_micro(tabs)
+            if use_accel and not cease:                              # crm_module.F90:866-868
+                cease, t_a, qt_a, u_a, qv_a, qcl_a, qci_a = accelerate_crm_2d(t, qt, u, qv, qcl, qci, t0, q0, u0, accel_uv, accel_factor)
+                if cease:
+                    nstop = int(nstop + (nstop - nstep + 1) * accel_factor)
+                else:
+                    t, qt, u, qv, qcl, qci = t_a, qt_a, u_a, qv_a, qcl_a, qci_a
             # diagnose
             tabs = t - gamaz[None, :] + fac_cond * (qcl + qpl) + fac_sub * (qci + qpi)
-            u0 = mean(u); tabs0 = mean(tabs); q0 = mean(qv + qcl + qci); qn0 = mean(qcl + qci); qp0 = mean(qpl + qpi)
+            u0 = mean(u); t0 = mean(t); tabs0 = mean(tabs); q0 = mean(qv + qcl + qci); qn0 = mean(qcl + qci); qp0 = mean(qpl + qpi)
             qv0 = q0 - qn0
             na, nb, nc = nc, na, nb                                  # nn = na; na = nc; nc = nb; nb = nn
         last = nstep == nstop

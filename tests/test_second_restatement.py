@@ -566,3 +566,48 @@ def test_whole_crm_call_against_the_numpy_composition(nzm, plev, spin, nsteps, w
         a = float(getattr(out, n)[ic]); worst[n] = abs(a - r["out"][n]) / max(abs(a), 1e-300) if a != 0 else abs(r["out"][n])
     bad = {k: v for k, v in worst.items() if v > 1e-10}
     assert not bad, bad
+
+
+@pytest.mark.parametrize("variant", ["setperturb", "msa", "msa_uv"])
+def test_whole_crm_call_with_setperturb_and_mean_state_acceleration(variant):
+    """The numpy crm() with the first-step noise (igstep = 1: RNG_MT draws seeded with gcol * 1000, setperturb.F90) and with mean-state
+    acceleration (accelerate_crm.F90: nstop / (1 + factor), acceleration after micro_proc of every sub-step) against the oracle."""
+    import test_oracle_kat as tk
+    kw = {}
+    nsteps = 4
+    if variant.startswith("msa"):
+        kw = dict(use_crm_accel=True, crm_accel_factor=2.0, crm_accel_uv=variant == "msa_uv")
+        nsteps = 6
+    dims = cm.small_dims(ncrms=6, nx=16, nzm=28, plev=30, nsteps=nsteps, **kw)
+    dims, inp, st, rad = cm.make_case(dims, 300)
+    ic = int(np.argmax(st.qp.reshape(dims.ncrms, -1).max(axis=1)))
+    dims, inp, st, rad = cm.single_crm_case(dims, inp, st, rad, ic)
+    if variant == "setperturb":
+        dims = dims.copy(igstep=1)
+    st_in = st.copy()
+    out, stats = cm.ob.run(dims, inp, st, rad)
+    g = rn.crm_grid(inp.zmid[0], inp.zint[0], inp.pmid[0], inp.pint[0], inp.pdel[0], dims.nzm)
+    col = dict(tl=inp.tl[0], ql=inp.ql[0], qccl=inp.qccl[0], qiil=inp.qiil[0], ul=inp.ul[0], pdel=inp.pdel[0])
+    r = rn.crm_call_numpy(g, dims.plev, dims.dx, dims.dt, dims.dt_gl, col, st_in.u_wind[0][:, 0, :], st_in.w_wind[0][:, 0, :],
+                          st_in.temperature[0][:, 0, :], st_in.qt[0][:, 0, :], st_in.qp[0][:, 0, :], st_in.qn[0][:, 0, :], rad.qrad[0][:, 0, :],
+                          igstep=dims.igstep, gcol=int(inp.gcol[0]), rng=tk._rng_mt_python, use_accel=dims.use_crm_accel,
+                          accel_uv=dims.crm_accel_uv, accel_factor=dims.crm_accel_factor)
+    assert r["out"]["ncycle_sum"] == stats["ncycle_sum"]
+    if variant.startswith("msa"):
+        assert stats["nstop"] == 2                                 # 6 / (1 + 2)
+    worst = {}
+    for n in ("u_wind", "w_wind", "temperature", "qt", "qp", "qn"):
+        a = getattr(st, n)[0][:, 0, :]; b = r["state"][n]
+        worst["state." + n] = float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-300))
+    for n in ("sltend", "qltend", "qcltend", "qiltend", "cld", "gliqwp", "mcup", "mu_crm", "qr_mean"):
+        a = getattr(out, n)[0]; b = r["out"][n]
+        worst[n] = float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-300)) if np.abs(a).max() > 0 else float(np.abs(b).max())
+    for n in ("temperature", "qv", "qc"):
+        a = getattr(rad, n)[0][:, 0, :]; b = r["out"]["rad"][n][:, 0, :]
+        worst["rad." + n] = float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-300))
+    bad = {k: v for k, v in worst.items() if v > 1e-10}
+    assert not bad, bad
+    if variant == "setperturb":                                   # the noise really went in: the result differs from the unperturbed call
+        r0 = rn.crm_call_numpy(g, dims.plev, dims.dx, dims.dt, dims.dt_gl, col, st_in.u_wind[0][:, 0, :], st_in.w_wind[0][:, 0, :],
+                               st_in.temperature[0][:, 0, :], st_in.qt[0][:, 0, :], st_in.qp[0][:, 0, :], st_in.qn[0][:, 0, :], rad.qrad[0][:, 0, :])
+        assert float(np.abs(r0["state"]["temperature"] - r["state"]["temperature"]).max()) > 1e-3
