@@ -1566,9 +1566,9 @@ def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad, ig
             qt, t, _, _, pice = ice_fall_2d(qcl, qci, tabs, qt, t, dz, dtn, adz, rho)
             precsfc = precsfc + pice
             # sgs_proc, advect_mom, sgs_mom
-            tk, tkh, _ = sgs_2d(dx, dt, dz, adz, adzw, bet, presi, u0, u, wf, t, tabs, qv, qcl, qci, qpl, qpi, tk)
-            da, dwa, _ = advect_mom_2d(u, wf, dx, dz, rho, rhow, adz, adzw)
-            dd, dwd, _ = diffuse_mom_2d(u, wf, tk, dx, dz, rho, rhow, adz, adzw, grdf_x, grdf_z)
+            tk, tkh, tke = sgs_2d(dx, dt, dz, adz, adzw, bet, presi, u0, u, wf, t, tabs, qv, qcl, qci, qpl, qpi, tk)
+            da, dwa, uwle = advect_mom_2d(u, wf, dx, dz, rho, rhow, adz, adzw)
+            dd, dwd, uwsb = diffuse_mom_2d(u, wf, tk, dx, dz, rho, rhow, adz, adzw, grdf_x, grdf_z)
             du[na] = du[na] + da + dd; dw[na] = dw[na] + dwa + dwd
             # pressure, adams
             du[na], dw[na], _ = pressure_2d(u, wf, [du[na], du[nb], du[nc]], [dw[na], dw[nb], dw[nc]], (at, bt, ct, dt3[na]), dx, dz, rho, rhow, adz, adzw)
@@ -1578,24 +1578,30 @@ def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad, ig
             wmf = 0.5 * (wf + dw[nc]) * (rhow * (dtn / dz))[None, :]
             # advect_all_scalars (incl. micro_precip_fall), uvw
             t, _ = advect_scalar2d(t, umf, wmf, rho, rhow, adz)
-            qt, _ = advect_scalar2d(qt, umf, wmf, rho, rhow, adz)
-            qp, _ = advect_scalar2d(qp, umf, wmf, rho, rhow, adz)
+            qt_b, qp_b = qt, qp
+            qt, mkwle1 = advect_scalar2d(qt, umf, wmf, rho, rhow, adz)
+            qp, mkwle2 = advect_scalar2d(qp, umf, wmf, rho, rhow, adz)
+            mkadv1 = np.array([_slab((qt - qt_b)[:, k:k + 1]) for k in range(nzm)]); mkadv2 = np.array([_slab((qp - qp_b)[:, k:k + 1]) for k in range(nzm)])
             qp, t, pfall, _ = precip_fall_columns(dz, dtn, rho, rhow, adz, tabs, qp, t)
             precsfc = precsfc + pfall
             u = du[nc]; wf = dw[nc]
             # sgs_scalars
             t, _ = diffuse_scalar_2d(t, tkh, dx, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_z, zf, zf)
-            qt, _ = diffuse_scalar_2d(qt, tkh, dx, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_z, zf, zf)
-            qp, _ = diffuse_scalar_2d(qp, tkh, dx, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_z, zf, zf)
+            qt_b, qp_b = qt, qp
+            qt, mkwsb1 = diffuse_scalar_2d(qt, tkh, dx, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_z, zf, zf)
+            qp, mkwsb2 = diffuse_scalar_2d(qp, tkh, dx, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_z, zf, zf)
+            mkdiff1 = np.array([_slab((qt - qt_b)[:, k:k + 1]) for k in range(nzm)]); mkdiff2 = np.array([_slab((qp - qp_b)[:, k:k + 1]) for k in range(nzm)])
             # micro_proc: the bulk coefficients are refreshed with the current tabs0 on the first sub-step of every CRM step
             # (MICRO_SAM1MOM/microphysics.F90:309)
             if icyc == 1:
                 coefs = [precip_coefs(rho[k], tabs0[k], pres[k]) for k in range(nzm)]
             qn = np.zeros((nx, nzm)); tabs = tabs.copy()
+            qpsrc = np.zeros(nzm); qpevp = np.zeros(nzm)
             for k in range(nzm):
                 for i in range(nx):
                     q_, qp_, tb, qn_ = cloud_cell(t[i, k], gamaz[k], pres[k], qt[i, k], qp[i, k])
-                    q_, qp_, qn_, _, _ = precip_proc_cell(dtn, tb, pres[k], coefs[k], q_, qp_, qn_)
+                    q_, qp_, qn_, ds_, de_ = precip_proc_cell(dtn, tb, pres[k], coefs[k], q_, qp_, qn_)
+                    qpsrc[k] = qpsrc[k] + ds_; qpevp[k] = qpevp[k] + de_
                     qt[i, k] = q_; qp[i, k] = qp_; qn[i, k] = qn_; tabs[i, k] = tb
             qv, qcl, qci, qpl, qpi = diagnose_micro(tabs)
             if use_accel and not cease:                              # crm_module.F90:866-868
@@ -1617,6 +1623,28 @@ def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad, ig
     out["prec_crm"] = precsfc * dz / dt / float(nstop) / f4(1000.)
     out["tk"] = tk; out["tkh"] = tkh; out["qcl"] = qcl; out["qci"] = qci; out["qpl"] = qpl; out["qpi"] = qpi
     out["ncycle_sum"] = ncycle_sum
+    # fluxes and other statistics of crm_module.F90:1516-1585: values of the LAST sub-step, scaled as the reference scales them
+    irt = 1. / dt_gl
+    for name in ("flux_qt", "fluxsgs_qt", "flux_qp", "qt_trans", "qp_trans", "flux_u", "tkz", "tkez", "tkesgsz", "qt_ls", "t_ls", "qp_src", "qp_evp"):
+        out[name] = np.zeros(plev)
+    for k in range(1, nzm + 1):
+        l = plev - k
+        tmp1 = dz / rhow[k - 1]; tmp2 = tmp1 / dtn
+        wsb1 = mkwsb1[k - 1] * tmp1 * rhow[k - 1] * factor_xy / nstop; wsb2 = mkwsb2[k - 1] * tmp1 * rhow[k - 1] * factor_xy / nstop
+        wle1 = mkwle1[k - 1] * tmp2 * rhow[k - 1] * factor_xy / nstop; wle2 = mkwle2[k - 1] * tmp2 * rhow[k - 1] * factor_xy / nstop
+        out["flux_qt"][l] = wle1 + wsb1; out["fluxsgs_qt"][l] = wsb1; out["flux_qp"][l] = wle2 + wsb2
+        out["qt_trans"][l] = mkadv1[k - 1] * factor_xy * irt + mkdiff1[k - 1] * factor_xy * irt
+        out["qp_trans"][l] = mkadv2[k - 1] * factor_xy * irt + mkdiff2[k - 1] * factor_xy * irt
+        out["flux_u"][l] = (uwle[k - 1] + uwsb[k - 1]) * tmp1 * factor_xy / nstop
+        u2z = w2z = 0.
+        for i in range(nx):
+            u2z = u2z + (u[i, k - 1] - u0[k - 1]) ** 2
+            w2z = w2z + 0.5 * (wf[i, k] ** 2 + wf[i, k - 1] ** 2)
+        out["tkesgsz"][l] = rho[k - 1] * _slab(tke[:, k - 1:k]) * factor_xy
+        out["tkez"][l] = rho[k - 1] * 0.5 * (u2z + 0. + w2z) * factor_xy + out["tkesgsz"][l]
+        out["tkz"][l] = _slab(tk[:, k - 1:k]) * factor_xy
+        out["qp_src"][l] = qpsrc[k - 1] * factor_xy * irt; out["qp_evp"][l] = qpevp[k - 1] * factor_xy * irt
+        out["qt_ls"][l] = qtend[k - 1]; out["t_ls"][l] = ttend[k - 1]
     return dict(state=dict(u_wind=u, w_wind=wf[:, :nzm], temperature=tabs, qt=qt, qp=qp, qn=qn), out=out)
 
 
