@@ -355,9 +355,10 @@ def fall_coefs():
     return vrain, vsnow, vgrau, crain, csnow, cgrau
 
 
-def precip_fall_columns(dz, dtn, rho, rhow, adz, tabs, qp, t):
+def precip_fall_columns(dz, dtn, rho, rhow, adz, tabs, qp, t, stats=None):
     """micro_precip_fall / precip_fall (microphysics.F90:491-830, hydro_type 2) for columns (ncol, nzm) sharing one batch-global
-    nprec.  Returns (qp, t, precsfc(ncol), nprec)."""
+    nprec.  Returns (qp, t, precsfc(ncol), nprec).  `stats` (optional dict with arrays qpfall(nzm), precflux(nzm), precssfc(ncol)) accumulates
+    the budget statistics of microphysics.F90:772-785 in place."""
     ncol, nzm = qp.shape
     v = fall_coefs()
     eps = f4(1.e-10)
@@ -399,7 +400,12 @@ def precip_fall_columns(dz, dtn, rho, rhow, adz, tabs, qp, t):
                 qp[c, k] = qp[c, k] - (fz[k + 1] - fz[k]) * irhoadz[k]
                 lat_heat = -(lfac[c, k + 1] * fz[k + 1] - lfac[c, k] * fz[k]) * irhoadz[k]
                 t[c, k] = t[c, k] - lat_heat
+                if stats is not None:
+                    stats["qpfall"][k] = stats["qpfall"][k] + (-(fz[k + 1] - fz[k]) * irhoadz[k] * 1.)
+                    stats["precflux"][k] = stats["precflux"][k] - fz[k] * 1.
             precsfc[c] = precsfc[c] - fz[0] * 1.
+            if stats is not None:
+                stats["precssfc"][c] = stats["precssfc"][c] - fz[0] * (1. - omega[c, 0]) * 1.
             if iprec < nprec:
                 for k in range(nzm):
                     w0 = rhofac[k] * term_vel_qp(qp[c, k], rho[k], tabs[c, k], v)
@@ -1539,7 +1545,7 @@ def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad, ig
     na, nb, nc = 0, 1, 2
     dt3 = [0., 0., 0.]
     tk = np.zeros((nx, nzm)); tkh = np.zeros((nx, nzm))
-    precsfc = np.zeros(nx)
+    precsfc = np.zeros(nx); pstats = dict(qpfall=np.zeros(nzm), precflux=np.zeros(nzm), precssfc=np.zeros(nx))
     acc = None
     ncycle_sum = 0
     nxr = qrad.shape[0]
@@ -1564,7 +1570,7 @@ def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad, ig
             du_d, dw_d, t, qt = damping_2d(u, wf, t, qt, qv, qv0, z, dt, dtn)
             du[na] = du[na] + du_d; dw[na] = dw[na] + dw_d
             qt, t, _, _, pice = ice_fall_2d(qcl, qci, tabs, qt, t, dz, dtn, adz, rho)
-            precsfc = precsfc + pice
+            precsfc = precsfc + pice; pstats["precssfc"] = pstats["precssfc"] + pice      # ice_fall.F90:158-159: all of it is solid
             # sgs_proc, advect_mom, sgs_mom
             tk, tkh, tke = sgs_2d(dx, dt, dz, adz, adzw, bet, presi, u0, u, wf, t, tabs, qv, qcl, qci, qpl, qpi, tk)
             da, dwa, uwle = advect_mom_2d(u, wf, dx, dz, rho, rhow, adz, adzw)
@@ -1582,7 +1588,7 @@ def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad, ig
             qt, mkwle1 = advect_scalar2d(qt, umf, wmf, rho, rhow, adz)
             qp, mkwle2 = advect_scalar2d(qp, umf, wmf, rho, rhow, adz)
             mkadv1 = np.array([_slab((qt - qt_b)[:, k:k + 1]) for k in range(nzm)]); mkadv2 = np.array([_slab((qp - qp_b)[:, k:k + 1]) for k in range(nzm)])
-            qp, t, pfall, _ = precip_fall_columns(dz, dtn, rho, rhow, adz, tabs, qp, t)
+            qp, t, pfall, _ = precip_fall_columns(dz, dtn, rho, rhow, adz, tabs, qp, t, stats=pstats)
             precsfc = precsfc + pfall
             u = du[nc]; wf = dw[nc]
             # sgs_scalars
@@ -1625,7 +1631,8 @@ def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad, ig
     out["ncycle_sum"] = ncycle_sum
     # fluxes and other statistics of crm_module.F90:1516-1585: values of the LAST sub-step, scaled as the reference scales them
     irt = 1. / dt_gl
-    for name in ("flux_qt", "fluxsgs_qt", "flux_qp", "qt_trans", "qp_trans", "flux_u", "tkz", "tkez", "tkesgsz", "qt_ls", "t_ls", "qp_src", "qp_evp"):
+    for name in ("flux_qt", "fluxsgs_qt", "flux_qp", "qt_trans", "qp_trans", "flux_u", "tkz", "tkez", "tkesgsz", "qt_ls", "t_ls", "qp_src", "qp_evp", "qp_fall",
+                 "precflux"):
         out[name] = np.zeros(plev)
     for k in range(1, nzm + 1):
         l = plev - k
@@ -1645,6 +1652,18 @@ def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad, ig
         out["tkz"][l] = _slab(tk[:, k - 1:k]) * factor_xy
         out["qp_src"][l] = qpsrc[k - 1] * factor_xy * irt; out["qp_evp"][l] = qpevp[k - 1] * factor_xy * irt
         out["qt_ls"][l] = qtend[k - 1]; out["t_ls"][l] = ttend[k - 1]
+        out["qp_fall"][l] = pstats["qpfall"][k - 1] * factor_xy * irt
+        out["precflux"][l] = pstats["precflux"][k - 1] * factor_xy * dz / dt / nstop / f4(1000.)
+    # surface precipitation split (crm_module.F90:1422-1473): convective above 10 mm/day, stratiform below; snow parts from precssfc
+    ps = precsfc * dz / dt / float(nstop); pss = pstats["precssfc"] * dz / dt / float(nstop)
+    pc = pl = psc = psl = 0.
+    for i in range(nx):
+        if ps[i] > f4(10.) / f4(86400.):
+            pc = pc + ps[i]; psc = psc + pss[i]
+        else:
+            pl = pl + ps[i]; psl = psl + pss[i]
+    out["precc"] = pc * factor_xy / f4(1000.); out["precl"] = pl * factor_xy / f4(1000.)
+    out["precsc"] = psc * factor_xy / f4(1000.); out["precsl"] = psl * factor_xy / f4(1000.)
     return dict(state=dict(u_wind=u, w_wind=wf[:, :nzm], temperature=tabs, qt=qt, qp=qp, qn=qn), out=out)
 
 

@@ -556,14 +556,15 @@ def test_whole_crm_call_against_the_numpy_composition(nzm, plev, spin, nsteps, w
         worst[n] = float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-300))
     for n in ("sltend", "qltend", "qcltend", "qiltend", "cld", "cldtop", "gicewp", "gliqwp", "mcup", "mcdn", "mcuup", "mcudn", "mctot", "qc_mean", "qi_mean",
               "qs_mean", "qg_mean", "qr_mean", "mu_crm", "md_crm", "eu_crm", "du_crm", "ed_crm",
-              "flux_qt", "fluxsgs_qt", "flux_qp", "qt_trans", "qp_trans", "flux_u", "tkz", "tkez", "tkesgsz", "qt_ls", "t_ls", "qp_src", "qp_evp"):
+              "flux_qt", "fluxsgs_qt", "flux_qp", "qt_trans", "qp_trans", "flux_u", "tkz", "tkez", "tkesgsz", "qt_ls", "t_ls", "qp_src", "qp_evp", "qp_fall",
+              "precflux"):
         a = getattr(out, n)[ic]; b = r["out"][n]
         worst[n] = float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-300)) if np.abs(a).max() > 0 else float(np.abs(b).max())
     worst["prec_crm"] = float(np.abs(out.prec_crm[ic][:, 0] - r["out"]["prec_crm"]).max() / max(np.abs(out.prec_crm[ic]).max(), 1e-300))
     for n in ("temperature", "qv", "qc", "qi", "cld"):
         a = getattr(rad, n)[ic][:, 0, :]; b = r["out"]["rad"][n][:, 0, :]
         worst["rad." + n] = float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-300)) if np.abs(a).max() > 0 else float(np.abs(b).max())
-    for n in ("cltot", "clhgh", "clmed", "cllow", "prectend", "precstend"):
+    for n in ("cltot", "clhgh", "clmed", "cllow", "prectend", "precstend", "precc", "precl", "precsc", "precsl"):
         a = float(getattr(out, n)[ic]); worst[n] = abs(a - r["out"][n]) / max(abs(a), 1e-300) if a != 0 else abs(r["out"][n])
     bad = {k: v for k, v in worst.items() if v > 1e-10}
     assert not bad, bad
