@@ -1847,3 +1847,25 @@ def crm_call_numpy_3d(g, plev, dx, dt, dt_gl, inp, u, v, w, tabs, qt, qp, qn, qr
     out["tk"] = tk; out["tkh"] = tkh; out["qcl"] = qcl; out["qci"] = qci; out["qpl"] = qpl; out["qpi"] = qpi
     out["ncycle_sum"] = ncycle_sum
     return dict(state=dict(u_wind=u, v_wind=v, w_wind=wf[:, :, :nzm], temperature=tabs, qt=qt, qp=qp, qn=qn), out=out)
+
+
+def z0_est(z, bflx, wnd, ustar):
+    """crmsurface.F90:104-131 (REAL(4) parameters; c1 = 3.14159/2. - 3.*log(2.) is a REAL(4) expression)."""
+    vonk, am, bm, eps = f4(0.4), f4(4.8), f4(19.3), f4(1.e-10)
+    c1 = float(F(3.14159) / F(2.) - F(3.) * np.log(F(2.)))
+    rlmo = -bflx * vonk / (ustar ** 3 + eps)
+    zeta = min(1., z * rlmo)
+    if zeta >= 0.:
+        psi1 = -am * zeta
+    else:
+        x = math.sqrt(math.sqrt(f4(1.0) - bm * zeta))
+        psi1 = 2. * math.log(f4(1.0) + x) + math.log(f4(1.0) + x * x) - 2. * math.atan(x) + c1
+    lnz = max(0., vonk * wnd / (ustar + eps) + psi1)
+    return z * math.exp(-lnz)
+
+
+def crm_z0m(g, tau00, bflxls, wndls):
+    """crm_module.F90:583-585: the roughness length handed back in crm_output%z0m."""
+    ustar = math.sqrt(tau00 / g["rho"][0])
+    z0 = z0_est(g["z"][0], bflxls, wndls, ustar)
+    return max(f4(0.00001), min(1., z0))

@@ -607,6 +607,10 @@ def test_whole_crm_call_with_setperturb_and_mean_state_acceleration(variant):
     for n in ("temperature", "qv", "qc"):
         a = getattr(rad, n)[0][:, 0, :]; b = r["out"]["rad"][n][:, 0, :]
         worst["rad." + n] = float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-300))
+    worst["z0m"] = abs(rn.crm_z0m(g, float(inp.tau00[0]), float(inp.bflxls[0]), float(inp.wndls[0])) - float(out.z0m[0])) / float(out.z0m[0])
+    assert float(out.taux[0]) == 0. and float(out.tauy[0]) == 0.          # crmsurface is off by default (dosurface = .false.)
+    worst["z0m"] = abs(rn.crm_z0m(g, float(inp.tau00[0]), float(inp.bflxls[0]), float(inp.wndls[0])) - float(out.z0m[0])) / float(out.z0m[0])
+    assert float(out.taux[0]) == 0. and float(out.tauy[0]) == 0.          # crmsurface is off by default (dosurface = .false.)
     bad = {k: v for k, v in worst.items() if v > 1e-10}
     assert not bad, bad
     if variant == "setperturb":                                   # the noise really went in: the result differs from the unperturbed call
