@@ -617,3 +617,40 @@ def test_whole_crm_call_with_setperturb_and_mean_state_acceleration(variant):
         r0 = rn.crm_call_numpy(g, dims.plev, dims.dx, dims.dt, dims.dt_gl, col, st_in.u_wind[0][:, 0, :], st_in.w_wind[0][:, 0, :],
                                st_in.temperature[0][:, 0, :], st_in.qt[0][:, 0, :], st_in.qp[0][:, 0, :], st_in.qn[0][:, 0, :], rad.qrad[0][:, 0, :])
         assert float(np.abs(r0["state"]["temperature"] - r["state"]["temperature"]).max()) > 1e-3
+
+
+@pytest.mark.parametrize("nsteps,wind", [(4, 1.), (3, 6.)])
+def test_whole_3d_crm_call_against_the_numpy_composition(nsteps, wind):
+    """The 3-D CRM as a whole call: ref_numpy.crm_call_numpy_3d (RUN3D momentum routines, advect_scalar3D, diffuse_scalar3D, shear_prod3D, a
+    dense 3-D pressure solve, v everywhere) against the oracle over several CRM steps; `wind` scales u and v so that kurant() sub-cycles."""
+    dims = cm.pkg.CrmDims(ncrms=3, nx=8, ny=8, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=20.0 * nsteps, igstep=3, nx_rad=2, ny_rad=2)
+    dims, inp, st, rad = cm.make_case(dims, 150)
+    ic = int(np.argmax(st.qp.reshape(dims.ncrms, -1).max(axis=1)))
+    dims, inp, st, rad = cm.single_crm_case(dims, inp, st, rad, ic)
+    st.u_wind *= wind; st.v_wind *= wind
+    st_in = st.copy()
+    out, stats = cm.ob.run(dims, inp, st, rad)
+    g = rn.crm_grid(inp.zmid[0], inp.zint[0], inp.pmid[0], inp.pint[0], inp.pdel[0], dims.nzm)
+    col = dict(tl=inp.tl[0], ql=inp.ql[0], qccl=inp.qccl[0], qiil=inp.qiil[0], ul=inp.ul[0], vl=inp.vl[0], pdel=inp.pdel[0])
+    r = rn.crm_call_numpy_3d(g, dims.plev, dims.dx, dims.dt, dims.dt_gl, col, st_in.u_wind[0], st_in.v_wind[0], st_in.w_wind[0], st_in.temperature[0],
+                             st_in.qt[0], st_in.qp[0], st_in.qn[0], rad.qrad[0])
+    assert r["out"]["ncycle_sum"] == stats["ncycle_sum"]
+    if wind > 1.:
+        assert stats["ncycle_sum"] > nsteps
+    worst = {}
+    for n in ("u_wind", "v_wind", "w_wind", "temperature", "qt", "qp", "qn"):
+        a = getattr(st, n)[0]; b = r["state"][n]
+        worst["state." + n] = float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-300))
+    for n in ("qcl", "qci", "qpl", "qpi", "tk", "tkh"):
+        worst[n] = float(np.abs(getattr(out, n)[0] - r["out"][n]).max() / max(np.abs(getattr(out, n)[0]).max(), 1e-300))
+    for n in ("sltend", "qltend", "qcltend", "qiltend", "cld", "cldtop", "gicewp", "gliqwp", "mcup", "mcdn", "mcuup", "mcudn", "qc_mean", "qr_mean", "mu_crm",
+              "md_crm"):
+        a = getattr(out, n)[0]; b = r["out"][n]
+        worst[n] = float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-300)) if np.abs(a).max() > 0 else float(np.abs(b).max())
+    worst["prec_crm"] = float(np.abs(out.prec_crm[0] - r["out"]["prec_crm"]).max() / max(np.abs(out.prec_crm[0]).max(), 1e-300))
+    for n in ("temperature", "qv", "qc", "qi", "cld"):
+        a = getattr(rad, n)[0]; b = r["out"]["rad"][n]
+        worst["rad." + n] = float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-300)) if np.abs(a).max() > 0 else float(np.abs(b).max())
+    bad = {k: v for k, v in worst.items() if v > 1e-10}
+    assert not bad, bad
+    assert float(np.abs(st.v_wind).max()) > 0 and float(out.cld.max()) > 0
