@@ -41,7 +41,7 @@ def main():
         dims, inp, st, rad = cm.single_crm_case(dims, inp, st, rad, ic)
         st.u_wind *= wind
         g = rn.crm_grid(inp.zmid[0], inp.zint[0], inp.pmid[0], inp.pint[0], inp.pdel[0], dims.nzm)
-        col = dict(tl=inp.tl[0], ql=inp.ql[0], qccl=inp.qccl[0], qiil=inp.qiil[0], ul=inp.ul[0], pdel=inp.pdel[0])
+        col = dict(tl=inp.tl[0], ql=inp.ql[0], qccl=inp.qccl[0], qiil=inp.qiil[0], ul=inp.ul[0], vl=inp.vl[0], pdel=inp.pdel[0])
         r = rn.crm_call_numpy(g, dims.plev, dims.dx, dims.dt, dims.dt_gl, col, st.u_wind[0][:, 0, :], st.w_wind[0][:, 0, :], st.temperature[0][:, 0, :],
                               st.qt[0][:, 0, :], st.qp[0][:, 0, :], st.qn[0][:, 0, :], rad.qrad[0][:, 0, :])
         d = {"dims": np.array([dims.nx, dims.nzm, dims.plev, dims.nx_rad, nsteps]), "dxdt": np.array([dims.dx, dims.dt, dims.dt_gl]),

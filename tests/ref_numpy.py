@@ -1654,6 +1654,15 @@ def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad, ig
         out["qt_ls"][l] = qtend[k - 1]; out["t_ls"][l] = ttend[k - 1]
         out["qp_fall"][l] = pstats["qpfall"][k - 1] * factor_xy * irt
         out["precflux"][l] = pstats["precflux"][k - 1] * factor_xy * dz / dt / nstop / f4(1000.)
+    # SPMOMTRANS (crm_module.F90:1200-1211): the reference forms these BEFORE it scales the slab sums by factor_xy (:1214-1224), so uln is
+    # the raw SUM of u over the CRM's columns -- reproduced as it is ("reference quirks")
+    ptop = plev - nzm + 1
+    out["ultend"] = np.zeros(plev); out["vltend"] = np.zeros(plev)
+    for k in range(1, nzm + 1):
+        l = plev - k
+        out["ultend"][l] = (_slab(u[:, k - 1:k]) - inp["ul"][l]) * irt
+        out["vltend"][l] = (0. - inp["vl"][l]) * irt                # 2-D: v == 0 in the CRM (v * YES3D), vln is the zero sum
+    out["ultend"][ptop - 1:ptop + 1] = 0.; out["vltend"][ptop - 1:ptop + 1] = 0.
     # surface precipitation split (crm_module.F90:1422-1473): convective above 10 mm/day, stratiform below; snow parts from precssfc
     ps = precsfc * dz / dt / float(nstop); pss = pstats["precssfc"] * dz / dt / float(nstop)
     pc = pl = psc = psl = 0.

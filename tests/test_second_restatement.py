@@ -537,7 +537,7 @@ def test_whole_crm_call_against_the_numpy_composition(nzm, plev, spin, nsteps, w
     out, stats = cm.ob.run(dims, inp, st, rad)
     ic = 0
     g = rn.crm_grid(inp.zmid[ic], inp.zint[ic], inp.pmid[ic], inp.pint[ic], inp.pdel[ic], dims.nzm)
-    col = dict(tl=inp.tl[ic], ql=inp.ql[ic], qccl=inp.qccl[ic], qiil=inp.qiil[ic], ul=inp.ul[ic], pdel=inp.pdel[ic])
+    col = dict(tl=inp.tl[ic], ql=inp.ql[ic], qccl=inp.qccl[ic], qiil=inp.qiil[ic], ul=inp.ul[ic], vl=inp.vl[ic], pdel=inp.pdel[ic])
     r = rn.crm_call_numpy(g, dims.plev, dims.dx, dims.dt, dims.dt_gl, col, st_in.u_wind[ic][:, 0, :], st_in.w_wind[ic][:, 0, :],
                           st_in.temperature[ic][:, 0, :], st_in.qt[ic][:, 0, :], st_in.qp[ic][:, 0, :], st_in.qn[ic][:, 0, :], rad.qrad[ic][:, 0, :])
     assert r["out"]["ncycle_sum"] == stats["ncycle_sum"] and stats["nstop"] == nsteps
@@ -557,7 +557,7 @@ def test_whole_crm_call_against_the_numpy_composition(nzm, plev, spin, nsteps, w
     for n in ("sltend", "qltend", "qcltend", "qiltend", "cld", "cldtop", "gicewp", "gliqwp", "mcup", "mcdn", "mcuup", "mcudn", "mctot", "qc_mean", "qi_mean",
               "qs_mean", "qg_mean", "qr_mean", "mu_crm", "md_crm", "eu_crm", "du_crm", "ed_crm",
               "flux_qt", "fluxsgs_qt", "flux_qp", "qt_trans", "qp_trans", "flux_u", "tkz", "tkez", "tkesgsz", "qt_ls", "t_ls", "qp_src", "qp_evp", "qp_fall",
-              "precflux"):
+              "precflux", "ultend", "vltend"):
         a = getattr(out, n)[ic]; b = r["out"][n]
         worst[n] = float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-300)) if np.abs(a).max() > 0 else float(np.abs(b).max())
     worst["prec_crm"] = float(np.abs(out.prec_crm[ic][:, 0] - r["out"]["prec_crm"]).max() / max(np.abs(out.prec_crm[ic]).max(), 1e-300))
@@ -589,7 +589,7 @@ def test_whole_crm_call_with_setperturb_and_mean_state_acceleration(variant):
     st_in = st.copy()
     out, stats = cm.ob.run(dims, inp, st, rad)
     g = rn.crm_grid(inp.zmid[0], inp.zint[0], inp.pmid[0], inp.pint[0], inp.pdel[0], dims.nzm)
-    col = dict(tl=inp.tl[0], ql=inp.ql[0], qccl=inp.qccl[0], qiil=inp.qiil[0], ul=inp.ul[0], pdel=inp.pdel[0])
+    col = dict(tl=inp.tl[0], ql=inp.ql[0], qccl=inp.qccl[0], qiil=inp.qiil[0], ul=inp.ul[0], vl=inp.vl[0], pdel=inp.pdel[0])
     r = rn.crm_call_numpy(g, dims.plev, dims.dx, dims.dt, dims.dt_gl, col, st_in.u_wind[0][:, 0, :], st_in.w_wind[0][:, 0, :],
                           st_in.temperature[0][:, 0, :], st_in.qt[0][:, 0, :], st_in.qp[0][:, 0, :], st_in.qn[0][:, 0, :], rad.qrad[0][:, 0, :],
                           igstep=dims.igstep, gcol=int(inp.gcol[0]), rng=tk._rng_mt_python, use_accel=dims.use_crm_accel,
