@@ -1114,7 +1114,7 @@ def crm_grid(zmid, zint, pmid, pint, pdel, nzm):
     rhow[0] = 2. * rhow[1] - rhow[2]
     rhow[nz - 1] = 2. * rhow[nzm - 1] - rhow[nzm - 2]
     presi = np.array([pint[plev - k + 1] / 100. for k in range(1, nz + 1)])
-    return dict(z=z, pres=pres, presi=presi, dz=dz, adz=adz, adzw=adzw, rho=rho, rhow=rhow)
+    return dict(z=z, zi=zi, pres=pres, presi=presi, dz=dz, adz=adz, adzw=adzw, rho=rho, rhow=rhow)
 
 
 def crm_outputs_one_step(g, plev, dt_gl, inp, tabs_in, qp_in, u, v, w, tabs, qv, qcl, qci, qpl, qpi, nx_rad, ny_rad, nstop=1, acc=None, finalize=True):
@@ -1481,13 +1481,15 @@ def abcoefs(nstep, dt3, na, nb, nc):
 
 
 def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad, igstep=3, gcol=0, rng=None, use_accel=False, accel_uv=False,
-                   accel_factor=0.):
+                   accel_factor=0., esmt=False):
     """A complete crm() call (crm_module.F90:286-1594) of ONE 2-D sam1mom CRM in numpy, composed from the routine restatements of this file:
     prologue, the step loop with the CFL sub-cycling of kurant (ncycle) and the variable-step Adams-Bashforth rotation of the tendency slots,
     per-step statistics, epilogue; optionally the first-step noise of setperturb.F90 (igstep <= 1: `rng(seed, n)` must return the Mersenne-Twister
     draws of RNG_MT.F90, seed = gcol * 1000, crm_module.F90:677-681) and mean-state acceleration (accelerate_crm.F90: nstop reduced by
     1 + crm_accel_factor, acceleration after micro_proc of every sub-step, nstop extended once if the 5 K guard fires).
-    Returns dict(state=..., out=...)."""
+    esmt = True: explicit scalar momentum transport (-DSP_ESMT, scalar_momentum.F90; inp needs ul_esmt, vl_esmt): two more scalars advected with
+    a positive offset, diffused, and pushed by the spectral pressure-gradient force every sub-step; every CRM starts from its OWN column of
+    ul_esmt (the reference's :419-424 reads row ncrms+1).  Returns dict(state=..., out=...)."""
     nx, nzm = tabs.shape
     u, w, tabs, qt, qp, qn = (a.copy() for a in (u, w, tabs, qt, qp, qn))
     tabs_in, qp_in = tabs.copy(), qp.copy()
@@ -1536,6 +1538,10 @@ def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad, ig
                 n_ += 1
                 t02 = t02 + t[i, k] * factor_xy
             t[:, k] = t[:, k] * t0[k] / t02
+    if esmt:
+        u_es = np.zeros((nx, nzm)); v_es = np.zeros((nx, nzm))
+        for k in range(1, nzm + 1):
+            u_es[:, k - 1] = inp["ul_esmt"][plev - k]; v_es[:, k - 1] = inp["vl_esmt"][plev - k]
     cease = False
     if use_accel:
         assert nstop % int(1 + accel_factor) == 0
@@ -1590,6 +1596,10 @@ def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad, ig
             mkadv1 = np.array([_slab((qt - qt_b)[:, k:k + 1]) for k in range(nzm)]); mkadv2 = np.array([_slab((qp - qp_b)[:, k:k + 1]) for k in range(nzm)])
             qp, t, pfall, _ = precip_fall_columns(dz, dtn, rho, rhow, adz, tabs, qp, t, stats=pstats)
             precsfc = precsfc + pfall
+            if esmt:                                                 # advect_all_scalars.F90:74-88
+                off = abs(min(float(u_es.min()), float(v_es.min()))) + f4(50.)
+                u_es, _ = advect_scalar2d(u_es + off, umf, wmf, rho, rhow, adz); v_es, _ = advect_scalar2d(v_es + off, umf, wmf, rho, rhow, adz)
+                u_es = u_es - off; v_es = v_es - off
             u = du[nc]; wf = dw[nc]
             # sgs_scalars
             t, _ = diffuse_scalar_2d(t, tkh, dx, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_z, zf, zf)
@@ -1597,6 +1607,11 @@ def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad, ig
             qt, mkwsb1 = diffuse_scalar_2d(qt, tkh, dx, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_z, zf, zf)
             qp, mkwsb2 = diffuse_scalar_2d(qp, tkh, dx, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_z, zf, zf)
             mkdiff1 = np.array([_slab((qt - qt_b)[:, k:k + 1]) for k in range(nzm)]); mkdiff2 = np.array([_slab((qp - qp_b)[:, k:k + 1]) for k in range(nzm)])
+            if esmt:                                                 # sgs.F90:445-450, then scalar_momentum_tend (crm_module.F90:855-857)
+                u_es, _ = diffuse_scalar_2d(u_es, tkh, dx, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_z, zf, zf)
+                v_es, _ = diffuse_scalar_2d(v_es, tkh, dx, dz, dtn, rho, rhow, adz, adzw, grdf_x, grdf_z, zf, zf)
+                u_es = u_es + esmt_pgf(u_es, wf, g["zi"], z, rho, dx) * dtn
+                v_es = v_es + esmt_pgf(v_es, wf, g["zi"], z, rho, dx) * dtn
             # micro_proc: the bulk coefficients are refreshed with the current tabs0 on the first sub-step of every CRM step
             # (MICRO_SAM1MOM/microphysics.F90:309)
             if icyc == 1:
@@ -1654,6 +1669,14 @@ def crm_call_numpy(g, plev, dx, dt, dt_gl, inp, u, w, tabs, qt, qp, qn, qrad, ig
         out["qt_ls"][l] = qtend[k - 1]; out["t_ls"][l] = ttend[k - 1]
         out["qp_fall"][l] = pstats["qpfall"][k - 1] * factor_xy * irt
         out["precflux"][l] = pstats["precflux"][k - 1] * factor_xy * dz / dt / nstop / f4(1000.)
+    if esmt:                                                         # crm_module.F90:1162-1192
+        out["u_tend_esmt"] = np.zeros(plev); out["v_tend_esmt"] = np.zeros(plev)
+        ptop_ = plev - nzm + 1
+        for k in range(1, nzm + 1):
+            l = plev - k
+            out["u_tend_esmt"][l] = (_slab(u_es[:, k - 1:k]) * factor_xy - inp["ul_esmt"][l]) * irt
+            out["v_tend_esmt"][l] = (_slab(v_es[:, k - 1:k]) * factor_xy - inp["vl_esmt"][l]) * irt
+        out["u_tend_esmt"][ptop_ - 1:ptop_ + 1] = 0.; out["v_tend_esmt"][ptop_ - 1:ptop_ + 1] = 0.
     # SPMOMTRANS (crm_module.F90:1200-1211): the reference forms these BEFORE it scales the slab sums by factor_xy (:1214-1224), so uln is
     # the raw SUM of u over the CRM's columns -- reproduced as it is ("reference quirks")
     ptop = plev - nzm + 1

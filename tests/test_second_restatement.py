@@ -654,3 +654,25 @@ def test_whole_3d_crm_call_against_the_numpy_composition(nsteps, wind):
     bad = {k: v for k, v in worst.items() if v > 1e-10}
     assert not bad, bad
     assert float(np.abs(st.v_wind).max()) > 0 and float(out.cld.max()) > 0
+
+
+def test_whole_crm_call_with_explicit_scalar_momentum_transport():
+    """-DSP_ESMT in the numpy crm(): u_esmt / v_esmt initialised from the column's ul_esmt / vl_esmt, advected with the positive offset,
+    diffused, pushed by the spectral pressure-gradient force every sub-step; crm_output%u_tend_esmt / v_tend_esmt against the oracle."""
+    dims = cm.small_dims(ncrms=6, nx=16, nzm=28, plev=30, nsteps=4, esmt=True)
+    dims, inp, st, rad = cm.make_case(dims, 300)
+    ic = int(np.argmax(st.qp.reshape(dims.ncrms, -1).max(axis=1)))
+    ul_e, vl_e = inp.ul_esmt[ic].copy(), inp.vl_esmt[ic].copy()
+    dims, inp1, st, rad = cm.single_crm_case(dims, inp, st, rad, ic)
+    inp1.ul_esmt = np.asfortranarray(ul_e[None, :]); inp1.vl_esmt = np.asfortranarray(vl_e[None, :])
+    st_in = st.copy()
+    out, stats = cm.ob.run(dims, inp1, st, rad)
+    g = rn.crm_grid(inp1.zmid[0], inp1.zint[0], inp1.pmid[0], inp1.pint[0], inp1.pdel[0], dims.nzm)
+    col = dict(tl=inp1.tl[0], ql=inp1.ql[0], qccl=inp1.qccl[0], qiil=inp1.qiil[0], ul=inp1.ul[0], vl=inp1.vl[0], pdel=inp1.pdel[0], ul_esmt=ul_e, vl_esmt=vl_e)
+    r = rn.crm_call_numpy(g, dims.plev, dims.dx, dims.dt, dims.dt_gl, col, st_in.u_wind[0][:, 0, :], st_in.w_wind[0][:, 0, :],
+                          st_in.temperature[0][:, 0, :], st_in.qt[0][:, 0, :], st_in.qp[0][:, 0, :], st_in.qn[0][:, 0, :], rad.qrad[0][:, 0, :], esmt=True)
+    assert r["out"]["ncycle_sum"] == stats["ncycle_sum"]
+    for n in ("u_tend_esmt", "v_tend_esmt", "sltend"):
+        a = getattr(out, n)[0]; b = r["out"][n]
+        assert np.abs(a).max() > 0
+        assert _close(b, a, 1e-9), (n, float(np.abs(a - b).max() / np.abs(a).max()))
