@@ -74,15 +74,16 @@ def _dims3d(ncrms, nx, ny, nsteps, **kw):
                           nx_rad=max(1, nx // 4), ny_rad=max(1, ny // 4), **kw)
 
 
-def test_emu_3d_ab3_and_padding(emu):
-    # 3-D CRM 8x8x28 (tile of 4 CRMs, 256 emulated threads), three steps (AB1..AB3), 5 CRMs -> padded second tile
-    ro, rg = _check(emu, _dims3d(5, 8, 8, 3), 40, 1e-11)
+def test_emu_3d_ab3_and_padding(emu, monkeypatch):
+    # 3-D CRM 8x8x28 (tile of 2 CRMs, 128 emulated threads: 4 warps), three steps (AB1..AB3), 3 CRMs -> padded second tile
+    monkeypatch.setenv("CRM_B200_CT", "2")
+    ro, rg = _check(emu, _dims3d(3, 8, 8, 3), 40, 1e-11)
     assert np.abs(rg[0].v_wind).max() > 0
 
 
 def test_emu_3d_rectangular_setperturb(emu, monkeypatch):
     # 16x8 columns (different transform lengths in x and y), first call of a run (setperturb)
-    monkeypatch.setenv("CRM_B200_CT", "2")
+    monkeypatch.setenv("CRM_B200_CT", "1")
     _check(emu, _dims3d(3, 16, 8, 2, igstep=1), 0, 1e-11)
 
 
@@ -103,7 +104,8 @@ def test_emu_per_phase_intermediate_state(emu, stop):
 
 
 @pytest.mark.parametrize("stop", [3, 4, 8])      # the GPU suite runs 1, 3, 4, 6, 8
-def test_emu_per_phase_intermediate_state_3d(emu, stop):
+def test_emu_per_phase_intermediate_state_3d(emu, stop, monkeypatch):
+    monkeypatch.setenv("CRM_B200_CT", "2")      # one tile of 2 CRMs, 128 emulated threads
     dims = cm.pkg.CrmDims(ncrms=2, nx=8, ny=8, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=20.0, igstep=3, nx_rad=2, ny_rad=2)
     dims, inp, st, rad = cm.make_case(dims, spinup_steps=40)
     for name, err, scale in cm.phase_errors(dims, inp, st, rad, stop, lib_path=emu):
@@ -117,7 +119,8 @@ def test_emu_esmt_2d(emu):
     assert np.abs(ro[2].u_tend_esmt).max() > 1e-7
 
 
-def test_emu_esmt_3d(emu):
+def test_emu_esmt_3d(emu, monkeypatch):
+    monkeypatch.setenv("CRM_B200_CT", "2")
     dims = cm.pkg.CrmDims(ncrms=2, nx=8, ny=8, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=40.0, igstep=3, nx_rad=2, ny_rad=2, esmt=True)
     ro, rg = _check(emu, dims, 30, 1e-10)
     assert np.abs(ro[2].v_tend_esmt).max() > 1e-7
@@ -132,8 +135,9 @@ def test_emu_resident_state_and_history(emu):
     assert np.all(res[0].qt[dims.ncrms:] == 0.0) and np.all(hist["CRM_QV"][dims.ncrms:] == 0.0)
 
 
-def test_emu_resident_3d(emu):
+def test_emu_resident_3d(emu, monkeypatch):
     """The resident path of a 3-D CRM (v_wind round trip); the m2005 members are covered on the GPU (test_resident_m2005_and_3d)."""
+    monkeypatch.setenv("CRM_B200_CT", "2")
     d3 = cm.pkg.CrmDims(ncrms=2, nx=8, ny=8, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=20.0, igstep=3, nx_rad=2, ny_rad=2)
     host, res, orc, hist, _ = cm.resident_case(d3, lib_path=emu, ncalls=1)
     cm.check_resident(d3, host, res, orc, hist, 1e-10)
