@@ -186,3 +186,50 @@ def test_emu_device_code_matches_the_numpy_golden_fixture_3d(emu, monkeypatch):
     h.close()
     bad = mgn.compare_3d(dims, st, rad, out, z, 1e-9)
     assert not bad, bad
+
+
+@pytest.mark.parametrize("variant", ["setperturb", "msa_uv", "esmt"])
+def test_emu_device_code_matches_the_numpy_crm_variants(emu, variant):
+    """Device code (emulated) against the independent numpy crm() computed on the fly for the variants the committed fixtures do not hold:
+    first-step noise (setperturb + RNG_MT), mean-state acceleration with the wind, explicit scalar momentum transport."""
+    import ref_numpy as rn
+    import test_oracle_kat as tk
+    kw = {}
+    nsteps = 3
+    if variant == "msa_uv":
+        kw = dict(use_crm_accel=True, crm_accel_factor=1.0, crm_accel_uv=True); nsteps = 4
+    if variant == "esmt":
+        kw = dict(esmt=True)
+    dims = cm.small_dims(ncrms=6, nx=16, nzm=28, plev=30, nsteps=nsteps, **kw)
+    dims, inp, st, rad = cm.make_case(dims, 300)
+    ic = int(np.argmax(st.qp.reshape(dims.ncrms, -1).max(axis=1)))
+    esm = (inp.ul_esmt[ic].copy(), inp.vl_esmt[ic].copy()) if variant == "esmt" else None
+    dims, inp, st, rad = cm.single_crm_case(dims, inp, st, rad, ic)
+    if esm:
+        inp.ul_esmt = np.asfortranarray(esm[0][None, :]); inp.vl_esmt = np.asfortranarray(esm[1][None, :])
+    if variant == "setperturb":
+        dims = dims.copy(igstep=1)
+    st_in = st.copy()
+    h = cm.libmod.CrmHandle(dims, lib_path=emu)
+    out = h.run(dims, inp, st, rad)
+    ncyc = h.stats()["ncycle_sum"]
+    h.close()
+    g = rn.crm_grid(inp.zmid[0], inp.zint[0], inp.pmid[0], inp.pint[0], inp.pdel[0], dims.nzm)
+    col = dict(tl=inp.tl[0], ql=inp.ql[0], qccl=inp.qccl[0], qiil=inp.qiil[0], ul=inp.ul[0], vl=inp.vl[0], pdel=inp.pdel[0])
+    if esm:
+        col.update(ul_esmt=esm[0], vl_esmt=esm[1])
+    r = rn.crm_call_numpy(g, dims.plev, dims.dx, dims.dt, dims.dt_gl, col, st_in.u_wind[0][:, 0, :], st_in.w_wind[0][:, 0, :],
+                          st_in.temperature[0][:, 0, :], st_in.qt[0][:, 0, :], st_in.qp[0][:, 0, :], st_in.qn[0][:, 0, :], rad.qrad[0][:, 0, :],
+                          igstep=dims.igstep, gcol=int(inp.gcol[0]), rng=tk._rng_mt_python, use_accel=dims.use_crm_accel, accel_uv=dims.crm_accel_uv,
+                          accel_factor=dims.crm_accel_factor, esmt=bool(esm))
+    assert r["out"]["ncycle_sum"] == ncyc
+    worst = {}
+    for n in ("u_wind", "w_wind", "temperature", "qt", "qp", "qn"):
+        a = getattr(st, n)[0][:, 0, :]; b = r["state"][n]
+        worst["state." + n] = float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+    names = ["sltend", "qltend", "qcltend", "cld", "gliqwp", "mu_crm", "flux_qt", "qt_trans", "precflux", "ultend"] + (["u_tend_esmt", "v_tend_esmt"] if esm else [])
+    for n in names:
+        a = getattr(out, n)[0]; b = r["out"][n]
+        worst[n] = float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)) if np.abs(b).max() > 0 else float(np.abs(a).max())
+    bad = {k: v for k, v in worst.items() if v > 1e-9}
+    assert not bad, bad
