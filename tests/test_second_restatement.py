@@ -676,3 +676,33 @@ def test_whole_crm_call_with_explicit_scalar_momentum_transport():
         a = getattr(out, n)[0]; b = r["out"][n]
         assert np.abs(a).max() > 0
         assert _close(b, a, 1e-9), (n, float(np.abs(a - b).max() / np.abs(a).max()))
+
+
+def test_m2005_diagnose_statistics_and_epilogue_against_second_restatement():
+    """The M2005 driver around the column scheme, as far as it can be recomputed from what a caller sees: micro_diagnose
+    (MICRO_M2005/microphysics.F90:1305-1358: qcl = cloud liquid, qci = cloud ice, qpl = rain, qpi = snow + graupel, qv = qt - qc) and, with those,
+    the per-step statistics and the epilogue of crm_module.F90 for a one-step call."""
+    dims = cm.pkg.CrmDims(ncrms=3, nx=16, ny=1, nzm=28, plev=30, dx=4000.0, dt=20.0, dt_gl=20.0, igstep=3, micro=1)
+    dims, inp, st, rad = cm.make_case(dims, 120)
+    st0 = st.copy()
+    out, stats = cm.ob.run(dims, inp, st, rad)
+    assert stats["nstop"] == 1
+    n = dims.ncrms
+    assert np.array_equal(out.qcl[:n], st.qc[:n]) and np.array_equal(out.qci[:n], st.qi[:n]) and np.array_equal(out.qpl[:n], st.qr[:n])
+    assert np.array_equal(out.qpi[:n], st.qs[:n] + st.qg[:n])
+    assert float(st.qr.max()) > 0 and float((st.qs + st.qg).max()) > 0 and float(st.qi.max()) > 0     # rain, snow / graupel and ice exist
+    checked = 0
+    for ic in range(n):
+        g = rn.crm_grid(inp.zmid[ic], inp.zint[ic], inp.pmid[ic], inp.pint[ic], inp.pdel[ic], dims.nzm)
+        w = np.zeros((dims.nx, dims.ny, dims.nzm + 1)); w[:, :, :dims.nzm] = st.w_wind[ic]
+        col = dict(tl=inp.tl[ic], ql=inp.ql[ic], qccl=inp.qccl[ic], qiil=inp.qiil[ic], pdel=inp.pdel[ic])
+        r = rn.crm_outputs_one_step(g, dims.plev, dims.dt_gl, col, st0.temperature[ic], 0. * st0.qt[ic], st.u_wind[ic], st.v_wind[ic], w, st.temperature[ic],
+                                    st.qt[ic] - st.qc[ic], st.qc[ic], st.qi[ic], st.qr[ic], st.qs[ic] + st.qg[ic], dims.nx_rad, dims.ny_rad)
+        for name in ("sltend", "qltend", "qcltend", "qiltend", "cld", "cldtop", "gicewp", "gliqwp", "mcup", "mcdn", "mcuup", "mcudn", "mctot", "qc_mean",
+                     "qi_mean", "qr_mean", "mu_crm", "md_crm", "eu_crm", "du_crm", "ed_crm"):
+            a = getattr(out, name)[ic]
+            assert _close(r[name], a, 1e-11, floor=1e-30), (ic, name, float(np.abs(r[name] - a).max()), float(np.abs(a).max()))
+            checked += int(np.abs(a).max() > 0)
+        for name in ("temperature", "qv", "qc", "qi", "cld"):
+            assert _close(r["rad"][name], getattr(rad, name)[ic], 1e-13, floor=1e-30), (ic, name)
+    assert checked > 8 * n
